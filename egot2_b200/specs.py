@@ -1,0 +1,180 @@
+"""Static description of each EgoT2 translator variant on the hot path.
+
+A `TranslatorSpec` says which per-task feature streams enter the translator, how each is
+projected to `hidden`, what is added after the shared LayerNorm (HHI: learned task embedding
++ sinusoidal PE that restarts per task; HOI: one learned `pe`), the encoder geometry and the
+head.  The spec also fixes the reference's state_dict key of every parameter, so the drop-in
+modules, the synthetic-weight generator and the parity tests all agree on names/shapes.
+
+Reference (relative to /root/reference):
+  HHI/models/ttm/model_taskspecific.py:154-245   TaskFusionMFTransformer{2,3}Task (TTM)
+  HHI/models/asd/model_taskspecific.py:109-158   TaskFusionMFTransformer3Task (ASD)
+  HOI/models/pnr/video_model_transfer_3task.py:212-258   TaskFusionMFTransformer3TaskDropout
+  HOI/models/lta/lta_models_lta_transfer.py:257-377      TaskFusionMFTransformerLTA4Task
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+
+@dataclass(frozen=True)
+class Segment:
+    """One task's feature stream = one contiguous run of tokens in every clip."""
+    name: str                     # "ttm", "lam", "asd", "pnr", "oscc", "slow", "fast", "action", "lta"
+    in_dim: int                   # feature width K of this task's frozen backbone
+    proj: Optional[str]           # state_dict prefix of its nn.Linear(K, hidden); None = already `hidden` wide
+    tokens: Optional[int] = None  # tokens per clip if fixed by the model (HOI); None = taken from the input (HHI)
+    task_id: Optional[int] = None # row of `task_embed` added to these tokens (HHI only)
+
+
+@dataclass(frozen=True)
+class TranslatorSpec:
+    family: str                   # "hhi_ttm" | "hhi_asd" | "hoi_pnr" | "hoi_lta"
+    hidden: int
+    heads: int
+    ffn: int
+    layers: int
+    segments: Tuple[Segment, ...]
+    embed: str                    # "task_sinusoid" (HHI) | "learned_pe" (HOI)
+    encoder_prefix: str           # "transformer_encoder." (HHI) | "transformer." (HOI)
+    head: str                     # "pool_ln_linear" | "tokens" | "pool_multilinear"
+    n_out: int                    # logits per clip (2 / 16 / Z*593); for "tokens": hidden
+    head_ln_shared: bool = False  # HOI PNR: linear_head.0 IS self.ln (one gamma/beta, two uses)
+    p_layer: float = 0.0          # dropout inside every encoder layer (4 sites)
+    p_embed: float = 0.0          # dropout after the embedding add (HHI PositionalEncoding: fixed 0.1)
+    p_feat: float = 0.0           # dropout on projected features before the LN (HOI self.dp)
+    p_head: float = 0.0           # dropout before the head projections (LTA MultiTaskHead)
+    n_task_embed: int = 0
+    head_groups: Tuple[int, ...] = ()   # LTA: class-group sizes inside each of the Z heads (115, 478)
+    n_heads_out: int = 1                # LTA: Z = number of independent Linear heads
+
+    @property
+    def fixed_tokens(self) -> Optional[int]:
+        if any(s.tokens is None for s in self.segments):
+            return None
+        return sum(s.tokens for s in self.segments)
+
+    # ---- parameter inventory: reference state_dict key -> shape ------------------------
+    def param_shapes(self, tokens: Optional[int] = None) -> Dict[str, Tuple[int, ...]]:
+        H, FF = self.hidden, self.ffn
+        out: Dict[str, Tuple[int, ...]] = {}
+        if self.embed == "task_sinusoid":
+            for s in self.segments:
+                pass
+            # reference registration order: proj_lam, proj_ttm[, proj_asd], task_embed, ..., ln, linear_head
+            names = [s.name for s in self.segments]
+            for nm in ("lam", "ttm", "asd"):
+                if nm in names:
+                    out[f"proj_{nm}.weight"] = (H, 256)
+                    out[f"proj_{nm}.bias"] = (H,)
+            out["task_embed"] = (1, self.n_task_embed, H)
+        else:
+            T = self.fixed_tokens
+            out["pe"] = (1, T, H)
+            for s in self.segments:
+                if s.proj is not None:
+                    out[f"{s.proj}.weight"] = (H, s.in_dim)
+                    out[f"{s.proj}.bias"] = (H,)
+        if self.family == "hoi_pnr":
+            out["ln.weight"] = (H,)
+            out["ln.bias"] = (H,)
+        for i in range(self.layers):
+            p = f"{self.encoder_prefix}layers.{i}."
+            out[p + "self_attn.in_proj_weight"] = (3 * H, H)
+            out[p + "self_attn.in_proj_bias"] = (3 * H,)
+            out[p + "self_attn.out_proj.weight"] = (H, H)
+            out[p + "self_attn.out_proj.bias"] = (H,)
+            out[p + "linear1.weight"] = (FF, H)
+            out[p + "linear1.bias"] = (FF,)
+            out[p + "linear2.weight"] = (H, FF)
+            out[p + "linear2.bias"] = (H,)
+            out[p + "norm1.weight"] = (H,)
+            out[p + "norm1.bias"] = (H,)
+            out[p + "norm2.weight"] = (H,)
+            out[p + "norm2.bias"] = (H,)
+        if self.family != "hoi_pnr":
+            out["ln.weight"] = (H,)
+            out["ln.bias"] = (H,)
+        if self.family in ("hhi_ttm", "hhi_asd"):
+            out["linear_head.0.weight"] = (H,)
+            out["linear_head.0.bias"] = (H,)
+            out["linear_head.1.weight"] = (2, H)
+            out["linear_head.1.bias"] = (2,)
+        elif self.family == "hoi_pnr":
+            # linear_head.0.* alias ln.* in the reference state_dict (same tensor)
+            out["linear_head.1.weight"] = (self.n_out, H)
+            out["linear_head.1.bias"] = (self.n_out,)
+        elif self.family == "hoi_lta":
+            per = sum(self.head_groups)
+            for z in range(self.n_heads_out):
+                out[f"head.projections.{z}.weight"] = (per, H)
+                out[f"head.projections.{z}.bias"] = (per,)
+        return out
+
+    def n_params(self) -> int:
+        n = 0
+        for shp in self.param_shapes().values():
+            k = 1
+            for d in shp:
+                k *= d
+            n += k
+        return n
+
+    # ---- algorithmic work per clip --------------------------------------
+    def flops_per_clip(self, seg_tokens: Tuple[int, ...], backward: bool = False) -> float:
+        H, FF, L = self.hidden, self.ffn, self.layers
+        T = sum(seg_tokens)
+        proj = sum(2.0 * t * s.in_dim * H for t, s in zip(seg_tokens, self.segments) if s.proj is not None)
+        layer = 2.0 * T * H * 3 * H + 4.0 * T * T * H + 2.0 * T * H * H + 4.0 * T * H * FF
+        if self.head == "tokens":
+            head = 0.0
+        else:
+            head = 2.0 * H * self.n_out
+        rest = L * layer + head
+        return 2.0 * proj + 3.0 * rest if backward else proj + rest
+
+    def feature_elems_per_clip(self, seg_tokens: Tuple[int, ...]) -> int:
+        return sum(t * s.in_dim for t, s in zip(seg_tokens, self.segments))
+
+
+# --------------------------------------------------------------------------------------
+# factories for the shipped variants
+# --------------------------------------------------------------------------------------
+def hhi_ttm_spec(hidden=128, heads=4, layers=1, dropout=0.5, three_task=True, ffn=2048) -> TranslatorSpec:
+    """TTM-of-interest: token order (ttm id0, lam id1[, asd id2]) — model_taskspecific.py:188-190,238-241."""
+    segs = [Segment("ttm", 256, "proj_ttm", None, 0), Segment("lam", 256, "proj_lam", None, 1)]
+    if three_task:
+        segs.append(Segment("asd", 256, "proj_asd", None, 2))
+    return TranslatorSpec("hhi_ttm", hidden, heads, ffn, layers, tuple(segs), "task_sinusoid",
+                          "transformer_encoder.", "pool_ln_linear", 2, False, dropout, 0.1, 0.0, 0.0,
+                          3 if three_task else 2)
+
+
+def hhi_asd_spec(hidden=128, heads=4, layers=1, dropout=0.5, ffn=2048) -> TranslatorSpec:
+    """ASD-of-interest: token order (asd id2, ttm id0, lam id1), returns the first D tokens —
+    HHI/models/asd/model_taskspecific.py:151-157."""
+    segs = (Segment("asd", 256, "proj_asd", None, 2), Segment("ttm", 256, "proj_ttm", None, 0),
+            Segment("lam", 256, "proj_lam", None, 1))
+    return TranslatorSpec("hhi_asd", hidden, heads, ffn, layers, segs, "task_sinusoid",
+                          "transformer_encoder.", "tokens", hidden, False, dropout, 0.1, 0.0, 0.0, 3)
+
+
+def hoi_pnr_spec(hidden=128, layers=6, n_cls=16, feat_dropout=0.5, tr_dropout=0.1) -> TranslatorSpec:
+    """PNR/OSCC EgoT2-s: tokens (pnr16, oscc16, slow8, fast8), nh=8, FF=2H — video_model_transfer_3task.py:219-236."""
+    segs = (Segment("pnr", 8192, "proj1", 16), Segment("oscc", 8192, "proj2", 16),
+            Segment("slow", 2048, "proj3_slow", 8), Segment("fast", 256, "proj3_fast", 8))
+    return TranslatorSpec("hoi_pnr", hidden, 8, 2 * hidden, layers, segs, "learned_pe", "transformer.",
+                          "pool_ln_linear", n_cls, True, tr_dropout, 0.0, feat_dropout, 0.0)
+
+
+def hoi_lta_spec(hidden=512, layers=4, heads=8, dropout=0.5, num_input_clips=2, num_actions=20,
+                 num_classes=(115, 478), head_dropout=0.5, ffn=2048) -> TranslatorSpec:
+    """LTA EgoT2-s: tokens (pnr, oscc, action, lta) x num_input_clips, FF=2048 (torch default),
+    head = Z x Linear(H, 593) — lta_models_lta_transfer.py:262-275,306-313,354-363."""
+    n = num_input_clips
+    segs = (Segment("pnr", 8192, "proj_pnr", n), Segment("oscc", 8192, "proj_oscc", n),
+            Segment("action", hidden, None, n), Segment("lta", 2048, "proj_lta", n))
+    return TranslatorSpec("hoi_lta", hidden, heads, ffn, layers, segs, "learned_pe", "transformer.",
+                          "pool_multilinear", num_actions * sum(num_classes), False, dropout, 0.0, 0.0,
+                          head_dropout, 0, tuple(num_classes), num_actions)

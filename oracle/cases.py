@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE ONLY — the seeded parity cases shared by the golden generator and tests.
+
+Each case = (spec, batch, tokens per segment, seed).  Inputs and weights are regenerated from
+the seed by `egot2_b200.synth`, so only the *outputs* of the reference are stored as goldens.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from egot2_b200 import specs, synth
+from . import translator_oracle as O
+
+
+@dataclass(frozen=True)
+class Case:
+    name: str
+    spec: specs.TranslatorSpec
+    batch: int
+    seg_tokens: Tuple[int, ...]
+    seed: int = 0
+    raw_slowfast: bool = False     # hoi_pnr: feed raw 5-D SlowFast maps (pool inside the translator)
+
+
+CASES = {c.name: c for c in [
+    # BASELINE config 1 family: HHI 2-task, 1 layer, hidden 128, 4 heads
+    Case("hhi2_h128_l1", specs.hhi_ttm_spec(128, 4, 1, 0.5, three_task=False), 4, (7, 7), 1),
+    # BASELINE config 2 family: HHI 3-task, D_asd may differ from D
+    Case("hhi3_h128_l1", specs.hhi_ttm_spec(128, 4, 1, 0.5, three_task=True), 5, (9, 9, 6), 2),
+    Case("hhi3_h64_l2", specs.hhi_ttm_spec(64, 2, 2, 0.1, three_task=True), 3, (15, 15, 15), 3),
+    Case("hhi3_h128_d30", specs.hhi_ttm_spec(128, 4, 1, 0.5, three_task=True), 8, (30, 30, 30), 4),
+    # ASD-of-interest (per-frame tokens out) + lossAV
+    Case("hhi_asd_h128_l1", specs.hhi_asd_spec(128, 4, 1, 0.5), 4, (8, 8, 8), 5),
+    # BASELINE config 4: HOI PNR keyframe localisation (48 tokens) and the OSCC variant
+    Case("hoi_pnr_h128_l6", specs.hoi_pnr_spec(128, 6, 16, 0.5, 0.1), 6, (16, 16, 8, 8), 6),
+    Case("hoi_pnr_raw_maps", specs.hoi_pnr_spec(128, 6, 16, 0.5, 0.1), 2, (16, 16, 8, 8), 7, raw_slowfast=True),
+    Case("hoi_oscc_h256_l5", specs.hoi_pnr_spec(256, 5, 2, 0.1, 0.1), 4, (16, 16, 8, 8), 8),
+    # BASELINE config 5 (scaled) and the shipped LTA config (H=1024, L=1)
+    Case("hoi_lta_h512_l4", specs.hoi_lta_spec(512, 4, 8, 0.5), 3, (2, 2, 2, 2), 9),
+    Case("hoi_lta_h1024_l1", specs.hoi_lta_spec(1024, 1, 8, 0.5), 2, (2, 2, 2, 2), 10),
+]}
+
+
+def case_inputs(case: Case):
+    """(state_dict, feats, labels) for a case — CPU fp32."""
+    sd = synth.make_state_dict(case.spec, case.seed)
+    feats = synth.make_features(case.spec, case.batch, case.seg_tokens, case.seed)
+    labels = synth.make_labels(case.spec, case.batch, case.seg_tokens, case.seed)
+    extra = {}
+    if case.spec.family == "hhi_asd":
+        g = synth._gen(case.seed, "lossAV")
+        H = case.spec.hidden
+        extra["FC.weight"] = (torch.rand((2, H), generator=g) * 2 - 1) / H ** 0.5
+        extra["FC.bias"] = (torch.rand((2,), generator=g) * 2 - 1) * 0.1
+    if case.raw_slowfast:
+        g = synth._gen(case.seed, "raw_slowfast")
+        B = case.batch
+        extra["slow5"] = torch.randn((B, 2048, 8, 7, 7), generator=g)
+        extra["fast5"] = torch.randn((B, 256, 32, 7, 7), generator=g)
+    return sd, feats, labels, extra
+
+
+def oracle_forward_loss(case: Case, P: Dict[str, torch.Tensor], feats, labels, extra):
+    """Run the restatement in eval mode (no dropout): returns (output, loss)."""
+    sp = case.spec
+    if sp.family == "hhi_ttm":
+        out = O.hhi_ttm_forward(P, feats, sp.heads)
+        loss = O.ce_loss(out, labels, torch.tensor([0.266, 0.734]))
+    elif sp.family == "hhi_asd":
+        out = O.hhi_asd_forward(P, feats, sp.heads)
+        loss = O.loss_av(extra, out, labels)[0]
+    elif sp.family == "hoi_pnr":
+        if case.raw_slowfast:
+            out = O.hoi_pnr_forward(P, feats["pnr"], feats["oscc"], extra["slow5"], extra["fast5"], sp.heads)
+        else:
+            out = O.hoi_pnr_forward(P, feats["pnr"], feats["oscc"], feats["slow"], feats["fast"], sp.heads)
+        if sp.n_out == 16:
+            loss = O.bce_sigmoid_loss(out, torch.nn.functional.one_hot(labels, 16).float())
+        else:
+            loss = O.ce_loss(out, labels)
+    elif sp.family == "hoi_lta":
+        out = O.hoi_lta_forward(P, feats["pnr"], feats["oscc"], feats["action"], feats["lta"], sp.heads)
+        loss = O.lta_loss(out, labels, sp.head_groups)
+    else:
+        raise ValueError(sp.family)
+    return out, loss
+
+
+def grad_digest(g: torch.Tensor) -> torch.Tensor:
+    """Compact fingerprint of a gradient tensor: [sum, l2, absmax, 61 strided samples]."""
+    f = g.detach().double().flatten()
+    n = f.numel()
+    idx = torch.linspace(0, n - 1, 61).long()
+    return torch.cat([torch.stack([f.sum(), f.norm(), f.abs().max()]), f[idx]]).float()

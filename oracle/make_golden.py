@@ -1,0 +1,143 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the REAL reference classes.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+For each case in `oracle/cases.py` the reference translator class (verbatim code, backbones
+stubbed — see ref_shims.py) is constructed, the seeded synthetic state_dict is loaded, and in
+eval mode (dropout off; torch MHA fast path disabled so the documented slow-path math runs)
+we record: the output, the task loss, and a digest of d(loss)/d(param) for every translator
+parameter.  The script also asserts on the spot that the restatement in translator_oracle.py
+reproduces those numbers (fp32, atol 2e-5 / rtol 1e-4).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import ref_shims as rs                      # noqa: E402
+from oracle import translator_oracle as O               # noqa: E402
+from oracle.cases import CASES, Case, case_inputs, grad_digest, oracle_forward_loss  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def build_reference(case: Case, hhi, hoi):
+    sp = case.spec
+    if sp.family == "hhi_ttm":
+        three = len(sp.segments) == 3
+        cls = hhi.ttm.TaskFusionMFTransformer3Task if three else hhi.ttm.TaskFusionMFTransformer2Task
+        return cls(rs.hhi_args(sp.hidden, sp.heads, sp.layers, sp.p_layer, three))
+    if sp.family == "hhi_asd":
+        return hhi.asd.TaskFusionMFTransformer3Task(rs.hhi_args(sp.hidden, sp.heads, sp.layers, sp.p_layer, True))
+    if sp.family == "hoi_pnr":
+        task = "keyframe_localization_2loader" if sp.n_out == 16 else "state_change_detection"
+        m = hoi.pnr3.TaskFusionMFTransformer3TaskDropout(rs.hoi_pnr_cfg(sp.hidden, sp.layers, sp.p_feat, sp.p_layer, task))
+        return m
+    if sp.family == "hoi_lta":
+        return hoi.lta4.TaskFusionMFTransformerLTA4Task(
+            rs.hoi_lta_cfg(sp.hidden, sp.layers, sp.heads, sp.p_layer, sp.segments[0].tokens, sp.n_heads_out,
+                           sp.head_groups, sp.p_head))
+    raise ValueError(sp.family)
+
+
+def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
+    """Drive the reference module through its own forward() and the loss its Lightning task uses."""
+    sp = case.spec
+    if sp.family == "hhi_ttm":
+        if len(sp.segments) == 3:
+            out = m(*rs.hhi_inputs(feats))
+        else:
+            out = m(rs._DictVideo(feats), None)
+        # HHI/tasks/ttm/video_task.py:23-24,36
+        loss = torch.nn.CrossEntropyLoss(weight=torch.tensor([0.266, 0.734]))(out, labels)
+    elif sp.family == "hhi_asd":
+        out = m(*rs.hhi_inputs(feats))
+        lav = hhi.asd_loss.lossAV(dim=sp.hidden)
+        lav.load_state_dict({"criterion.weight": torch.tensor([1.0, 4.0]), "FC.weight": extra["FC.weight"],
+                             "FC.bias": extra["FC.bias"]})
+        loss = lav(out, labels)[0]
+    elif sp.family == "hoi_pnr":
+        slow = extra["slow5"] if case.raw_slowfast else feats["slow"].permute(0, 2, 1)[..., None, None]
+        fast = extra["fast5"] if case.raw_slowfast else \
+            feats["fast"].permute(0, 2, 1).repeat_interleave(4, dim=2)[..., None, None]   # (B,256,32,1,1)
+        m.pnr_model = rs.FeatureBackbone(); m.pnr_model.slot = "pnr"
+        m.oscc_model = rs.FeatureBackbone(); m.oscc_model.slot = "oscc"
+
+        class _SF(torch.nn.Module):
+            def forward(self, x, middle=False):
+                return [slow, fast]
+        m.recognition_model = _SF()
+        out = m([{"pnr": feats["pnr"], "oscc": feats["oscc"]}], None)
+        if sp.n_out == 16:
+            out = out.squeeze(1)                                   # (B,1,16) -> (B,16)
+            # HOI/tasks/pnr/video_taskspecific_pnr.py:29-31
+            loss = torch.nn.BCELoss()(torch.sigmoid(out), torch.nn.functional.one_hot(labels, 16).float())
+        else:
+            out = out.squeeze(2)                                   # (B,2,1) -> (B,2)
+            loss = torch.nn.functional.cross_entropy(out, labels)  # :143-146
+    elif sp.family == "hoi_lta":
+        # forward() lines 355-358 run the backbones; we enter at the projections (359-363)
+        feat = torch.cat((m.proj_pnr(feats["pnr"]), m.proj_oscc(feats["oscc"]), feats["action"],
+                          m.proj_lta(feats["lta"])), dim=1)
+        feat = m.ln(feat) + m.pe
+        out_t = m.transformer(feat).mean(dim=1)
+        m.head.training = True                                     # raw logits (train-mode head), dropout is p=0 below
+        if hasattr(m.head, "dropout"):
+            m.head.dropout.p = 0.0
+        preds = m.decode(out_t)                                    # [(B,Z,115),(B,Z,478)]
+        out = torch.cat(preds, dim=-1)
+        # HOI/tasks/lta/long_term_anticipation_taskspecfic.py:177-183
+        loss = 0
+        for h, head_x in enumerate(preds):
+            for z in range(head_x.shape[1]):
+                loss = loss + torch.nn.functional.cross_entropy(head_x[:, z], labels[:, z, h])
+    return out, loss
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    torch.backends.mha.set_fastpath_enabled(False)
+    torch.set_num_threads(8)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    hhi, hoi = rs.load_hhi(), rs.load_hoi()
+    for name, case in CASES.items():
+        sd, feats, labels, extra = case_inputs(case)
+        m = build_reference(case, hhi, hoi)
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        # everything we do not set must be a buffer / alias / backbone, never a translator weight
+        allowed = ("pos_embed.pe", "linear_head.0.", "lam_model", "ttm_model", "asd_model")
+        assert not unexpected, unexpected
+        assert all(k.startswith(allowed) for k in missing), missing
+        m.eval()
+        out, loss = reference_forward_loss(case, m, hhi, feats, labels, extra)
+        params = dict(m.named_parameters())
+        names = [k for k in sd if k in params]
+        grads = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)
+        rec = {"output": out.detach().numpy(), "loss": np.float32(loss.item())}
+        for k, g in zip(names, grads):
+            rec["grad/" + k] = grad_digest(g if g is not None else torch.zeros_like(params[k])).numpy()
+
+        # --- pin the restatement against the reference right here ---
+        P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        o_out, o_loss = oracle_forward_loss(case, P, feats, labels, extra)
+        torch.testing.assert_close(o_out, out.detach(), atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(o_loss.detach(), loss.detach(), atol=2e-5, rtol=1e-4)
+        o_grads = torch.autograd.grad(o_loss, [P[k] for k in names], allow_unused=True)
+        for k, g_ref, g_o in zip(names, grads, o_grads):
+            if g_ref is None:
+                assert g_o is None or float(g_o.abs().max()) == 0.0, k
+                continue
+            scale = float(g_ref.abs().max()) + 1e-12
+            err = float((g_ref - g_o).abs().max()) / scale
+            assert err < 2e-4, (name, k, err)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **rec)
+        print(f"{name:22s} out{tuple(out.shape)} loss={loss.item():.6f}  params={len(names)}  oracle==reference OK")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,313 @@
+"""TEST INFRASTRUCTURE ONLY — loads the *real* EgoT2 reference classes from /root/reference.
+
+This file is part of the parity oracle.  It is used only in the build container (where
+/root/reference is mounted) by `oracle/make_golden.py` and by the `requires_reference`
+tests, to (a) validate the restatement in `oracle/translator_oracle.py` and (b) generate
+the golden vectors committed under `tests/golden/`.  Nothing in the product package
+(`egot2_b200/`) may import it, and nothing that runs on the GPU box may need it
+(/root/reference does not exist there).
+
+The reference needs pytorch_lightning / fvcore / torchtext / detectron2 etc. which are
+absent here, and its translator classes construct + load frozen backbones from Ego4D
+checkpoints.  We therefore:
+  * inject minimal stand-ins for the missing third-party modules into `sys.modules`;
+  * replace the frozen backbones by pass-through stubs that hand the synthetic per-frame
+    features straight to the translator;
+so that everything AFTER the backbone features — the hot path — is the verbatim reference
+code executing under this container's torch.
+"""
+from __future__ import annotations
+
+import contextlib
+import copy
+import importlib
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+REFERENCE_ROOT = os.environ.get("EGOT2_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "HHI", "models"))
+
+
+# --------------------------------------------------------------------------------------
+# third-party stand-ins
+# --------------------------------------------------------------------------------------
+class _Registry(dict):
+    """Stand-in for fvcore.common.registry.Registry."""
+
+    def __init__(self, name="R"):
+        super().__init__()
+        self._name = name
+
+    def register(self, obj=None):
+        if obj is None:
+            def deco(o):
+                self[o.__name__] = o
+                return o
+            return deco
+        self[obj.__name__] = obj
+        return obj
+
+    def get(self, name):
+        return self[name]
+
+
+class CfgNode(dict):
+    """Stand-in for fvcore.common.config.CfgNode (attribute dict)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+    def merge_from_file(self, f):
+        pass
+
+    def merge_from_list(self, l):
+        pass
+
+    def __deepcopy__(self, memo):
+        return CfgNode({k: copy.deepcopy(v, memo) for k, v in self.items()})
+
+
+def _mod(name, **kw):
+    m = types.ModuleType(name)
+    m.__dict__.update(kw)
+    sys.modules[name] = m
+    return m
+
+
+_THIRD_PARTY = [
+    "fvcore", "fvcore.common", "fvcore.common.registry", "fvcore.common.config", "fvcore.nn",
+    "fvcore.nn.weight_init", "fvcore.nn.precise_bn", "detectron2", "detectron2.layers",
+    "torchtext", "torchtext.vocab", "fvcore.common.file_io", "iopath", "iopath.common",
+    "iopath.common.file_io",
+]
+
+
+def _install_third_party():
+    _mod("fvcore").__path__ = []
+    _mod("fvcore.common").__path__ = []
+    _mod("fvcore.common.registry", Registry=_Registry)
+    _mod("fvcore.common.config", CfgNode=CfgNode)
+    _mod("fvcore.common.file_io", PathManager=SimpleNamespace(open=open))
+    _mod("fvcore.nn").__path__ = []
+    _mod("fvcore.nn.weight_init", c2_msra_fill=lambda *a, **k: None, c2_xavier_fill=lambda *a, **k: None)
+    _mod("fvcore.nn.precise_bn", get_bn_modules=lambda m: [], update_bn_stats=lambda *a, **k: None)
+    _mod("detectron2").__path__ = []
+    _mod("detectron2.layers", ROIAlign=object)
+    _mod("torchtext").__path__ = []
+    _mod("torchtext.vocab", vocab=lambda *a, **k: None, build_vocab_from_iterator=lambda *a, **k: None)
+    _mod("iopath").__path__ = []
+    _mod("iopath.common").__path__ = []
+    _mod("iopath.common.file_io", g_pathmgr=SimpleNamespace(open=open))
+
+
+@contextlib.contextmanager
+def _reference_tree(sub: str):
+    """Temporarily put /root/reference/<sub> first on sys.path with a clean `models`/`utils`
+    namespace (HHI and HOI both have top-level packages of those names)."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    saved = {k: v for k, v in sys.modules.items()
+             if k.split(".")[0] in ("models", "utils", "configs", "tasks", "dataset", "evaluation", "optimizers")}
+    for k in saved:
+        del sys.modules[k]
+    saved_tp = {k: sys.modules.get(k) for k in _THIRD_PARTY}
+    _install_third_party()
+    path = os.path.join(REFERENCE_ROOT, sub)
+    sys.path.insert(0, path)
+    try:
+        yield
+    finally:
+        sys.path.remove(path)
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("models", "utils", "configs", "tasks", "dataset", "evaluation", "optimizers"):
+                del sys.modules[k]
+        sys.modules.update(saved)
+        for k, v in saved_tp.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+# --------------------------------------------------------------------------------------
+# pass-through backbones: the "video"/"audio" tensors handed to forward() ARE the features
+# --------------------------------------------------------------------------------------
+class FeatureBackbone(nn.Module):
+    """Stands in for LAMBackbone / TTMBackbone / PNR / OSCC ResNets: returns input[slot]."""
+
+    def __init__(self, *a, **k):
+        super().__init__()
+        self.slot = None
+
+    def forward(self, *inputs, middle=False, **kw):
+        x = inputs[0]
+        if isinstance(x, (list, tuple)):
+            x = x[0]
+        if isinstance(x, dict):
+            x = x[self.slot]
+        return x
+
+
+class _TalkNetStub(nn.Module):
+    """talkNetModel stand-in: visual frontend carries the (N,D,256) ASD features through."""
+
+    def forward_audio_frontend(self, a):
+        return a
+
+    def forward_visual_frontend(self, v):
+        return v
+
+    def forward_cross_attention(self, a, v):
+        return a, v
+
+    def forward_audio_visual_backend(self, a, v):
+        # reference: outsAV (N*D, 256); `v` here is our feature dict
+        return v["asd"].reshape(-1, v["asd"].shape[-1])
+
+
+class _DictVideo(dict):
+    """A dict of feature tensors that also answers `.shape` like video_asd (N, D, H, W)."""
+
+    @property
+    def shape(self):
+        n, d, _ = self["asd"].shape
+        return (n, d, 1, 1)
+
+
+def hhi_inputs(feats: dict):
+    """Package synthetic features {ttm,lam,asd: (B,D,256)} as the reference forward()'s
+    (video, video_asd, audio, audio_asd) arguments understood by the stub backbones."""
+    v = _DictVideo(feats)
+    return v, v, None, None
+
+
+def load_hhi():
+    """Returns SimpleNamespace(ttm=<module models.ttm.model_taskspecific>, asd=..., multitask=...)
+    with backbones stubbed.  Class objects remain usable after the context exits."""
+    with _reference_tree("HHI"):
+        # pre-seed the heavy backbone modules so the conv nets / cv2 / python_speech_features
+        # are never imported
+        class LAMBackbone(FeatureBackbone):
+            def __init__(self, *a, **k):
+                super().__init__(); self.slot = "lam"
+
+        class TTMBackbone(FeatureBackbone):
+            def __init__(self, *a, **k):
+                super().__init__(); self.slot = "ttm"
+
+        _mod("models").__path__ = [os.path.join(REFERENCE_ROOT, "HHI/models")]
+        _mod("models.lam").__path__ = [os.path.join(REFERENCE_ROOT, "HHI/models/lam")]
+        _mod("models.lam.model", LAMBackbone=LAMBackbone)
+        _mod("models.ttm").__path__ = [os.path.join(REFERENCE_ROOT, "HHI/models/ttm")]
+        _mod("models.ttm.model", TTMBackbone=TTMBackbone)
+        _mod("models.asd").__path__ = [os.path.join(REFERENCE_ROOT, "HHI/models/asd")]
+        _mod("models.asd.talkNetModel", talkNetModel=_TalkNetStub)
+        _mod("utils").__path__ = []
+        _mod("utils.utils", load_ckpt=lambda *a, **k: None,
+             freeze_params=lambda m: [p.requires_grad_(False) for p in m.parameters()],
+             build_vocab=lambda *a, **k: None)
+        ttm = importlib.import_module("models.ttm.model_taskspecific")
+        asd = importlib.import_module("models.asd.model_taskspecific")
+        try:
+            _mod("models.multitask").__path__ = [os.path.join(REFERENCE_ROOT, "HHI/models/multitask")]
+            mt = importlib.import_module("models.multitask.task_prompt_model")
+            # torch>=2 passes is_causal to _mha_block; the reference override predates it
+            def _mha_block(self, x, mem, attn_mask, key_padding_mask, is_causal=False):
+                x = self.multihead_attn(x, mem, mem, attn_mask=attn_mask,
+                                        key_padding_mask=key_padding_mask, need_weights=True)[0]
+                return self.dropout2(x)
+            mt.CustomDecoderLayer._mha_block = _mha_block
+        except Exception as e:  # pragma: no cover
+            mt = e
+        lossmod = None
+        try:
+            spec = importlib.util.spec_from_file_location(
+                "_ref_hhi_asd_loss", os.path.join(REFERENCE_ROOT, "HHI/tasks/asd/loss.py"))
+            lossmod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(lossmod)
+        except Exception as e:  # pragma: no cover
+            lossmod = e
+    return SimpleNamespace(ttm=ttm, asd=asd, multitask=mt, asd_loss=lossmod)
+
+
+def hhi_args(hidden_dim=128, num_heads=4, num_layers=1, dropout=0.5, three_task=True):
+    return SimpleNamespace(lam_checkpoint="x", ttm_checkpoint="x",
+                           asd_checkpoint="x" if three_task else None, nofreeze=False,
+                           hidden_dim=hidden_dim, num_heads=num_heads, dropout=dropout,
+                           num_layers=num_layers)
+
+
+# --------------------------------------------------------------------------------------
+# HOI
+# --------------------------------------------------------------------------------------
+def load_hoi():
+    """Returns SimpleNamespace(pnr3=<module video_model_transfer_3task>, lta4=<module
+    lta_models_lta_transfer>, head=<module lta.head_helper>) with backbone construction
+    disabled."""
+    with _reference_tree("HOI"):
+        root = os.path.join(REFERENCE_ROOT, "HOI")
+        _mod("models").__path__ = [os.path.join(root, "models")]
+        _mod("models.pnr").__path__ = [os.path.join(root, "models/pnr")]
+        _mod("models.lta").__path__ = [os.path.join(root, "models/lta")]
+        _mod("models.pnr.build", MODEL_REGISTRY=_Registry("MODEL"))
+        _mod("models.lta.build", MODEL_REGISTRY=_Registry("MODEL"))
+        _mod("models.pnr.video_model_builder", KeyframeLocalizationResNet=FeatureBackbone,
+             StateChangeClsResNet=FeatureBackbone, DualHeadResNet=FeatureBackbone)
+        _mod("models.lta.video_model_builder", SlowFast=FeatureBackbone, ResNet=FeatureBackbone,
+             MViT=FeatureBackbone, _POOL1={})
+        _mod("models.lta.lta_models", ForecastingEncoderDecoder=FeatureBackbone)
+        noop = lambda *a, **k: None
+        _mod("utils").__path__ = []
+        _mod("utils.pnr").__path__ = []
+        _mod("utils.lta").__path__ = []
+        _mod("utils.multitask").__path__ = []
+        _mod("utils.pnr.parser", load_config_file=lambda f: CfgNode(
+            MISC=CfgNode(CHECKPOINT_FILE_PATH=None), MODEL=CfgNode(NO_TEMP_POOL=False)))
+        _mod("utils.lta.parser", load_config_from_file=noop, parse_args=noop)
+        _mod("utils.multitask.build_vocab", vocab_idx_to_orig=noop, build_vocab=noop)
+        _mod("utils.multitask.load_model", load_checkpoint=noop, freeze_params=noop,
+             load_recognition_backbone=noop, freeze_backbone_params=noop, load_ckpt=noop,
+             load_lta_backbone=noop)
+        pnr3 = importlib.import_module("models.pnr.video_model_transfer_3task")
+        pnr2 = importlib.import_module("models.pnr.video_model_transfer")
+        head = importlib.import_module("models.lta.head_helper")
+        lta4 = importlib.import_module("models.lta.lta_models_lta_transfer")
+        # skip backbone construction in the 3-task base class
+        pnr3.TaskFusion3Task.__init__ = lambda self, cfg, *a, **k: nn.Module.__init__(self)
+    return SimpleNamespace(pnr3=pnr3, pnr2=pnr2, lta4=lta4, head=head)
+
+
+def hoi_pnr_cfg(hidden=128, layers=6, feat_dropout=0.5, tr_dropout=0.1, task="keyframe_localization_2loader"):
+    return CfgNode(DATA=CfgNode(TASK=task),
+                   MODEL=CfgNode(TRANSLATION_INPUT_FEATURES=hidden, TRANSLATION_LAYERS=layers,
+                                 FEAT_DROPOUT_RATE=feat_dropout, TRANSFORMER_DROPOUT_RATE=tr_dropout),
+                   PRETRAIN=CfgNode(PNR_CFG=None, OSCC_CFG=None, ACTION_CFG=None))
+
+
+def hoi_lta_cfg(hidden=512, layers=4, heads=8, dropout=0.5, num_input_clips=2, num_actions=20,
+                num_classes=(115, 478), head_dropout=0.5):
+    return CfgNode(
+        MODEL=CfgNode(TRANSLATION_INPUT_FEATURES=hidden, TRANSLATION_LAYERS=layers,
+                      TRANSLATION_HEADS=heads, TRANSLATION_DROPOUT=dropout,
+                      NUM_CLASSES=list(num_classes), DROPOUT_RATE=head_dropout, HEAD_ACT="softmax"),
+        FORECASTING=CfgNode(NUM_INPUT_CLIPS=num_input_clips, NUM_ACTIONS_TO_PREDICT=num_actions),
+        PRETRAIN=CfgNode(PNR_CFG="x", OSCC_CFG="x"),
+        TEST=CfgNode(NO_ACT=False),
+        CHECKPOINT_FILE_PATH_AR=None, CHECKPOINT_FILE_PATH_LTA=None)

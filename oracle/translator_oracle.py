@@ -1,0 +1,254 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement (the parity oracle) of EgoT2's task-translation path.
+
+Plain torch-on-CPU arithmetic written out op by op (matmul / softmax / mean / var), NOT a
+wrapper around nn.TransformerEncoder, so that every line can be checked against the reference
+lines it restates.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
+`--impl reference` legs may import this module; the product (`egot2_b200/`) never does.
+
+Pinning: the reference ships no tests and no golden vectors — the oracle is
+pinned instead against outputs of the reference classes themselves executed in the build
+container (`oracle/ref_shims.py` + `oracle/make_golden.py` → `tests/golden/*.npz`); see
+`tests/test_oracle_golden.py` (fixtures, runs anywhere) and
+`tests/test_oracle_vs_reference.py` (live, only where /root/reference exists).
+
+Parameters are passed as a dict keyed by the reference module's own state_dict names.
+All citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+Params = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------------------
+# primitives (torch.nn semantics the reference relies on; torch 1.12 == 2.x for these)
+# --------------------------------------------------------------------------------------
+def layer_norm(x: Tensor, g: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
+    """nn.LayerNorm over the last dim: biased variance, eps inside the sqrt."""
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * g + b
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    y = x @ w.t()
+    return y if b is None else y + b
+
+
+def _drop(x: Tensor, p: float, training: bool) -> Tensor:
+    return F.dropout(x, p, True) if (training and p > 0.0) else x
+
+
+def sinusoid_table(n: int, dim: int) -> Tensor:
+    """PositionalEncoding buffer `pe` — HHI/models/ttm/model_taskspecific.py:141-147:
+    pe[p,2i]=sin(p*exp(-2i*ln(1e4)/dim)), pe[p,2i+1]=cos(same)."""
+    pos = torch.arange(n, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, dim, 2).float() * (-math.log(10000.0) / dim))
+    pe = torch.zeros(n, dim)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+def self_attention(x: Tensor, P: Params, pre: str, n_heads: int, p_drop: float, training: bool) -> Tensor:
+    """nn.MultiheadAttention with packed in_proj (q,k,v rows of in_proj_weight in that order),
+    scale 1/sqrt(dh) applied to q, softmax over keys, dropout on the probabilities, out_proj.
+    x: (B,T,H) batch-first (the reference's seq-first HHI layout is the same math)."""
+    B, T, H = x.shape
+    dh = H // n_heads
+    qkv = linear(x, P[pre + "in_proj_weight"], P[pre + "in_proj_bias"])       # (B,T,3H)
+    q, k, v = qkv.split(H, dim=-1)
+    q = q.reshape(B, T, n_heads, dh).transpose(1, 2)                              # (B,nh,T,dh)
+    k = k.reshape(B, T, n_heads, dh).transpose(1, 2)
+    v = v.reshape(B, T, n_heads, dh).transpose(1, 2)
+    s = (q * (1.0 / math.sqrt(dh))) @ k.transpose(-1, -2)                         # (B,nh,T,T)
+    a = torch.softmax(s, dim=-1)
+    a = _drop(a, p_drop, training)
+    o = (a @ v).transpose(1, 2).reshape(B, T, H)
+    return linear(o, P[pre + "out_proj.weight"], P[pre + "out_proj.bias"])
+
+
+def encoder_layer(x: Tensor, P: Params, pre: str, n_heads: int, p_drop: float = 0.0,
+                  training: bool = False) -> Tensor:
+    """nn.TransformerEncoderLayer defaults used by every nn.Transformer translator in the
+    reference: post-norm, ReLU, eps 1e-5 (SURVEY.md F2;
+    HHI/models/ttm/model_taskspecific.py:168-171, HOI/models/pnr/video_model_transfer_3task.py:231-235):
+        x = norm1(x + dropout1(self_attn(x)));  x = norm2(x + dropout2(linear2(dropout(relu(linear1(x))))))"""
+    a = self_attention(x, P, pre + "self_attn.", n_heads, p_drop, training)
+    x = layer_norm(x + _drop(a, p_drop, training), P[pre + "norm1.weight"], P[pre + "norm1.bias"])
+    h = torch.relu(linear(x, P[pre + "linear1.weight"], P[pre + "linear1.bias"]))
+    h = _drop(h, p_drop, training)
+    f = linear(h, P[pre + "linear2.weight"], P[pre + "linear2.bias"])
+    return layer_norm(x + _drop(f, p_drop, training), P[pre + "norm2.weight"], P[pre + "norm2.bias"])
+
+
+def encoder(x: Tensor, P: Params, pre: str, n_layers: int, n_heads: int, p_drop: float = 0.0,
+            training: bool = False) -> Tensor:
+    """nn.TransformerEncoder without a final norm (none of the call sites passes `norm=`)."""
+    for i in range(n_layers):
+        x = encoder_layer(x, P, f"{pre}layers.{i}.", n_heads, p_drop, training)
+    return x
+
+
+def count_layers(P: Params, pre: str) -> int:
+    n = 0
+    while f"{pre}layers.{n}.norm1.weight" in P:
+        n += 1
+    return n
+
+
+# --------------------------------------------------------------------------------------
+# HHI EgoT2-s translators
+# --------------------------------------------------------------------------------------
+_HHI_TASK_ID = {"ttm": 0, "lam": 1, "asd": 2}   # model_taskspecific.py:238-240 (encode_prepare ids)
+
+
+def hhi_tokens(P: Params, feats: Dict[str, Tensor], order: Sequence[str], training: bool = False) -> Tensor:
+    """proj_k -> shared ln -> + task_embed[k] -> + sinusoidal pe restarting at 0 per task ->
+    Dropout(0.1) -> concat over tokens.  HHI/models/ttm/model_taskspecific.py:178-182,188-190
+    (2-task), :222-226,238-241 (3-task); HHI/models/asd/model_taskspecific.py:133-137,151-154."""
+    H = P["ln.weight"].numel()
+    segs = []
+    for name in order:
+        f = feats[name]                                                     # (B,D_k,256)
+        x = linear(f, P[f"proj_{name}.weight"], P[f"proj_{name}.bias"])
+        x = layer_norm(x, P["ln.weight"], P["ln.bias"]) + P["task_embed"][:, _HHI_TASK_ID[name], :]
+        x = x + sinusoid_table(f.shape[1], H).unsqueeze(0)
+        segs.append(_drop(x, 0.1, training))
+    return torch.cat(segs, dim=1)                                           # (B,T,H)
+
+
+def hhi_ttm_forward(P: Params, feats: Dict[str, Tensor], n_heads: int, p_drop: float = 0.0,
+                    training: bool = False) -> Tensor:
+    """TaskFusionMFTransformer2Task / 3Task (TTM of interest) -> (B,2) logits.
+    HHI/models/ttm/model_taskspecific.py:184-194 and :228-245.  Token order (ttm, lam[, asd])."""
+    order = ("ttm", "lam", "asd") if "proj_asd.weight" in P else ("ttm", "lam")
+    x = hhi_tokens(P, feats, order, training)
+    x = encoder(x, P, "transformer_encoder.", count_layers(P, "transformer_encoder."), n_heads, p_drop, training)
+    g = x.mean(dim=1)
+    g = layer_norm(g, P["linear_head.0.weight"], P["linear_head.0.bias"])
+    return linear(g, P["linear_head.1.weight"], P["linear_head.1.bias"])
+
+
+def hhi_asd_forward(P: Params, feats: Dict[str, Tensor], n_heads: int, p_drop: float = 0.0,
+                    training: bool = False) -> Tensor:
+    """ASD-of-interest TaskFusionMFTransformer3Task -> (B*D, H): the first D (= asd) encoded
+    tokens of each clip, no pooling, no head.  HHI/models/asd/model_taskspecific.py:139-158;
+    token order (asd, ttm, lam)."""
+    x = hhi_tokens(P, feats, ("asd", "ttm", "lam"), training)
+    x = encoder(x, P, "transformer_encoder.", count_layers(P, "transformer_encoder."), n_heads, p_drop, training)
+    D = feats["asd"].shape[1]
+    return x[:, :D, :].reshape(-1, x.shape[-1])
+
+
+def loss_av(P: Params, x: Tensor, labels: Tensor):
+    """lossAV — HHI/tasks/asd/loss.py:11-30: FC(H->2), CE(weight [1,4]), softmax score,
+    round(softmax)[:,1] label, correct count.  `P` holds 'FC.weight', 'FC.bias'."""
+    z = linear(x, P["FC.weight"], P["FC.bias"])
+    loss = ce_loss(z, labels, torch.tensor([1.0, 4.0]))
+    score = torch.softmax(z, dim=-1)
+    label = torch.round(score)[:, 1]
+    return loss, score, label, (label == labels).sum().float()
+
+
+# --------------------------------------------------------------------------------------
+# HOI EgoT2-s translators
+# --------------------------------------------------------------------------------------
+def pool_slowfast(slow5: Tensor, fast5: Tensor):
+    """AdaptiveAvgPool3d((None,1,1)) / ((8,1,1)) + squeeze + permute —
+    HOI/models/pnr/video_model_transfer_3task.py:226-227,245-247.
+    slow5 (B,2048,8,h,w) -> (B,8,2048); fast5 (B,256,32,h,w) -> (B,8,256) (mean over h,w and
+    over groups of 32/8 consecutive frames)."""
+    slow = slow5.mean(dim=(-1, -2)).permute(0, 2, 1)
+    B, C, Tf = fast5.shape[:3]
+    fast = fast5.mean(dim=(-1, -2)).reshape(B, C, 8, Tf // 8).mean(dim=-1).permute(0, 2, 1)
+    return slow, fast
+
+
+def hoi_pnr_forward(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: Tensor, n_heads: int = 8,
+                    p_feat: float = 0.0, p_drop: float = 0.0, training: bool = False) -> Tensor:
+    """TaskFusionMFTransformer3TaskDropout -> (B, n_cls) logits (before the unsqueeze).
+    HOI/models/pnr/video_model_transfer_3task.py:238-258.  Token order (pnr, oscc, slow, fast);
+    learned pe; `ln` shared between the token LN and the head LN (F5).
+    slow/fast may be the raw 5-D SlowFast maps or the already pooled (B,8,C) features."""
+    if slow.dim() == 5:
+        slow, fast = pool_slowfast(slow, fast)
+    z = torch.cat([
+        _drop(linear(pnr, P["proj1.weight"], P["proj1.bias"]), p_feat, training),
+        _drop(linear(oscc, P["proj2.weight"], P["proj2.bias"]), p_feat, training),
+        _drop(linear(slow, P["proj3_slow.weight"], P["proj3_slow.bias"]), p_feat, training),
+        _drop(linear(fast, P["proj3_fast.weight"], P["proj3_fast.bias"]), p_feat, training)], dim=1)
+    x = layer_norm(z, P["ln.weight"], P["ln.bias"]) + P["pe"]
+    x = encoder(x, P, "transformer.", count_layers(P, "transformer."), n_heads, p_drop, training)
+    g = layer_norm(x.mean(dim=1), P["ln.weight"], P["ln.bias"])
+    return linear(g, P["linear_head.1.weight"], P["linear_head.1.bias"])
+
+
+def hoi_lta_forward(P: Params, pnr: Tensor, oscc: Tensor, action: Tensor, lta: Tensor, n_heads: int = 8,
+                    p_drop: float = 0.0, p_head: float = 0.0, training: bool = False,
+                    eval_softmax: bool = False) -> Tensor:
+    """TaskFusionMFTransformerLTA4Task -> (B, Z, n_verbs+n_nouns) stacked head outputs.
+    HOI/models/lta/lta_models_lta_transfer.py:354-363 + decode :348-352 +
+    MultiTaskHead HOI/models/lta/head_helper.py:262-290.  Inputs are the per-input-clip
+    features: pnr/oscc (B,2,8192) (already temporally averaged, :339-346), action (B,2,H),
+    lta (B,2,2048).  Token order (pnr, oscc, action, lta).  eval_softmax=True reproduces the
+    eval-mode Softmax(dim=4) over all classes (head_helper.py:284-286)."""
+    z = torch.cat([linear(pnr, P["proj_pnr.weight"], P["proj_pnr.bias"]),
+                   linear(oscc, P["proj_oscc.weight"], P["proj_oscc.bias"]),
+                   action,
+                   linear(lta, P["proj_lta.weight"], P["proj_lta.bias"])], dim=1)
+    x = layer_norm(z, P["ln.weight"], P["ln.bias"]) + P["pe"]
+    x = encoder(x, P, "transformer.", count_layers(P, "transformer."), n_heads, p_drop, training)
+    g = _drop(x.mean(dim=1), p_head, training)
+    outs = []
+    z_idx = 0
+    while f"head.projections.{z_idx}.weight" in P:
+        o = linear(g, P[f"head.projections.{z_idx}.weight"], P[f"head.projections.{z_idx}.bias"])
+        outs.append(torch.softmax(o, dim=-1) if eval_softmax else o)
+        z_idx += 1
+    return torch.stack(outs, dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------------------
+def ce_loss(logits: Tensor, target: Tensor, weight: Optional[Tensor] = None) -> Tensor:
+    """nn.CrossEntropyLoss(weight=w), reduction='mean':  sum_b w[y_b]*nll_b / sum_b w[y_b].
+    TTM weight [0.266,0.734]: HHI/configs/ttm/config.py:36, HHI/tasks/ttm/video_task.py:23-24."""
+    lse = torch.logsumexp(logits, dim=-1)
+    nll = lse - logits.gather(-1, target.unsqueeze(-1)).squeeze(-1)
+    if weight is None:
+        return nll.mean()
+    w = weight.to(logits.dtype)[target]
+    return (w * nll).sum() / w.sum()
+
+
+def bce_sigmoid_loss(logits: Tensor, onehot: Tensor) -> Tensor:
+    """PNR: nn.BCELoss(mean)(sigmoid(logits), onehot) — HOI/tasks/pnr/video_taskspecific_pnr.py:29-31.
+    (BCELoss clamps log terms at -100.)"""
+    p = torch.sigmoid(logits)
+    lp = torch.clamp(torch.log(p), min=-100.0)
+    l1p = torch.clamp(torch.log(1.0 - p), min=-100.0)
+    return -(onehot * lp + (1.0 - onehot) * l1p).mean()
+
+
+def lta_loss(stacked: Tensor, labels: Tensor, num_classes=(115, 478)) -> Tensor:
+    """sum over heads (verb, noun) and the Z future steps of mean-CE —
+    HOI/tasks/lta/long_term_anticipation_taskspecfic.py:177-183.  stacked (B,Z,593), labels (B,Z,2)."""
+    parts = torch.split(stacked, list(num_classes), dim=-1)
+    loss = stacked.new_zeros(())
+    for h, part in enumerate(parts):
+        for z in range(part.shape[1]):
+            loss = loss + ce_loss(part[:, z], labels[:, z, h])
+    return loss
+
+
+def keyframe_index(logits: Tensor) -> Tensor:
+    """argmax over the 16 PNR logits — HOI/evaluation/pnr/metrics.py:56, HOI/submission/eval_pnr.py:23."""
+    return logits.argmax(dim=-1)
