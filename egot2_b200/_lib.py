@@ -1,0 +1,150 @@
+"""ctypes binding of libegot2.so (the C ABI declared in include/egot2.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or fails to load, importing
+the ops raises — the product path never routes through PyTorch eager or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+MAX_SEG = 8
+MAX_GROUPS = 4
+F32, BF16 = 0, 1
+LOSS_NONE, LOSS_CE, LOSS_BCE_SIGMOID, LOSS_CE_GROUPS = 0, 1, 2, 3
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libegot2.so")
+
+i32, u64, f32, vp, sz = C.c_int32, C.c_uint64, C.c_float, C.c_void_p, C.c_size_t
+
+
+class EmbedDesc(C.Structure):
+    _fields_ = [("dtype", i32), ("feat_dtype", i32), ("B", i32), ("T", i32), ("H", i32), ("n_seg", i32),
+                ("seg_tokens", i32 * MAX_SEG), ("seg_in_dim", i32 * MAX_SEG), ("seg_offset", i32 * MAX_SEG),
+                ("seg_has_proj", i32 * MAX_SEG), ("training", i32), ("p_feat", f32), ("p_embed", f32),
+                ("ln_eps", f32), ("seed", u64)]
+
+
+class EmbedIn(C.Structure):
+    _fields_ = [("feat", vp * MAX_SEG), ("proj_w", vp * MAX_SEG), ("proj_b", vp * MAX_SEG), ("ln_g", vp),
+                ("ln_b", vp), ("tok_table", vp)]
+
+
+class EmbedOut(C.Structure):
+    _fields_ = [("z", vp), ("stat", vp), ("x", vp)]
+
+
+class EmbedGrads(C.Structure):
+    _fields_ = [("proj_w", vp * MAX_SEG), ("proj_b", vp * MAX_SEG), ("ln_g", vp), ("ln_b", vp), ("tok_table", vp),
+                ("dfeat", vp * MAX_SEG)]
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("T", i32), ("H", i32), ("FF", i32), ("heads", i32), ("training", i32),
+                ("layer_index", i32), ("p_drop", f32), ("ln_eps", f32), ("seed", u64)]
+
+
+_LAYER_FIELDS = ["in_proj_w", "out_proj_w", "lin1_w", "lin2_w", "in_proj_b", "out_proj_b", "lin1_b", "lin2_b",
+                 "norm1_g", "norm1_b", "norm2_g", "norm2_b"]
+
+
+class LayerParams(C.Structure):
+    _fields_ = [(n, vp) for n in _LAYER_FIELDS]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [(n, vp) for n in _LAYER_FIELDS]
+
+
+class LayerSaved(C.Structure):
+    _fields_ = [(n, vp) for n in ["qkv", "attn", "lse", "y1", "stat1", "x1", "hid", "y2", "stat2"]]
+
+
+class HeadDesc(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("T", i32), ("H", i32), ("pool", i32), ("row_tokens", i32),
+                ("use_ln", i32), ("n_out", i32), ("loss", i32), ("n_groups", i32), ("group_size", i32 * MAX_GROUPS),
+                ("sub_rows", i32), ("training", i32), ("p_head", f32), ("ln_eps", f32), ("seed", u64)]
+
+
+class HeadIn(C.Structure):
+    _fields_ = [(n, vp) for n in ["x", "ln_g", "ln_b", "w", "b", "labels", "class_weight"]]
+
+
+class HeadOut(C.Structure):
+    _fields_ = [(n, vp) for n in ["pooled", "stat", "g", "logits", "loss", "argmax", "row_loss"]]
+
+
+class HeadGrads(C.Structure):
+    _fields_ = [(n, vp) for n in ["ln_g", "ln_b", "w", "b"]]
+
+
+P = C.POINTER
+
+# name -> (restype, argtypes); every symbol declared in include/egot2.h must be listed here
+SIGNATURES = {
+    "egot2_version": (C.c_char_p, []),
+    "egot2_last_error": (C.c_char_p, []),
+    "egot2_sm_count": (C.c_int, []),
+    "egot2_embed_workspace_bytes": (sz, [P(EmbedDesc), C.c_int]),
+    "egot2_embed_fwd": (C.c_int, [P(EmbedDesc), P(EmbedIn), P(EmbedOut), vp, sz, vp]),
+    "egot2_embed_bwd": (C.c_int, [P(EmbedDesc), P(EmbedIn), P(EmbedOut), vp, P(EmbedGrads), vp, sz, vp]),
+    "egot2_hhi_tok_table_fwd": (C.c_int, [vp, vp, i32, i32, P(i32), P(i32), i32, vp, vp]),
+    "egot2_hhi_tok_table_bwd": (C.c_int, [vp, i32, P(i32), P(i32), i32, vp, vp]),
+    "egot2_encoder_layer_workspace_bytes": (sz, [P(LayerDesc), C.c_int]),
+    "egot2_encoder_layer_fwd": (C.c_int, [P(LayerDesc), P(LayerParams), vp, vp, P(LayerSaved), vp, sz, vp]),
+    "egot2_encoder_layer_bwd": (C.c_int, [P(LayerDesc), P(LayerParams), vp, P(LayerSaved), vp, vp, P(LayerGrads),
+                                          vp, sz, vp]),
+    "egot2_head_rows": (C.c_int, [P(HeadDesc)]),
+    "egot2_head_workspace_bytes": (sz, [P(HeadDesc)]),
+    "egot2_head_loss_fwd": (C.c_int, [P(HeadDesc), P(HeadIn), P(HeadOut), vp]),
+    "egot2_head_loss_bwd": (C.c_int, [P(HeadDesc), P(HeadIn), P(HeadOut), vp, f32, vp, P(HeadGrads), vp, sz, vp]),
+    "egot2_slowfast_pool_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "egot2_cast_f32_to_bf16": (C.c_int, [vp, vp, sz, vp]),
+    "egot2_cast_bf16_to_f32": (C.c_int, [vp, vp, sz, vp]),
+    "egot2_adam_step": (C.c_int, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp]),
+    "egot2_gemm": (C.c_int, [i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, vp]),
+    "egot2_layernorm_fwd": (C.c_int, [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp]),
+    "egot2_attention_fwd": (C.c_int, [i32, i32, i32, i32, i32, vp, vp, vp, f32, i32, u64, vp]),
+    "egot2_attention_bwd": (C.c_int, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, i32, u64, vp, sz, vp]),
+    "egot2_attention_bwd_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
+    "egot2_pool_fwd": (C.c_int, [i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "egot2_pool_bwd": (C.c_int, [i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+}
+
+_lib = None
+
+
+class Egot2Error(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load libegot2.so (once).  Raises if it has not been built — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise Egot2Error(f"{_LIB_PATH} not found: build it with `python -m egot2_b200.build` "
+                         "(the CUDA library is mandatory; there is no PyTorch/CPU fallback)")
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().egot2_last_error().decode(errors="replace")
+        raise Egot2Error(f"{what or 'egot2 call'} failed (rc={rc}): {msg}")
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise Egot2Error on failure."""
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,525 @@
+// api.cu — the stage-level C ABI of include/egot2.h: each entry point enqueues the kernels of one
+// stage of the translator (embed, encoder layer, head+loss) on the caller's stream.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ops.h"
+
+namespace egot2 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// split-K factor for a weight-gradient GEMM (small M x N output, K = all tokens): fill ~2 waves.
+int suggest_split_k(int M, int N, int K) {
+  const int tile = (M <= 64 || N <= 64) ? 64 : 128;
+  const long long tiles = (long long)((M + tile - 1) / tile) * ((N + tile - 1) / tile);
+  long long want = (2LL * sm_count() + tiles - 1) / tiles;
+  long long max_by_k = K / 256;
+  if (want > max_by_k) want = max_by_k;
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  return (int)want;
+}
+
+static thread_local const char* g_gemm_impl = "none";
+const char* gemm_last_impl() { return g_gemm_impl; }
+
+static int gemm_impl_mode() {   // 0 auto, 1 force CUDA-core (diagnostics: EGOT2_GEMM=simt)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("EGOT2_GEMM");
+    mode = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+  }
+  return mode;
+}
+
+int gemm(const GemmArgs& a, cudaStream_t st) {
+  if (a.in_dtype == EGOT2_BF16 && gemm_impl_mode() == 0) {
+    const int rc = gemm_sm100(a, st);
+    if (rc >= 0) { if (rc == 0) g_gemm_impl = "tcgen05"; return rc; }
+  }
+  g_gemm_impl = "simt";
+  return gemm_simt(a, st);
+}
+
+int attention_fwd(int dtype, int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p_drop,
+                  uint64_t drop_key, cudaStream_t st) {
+  return attention_simt_fwd(dtype, B, T, H, heads, qkv, out, lse, p_drop, drop_key, st);
+}
+int attention_bwd(int dtype, int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse,
+                  const void* dout, void* dqkv, float p_drop, uint64_t drop_key, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  return attention_simt_bwd(dtype, B, T, H, heads, qkv, out, lse, dout, dqkv, p_drop, drop_key, ws, ws_bytes, st);
+}
+
+namespace {
+
+struct Carver {   // bump allocator over the caller's workspace
+  char* base; size_t size, off = 0;
+  Carver(void* p, size_t n) : base((char*)p), size(n) {}
+  void* take(size_t bytes) {
+    void* r = base ? base + off : nullptr;
+    off += align_up(bytes);
+    return r;
+  }
+  bool ok() const { return off <= size && (base != nullptr || off == 0); }
+};
+
+// weight-gradient GEMM: dW[N_out, K_in] += dY^T . X     (dY: (rows, N_out), X: (rows, K_in))
+int wgrad(int dtype, int rows, int n_out, int k_in, const void* dY, int ld_dy, int dy_rpg, int dy_gs, const void* X,
+          int ld_x, int x_rpg, int x_gs, float* dW, cudaStream_t st) {
+  GemmArgs g;
+  g.M = n_out; g.N = k_in; g.K = rows;
+  g.A = dY; g.lda = ld_dy; g.trans_a = 1; g.a_rpg = dy_rpg; g.a_gstride = dy_gs;
+  g.B = X; g.ldb = ld_x; g.trans_b = 0; g.b_rpg = x_rpg; g.b_gstride = x_gs;
+  g.C = dW; g.ldc = k_in; g.in_dtype = dtype; g.out_dtype = EGOT2_F32; g.accumulate = 1;
+  g.split_k = suggest_split_k(g.M, g.N, g.K);
+  return gemm(g, st);
+}
+
+}  // namespace
+}  // namespace egot2
+
+using namespace egot2;
+
+extern "C" const char* egot2_version(void) { return "egot2-b200 0.1 (sm_100a)"; }
+extern "C" const char* egot2_last_error(void) { return g_err; }
+extern "C" int egot2_sm_count(void) { return sm_count(); }
+
+// =============================================================================== embed stage
+extern "C" size_t egot2_embed_workspace_bytes(const egot2_embed_desc* d, int backward) {
+  size_t n = 256;
+  if (!backward && d->feat_dtype != d->dtype) {
+    size_t mx = 0;
+    for (int k = 0; k < d->n_seg; ++k) {
+      const size_t e = (size_t)d->B * d->seg_tokens[k] * d->seg_in_dim[k];
+      if (e > mx) mx = e;
+    }
+    n += align_up(mx * dtype_size(d->dtype));
+  }
+  if (backward && d->feat_dtype != d->dtype) {
+    size_t mx = 0;
+    for (int k = 0; k < d->n_seg; ++k) {
+      const size_t e = (size_t)d->B * d->seg_tokens[k] * d->seg_in_dim[k];
+      if (e > mx) mx = e;
+    }
+    n += align_up(mx * dtype_size(d->dtype));
+  }
+  return n;
+}
+
+static int embed_check(const egot2_embed_desc* d) {
+  EGOT2_CHECK(d->n_seg >= 1 && d->n_seg <= EGOT2_MAX_SEG, "embed: n_seg=%d out of range", d->n_seg);
+  EGOT2_CHECK(d->dtype == EGOT2_F32 || d->dtype == EGOT2_BF16, "embed: bad dtype %d", d->dtype);
+  EGOT2_CHECK(d->feat_dtype == d->dtype || (d->feat_dtype == EGOT2_F32 && d->dtype == EGOT2_BF16),
+              "embed: features must be in the compute dtype, or fp32 with bf16 compute");
+  int tot = 0;
+  for (int k = 0; k < d->n_seg; ++k) {
+    EGOT2_CHECK(d->seg_offset[k] == tot, "embed: segment %d offset %d != running total %d", k, d->seg_offset[k], tot);
+    EGOT2_CHECK(d->seg_has_proj[k] || d->seg_in_dim[k] == d->H, "embed: pass-through segment %d must be H wide", k);
+    tot += d->seg_tokens[k];
+  }
+  EGOT2_CHECK(tot == d->T, "embed: segments cover %d tokens, T=%d", tot, d->T);
+  return 0;
+}
+
+extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* in, const egot2_embed_out* out,
+                               void* workspace, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGOT2_TRY(embed_check(d));
+  if (d->B == 0 || d->T == 0) return 0;
+  const size_t es = dtype_size(d->dtype);
+  Carver ws(workspace, ws_bytes);
+  void* cast_buf = nullptr;
+  if (d->feat_dtype != d->dtype) {
+    cast_buf = ws.take(egot2_embed_workspace_bytes(d, 0) - 256);
+    EGOT2_CHECK(ws.ok(), "embed_fwd: workspace too small (%zu < %zu)", ws_bytes, ws.off);
+  }
+  for (int k = 0; k < d->n_seg; ++k) {
+    const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
+    if (Dk == 0) continue;
+    char* zk = (char*)out->z + (size_t)d->seg_offset[k] * d->H * es;
+    const void* feat = in->feat[k];
+    if (d->feat_dtype != d->dtype) {
+      EGOT2_TRY(cast_f32_to(d->dtype, (const float*)feat, cast_buf, (size_t)d->B * Dk * Kk, st));
+      feat = cast_buf;
+    }
+    if (d->seg_has_proj[k]) {
+      GemmArgs g;
+      g.M = d->B * Dk; g.N = d->H; g.K = Kk;
+      g.A = feat; g.lda = Kk;
+      g.B = in->proj_w[k]; g.ldb = Kk; g.trans_b = 1;
+      g.C = zk; g.ldc = d->H; g.c_rpg = Dk; g.c_gstride = d->T;
+      g.bias = in->proj_b[k];
+      g.in_dtype = d->dtype; g.out_dtype = d->dtype;
+      EGOT2_TRY(gemm(g, st));
+    } else {
+      EGOT2_CUDA(cudaMemcpy2DAsync(zk, (size_t)d->T * d->H * es, feat, (size_t)Dk * d->H * es, (size_t)Dk * d->H * es,
+                                   d->B, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  const size_t n = (size_t)d->B * d->T * d->H;
+  if (d->training && d->p_feat > 0.f)
+    EGOT2_TRY(dropout_inplace(d->dtype, out->z, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+  LayerNormArgs l;
+  l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = out->z; l.g = in->ln_g; l.b = in->ln_b; l.eps = d->ln_eps;
+  l.y = out->x; l.stat = out->stat; l.table = in->tok_table; l.table_rows = d->T;
+  if (d->training && d->p_embed > 0.f) { l.p_drop = d->p_embed; l.drop_key = site_key(d->seed, SITE_EMBED, 0); }
+  return layernorm_fwd(l, st);
+}
+
+extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* in, const egot2_embed_out* saved,
+                               const void* dx_c, const egot2_embed_grads* g, void* workspace, size_t ws_bytes,
+                               void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGOT2_TRY(embed_check(d));
+  if (d->B == 0 || d->T == 0) return 0;
+  void* dx = const_cast<void*>(dx_c);
+  const size_t es = dtype_size(d->dtype);
+  const size_t n = (size_t)d->B * d->T * d->H;
+  Carver ws(workspace, ws_bytes);
+  void* cast_buf = nullptr;
+  if (d->feat_dtype != d->dtype) {
+    cast_buf = ws.take(egot2_embed_workspace_bytes(d, 1) - 256);
+    EGOT2_CHECK(ws.ok(), "embed_bwd: workspace too small (%zu < %zu)", ws_bytes, ws.off);
+  }
+  if (d->training && d->p_embed > 0.f)
+    EGOT2_TRY(dropout_inplace(d->dtype, dx, n, d->p_embed, site_key(d->seed, SITE_EMBED, 0), st));
+  if (g->tok_table) EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dx, g->tok_table, st));
+  LayerNormBwdArgs l;
+  l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = saved->z; l.stat = saved->stat; l.g = in->ln_g;
+  l.dy = dx; l.dx = dx; l.dg = g->ln_g; l.db = g->ln_b;
+  EGOT2_TRY(layernorm_bwd(l, st));
+  if (d->training && d->p_feat > 0.f)
+    EGOT2_TRY(dropout_inplace(d->dtype, dx, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+  for (int k = 0; k < d->n_seg; ++k) {
+    const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
+    if (Dk == 0) continue;
+    const char* dzk = (const char*)dx + (size_t)d->seg_offset[k] * d->H * es;
+    if (d->seg_has_proj[k]) {
+      const void* feat = in->feat[k];
+      if (d->feat_dtype != d->dtype) {
+        EGOT2_TRY(cast_f32_to(d->dtype, (const float*)feat, cast_buf, (size_t)d->B * Dk * Kk, st));
+        feat = cast_buf;
+      }
+      if (g->proj_w[k])
+        EGOT2_TRY(wgrad(d->dtype, d->B * Dk, d->H, Kk, dzk, d->H, Dk, d->T, feat, Kk, 0, 0, g->proj_w[k], st));
+      if (g->proj_b[k]) EGOT2_TRY(colsum_accum(d->dtype, d->B * Dk, d->H, dzk, d->H, Dk, d->T, g->proj_b[k], st));
+      if (g->dfeat[k]) {   // dF = dZ . W   (only for a trainable backbone: HHI --nofreeze)
+        GemmArgs m;
+        m.M = d->B * Dk; m.N = Kk; m.K = d->H;
+        m.A = dzk; m.lda = d->H; m.a_rpg = Dk; m.a_gstride = d->T;
+        m.B = in->proj_w[k]; m.ldb = Kk; m.trans_b = 0;
+        m.C = g->dfeat[k]; m.ldc = Kk; m.in_dtype = d->dtype; m.out_dtype = EGOT2_F32;
+        EGOT2_TRY(gemm(m, st));
+      }
+    } else if (g->dfeat[k]) {   // pass-through stream (LTA action features come from a trainable head)
+      if (d->dtype == EGOT2_F32) {
+        EGOT2_CUDA(cudaMemcpy2DAsync(g->dfeat[k], (size_t)Dk * d->H * 4, dzk, (size_t)d->T * d->H * 4,
+                                     (size_t)Dk * d->H * 4, d->B, cudaMemcpyDeviceToDevice, st));
+      } else {
+        for (int b = 0; b < d->B; ++b)
+          EGOT2_TRY(cast_to_f32(d->dtype, dzk + (size_t)b * d->T * d->H * es, g->dfeat[k] + (size_t)b * Dk * d->H,
+                                (size_t)Dk * d->H, st));
+      }
+    }
+  }
+  return 0;
+}
+
+// =============================================================================== encoder layer
+namespace {
+struct LayerWs {
+  void *d1, *d2, *d3, *dhid, *dqkv, *attn_ws;
+  size_t attn_ws_bytes;
+};
+size_t layer_ws_layout(const egot2_layer_desc* d, int backward, void* base, size_t bytes, LayerWs* out) {
+  Carver ws(base, bytes);
+  if (backward) {
+    const size_t es = dtype_size(d->dtype);
+    const size_t M = (size_t)d->B * d->T;
+    LayerWs w;
+    w.d1 = ws.take(M * d->H * es);
+    w.d2 = ws.take(M * d->H * es);
+    w.d3 = ws.take(M * d->H * es);
+    w.dhid = ws.take(M * d->FF * es);
+    w.dqkv = ws.take(M * 3 * d->H * es);
+    w.attn_ws_bytes = attention_bwd_workspace(d->dtype, d->B, d->T, d->H, d->heads);
+    w.attn_ws = ws.take(w.attn_ws_bytes);
+    if (out) *out = w;
+  }
+  return ws.off + 256;
+}
+int layer_check(const egot2_layer_desc* d) {
+  EGOT2_CHECK(d->dtype == EGOT2_F32 || d->dtype == EGOT2_BF16, "layer: bad dtype %d", d->dtype);
+  EGOT2_CHECK(d->heads > 0 && d->H % d->heads == 0, "layer: H=%d not divisible by heads=%d", d->H, d->heads);
+  EGOT2_CHECK(d->p_drop >= 0.f && d->p_drop < 1.f, "layer: dropout p=%f out of [0,1)", d->p_drop);
+  return 0;
+}
+}  // namespace
+
+extern "C" size_t egot2_encoder_layer_workspace_bytes(const egot2_layer_desc* d, int backward) {
+  return layer_ws_layout(d, backward, nullptr, 0, nullptr);
+}
+
+extern "C" int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_layer_params* p, const void* x_in,
+                                       void* x_out, const egot2_layer_saved* s, void* workspace, size_t ws_bytes,
+                                       void* stream) {
+  (void)workspace; (void)ws_bytes;
+  cudaStream_t st = (cudaStream_t)stream;
+  EGOT2_TRY(layer_check(d));
+  const int M = d->B * d->T, H = d->H, FF = d->FF;
+  if (M == 0) return 0;
+  const float pd = d->training ? d->p_drop : 0.f;
+  const uint32_t L = (uint32_t)d->layer_index;
+  // 1. packed in-projection: qkv = x . Win^T + bin
+  {
+    GemmArgs g; g.M = M; g.N = 3 * H; g.K = H; g.A = x_in; g.lda = H; g.B = p->in_proj_w; g.ldb = H; g.trans_b = 1;
+    g.C = s->qkv; g.ldc = 3 * H; g.bias = p->in_proj_b; g.in_dtype = d->dtype; g.out_dtype = d->dtype;
+    EGOT2_TRY(gemm(g, st));
+  }
+  // 2. per-clip, per-head softmax(q k^T / sqrt(dh)) v
+  EGOT2_TRY(attention_fwd(d->dtype, d->B, d->T, H, d->heads, s->qkv, s->attn, s->lse, pd, site_key(d->seed, SITE_ATTN, L), st));
+  // 3. y1 = x + dropout1(attn . Wo^T + bo)
+  {
+    GemmArgs g; g.M = M; g.N = H; g.K = H; g.A = s->attn; g.lda = H; g.B = p->out_proj_w; g.ldb = H; g.trans_b = 1;
+    g.C = s->y1; g.ldc = H; g.bias = p->out_proj_b; g.residual = x_in; g.ldr = H;
+    g.p_drop = pd; g.drop_key = site_key(d->seed, SITE_DROP1, L); g.in_dtype = d->dtype; g.out_dtype = d->dtype;
+    EGOT2_TRY(gemm(g, st));
+  }
+  // 4. x1 = norm1(y1)
+  {
+    LayerNormArgs l; l.rows = M; l.H = H; l.dtype = d->dtype; l.x = s->y1; l.g = p->norm1_g; l.b = p->norm1_b;
+    l.eps = d->ln_eps; l.y = s->x1; l.stat = s->stat1;
+    EGOT2_TRY(layernorm_fwd(l, st));
+  }
+  // 5. hid = dropout(relu(x1 . W1^T + b1))
+  {
+    GemmArgs g; g.M = M; g.N = FF; g.K = H; g.A = s->x1; g.lda = H; g.B = p->lin1_w; g.ldb = H; g.trans_b = 1;
+    g.C = s->hid; g.ldc = FF; g.bias = p->lin1_b; g.relu = 1;
+    g.p_drop = pd; g.drop_key = site_key(d->seed, SITE_FFN, L); g.in_dtype = d->dtype; g.out_dtype = d->dtype;
+    EGOT2_TRY(gemm(g, st));
+  }
+  // 6. y2 = x1 + dropout2(hid . W2^T + b2)
+  {
+    GemmArgs g; g.M = M; g.N = H; g.K = FF; g.A = s->hid; g.lda = FF; g.B = p->lin2_w; g.ldb = FF; g.trans_b = 1;
+    g.C = s->y2; g.ldc = H; g.bias = p->lin2_b; g.residual = s->x1; g.ldr = H;
+    g.p_drop = pd; g.drop_key = site_key(d->seed, SITE_DROP2, L); g.in_dtype = d->dtype; g.out_dtype = d->dtype;
+    EGOT2_TRY(gemm(g, st));
+  }
+  // 7. x_out = norm2(y2)
+  {
+    LayerNormArgs l; l.rows = M; l.H = H; l.dtype = d->dtype; l.x = s->y2; l.g = p->norm2_g; l.b = p->norm2_b;
+    l.eps = d->ln_eps; l.y = x_out; l.stat = s->stat2;
+    EGOT2_TRY(layernorm_fwd(l, st));
+  }
+  return 0;
+}
+
+extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_layer_params* p, const void* x_in,
+                                       const egot2_layer_saved* s, void* dx_out, void* dx_in,
+                                       const egot2_layer_grads* g, void* workspace, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGOT2_TRY(layer_check(d));
+  const int M = d->B * d->T, H = d->H, FF = d->FF;
+  if (M == 0) return 0;
+  LayerWs w;
+  const size_t need = layer_ws_layout(d, 1, workspace, ws_bytes, &w);
+  EGOT2_CHECK(workspace && ws_bytes + 256 >= need, "encoder_layer_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  const size_t es = dtype_size(d->dtype);
+  const float pd = d->training ? d->p_drop : 0.f;
+  const float inv_keep = pd > 0.f ? 1.f / (1.f - pd) : 1.f;
+  const uint32_t L = (uint32_t)d->layer_index;
+  const int dt = d->dtype;
+
+  // 1. through norm2: d1 = dL/dy2
+  {
+    LayerNormBwdArgs l; l.rows = M; l.H = H; l.dtype = dt; l.x = s->y2; l.stat = s->stat2; l.g = p->norm2_g;
+    l.dy = dx_out; l.dx = w.d1; l.dg = g->norm2_g; l.db = g->norm2_b;
+    EGOT2_TRY(layernorm_bwd(l, st));
+  }
+  // 2. dropout2 mask -> d2 = dL/d(linear2 out)
+  const void* d2 = w.d1;
+  if (pd > 0.f) {
+    EGOT2_CUDA(cudaMemcpyAsync(w.d2, w.d1, (size_t)M * H * es, cudaMemcpyDeviceToDevice, st));
+    EGOT2_TRY(dropout_inplace(dt, w.d2, (size_t)M * H, pd, site_key(d->seed, SITE_DROP2, L), st));
+    d2 = w.d2;
+  }
+  //    linear2: dW2 += d2^T . hid ; db2 += colsum(d2) ; dhid = (d2 . W2) * relu'(hid) * ffn-dropout scale
+  EGOT2_TRY(wgrad(dt, M, H, FF, d2, H, 0, 0, s->hid, FF, 0, 0, g->lin2_w, st));
+  EGOT2_TRY(colsum_accum(dt, M, H, d2, H, 0, 0, g->lin2_b, st));
+  {
+    GemmArgs m; m.M = M; m.N = FF; m.K = H; m.A = d2; m.lda = H; m.B = p->lin2_w; m.ldb = FF; m.trans_b = 0;
+    m.C = w.dhid; m.ldc = FF; m.mask = s->hid; m.ldm = FF; m.mask_scale = inv_keep; m.in_dtype = dt; m.out_dtype = dt;
+    EGOT2_TRY(gemm(m, st));
+  }
+  // 3. linear1: dW1 += dhid^T . x1 ; db1 += colsum(dhid) ; d3 = dhid . W1 + d1 (residual branch)
+  EGOT2_TRY(wgrad(dt, M, FF, H, w.dhid, FF, 0, 0, s->x1, H, 0, 0, g->lin1_w, st));
+  EGOT2_TRY(colsum_accum(dt, M, FF, w.dhid, FF, 0, 0, g->lin1_b, st));
+  {
+    GemmArgs m; m.M = M; m.N = H; m.K = FF; m.A = w.dhid; m.lda = FF; m.B = p->lin1_w; m.ldb = H; m.trans_b = 0;
+    m.C = w.d3; m.ldc = H; m.residual = w.d1; m.ldr = H; m.in_dtype = dt; m.out_dtype = dt;
+    EGOT2_TRY(gemm(m, st));
+  }
+  // 4. through norm1: d1 = dL/dy1
+  {
+    LayerNormBwdArgs l; l.rows = M; l.H = H; l.dtype = dt; l.x = s->y1; l.stat = s->stat1; l.g = p->norm1_g;
+    l.dy = w.d3; l.dx = w.d1; l.dg = g->norm1_g; l.db = g->norm1_b;
+    EGOT2_TRY(layernorm_bwd(l, st));
+  }
+  // 5. dropout1 mask -> d4 ; out_proj: dWo += d4^T . attn ; dbo += colsum(d4) ; dattn = d4 . Wo
+  const void* d4 = w.d1;
+  if (pd > 0.f) {
+    EGOT2_CUDA(cudaMemcpyAsync(w.d2, w.d1, (size_t)M * H * es, cudaMemcpyDeviceToDevice, st));
+    EGOT2_TRY(dropout_inplace(dt, w.d2, (size_t)M * H, pd, site_key(d->seed, SITE_DROP1, L), st));
+    d4 = w.d2;
+  }
+  EGOT2_TRY(wgrad(dt, M, H, H, d4, H, 0, 0, s->attn, H, 0, 0, g->out_proj_w, st));
+  EGOT2_TRY(colsum_accum(dt, M, H, d4, H, 0, 0, g->out_proj_b, st));
+  {
+    GemmArgs m; m.M = M; m.N = H; m.K = H; m.A = d4; m.lda = H; m.B = p->out_proj_w; m.ldb = H; m.trans_b = 0;
+    m.C = w.d3; m.ldc = H; m.in_dtype = dt; m.out_dtype = dt;
+    EGOT2_TRY(gemm(m, st));
+  }
+  // 6. attention backward -> dqkv
+  EGOT2_TRY(attention_bwd(dt, d->B, d->T, H, d->heads, s->qkv, s->attn, s->lse, w.d3, w.dqkv, pd,
+                          site_key(d->seed, SITE_ATTN, L), w.attn_ws, w.attn_ws_bytes, st));
+  // 7. in_proj: dWin += dqkv^T . x ; dbin += colsum(dqkv) ; dx = dqkv . Win + d1 (residual branch)
+  EGOT2_TRY(wgrad(dt, M, 3 * H, H, w.dqkv, 3 * H, 0, 0, x_in, H, 0, 0, g->in_proj_w, st));
+  EGOT2_TRY(colsum_accum(dt, M, 3 * H, w.dqkv, 3 * H, 0, 0, g->in_proj_b, st));
+  {
+    GemmArgs m; m.M = M; m.N = H; m.K = 3 * H; m.A = w.dqkv; m.lda = 3 * H; m.B = p->in_proj_w; m.ldb = H; m.trans_b = 0;
+    m.C = dx_in; m.ldc = H; m.residual = w.d1; m.ldr = H; m.in_dtype = dt; m.out_dtype = dt;
+    EGOT2_TRY(gemm(m, st));
+  }
+  return 0;
+}
+
+// =============================================================================== head + loss
+extern "C" int egot2_head_rows(const egot2_head_desc* d) { return d->pool ? d->B : d->B * d->row_tokens; }
+
+extern "C" size_t egot2_head_workspace_bytes(const egot2_head_desc* d) {
+  const size_t rows = (size_t)egot2_head_rows(d), es = dtype_size(d->dtype);
+  return align_up(rows * d->n_out * es) + align_up(rows * d->H * es) + align_up(rows * d->H * 4) + 256;
+}
+
+extern "C" int egot2_head_loss_fwd(const egot2_head_desc* d, const egot2_head_in* in, const egot2_head_out* out,
+                                   void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = egot2_head_rows(d);
+  if (rows == 0) return 0;
+  EGOT2_CHECK(d->pool || (d->row_tokens > 0 && d->row_tokens <= d->T), "head: row_tokens=%d out of range", d->row_tokens);
+  EGOT2_TRY(pool_fwd(d->dtype, d->B, d->T, d->H, d->pool, d->row_tokens, in->x, out->pooled, st));
+  const float ph = d->training ? d->p_head : 0.f;
+  if (d->use_ln) {
+    LayerNormArgs l; l.rows = rows; l.H = d->H; l.dtype = d->dtype; l.x = out->pooled; l.x_is_f32 = 1; l.g = in->ln_g;
+    l.b = in->ln_b; l.eps = d->ln_eps; l.y = out->g; l.stat = out->stat;
+    l.p_drop = ph; l.drop_key = site_key(d->seed, SITE_HEAD, 0);
+    EGOT2_TRY(layernorm_fwd(l, st));
+  } else {
+    EGOT2_TRY(cast_f32_to(d->dtype, out->pooled, out->g, (size_t)rows * d->H, st));
+    EGOT2_TRY(dropout_inplace(d->dtype, out->g, (size_t)rows * d->H, ph, site_key(d->seed, SITE_HEAD, 0), st));
+  }
+  {
+    GemmArgs g; g.M = rows; g.N = d->n_out; g.K = d->H; g.A = out->g; g.lda = d->H; g.B = in->w; g.ldb = d->H; g.trans_b = 1;
+    g.C = out->logits; g.ldc = d->n_out; g.bias = in->b; g.in_dtype = d->dtype; g.out_dtype = EGOT2_F32;
+    EGOT2_TRY(gemm(g, st));
+  }
+  return loss_fwd(*d, rows, out->logits, in->labels, in->class_weight, out->row_loss, out->loss, out->argmax, st);
+}
+
+extern "C" int egot2_head_loss_bwd(const egot2_head_desc* d, const egot2_head_in* in, const egot2_head_out* saved,
+                                   float* dlogits, float dloss_scale, void* dx, const egot2_head_grads* g,
+                                   void* workspace, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = egot2_head_rows(d);
+  if (rows == 0) return 0;
+  const size_t es = dtype_size(d->dtype);
+  EGOT2_CHECK(workspace && ws_bytes >= egot2_head_workspace_bytes(d) - 256, "head_loss_bwd: workspace too small");
+  Carver ws(workspace, ws_bytes);
+  void* dl_lp = ws.take((size_t)rows * d->n_out * es);
+  void* dg = ws.take((size_t)rows * d->H * es);
+  float* dpooled = (float*)ws.take((size_t)rows * d->H * 4);
+  if (d->loss != EGOT2_LOSS_NONE)
+    EGOT2_TRY(loss_bwd(*d, rows, saved->logits, in->labels, in->class_weight, saved->loss, dloss_scale, dlogits, st));
+  const void* dl = dlogits;
+  if (d->dtype != EGOT2_F32) {
+    EGOT2_TRY(cast_f32_to(d->dtype, dlogits, dl_lp, (size_t)rows * d->n_out, st));
+    dl = dl_lp;
+  }
+  if (g->w) EGOT2_TRY(wgrad(d->dtype, rows, d->n_out, d->H, dl, d->n_out, 0, 0, saved->g, d->H, 0, 0, g->w, st));
+  if (g->b) EGOT2_TRY(colsum_accum(EGOT2_F32, rows, d->n_out, dlogits, d->n_out, 0, 0, g->b, st));
+  {
+    GemmArgs m; m.M = rows; m.N = d->H; m.K = d->n_out; m.A = dl; m.lda = d->n_out; m.B = in->w; m.ldb = d->H; m.trans_b = 0;
+    m.C = dg; m.ldc = d->H; m.in_dtype = d->dtype; m.out_dtype = d->dtype;
+    EGOT2_TRY(gemm(m, st));
+  }
+  const float ph = d->training ? d->p_head : 0.f;
+  EGOT2_TRY(dropout_inplace(d->dtype, dg, (size_t)rows * d->H, ph, site_key(d->seed, SITE_HEAD, 0), st));
+  if (d->use_ln) {
+    LayerNormBwdArgs l; l.rows = rows; l.H = d->H; l.dtype = d->dtype; l.x = saved->pooled; l.x_is_f32 = 1;
+    l.stat = saved->stat; l.g = in->ln_g; l.dy = dg; l.dy_is_f32 = (d->dtype == EGOT2_F32); l.dx = dpooled; l.dx_is_f32 = 1;
+    l.dg = g->ln_g; l.db = g->ln_b;
+    EGOT2_TRY(layernorm_bwd(l, st));
+  } else {
+    EGOT2_TRY(cast_to_f32(d->dtype, dg, dpooled, (size_t)rows * d->H, st));
+  }
+  return pool_bwd(d->dtype, d->B, d->T, d->H, d->pool, d->row_tokens, dpooled, dx, st);
+}
+
+// =============================================================================== op-level entry points
+extern "C" int egot2_gemm(int32_t dtype, int32_t M, int32_t N, int32_t K, const void* A, int32_t trans_a, const void* B,
+                          int32_t trans_b, const float* bias, int32_t relu, void* C, int32_t c_is_f32,
+                          int32_t accumulate, void* stream) {
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.trans_a = trans_a; g.lda = trans_a ? M : K;
+  g.B = B; g.trans_b = trans_b; g.ldb = trans_b ? K : N;
+  g.C = C; g.ldc = N; g.bias = bias; g.relu = relu;
+  g.in_dtype = dtype; g.out_dtype = c_is_f32 ? EGOT2_F32 : dtype; g.accumulate = accumulate;
+  if (accumulate && !relu) g.split_k = suggest_split_k(M, N, K);
+  return gemm(g, (cudaStream_t)stream);
+}
+
+extern "C" int egot2_attention_fwd(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t heads, const void* qkv,
+                                   void* out, float* lse, float p_drop, int32_t training, uint64_t seed, void* stream) {
+  return attention_fwd(dtype, B, T, H, heads, qkv, out, lse, training ? p_drop : 0.f, site_key(seed, SITE_ATTN, 0),
+                       (cudaStream_t)stream);
+}
+extern "C" int egot2_attention_bwd(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t heads, const void* qkv,
+                                   const void* out, const float* lse, const void* dout, void* dqkv, float p_drop,
+                                   int32_t training, uint64_t seed, void* workspace, size_t ws_bytes, void* stream) {
+  return attention_bwd(dtype, B, T, H, heads, qkv, out, lse, dout, dqkv, training ? p_drop : 0.f,
+                       site_key(seed, SITE_ATTN, 0), workspace, ws_bytes, (cudaStream_t)stream);
+}
+extern "C" size_t egot2_attention_bwd_workspace_bytes(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t heads) {
+  return attention_bwd_workspace(dtype, B, T, H, heads);
+}
+extern "C" int egot2_pool_fwd(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t pool, int32_t row_tokens,
+                              const void* x, float* pooled, void* stream) {
+  return pool_fwd(dtype, B, T, H, pool, row_tokens, x, pooled, (cudaStream_t)stream);
+}
+extern "C" int egot2_pool_bwd(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t pool, int32_t row_tokens,
+                              const float* dpooled, void* dx, void* stream) {
+  return pool_bwd(dtype, B, T, H, pool, row_tokens, dpooled, dx, (cudaStream_t)stream);
+}

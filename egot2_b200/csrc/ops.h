@@ -1,0 +1,90 @@
+// ops.h — internal launchers shared by the stage-level C ABI (api.cu).
+#pragma once
+#include "common.cuh"
+
+namespace egot2 {
+
+// C[M,N] = epilogue( op(A)[M,K] . op(B)[K,N] )
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const void* A = nullptr; int lda = 0; int trans_a = 0;   // trans_a: stored (K,M)
+  const void* B = nullptr; int ldb = 0; int trans_b = 0;   // trans_b: stored (N,K)  [nn.Linear weight]
+  void* C = nullptr;       int ldc = 0;
+  int in_dtype = EGOT2_F32;      // dtype of A and B
+  int out_dtype = EGOT2_F32;     // dtype of C (and of residual / mask)
+  // storage-row remap (segment scatter/gather inside (B,T,H) tensors):
+  //   physical row = (r / rpg) * gstride + (r % rpg)   when rpg > 0
+  int a_rpg = 0, a_gstride = 0;
+  int b_rpg = 0, b_gstride = 0;
+  int c_rpg = 0, c_gstride = 0;
+  // epilogue, applied in this order
+  const float* bias = nullptr;   // + bias[n]
+  int relu = 0;                  // max(.,0)
+  const void* mask = nullptr; int ldm = 0; float mask_scale = 1.f;   // * (mask[m,n] > 0 ? mask_scale : 0)
+  float p_drop = 0.f; uint64_t drop_key = 0;                         // * dropmask(m*N+n)/(1-p)
+  const void* residual = nullptr; int ldr = 0;                       // + residual[m,n]
+  int accumulate = 0;            // C += value (fp32 C only); split-K uses atomics
+  int split_k = 1;
+};
+int gemm(const GemmArgs& a, cudaStream_t st);          // dispatch: tcgen05 (bf16, supported shapes) or CUDA-core
+int gemm_simt(const GemmArgs& a, cudaStream_t st);     // gemm_simt.cu
+int gemm_sm100(const GemmArgs& a, cudaStream_t st);    // gemm_sm100.cu; returns -1 if the shape is not handled
+int suggest_split_k(int M, int N, int K);
+// which implementation handled the last bf16 GEMM ("tcgen05" | "simt"); diagnostics only
+const char* gemm_last_impl();
+
+// y = LN(x [+ res]) * g + b (+ table[row % table_rows]); optional dropout after; stat = (mean, rstd)
+struct LayerNormArgs {
+  int rows = 0, H = 0; int dtype = EGOT2_F32;
+  const void* x = nullptr; const float* g = nullptr; const float* b = nullptr; float eps = 1e-5f;
+  void* y = nullptr; float* stat = nullptr;
+  const float* table = nullptr; int table_rows = 0;
+  float p_drop = 0.f; uint64_t drop_key = 0;
+  int x_is_f32 = 0;              // x is fp32 regardless of dtype (pooled vectors)
+};
+int layernorm_fwd(const LayerNormArgs& a, cudaStream_t st);
+// dx = LN'(dy) (+ dres);  dg += sum dy*xhat;  db += sum dy
+struct LayerNormBwdArgs {
+  int rows = 0, H = 0; int dtype = EGOT2_F32;
+  const void* x = nullptr; const float* stat = nullptr; const float* g = nullptr;
+  const void* dy = nullptr;      // dtype (fp32 if dy_is_f32)
+  void* dx = nullptr;            // dtype (fp32 if dx_is_f32); may alias dy
+  const void* dres = nullptr;    // optional (dtype): dx += dres, the gradient arriving through a residual branch
+  float* dg = nullptr; float* db = nullptr;
+  int x_is_f32 = 0; int dx_is_f32 = 0; int dy_is_f32 = 0;
+};
+int layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t st);
+
+int attention_simt_fwd(int dtype, int B, int T, int H, int heads, const void* qkv, void* out, float* lse,
+                       float p_drop, uint64_t drop_key, cudaStream_t st);
+int attention_simt_bwd(int dtype, int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse,
+                       const void* dout, void* dqkv, float p_drop, uint64_t drop_key, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
+int attention_fwd(int dtype, int B, int T, int H, int heads, const void* qkv, void* out, float* lse,
+                  float p_drop, uint64_t drop_key, cudaStream_t st);
+size_t attention_bwd_workspace(int dtype, int B, int T, int H, int heads);
+int attention_bwd(int dtype, int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse,
+                  const void* dout, void* dqkv, float p_drop, uint64_t drop_key, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+
+// dtable[t,:] += sum_b dy[b,t,:]   (gradient of the (T,H) token table added after the embed LN)
+int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, cudaStream_t st);
+// column sums: out[n] += sum_m x[m,n]   (bias gradients)
+int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int gstride, float* out, cudaStream_t st);
+// in-place x *= dropmask/(1-p) over n elements (idx = linear element index)
+int dropout_inplace(int dtype, void* x, size_t n, float p, uint64_t key, cudaStream_t st);
+// pooled[b,:] = mean_t x[b,t,:]   or gather of the first row_tokens tokens (pool==0)
+int pool_fwd(int dtype, int B, int T, int H, int pool, int row_tokens, const void* x, float* pooled, cudaStream_t st);
+int pool_bwd(int dtype, int B, int T, int H, int pool, int row_tokens, const float* dpooled, void* dx, cudaStream_t st);
+int cast_f32_to(int dtype, const float* src, void* dst, size_t n, cudaStream_t st);
+int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t st);
+int zero_f32(float* p, size_t n, cudaStream_t st);
+
+// losses on fp32 logits (rows, n_out)
+int loss_fwd(const egot2_head_desc& d, int rows, const float* logits, const int64_t* labels, const float* class_weight,
+             float* row_loss, float* loss, int32_t* argmax, cudaStream_t st);
+// loss2 = the (2,) buffer written by loss_fwd: [loss, total weight]
+int loss_bwd(const egot2_head_desc& d, int rows, const float* logits, const int64_t* labels, const float* class_weight,
+             const float* loss2, float dloss_scale, float* dlogits, cudaStream_t st);
+
+}  // namespace egot2

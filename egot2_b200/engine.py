@@ -1,0 +1,447 @@
+"""Host-side driver of the translator hot path: parameter arena, activation buffers, and the
+sequence of C-ABI stage calls (embed -> L x encoder layer -> head[+loss]) forward and backward.
+
+PyTorch is used here for device memory (caching allocator), streams and views only; every
+FLOP on the path is executed by libegot2.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .specs import TranslatorSpec
+
+_ALIGN = 64  # elements: keeps every tensor 256 B (fp32) / 128 B (bf16) aligned for vector + TMA access
+
+
+def _dt(dtype: str) -> int:
+    return {"fp32": L.F32, "bf16": L.BF16}[dtype]
+
+
+def _torch_dt(dtype: str) -> torch.dtype:
+    return {"fp32": torch.float32, "bf16": torch.bfloat16}[dtype]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class ParamArena:
+    """All translator parameters in ONE flat fp32 buffer (+ same-layout gradient buffer and bf16
+    shadow).  One buffer = one NCCL all-reduce, one Adam launch, one fp32->bf16 cast launch.
+    The LTA head's Z independent Linear layers are laid out back to back so that they form one
+    (Z*593, H) matrix for a single GEMM."""
+
+    def __init__(self, spec: TranslatorSpec, device: torch.device):
+        self.spec = spec
+        self.device = torch.device(device)
+        shapes = spec.param_shapes()
+        self.shapes = shapes
+        self.offsets: Dict[str, int] = {}
+        off = 0
+
+        def place(name, numel, align=True):
+            nonlocal off
+            if align:
+                off = (off + _ALIGN - 1) // _ALIGN * _ALIGN
+            self.offsets[name] = off
+            off += numel
+
+        head_w = [n for n in shapes if re.fullmatch(r"head\.projections\.\d+\.weight", n)]
+        head_b = [n for n in shapes if re.fullmatch(r"head\.projections\.\d+\.bias", n)]
+        for name, shp in shapes.items():
+            if name in head_w or name in head_b:
+                continue
+            place(name, _numel(shp))
+        for i, name in enumerate(head_w):      # contiguous block, no padding between heads
+            place(name, _numel(shapes[name]), align=(i == 0))
+        for i, name in enumerate(head_b):
+            place(name, _numel(shapes[name]), align=(i == 0))
+        self.numel = (off + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.param = torch.zeros(self.numel, device=self.device, dtype=torch.float32)
+        self.grad = torch.zeros(self.numel, device=self.device, dtype=torch.float32)
+        self.shadow: Optional[torch.Tensor] = None
+        self.head_w_names, self.head_b_names = head_w, head_b
+
+    def view(self, name: str, base: Optional[torch.Tensor] = None) -> torch.Tensor:
+        base = self.param if base is None else base
+        shp = self.shapes[name]
+        o = self.offsets[name]
+        return base[o:o + _numel(shp)].view(shp)
+
+    def stacked_head(self, base: Optional[torch.Tensor] = None):
+        """(Z*per, H) weight and (Z*per,) bias views of the LTA head."""
+        base = self.param if base is None else base
+        w0, b0 = self.head_w_names[0], self.head_b_names[0]
+        per, H = self.shapes[w0]
+        Z = len(self.head_w_names)
+        ow, ob = self.offsets[w0], self.offsets[b0]
+        return base[ow:ow + Z * per * H].view(Z * per, H), base[ob:ob + Z * per]
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        with torch.no_grad():
+            for name in self.shapes:
+                self.view(name).copy_(sd[name].to(device=self.device, dtype=torch.float32))
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {name: self.view(name).clone() for name in self.shapes}
+
+    def refresh_shadow(self):
+        """fp32 -> bf16 shadow of the whole arena (one launch)."""
+        if self.shadow is None:
+            self.shadow = torch.empty(self.numel, device=self.device, dtype=torch.bfloat16)
+        L.call("egot2_cast_f32_to_bf16", self.param.data_ptr(), self.shadow.data_ptr(), self.numel, _stream())
+
+
+def _numel(shp) -> int:
+    n = 1
+    for d in shp:
+        n *= d
+    return n
+
+
+@dataclass
+class Activations:
+    """Everything one forward leaves behind for its backward (device buffers + the descriptors)."""
+    B: int
+    seg_tokens: Tuple[int, ...]
+    T: int
+    training: bool
+    seed: int
+    feats: List[torch.Tensor] = field(default_factory=list)
+    t: Dict[str, torch.Tensor] = field(default_factory=dict)     # named buffers
+    embed_desc: Optional[L.EmbedDesc] = None
+    embed_in: Optional[L.EmbedIn] = None
+    embed_out: Optional[L.EmbedOut] = None
+    layer_desc: List[L.LayerDesc] = field(default_factory=list)
+    layer_params: List[L.LayerParams] = field(default_factory=list)
+    layer_saved: List[L.LayerSaved] = field(default_factory=list)
+    head_desc: Optional[L.HeadDesc] = None
+    head_in: Optional[L.HeadIn] = None
+    head_out: Optional[L.HeadOut] = None
+    rows: int = 0
+
+
+class TranslatorEngine:
+    """Runs one translator variant (`spec`) on one GPU in `dtype` ("fp32" parity mode or "bf16")."""
+
+    def __init__(self, spec: TranslatorSpec, device, dtype: str = "fp32", arena: Optional[ParamArena] = None):
+        L.load()
+        if not torch.cuda.is_available():
+            raise L.Egot2Error("egot2_b200 needs a CUDA device (no CPU fallback)")
+        self.spec = spec
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.dt = _dt(dtype)
+        self.tdt = _torch_dt(dtype)
+        self.arena = arena if arena is not None else ParamArena(spec, self.device)
+        self.pe_buffer: Optional[torch.Tensor] = None     # HHI: (max_len, H) sinusoid table (pos_embed.pe)
+        self.lossav: Optional[Dict[str, torch.Tensor]] = None
+        self._ws: Optional[torch.Tensor] = None
+        self._persistent: Dict[Tuple, Activations] = {}
+        self.shadow_valid = False
+
+    # ------------------------------------------------------------------ helpers
+    def _mat(self, name: str) -> torch.Tensor:
+        """Matrix parameter in the compute dtype."""
+        if self.dtype == "bf16":
+            return self.arena.view(name, self.arena.shadow)
+        return self.arena.view(name)
+
+    def _vec(self, name: str) -> torch.Tensor:
+        return self.arena.view(name)
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes), device=self.device, dtype=torch.uint8)
+        return self._ws
+
+    def set_sinusoid(self, pe: torch.Tensor):
+        """pe: the module's registered buffer pos_embed.pe, (max_len, 1, H) or (max_len, H)."""
+        self.pe_buffer = pe.reshape(pe.shape[0], -1).to(device=self.device, dtype=torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, feats: Sequence[torch.Tensor], training: bool = False, seed: int = 0,
+                labels: Optional[torch.Tensor] = None, loss: int = L.LOSS_NONE,
+                class_weight: Optional[torch.Tensor] = None, persistent: bool = False) -> Activations:
+        sp = self.spec
+        assert len(feats) == len(sp.segments), f"expected {len(sp.segments)} feature streams"
+        B = int(feats[0].shape[0])
+        seg_tokens = tuple(int(f.shape[1]) for f in feats)
+        for f, s in zip(feats, sp.segments):
+            assert f.shape[0] == B and f.shape[2] == s.in_dim, f"{s.name}: bad feature shape {tuple(f.shape)}"
+            assert s.tokens is None or f.shape[1] == s.tokens, f"{s.name}: expected {s.tokens} tokens"
+        feat_dt = feats[0].dtype
+        if self.dtype == "fp32":
+            feats = [f.float().contiguous() for f in feats]
+            feat_dt = torch.float32
+        else:
+            if any(f.dtype != feat_dt for f in feats) or feat_dt not in (torch.float32, torch.bfloat16):
+                feats = [f.to(torch.bfloat16) for f in feats]
+                feat_dt = torch.bfloat16
+            feats = [f.contiguous() for f in feats]
+        T = sum(seg_tokens)
+        H, FF = sp.hidden, sp.ffn
+        M = B * T
+        dev, tdt = self.device, self.tdt
+        st = _stream()
+        if self.dtype == "bf16":
+            self.arena.refresh_shadow()
+
+        key = (B, seg_tokens, bool(training), feat_dt, loss)
+        act = self._persistent.get(key) if persistent else None
+        fresh = act is None
+        if fresh:
+            act = Activations(B, seg_tokens, T, bool(training), int(seed))
+            if persistent:
+                self._persistent[key] = act
+        act.seed = int(seed)
+        act.feats = list(feats)
+        t = act.t
+
+        def buf(name, shape, dtype):
+            if name not in t:
+                t[name] = torch.empty(shape, device=dev, dtype=dtype)
+            return t[name]
+
+        # ---- token table (what is added after the shared LN)
+        if sp.embed == "task_sinusoid":
+            if self.pe_buffer is None:
+                raise L.Egot2Error("HHI translator: call set_sinusoid(pos_embed.pe) first")
+            table = buf("tok_table", (T, H), torch.float32)
+            segs = (C.c_int32 * len(seg_tokens))(*seg_tokens)
+            ids = (C.c_int32 * len(seg_tokens))(*[s.task_id for s in sp.segments])
+            L.call("egot2_hhi_tok_table_fwd", self._vec("task_embed").data_ptr(), self.pe_buffer.data_ptr(),
+                   int(self.pe_buffer.shape[0]), len(seg_tokens), segs, ids, H, table.data_ptr(), st)
+        else:
+            table = self._vec("pe").view(T, H)
+
+        # ---- embed
+        if fresh or act.embed_desc is None:
+            d = L.EmbedDesc()
+            d.dtype = self.dt
+            d.B, d.T, d.H, d.n_seg = B, T, H, len(seg_tokens)
+            off = 0
+            for k, (s, dk) in enumerate(zip(sp.segments, seg_tokens)):
+                d.seg_tokens[k], d.seg_in_dim[k], d.seg_offset[k] = dk, s.in_dim, off
+                d.seg_has_proj[k] = 1 if s.proj is not None else 0
+                off += dk
+            d.ln_eps = 1e-5
+            act.embed_desc = d
+            act.embed_in, act.embed_out = L.EmbedIn(), L.EmbedOut()
+        d = act.embed_desc
+        d.feat_dtype = L.F32 if feat_dt == torch.float32 else L.BF16
+        d.training, d.p_feat, d.p_embed, d.seed = int(training), sp.p_feat, sp.p_embed, int(seed)
+        ein, eout = act.embed_in, act.embed_out
+        for k, s in enumerate(sp.segments):
+            ein.feat[k] = feats[k].data_ptr()
+            if s.proj is not None:
+                ein.proj_w[k] = self._mat(s.proj + ".weight").data_ptr()
+                ein.proj_b[k] = self._vec(s.proj + ".bias").data_ptr()
+        ein.ln_g, ein.ln_b = self._vec("ln.weight").data_ptr(), self._vec("ln.bias").data_ptr()
+        ein.tok_table = table.data_ptr()
+        eout.z = buf("z", (B, T, H), tdt).data_ptr()
+        eout.stat = buf("stat0", (M, 2), torch.float32).data_ptr()
+        x = buf("x0", (B, T, H), tdt)
+        eout.x = x.data_ptr()
+        ws_bytes = L.load().egot2_embed_workspace_bytes(C.byref(d), 0)
+        ws = self._workspace(ws_bytes)
+        L.call("egot2_embed_fwd", C.byref(d), C.byref(ein), C.byref(eout), ws.data_ptr(), ws.numel(), st)
+
+        # ---- encoder layers
+        if fresh or not act.layer_desc:
+            act.layer_desc, act.layer_params, act.layer_saved = [], [], []
+            for i in range(sp.layers):
+                ld = L.LayerDesc()
+                ld.dtype, ld.B, ld.T, ld.H, ld.FF, ld.heads = self.dt, B, T, H, FF, sp.heads
+                ld.layer_index, ld.ln_eps = i, 1e-5
+                act.layer_desc.append(ld)
+                act.layer_params.append(L.LayerParams())
+                act.layer_saved.append(L.LayerSaved())
+        for i in range(sp.layers):
+            ld, lp, ls = act.layer_desc[i], act.layer_params[i], act.layer_saved[i]
+            ld.training, ld.p_drop, ld.seed = int(training), sp.p_layer, int(seed)
+            self._fill_layer_params(lp, i)
+            ls.qkv = buf(f"qkv{i}", (M, 3 * H), tdt).data_ptr()
+            ls.attn = buf(f"attn{i}", (M, H), tdt).data_ptr()
+            ls.lse = buf(f"lse{i}", (B, sp.heads, T), torch.float32).data_ptr()
+            ls.y1 = buf(f"y1_{i}", (M, H), tdt).data_ptr()
+            ls.stat1 = buf(f"stat1_{i}", (M, 2), torch.float32).data_ptr()
+            ls.x1 = buf(f"x1_{i}", (M, H), tdt).data_ptr()
+            ls.hid = buf(f"hid{i}", (M, FF), tdt).data_ptr()
+            ls.y2 = buf(f"y2_{i}", (M, H), tdt).data_ptr()
+            ls.stat2 = buf(f"stat2_{i}", (M, 2), torch.float32).data_ptr()
+            x_out = buf(f"x{i + 1}", (B, T, H), tdt)
+            L.call("egot2_encoder_layer_fwd", C.byref(ld), C.byref(lp), x.data_ptr(), x_out.data_ptr(), C.byref(ls),
+                   None, 0, st)
+            x = x_out
+        t["x_last"] = x
+
+        # ---- head
+        if sp.head == "tokens":
+            D0 = seg_tokens[0]
+            act.rows = B * D0
+            out = buf("pooled", (act.rows, H), torch.float32)
+            L.call("egot2_pool_fwd", self.dt, B, T, H, 0, D0, x.data_ptr(), out.data_ptr(), st)
+            t["out"] = out
+            return act
+        if fresh or act.head_desc is None:
+            hd = L.HeadDesc()
+            hd.dtype, hd.B, hd.T, hd.H, hd.pool, hd.row_tokens = self.dt, B, T, H, 1, 0
+            hd.use_ln = 1 if sp.head == "pool_ln_linear" else 0
+            hd.n_out, hd.ln_eps = sp.n_out, 1e-5
+            if sp.head == "pool_multilinear":
+                hd.n_groups, hd.sub_rows = len(sp.head_groups), sp.n_heads_out
+                for gi, gs in enumerate(sp.head_groups):
+                    hd.group_size[gi] = gs
+            act.head_desc, act.head_in, act.head_out = hd, L.HeadIn(), L.HeadOut()
+        hd, hin, hout = act.head_desc, act.head_in, act.head_out
+        hd.loss, hd.training, hd.p_head, hd.seed = int(loss), int(training), sp.p_head, int(seed)
+        rows = B
+        act.rows = rows
+        hin.x = x.data_ptr()
+        if sp.head == "pool_ln_linear":
+            ln_name = "ln" if sp.head_ln_shared else "linear_head.0"
+            hin.ln_g, hin.ln_b = self._vec(ln_name + ".weight").data_ptr(), self._vec(ln_name + ".bias").data_ptr()
+            hin.w, hin.b = self._mat("linear_head.1.weight").data_ptr(), self._vec("linear_head.1.bias").data_ptr()
+        else:
+            base = self.arena.shadow if self.dtype == "bf16" else self.arena.param
+            w, _ = self.arena.stacked_head(base)
+            _, bvec = self.arena.stacked_head(self.arena.param)
+            hin.w, hin.b = w.data_ptr(), bvec.data_ptr()
+        if loss != L.LOSS_NONE:
+            assert labels is not None
+            lab = labels.to(device=dev, dtype=torch.int64).contiguous()
+            t["labels"] = lab
+            hin.labels = lab.data_ptr()
+            if class_weight is not None:
+                cw = class_weight.to(device=dev, dtype=torch.float32).contiguous()
+                t["class_weight"] = cw
+                hin.class_weight = cw.data_ptr()
+            else:
+                hin.class_weight = None
+            segs = rows * (sp.n_heads_out * len(sp.head_groups) if sp.head == "pool_multilinear" else 1)
+            hout.row_loss = buf("row_loss", (segs, 2), torch.float32).data_ptr()
+            hout.loss = buf("loss", (2,), torch.float32).data_ptr()
+            hout.argmax = buf("argmax", (segs,), torch.int32).data_ptr()
+        hout.pooled = buf("pooled", (rows, H), torch.float32).data_ptr()
+        hout.stat = buf("stat_head", (rows, 2), torch.float32).data_ptr()
+        hout.g = buf("g_head", (rows, H), tdt).data_ptr()
+        logits = buf("logits", (rows, sp.n_out), torch.float32)
+        hout.logits = logits.data_ptr()
+        L.call("egot2_head_loss_fwd", C.byref(hd), C.byref(hin), C.byref(hout), st)
+        t["out"] = logits
+        return act
+
+    def _fill_layer_params(self, lp: L.LayerParams, i: int, grads_base: Optional[torch.Tensor] = None):
+        p = f"{self.spec.encoder_prefix}layers.{i}."
+        names = {"in_proj_w": "self_attn.in_proj_weight", "out_proj_w": "self_attn.out_proj.weight",
+                 "lin1_w": "linear1.weight", "lin2_w": "linear2.weight", "in_proj_b": "self_attn.in_proj_bias",
+                 "out_proj_b": "self_attn.out_proj.bias", "lin1_b": "linear1.bias", "lin2_b": "linear2.bias",
+                 "norm1_g": "norm1.weight", "norm1_b": "norm1.bias", "norm2_g": "norm2.weight", "norm2_b": "norm2.bias"}
+        for f, n in names.items():
+            if grads_base is not None:
+                setattr(lp, f, self.arena.view(p + n, grads_base).data_ptr())
+            elif f.endswith("_w"):
+                setattr(lp, f, self._mat(p + n).data_ptr())
+            else:
+                setattr(lp, f, self._vec(p + n).data_ptr())
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, act: Activations, dout: Optional[torch.Tensor] = None, dloss_scale: float = 1.0,
+                 grad: Optional[torch.Tensor] = None, zero_grad: bool = True,
+                 want_dfeat: Sequence[bool] = ()) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+        """Gradients of every translator parameter, accumulated into `grad` (a flat fp32 buffer with the
+        arena layout; default: arena.grad).  `dout`: gradient w.r.t. the forward output when the loss was
+        computed outside (drop-in autograd path); with a fused loss pass dloss_scale instead."""
+        sp = self.spec
+        B, T, H = act.B, act.T, sp.hidden
+        grad = self.arena.grad if grad is None else grad
+        if zero_grad:
+            grad.zero_()
+        st = _stream()
+        tdt, dev = self.tdt, self.device
+        t = act.t
+        gv = lambda name: self.arena.view(name, grad)
+        dx = torch.empty((B, T, H), device=dev, dtype=tdt)
+
+        # ---- head
+        if sp.head == "tokens":
+            assert dout is not None
+            dp = dout.to(device=dev, dtype=torch.float32).contiguous()
+            L.call("egot2_pool_bwd", self.dt, B, T, H, 0, act.seg_tokens[0], dp.data_ptr(), dx.data_ptr(), st)
+        else:
+            hd = act.head_desc
+            if hd.loss == L.LOSS_NONE:
+                assert dout is not None
+                dlogits = dout.to(device=dev, dtype=torch.float32).contiguous().clone()
+            else:
+                dlogits = torch.empty((act.rows, sp.n_out), device=dev, dtype=torch.float32)
+            hg = L.HeadGrads()
+            if sp.head == "pool_ln_linear":
+                ln_name = "ln" if sp.head_ln_shared else "linear_head.0"
+                hg.ln_g, hg.ln_b = gv(ln_name + ".weight").data_ptr(), gv(ln_name + ".bias").data_ptr()
+                hg.w, hg.b = gv("linear_head.1.weight").data_ptr(), gv("linear_head.1.bias").data_ptr()
+            else:
+                w, bvec = self.arena.stacked_head(grad)
+                hg.w, hg.b = w.data_ptr(), bvec.data_ptr()
+            ws = self._workspace(L.load().egot2_head_workspace_bytes(C.byref(hd)))
+            L.call("egot2_head_loss_bwd", C.byref(hd), C.byref(act.head_in), C.byref(act.head_out), dlogits.data_ptr(),
+                   float(dloss_scale), dx.data_ptr(), C.byref(hg), ws.data_ptr(), ws.numel(), st)
+
+        # ---- encoder layers (reverse)
+        for i in reversed(range(sp.layers)):
+            ld = act.layer_desc[i]
+            lg = L.LayerGrads()
+            self._fill_layer_params(lg, i, grads_base=grad)
+            x_in = t["x0"] if i == 0 else t[f"x{i}"]
+            ws = self._workspace(L.load().egot2_encoder_layer_workspace_bytes(C.byref(ld), 1))
+            L.call("egot2_encoder_layer_bwd", C.byref(ld), C.byref(act.layer_params[i]), x_in.data_ptr(),
+                   C.byref(act.layer_saved[i]), dx.data_ptr(), dx.data_ptr(), C.byref(lg), ws.data_ptr(), ws.numel(), st)
+
+        # ---- embed
+        eg = L.EmbedGrads()
+        dfeats: List[Optional[torch.Tensor]] = [None] * len(sp.segments)
+        for k, s in enumerate(sp.segments):
+            if s.proj is not None:
+                eg.proj_w[k] = gv(s.proj + ".weight").data_ptr()
+                eg.proj_b[k] = gv(s.proj + ".bias").data_ptr()
+            if k < len(want_dfeat) and want_dfeat[k]:
+                dfeats[k] = torch.empty((B, act.seg_tokens[k], s.in_dim), device=dev, dtype=torch.float32)
+                eg.dfeat[k] = dfeats[k].data_ptr()
+        eg.ln_g, eg.ln_b = gv("ln.weight").data_ptr(), gv("ln.bias").data_ptr()
+        if sp.embed == "task_sinusoid":
+            dtable = torch.zeros((T, H), device=dev, dtype=torch.float32)
+        else:
+            dtable = gv("pe").view(T, H)
+        eg.tok_table = dtable.data_ptr()
+        d = act.embed_desc
+        ws = self._workspace(L.load().egot2_embed_workspace_bytes(C.byref(d), 1))
+        L.call("egot2_embed_bwd", C.byref(d), C.byref(act.embed_in), C.byref(act.embed_out), dx.data_ptr(), C.byref(eg),
+               ws.data_ptr(), ws.numel(), st)
+        if sp.embed == "task_sinusoid":
+            segs = (C.c_int32 * len(act.seg_tokens))(*act.seg_tokens)
+            ids = (C.c_int32 * len(act.seg_tokens))(*[s.task_id for s in sp.segments])
+            L.call("egot2_hhi_tok_table_bwd", dtable.data_ptr(), len(act.seg_tokens), segs, ids, H,
+                   gv("task_embed").data_ptr(), st)
+        return grad, dfeats
+
+    # ------------------------------------------------------------------ fused optimizer
+    def adam_step(self, state: Dict[str, torch.Tensor], step: int, lr: float = 5e-4, betas=(0.9, 0.999),
+                  eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0):
+        """torch.optim.Adam over the whole arena in one launch (HHI/tasks/ttm/video_task.py:64-66: lr 5e-4)."""
+        if "m" not in state:
+            state["m"] = torch.zeros_like(self.arena.param)
+            state["v"] = torch.zeros_like(self.arena.param)
+        L.call("egot2_adam_step", self.arena.param.data_ptr(), self.arena.grad.data_ptr(), state["m"].data_ptr(),
+               state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps, weight_decay, int(step),
+               float(grad_scale), _stream())

@@ -1,0 +1,262 @@
+/*
+ * egot2.h — C ABI of libegot2.so: the B200 (sm_100a) implementation of EgoT2's task-translation
+ * hot path (per-task projection -> LayerNorm + task/positional embedding -> TransformerEncoder over
+ * the task x frame tokens -> task-of-interest head + loss, forward and backward).
+ *
+ * The reference (facebookresearch/EgoT2) is pure PyTorch: there is no FFI on this path.  The
+ * boundary these entry points replace is the arithmetic that the reference's nn.Module classes
+ * delegate to torch.nn / ATen (paths relative to the reference root):
+ *
+ *   egot2_embed_fwd/bwd          proj_* + self.ln + task_embed/pe (+dropouts)
+ *                                HHI/models/ttm/model_taskspecific.py:178-182,188-190,222-226,238-241
+ *                                HHI/models/asd/model_taskspecific.py:133-137,151-154
+ *                                HOI/models/pnr/video_model_transfer_3task.py:249-254
+ *                                HOI/models/lta/lta_models_lta_transfer.py:355-360
+ *   egot2_hhi_tok_table_fwd/bwd  task_embed[:,k,:] + PositionalEncoding.pe[:D]
+ *                                HHI/models/ttm/model_taskspecific.py:131-151,179-181
+ *   egot2_encoder_layer_fwd/bwd  one nn.TransformerEncoderLayer (post-norm, ReLU, eps 1e-5)
+ *                                HHI/models/ttm/model_taskspecific.py:168-171,191,242
+ *                                HOI/models/pnr/video_model_transfer_3task.py:231-235,255
+ *                                HOI/models/lta/lta_models_lta_transfer.py:272-275,361
+ *   egot2_head_loss_fwd/bwd      mean over tokens + linear_head (+ loss)
+ *                                HHI/models/ttm/model_taskspecific.py:192-193,243-244
+ *                                HHI/tasks/ttm/video_task.py:23-24,36 (weighted CE)
+ *                                HHI/tasks/asd/loss.py:11-30 (lossAV: FC + CE[1,4])
+ *                                HOI/models/pnr/video_model_transfer_3task.py:256-257
+ *                                HOI/tasks/pnr/video_taskspecific_pnr.py:29-31,143-146 (sigmoid+BCE / CE)
+ *                                HOI/models/lta/head_helper.py:262-290, lta_models_lta_transfer.py:348-352
+ *                                HOI/tasks/lta/long_term_anticipation_taskspecfic.py:177-183 (sum of 40 CE)
+ *   egot2_slowfast_pool_fwd      AdaptiveAvgPool3d of the raw SlowFast maps
+ *                                HOI/models/pnr/video_model_transfer_3task.py:226-227,245-247
+ *   egot2_adam_step              torch.optim.Adam over the flat translator parameter arena
+ *                                HHI/tasks/ttm/video_task.py:64-66
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (row-major, contiguous) unless the name ends in _host;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no hidden
+ *     allocation, no host sync; scratch comes from the caller via workspace/ws_bytes;
+ *   - return 0 on success; otherwise a non-zero code and egot2_last_error() (thread-local text);
+ *   - "dtype" is the activation / GEMM-operand type of the call: EGOT2_F32 runs fp32 CUDA-core
+ *     arithmetic (parity mode: logits within 1e-3 of the reference, argmax bit-exact);
+ *     EGOT2_BF16 runs bf16 tensor-core GEMMs (tcgen05/TMEM) with fp32 accumulation and fp32
+ *     LayerNorm/softmax statistics.  Matrix weights are passed in `dtype`; vectors (bias, LN
+ *     gamma/beta, embeddings), statistics, losses and ALL gradients are fp32;
+ *   - gradients are ACCUMULATED (+=) into the caller's buffers: zero the gradient arena once per
+ *     step (this is also what lets `ln` be shared by two uses in the HOI PNR translator);
+ *   - dropout masks are a pure function of (seed, site, element index), so forward and backward
+ *     regenerate the same mask; nothing is stored.
+ */
+#ifndef EGOT2_H_
+#define EGOT2_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGOT2_MAX_SEG 8
+#define EGOT2_MAX_GROUPS 4
+
+enum { EGOT2_F32 = 0, EGOT2_BF16 = 1 };
+enum { EGOT2_LOSS_NONE = 0, EGOT2_LOSS_CE = 1, EGOT2_LOSS_BCE_SIGMOID = 2, EGOT2_LOSS_CE_GROUPS = 3 };
+
+const char* egot2_version(void);
+const char* egot2_last_error(void);
+/* SM count of the current device (cached per device). */
+int egot2_sm_count(void);
+
+/* ------------------------------------------------------------------ embed stage */
+typedef struct {
+  int32_t dtype;                      /* token dtype */
+  int32_t feat_dtype;                 /* dtype of the per-task feature tensors */
+  int32_t B, T, H;                    /* clips, tokens per clip, hidden */
+  int32_t n_seg;
+  int32_t seg_tokens[EGOT2_MAX_SEG];  /* D_k: tokens this task contributes per clip */
+  int32_t seg_in_dim[EGOT2_MAX_SEG];  /* K_k: feature width */
+  int32_t seg_offset[EGOT2_MAX_SEG];  /* first token index of the task inside a clip */
+  int32_t seg_has_proj[EGOT2_MAX_SEG];/* 0: feature is already H wide and is copied through */
+  int32_t training;
+  float p_feat;                       /* dropout on the projected features BEFORE the LN (HOI self.dp) */
+  float p_embed;                      /* dropout AFTER the embedding add (HHI PositionalEncoding.dropout) */
+  float ln_eps;
+  uint64_t seed;
+} egot2_embed_desc;
+
+typedef struct {
+  const void* feat[EGOT2_MAX_SEG];    /* (B, D_k, K_k), feat_dtype */
+  const void* proj_w[EGOT2_MAX_SEG];  /* (H, K_k), dtype */
+  const float* proj_b[EGOT2_MAX_SEG]; /* (H) */
+  const float* ln_g;                  /* (H) shared self.ln */
+  const float* ln_b;
+  const float* tok_table;             /* (T, H): added after the LN */
+} egot2_embed_in;
+
+typedef struct {
+  void* z;                            /* (B,T,H) dtype: projected (+feature-dropped) features, LN input  [saved] */
+  float* stat;                        /* (B*T, 2): mean, rstd                                              [saved] */
+  void* x;                            /* (B,T,H) dtype: tokens handed to the encoder */
+} egot2_embed_out;
+
+typedef struct {
+  float* proj_w[EGOT2_MAX_SEG];
+  float* proj_b[EGOT2_MAX_SEG];
+  float* ln_g;
+  float* ln_b;
+  float* tok_table;                   /* (T,H) */
+  float* dfeat[EGOT2_MAX_SEG];        /* optional (B,D_k,K_k) fp32 gradient w.r.t. a feature stream; NULL = frozen */
+} egot2_embed_grads;
+
+size_t egot2_embed_workspace_bytes(const egot2_embed_desc* d, int backward);
+int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* in, const egot2_embed_out* out,
+                    void* workspace, size_t ws_bytes, void* stream);
+int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* in, const egot2_embed_out* saved,
+                    const void* dx /* (B,T,H) dtype; clobbered */, const egot2_embed_grads* g,
+                    void* workspace, size_t ws_bytes, void* stream);
+
+/* HHI: tok_table[off_k + d, :] = task_embed[task_id_k, :] + pe[d, :]  (d restarts per task; `pe` is the module's
+ * registered sinusoid buffer pos_embed.pe viewed as (pe_len,H); seg_* are HOST arrays) */
+int egot2_hhi_tok_table_fwd(const float* task_embed /* (n_task,H) */, const float* pe, int32_t pe_len, int32_t n_seg,
+                            const int32_t* seg_tokens_host, const int32_t* seg_task_id_host, int32_t H,
+                            float* tok_table /* (T,H) */, void* stream);
+int egot2_hhi_tok_table_bwd(const float* d_tok_table, int32_t n_seg, const int32_t* seg_tokens_host,
+                            const int32_t* seg_task_id_host, int32_t H, float* d_task_embed /* += */, void* stream);
+
+/* ------------------------------------------------------------------ encoder layer */
+typedef struct {
+  int32_t dtype;
+  int32_t B, T, H, FF, heads;
+  int32_t training;
+  int32_t layer_index;                /* decorrelates dropout masks between layers */
+  float p_drop;                       /* the layer's `dropout=`: attention probs, dropout1, dropout, dropout2 */
+  float ln_eps;
+  uint64_t seed;
+} egot2_layer_desc;
+
+typedef struct {
+  const void* in_proj_w;              /* (3H,H) dtype */
+  const void* out_proj_w;             /* (H,H)  */
+  const void* lin1_w;                 /* (FF,H) */
+  const void* lin2_w;                 /* (H,FF) */
+  const float *in_proj_b, *out_proj_b, *lin1_b, *lin2_b;
+  const float *norm1_g, *norm1_b, *norm2_g, *norm2_b;
+} egot2_layer_params;
+
+typedef struct {
+  float *in_proj_w, *out_proj_w, *lin1_w, *lin2_w;
+  float *in_proj_b, *out_proj_b, *lin1_b, *lin2_b;
+  float *norm1_g, *norm1_b, *norm2_g, *norm2_b;
+} egot2_layer_grads;
+
+typedef struct {                      /* activations kept for backward; caller-allocated */
+  void* qkv;                          /* (B*T, 3H) dtype */
+  void* attn;                         /* (B*T, H)  dtype: concat of per-head P.V, input of out_proj */
+  float* lse;                         /* (B, heads, T): log-sum-exp of the scaled scores */
+  void* y1;                           /* (B*T, H) dtype: x + dropout1(attn out), LN1 input */
+  float* stat1;                       /* (B*T, 2) */
+  void* x1;                           /* (B*T, H) dtype: LN1 output */
+  void* hid;                          /* (B*T, FF) dtype: dropout(relu(linear1(x1))) */
+  void* y2;                           /* (B*T, H) dtype: x1 + dropout2(linear2(hid)), LN2 input */
+  float* stat2;                       /* (B*T, 2) */
+} egot2_layer_saved;
+
+size_t egot2_encoder_layer_workspace_bytes(const egot2_layer_desc* d, int backward);
+int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_layer_params* p, const void* x_in,
+                            void* x_out, const egot2_layer_saved* s, void* workspace, size_t ws_bytes,
+                            void* stream);
+/* dx_out is clobbered; dx_in may alias dx_out. */
+int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_layer_params* p, const void* x_in,
+                            const egot2_layer_saved* s, void* dx_out, void* dx_in,
+                            const egot2_layer_grads* g, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ head + loss */
+typedef struct {
+  int32_t dtype;
+  int32_t B, T, H;                    /* rows are mean-pooled over T when pool != 0 */
+  int32_t pool;                       /* 1: rows = B clips (mean over T tokens); 0: rows = B*T tokens (ASD) */
+  int32_t row_tokens;                 /* pool==0: use only the first row_tokens tokens of each clip */
+  int32_t use_ln;                     /* LayerNorm before the Linear (linear_head.0) */
+  int32_t n_out;                      /* width of the Linear: 2 | 16 | Z*593 */
+  int32_t loss;                       /* EGOT2_LOSS_* */
+  int32_t n_groups;                   /* CE_GROUPS: class groups inside each sub-row (verbs, nouns) */
+  int32_t group_size[EGOT2_MAX_GROUPS];
+  int32_t sub_rows;                   /* CE_GROUPS: Z sub-rows per row (n_out = sub_rows * sum(group_size)) */
+  int32_t training;
+  float p_head;                       /* dropout on the pooled vector (LTA MultiTaskHead) */
+  float ln_eps;
+  uint64_t seed;
+} egot2_head_desc;
+
+typedef struct {
+  const void* x;                      /* (B,T,H) dtype encoder output */
+  const float *ln_g, *ln_b;           /* (H) or NULL */
+  const void* w;                      /* (n_out,H) dtype */
+  const float* b;                     /* (n_out) */
+  const int64_t* labels;              /* CE: (rows); BCE: (rows) index of the 1 in the one-hot; CE_GROUPS: (rows, sub_rows, n_groups) */
+  const float* class_weight;          /* CE: (n_out) or NULL */
+} egot2_head_in;
+
+typedef struct {
+  float* pooled;                      /* (rows,H) fp32: mean over tokens (or gathered tokens)  [saved] */
+  float* stat;                        /* (rows,2)                                             [saved] */
+  void* g;                            /* (rows,H) dtype: LN'd (+dropped) vector fed to the Linear [saved] */
+  float* logits;                      /* (rows,n_out) fp32 */
+  float* loss;                        /* (2): [0] the scalar loss, [1] its normaliser (sum of class weights | rows) */
+  int32_t* argmax;                    /* (rows*sub_rows*max(1,n_groups)) index of the max logit (per group) or NULL */
+  float* row_loss;                    /* (rows,2) scratch: weighted nll, weight */
+} egot2_head_out;
+
+typedef struct {
+  float *ln_g, *ln_b, *w, *b;
+} egot2_head_grads;
+
+int egot2_head_rows(const egot2_head_desc* d);
+int egot2_head_loss_fwd(const egot2_head_desc* d, const egot2_head_in* in, const egot2_head_out* out, void* stream);
+/* If d->loss != NONE, dlogits is derived from the loss scaled by *dloss_scale_host (usually 1.0f) and
+ * written to out->logits' gradient buffer `dlogits`; otherwise the caller provides dlogits. */
+int egot2_head_loss_bwd(const egot2_head_desc* d, const egot2_head_in* in, const egot2_head_out* saved,
+                        float* dlogits /* (rows,n_out) fp32 in/out */, float dloss_scale,
+                        void* dx /* (B,T,H) dtype, written (=, not +=) */, const egot2_head_grads* g,
+                        void* workspace, size_t ws_bytes, void* stream);
+size_t egot2_head_workspace_bytes(const egot2_head_desc* d);
+
+/* ------------------------------------------------------------------ utilities */
+/* AdaptiveAvgPool3d of raw SlowFast maps: in (B,C,Tin,h,w) -> out (B,Tout,C), mean over h,w and Tin/Tout frames. */
+int egot2_slowfast_pool_fwd(const void* in, int32_t in_dtype, int32_t B, int32_t C, int32_t Tin, int32_t hw,
+                            int32_t Tout, void* out, int32_t out_dtype, void* stream);
+/* fp32 -> bf16 shadow copy of (part of) the parameter arena. */
+int egot2_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
+int egot2_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);
+/* torch.optim.Adam (no amsgrad) over a flat arena; grad_scale multiplies the gradient first (1/world for DP mean). */
+int egot2_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                    void* stream);
+
+/* ------------------------------------------------------------------ op-level entry points (diagnostics / unit tests) */
+/* C[M,N] = op(A)[M,K] . op(B)[K,N] (+bias[N]) ; A stored (M,K) or, if trans_a, (K,M); B stored (K,N) or, if
+ * trans_b, (N,K) [nn.Linear weight layout]; relu optional; C fp32 or bf16 per `dtype` (A,B in `dtype`). */
+int egot2_gemm(int32_t dtype, int32_t M, int32_t N, int32_t K, const void* A, int32_t trans_a, const void* B,
+               int32_t trans_b, const float* bias, int32_t relu, void* C, int32_t c_is_f32, int32_t accumulate,
+               void* stream);
+int egot2_layernorm_fwd(int32_t dtype, int32_t rows, int32_t H, const void* x, const float* g, const float* b,
+                        float eps, void* y, float* stat, void* stream);
+/* self-attention over (B,T,3H) packed q|k|v -> (B,T,H); lse (B,heads,T). */
+int egot2_attention_fwd(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t heads, const void* qkv, void* out,
+                        float* lse, float p_drop, int32_t training, uint64_t seed, void* stream);
+int egot2_attention_bwd(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t heads, const void* qkv,
+                        const void* out, const float* lse, const void* dout, void* dqkv, float p_drop,
+                        int32_t training, uint64_t seed, void* workspace, size_t ws_bytes, void* stream);
+
+size_t egot2_attention_bwd_workspace_bytes(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t heads);
+/* pooled[b,:] = mean_t x[b,t,:] (pool=1) or the first row_tokens tokens of every clip (pool=0; the ASD-of-interest
+ * translator returns encoder tokens, HHI/models/asd/model_taskspecific.py:156-157); pooled is fp32. */
+int egot2_pool_fwd(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t pool, int32_t row_tokens, const void* x,
+                   float* pooled, void* stream);
+int egot2_pool_bwd(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t pool, int32_t row_tokens,
+                   const float* dpooled, void* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOT2_H_ */

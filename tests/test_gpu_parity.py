@@ -1,0 +1,171 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed goldens
+of the real reference.  fp32 mode: 1e-3 of the output range (we assert far tighter) and
+argmax bit-exact; bf16 mode: 2e-2 (north_star tolerances)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from egot2_b200 import _lib as L
+from oracle.cases import CASES, case_inputs, grad_digest, oracle_forward_loss
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+# tolerances relative to the reference tensor's absmax
+TOL = {"fp32": dict(out=2e-4, loss=2e-4, grad=2e-3), "bf16": dict(out=2e-2, loss=2e-2, grad=6e-2)}
+
+
+def _loss_kind(case):
+    sp = case.spec
+    if sp.family == "hhi_ttm":
+        return L.LOSS_CE, torch.tensor([0.266, 0.734])
+    if sp.family == "hoi_pnr":
+        return (L.LOSS_BCE_SIGMOID if sp.n_out == 16 else L.LOSS_CE), None
+    if sp.family == "hoi_lta":
+        return L.LOSS_CE_GROUPS, None
+    return L.LOSS_NONE, None
+
+
+def _engine_feats(case, eng, feats, extra, dtype):
+    from egot2_b200 import engine as E
+    dev = eng.device
+    out = []
+    for s in case.spec.segments:
+        if case.raw_slowfast and s.name in ("slow", "fast"):
+            raw = extra["slow5" if s.name == "slow" else "fast5"].to(dev)
+            B, Cc, Tin, h, w = raw.shape
+            o = torch.empty((B, 8, Cc), device=dev, dtype=torch.float32)
+            L.call("egot2_slowfast_pool_fwd", raw.data_ptr(), L.F32, B, Cc, Tin, h * w, 8, o.data_ptr(), L.F32,
+                   E._stream())
+            out.append(o if dtype == "fp32" else o.to(torch.bfloat16))
+        else:
+            f = feats[s.name].to(dev)
+            out.append(f if dtype == "fp32" else f.to(torch.bfloat16))
+    return out
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_engine_matches_oracle_and_golden(name, dtype):
+    from egot2_b200.engine import TranslatorEngine
+    from oracle import translator_oracle as O
+    case = CASES[name]
+    sp = case.spec
+    tol = TOL[dtype]
+    sd, feats, labels, extra = case_inputs(case)
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+
+    eng = TranslatorEngine(sp, "cuda:0", dtype)
+    eng.arena.load_state_dict(sd)
+    if sp.embed == "task_sinusoid":
+        eng.set_sinusoid(O.sinusoid_table(1000, sp.hidden))
+    loss_kind, cw = _loss_kind(case)
+    gfeats = _engine_feats(case, eng, feats, extra, dtype)
+    act = eng.forward(gfeats, training=False, labels=labels, loss=loss_kind, class_weight=cw)
+    out = act.t["out"].float().cpu()
+
+    # oracle (CPU, fp32) on the same inputs
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o_out, o_loss = oracle_forward_loss(case, P, feats, labels, extra)
+    ref_out = torch.from_numpy(gold["output"]).reshape(o_out.shape)
+    scale = float(ref_out.abs().max())
+    assert float((out.reshape(o_out.shape) - o_out.detach()).abs().max()) <= tol["out"] * scale, "vs oracle"
+    assert float((out.reshape(o_out.shape) - ref_out).abs().max()) <= tol["out"] * scale, "vs reference golden"
+    if dtype == "fp32" and o_out.dim() == 2 and o_out.shape[1] in (2, 16):
+        assert torch.equal(out.argmax(-1), ref_out.argmax(-1)), "argmax / keyframe index must be bit-exact in fp32"
+        if loss_kind != L.LOSS_NONE:
+            assert torch.equal(act.t["argmax"].cpu().long(), ref_out.argmax(-1))
+
+    names = [k[len("grad/"):] for k in gold.files if k.startswith("grad/")]
+    if loss_kind != L.LOSS_NONE:
+        loss = float(act.t["loss"][0].cpu())
+        assert abs(loss - float(gold["loss"])) <= tol["loss"] * abs(float(gold["loss"])) + 1e-6
+        grad, _ = eng.backward(act)
+    else:  # ASD: the loss (lossAV) lives outside the translator; feed d(loss)/d(out) computed by the oracle
+        o2 = out.clone().requires_grad_(True)
+        l2 = O.loss_av(extra, o2, labels)[0]
+        (dout,) = torch.autograd.grad(l2, o2)
+        grad, _ = eng.backward(act, dout=dout.cuda())
+    o_grads = torch.autograd.grad(o_loss, [P[k] for k in names], allow_unused=True)
+    for k, g_ref in zip(names, o_grads):
+        g = eng.arena.view(k, grad).float().cpu()
+        if g_ref is None:
+            assert float(g.abs().max()) == 0.0, k
+            continue
+        gscale = float(g_ref.abs().max()) + 1e-12
+        err = float((g - g_ref).abs().max()) / gscale
+        assert err <= tol["grad"], f"{k}: rel err {err:.3e}"
+        dg = grad_digest(g)
+        ref_d = torch.from_numpy(gold["grad/" + k])
+        assert abs(float(dg[1] - ref_d[1])) <= 2 * tol["grad"] * float(ref_d[1]) + 1e-7, f"{k}: l2 norm vs golden"
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_gemm_orientations(dtype, ta, tb):
+    from egot2_b200 import engine as E
+    torch.manual_seed(0)
+    M, N, K = 200, 136, 264
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    A = torch.randn(M, K, device="cuda").to(tdt)
+    B = torch.randn(K, N, device="cuda").to(tdt)
+    bias = torch.randn(N, device="cuda")
+    As = A.t().contiguous() if ta else A.contiguous()
+    Bs = B.t().contiguous() if tb else B.contiguous()
+    Cout = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    L.call("egot2_gemm", E._dt(dtype), M, N, K, As.data_ptr(), ta, Bs.data_ptr(), tb, bias.data_ptr(), 1,
+           Cout.data_ptr(), 1, 0, E._stream())
+    ref = torch.relu(A.double() @ B.double() + bias.double()).float()
+    tol = 1e-5 if dtype == "fp32" else 1e-5   # bf16 inputs are exact in fp32; accumulation is fp32 either way
+    assert float((Cout - ref).abs().max()) <= tol * float(ref.abs().max()) + 1e-4
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("T,H,heads", [(7, 128, 4), (90, 128, 4), (48, 128, 8), (150, 256, 4), (8, 1024, 8), (453, 64, 2)])
+def test_attention_fwd_bwd(dtype, T, H, heads):
+    from egot2_b200 import engine as E
+    torch.manual_seed(1)
+    B = 3
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    qkv = (torch.randn(B, T, 3 * H, device="cuda") * 0.7).to(tdt)
+    dout = torch.randn(B, T, H, device="cuda").to(tdt)
+    out = torch.empty(B, T, H, device="cuda", dtype=tdt)
+    lse = torch.empty(B, heads, T, device="cuda", dtype=torch.float32)
+    dqkv = torch.empty_like(qkv)
+    L.call("egot2_attention_fwd", E._dt(dtype), B, T, H, heads, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), 0.0, 0, 0,
+           E._stream())
+    nws = L.load().egot2_attention_bwd_workspace_bytes(E._dt(dtype), B, T, H, heads)
+    ws = torch.empty(nws, device="cuda", dtype=torch.uint8)
+    L.call("egot2_attention_bwd", E._dt(dtype), B, T, H, heads, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(),
+           dout.data_ptr(), dqkv.data_ptr(), 0.0, 0, 0, ws.data_ptr(), nws, E._stream())
+    q = qkv.double().requires_grad_(True)
+    dh = H // heads
+    qq, kk, vv = q.split(H, dim=-1)
+    sh = lambda x: x.reshape(B, T, heads, dh).transpose(1, 2)
+    s = (sh(qq) / dh ** 0.5) @ sh(kk).transpose(-1, -2)
+    ref = (torch.softmax(s, -1) @ sh(vv)).transpose(1, 2).reshape(B, T, H)
+    (gref,) = torch.autograd.grad(ref, q, dout.double())
+    t_out, t_g = (1e-4, 1e-3) if dtype == "fp32" else (1e-2, 2e-2)
+    assert float((out.double() - ref).abs().max()) <= t_out * float(ref.abs().max())
+    assert float((lse.double() - torch.logsumexp(s, -1)).abs().max()) <= 1e-3
+    assert float((dqkv.double() - gref).abs().max()) <= t_g * float(gref.abs().max())
+
+
+def test_adam_matches_torch():
+    from egot2_b200 import engine as E
+    torch.manual_seed(2)
+    n = 10007
+    p = torch.randn(n, device="cuda")
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=5e-4, weight_decay=0.01)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda")
+        ref.grad = g.clone()
+        opt.step()
+        L.call("egot2_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 5e-4, 0.9, 0.999, 1e-8,
+               0.01, step, 1.0, E._stream())
+    assert float((p - ref.detach()).abs().max()) < 1e-6
