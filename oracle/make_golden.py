@@ -105,6 +105,13 @@ def main():
     torch.set_num_threads(8)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     hhi, hoi = rs.load_hhi(), rs.load_hoi()
+    ref_keys = {}
+    for name, case in CASES.items():
+        m0 = build_reference(case, hhi, hoi)
+        ref_keys[name] = {k: list(v.shape) for k, v in m0.state_dict().items()}
+    import json
+    with open(os.path.join(GOLDEN_DIR, "state_dict_keys.json"), "w") as f:
+        json.dump(ref_keys, f, indent=0, sort_keys=True)
     for name, case in CASES.items():
         sd, feats, labels, extra = case_inputs(case)
         m = build_reference(case, hhi, hoi)

@@ -1,0 +1,239 @@
+"""The drop-in nn.Module classes: state_dict / ctor parity with the reference (CPU) and forward +
+autograd-backward parity with the oracle through the public module API (GPU)."""
+import json
+import os
+import warnings
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from egot2_b200 import hhi, hoi
+from egot2_b200.modules import PrecomputedFeatures
+from oracle.cases import CASES, case_inputs, oracle_forward_loss
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+class CfgNode(dict):
+    __getattr__ = lambda s, k: s[k]
+    __setattr__ = dict.__setitem__
+
+
+class _TalkNetFeatures(torch.nn.Module):
+    """talkNetModel stand-in speaking the 4-call protocol the translator uses; carries (N,D,256) features."""
+    def forward_audio_frontend(self, a): return a
+    def forward_visual_frontend(self, v): return v
+    def forward_cross_attention(self, a, v): return a, v
+    def forward_audio_visual_backend(self, a, v): return v["asd"].reshape(-1, v["asd"].shape[-1])
+
+
+class _Feats(dict):
+    @property
+    def shape(self):
+        n, d, _ = self["asd"].shape
+        return (n, d, 1, 1)
+
+
+def build_ours(case, backbones=True):
+    sp = case.spec
+    if sp.family in ("hhi_ttm", "hhi_asd"):
+        args = SimpleNamespace(lam_checkpoint="x", ttm_checkpoint="x", asd_checkpoint="x", nofreeze=False,
+                               hidden_dim=sp.hidden, num_heads=sp.heads, dropout=sp.p_layer, num_layers=sp.layers)
+        bb = {"lam_model": PrecomputedFeatures("lam"), "ttm_model": PrecomputedFeatures("ttm")}
+        if len(sp.segments) == 3:
+            bb["asd_model"] = _TalkNetFeatures()
+        if sp.family == "hhi_asd":
+            return hhi.asd.TaskFusionMFTransformer3Task(args, backbones=bb)
+        cls = hhi.ttm.TaskFusionMFTransformer3Task if len(sp.segments) == 3 else hhi.ttm.TaskFusionMFTransformer2Task
+        return cls(args, backbones=bb)
+    if sp.family == "hoi_pnr":
+        cfg = CfgNode(DATA=CfgNode(TASK="keyframe_localization_2loader" if sp.n_out == 16 else "state_change"),
+                      MODEL=CfgNode(TRANSLATION_INPUT_FEATURES=sp.hidden, TRANSLATION_LAYERS=sp.layers,
+                                    FEAT_DROPOUT_RATE=sp.p_feat, TRANSFORMER_DROPOUT_RATE=sp.p_layer))
+        bb = {"pnr_model": PrecomputedFeatures("pnr"), "oscc_model": PrecomputedFeatures("oscc"),
+              "recognition_model": PrecomputedFeatures("slowfast")}
+        return hoi.pnr.TaskFusionMFTransformer3TaskDropout(cfg, backbones=bb)
+    if sp.family == "hoi_lta":
+        cfg = CfgNode(MODEL=CfgNode(TRANSLATION_INPUT_FEATURES=sp.hidden, TRANSLATION_LAYERS=sp.layers,
+                                    TRANSLATION_HEADS=sp.heads, TRANSLATION_DROPOUT=sp.p_layer,
+                                    NUM_CLASSES=list(sp.head_groups), DROPOUT_RATE=sp.p_head, HEAD_ACT="softmax"),
+                      FORECASTING=CfgNode(NUM_INPUT_CLIPS=sp.segments[0].tokens, NUM_ACTIONS_TO_PREDICT=sp.n_heads_out),
+                      TEST=CfgNode(NO_ACT=True))   # raw logits in eval mode (parity); see the softmax test
+        return hoi.lta.TaskFusionMFTransformerLTA4Task(cfg, backbones={})
+    raise ValueError(sp.family)
+
+
+def run_ours(case, m, feats, extra, dev):
+    sp = case.spec
+    f = {k: v.to(dev) for k, v in feats.items()}
+    if sp.family == "hhi_ttm" and len(sp.segments) == 2:
+        return m(_Feats(f), None)
+    if sp.family in ("hhi_ttm", "hhi_asd"):
+        v = _Feats(f)
+        return m(v, v, None, None)
+    if sp.family == "hoi_pnr":
+        if case.raw_slowfast:
+            sf = [extra["slow5"].to(dev), extra["fast5"].to(dev)]
+        else:
+            sf = [f["slow"], f["fast"]]
+        out = m([{"pnr": f["pnr"], "oscc": f["oscc"]}], {"slowfast": sf})
+        return out.squeeze(1) if sp.n_out == 16 else out.squeeze(2)
+    if sp.family == "hoi_lta":
+        return torch.cat(m.translate(f["pnr"], f["oscc"], f["action"], f["lta"]), dim=-1)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_state_dict_keys_and_shapes_match_reference(name):
+    """Released egot2 checkpoints must load: identical keys/shapes (incl. pos_embed.pe and the aliased ln)."""
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = build_ours(CASES[name])
+    ours = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert ours == ref
+
+
+def test_container_forward_is_poisoned():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = build_ours(CASES["hhi2_h128_l1"])
+    with pytest.raises(RuntimeError, match="libegot2"):
+        m.transformer_encoder(torch.zeros(3, 1, 128))
+    with pytest.raises(RuntimeError, match="libegot2"):
+        m.proj_lam(torch.zeros(1, 256))
+
+
+@pytest.mark.requires_reference
+@pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_l1", "hhi_asd_h128_l1", "hoi_pnr_h128_l6", "hoi_lta_h512_l4"])
+def test_same_seed_same_init_as_reference(name):
+    """ctor parity: under the same torch seed our module draws exactly the reference's initial weights."""
+    from oracle import ref_shims as rs
+    from oracle.make_golden import build_reference
+    warnings.filterwarnings("ignore")
+    hhi_ref, hoi_ref = rs.load_hhi(), rs.load_hoi()
+    case = CASES[name]
+    torch.manual_seed(123)
+    ref = build_reference(case, hhi_ref, hoi_ref)
+    torch.manual_seed(123)
+    ours = build_ours(case)
+    sd_ref, sd = ref.state_dict(), ours.state_dict()
+    assert sd.keys() == sd_ref.keys()
+    for k in sd:
+        assert torch.equal(sd[k], sd_ref[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_d30", "hhi_asd_h128_l1", "hoi_pnr_h128_l6",
+                                  "hoi_pnr_raw_maps", "hoi_lta_h512_l4"])
+def test_module_forward_backward_vs_oracle(name, dtype):
+    from oracle import translator_oracle as O
+    warnings.filterwarnings("ignore")
+    case = CASES[name]
+    sp = case.spec
+    dev = torch.device("cuda:0")
+    sd, feats, labels, extra = case_inputs(case)
+    m = build_ours(case)
+    m.load_state_dict(sd, strict=False)
+    m.to(dev).set_compute_dtype(dtype)
+    m.eval()
+    out = run_ours(case, m, feats, extra, dev)
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o_out, o_loss = oracle_forward_loss(case, P, feats, labels, extra)
+    tol_o, tol_g = (2e-4, 2e-3) if dtype == "fp32" else (2e-2, 5e-2)
+    scale = float(o_out.abs().max())
+    assert out.shape == tuple(o_out.reshape(out.shape).shape)
+    assert float((out.float().cpu() - o_out.detach().reshape(out.shape)).abs().max()) <= tol_o * scale
+
+    # loss with the reference task's own torch loss on OUR output -> loss.backward() -> .grad on our parameters
+    lab = labels.to(dev)
+    if sp.family == "hhi_ttm":
+        loss = torch.nn.CrossEntropyLoss(weight=torch.tensor([0.266, 0.734], device=dev))(out, lab)
+    elif sp.family == "hhi_asd":
+        lav = hhi.lossAV(dim=sp.hidden).to(dev)
+        lav.load_state_dict({"criterion.weight": torch.tensor([1.0, 4.0]), "FC.weight": extra["FC.weight"],
+                             "FC.bias": extra["FC.bias"]})
+        loss, score, label, correct = lav(out, lab)
+        o_l, o_score, o_label, o_correct = O.loss_av(extra, o_out.detach(), labels)
+        assert float((score.cpu() - o_score).abs().max()) < (1e-4 if dtype == "fp32" else 2e-2)
+    elif sp.family == "hoi_pnr":
+        loss = torch.nn.BCELoss()(torch.sigmoid(out), torch.nn.functional.one_hot(lab, 16).float())
+    else:
+        loss = O.lta_loss(out.view(out.shape[0], sp.n_heads_out, -1), lab, sp.head_groups)
+    assert abs(float(loss) - float(o_loss)) <= (2e-4 if dtype == "fp32" else 2e-2) * abs(float(o_loss)) + 1e-6
+    loss.backward()
+    names = list(sd.keys())
+    o_grads = torch.autograd.grad(o_loss, [P[k] for k in names], allow_unused=True)
+    for k, g_ref in zip(names, o_grads):
+        g = m.get_parameter(k).grad
+        assert g is not None, k
+        if g_ref is None:
+            continue
+        err = float((g.cpu() - g_ref).norm()) / (float(g_ref.norm()) + 1e-12)
+        assert err <= tol_g, f"{k}: rel L2 err {err:.3e}"
+
+
+@pytest.mark.gpu
+def test_lta_eval_applies_softmax_like_reference_head():
+    warnings.filterwarnings("ignore")
+    case = CASES["hoi_lta_h512_l4"]
+    dev = torch.device("cuda:0")
+    sd, feats, labels, extra = case_inputs(case)
+    m = build_ours(case)
+    m.load_state_dict(sd, strict=False)
+    m.to(dev).eval()
+    m.test_noact = False
+    f = {k: v.to(dev) for k, v in feats.items()}
+    verbs, nouns = m.translate(f["pnr"], f["oscc"], f["action"], f["lta"])
+    assert verbs.shape == (case.batch, 20, 115) and nouns.shape == (case.batch, 20, 478)
+    tot = verbs.sum(-1) + nouns.sum(-1)      # softmax over all 593 classes (head_helper.py:284-286)
+    assert float((tot - 1).abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_training_dropout_is_consistent_and_calibrated():
+    """Train mode: (i) same seed -> identical output, different seed -> different; (ii) the gradient matches a
+    finite-difference probe under the SAME masks (forward/backward regenerate identical masks); (iii) the
+    expectation over masks of the embed dropout keeps the token mean."""
+    from egot2_b200.engine import TranslatorEngine
+    from egot2_b200 import _lib as L
+    from oracle import translator_oracle as O
+    case = CASES["hhi3_h128_l1"]
+    sd, feats, labels, _ = case_inputs(case)
+    eng = TranslatorEngine(case.spec, "cuda:0", "fp32")
+    eng.arena.load_state_dict(sd)
+    eng.set_sinusoid(O.sinusoid_table(1000, case.spec.hidden))
+    gf = [feats[s.name].cuda() for s in case.spec.segments]
+    cw = torch.tensor([0.266, 0.734])
+    a1 = eng.forward(gf, training=True, seed=7, labels=labels, loss=L.LOSS_CE, class_weight=cw)
+    o1, l1 = a1.t["out"].clone(), float(a1.t["loss"][0])
+    a2 = eng.forward(gf, training=True, seed=7, labels=labels, loss=L.LOSS_CE, class_weight=cw)
+    assert torch.equal(o1, a2.t["out"])
+    a3 = eng.forward(gf, training=True, seed=8, labels=labels, loss=L.LOSS_CE, class_weight=cw)
+    assert not torch.equal(o1, a3.t["out"])
+    # (ii) directional derivative along a random direction of one weight matrix, same seed
+    grad, _ = eng.backward(a2)
+    name = "proj_ttm.weight"
+    g = eng.arena.view(name, grad).clone()
+    torch.manual_seed(0)
+    d = torch.randn_like(g)
+    d /= d.norm()
+    w = eng.arena.view(name)
+    w0 = w.clone()
+    eps = 1e-2
+    ls = []
+    for sgn in (+1, -1):
+        w.copy_(w0 + sgn * eps * d)
+        a = eng.forward(gf, training=True, seed=7, labels=labels, loss=L.LOSS_CE, class_weight=cw)
+        ls.append(float(a.t["loss"][0]))
+    w.copy_(w0)
+    fd = (ls[0] - ls[1]) / (2 * eps)
+    an = float((g * d).sum())
+    assert abs(fd - an) <= 0.05 * max(abs(an), abs(fd)) + 2e-4, (fd, an)
+    # (iii) keep-rate of the embed dropout (p=0.1): fraction of exact zeros in the token tensor
+    x0 = a2.t["x0"]
+    frac = float((x0 == 0).float().mean())
+    assert abs(frac - 0.1) < 0.02, frac
