@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the EgoT2 task-translation hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--dtype bf16|fp32]
+
+Metric (BASELINE.json): translator forward+backward clips/sec.  Default workload = BASELINE config 2:
+HHI TaskFusionMFTransformer3Task (LAM+TTM+ASD -> TTM) training, 1 layer, hidden 128, 4 heads, FFN 2048,
+256 clips per GPU x 3 tasks x 30 frames (T = 90 tokens), synthetic per-frame features (256-wide), seeded weights.
+One step = forward + fused weighted-CE loss + backward of every translator parameter + (N>1: one NCCL
+all-reduce of the flat gradient arena) + one fused Adam launch.
+
+Lines printed by rank 0 (ONE JSON line):
+  value     whole-job clips/s, features already resident in HBM (rotating pool larger than L2), CUDA-event timed,
+            max over ranks;
+  e2e       same step driven from pinned HOST buffers (H2D of features+labels and D2H of the loss inside the timed region);
+  roofline  the dominant kernel of the step timed alone with CUDA events on its launch stream;
+  cpu_baseline  the CPU oracle (torch restatement of the reference translator) on this box's host cores.
+`--impl reference` times that CPU implementation as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from egot2_b200 import specs, synth  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "hhi_ttm3_train_b256": dict(spec=lambda: specs.hhi_ttm_spec(128, 4, 1, 0.5, True), batch=256, seg_tokens=(30, 30, 30)),
+    # BASELINE.json configs[3] (per-frame features; bf16)
+    "hoi_pnr_train_b256": dict(spec=lambda: specs.hoi_pnr_spec(128, 6, 16, 0.5, 0.1), batch=256, seg_tokens=(16, 16, 8, 8)),
+    # BASELINE.json configs[4]
+    "hoi_lta_train_b512": dict(spec=lambda: specs.hoi_lta_spec(512, 4, 8, 0.5), batch=512, seg_tokens=(2, 2, 2, 2)),
+}
+L2_BYTES = 126 * 2 ** 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_oracle_step_fn(spec, batch, seg_tokens, seed=0):
+    """fwd (train mode, dropout on) + loss + backward of the CPU oracle on `batch` clips; returns a closure."""
+    from oracle import translator_oracle as O
+    sd = synth.make_state_dict(spec, seed)
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    feats = synth.make_features(spec, batch, seg_tokens, seed)
+    labels = synth.make_labels(spec, batch, seg_tokens, seed)
+    cw = torch.tensor([0.266, 0.734])
+
+    def step():
+        for p in P.values():
+            p.grad = None
+        if spec.family == "hhi_ttm":
+            out = O.hhi_ttm_forward(P, feats, spec.heads, spec.p_layer, True)
+            loss = O.ce_loss(out, labels, cw)
+        elif spec.family == "hoi_pnr":
+            out = O.hoi_pnr_forward(P, feats["pnr"], feats["oscc"], feats["slow"], feats["fast"], spec.heads,
+                                    spec.p_feat, spec.p_layer, True)
+            loss = O.bce_sigmoid_loss(out, torch.nn.functional.one_hot(labels, 16).float())
+        else:
+            out = O.hoi_lta_forward(P, feats["pnr"], feats["oscc"], feats["action"], feats["lta"], spec.heads,
+                                    spec.p_layer, spec.p_head, True)
+            loss = O.lta_loss(out, labels, spec.head_groups)
+        loss.backward()
+        return float(loss)
+    return step
+
+
+def time_cpu(spec, batch, seg_tokens, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_oracle_step_fn(spec, batch, seg_tokens)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference(args, wl, spec):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = min(wl["batch"], 256)
+    steps, warm = max(1, args.steps), max(1, min(args.warmup, 2))
+    # bound the run: ~2 s per 256-clip step on 8 cores -> cap the number of timed steps
+    steps = min(steps, 10)
+    cps, sec = time_cpu(spec, sample_batch, wl["seg_tokens"], steps, warm)
+    cores = torch.get_num_threads()
+    sample = f"{steps} steps x {sample_batch} clips (fwd+loss+bwd, dropout on) of the CPU oracle, {cores} threads"
+    line = {"impl": "reference", "metric": "translator fwd+bwd clips/sec", "value": cps, "unit": "clips/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "clips_per_step": sample_batch, "tokens_per_clip": sum(wl["seg_tokens"])},
+            "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hhi_ttm3_train_b256", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's)")
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    spec = wl["spec"]()
+    if args.impl == "reference":
+        return run_reference(args, wl, spec)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    from egot2_b200 import _lib as L
+    from egot2_b200.trainer import TranslatorTrainer
+
+    B, seg = wl["batch"], wl["seg_tokens"]
+    tr = TranslatorTrainer(spec, dev, args.dtype, use_graphs=not args.no_graphs)
+    tr.load_state_dict(synth.make_state_dict(spec, 0))          # identical weights on every rank
+    fdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    feat_bytes = spec.feature_elems_per_clip(seg) * B * (2 if args.dtype == "bf16" else 4)
+    n_pool = max(3, -(-2 * L2_BYTES // feat_bytes))              # pool of distinct batches >= 2 x L2
+    n_pool = min(n_pool, 64)
+    pool = []
+    for i in range(n_pool):
+        f = synth.make_features(spec, B, seg, seed=1000 * rank + i, dtype=fdt)
+        pool.append(([f[s.name].to(dev) for s in spec.segments],
+                     synth.make_labels(spec, B, seg, seed=1000 * rank + i).to(dev)))
+    lib = L.load()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run_steps(n, start=0):
+        for i in range(n):
+            fe, la = pool[(start + i) % n_pool]
+            tr.train_step(fe, la, graph_key=(start + i) % n_pool)
+
+    # ---- device-resident throughput
+    run_steps(max(args.warmup, n_pool if tr.use_graphs else args.warmup))     # capture every pool graph first
+    barrier()
+    l0 = lib.egot2_launch_count()
+    tr.use_graphs, keep = False, tr.use_graphs
+    run_steps(1)                                                                # one eager step to count our launches
+    launches_per_step = lib.egot2_launch_count() - l0
+    tr.use_graphs = keep
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    run_steps(args.steps, start=1)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clock_info = clocks.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end from pinned host buffers (H2D + step + D2H of the loss inside the timed region)
+    host = []
+    for i in range(2):
+        f = synth.make_features(spec, B, seg, seed=5000 + 10 * rank + i, dtype=fdt)
+        host.append(([f[s.name].pin_memory() for s in spec.segments],
+                     synth.make_labels(spec, B, seg, seed=5000 + 10 * rank + i).pin_memory()))
+    e2e_steps = max(5, min(args.steps, 30))
+    for i in range(3):
+        tr.train_step_host(*host[i % 2], slot=i % 2)
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        tr.train_step_host(*host[i % 2], slot=i % 2)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(ms2.item()) * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0][0]) + host[0][1].numel() * 8
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (timed alone, CUDA events on its launch stream)
+    peaks = load_peaks()
+    roof = dominant_kernel_roofline(spec, B, seg, args.dtype, dev, peaks)
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
+    cpu = None
+    if world == 1 and not args.skip_cpu_baseline:
+        sample_b = min(B, 256)
+        cps, sec = time_cpu(spec, sample_b, seg, steps=5, warmup=1)
+        cpu = {"value": cps, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"5 steps x {sample_b} clips (fwd+loss+bwd, dropout on) of the CPU oracle"}
+
+    flops_step = spec.flops_per_clip(seg, backward=True) * B
+    line = {
+        "metric": "translator fwd+bwd clips/sec", "value": value, "unit": "clips/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "translator": spec.family, "hidden": spec.hidden, "layers": spec.layers,
+                   "heads": spec.heads, "ffn": spec.ffn, "clips_per_gpu": B, "tokens_per_clip": sum(seg),
+                   "step": "fwd + fused loss + bwd (all translator grads) + grad all-reduce (N>1) + fused Adam",
+                   "l2_policy": f"inputs rotate over a pool of {n_pool} batches = {n_pool * feat_bytes / 2**20:.0f} MiB "
+                                f"> 126 MiB L2; saved activations add more per step",
+                   "cuda_graphs": bool(tr.use_graphs), "parallelism": f"dp{world} (clips sharded, no data-path collective)"},
+        "model_tflops_per_s": flops_step * world * args.steps / (ms_total * 1e-3) / 1e12,
+        "clocks": clock_info,
+        "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": int(launches_per_step),
+        "roofline": roof,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def dominant_kernel_roofline(spec, B, seg, dtype, dev, peaks):
+    """Time the dominant kernel of the step — the FFN linear1 GEMM(+bias+ReLU), the largest single GEMM of the
+    layer — alone, through the op-level C-ABI entry point, on operands larger than L2."""
+    import ctypes as C
+    from egot2_b200 import _lib as L
+    from egot2_b200.engine import _dt, _stream
+    lib = L.load()
+    M, H, FF = B * sum(seg), spec.hidden, spec.ffn
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    es = 2 if dtype == "bf16" else 4
+    n_rot = max(2, -(-2 * L2_BYTES // (M * (H + FF) * es)))
+    xs = [torch.randn(M, H, device=dev).to(tdt) for _ in range(n_rot)]
+    outs = [torch.empty(M, FF, device=dev, dtype=tdt) for _ in range(n_rot)]
+    W = (torch.randn(FF, H, device=dev) / H ** 0.5).to(tdt)
+    bias = torch.zeros(FF, device=dev)
+    st = _stream()
+
+    def launch(i):
+        L.call("egot2_gemm", _dt(dtype), M, FF, H, xs[i % n_rot].data_ptr(), 0, W.data_ptr(), 1, bias.data_ptr(), 1,
+               outs[i % n_rot].data_ptr(), 0, 0, st)
+    for i in range(5):
+        launch(i)
+    torch.cuda.synchronize(dev)
+    iters = 40
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        launch(i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sec = e0.elapsed_time(e1) * 1e-3 / iters
+    flops = 2.0 * M * H * FF
+    bytes_alg = (M * H + FF * H + M * FF) * es
+    ai = flops / bytes_alg
+    ridge = peaks["bf16_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    if dtype == "bf16" and ai >= ridge:
+        bound, achieved, peak, unit = "tensor", flops / sec / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+    else:
+        bound, achieved, peak, unit = "hbm", bytes_alg / sec / 1e9, peaks["hbm_gbs"], "GB/s"
+    return {"kernel": "ffn.linear1 GEMM+bias+ReLU (M=%d,N=%d,K=%d) via egot2_gemm" % (M, FF, H), "bound": bound,
+            "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
+            "us_per_launch": sec * 1e6, "arith_intensity_flop_per_byte": ai, "peak_source": peaks["source"] + " (burst)",
+            "impl": lib.egot2_version().decode()}
+
+
+if __name__ == "__main__":
+    main()

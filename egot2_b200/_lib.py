@@ -85,6 +85,7 @@ SIGNATURES = {
     "egot2_version": (C.c_char_p, []),
     "egot2_last_error": (C.c_char_p, []),
     "egot2_sm_count": (C.c_int, []),
+    "egot2_launch_count": (C.c_uint64, []),
     "egot2_embed_workspace_bytes": (sz, [P(EmbedDesc), C.c_int]),
     "egot2_embed_fwd": (C.c_int, [P(EmbedDesc), P(EmbedIn), P(EmbedOut), vp, sz, vp]),
     "egot2_embed_bwd": (C.c_int, [P(EmbedDesc), P(EmbedIn), P(EmbedOut), vp, P(EmbedGrads), vp, sz, vp]),

@@ -9,6 +9,7 @@
 namespace egot2 {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -105,6 +106,7 @@ using namespace egot2;
 extern "C" const char* egot2_version(void) { return "egot2-b200 0.1 (sm_100a)"; }
 extern "C" const char* egot2_last_error(void) { return g_err; }
 extern "C" int egot2_sm_count(void) { return sm_count(); }
+extern "C" uint64_t egot2_launch_count(void) { return g_launch_count; }
 
 // =============================================================================== embed stage
 extern "C" size_t egot2_embed_workspace_bytes(const egot2_embed_desc* d, int backward) {

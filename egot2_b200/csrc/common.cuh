@@ -29,7 +29,13 @@ void set_error(const char* fmt, ...);
       return 2;                                                                              \
     }                                                                                        \
   } while (0)
-#define EGOT2_LAUNCH_CHECK() EGOT2_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here exactly once (also feeds egot2_launch_count())
+extern unsigned long long g_launch_count;
+#define EGOT2_LAUNCH_CHECK()              \
+  do {                                    \
+    ++::egot2::g_launch_count;            \
+    EGOT2_CUDA(cudaGetLastError());       \
+  } while (0)
 #define EGOT2_TRY(expr)      \
   do {                       \
     int rc__ = (expr);       \

@@ -1,0 +1,131 @@
+"""Fused training / inference steps over a TranslatorEngine: the public API the benchmark and
+the end-to-end path use.
+
+One training step = forward (fused loss) -> backward into the flat gradient arena ->
+[data-parallel: ONE NCCL all-reduce of that arena over NVLink] -> one fused Adam launch.
+Clips shard across ranks (each rank steps its own clips; no data-path collective), the only
+exchange is the translator-gradient all-reduce.  The forward+backward launch
+sequence is captured once per input batch into a CUDA graph (the step is launch-bound at the
+reference's batch sizes), replayed afterwards.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from .engine import Activations, TranslatorEngine
+from .specs import TranslatorSpec
+
+
+def default_loss(spec: TranslatorSpec):
+    """(loss kind, class weights) the reference task uses for this translator."""
+    if spec.family == "hhi_ttm":
+        return L.LOSS_CE, torch.tensor([0.266, 0.734])
+    if spec.family == "hoi_pnr":
+        return (L.LOSS_BCE_SIGMOID if spec.n_out == 16 else L.LOSS_CE), None
+    if spec.family == "hoi_lta":
+        return L.LOSS_CE_GROUPS, None
+    raise ValueError(f"{spec.family}: the loss lives outside the translator (use the nn.Module API)")
+
+
+class TranslatorTrainer:
+    def __init__(self, spec: TranslatorSpec, device, dtype: str = "bf16", lr: float = 5e-4, betas=(0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 0.0, process_group=None, use_graphs: bool = True,
+                 sinusoid: Optional[torch.Tensor] = None):
+        self.spec = spec
+        self.device = torch.device(device)
+        self.engine = TranslatorEngine(spec, self.device, dtype)
+        if spec.embed == "task_sinusoid":
+            if sinusoid is None:
+                from .hhi import PositionalEncoding
+                sinusoid = PositionalEncoding(spec.hidden).pe
+            self.engine.set_sinusoid(sinusoid)
+        self.loss_kind, cw = default_loss(spec)
+        self.class_weight = None if cw is None else cw.to(self.device)
+        self.hp = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.opt_state: Dict[str, torch.Tensor] = {}
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.use_graphs = use_graphs
+        self._graphs: Dict[int, tuple] = {}
+        self._h2d: Dict[int, List[torch.Tensor]] = {}
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+
+    # ------------------------------------------------------------------ parameters
+    def load_state_dict(self, sd):
+        self.engine.arena.load_state_dict(sd)
+
+    def state_dict(self):
+        return self.engine.arena.state_dict()
+
+    # ------------------------------------------------------------------ device-resident step
+    def _fwd_bwd(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, seed: int) -> Activations:
+        act = self.engine.forward(feats, training=True, seed=seed, labels=labels, loss=self.loss_kind,
+                                  class_weight=self.class_weight, persistent=True)
+        self.engine.backward(act)
+        return act
+
+    def train_step(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, graph_key: Optional[int] = None):
+        """One optimisation step on device-resident features.  Returns the (device) loss tensor.
+        graph_key: a stable id for this exact set of input buffers; its launch sequence is captured into a CUDA
+        graph on first use (dropout then reuses the captured seed — fine for benchmarking, for real training
+        leave graph_key=None)."""
+        self.step_count += 1
+        if graph_key is not None and self.use_graphs:
+            entry = self._graphs.get(graph_key)
+            if entry is None:
+                entry = self._capture(feats, labels, graph_key)
+            graph, act = entry
+            graph.replay()
+        else:
+            act = self._fwd_bwd(feats, labels, seed=self.step_count)
+        self._reduce_and_update()
+        return act.t["loss"][0]
+
+    def _capture(self, feats, labels, key):
+        labels = labels.to(self.device, torch.int64).contiguous()
+        # warm-up on a side stream (allocations, workspace sizing), then capture
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._fwd_bwd(feats, labels, seed=1 + key)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            act = self._fwd_bwd(feats, labels, seed=1 + key)
+        self._graphs[key] = (g, act)
+        return g, act
+
+    def _reduce_and_update(self):
+        eng = self.engine
+        if self.world > 1:
+            torch.distributed.all_reduce(eng.arena.grad, group=self.pg)     # ONE flat NCCL all-reduce (NVLink)
+        eng.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
+                      self.hp["weight_decay"], grad_scale=1.0 / self.world)
+
+    # ------------------------------------------------------------------ host-buffer (end-to-end) step
+    def train_step_host(self, host_feats: Sequence[torch.Tensor], host_labels: torch.Tensor, slot: int = 0) -> float:
+        """End-to-end step from pinned HOST buffers: H2D copy of the features + labels, the step, and a D2H read
+        of the loss.  Device staging buffers are double-buffered per `slot`."""
+        bufs = self._h2d.get(slot)
+        if bufs is None:
+            bufs = [torch.empty(f.shape, device=self.device, dtype=f.dtype) for f in host_feats]
+            bufs.append(torch.empty(host_labels.shape, device=self.device, dtype=torch.int64))
+            self._h2d[slot] = bufs
+        for b, f in zip(bufs[:-1], host_feats):
+            b.copy_(f, non_blocking=True)
+        bufs[-1].copy_(host_labels, non_blocking=True)
+        loss = self.train_step(bufs[:-1], bufs[-1], graph_key=-(slot + 1) if self.use_graphs else None)
+        return float(loss.item())
+
+    # ------------------------------------------------------------------ inference
+    @torch.no_grad()
+    def infer(self, feats: Sequence[torch.Tensor]) -> torch.Tensor:
+        act = self.engine.forward(feats, training=False, persistent=True)
+        return act.t["out"]

@@ -66,6 +66,8 @@ const char* egot2_version(void);
 const char* egot2_last_error(void);
 /* SM count of the current device (cached per device). */
 int egot2_sm_count(void);
+/* Number of kernels this library has launched in this process so far (all streams). */
+uint64_t egot2_launch_count(void);
 
 /* ------------------------------------------------------------------ embed stage */
 typedef struct {
