@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
             list(ex.map(lambda s: _compile(s, verbose), todo))
     if todo or not os.path.exists(LIB):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcuda"]
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

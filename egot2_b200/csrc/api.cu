@@ -503,6 +503,8 @@ extern "C" int egot2_gemm(int32_t dtype, int32_t M, int32_t N, int32_t K, const 
   return gemm(g, (cudaStream_t)stream);
 }
 
+extern "C" const char* egot2_gemm_last_impl(void) { return gemm_last_impl(); }
+
 extern "C" int egot2_attention_fwd(int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t heads, const void* qkv,
                                    void* out, float* lse, float p_drop, int32_t training, uint64_t seed, void* stream) {
   return attention_fwd(dtype, B, T, H, heads, qkv, out, lse, training ? p_drop : 0.f, site_key(seed, SITE_ATTN, 0),

@@ -1,5 +1,295 @@
-// gemm_sm100.cu — tcgen05/TMEM/TMA GEMM for bf16 operands (placeholder until the kernel lands).
+// gemm_sm100.cu — bf16 GEMM on the 5th-gen tensor cores: TMA -> 128B-swizzled smem -> tcgen05.mma -> TMEM
+// -> tcgen05.ld -> fused epilogue (bias / ReLU / ReLU-gate / dropout / residual / accumulate) -> HBM.
+//
+//   C[M,N] = epilogue( op(A)[M,K] . op(B)[K,N] ),  A,B bf16, accumulation fp32 in TMEM, C bf16 or fp32.
+//
+// One CTA owns one 128 x BN output tile (UMMA M=128, N=BN, K=16 per instruction, cta_group::1) and walks its
+// K range in 64-wide blocks through a 4-stage TMA/mbarrier ring.  Warp roles (192 threads):
+//   warp 0  TMA producer (one elected lane)       warp 1  TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-5  epilogue: each owns the TMEM lane quadrant (warp_id % 4), one accumulator row per thread
+// Operand orientation is handled by the descriptors, not by copies:
+//   K-major  (row-major, K contiguous; activations (M,K) / nn.Linear weights (N,K)): one TMA box {64 k, rows}
+//   MN-major (K rows, M|N contiguous; used by dX = dY.W and dW = dY^T.X):            boxes of {64 mn, 64 k}
+// gridDim.z > 1 = split-K for the weight-gradient GEMMs (K = every token of the batch): fp32 atomics into C.
 #include "ops.h"
+#include "sm100.cuh"
+
 namespace egot2 {
-int gemm_sm100(const GemmArgs& a, cudaStream_t st) { (void)a; (void)st; return -1; }
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // bf16 elements = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 192;
+
+struct EpiArgs {
+  int M, N;
+  void* C; int ldc; int c_rpg, c_gstride;
+  const float* bias; int relu;
+  const void* mask; int ldm; float mask_scale;
+  float p_drop; uint64_t drop_key;
+  const void* residual; int ldr;
+  int accumulate; int atomic;
+};
+
+__device__ __forceinline__ long long remap(int r, int rpg, int gstride) {
+  return rpg > 0 ? (long long)(r / rpg) * gstride + (r % rpg) : (long long)r;
+}
+
+template <int BN, bool A_MN, bool B_MN, typename TO>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const EpiArgs e,
+                  const int k_blocks_total, const int k_blocks_per_split) {
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024 B alignment
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + STAGES * A_BYTES;
+  const uint32_t bars = sB + STAGES * B_BYTES;                            // full[STAGES], empty[STAGES], tmem_full
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES;
+  const uint32_t tmem_slot = tmem_full + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_begin = blockIdx.z * k_blocks_per_split;
+  const int kb_end = min(k_blocks_total, kb_begin + k_blocks_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+        const int k = (kb_begin + i) * BK;
+        if (!A_MN) {
+          tma_load_2d(sA + s * A_BYTES, &tma_a, full0 + 8 * s, k, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + s * A_BYTES + j * 8192, &tma_a, full0 + 8 * s, m0 + 64 * j, k);
+        }
+        if (!B_MN) {
+          tma_load_2d(sB + s * B_BYTES, &tma_b, full0 + 8 * s, k, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + s * B_BYTES + j * 8192, &tma_b, full0 + 8 * s, n0 + 64 * j, k);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          // K-major: 16 k = 32 B inside the 128 B swizzle row; MN-major: 16 k = 16 rows of 128 B
+          const uint64_t ad = A_MN ? make_smem_desc_sw128(sA + s * A_BYTES + kk * 2048, 8192, 1024)
+                                   : make_smem_desc_sw128(sA + s * A_BYTES + kk * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_smem_desc_sw128(sB + s * B_BYTES + kk * 2048, 8192, 1024)
+                                   : make_smem_desc_sw128(sB + s * B_BYTES + kk * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);          // smem slot reusable once these MMAs retire
+      }
+      umma_commit(tmem_full);                 // accumulator complete
+    }
+  } else {
+    // ================================================================ epilogue (warps 2..5)
+    const int q = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const float inv_keep = e.p_drop > 0.f ? 1.f / (1.f - e.p_drop) : 1.f;
+    const bool row_ok = m < e.M;
+    const long long crow = row_ok ? remap(m, e.c_rpg, e.c_gstride) : 0;
+    TO* __restrict__ C = (TO*)e.C;
+    const bool first_split = blockIdx.z == 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (!row_ok || n0 + c0 >= e.N || nkb <= 0) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c0 + j;
+        float x = __uint_as_float(r[j]);
+        if (n < e.N) {
+          if (e.bias && first_split) x += __ldg(e.bias + n);
+          if (e.relu) x = fmaxf(x, 0.f);
+          if (e.mask) x = to_f32(((const TO*)e.mask)[(long long)m * e.ldm + n]) > 0.f ? x * e.mask_scale : 0.f;
+          if (e.p_drop > 0.f) x *= drop_scale(e.drop_key, (uint64_t)m * e.N + n, e.p_drop, inv_keep);
+          if (e.residual && first_split) x += to_f32(((const TO*)e.residual)[(long long)m * e.ldr + n]);
+        }
+        v[j] = x;
+      }
+      TO* dst = C + crow * e.ldc + n0 + c0;
+      const bool full = (n0 + c0 + 32 <= e.N);
+      if (e.accumulate) {
+        if constexpr (sizeof(TO) == 4) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + c0 + j < e.N) {
+              if (e.atomic) atomicAdd((float*)dst + j, v[j]);
+              else ((float*)dst)[j] += v[j];
+            }
+        }
+      } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        if constexpr (sizeof(TO) == 4) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>((float*)dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 o;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>((bf16*)dst + j) = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < e.N) dst[j] = from_f32<TO>(v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major (rows, inner) matrix with leading dimension ld (elements).
+int make_map(CUtensorMap* map, const void* base, int inner, int rows, int ld, int box_inner, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  EGOT2_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGOT2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) inner=%d rows=%d ld=%d", (int)r, inner, rows, ld);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, typename TO>
+int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
+  constexpr size_t smem = 1024 + STAGES * (BM * BK * 2 + BN * BK * 2) + 16 * STAGES + 64;
+  static bool attr_set = false;
+  auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, TO>;
+  if (!attr_set) {
+    EGOT2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  EpiArgs e;
+  e.M = a.M; e.N = a.N; e.C = a.C; e.ldc = a.ldc; e.c_rpg = a.c_rpg; e.c_gstride = a.c_gstride;
+  e.bias = a.bias; e.relu = a.relu; e.mask = a.mask; e.ldm = a.ldm; e.mask_scale = a.mask_scale;
+  e.p_drop = a.p_drop; e.drop_key = a.drop_key; e.residual = a.residual; e.ldr = a.ldr;
+  e.accumulate = a.accumulate; e.atomic = a.split_k > 1;
+  const int kb_total = (a.K + BK - 1) / BK;
+  int splits = a.split_k < 1 ? 1 : a.split_k;
+  if (splits > kb_total) splits = kb_total;
+  const int kb_per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + kb_per - 1) / kb_per;
+  e.atomic = splits > 1;
+  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, splits);
+  kern<<<grid, NTHREADS, smem, st>>>(ma, mb, e, kb_total, kb_per);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool A_MN, bool B_MN, typename TO>
+int pick_bn(const GemmArgs& a, int bn, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch<64, A_MN, B_MN, TO>(a, ma, mb, st);
+    case 128: return launch<128, A_MN, B_MN, TO>(a, ma, mb, st);
+    default: return launch<256, A_MN, B_MN, TO>(a, ma, mb, st);
+  }
+}
+
+template <typename TO>
+int pick_major(const GemmArgs& a, int bn, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
+  if (!a.trans_a && a.trans_b) return pick_bn<false, false, TO>(a, bn, ma, mb, st);
+  if (!a.trans_a && !a.trans_b) return pick_bn<false, true, TO>(a, bn, ma, mb, st);
+  if (a.trans_a && !a.trans_b) return pick_bn<true, true, TO>(a, bn, ma, mb, st);
+  return pick_bn<true, false, TO>(a, bn, ma, mb, st);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// returns -1 when this kernel does not take the problem (caller falls back to the CUDA-core GEMM)
+int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
+  if (a.in_dtype != EGOT2_BF16) return -1;
+  if (a.a_rpg > 0 || a.b_rpg > 0) return -1;                      // gathered operands: not yet on the TMA path
+  if (a.M < 1 || a.N < 32 || a.K < 16) return -1;                  // degenerate tiles (tiny heads) stay on CUDA cores
+  if (!aligned16(a.A) || !aligned16(a.B) || (a.lda % 8) || (a.ldb % 8)) return -1;
+  if (a.accumulate && a.out_dtype != EGOT2_F32) return -1;
+  if (a.split_k > 1 && (!a.accumulate || a.relu || a.mask || a.p_drop > 0.f)) return -1;
+  const int bn = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : ((a.N % 256 == 0 || a.N > 512) ? 256 : 128));
+  CUtensorMap ma, mb;
+  // A: K-major (M,K) -> box {64 k, 128 m};  MN-major (K,M) -> box {64 m, 64 k}
+  if (!a.trans_a) EGOT2_TRY(make_map(&ma, a.A, a.K, a.M, a.lda, BK, BM));
+  else EGOT2_TRY(make_map(&ma, a.A, a.M, a.K, a.lda, 64, BK));
+  // B: K-major (N,K) -> box {64 k, BN n};   MN-major (K,N) -> box {64 n, 64 k}
+  if (a.trans_b) EGOT2_TRY(make_map(&mb, a.B, a.K, a.N, a.ldb, BK, bn));
+  else EGOT2_TRY(make_map(&mb, a.B, a.N, a.K, a.ldb, 64, BK));
+  if (a.out_dtype == EGOT2_F32) return pick_major<float>(a, bn, ma, mb, st);
+  return pick_major<bf16>(a, bn, ma, mb, st);
+}
+
 }  // namespace egot2

@@ -241,6 +241,8 @@ int egot2_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
 int egot2_gemm(int32_t dtype, int32_t M, int32_t N, int32_t K, const void* A, int32_t trans_a, const void* B,
                int32_t trans_b, const float* bias, int32_t relu, void* C, int32_t c_is_f32, int32_t accumulate,
                void* stream);
+/* "tcgen05" | "simt": which GEMM implementation served the most recent GEMM of this thread (diagnostics). */
+const char* egot2_gemm_last_impl(void);
 int egot2_layernorm_fwd(int32_t dtype, int32_t rows, int32_t H, const void* x, const float* g, const float* b,
                         float eps, void* y, float* stat, void* stream);
 /* self-attention over (B,T,3H) packed q|k|v -> (B,T,H); lse (B,heads,T). */

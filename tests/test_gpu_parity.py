@@ -175,3 +175,39 @@ def test_adam_matches_torch():
         L.call("egot2_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 5e-4, 0.9, 0.999, 1e-8,
                0.01, step, 1.0, E._stream())
     assert float((p - ref.detach()).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb,acc", [
+    (23040, 2048, 128, 0, 1, 0),     # ffn.linear1 forward
+    (23040, 128, 2048, 0, 1, 0),     # ffn.linear2 forward (long K, 4-stage ring wraps)
+    (23040, 384, 128, 0, 1, 0),      # packed qkv projection
+    (23040, 2048, 128, 0, 0, 0),     # dhid = dy . W2      (B is MN-major)
+    (2048, 128, 23040, 1, 0, 1),     # dW1 = dhid^T . x1   (A and B MN-major, split-K atomics)
+    (128, 2048, 23040, 1, 0, 1),     # dW2 = dy^T . hid
+    (300, 136, 264, 0, 1, 0), (300, 136, 264, 0, 0, 0), (300, 136, 264, 1, 0, 1), (300, 136, 264, 1, 1, 0),
+])
+def test_tcgen05_gemm(M, N, K, ta, tb, acc):
+    """The bf16 GEMMs of the step must be served by the tcgen05/TMEM/TMA kernel and match an fp64 reference."""
+    from egot2_b200 import engine as E
+    torch.manual_seed(3)
+    A = (torch.randn(M, K, device="cuda") / K ** 0.25).to(torch.bfloat16)
+    B = (torch.randn(K, N, device="cuda") / K ** 0.25).to(torch.bfloat16)
+    As = A.t().contiguous() if ta else A.contiguous()
+    Bs = B.t().contiguous() if tb else B.contiguous()
+    bias = None if acc else torch.randn(N, device="cuda")
+    C0 = torch.randn(M, N, device="cuda") if acc else torch.zeros(M, N, device="cuda")
+    Cout = C0.clone()
+    L.call("egot2_gemm", L.BF16, M, N, K, As.data_ptr(), ta, Bs.data_ptr(), tb, None if acc else bias.data_ptr(), 0,
+           Cout.data_ptr(), 1, acc, E._stream())
+    torch.cuda.synchronize()
+    assert L.load().egot2_gemm_last_impl() == b"tcgen05"
+    ref = A.double() @ B.double() + (C0.double() if acc else bias.double())
+    err = float((Cout.double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-5, err
+    # bf16 output path
+    if not acc:
+        Cb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        L.call("egot2_gemm", L.BF16, M, N, K, As.data_ptr(), ta, Bs.data_ptr(), tb, bias.data_ptr(), 1, Cb.data_ptr(), 0, 0,
+               E._stream())
+        refb = torch.relu(A.double() @ B.double() + bias.double())
+        assert float((Cb.double() - refb).abs().max()) / float(refb.abs().max()) < 1e-2
