@@ -1,0 +1,368 @@
+// attention_mma.cu — short-sequence self-attention on tensor cores (bf16 mma.sync m16n8k16, fp32 softmax).
+//
+// One CTA per (clip, head).  The clip's whole token set for that head (Q, K, V, and in backward dO) is staged
+// ONCE into shared memory (rows padded by 8 bf16 -> conflict-free ldmatrix); each warp owns a 16-row tile and keeps
+// its full 16 x T score tile in registers, so there is no online-softmax rescaling, no T x T traffic, and no
+// cross-warp reduction or atomic anywhere:
+//   forward            S = Q_i K^T, P = softmax(scale S) (quad shuffles), O_i = P V, lse
+//   backward, pass 1   rows = queries: recompute P from lse, dP = dO_i V^T, dS = P (dP - D), dQ_i = scale dS K
+//   backward, pass 2   rows = keys:    S^T = K_j Q^T, dP^T = V_j dO^T, dV_j = P^T dO, dK_j = scale dS^T Q
+// T <= 128 (the HOI translators: 48 / 8 tokens; HHI at D <= 42 frames x 3 tasks); longer clips use the
+// shape-general kernels of attention_simt.cu.  Dropout masks are regenerated from (key, b, h, query, key index).
+#include <math.h>
+
+#include "ops.h"
+
+namespace egot2 {
+
+namespace {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int DH> struct Tile {
+  static constexpr int LD = DH + 8;          // padded row length (elements)
+  static constexpr int KS = DH / 16;         // k16 steps over the head dim
+  static constexpr int ND = DH / 8;          // n8 tiles over the head dim
+};
+
+// A fragments of the 16 x DH row tile starting at row r0 of a [rows][LD] smem matrix
+template <int DH>
+__device__ __forceinline__ void load_a(uint32_t sbase, int r0, uint32_t (&a)[Tile<DH>::KS][4]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int ks = 0; ks < Tile<DH>::KS; ++ks)
+    ldsm_x4(sbase + (uint32_t)(((r0 + (lane & 15)) * Tile<DH>::LD + ks * 16 + 8 * (lane >> 4)) * 2), a[ks]);
+}
+// acc[nt] (16 x 8 each) = A(16 x DH) . Bs^T, Bs = [NT*8 rows][LD]  (row index of Bs = output column)
+template <int DH, int NT>
+__device__ __forceinline__ void gemm_rc(float (&acc)[NT][4], const uint32_t (&a)[Tile<DH>::KS][4], uint32_t sB) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int n2 = 0; n2 < NT / 2; ++n2) {
+#pragma unroll
+    for (int ks = 0; ks < Tile<DH>::KS; ++ks) {
+      uint32_t b[4];
+      ldsm_x4(sB + (uint32_t)(((n2 * 16 + (lane & 7) + 8 * (lane >> 4)) * Tile<DH>::LD + ks * 16 + 8 * ((lane >> 3) & 1)) * 2), b);
+      mma16816(acc[2 * n2], a[ks], b[0], b[1]);
+      mma16816(acc[2 * n2 + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+// o[nd] (16 x 8 each over the head dim) += P(16 x NT*8) . Bs, Bs = [NT*8 rows][LD]  (row index of Bs = reduction index)
+template <int DH, int NT>
+__device__ __forceinline__ void gemm_pv(float (&o)[Tile<DH>::ND][4], const uint32_t (&p)[NT / 2][4], uint32_t sB) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int kb = 0; kb < NT / 2; ++kb) {
+#pragma unroll
+    for (int d2 = 0; d2 < Tile<DH>::ND / 2; ++d2) {
+      uint32_t b[4];
+      ldsm_x4_t(sB + (uint32_t)(((kb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * Tile<DH>::LD + d2 * 16 + 8 * (lane >> 4)) * 2), b);
+      mma16816(o[2 * d2], p[kb], b[0], b[1]);
+      mma16816(o[2 * d2 + 1], p[kb], b[2], b[3]);
+    }
+  }
+}
+
+// stage rows [0,T) x DH of a strided global matrix into smem [Tpad][LD]; rows >= T are zero
+template <int DH>
+__device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, int ld_src, int T, int Tpad) {
+  constexpr int CH = DH / 8;                 // 16-byte chunks per row
+  for (int e = threadIdx.x; e < Tpad * CH; e += blockDim.x) {
+    const int r = e / CH, c = (e % CH) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < T) v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld_src + c);
+    *reinterpret_cast<uint4*>(dst + r * Tile<DH>::LD + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------ forward
+template <int DH, int TK16>
+__global__ void __launch_bounds__(TK16 * 32) attn_mma_fwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv,
+                                                                 bf16* __restrict__ out, float* __restrict__ lse,
+                                                                 float p_drop, uint64_t drop_key) {
+  constexpr int NT = TK16 * 2, LD = Tile<DH>::LD, TP = TK16 * 16;
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem);
+  bf16* sK = sQ + TP * LD;
+  bf16* sV = sK + TP * LD;
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* base = qkv + (size_t)b * T * 3 * H + h * DH;
+  stage<DH>(sQ, base, 3 * H, T, TP);
+  stage<DH>(sK, base + H, 3 * H, T, TP);
+  stage<DH>(sV, base + 2 * H, 3 * H, T, TP);
+  __syncthreads();
+  const int r0 = warp * 16;
+  if (r0 >= T) return;
+  uint32_t aq[Tile<DH>::KS][4];
+  load_a<DH>((uint32_t)__cvta_generic_to_shared(sQ), r0, aq);
+  float s[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+  gemm_rc<DH, NT>(s, aq, (uint32_t)__cvta_generic_to_shared(sK));
+  // softmax over keys; thread holds rows (lane/4) and (lane/4 + 8), columns nt*8 + 2*(lane%4) + {0,1}
+  const float sc = rsqrtf((float)DH) * 1.4426950408889634f;        // scale * log2(e)
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int c = nt * 8 + 2 * (lane & 3);
+    if (c >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+    if (c + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+  const int q0 = r0 + (lane >> 2), q1 = q0 + 8;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  uint32_t p[NT / 2][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    float e0 = exp2f((s[nt][0] - mx0) * sc), e1 = exp2f((s[nt][1] - mx0) * sc);
+    float e2 = exp2f((s[nt][2] - mx1) * sc), e3 = exp2f((s[nt][3] - mx1) * sc);
+    sum0 += e0 + e1; sum1 += e2 + e3;
+    if (p_drop > 0.f) {
+      const int c = nt * 8 + 2 * (lane & 3);
+      e0 *= drop_scale(drop_key, ((uint64_t)bh * T + q0) * T + c, p_drop, inv_keep);
+      e1 *= drop_scale(drop_key, ((uint64_t)bh * T + q0) * T + c + 1, p_drop, inv_keep);
+      e2 *= drop_scale(drop_key, ((uint64_t)bh * T + q1) * T + c, p_drop, inv_keep);
+      e3 *= drop_scale(drop_key, ((uint64_t)bh * T + q1) * T + c + 1, p_drop, inv_keep);
+    }
+    p[nt >> 1][(nt & 1) * 2] = pack_bf16(e0, e1);
+    p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(e2, e3);
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  float o[Tile<DH>::ND][4];
+#pragma unroll
+  for (int i = 0; i < Tile<DH>::ND; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  gemm_pv<DH, NT>(o, p, (uint32_t)__cvta_generic_to_shared(sV));
+  const float i0 = 1.f / sum0, i1 = 1.f / sum1;
+  bf16* ob = out + (size_t)b * T * H + h * DH;
+#pragma unroll
+  for (int nd = 0; nd < Tile<DH>::ND; ++nd) {
+    const int c = nd * 8 + 2 * (lane & 3);
+    if (q0 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)q0 * H + c) = pack_bf16(o[nd][0] * i0, o[nd][1] * i0);
+    if (q1 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)q1 * H + c) = pack_bf16(o[nd][2] * i1, o[nd][3] * i1);
+  }
+  if ((lane & 3) == 0) {
+    const float scn = rsqrtf((float)DH);
+    if (q0 < T) lse[(size_t)bh * T + q0] = mx0 * scn + logf(sum0);
+    if (q1 < T) lse[(size_t)bh * T + q1] = mx1 * scn + logf(sum1);
+  }
+}
+
+// ------------------------------------------------------------------ backward
+template <int DH, int TK16>
+__global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv,
+                                                                 const bf16* __restrict__ out, const float* __restrict__ lse,
+                                                                 const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
+                                                                 float p_drop, uint64_t drop_key) {
+  constexpr int NT = TK16 * 2, LD = Tile<DH>::LD, TP = TK16 * 16;
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem);
+  bf16* sK = sQ + TP * LD;
+  bf16* sV = sK + TP * LD;
+  bf16* sdO = sV + TP * LD;
+  float* sL = reinterpret_cast<float*>(sdO + TP * LD);      // lse per query
+  float* sD = sL + TP;                                      // D = rowsum(dO * O) per query
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* base = qkv + (size_t)b * T * 3 * H + h * DH;
+  const bf16* ob = out + (size_t)b * T * H + h * DH;
+  const bf16* dob = dout + (size_t)b * T * H + h * DH;
+  stage<DH>(sQ, base, 3 * H, T, TP);
+  stage<DH>(sK, base + H, 3 * H, T, TP);
+  stage<DH>(sV, base + 2 * H, 3 * H, T, TP);
+  stage<DH>(sdO, dob, H, T, TP);
+  // D_i and lse_i: 4 lanes per query row
+  for (int r = (threadIdx.x >> 2); r < TP; r += (blockDim.x >> 2)) {
+    float d = 0.f;
+    if (r < T)
+      for (int c = (threadIdx.x & 3) * 2; c < DH; c += 8) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dob + (size_t)r * H + c));
+        const float2 o2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + (size_t)r * H + c));
+        d += a.x * o2.x + a.y * o2.y;
+      }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    if ((threadIdx.x & 3) == 0) { sD[r] = d; sL[r] = r < T ? lse[(size_t)bh * T + r] : 0.f; }
+  }
+  __syncthreads();
+  const int r0 = warp * 16;
+  if (r0 >= T) return;
+  const float scn = rsqrtf((float)DH);
+  const float sc2 = scn * 1.4426950408889634f, l2e = 1.4426950408889634f;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const int ra = r0 + (lane >> 2), rb = ra + 8;            // this thread's two tile rows
+  const uint32_t uQ = (uint32_t)__cvta_generic_to_shared(sQ), uK = (uint32_t)__cvta_generic_to_shared(sK);
+  const uint32_t uV = (uint32_t)__cvta_generic_to_shared(sV), udO = (uint32_t)__cvta_generic_to_shared(sdO);
+  bf16* dq = dqkv + (size_t)b * T * 3 * H + h * DH;
+
+  // ---------------- pass 1: rows = queries -> dQ
+  {
+    uint32_t a1[Tile<DH>::KS][4], a2[Tile<DH>::KS][4];
+    load_a<DH>(uQ, r0, a1);
+    load_a<DH>(udO, r0, a2);
+    float s[NT][4], dp[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+    gemm_rc<DH, NT>(s, a1, uK);
+    gemm_rc<DH, NT>(dp, a2, uV);
+    const float la = sL[ra] * l2e, lb = sL[rb] * l2e, da = sD[ra], db = sD[rb];
+    uint32_t ds[NT / 2][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int c = nt * 8 + 2 * (lane & 3);
+      float p0 = c < T ? exp2f(s[nt][0] * sc2 - la) : 0.f, p1 = c + 1 < T ? exp2f(s[nt][1] * sc2 - la) : 0.f;
+      float p2 = c < T ? exp2f(s[nt][2] * sc2 - lb) : 0.f, p3 = c + 1 < T ? exp2f(s[nt][3] * sc2 - lb) : 0.f;
+      float g0 = dp[nt][0], g1 = dp[nt][1], g2 = dp[nt][2], g3 = dp[nt][3];
+      if (p_drop > 0.f) {
+        g0 *= drop_scale(drop_key, ((uint64_t)bh * T + ra) * T + c, p_drop, inv_keep);
+        g1 *= drop_scale(drop_key, ((uint64_t)bh * T + ra) * T + c + 1, p_drop, inv_keep);
+        g2 *= drop_scale(drop_key, ((uint64_t)bh * T + rb) * T + c, p_drop, inv_keep);
+        g3 *= drop_scale(drop_key, ((uint64_t)bh * T + rb) * T + c + 1, p_drop, inv_keep);
+      }
+      ds[nt >> 1][(nt & 1) * 2] = pack_bf16(p0 * (g0 - da), p1 * (g1 - da));
+      ds[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2 * (g2 - db), p3 * (g3 - db));
+    }
+    float o[Tile<DH>::ND][4];
+#pragma unroll
+    for (int i = 0; i < Tile<DH>::ND; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    gemm_pv<DH, NT>(o, ds, uK);
+#pragma unroll
+    for (int nd = 0; nd < Tile<DH>::ND; ++nd) {
+      const int c = nd * 8 + 2 * (lane & 3);
+      if (ra < T) *reinterpret_cast<uint32_t*>(dq + (size_t)ra * 3 * H + c) = pack_bf16(o[nd][0] * scn, o[nd][1] * scn);
+      if (rb < T) *reinterpret_cast<uint32_t*>(dq + (size_t)rb * 3 * H + c) = pack_bf16(o[nd][2] * scn, o[nd][3] * scn);
+    }
+  }
+  // ---------------- pass 2: rows = keys -> dK, dV   (tile element (r, c) = (key r, query c))
+  {
+    uint32_t a1[Tile<DH>::KS][4], a2[Tile<DH>::KS][4];
+    load_a<DH>(uK, r0, a1);
+    load_a<DH>(uV, r0, a2);
+    float s[NT][4], dp[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+    gemm_rc<DH, NT>(s, a1, uQ);
+    gemm_rc<DH, NT>(dp, a2, udO);
+    uint32_t pf[NT / 2][4], ds[NT / 2][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int c = nt * 8 + 2 * (lane & 3);
+      const float l0 = sL[c] * l2e, l1 = sL[c + 1] * l2e, d0 = sD[c], d1 = sD[c + 1];
+      float p0 = c < T ? exp2f(s[nt][0] * sc2 - l0) : 0.f, p1 = c + 1 < T ? exp2f(s[nt][1] * sc2 - l1) : 0.f;
+      float p2 = c < T ? exp2f(s[nt][2] * sc2 - l0) : 0.f, p3 = c + 1 < T ? exp2f(s[nt][3] * sc2 - l1) : 0.f;
+      float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
+      if (p_drop > 0.f) {
+        m0 = drop_scale(drop_key, ((uint64_t)bh * T + c) * T + ra, p_drop, inv_keep);
+        m1 = drop_scale(drop_key, ((uint64_t)bh * T + c + 1) * T + ra, p_drop, inv_keep);
+        m2 = drop_scale(drop_key, ((uint64_t)bh * T + c) * T + rb, p_drop, inv_keep);
+        m3 = drop_scale(drop_key, ((uint64_t)bh * T + c + 1) * T + rb, p_drop, inv_keep);
+      }
+      pf[nt >> 1][(nt & 1) * 2] = pack_bf16(p0 * m0, p1 * m1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2 * m2, p3 * m3);
+      ds[nt >> 1][(nt & 1) * 2] = pack_bf16(p0 * (dp[nt][0] * m0 - d0), p1 * (dp[nt][1] * m1 - d1));
+      ds[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2 * (dp[nt][2] * m2 - d0), p3 * (dp[nt][3] * m3 - d1));
+    }
+    float ov[Tile<DH>::ND][4], ok[Tile<DH>::ND][4];
+#pragma unroll
+    for (int i = 0; i < Tile<DH>::ND; ++i) { ov[i][0] = ov[i][1] = ov[i][2] = ov[i][3] = 0.f; ok[i][0] = ok[i][1] = ok[i][2] = ok[i][3] = 0.f; }
+    gemm_pv<DH, NT>(ov, pf, udO);
+    gemm_pv<DH, NT>(ok, ds, uQ);
+#pragma unroll
+    for (int nd = 0; nd < Tile<DH>::ND; ++nd) {
+      const int c = nd * 8 + 2 * (lane & 3);
+      if (ra < T) {
+        *reinterpret_cast<uint32_t*>(dq + (size_t)ra * 3 * H + H + c) = pack_bf16(ok[nd][0] * scn, ok[nd][1] * scn);
+        *reinterpret_cast<uint32_t*>(dq + (size_t)ra * 3 * H + 2 * H + c) = pack_bf16(ov[nd][0], ov[nd][1]);
+      }
+      if (rb < T) {
+        *reinterpret_cast<uint32_t*>(dq + (size_t)rb * 3 * H + H + c) = pack_bf16(ok[nd][2] * scn, ok[nd][3] * scn);
+        *reinterpret_cast<uint32_t*>(dq + (size_t)rb * 3 * H + 2 * H + c) = pack_bf16(ov[nd][2], ov[nd][3]);
+      }
+    }
+  }
+}
+
+template <int DH, int TK16>
+int launch_fwd(int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p, uint64_t key, cudaStream_t st) {
+  constexpr size_t smem = (size_t)3 * TK16 * 16 * Tile<DH>::LD * 2;
+  auto kern = attn_mma_fwd_kernel<DH, TK16>;
+  static bool set = false;
+  if (!set) { EGOT2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+  kern<<<B * heads, TK16 * 32, smem, st>>>(T, H, heads, (const bf16*)qkv, (bf16*)out, lse, p, key);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+template <int DH, int TK16>
+int launch_bwd(int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse, const void* dout,
+               void* dqkv, float p, uint64_t key, cudaStream_t st) {
+  constexpr size_t smem = (size_t)4 * TK16 * 16 * Tile<DH>::LD * 2 + 2 * TK16 * 16 * 4;
+  auto kern = attn_mma_bwd_kernel<DH, TK16>;
+  static bool set = false;
+  if (!set) { EGOT2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+  kern<<<B * heads, TK16 * 32, smem, st>>>(T, H, heads, (const bf16*)qkv, (const bf16*)out, lse, (const bf16*)dout,
+                                          (bf16*)dqkv, p, key);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int pick_tk16(int T) { return T <= 16 ? 1 : (T <= 32 ? 2 : (T <= 64 ? 4 : (T <= 96 ? 6 : 8))); }
+
+}  // namespace
+
+bool attention_mma_supported(int dtype, int T, int H, int heads) {
+  if (dtype != EGOT2_BF16 || heads <= 0 || H % heads) return false;
+  const int dh = H / heads;
+  return T >= 1 && T <= 128 && (dh == 16 || dh == 32 || dh == 64) && (H % 8 == 0);
+}
+
+#define EGOT2_ATT_SWITCH(FN, ...)                                                     \
+  switch (dh * 16 + tk) {                                                             \
+    case 16 * 16 + 1: return FN<16, 1>(__VA_ARGS__);  case 16 * 16 + 2: return FN<16, 2>(__VA_ARGS__); \
+    case 16 * 16 + 4: return FN<16, 4>(__VA_ARGS__);  case 16 * 16 + 6: return FN<16, 6>(__VA_ARGS__); \
+    case 16 * 16 + 8: return FN<16, 8>(__VA_ARGS__);                                  \
+    case 32 * 16 + 1: return FN<32, 1>(__VA_ARGS__);  case 32 * 16 + 2: return FN<32, 2>(__VA_ARGS__); \
+    case 32 * 16 + 4: return FN<32, 4>(__VA_ARGS__);  case 32 * 16 + 6: return FN<32, 6>(__VA_ARGS__); \
+    case 32 * 16 + 8: return FN<32, 8>(__VA_ARGS__);                                  \
+    case 64 * 16 + 1: return FN<64, 1>(__VA_ARGS__);  case 64 * 16 + 2: return FN<64, 2>(__VA_ARGS__); \
+    case 64 * 16 + 4: return FN<64, 4>(__VA_ARGS__);  case 64 * 16 + 6: return FN<64, 6>(__VA_ARGS__); \
+    case 64 * 16 + 8: return FN<64, 8>(__VA_ARGS__);                                  \
+  }
+
+int attention_mma_fwd(int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p_drop,
+                      uint64_t drop_key, cudaStream_t st) {
+  if (B * T == 0) return 0;
+  const int dh = H / heads, tk = pick_tk16(T);
+  EGOT2_ATT_SWITCH(launch_fwd, B, T, H, heads, qkv, out, lse, p_drop, drop_key, st)
+  EGOT2_CHECK(false, "attention_mma_fwd: unsupported dh=%d T=%d", dh, T);
+}
+int attention_mma_bwd(int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse, const void* dout,
+                      void* dqkv, float p_drop, uint64_t drop_key, cudaStream_t st) {
+  if (B * T == 0) return 0;
+  const int dh = H / heads, tk = pick_tk16(T);
+  EGOT2_ATT_SWITCH(launch_bwd, B, T, H, heads, qkv, out, lse, dout, dqkv, p_drop, drop_key, st)
+  EGOT2_CHECK(false, "attention_mma_bwd: unsupported dh=%d T=%d", dh, T);
+}
+
+}  // namespace egot2

@@ -22,7 +22,6 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements = one 128-byte swizzle row
-constexpr int STAGES = 4;
 constexpr int NTHREADS = 192;
 
 struct EpiArgs {
@@ -39,12 +38,57 @@ __device__ __forceinline__ long long remap(int r, int rpg, int gstride) {
   return rpg > 0 ? (long long)(r / rpg) * gstride + (r % rpg) : (long long)r;
 }
 
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// 32 contiguous elements <-> 32 fp32 registers with 128-bit accesses (pointer must be 16 B aligned)
+__device__ __forceinline__ void load32(const float* p, float (&o)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + j);
+    o[j] = t.x; o[j + 1] = t.y; o[j + 2] = t.z; o[j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void load32(const bf16* p, float (&o)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p + j);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[j + 2 * k] = __uint_as_float(w[k] << 16);
+      o[j + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+  }
+}
+__device__ __forceinline__ void store32(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+__device__ __forceinline__ void store32(bf16* p, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 o;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(p + j) = o;
+  }
+}
+
+template <int BN> struct TileCfg {            // stages chosen so that BN<=128 tiles fit two CTAs per SM
+  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int MIN_CTAS = BN == 256 ? 1 : 2;
+};
+
 template <int BN, bool A_MN, bool B_MN, typename TO>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, TileCfg<BN>::MIN_CTAS)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const EpiArgs e,
                   const int k_blocks_total, const int k_blocks_per_split) {
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr int STAGES = TileCfg<BN>::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024 B alignment
   const uint32_t sA = smem_base;
@@ -120,66 +164,99 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
   } else {
     // ================================================================ epilogue (warps 2..5)
+    // One accumulator row per thread.  Fast path (full 32-column chunk, 16 B-aligned rows): every global access is
+    // a 128-bit vector, the one large auxiliary operand (ReLU gate or residual) is fetched while the TMEM load is
+    // in flight, and there is no per-element control flow.  Edge chunks take the scalar path.
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
     const int m = m0 + q * 32 + lane;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const float inv_keep = e.p_drop > 0.f ? 1.f / (1.f - e.p_drop) : 1.f;
-    const bool row_ok = m < e.M;
+    const bool row_ok = (m < e.M) && nkb > 0;
     const long long crow = row_ok ? remap(m, e.c_rpg, e.c_gstride) : 0;
-    TO* __restrict__ C = (TO*)e.C;
+    TO* __restrict__ crow_ptr = (TO*)e.C + crow * e.ldc;
     const bool first_split = blockIdx.z == 0;
+    const float* bias = first_split ? e.bias : nullptr;
+    const TO* mask_row = e.mask ? (const TO*)e.mask + (long long)(row_ok ? m : 0) * e.ldm : nullptr;
+    const TO* res_row = (e.residual && first_split) ? (const TO*)e.residual + (long long)(row_ok ? m : 0) * e.ldr : nullptr;
+    const bool vec_ok = aligned16(crow_ptr) && aligned16(mask_row) && aligned16(res_row) && aligned16(bias);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      const int nb = n0 + c0;
+      const bool active = row_ok && nb < e.N;
+      const bool fast = active && vec_ok && (nb + 32 <= e.N);
+      float aux[32];
+      const TO* aux_row = mask_row ? mask_row : res_row;
+      if (fast && aux_row) load32(aux_row + nb, aux);
       tmem_ld_wait();
-      if (!row_ok || n0 + c0 >= e.N || nkb <= 0) continue;
+      if (!active) continue;
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c0 + j;
-        float x = __uint_as_float(r[j]);
-        if (n < e.N) {
-          if (e.bias && first_split) x += __ldg(e.bias + n);
-          if (e.relu) x = fmaxf(x, 0.f);
-          if (e.mask) x = to_f32(((const TO*)e.mask)[(long long)m * e.ldm + n]) > 0.f ? x * e.mask_scale : 0.f;
-          if (e.p_drop > 0.f) x *= drop_scale(e.drop_key, (uint64_t)m * e.N + n, e.p_drop, inv_keep);
-          if (e.residual && first_split) x += to_f32(((const TO*)e.residual)[(long long)m * e.ldr + n]);
-        }
-        v[j] = x;
-      }
-      TO* dst = C + crow * e.ldc + n0 + c0;
-      const bool full = (n0 + c0 + 32 <= e.N);
-      if (e.accumulate) {
-        if constexpr (sizeof(TO) == 4) {
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (fast) {
+        if (bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + c0 + j < e.N) {
-              if (e.atomic) atomicAdd((float*)dst + j, v[j]);
-              else ((float*)dst)[j] += v[j];
-            }
-        }
-      } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-        if constexpr (sizeof(TO) == 4) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>((float*)dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>((bf16*)dst + j) = o;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
           }
+        }
+        if (e.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (mask_row) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = aux[j] > 0.f ? v[j] * e.mask_scale : 0.f;
+        }
+        if (e.p_drop > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key, (uint64_t)m * e.N + nb + j, e.p_drop, inv_keep);
+        }
+        if (res_row) {
+          if (mask_row) load32(res_row + nb, aux);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += aux[j];
+        }
+        if (e.accumulate) {
+          if constexpr (sizeof(TO) == 4) {
+            float* dst = (float*)crow_ptr + nb;
+            if (e.atomic) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+            } else {
+              float old[32];
+              load32(dst, old);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += old[j];
+              store32(dst, v);
+            }
+          }
+        } else {
+          store32(crow_ptr + nb, v);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c0 + j < e.N) dst[j] = from_f32<TO>(v[j]);
+        for (int j = 0; j < 32; ++j) {
+          const int n = nb + j;
+          if (n >= e.N) continue;
+          float x = v[j];
+          if (bias) x += __ldg(bias + n);
+          if (e.relu) x = fmaxf(x, 0.f);
+          if (mask_row) x = to_f32(mask_row[n]) > 0.f ? x * e.mask_scale : 0.f;
+          if (e.p_drop > 0.f) x *= drop_scale(e.drop_key, (uint64_t)m * e.N + n, e.p_drop, inv_keep);
+          if (res_row) x += to_f32(res_row[n]);
+          if (e.accumulate) {
+            if constexpr (sizeof(TO) == 4) {
+              if (e.atomic) atomicAdd((float*)crow_ptr + n, x);
+              else ((float*)crow_ptr)[n] += x;
+            }
+          } else {
+            crow_ptr[n] = from_f32<TO>(x);
+          }
+        }
       }
     }
   }
@@ -227,6 +304,7 @@ int make_map(CUtensorMap* map, const void* base, int inner, int rows, int ld, in
 
 template <int BN, bool A_MN, bool B_MN, typename TO>
 int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
+  constexpr int STAGES = TileCfg<BN>::STAGES;
   constexpr size_t smem = 1024 + STAGES * (BM * BK * 2 + BN * BK * 2) + 16 * STAGES + 64;
   static bool attr_set = false;
   auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, TO>;
@@ -268,7 +346,7 @@ int pick_major(const GemmArgs& a, int bn, const CUtensorMap& ma, const CUtensorM
   return pick_bn<true, false, TO>(a, bn, ma, mb, st);
 }
 
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+bool host_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 
@@ -277,10 +355,11 @@ int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
   if (a.in_dtype != EGOT2_BF16) return -1;
   if (a.a_rpg > 0 || a.b_rpg > 0) return -1;                      // gathered operands: not yet on the TMA path
   if (a.M < 1 || a.N < 32 || a.K < 16) return -1;                  // degenerate tiles (tiny heads) stay on CUDA cores
-  if (!aligned16(a.A) || !aligned16(a.B) || (a.lda % 8) || (a.ldb % 8)) return -1;
+  if (!host_aligned16(a.A) || !host_aligned16(a.B) || (a.lda % 8) || (a.ldb % 8)) return -1;
   if (a.accumulate && a.out_dtype != EGOT2_F32) return -1;
   if (a.split_k > 1 && (!a.accumulate || a.relu || a.mask || a.p_drop > 0.f)) return -1;
-  const int bn = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : ((a.N % 256 == 0 || a.N > 512) ? 256 : 128));
+  // short-K problems are epilogue/store bound: 128-wide tiles run two CTAs per SM; long-K ones amortise A over 256 columns
+  const int bn = a.N <= 64 ? 64 : ((a.N <= 128 || a.K <= 512) ? 128 : ((a.N % 256 == 0 || a.N > 512) ? 256 : 128));
   CUtensorMap ma, mb;
   // A: K-major (M,K) -> box {64 k, 128 m};  MN-major (K,M) -> box {64 m, 64 k}
   if (!a.trans_a) EGOT2_TRY(make_map(&ma, a.A, a.K, a.M, a.lda, BK, BM));

@@ -60,6 +60,11 @@ int attention_simt_fwd(int dtype, int B, int T, int H, int heads, const void* qk
 int attention_simt_bwd(int dtype, int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse,
                        const void* dout, void* dqkv, float p_drop, uint64_t drop_key, void* ws, size_t ws_bytes,
                        cudaStream_t st);
+bool attention_mma_supported(int dtype, int T, int H, int heads);           // attention_mma.cu (bf16, T <= 128)
+int attention_mma_fwd(int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p_drop,
+                      uint64_t drop_key, cudaStream_t st);
+int attention_mma_bwd(int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse,
+                      const void* dout, void* dqkv, float p_drop, uint64_t drop_key, cudaStream_t st);
 int attention_fwd(int dtype, int B, int T, int H, int heads, const void* qkv, void* out, float* lse,
                   float p_drop, uint64_t drop_key, cudaStream_t st);
 size_t attention_bwd_workspace(int dtype, int B, int T, int H, int heads);

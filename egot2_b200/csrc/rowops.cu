@@ -100,36 +100,62 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) ln_bwd_kernel(const LayerNo
 
 // ------------------------------------------------------------------ misc elementwise / reductions
 template <typename TT>
-__global__ void table_grad_kernel(int B, int T, int H, const TT* __restrict__ dy, float* __restrict__ dtable) {
-  // one CTA per (token t, column block); loop over clips
+__global__ void table_grad_kernel(int B, int T, int H, int clips_per_cta, const TT* __restrict__ dy,
+                                  float* __restrict__ dtable) {
+  // CTA (t, chunk): sums its chunk of clips for token t, then one atomic per column
   const int t = blockIdx.x;
+  const int b0 = blockIdx.y * clips_per_cta, b1 = min(B, b0 + clips_per_cta);
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += to_f32(dy[((size_t)b * T + t) * H + c]);
-    dtable[(size_t)t * H + c] += s;
+    for (int b = b0; b < b1; ++b) s += to_f32(dy[((size_t)b * T + t) * H + c]);
+    atomicAdd(dtable + (size_t)t * H + c, s);
   }
 }
+
+template <typename T> struct Pair;
+template <> struct Pair<float> { typedef float2 type; };
+template <> struct Pair<bf16> { typedef __nv_bfloat162 type; };
+__device__ __forceinline__ float2 pair_f32(float2 v) { return v; }
+__device__ __forceinline__ float2 pair_f32(__nv_bfloat162 v) { return __bfloat1622float2(v); }
 
 template <typename T>
 __global__ void colsum_kernel(int M, int N, const T* __restrict__ x, int ldx, int rpg, int gstride,
                               float* __restrict__ out, int rows_per_cta) {
-  // blockDim = (32 cols, 8 row-lanes)
-  const int n = blockIdx.x * 32 + threadIdx.x;
+  // blockDim = (32 column pairs, 8 row lanes): a warp reads 64 consecutive columns of one row per load
+  typedef typename Pair<T>::type P2;
+  const int n = (blockIdx.x * 32 + threadIdx.x) * 2;
   const int mbeg = blockIdx.y * rows_per_cta, mend = min(M, mbeg + rows_per_cta);
-  float s = 0.f;
-  if (n < N)
-    for (int m = mbeg + threadIdx.y; m < mend; m += 8) {
-      const long long r = rpg > 0 ? (long long)(m / rpg) * gstride + (m % rpg) : m;
-      s += to_f32(x[r * ldx + n]);
-    }
-  __shared__ float red[8][33];
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && n < N) {
-    float t = 0.f;
+  float s0 = 0.f, s1 = 0.f;
+  const bool vec = (n + 1 < N) && ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & (2 * sizeof(T) - 1)) == 0);
+  if (n < N) {
+    for (int mb = mbeg + threadIdx.y; mb < mend; mb += 32) {
+      float2 v[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    atomicAdd(out + n, t);
+      for (int u = 0; u < 4; ++u) {
+        const int m = mb + 8 * u;
+        v[u] = make_float2(0.f, 0.f);
+        if (m < mend) {
+          const long long r = rpg > 0 ? (long long)(m / rpg) * gstride + (m % rpg) : m;
+          if (vec) v[u] = pair_f32(*reinterpret_cast<const P2*>(x + r * ldx + n));
+          else { v[u].x = to_f32(x[r * ldx + n]); if (n + 1 < N) v[u].y = to_f32(x[r * ldx + n + 1]); }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s0 += v[u].x; s1 += v[u].y; }
+    }
+  }
+  __shared__ float red[8][65];
+  red[threadIdx.y][2 * threadIdx.x] = s0;
+  red[threadIdx.y][2 * threadIdx.x + 1] = s1;
+  __syncthreads();
+  if (threadIdx.y < 2) {
+    const int c = 2 * threadIdx.x + threadIdx.y, nn = blockIdx.x * 64 + c;
+    if (nn < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][c];
+      atomicAdd(out + nn, t);
+    }
   }
 }
 
@@ -306,16 +332,21 @@ int layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t st) {
 
 int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, cudaStream_t st) {
   const int nt = H < 256 ? ((H + 31) / 32 * 32) : 256;
-  if (dtype == EGOT2_F32) table_grad_kernel<float><<<T, nt, 0, st>>>(B, T, H, (const float*)dy, dtable);
-  else table_grad_kernel<bf16><<<T, nt, 0, st>>>(B, T, H, (const bf16*)dy, dtable);
+  int chunks = (4 * sm_count() + T - 1) / T;           // ~4 CTAs per SM
+  if (chunks > B) chunks = B;
+  if (chunks < 1) chunks = 1;
+  const int per = (B + chunks - 1) / chunks;
+  dim3 grid(T, (B + per - 1) / per);
+  if (dtype == EGOT2_F32) table_grad_kernel<float><<<grid, nt, 0, st>>>(B, T, H, per, (const float*)dy, dtable);
+  else table_grad_kernel<bf16><<<grid, nt, 0, st>>>(B, T, H, per, (const bf16*)dy, dtable);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
 
 int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int gstride, float* out, cudaStream_t st) {
   if (M == 0 || N == 0) return 0;
-  const int col_blocks = (N + 31) / 32;
-  int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
+  const int col_blocks = (N + 63) / 64;
+  int row_blocks = (sm_count() * 8 + col_blocks - 1) / col_blocks;
   int rows_per_cta = (M + row_blocks - 1) / row_blocks;
   if (rows_per_cta < 64) rows_per_cta = 64;
   row_blocks = (M + rows_per_cta - 1) / rows_per_cta;

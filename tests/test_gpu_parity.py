@@ -211,3 +211,55 @@ def test_tcgen05_gemm(M, N, K, ta, tb, acc):
                E._stream())
         refb = torch.relu(A.double() @ B.double() + bias.double())
         assert float((Cb.double() - refb).abs().max()) / float(refb.abs().max()) < 1e-2
+
+
+def _np_mix64(x):
+    import numpy as np
+    x = x.astype(np.uint64)
+    x ^= x >> np.uint64(33); x *= np.uint64(0xff51afd7ed558ccd)
+    x ^= x >> np.uint64(33); x *= np.uint64(0xc4ceb9fe1a85ec53)
+    x ^= x >> np.uint64(33)
+    return x
+
+
+def dropout_mask_oracle(seed, site, layer, n, p):
+    """Bit-exact restatement of csrc/common.cuh drop_scale(): multiplier (0 or 1/(1-p)) for element indices 0..n-1."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        key = _np_mix64(np.array([seed], dtype=np.uint64) ^ (np.uint64(0x9E3779B97F4A7C15) * np.uint64(site + 16 * layer + 1)))
+        h = _np_mix64(key + np.arange(n, dtype=np.uint64) * np.uint64(0xD6E8FEB86659FD93))
+    u = (h >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return torch.from_numpy(np.where(u >= np.float32(p), np.float32(1.0 / (1.0 - p)), np.float32(0.0)))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("T,H,heads", [(90, 128, 4), (48, 128, 8), (128, 256, 4), (33, 64, 4), (150, 128, 4)])
+def test_attention_dropout_mask_is_exact(dtype, T, H, heads):
+    """Attention with dropout on the probabilities (train mode): forward and backward must use exactly the mask of
+    the documented counter-based generator — checked against a torch reference fed the same mask."""
+    from egot2_b200 import engine as E
+    torch.manual_seed(4)
+    B, p, seed = 2, 0.25, 99
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    qkv = (torch.randn(B, T, 3 * H, device="cuda") * 0.7).to(tdt)
+    dout = torch.randn(B, T, H, device="cuda").to(tdt)
+    out = torch.empty(B, T, H, device="cuda", dtype=tdt)
+    lse = torch.empty(B, heads, T, device="cuda", dtype=torch.float32)
+    dqkv = torch.empty_like(qkv)
+    L.call("egot2_attention_fwd", E._dt(dtype), B, T, H, heads, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), p, 1, seed,
+           E._stream())
+    nws = L.load().egot2_attention_bwd_workspace_bytes(E._dt(dtype), B, T, H, heads)
+    ws = torch.empty(max(nws, 16), device="cuda", dtype=torch.uint8)
+    L.call("egot2_attention_bwd", E._dt(dtype), B, T, H, heads, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(),
+           dout.data_ptr(), dqkv.data_ptr(), p, 1, seed, ws.data_ptr(), nws, E._stream())
+    mask = dropout_mask_oracle(seed, 3, 0, B * heads * T * T, p).reshape(B, heads, T, T).cuda().double()   # SITE_ATTN = 3
+    q = qkv.double().requires_grad_(True)
+    dh = H // heads
+    qq, kk, vv = q.split(H, dim=-1)
+    sh = lambda x: x.reshape(B, T, heads, dh).transpose(1, 2)
+    s = (sh(qq) / dh ** 0.5) @ sh(kk).transpose(-1, -2)
+    ref = ((torch.softmax(s, -1) * mask) @ sh(vv)).transpose(1, 2).reshape(B, T, H)
+    (gref,) = torch.autograd.grad(ref, q, dout.double())
+    t_out, t_g = (1e-4, 1e-3) if dtype == "fp32" else (1.5e-2, 3e-2)
+    assert float((out.double() - ref.detach()).abs().max()) <= t_out * float(ref.abs().max())
+    assert float((dqkv.double() - gref).abs().max()) <= t_g * float(gref.abs().max())
