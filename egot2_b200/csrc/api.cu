@@ -441,6 +441,10 @@ extern "C" int egot2_head_loss_fwd(const egot2_head_desc* d, const egot2_head_in
   const int rows = egot2_head_rows(d);
   if (rows == 0) return 0;
   EGOT2_CHECK(d->pool || (d->row_tokens > 0 && d->row_tokens <= d->T), "head: row_tokens=%d out of range", d->row_tokens);
+  if (head_fused_supported(*d)) {
+    EGOT2_TRY(head_fused_fwd(*d, *in, *out, st));
+    return loss_fwd(*d, rows, out->logits, in->labels, in->class_weight, out->row_loss, out->loss, out->argmax, st);
+  }
   EGOT2_TRY(pool_fwd(d->dtype, d->B, d->T, d->H, d->pool, d->row_tokens, in->x, out->pooled, st));
   const float ph = d->training ? d->p_head : 0.f;
   if (d->use_ln) {
@@ -467,6 +471,11 @@ extern "C" int egot2_head_loss_bwd(const egot2_head_desc* d, const egot2_head_in
   const int rows = egot2_head_rows(d);
   if (rows == 0) return 0;
   const size_t es = dtype_size(d->dtype);
+  if (head_fused_supported(*d)) {
+    if (d->loss != EGOT2_LOSS_NONE)
+      EGOT2_TRY(loss_bwd(*d, rows, saved->logits, in->labels, in->class_weight, saved->loss, dloss_scale, dlogits, st));
+    return head_fused_bwd(*d, *in, *saved, dlogits, dx, *g, st);
+  }
   EGOT2_CHECK(workspace && ws_bytes >= egot2_head_workspace_bytes(d) - 256, "head_loss_bwd: workspace too small");
   Carver ws(workspace, ws_bytes);
   void* dl_lp = ws.take((size_t)rows * d->n_out * es);

@@ -32,12 +32,19 @@ struct EpiArgs {
   float p_drop; uint64_t drop_key;
   const void* residual; int ldr;
   int accumulate; int atomic;
+  // grouped-K addressing for gathered MN-major operands (3-D tensor maps): 64-row k-block = kg groups x kdpad rows
+  int k_grouped, kg, kdblocks;
 };
 
 __device__ __forceinline__ long long remap(int r, int rpg, int gstride) {
   return rpg > 0 ? (long long)(r / rpg) * gstride + (r % rpg) : (long long)r;
 }
 
+
+// one 128-bit reduction instead of four scalar atomics (split-K partial sums)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -125,7 +132,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
-        const int k = (kb_begin + i) * BK;
+        const int kb = kb_begin + i;
+        const int k = kb * BK;
+        if (A_MN && B_MN && e.k_grouped) {
+          // token rows live in (clip, frame) groups inside a (B,T,H) tensor: one k-block = kg clips x kdpad frames,
+          // frames beyond the segment are zero-filled by TMA (they contribute nothing to dW)
+          const int grp = (kb / e.kdblocks) * e.kg, d0 = (kb % e.kdblocks) * 64;
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_3d(sA + s * A_BYTES + j * 8192, &tma_a, full0 + 8 * s, m0 + 64 * j, d0, grp);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_3d(sB + s * B_BYTES + j * 8192, &tma_b, full0 + 8 * s, n0 + 64 * j, d0, grp);
+          continue;
+        }
         if (!A_MN) {
           tma_load_2d(sA + s * A_BYTES, &tma_a, full0 + 8 * s, k, m0);
         } else {
@@ -225,7 +243,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             float* dst = (float*)crow_ptr + nb;
             if (e.atomic) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+              for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
               float old[32];
               load32(dst, old);
@@ -302,8 +320,27 @@ int make_map(CUtensorMap* map, const void* base, int inner, int rows, int ld, in
   return 0;
 }
 
+// 3-D bf16 map over rows that live in groups: element (c, d, g) at base + ((g * gstride_rows + d) * ld + c)
+int make_map3(CUtensorMap* map, const void* base, int inner, int rpg, int groups, int ld, long long gstride_rows,
+              int box_inner, int box_d, int box_g) {
+  EncodeTiledFn fn = encode_fn();
+  EGOT2_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rpg, (cuuint64_t)groups};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)gstride_rows * ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_d, (cuuint32_t)box_g};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGOT2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed (%d) inner=%d rpg=%d groups=%d ld=%d", (int)r, inner,
+              rpg, groups, ld);
+  return 0;
+}
+
+struct KGroup { int on = 0, g = 1, dblocks = 1, kb_total = 0; };
+
 template <int BN, bool A_MN, bool B_MN, typename TO>
-int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
+int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, const KGroup& kg, cudaStream_t st) {
   constexpr int STAGES = TileCfg<BN>::STAGES;
   constexpr size_t smem = 1024 + STAGES * (BM * BK * 2 + BN * BK * 2) + 16 * STAGES + 64;
   static bool attr_set = false;
@@ -317,7 +354,8 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cuda
   e.bias = a.bias; e.relu = a.relu; e.mask = a.mask; e.ldm = a.ldm; e.mask_scale = a.mask_scale;
   e.p_drop = a.p_drop; e.drop_key = a.drop_key; e.residual = a.residual; e.ldr = a.ldr;
   e.accumulate = a.accumulate; e.atomic = a.split_k > 1;
-  const int kb_total = (a.K + BK - 1) / BK;
+  e.k_grouped = kg.on; e.kg = kg.g; e.kdblocks = kg.dblocks;
+  const int kb_total = kg.on ? kg.kb_total : (a.K + BK - 1) / BK;
   int splits = a.split_k < 1 ? 1 : a.split_k;
   if (splits > kb_total) splits = kb_total;
   const int kb_per = (kb_total + splits - 1) / splits;
@@ -330,20 +368,20 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cuda
 }
 
 template <bool A_MN, bool B_MN, typename TO>
-int pick_bn(const GemmArgs& a, int bn, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
+int pick_bn(const GemmArgs& a, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const KGroup& kg, cudaStream_t st) {
   switch (bn) {
-    case 64: return launch<64, A_MN, B_MN, TO>(a, ma, mb, st);
-    case 128: return launch<128, A_MN, B_MN, TO>(a, ma, mb, st);
-    default: return launch<256, A_MN, B_MN, TO>(a, ma, mb, st);
+    case 64: return launch<64, A_MN, B_MN, TO>(a, ma, mb, kg, st);
+    case 128: return launch<128, A_MN, B_MN, TO>(a, ma, mb, kg, st);
+    default: return launch<256, A_MN, B_MN, TO>(a, ma, mb, kg, st);
   }
 }
 
 template <typename TO>
-int pick_major(const GemmArgs& a, int bn, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
-  if (!a.trans_a && a.trans_b) return pick_bn<false, false, TO>(a, bn, ma, mb, st);
-  if (!a.trans_a && !a.trans_b) return pick_bn<false, true, TO>(a, bn, ma, mb, st);
-  if (a.trans_a && !a.trans_b) return pick_bn<true, true, TO>(a, bn, ma, mb, st);
-  return pick_bn<true, false, TO>(a, bn, ma, mb, st);
+int pick_major(const GemmArgs& a, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const KGroup& kg, cudaStream_t st) {
+  if (!a.trans_a && a.trans_b) return pick_bn<false, false, TO>(a, bn, ma, mb, kg, st);
+  if (!a.trans_a && !a.trans_b) return pick_bn<false, true, TO>(a, bn, ma, mb, kg, st);
+  if (a.trans_a && !a.trans_b) return pick_bn<true, true, TO>(a, bn, ma, mb, kg, st);
+  return pick_bn<true, false, TO>(a, bn, ma, mb, kg, st);
 }
 
 bool host_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -353,7 +391,19 @@ bool host_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15
 // returns -1 when this kernel does not take the problem (caller falls back to the CUDA-core GEMM)
 int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
   if (a.in_dtype != EGOT2_BF16) return -1;
-  if (a.a_rpg > 0 || a.b_rpg > 0) return -1;                      // gathered operands: not yet on the TMA path
+  KGroup kg;
+  if (a.a_rpg > 0 || a.b_rpg > 0) {
+    // gathered token rows are supported for the weight-gradient orientation (both operands MN-major, K = tokens)
+    if (!(a.trans_a && !a.trans_b)) return -1;
+    const int rpg = a.a_rpg > 0 ? a.a_rpg : a.b_rpg;
+    if ((a.a_rpg > 0 && a.b_rpg > 0 && a.a_rpg != a.b_rpg) || a.K % rpg) return -1;
+    kg.on = 1;
+    const int dpad = rpg <= 16 ? 16 : (rpg <= 32 ? 32 : 64);
+    kg.g = 64 / dpad;
+    kg.dblocks = (rpg + 63) / 64;
+    const int groups = a.K / rpg;
+    kg.kb_total = ((groups + kg.g - 1) / kg.g) * kg.dblocks;
+  }
   if (a.M < 1 || a.N < 32 || a.K < 16) return -1;                  // degenerate tiles (tiny heads) stay on CUDA cores
   if (!host_aligned16(a.A) || !host_aligned16(a.B) || (a.lda % 8) || (a.ldb % 8)) return -1;
   if (a.accumulate && a.out_dtype != EGOT2_F32) return -1;
@@ -362,13 +412,20 @@ int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
   const int bn = a.N <= 64 ? 64 : ((a.N <= 128 || a.K <= 512) ? 128 : ((a.N % 256 == 0 || a.N > 512) ? 256 : 128));
   CUtensorMap ma, mb;
   // A: K-major (M,K) -> box {64 k, 128 m};  MN-major (K,M) -> box {64 m, 64 k}
+  if (kg.on) {
+    const int rpg = a.a_rpg > 0 ? a.a_rpg : a.b_rpg, groups = a.K / rpg, dpad = 64 / kg.g;
+    EGOT2_TRY(make_map3(&ma, a.A, a.M, rpg, groups, a.lda, a.a_rpg > 0 ? a.a_gstride : rpg, 64, dpad, kg.g));
+    EGOT2_TRY(make_map3(&mb, a.B, a.N, rpg, groups, a.ldb, a.b_rpg > 0 ? a.b_gstride : rpg, 64, dpad, kg.g));
+    if (a.out_dtype == EGOT2_F32) return pick_major<float>(a, bn, ma, mb, kg, st);
+    return pick_major<bf16>(a, bn, ma, mb, kg, st);
+  }
   if (!a.trans_a) EGOT2_TRY(make_map(&ma, a.A, a.K, a.M, a.lda, BK, BM));
   else EGOT2_TRY(make_map(&ma, a.A, a.M, a.K, a.lda, 64, BK));
   // B: K-major (N,K) -> box {64 k, BN n};   MN-major (K,N) -> box {64 n, 64 k}
   if (a.trans_b) EGOT2_TRY(make_map(&mb, a.B, a.K, a.N, a.ldb, BK, bn));
   else EGOT2_TRY(make_map(&mb, a.B, a.N, a.K, a.ldb, 64, BK));
-  if (a.out_dtype == EGOT2_F32) return pick_major<float>(a, bn, ma, mb, st);
-  return pick_major<bf16>(a, bn, ma, mb, st);
+  if (a.out_dtype == EGOT2_F32) return pick_major<float>(a, bn, ma, mb, kg, st);
+  return pick_major<bf16>(a, bn, ma, mb, kg, st);
 }
 
 }  // namespace egot2

@@ -1,0 +1,159 @@
+// head_fused.cu — the small classification heads in one kernel per direction (one CTA per clip):
+//   forward : mean over the clip's T tokens -> LayerNorm (gamma/beta, optional dropout) -> Linear(H -> n_out <= 32)
+//   backward: dlogits -> d(LN output) -> LayerNorm backward -> broadcast 1/T to every token of the clip,
+//             plus d(gamma, beta, W, b) accumulated with one atomic per (clip, element)
+// Replaces pool + LN + cast + GEMM (+ colsum + wgrad + dgrad + LN-bwd + pool-bwd): ~15 tiny launches -> 2.
+// HHI TTM head (2 logits) and HOI PNR / OSCC heads (16 / 2 logits; LayerNorm shared with the token LN).
+#include "ops.h"
+
+namespace egot2 {
+
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < NT / 32; ++i) t += red[i];
+  return t;
+}
+
+template <typename TT>
+__global__ void __launch_bounds__(NT) head_fwd_kernel(int T, int H, int n_out, const TT* __restrict__ x,
+                                                      const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                      const TT* __restrict__ W, const float* __restrict__ bias, float eps,
+                                                      float p_drop, uint64_t drop_key, float* __restrict__ pooled,
+                                                      float* __restrict__ stat, TT* __restrict__ g_out,
+                                                      float* __restrict__ logits) {
+  extern __shared__ float sm[];
+  float* ps = sm;            // pooled (H)
+  float* gs = sm + H;        // LN output (H)
+  __shared__ float red[NT / 32];
+  const int row = blockIdx.x;
+  const TT* xb = x + (size_t)row * T * H;
+  for (int c = threadIdx.x; c < H; c += NT) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += to_f32(xb[(size_t)t * H + c]);
+    s /= (float)T;
+    ps[c] = s;
+    pooled[(size_t)row * H + c] = s;
+  }
+  __syncthreads();
+  float part = 0.f;
+  for (int c = threadIdx.x; c < H; c += NT) part += ps[c];
+  const float mean = block_sum(part, red) / (float)H;
+  part = 0.f;
+  for (int c = threadIdx.x; c < H; c += NT) { const float d = ps[c] - mean; part += d * d; }
+  const float rstd = rsqrtf(block_sum(part, red) / (float)H + eps);
+  if (threadIdx.x == 0) { stat[2 * (size_t)row] = mean; stat[2 * (size_t)row + 1] = rstd; }
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (int c = threadIdx.x; c < H; c += NT) {
+    float g = (ps[c] - mean) * rstd * ln_g[c] + ln_b[c];
+    if (p_drop > 0.f) g *= drop_scale(drop_key, (uint64_t)row * H + c, p_drop, inv_keep);
+    const TT gr = from_f32<TT>(g);
+    g_out[(size_t)row * H + c] = gr;
+    gs[c] = to_f32(gr);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < n_out; j += NT / 32) {
+    float d = 0.f;
+    for (int c = lane; c < H; c += 32) d += gs[c] * to_f32(W[(size_t)j * H + c]);
+    d = warp_sum(d);
+    if (lane == 0) logits[(size_t)row * n_out + j] = d + bias[j];
+  }
+}
+
+template <typename TT>
+__global__ void __launch_bounds__(NT) head_bwd_kernel(int T, int H, int n_out, const float* __restrict__ dlogits,
+                                                      const float* __restrict__ pooled, const float* __restrict__ stat,
+                                                      const TT* __restrict__ g_saved, const float* __restrict__ ln_g,
+                                                      const TT* __restrict__ W, float p_drop, uint64_t drop_key,
+                                                      TT* __restrict__ dx, float* __restrict__ d_ln_g,
+                                                      float* __restrict__ d_ln_b, float* __restrict__ dW,
+                                                      float* __restrict__ db) {
+  extern __shared__ float sm[];
+  float* dgs = sm;           // d(LN output) (H)
+  float* dps = sm + H;       // d(pooled) (H)
+  __shared__ float dl[32];
+  __shared__ float red[NT / 32];
+  const int row = blockIdx.x;
+  if (threadIdx.x < n_out) {
+    const float v = dlogits[(size_t)row * n_out + threadIdx.x];
+    dl[threadIdx.x] = v;
+    if (db) atomicAdd(db + threadIdx.x, v);
+  }
+  __syncthreads();
+  const float mean = stat[2 * (size_t)row], rstd = stat[2 * (size_t)row + 1];
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = threadIdx.x; c < H; c += NT) {
+    float dg = 0.f;
+    const float gsv = to_f32(g_saved[(size_t)row * H + c]);
+    for (int j = 0; j < n_out; ++j) {
+      dg += dl[j] * to_f32(W[(size_t)j * H + c]);
+      if (dW) atomicAdd(dW + (size_t)j * H + c, dl[j] * gsv);
+    }
+    if (p_drop > 0.f) dg *= drop_scale(drop_key, (uint64_t)row * H + c, p_drop, inv_keep);
+    const float xh = (pooled[(size_t)row * H + c] - mean) * rstd;
+    if (d_ln_g) { atomicAdd(d_ln_g + c, dg * xh); atomicAdd(d_ln_b + c, dg); }
+    const float dyg = dg * ln_g[c];
+    dgs[c] = dyg;
+    s1 += dyg;
+    s2 += dyg * xh;
+  }
+  s1 = block_sum(s1, red) / (float)H;
+  s2 = block_sum(s2, red) / (float)H;
+  const float invT = 1.f / (float)T;
+  for (int c = threadIdx.x; c < H; c += NT) {
+    const float xh = (pooled[(size_t)row * H + c] - mean) * rstd;
+    dps[c] = rstd * (dgs[c] - s1 - xh * s2) * invT;
+  }
+  __syncthreads();
+  TT* dxb = dx + (size_t)row * T * H;
+  for (int e = threadIdx.x; e < T * H; e += NT) dxb[e] = from_f32<TT>(dps[e % H]);
+}
+
+}  // namespace
+
+bool head_fused_supported(const egot2_head_desc& d) {
+  return d.pool && d.use_ln && d.n_out >= 1 && d.n_out <= 32 && d.H % 32 == 0 && d.H <= 2048 &&
+         (d.loss == EGOT2_LOSS_NONE || d.loss == EGOT2_LOSS_CE || d.loss == EGOT2_LOSS_BCE_SIGMOID);
+}
+
+int head_fused_fwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& out, cudaStream_t st) {
+  const float ph = d.training ? d.p_head : 0.f;
+  const uint64_t key = site_key(d.seed, SITE_HEAD, 0);
+  const size_t smem = 2 * (size_t)d.H * sizeof(float);
+  if (d.dtype == EGOT2_F32)
+    head_fwd_kernel<float><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, (const float*)in.x, in.ln_g, in.ln_b, (const float*)in.w,
+                                                  in.b, d.ln_eps, ph, key, out.pooled, out.stat, (float*)out.g, out.logits);
+  else
+    head_fwd_kernel<bf16><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, (const bf16*)in.x, in.ln_g, in.ln_b, (const bf16*)in.w,
+                                                 in.b, d.ln_eps, ph, key, out.pooled, out.stat, (bf16*)out.g, out.logits);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
+int head_fused_bwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& saved, const float* dlogits,
+                   void* dx, const egot2_head_grads& g, cudaStream_t st) {
+  const float ph = d.training ? d.p_head : 0.f;
+  const uint64_t key = site_key(d.seed, SITE_HEAD, 0);
+  const size_t smem = 2 * (size_t)d.H * sizeof(float);
+  if (d.dtype == EGOT2_F32)
+    head_bwd_kernel<float><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, dlogits, saved.pooled, saved.stat, (const float*)saved.g,
+                                                  in.ln_g, (const float*)in.w, ph, key, (float*)dx, g.ln_g, g.ln_b, g.w, g.b);
+  else
+    head_bwd_kernel<bf16><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, dlogits, saved.pooled, saved.stat, (const bf16*)saved.g,
+                                                 in.ln_g, (const bf16*)in.w, ph, key, (bf16*)dx, g.ln_g, g.ln_b, g.w, g.b);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace egot2

@@ -85,6 +85,12 @@ int cast_f32_to(int dtype, const float* src, void* dst, size_t n, cudaStream_t s
 int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t st);
 int zero_f32(float* p, size_t n, cudaStream_t st);
 
+// fused small heads (head_fused.cu): pool + LN + Linear(n_out <= 32) in one kernel per direction
+bool head_fused_supported(const egot2_head_desc& d);
+int head_fused_fwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& out, cudaStream_t st);
+int head_fused_bwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& saved, const float* dlogits,
+                   void* dx, const egot2_head_grads& g, cudaStream_t st);
+
 // losses on fp32 logits (rows, n_out)
 int loss_fwd(const egot2_head_desc& d, int rows, const float* logits, const int64_t* labels, const float* class_weight,
              float* row_loss, float* loss, int32_t* argmax, cudaStream_t st);
