@@ -63,6 +63,11 @@ int gemm(const GemmArgs& a, cudaStream_t st) {
   return gemm_simt(a, st);
 }
 
+static bool env_is(const char* name, const char* value) {
+  const char* e = getenv(name);
+  return e && strcmp(e, value) == 0;
+}
+
 static bool force_simt_attention() {   // diagnostics: EGOT2_ATTN=simt
   static int mode = -1;
   if (mode < 0) { const char* e = getenv("EGOT2_ATTN"); mode = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
@@ -325,6 +330,10 @@ extern "C" int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_la
     l.eps = d->ln_eps; l.y = s->x1; l.stat = s->stat1;
     EGOT2_TRY(layernorm_fwd(l, st));
   }
+  // 5-7 fused (bf16, H = 128): the hidden activation stays on chip between the two GEMMs
+  if (ffn_fused_supported(d->dtype, H, FF) && !env_is("EGOT2_FFN", "unfused"))
+    return ffn_fused_fwd(M, FF, s->x1, p->lin1_w, p->lin1_b, p->lin2_w, p->lin2_b, p->norm2_g, p->norm2_b, d->ln_eps,
+                         s->hid, s->y2, s->stat2, x_out, pd, site_key(d->seed, SITE_FFN, L), site_key(d->seed, SITE_DROP2, L), st);
   // 5. hid = dropout(relu(x1 . W1^T + b1))
   {
     GemmArgs g; g.M = M; g.N = FF; g.K = H; g.A = s->x1; g.lda = H; g.B = p->lin1_w; g.ldb = H; g.trans_b = 1;

@@ -80,6 +80,31 @@ __device__ __forceinline__ void gemm_pv(float (&o)[Tile<DH>::ND][4], const uint3
   }
 }
 
+// one 16-column block kb of gemm_rc: acc2 (16 x 16) = A(16 x DH) . Bs[kb*16 .. kb*16+15]^T
+template <int DH>
+__device__ __forceinline__ void gemm_rc_kb(float (&acc2)[2][4], const uint32_t (&a)[Tile<DH>::KS][4], uint32_t sB, int kb) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int ks = 0; ks < Tile<DH>::KS; ++ks) {
+    uint32_t b[4];
+    ldsm_x4(sB + (uint32_t)(((kb * 16 + (lane & 7) + 8 * (lane >> 4)) * Tile<DH>::LD + ks * 16 + 8 * ((lane >> 3) & 1)) * 2), b);
+    mma16816(acc2[0], a[ks], b[0], b[1]);
+    mma16816(acc2[1], a[ks], b[2], b[3]);
+  }
+}
+// one reduction block kb of gemm_pv: o += P_kb(16 x 16) . Bs[kb*16 .. kb*16+15]
+template <int DH>
+__device__ __forceinline__ void gemm_pv_kb(float (&o)[Tile<DH>::ND][4], const uint32_t (&p)[4], uint32_t sB, int kb) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d2 = 0; d2 < Tile<DH>::ND / 2; ++d2) {
+    uint32_t b[4];
+    ldsm_x4_t(sB + (uint32_t)(((kb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * Tile<DH>::LD + d2 * 16 + 8 * (lane >> 4)) * 2), b);
+    mma16816(o[2 * d2], p, b[0], b[1]);
+    mma16816(o[2 * d2 + 1], p, b[2], b[3]);
+  }
+}
+
 // stage rows [0,T) x DH of a strided global matrix into smem [Tpad][LD]; rows >= T are zero
 template <int DH>
 __device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, int ld_src, int T, int Tpad) {
@@ -217,37 +242,39 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
   const uint32_t uV = (uint32_t)__cvta_generic_to_shared(sV), udO = (uint32_t)__cvta_generic_to_shared(sdO);
   bf16* dq = dqkv + (size_t)b * T * 3 * H + h * DH;
 
-  // ---------------- pass 1: rows = queries -> dQ
+  // ---------------- pass 1: rows = queries -> dQ   (streamed over 16-key blocks: nothing T-wide stays in registers)
   {
     uint32_t a1[Tile<DH>::KS][4], a2[Tile<DH>::KS][4];
     load_a<DH>(uQ, r0, a1);
     load_a<DH>(udO, r0, a2);
-    float s[NT][4], dp[NT][4];
-#pragma unroll
-    for (int i = 0; i < NT; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
-    gemm_rc<DH, NT>(s, a1, uK);
-    gemm_rc<DH, NT>(dp, a2, uV);
     const float la = sL[ra] * l2e, lb = sL[rb] * l2e, da = sD[ra], db = sD[rb];
-    uint32_t ds[NT / 2][4];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const int c = nt * 8 + 2 * (lane & 3);
-      float p0 = c < T ? exp2f(s[nt][0] * sc2 - la) : 0.f, p1 = c + 1 < T ? exp2f(s[nt][1] * sc2 - la) : 0.f;
-      float p2 = c < T ? exp2f(s[nt][2] * sc2 - lb) : 0.f, p3 = c + 1 < T ? exp2f(s[nt][3] * sc2 - lb) : 0.f;
-      float g0 = dp[nt][0], g1 = dp[nt][1], g2 = dp[nt][2], g3 = dp[nt][3];
-      if (p_drop > 0.f) {
-        g0 *= drop_scale(drop_key, ((uint64_t)bh * T + ra) * T + c, p_drop, inv_keep);
-        g1 *= drop_scale(drop_key, ((uint64_t)bh * T + ra) * T + c + 1, p_drop, inv_keep);
-        g2 *= drop_scale(drop_key, ((uint64_t)bh * T + rb) * T + c, p_drop, inv_keep);
-        g3 *= drop_scale(drop_key, ((uint64_t)bh * T + rb) * T + c + 1, p_drop, inv_keep);
-      }
-      ds[nt >> 1][(nt & 1) * 2] = pack_bf16(p0 * (g0 - da), p1 * (g1 - da));
-      ds[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2 * (g2 - db), p3 * (g3 - db));
-    }
     float o[Tile<DH>::ND][4];
 #pragma unroll
     for (int i = 0; i < Tile<DH>::ND; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-    gemm_pv<DH, NT>(o, ds, uK);
+#pragma unroll
+    for (int kb = 0; kb < TK16; ++kb) {
+      if (kb * 16 >= T) break;
+      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      gemm_rc_kb<DH>(s, a1, uK, kb);
+      gemm_rc_kb<DH>(dp, a2, uV, kb);
+      uint32_t ds[4];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int c = kb * 16 + h2 * 8 + 2 * (lane & 3);
+        float p0 = c < T ? exp2f(s[h2][0] * sc2 - la) : 0.f, p1 = c + 1 < T ? exp2f(s[h2][1] * sc2 - la) : 0.f;
+        float p2 = c < T ? exp2f(s[h2][2] * sc2 - lb) : 0.f, p3 = c + 1 < T ? exp2f(s[h2][3] * sc2 - lb) : 0.f;
+        float g0 = dp[h2][0], g1 = dp[h2][1], g2 = dp[h2][2], g3 = dp[h2][3];
+        if (p_drop > 0.f) {
+          g0 *= drop_scale(drop_key, ((uint64_t)bh * T + ra) * T + c, p_drop, inv_keep);
+          g1 *= drop_scale(drop_key, ((uint64_t)bh * T + ra) * T + c + 1, p_drop, inv_keep);
+          g2 *= drop_scale(drop_key, ((uint64_t)bh * T + rb) * T + c, p_drop, inv_keep);
+          g3 *= drop_scale(drop_key, ((uint64_t)bh * T + rb) * T + c + 1, p_drop, inv_keep);
+        }
+        ds[h2 * 2] = pack_bf16(p0 * (g0 - da), p1 * (g1 - da));
+        ds[h2 * 2 + 1] = pack_bf16(p2 * (g2 - db), p3 * (g3 - db));
+      }
+      gemm_pv_kb<DH>(o, ds, uK, kb);
+    }
 #pragma unroll
     for (int nd = 0; nd < Tile<DH>::ND; ++nd) {
       const int c = nd * 8 + 2 * (lane & 3);
@@ -255,40 +282,42 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
       if (rb < T) *reinterpret_cast<uint32_t*>(dq + (size_t)rb * 3 * H + c) = pack_bf16(o[nd][2] * scn, o[nd][3] * scn);
     }
   }
-  // ---------------- pass 2: rows = keys -> dK, dV   (tile element (r, c) = (key r, query c))
+  // ---------------- pass 2: rows = keys -> dK, dV   (tile element (r, c) = (key r, query c), streamed over query blocks)
   {
     uint32_t a1[Tile<DH>::KS][4], a2[Tile<DH>::KS][4];
     load_a<DH>(uK, r0, a1);
     load_a<DH>(uV, r0, a2);
-    float s[NT][4], dp[NT][4];
-#pragma unroll
-    for (int i = 0; i < NT; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
-    gemm_rc<DH, NT>(s, a1, uQ);
-    gemm_rc<DH, NT>(dp, a2, udO);
-    uint32_t pf[NT / 2][4], ds[NT / 2][4];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const int c = nt * 8 + 2 * (lane & 3);
-      const float l0 = sL[c] * l2e, l1 = sL[c + 1] * l2e, d0 = sD[c], d1 = sD[c + 1];
-      float p0 = c < T ? exp2f(s[nt][0] * sc2 - l0) : 0.f, p1 = c + 1 < T ? exp2f(s[nt][1] * sc2 - l1) : 0.f;
-      float p2 = c < T ? exp2f(s[nt][2] * sc2 - l0) : 0.f, p3 = c + 1 < T ? exp2f(s[nt][3] * sc2 - l1) : 0.f;
-      float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
-      if (p_drop > 0.f) {
-        m0 = drop_scale(drop_key, ((uint64_t)bh * T + c) * T + ra, p_drop, inv_keep);
-        m1 = drop_scale(drop_key, ((uint64_t)bh * T + c + 1) * T + ra, p_drop, inv_keep);
-        m2 = drop_scale(drop_key, ((uint64_t)bh * T + c) * T + rb, p_drop, inv_keep);
-        m3 = drop_scale(drop_key, ((uint64_t)bh * T + c + 1) * T + rb, p_drop, inv_keep);
-      }
-      pf[nt >> 1][(nt & 1) * 2] = pack_bf16(p0 * m0, p1 * m1);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2 * m2, p3 * m3);
-      ds[nt >> 1][(nt & 1) * 2] = pack_bf16(p0 * (dp[nt][0] * m0 - d0), p1 * (dp[nt][1] * m1 - d1));
-      ds[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2 * (dp[nt][2] * m2 - d0), p3 * (dp[nt][3] * m3 - d1));
-    }
     float ov[Tile<DH>::ND][4], ok[Tile<DH>::ND][4];
 #pragma unroll
     for (int i = 0; i < Tile<DH>::ND; ++i) { ov[i][0] = ov[i][1] = ov[i][2] = ov[i][3] = 0.f; ok[i][0] = ok[i][1] = ok[i][2] = ok[i][3] = 0.f; }
-    gemm_pv<DH, NT>(ov, pf, udO);
-    gemm_pv<DH, NT>(ok, ds, uQ);
+#pragma unroll
+    for (int kb = 0; kb < TK16; ++kb) {
+      if (kb * 16 >= T) break;
+      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      gemm_rc_kb<DH>(s, a1, uQ, kb);
+      gemm_rc_kb<DH>(dp, a2, udO, kb);
+      uint32_t pf[4], ds[4];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int c = kb * 16 + h2 * 8 + 2 * (lane & 3);
+        const float l0 = sL[c] * l2e, l1 = sL[c + 1] * l2e, d0 = sD[c], d1 = sD[c + 1];
+        float p0 = c < T ? exp2f(s[h2][0] * sc2 - l0) : 0.f, p1 = c + 1 < T ? exp2f(s[h2][1] * sc2 - l1) : 0.f;
+        float p2 = c < T ? exp2f(s[h2][2] * sc2 - l0) : 0.f, p3 = c + 1 < T ? exp2f(s[h2][3] * sc2 - l1) : 0.f;
+        float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
+        if (p_drop > 0.f) {
+          m0 = drop_scale(drop_key, ((uint64_t)bh * T + c) * T + ra, p_drop, inv_keep);
+          m1 = drop_scale(drop_key, ((uint64_t)bh * T + c + 1) * T + ra, p_drop, inv_keep);
+          m2 = drop_scale(drop_key, ((uint64_t)bh * T + c) * T + rb, p_drop, inv_keep);
+          m3 = drop_scale(drop_key, ((uint64_t)bh * T + c + 1) * T + rb, p_drop, inv_keep);
+        }
+        pf[h2 * 2] = pack_bf16(p0 * m0, p1 * m1);
+        pf[h2 * 2 + 1] = pack_bf16(p2 * m2, p3 * m3);
+        ds[h2 * 2] = pack_bf16(p0 * (dp[h2][0] * m0 - d0), p1 * (dp[h2][1] * m1 - d1));
+        ds[h2 * 2 + 1] = pack_bf16(p2 * (dp[h2][2] * m2 - d0), p3 * (dp[h2][3] * m3 - d1));
+      }
+      gemm_pv_kb<DH>(ov, pf, udO, kb);
+      gemm_pv_kb<DH>(ok, ds, uQ, kb);
+    }
 #pragma unroll
     for (int nd = 0; nd < Tile<DH>::ND; ++nd) {
       const int c = nd * 8 + 2 * (lane & 3);

@@ -85,6 +85,12 @@ int cast_f32_to(int dtype, const float* src, void* dst, size_t n, cudaStream_t s
 int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t st);
 int zero_f32(float* p, size_t n, cudaStream_t st);
 
+// fused FFN block on tcgen05 (ffn_sm100.cu): x_out = LN2(x1 + drop2(drop(relu(x1 W1^T + b1)) W2^T + b2))
+bool ffn_fused_supported(int dtype, int H, int FF);
+int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1, const void* W2, const float* b2,
+                  const float* ln_g, const float* ln_b, float eps, void* hid, void* y2, float* stat2, void* x_out,
+                  float p_drop, uint64_t key_ffn, uint64_t key_drop2, cudaStream_t st);
+
 // fused small heads (head_fused.cu): pool + LN + Linear(n_out <= 32) in one kernel per direction
 bool head_fused_supported(const egot2_head_desc& d);
 int head_fused_fwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& out, cudaStream_t st);

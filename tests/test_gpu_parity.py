@@ -263,3 +263,32 @@ def test_attention_dropout_mask_is_exact(dtype, T, H, heads):
     t_out, t_g = (1e-4, 1e-3) if dtype == "fp32" else (1.5e-2, 3e-2)
     assert float((out.double() - ref.detach()).abs().max()) <= t_out * float(ref.abs().max())
     assert float((dqkv.double() - gref).abs().max()) <= t_g * float(gref.abs().max())
+
+
+@pytest.mark.parametrize("name", ["hhi3_h128_d30", "hoi_pnr_h128_l6"])
+def test_fused_ffn_matches_unfused_with_dropout(name, monkeypatch):
+    """The tcgen05 fused FFN (GEMM+ReLU+dropout+GEMM+residual+LN) must reproduce the unfused kernel sequence in
+    TRAIN mode too: same dropout masks (counter-based), same bf16 rounding points; only the fp32 accumulation
+    order differs."""
+    from egot2_b200.engine import TranslatorEngine
+    from oracle import translator_oracle as O
+    case = CASES[name]
+    sp = case.spec
+    sd, feats, labels, extra = case_inputs(case)
+    outs = {}
+    for mode in ("unfused", "fused"):
+        monkeypatch.setenv("EGOT2_FFN", mode)
+        eng = TranslatorEngine(sp, "cuda:0", "bf16")
+        eng.arena.load_state_dict(sd)
+        if sp.embed == "task_sinusoid":
+            eng.set_sinusoid(O.sinusoid_table(1000, sp.hidden))
+        gf = [feats[s.name].cuda().bfloat16() for s in sp.segments]
+        act = eng.forward(gf, training=True, seed=11)
+        torch.cuda.synchronize()
+        outs[mode] = {k: act.t[k].float().clone() for k in ("hid0", "y2_0", "x1", "out")}
+    for k in outs["fused"]:
+        a, b = outs["fused"][k], outs["unfused"][k]
+        scale = float(b.abs().max())
+        frac_zero_a, frac_zero_b = float((a == 0).float().mean()), float((b == 0).float().mean())
+        assert abs(frac_zero_a - frac_zero_b) < 2e-3, k              # same dropout pattern
+        assert float((a - b).abs().max()) <= 2e-2 * scale, k
