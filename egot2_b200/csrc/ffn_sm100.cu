@@ -56,9 +56,15 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   const uint32_t x_full = bars, w_full = bars + 8, w_empty = w_full + 8 * NST, a1_full = w_empty + 8 * NST,
                  a1_empty = a1_full + 16, h_full = a1_empty + 16, h_empty = h_full + 8, a2_full = h_empty + 8,
                  tmem_slot = a2_full + 8;
-  const uint32_t red_off = tmem_slot + 8;           // float red[2][128] for the LayerNorm row statistics
+  const uint32_t red_off = (tmem_slot + 8 + 15u) & ~15u;   // float red[2][128] for the LayerNorm row statistics (16 B aligned)
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));   // generic pointer to `base`
   float* red = reinterpret_cast<float*>(gen + (red_off - base));
+  // bias / LayerNorm vectors live in shared memory: every lane of an epilogue warp reads the same column values, so
+  // these are conflict-free broadcasts instead of a chain of dependent global loads on the per-chunk critical path
+  float* sVec = red + 256;                 // b2[128], ln_g[128], ln_b[128]
+  float* sB1 = sVec + 384;                 // b1[FF]
+  for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i];
+  for (int i = threadIdx.x; i < 128; i += NTHREADS) { sVec[i] = a.b2[i]; sVec[128 + i] = a.ln_g[i]; sVec[256 + i] = a.ln_b[i]; }
   const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,15 +144,17 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       mbar_wait(a1_full + 8 * bsel, (c >> 1) & 1);
       tc_fence_after();
       uint32_t packed[32];
+      uint32_t rr0[32], rr1[32];
+      tmem_ld_32x32(tmem + lane_addr + bsel * 128 + ch * 64, rr0);
+      tmem_ld_32x32(tmem + lane_addr + bsel * 128 + ch * 64 + 32, rr1);
+      tmem_ld_wait();
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
-        uint32_t rr[32];
-        tmem_ld_32x32(tmem + lane_addr + bsel * 128 + ch * 64 + h2 * 32, rr);
-        tmem_ld_wait();
+        const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
         const int n0 = c * FC + ch * 64 + h2 * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b1 + n0 + j));
+          const float4 b4 = *reinterpret_cast<const float4*>(sB1 + n0 + j);
           float v0 = fmaxf(__uint_as_float(rr[j]) + b4.x, 0.f), v1 = fmaxf(__uint_as_float(rr[j + 1]) + b4.y, 0.f);
           float v2 = fmaxf(__uint_as_float(rr[j + 2]) + b4.z, 0.f), v3 = fmaxf(__uint_as_float(rr[j + 3]) + b4.w, 0.f);
           if (a.p_drop > 0.f) {
@@ -204,7 +212,7 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int j = j8 * 8 + 2 * k;
-        float v0 = y[j] + __ldg(a.b2 + nb + j), v1 = y[j + 1] + __ldg(a.b2 + nb + j + 1);
+        float v0 = y[j] + sVec[nb + j], v1 = y[j + 1] + sVec[nb + j + 1];
         if (a.p_drop > 0.f) {
           v0 *= drop_scale(a.key_drop2, (uint64_t)m * H + nb + j, a.p_drop, inv_keep);
           v1 *= drop_scale(a.key_drop2, (uint64_t)m * H + nb + j + 1, a.p_drop, inv_keep);
@@ -240,8 +248,8 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           const int j = j8 * 8 + 2 * k;
           __nv_bfloat162 t = __floats2bfloat162_rn(y[j], y[j + 1]);
           yy[k] = *reinterpret_cast<uint32_t*>(&t);
-          const float o0 = (y[j] - mean) * rstd * __ldg(a.ln_g + nb + j) + __ldg(a.ln_b + nb + j);
-          const float o1 = (y[j + 1] - mean) * rstd * __ldg(a.ln_g + nb + j + 1) + __ldg(a.ln_b + nb + j + 1);
+          const float o0 = (y[j] - mean) * rstd * sVec[128 + nb + j] + sVec[256 + nb + j];
+          const float o1 = (y[j + 1] - mean) * rstd * sVec[128 + nb + j + 1] + sVec[256 + nb + j + 1];
           __nv_bfloat162 u = __floats2bfloat162_rn(o0, o1);
           oo[k] = *reinterpret_cast<uint32_t*>(&u);
         }
@@ -307,11 +315,12 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
   a.M = M; a.FF = FF; a.b1 = b1; a.b2 = b2; a.ln_g = ln_g; a.ln_b = ln_b; a.eps = eps;
   a.hid = (bf16*)hid; a.y2 = (bf16*)y2; a.stat2 = stat2; a.x_out = (bf16*)x_out;
   a.p_drop = p_drop; a.key_ffn = key_ffn; a.key_drop2 = key_drop2;
-  constexpr size_t smem = 1024 + (size_t)TILE * (1 + 2 * NST + 1) + 256 + 2 * 128 * 4;
-  static bool set = false;
-  if (!set) {
+  const size_t smem = 1024 + (size_t)TILE * (1 + 2 * NST + 1) + 256 + (256 + 384 + (size_t)FF) * 4;
+  EGOT2_CHECK(smem <= 227 * 1024, "ffn_fused_fwd: FF=%d does not fit the bias stage in shared memory", FF);
+  static size_t set_for = 0;
+  if (set_for < smem) {
     EGOT2_CUDA(cudaFuncSetAttribute(ffn_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set = true;
+    set_for = smem;
   }
   ffn_fwd_sm100_kernel<<<(M + BM - 1) / BM, NTHREADS, smem, st>>>(tx, tw1, tw2, a);
   EGOT2_LAUNCH_CHECK();

@@ -103,6 +103,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const uint32_t bars = sB + STAGES * B_BYTES;                            // full[STAGES], empty[STAGES], tmem_full
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES;
   const uint32_t tmem_slot = tmem_full + 8;
+  const uint32_t bias_off = (tmem_slot + 8 + 15u) & ~15u;        // float sbias[BN]: this tile's bias columns (broadcast reads in the epilogue)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,6 +120,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  float* sbias = reinterpret_cast<float*>(smem_raw + (bias_off - smem_u32(smem_raw)));
+  if (warp >= 2) {
+    const bool has_bias = e.bias != nullptr && blockIdx.z == 0;
+    for (int i = threadIdx.x - 64; i < BN; i += NTHREADS - 64)
+      sbias[i] = (has_bias && n0 + i < e.N) ? __ldg(e.bias + n0 + i) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -197,7 +204,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const float* bias = first_split ? e.bias : nullptr;
     const TO* mask_row = e.mask ? (const TO*)e.mask + (long long)(row_ok ? m : 0) * e.ldm : nullptr;
     const TO* res_row = (e.residual && first_split) ? (const TO*)e.residual + (long long)(row_ok ? m : 0) * e.ldr : nullptr;
-    const bool vec_ok = aligned16(crow_ptr) && aligned16(mask_row) && aligned16(res_row) && aligned16(bias);
+    const bool vec_ok = aligned16(crow_ptr) && aligned16(mask_row) && aligned16(res_row);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -217,7 +224,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         if (bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
+            const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);
             v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
           }
         }
@@ -261,7 +268,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           const int n = nb + j;
           if (n >= e.N) continue;
           float x = v[j];
-          if (bias) x += __ldg(bias + n);
+          if (bias) x += sbias[c0 + j];
           if (e.relu) x = fmaxf(x, 0.f);
           if (mask_row) x = to_f32(mask_row[n]) > 0.f ? x * e.mask_scale : 0.f;
           if (e.p_drop > 0.f) x *= drop_scale(e.drop_key, (uint64_t)m * e.N + n, e.p_drop, inv_keep);
@@ -342,7 +349,7 @@ struct KGroup { int on = 0, g = 1, dblocks = 1, kb_total = 0; };
 template <int BN, bool A_MN, bool B_MN, typename TO>
 int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, const KGroup& kg, cudaStream_t st) {
   constexpr int STAGES = TileCfg<BN>::STAGES;
-  constexpr size_t smem = 1024 + STAGES * (BM * BK * 2 + BN * BK * 2) + 16 * STAGES + 64;
+  constexpr size_t smem = 1024 + STAGES * (BM * BK * 2 + BN * BK * 2) + 16 * STAGES + 64 + BN * 4;
   static bool attr_set = false;
   auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, TO>;
   if (!attr_set) {
