@@ -13,7 +13,8 @@ Lines printed by rank 0 (ONE JSON line):
   value     whole-job clips/s, features already resident in HBM (rotating pool larger than L2), CUDA-event timed,
             max over ranks;
   e2e       same step driven from pinned HOST buffers (H2D of features+labels and D2H of the loss inside the timed region);
-  roofline  the dominant kernel of the step timed alone with CUDA events on its launch stream;
+  roofline  the dominant kernel of the step (largest share of the summed kernel time), timed by CUDA events that the
+            library records around each launch on the launch stream during a pass of eager steps after the timed region;
   cpu_baseline  the CPU oracle (torch restatement of the reference translator) on this box's host cores.
 `--impl reference` times that CPU implementation as the reference arm.
 """
@@ -53,6 +54,22 @@ def load_peaks():
         return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"],
                     source="measured")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def load_ncu_traffic(tag: str):
+    """dram bytes (read+write) per launch of the dominant kernel, from the committed `ncu --set full` summary
+    (profiles/ncu_traffic.json: {launcher-tag prefix: bytes}); None when that kernel has no capture yet."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        table = json.load(open(p))
+    except Exception:
+        return None
+    for k, v in table.items():
+        if not k.startswith("_") and tag.startswith(k):
+            return v
+    return None
 
 
 class ClockSampler:
@@ -269,7 +286,13 @@ def main():
 
     # ---- roofline of the dominant kernel (timed alone, CUDA events on its launch stream)
     peaks = load_peaks()
-    roof = dominant_kernel_roofline(spec, B, seg, args.dtype, dev, peaks)
+    es = 2 if args.dtype == "bf16" else 4
+    prof_steps = max(3, min(args.steps, 10))
+    rows = profile_step_launchers(tr, [(fe, la) for fe, la in pool], n_pool, prof_steps, es)
+    roof = dominant_kernel_roofline(rows, prof_steps, peaks, es, ms_total / args.steps * 1e3)
+    traffic = load_ncu_traffic(roof["kernel"])
+    if traffic is not None:
+        roof["traffic"] = traffic
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     cpu = None
@@ -305,49 +328,92 @@ def main():
         torch.distributed.destroy_process_group()
 
 
-def dominant_kernel_roofline(spec, B, seg, dtype, dev, peaks):
-    """Time the dominant kernel of the step — the FFN linear1 GEMM(+bias+ReLU), the largest single GEMM of the
-    layer — alone, through the op-level C-ABI entry point, on operands larger than L2."""
-    import ctypes as C
-    from egot2_b200 import _lib as L
-    from egot2_b200.engine import _dt, _stream
-    lib = L.load()
-    M, H, FF = B * sum(seg), spec.hidden, spec.ffn
-    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
-    es = 2 if dtype == "bf16" else 4
-    n_rot = max(2, -(-2 * L2_BYTES // (M * (H + FF) * es)))
-    xs = [torch.randn(M, H, device=dev).to(tdt) for _ in range(n_rot)]
-    outs = [torch.empty(M, FF, device=dev, dtype=tdt) for _ in range(n_rot)]
-    W = (torch.randn(FF, H, device=dev) / H ** 0.5).to(tdt)
-    bias = torch.zeros(FF, device=dev)
-    st = _stream()
+def launcher_cost(tag: str, es: int):
+    """Algorithmic (flops, bytes) of ONE launch of the launcher `tag` (the tags carry the problem shape).
+    bytes = operands read once + results written once; es = bytes per activation element.  None = not modelled."""
+    import re
+    def ints(pat):
+        m = re.search(pat, tag)
+        return [int(x) for x in m.groups()] if m else None
+    if tag.startswith("ffn_fwd_sm100"):
+        M, FF = ints(r"M(\d+) H128 FF(\d+)")
+        H = 128          # x1 in, W1+W2, hid saved for backward, y2 + x_out out
+        return 4.0 * M * H * FF, (M * H + 2 * H * FF + M * FF + 2 * M * H) * es
+    if tag.startswith("ffn_bwd_sm100"):
+        M, FF = ints(r"M(\d+) H128 FF(\d+)")
+        H = 128          # dX GEMMs (2) + dW GEMMs (2); reads d2, x1, hid, W1, W2; writes d3 + fp32 dW1/dW2
+        return 8.0 * M * H * FF, (3 * M * H + M * FF + 2 * H * FF) * es + 2 * H * FF * 4
+    if tag.startswith("gemm_"):
+        M, N, K = ints(r"M(\d+) N(\d+) K(\d+)")
+        out_es = 4 if ",f32>" in tag or "<f32>" in tag else es
+        extra = M * N * es if ("+mask" in tag or "+res" in tag) else 0
+        return 2.0 * M * N * K, (M * K + N * K) * es + M * N * out_es + extra
+    if tag.startswith("attn_"):
+        B, T, H = ints(r"B(\d+) T(\d+) H(\d+)")
+        if "_fwd" in tag:      # QK^T + PV ; reads qkv, writes out
+            return 4.0 * B * T * T * H, B * T * 4 * H * es
+        return 10.0 * B * T * T * H, B * T * 8 * H * es      # S, dP, dV, dQ, dK ; reads qkv,out,dout, writes dqkv
+    m = ints(r"^ln_(?:fwd|bwd) rows(\d+) H(\d+)")
+    if m:
+        rows, H = m
+        return 8.0 * rows * H, rows * H * es * (2 if tag.startswith("ln_fwd") else 3)
+    m = ints(r"^colsum M(\d+) N(\d+)")
+    if m:
+        return float(m[0] * m[1]), m[0] * m[1] * es
+    m = ints(r"^dropout_inplace n(\d+)")
+    if m:
+        return float(m[0]), 2 * m[0] * es
+    return None
 
-    def launch(i):
-        L.call("egot2_gemm", _dt(dtype), M, FF, H, xs[i % n_rot].data_ptr(), 0, W.data_ptr(), 1, bias.data_ptr(), 1,
-               outs[i % n_rot].data_ptr(), 0, 0, st)
-    for i in range(5):
-        launch(i)
-    torch.cuda.synchronize(dev)
-    iters = 40
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        launch(i)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    sec = e0.elapsed_time(e1) * 1e-3 / iters
-    flops = 2.0 * M * H * FF
-    bytes_alg = (M * H + FF * H + M * FF) * es
-    ai = flops / bytes_alg
-    ridge = peaks["bf16_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
-    if dtype == "bf16" and ai >= ridge:
-        bound, achieved, peak, unit = "tensor", flops / sec / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+
+def profile_step_launchers(tr, pool, n_pool, steps, es):
+    """Per-launcher CUDA-event timing of `steps` eager (un-graphed) training steps, through the library's own
+    egot2_prof_* hooks: every launcher brackets its kernel(s) with events on the launch stream."""
+    from egot2_b200 import _lib as L
+    keep, keep_world = tr.use_graphs, tr.world
+    tr.use_graphs, tr.world = False, 1          # rank 0 profiles alone: no collective in this pass
+    for i in range(2):
+        tr.train_step(*pool[i % n_pool])
+    torch.cuda.synchronize()
+    L.prof_enable(True)
+    for i in range(steps):
+        tr.train_step(*pool[(2 + i) % n_pool])
+    torch.cuda.synchronize()
+    rows = L.prof_report()
+    L.prof_enable(False)
+    tr.use_graphs, tr.world = keep, keep_world
+    return rows
+
+
+def dominant_kernel_roofline(rows, steps, peaks, es, step_us_graph):
+    """rows: [(tag, launches, total_us)] from the profiled pass.  The dominant launcher = the largest share of the
+    summed kernel time; its achieved rate = algorithmic flops|bytes of one launch / its mean event-timed duration."""
+    tot = sum(r[2] for r in rows) or 1.0
+    ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    breakdown = []
+    for tag, n, us in rows[:8]:
+        c = launcher_cost(tag, es)
+        ent = {"launcher": tag, "launches_per_step": n / steps, "us_per_step": us / steps, "share": us / tot}
+        if c:
+            f, b = c
+            ent["tflops"] = f * n / (us * 1e-6) / 1e12
+            ent["gbs"] = b * n / (us * 1e-6) / 1e9
+        breakdown.append(ent)
+    tag, n, us = next(r for r in rows if launcher_cost(r[0], es))
+    flops, nbytes = launcher_cost(tag, es)
+    sec = us * 1e-6 / n
+    ai = flops / nbytes
+    # inside a long step the sustained tensor figure is the fair ceiling (MEASURED_PEAKS.json: burst vs sustained)
+    if es == 2 and ai >= ridge:
+        bound, achieved, peak, unit = "tensor", flops / sec / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
     else:
-        bound, achieved, peak, unit = "hbm", bytes_alg / sec / 1e9, peaks["hbm_gbs"], "GB/s"
-    return {"kernel": "ffn.linear1 GEMM+bias+ReLU (M=%d,N=%d,K=%d) via egot2_gemm" % (M, FF, H), "bound": bound,
-            "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
-            "us_per_launch": sec * 1e6, "arith_intensity_flop_per_byte": ai, "peak_source": peaks["source"] + " (burst)",
-            "impl": lib.egot2_version().decode()}
+        bound, achieved, peak, unit = "hbm", nbytes / sec / 1e9, peaks["hbm_gbs"], "GB/s"
+    return {"kernel": tag, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+            "traffic": None, "us_per_launch": sec * 1e6, "launches_per_step": n / steps, "share_of_step": us / tot,
+            "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": nbytes,
+            "arith_intensity_flop_per_byte": ai, "peak_source": peaks["source"] + " (sustained, timed inside the step)",
+            "timing": "CUDA events recorded by the library around the launch, on the launch stream, %d eager steps" % steps,
+            "sum_kernel_us_per_step": tot / steps, "graph_step_us": step_us_graph, "breakdown": breakdown}
 
 
 if __name__ == "__main__":

@@ -86,6 +86,8 @@ SIGNATURES = {
     "egot2_last_error": (C.c_char_p, []),
     "egot2_sm_count": (C.c_int, []),
     "egot2_launch_count": (C.c_uint64, []),
+    "egot2_prof_enable": (C.c_int, [C.c_int]),
+    "egot2_prof_report": (C.c_int, [C.c_char_p, sz]),
     "egot2_embed_workspace_bytes": (sz, [P(EmbedDesc), C.c_int]),
     "egot2_embed_fwd": (C.c_int, [P(EmbedDesc), P(EmbedIn), P(EmbedOut), vp, sz, vp]),
     "egot2_embed_bwd": (C.c_int, [P(EmbedDesc), P(EmbedIn), P(EmbedOut), vp, P(EmbedGrads), vp, sz, vp]),
@@ -150,3 +152,18 @@ def check(rc: int, what: str = ""):
 def call(name: str, *args):
     """Call an int-returning entry point and raise Egot2Error on failure."""
     check(getattr(load(), name)(*args), name)
+
+
+def prof_enable(on: bool = True):
+    check(load().egot2_prof_enable(1 if on else 0), "egot2_prof_enable")
+
+
+def prof_report():
+    """[(launcher tag, launches, total_us)] recorded since prof_enable(True), sorted by total time."""
+    buf = C.create_string_buffer(1 << 20)
+    check(load().egot2_prof_report(buf, len(buf)), "egot2_prof_report")
+    rows = []
+    for line in buf.value.decode().splitlines():
+        tag, n, us = line.split("\t")
+        rows.append((tag, int(n), float(us)))
+    return sorted(rows, key=lambda r: -r[2])

@@ -42,6 +42,32 @@ int suggest_split_k(int M, int N, int K) {
   return (int)want;
 }
 
+// ---------------------------------------------------------------- launcher timing (CUDA events on the launch stream)
+namespace {
+struct ProfRec { char tag[96]; cudaEvent_t e0, e1; };
+constexpr int kProfMax = 16384;
+ProfRec* g_prof = nullptr;
+int g_prof_n = 0;
+bool g_prof_on = false;
+}  // namespace
+bool prof_enabled() { return g_prof_on; }
+ProfScope::ProfScope(cudaStream_t stream, const char* fmt, ...) : st(stream), slot(-1) {
+  if (!g_prof_on || g_prof_n >= kProfMax) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  ProfRec& r = g_prof[g_prof_n];
+  if (!r.e0) { if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return; }
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(r.tag, sizeof(r.tag), fmt, ap);
+  va_end(ap);
+  slot = g_prof_n++;
+  cudaEventRecord(r.e0, st);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
+}
+
 static thread_local const char* g_gemm_impl = "none";
 const char* gemm_last_impl() { return g_gemm_impl; }
 
@@ -122,6 +148,41 @@ extern "C" const char* egot2_version(void) { return "egot2-b200 0.1 (sm_100a)"; 
 extern "C" const char* egot2_last_error(void) { return g_err; }
 extern "C" int egot2_sm_count(void) { return sm_count(); }
 extern "C" uint64_t egot2_launch_count(void) { return g_launch_count; }
+
+extern "C" int egot2_prof_enable(int on) {
+  if (on && !g_prof) {
+    g_prof = (ProfRec*)calloc(kProfMax, sizeof(ProfRec));
+    EGOT2_CHECK(g_prof != nullptr, "prof: out of host memory");
+  }
+  g_prof_on = on != 0;
+  if (on) g_prof_n = 0;
+  return 0;
+}
+// Text report, one line per launcher tag: "<tag>\t<launches>\t<total_us>\n" (synchronises the recorded events).
+extern "C" int egot2_prof_report(char* buf, size_t buf_bytes) {
+  EGOT2_CHECK(buf && buf_bytes > 0, "prof_report: no buffer");
+  struct Agg { const char* tag; int n; double us; };
+  Agg* agg = (Agg*)calloc(g_prof_n > 0 ? g_prof_n : 1, sizeof(Agg));
+  int na = 0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    EGOT2_CUDA(cudaEventSynchronize(g_prof[i].e1));
+    EGOT2_CUDA(cudaEventElapsedTime(&ms, g_prof[i].e0, g_prof[i].e1));
+    int j = 0;
+    for (; j < na; ++j) if (strcmp(agg[j].tag, g_prof[i].tag) == 0) break;
+    if (j == na) { agg[na].tag = g_prof[i].tag; agg[na].n = 0; agg[na].us = 0; ++na; }
+    agg[j].n += 1; agg[j].us += ms * 1e3;
+  }
+  size_t off = 0;
+  buf[0] = 0;
+  for (int j = 0; j < na; ++j) {
+    int w = snprintf(buf + off, buf_bytes - off, "%s\t%d\t%.3f\n", agg[j].tag, agg[j].n, agg[j].us);
+    if (w < 0 || (size_t)w >= buf_bytes - off) break;
+    off += w;
+  }
+  free(agg);
+  return 0;
+}
 
 // =============================================================================== embed stage
 extern "C" size_t egot2_embed_workspace_bytes(const egot2_embed_desc* d, int backward) {

@@ -339,6 +339,7 @@ int launch_fwd(int B, int T, int H, int heads, const void* qkv, void* out, float
   auto kern = attn_mma_fwd_kernel<DH, TK16>;
   static bool set = false;
   if (!set) { EGOT2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+  ProfScope prof(st, "attn_mma_fwd<dh%d,tk%d> B%d T%d H%d", DH, TK16 * 16, B, T, H);
   kern<<<B * heads, TK16 * 32, smem, st>>>(T, H, heads, (const bf16*)qkv, (bf16*)out, lse, p, key);
   EGOT2_LAUNCH_CHECK();
   return 0;
@@ -350,6 +351,7 @@ int launch_bwd(int B, int T, int H, int heads, const void* qkv, const void* out,
   auto kern = attn_mma_bwd_kernel<DH, TK16>;
   static bool set = false;
   if (!set) { EGOT2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+  ProfScope prof(st, "attn_mma_bwd<dh%d,tk%d> B%d T%d H%d", DH, TK16 * 16, B, T, H);
   kern<<<B * heads, TK16 * 32, smem, st>>>(T, H, heads, (const bf16*)qkv, (const bf16*)out, lse, (const bf16*)dout,
                                           (bf16*)dqkv, p, key);
   EGOT2_LAUNCH_CHECK();

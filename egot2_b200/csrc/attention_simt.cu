@@ -339,6 +339,7 @@ int fwd_launch(int B, int Tn, int H, int heads, const void* qkv, void* out, floa
                cudaStream_t st) {
   constexpr int RB = Cfg<DH>::RB;
   dim3 grid(B * heads, (Tn + RB - 1) / RB);
+  ProfScope prof(st, "attn_simt_fwd<dh%d> B%d T%d H%d", DH, B, Tn, H);
   attn_fwd_kernel<T, DH><<<grid, NW * 32, 0, st>>>(Tn, H, heads, (const T*)qkv, (T*)out, lse, p, key);
   EGOT2_LAUNCH_CHECK();
   return 0;
@@ -348,6 +349,7 @@ int bwd_launch(int B, int Tn, int H, int heads, const void* qkv, const void* out
                void* dqkv, float* Dvec, float p, uint64_t key, cudaStream_t st) {
   constexpr int RB = Cfg<DH>::RB;
   dim3 grid(B * heads, (Tn + RB - 1) / RB);
+  ProfScope prof(st, "attn_simt_bwd<dh%d> B%d T%d H%d (2 kernels)", DH, B, Tn, H);
   attn_bwd_dq_kernel<T, DH><<<grid, NW * 32, 0, st>>>(Tn, H, heads, (const T*)qkv, (const T*)out, lse, (const T*)dout,
                                                       (T*)dqkv, Dvec, p, key);
   EGOT2_LAUNCH_CHECK();

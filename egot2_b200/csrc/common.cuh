@@ -44,6 +44,16 @@ extern unsigned long long g_launch_count;
 
 int sm_count();
 
+// ---------------------------------------------------------------- per-launcher CUDA-event timing (egot2_prof_*)
+// When profiling is enabled (egot2_prof_enable(1); eager launches only, never during graph capture) every launcher
+// brackets the kernels it enqueues with a pair of CUDA events recorded on the launch stream.
+bool prof_enabled();
+struct ProfScope {
+  cudaStream_t st; int slot;
+  ProfScope(cudaStream_t stream, const char* fmt, ...);
+  ~ProfScope();
+};
+
 static inline size_t dtype_size(int dtype) { return dtype == EGOT2_BF16 ? 2 : 4; }
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

@@ -322,6 +322,7 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
     EGOT2_CUDA(cudaFuncSetAttribute(ffn_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set_for = smem;
   }
+  ProfScope prof(st, "ffn_fwd_sm100 M%d H128 FF%d", M, FF);
   ffn_fwd_sm100_kernel<<<(M + BM - 1) / BM, NTHREADS, smem, st>>>(tx, tw1, tw2, a);
   EGOT2_LAUNCH_CHECK();
   return 0;

@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs a) {
 template <typename TI, typename TO>
 int launch(const GemmArgs& a, cudaStream_t st) {
   const bool small = (a.M <= 64 || a.N <= 64);
+  ProfScope prof(st, "gemm_simt<%s> M%d N%d K%d ta%d tb%d sk%d", sizeof(TI) == 4 ? "f32" : "bf16", a.M, a.N, a.K, a.trans_a,
+                 a.trans_b, a.split_k);
   if (small) {
     dim3 grid((a.N + 63) / 64, (a.M + 63) / 64, a.split_k);
     gemm_simt_kernel<TI, TO, 64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(a);

@@ -369,6 +369,8 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   splits = (kb_total + kb_per - 1) / kb_per;
   e.atomic = splits > 1;
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, splits);
+  ProfScope prof(st, "gemm_sm100<bn%d,%s%s,%s> M%d N%d K%d sk%d%s", BN, A_MN ? "mn" : "k", B_MN ? "mn" : "k",
+                 sizeof(TO) == 4 ? "f32" : "bf16", a.M, a.N, a.K, splits, a.mask ? " +mask" : (a.residual ? " +res" : ""));
   kern<<<grid, NTHREADS, smem, st>>>(ma, mb, e, kb_total, kb_per);
   EGOT2_LAUNCH_CHECK();
   return 0;

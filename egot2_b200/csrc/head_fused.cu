@@ -131,6 +131,7 @@ int head_fused_fwd(const egot2_head_desc& d, const egot2_head_in& in, const egot
   const float ph = d.training ? d.p_head : 0.f;
   const uint64_t key = site_key(d.seed, SITE_HEAD, 0);
   const size_t smem = 2 * (size_t)d.H * sizeof(float);
+  ProfScope prof(st, "head_fwd B%d T%d H%d n%d", d.B, d.T, d.H, d.n_out);
   if (d.dtype == EGOT2_F32)
     head_fwd_kernel<float><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, (const float*)in.x, in.ln_g, in.ln_b, (const float*)in.w,
                                                   in.b, d.ln_eps, ph, key, out.pooled, out.stat, (float*)out.g, out.logits);
@@ -146,6 +147,7 @@ int head_fused_bwd(const egot2_head_desc& d, const egot2_head_in& in, const egot
   const float ph = d.training ? d.p_head : 0.f;
   const uint64_t key = site_key(d.seed, SITE_HEAD, 0);
   const size_t smem = 2 * (size_t)d.H * sizeof(float);
+  ProfScope prof(st, "head_bwd B%d T%d H%d n%d", d.B, d.T, d.H, d.n_out);
   if (d.dtype == EGOT2_F32)
     head_bwd_kernel<float><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, dlogits, saved.pooled, saved.stat, (const float*)saved.g,
                                                   in.ln_g, (const float*)in.w, ph, key, (float*)dx, g.ln_g, g.ln_b, g.w, g.b);

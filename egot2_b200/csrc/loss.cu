@@ -161,6 +161,7 @@ int loss_fwd(const egot2_head_desc& d, int rows, const float* logits, const int6
                 "loss: CE_GROUPS geometry %d*%d != n_out %d", g.per_sub, g.sub_rows, d.n_out);
   const long long segs = (long long)rows * g.sub_rows * g.n_groups;
   const int grid = (int)((segs * 32 + 255) / 256);
+  ProfScope prof(st, "loss_fwd kind%d rows%d n%d (2 kernels)", d.loss, rows, d.n_out);
   if (d.loss == EGOT2_LOSS_BCE_SIGMOID)
     bce_fwd_kernel<<<grid, 256, 0, st>>>(rows, d.n_out, logits, labels, row_loss, argmax);
   else
@@ -176,6 +177,7 @@ int loss_bwd(const egot2_head_desc& d, int rows, const float* logits, const int6
              const float* loss2, float dloss_scale, float* dlogits, cudaStream_t st) {
   if (d.loss == EGOT2_LOSS_NONE || rows == 0) return 0;
   const SegGeom g = geom(d);
+  ProfScope prof(st, "loss_bwd kind%d rows%d n%d", d.loss, rows, d.n_out);
   if (d.loss == EGOT2_LOSS_BCE_SIGMOID) {
     const long long total = (long long)rows * d.n_out;
     bce_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(total, d.n_out, logits, labels, dloss_scale, dlogits);

@@ -277,6 +277,7 @@ __global__ void slowfast_pool_kernel(const TI* __restrict__ in, int B, int C, in
 
 template <int NPL> int ln_fwd_dispatch(const LayerNormArgs& a, cudaStream_t st) {
   const int grid = row_grid(a.rows);
+  ProfScope prof(st, "ln_fwd rows%d H%d", a.rows, a.H);
   if (a.dtype == EGOT2_F32) ln_fwd_kernel<float, float, NPL><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
   else if (a.x_is_f32) ln_fwd_kernel<float, bf16, NPL><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
   else ln_fwd_kernel<bf16, bf16, NPL><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
@@ -287,6 +288,7 @@ template <int NPL> int ln_fwd_dispatch(const LayerNormArgs& a, cudaStream_t st) 
 template <int NPL> int ln_bwd_dispatch(const LayerNormBwdArgs& a, cudaStream_t st) {
   const int grid = row_grid(a.rows);
   const int nt = kWarpsPerCta * 32;
+  ProfScope prof(st, "ln_bwd rows%d H%d", a.rows, a.H);
   if (a.dtype == EGOT2_F32) {
     ln_bwd_kernel<float, float, float, float, NPL><<<grid, nt, 0, st>>>(a);
   } else {
@@ -337,6 +339,7 @@ int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, cu
   if (chunks < 1) chunks = 1;
   const int per = (B + chunks - 1) / chunks;
   dim3 grid(T, (B + per - 1) / per);
+  ProfScope prof(st, "table_grad B%d T%d H%d", B, T, H);
   if (dtype == EGOT2_F32) table_grad_kernel<float><<<grid, nt, 0, st>>>(B, T, H, per, (const float*)dy, dtable);
   else table_grad_kernel<bf16><<<grid, nt, 0, st>>>(B, T, H, per, (const bf16*)dy, dtable);
   EGOT2_LAUNCH_CHECK();
@@ -351,6 +354,7 @@ int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int g
   if (rows_per_cta < 64) rows_per_cta = 64;
   row_blocks = (M + rows_per_cta - 1) / rows_per_cta;
   dim3 grid(col_blocks, row_blocks), block(32, 8);
+  ProfScope prof(st, "colsum M%d N%d", M, N);
   if (dtype == EGOT2_F32) colsum_kernel<float><<<grid, block, 0, st>>>(M, N, (const float*)x, ldx, rpg, gstride, out, rows_per_cta);
   else colsum_kernel<bf16><<<grid, block, 0, st>>>(M, N, (const bf16*)x, ldx, rpg, gstride, out, rows_per_cta);
   EGOT2_LAUNCH_CHECK();
@@ -367,6 +371,7 @@ static inline int ew_grid(size_t n, int per_thread = 1) {
 int dropout_inplace(int dtype, void* x, size_t n, float p, uint64_t key, cudaStream_t st) {
   if (p <= 0.f || n == 0) return 0;
   const float inv_keep = 1.f / (1.f - p);
+  ProfScope prof(st, "dropout_inplace n%zu", n);
   if (dtype == EGOT2_F32) dropout_kernel<float><<<ew_grid(n), 256, 0, st>>>((float*)x, n, p, inv_keep, key);
   else dropout_kernel<bf16><<<ew_grid(n), 256, 0, st>>>((bf16*)x, n, p, inv_keep, key);
   EGOT2_LAUNCH_CHECK();
@@ -377,6 +382,7 @@ int pool_fwd(int dtype, int B, int T, int H, int pool, int row_tokens, const voi
   const int rows = pool ? B : B * row_tokens;
   if (rows == 0) return 0;
   const int nt = H < 256 ? ((H + 31) / 32 * 32) : 256;
+  ProfScope prof(st, "pool_fwd B%d T%d H%d", B, T, H);
   if (dtype == EGOT2_F32) pool_fwd_kernel<float><<<rows, nt, 0, st>>>(B, T, H, pool, row_tokens, (const float*)x, pooled);
   else pool_fwd_kernel<bf16><<<rows, nt, 0, st>>>(B, T, H, pool, row_tokens, (const bf16*)x, pooled);
   EGOT2_LAUNCH_CHECK();
@@ -386,6 +392,7 @@ int pool_fwd(int dtype, int B, int T, int H, int pool, int row_tokens, const voi
 int pool_bwd(int dtype, int B, int T, int H, int pool, int row_tokens, const float* dpooled, void* dx, cudaStream_t st) {
   if (B * T == 0) return 0;
   const int nt = H < 256 ? ((H + 31) / 32 * 32) : 256;
+  ProfScope prof(st, "pool_bwd B%d T%d H%d", B, T, H);
   if (dtype == EGOT2_F32) pool_bwd_kernel<float><<<B * T, nt, 0, st>>>(B, T, H, pool, row_tokens, dpooled, (float*)dx);
   else pool_bwd_kernel<bf16><<<B * T, nt, 0, st>>>(B, T, H, pool, row_tokens, dpooled, (bf16*)dx);
   EGOT2_LAUNCH_CHECK();
@@ -394,6 +401,7 @@ int pool_bwd(int dtype, int B, int T, int H, int pool, int row_tokens, const flo
 
 int cast_f32_to(int dtype, const float* src, void* dst, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
+  ProfScope prof(st, "cast_f32_to n%zu", n);
   if (dtype == EGOT2_BF16) {
     EGOT2_CHECK(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0), "cast: unaligned buffers");
     cast_to_bf16_kernel<<<ew_grid(n, 4), 256, 0, st>>>(src, (bf16*)dst, n);
@@ -406,6 +414,7 @@ int cast_f32_to(int dtype, const float* src, void* dst, size_t n, cudaStream_t s
 
 int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
+  ProfScope prof(st, "cast_to_f32 n%zu", n);
   if (dtype == EGOT2_BF16) cast_to_f32_kernel<<<ew_grid(n), 256, 0, st>>>((const bf16*)src, dst, n);
   else copy_f32_kernel<<<ew_grid(n), 256, 0, st>>>((const float*)src, dst, n);
   EGOT2_LAUNCH_CHECK();
@@ -440,6 +449,7 @@ extern "C" int egot2_adam_step(float* param, const float* grad, float* exp_avg, 
   if (n == 0) return 0;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
+  ProfScope prof((cudaStream_t)stream, "adam n%zu", n);
   adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                            weight_decay, bc1, sqrtf(bc2), grad_scale);
   EGOT2_LAUNCH_CHECK();
@@ -456,6 +466,7 @@ extern "C" int egot2_hhi_tok_table_fwd(const float* task_embed, const float* pe,
     s.tokens[i] = seg_tokens[i]; s.task[i] = seg_task_id[i]; T += seg_tokens[i];
   }
   if (T == 0) return 0;
+  ProfScope prof((cudaStream_t)stream, "hhi_tok_table_fwd T%d H%d", T, H);
   hhi_tok_table_fwd_kernel<<<T, 128, 0, (cudaStream_t)stream>>>(task_embed, pe, s, H, tok_table);
   EGOT2_LAUNCH_CHECK();
   return 0;
@@ -465,6 +476,7 @@ extern "C" int egot2_hhi_tok_table_bwd(const float* d_tok_table, int32_t n_seg, 
   EGOT2_CHECK(n_seg >= 1 && n_seg <= EGOT2_MAX_SEG, "tok_table: n_seg=%d", n_seg);
   SegList s; s.n = n_seg;
   for (int i = 0; i < n_seg; ++i) { s.tokens[i] = seg_tokens[i]; s.task[i] = seg_task_id[i]; }
+  ProfScope prof((cudaStream_t)stream, "hhi_tok_table_bwd H%d", H);
   hhi_tok_table_bwd_kernel<<<n_seg, 128, 0, (cudaStream_t)stream>>>(d_tok_table, s, H, d_task_embed);
   EGOT2_LAUNCH_CHECK();
   return 0;
@@ -477,6 +489,7 @@ extern "C" int egot2_slowfast_pool_fwd(const void* in, int32_t in_dtype, int32_t
   if (warps == 0) return 0;
   const int grid = (int)((warps * 32 + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(st, "slowfast_pool B%d C%d Tin%d hw%d", B, C, Tin, hw);
   if (in_dtype == EGOT2_F32 && out_dtype == EGOT2_F32)
     slowfast_pool_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, B, C, Tin, hw, Tout, (float*)out);
   else if (in_dtype == EGOT2_F32 && out_dtype == EGOT2_BF16)

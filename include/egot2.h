@@ -68,6 +68,11 @@ const char* egot2_last_error(void);
 int egot2_sm_count(void);
 /* Number of kernels this library has launched in this process so far (all streams). */
 uint64_t egot2_launch_count(void);
+/* Launcher timing for the benchmark's roofline: while enabled, every launcher of the library brackets the kernels it
+ * enqueues with CUDA events on the launch stream (eager launches only; ignored during stream capture).
+ * egot2_prof_report writes "<launcher tag>\t<launches>\t<total microseconds>\n" lines (host buffer). */
+int egot2_prof_enable(int on);
+int egot2_prof_report(char* buf_host, size_t buf_bytes);
 
 /* ------------------------------------------------------------------ embed stage */
 typedef struct {
