@@ -20,6 +20,7 @@ LIB = os.path.join(LIBDIR, "libegot2.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
+CFLAGS += os.environ.get("EGOT2_CFLAGS", "").split()      # e.g. EGOT2_CFLAGS=-DEGOT2_FFN_TRACE for a debugging build
 
 
 def sources():

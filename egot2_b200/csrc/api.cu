@@ -399,7 +399,7 @@ extern "C" int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_la
   {
     GemmArgs g; g.M = M; g.N = FF; g.K = H; g.A = s->x1; g.lda = H; g.B = p->lin1_w; g.ldb = H; g.trans_b = 1;
     g.C = s->hid; g.ldc = FF; g.bias = p->lin1_b; g.relu = 1;
-    g.p_drop = pd; g.drop_key = site_key(d->seed, SITE_FFN, L); g.in_dtype = d->dtype; g.out_dtype = d->dtype;
+    g.p_drop = pd; g.drop_key = site_key(d->seed, SITE_FFN, L); g.drop_bit_mode = 1; g.in_dtype = d->dtype; g.out_dtype = d->dtype;
     EGOT2_TRY(gemm(g, st));
   }
   // 6. y2 = x1 + dropout2(hid . W2^T + b2)

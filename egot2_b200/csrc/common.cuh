@@ -91,14 +91,32 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 __host__ __device__ __forceinline__ uint64_t site_key(uint64_t seed, uint32_t site, uint32_t layer) {
   return mix64(seed ^ (0x9E3779B97F4A7C15ULL * (uint64_t)(site + 16u * layer + 1u)));
 }
-// uniform in [0,1) with 24 bits
-__device__ __forceinline__ float uniform01(uint64_t key, uint64_t idx) {
-  uint64_t h = mix64(key + idx * 0xD6E8FEB86659FD93ULL);
-  return (float)(uint32_t)(h >> 40) * (1.0f / 16777216.0f);
+// 32 random bits for element `idx` of the dropout site `key`: a two-multiply xorshift hash (lowbias32-style) of the
+// 32-bit element index, keyed by both halves of the 64-bit site key.  ~7 integer instructions per element.
+__host__ __device__ __forceinline__ uint32_t drop_bits(uint64_t key, uint64_t idx) {
+  uint32_t x = (uint32_t)idx ^ (uint32_t)key ^ ((uint32_t)(idx >> 32) * 0x9E3779B1u);
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= (x >> 15) ^ (uint32_t)(key >> 32);
+  x *= 0x846ca68bu;
+  return x;
+}
+// keep threshold: an element is DROPPED iff drop_bits < p * 2^32
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  const float t = p * 4294967296.0f;
+  return t >= 4294967040.0f ? 0xFFFFFF00u : (uint32_t)(t + 0.5f);
+}
+// Bernoulli(1-p) keep decision for element idx: drop_bits(key, idx) >= p * 2^32.
+// bit_mode (FFN hidden-activation site only, and only for p == 0.5, the HHI default): ONE random bit per element - bit
+// idx%32 of the hash of idx/32 - so a kernel that owns 32 consecutive elements pays one hash per 32 elements instead of
+// one per element; that is what keeps the fused FFN epilogue off the critical path in training.
+__host__ __device__ __forceinline__ bool drop_keep(uint64_t key, uint64_t idx, float p, uint32_t thr, bool bit_mode = false) {
+  if (bit_mode && p == 0.5f) return (drop_bits(key, idx >> 5) >> (uint32_t)(idx & 31)) & 1u;
+  return drop_bits(key, idx) >= thr;
 }
 // returns the multiplier: 0 if dropped, 1/(1-p) if kept
-__device__ __forceinline__ float drop_scale(uint64_t key, uint64_t idx, float p, float inv_keep) {
-  return uniform01(key, idx) >= p ? inv_keep : 0.0f;
+__device__ __forceinline__ float drop_scale(uint64_t key, uint64_t idx, float p, float inv_keep, bool bit_mode = false) {
+  return drop_keep(key, idx, p, drop_threshold(p), bit_mode) ? inv_keep : 0.0f;
 }
 
 }  // namespace egot2

@@ -2,16 +2,31 @@
 //
 //     x_out = LayerNorm2( x1 + dropout2( dropout(relu(x1 W1^T + b1)) W2^T + b2 ) )
 //
-// One CTA owns 128 tokens.  The (tokens x FF) hidden activation never makes a round trip through HBM between the
-// two GEMMs: it is produced 128 columns at a time in TMEM, bias+ReLU(+dropout)'d in registers, written as a bf16
-// K-major swizzled A operand into shared memory and immediately consumed by the second GEMM, whose (128 x 128)
-// accumulator stays in TMEM for the whole FF loop.  The epilogue adds b2 and the residual (read back from the x1
-// tile that is still in shared memory) and applies LayerNorm2 with one token row per thread pair.
+// A CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) owns 256 tokens, 128 per CTA.  The (tokens x FF) hidden activation
+// never makes a round trip through HBM between the two GEMMs: it is produced 128 columns at a time in TMEM,
+// bias+ReLU(+dropout)'d in registers, written as a bf16 K-major swizzled A operand into shared memory and immediately
+// consumed by the second GEMM, whose (128 x 128 per CTA) accumulator stays in TMEM for the whole FF loop.  The same
+// swizzled tile is what TMA stores to HBM as the saved activation for backward.  The final epilogue adds b2 and the
+// residual (read back from the x1 tile still in shared memory), applies LayerNorm2 with one token row per thread pair,
+// and leaves through shared memory + TMA as well.
 //
-//   warp 0      TMA producer: x1 tile once, then per FF chunk the W1 rows and W2 columns (2-stage ring)
-//   warp 1      MMA issuer:   GEMM1(c) -> acc1[c&1]; GEMM2(c-1) -> acc2   (GEMM1 of chunk c overlaps epilogue c-1)
-//   warps 2-9   epilogue:     two warps per TMEM lane quadrant, 64 hidden columns each
-// TMEM: acc1 double-buffered (2 x 128 columns) + acc2 (128 columns).
+// Why a CTA pair: every token tile re-reads all of W1 and W2 (1 MB) from L2, and with one CTA per 128 tokens that
+// L2 -> SM fill (64 KB per 128-column chunk per SM, ~28 B/clk/SM measured, all 148 SMs pulling) bounded the kernel,
+// not the MMAs.  With cta_group::2 the B operand (the weights) is SPLIT across the pair - each SM fetches and holds only
+// 64 of the 128 rows of every weight stage - so the fill per SM halves, and the M=256 MMA runs at the 64-cycle floor
+// instead of the 83 cycles a lone M=128 x N=128 SS-MMA takes (shared-memory operand bandwidth; tools/ubench/umma_rate.cu).
+//
+//   warp 0      TMA producer (both CTAs): x1 tile, then this CTA's half of every weight stage; two rings (W1: 4, W2: 3
+//               stages of 16 KB = 64 rows x 128 k), polled so that neither ring holds the other back; ~4 chunks of loads
+//               in flight (TMA latency from L2 under load was measured at 2.3-3k cycles)
+//   warp 1      leader: MMA issuer A, GEMM1(c) -> acc1[c&1]      warp 11  leader: MMA issuer B, GEMM2(c) -> acc2
+//               (two issuing threads: every mbarrier wait / commit costs its thread 100-150 cycles in which it queues no
+//               MMAs - tools/ubench/umma_issue.cu - so one stream's synchronisation overlaps the other stream's MMAs)
+//   warps 2-9   epilogue (both CTAs): two warps per TMEM lane quadrant, 64 hidden columns each
+//   warp 10     TMA store of the hidden tile (both CTAs)
+// TMEM (per CTA): acc1 double-buffered (2 x 128 columns) + acc2 (128 columns).
+// Barriers that the leader's MMA threads wait on (operands of BOTH CTAs ready, accumulators drained by BOTH epilogues)
+// live in the leader and receive remote arrivals; completion barriers are signalled in both CTAs by multicast commits.
 #include "ops.h"
 #include "sm100.cuh"
 
@@ -22,40 +37,63 @@ using namespace sm100;
 namespace {
 
 constexpr int H = 128;
-constexpr int BM = 128;
+constexpr int BM = 128;                    // tokens per CTA (256 per pair)
 constexpr int FC = 128;                    // hidden columns per chunk
-constexpr int NST = 2;                     // weight ring stages
-constexpr int NTHREADS = 320;
+constexpr int R1 = 4, R2 = 3;              // W1 / W2 ring stages (16 KB: this CTA's 64 rows x 128 k, two 8 KB k-halves)
+constexpr int RING = R1 + R2;
+constexpr int HB = 2;                      // hidden-tile buffers in shared memory
+constexpr int NTHREADS = 384;
 constexpr uint32_t TILE = 128 * 128 * 2;   // one 128x128 bf16 operand tile = two 16 KB K-halves
 constexpr uint32_t HALF = 16384;
+constexpr uint32_t STAGE = 16384;          // one weight stage
 
 struct FfnArgs {
   int M, FF;
   const float* b1; const float* b2; const float* ln_g; const float* ln_b; float eps;
-  bf16* hid; bf16* y2; float* stat2; bf16* x_out;
+  float* stat2;
+  int save_hid;
   float p_drop; uint64_t key_ffn, key_drop2;
+  long long* trace;      // EGOT2_FFN_TRACE builds only: per-chunk clock64 stamps of CTA 0
 };
+
+#ifdef EGOT2_FFN_TRACE
+#define TR(c, slot) do { if (blockIdx.x == 0 && a.trace) a.trace[(c) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TR(c, slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// K-major SW128 descriptor for k16 step kk (0..7) of a 128x128 tile made of two 64-wide halves
+// K-major SW128 descriptor for k16 step kk (0..7) of a 128-row x 128-k tile made of two 64-wide k-halves
 __device__ __forceinline__ uint64_t kdesc(uint32_t tile, int kk) {
   return make_smem_desc_sw128(tile + (uint32_t)(kk >> 2) * HALF + (uint32_t)(kk & 3) * 32, 16, 1024);
 }
+// same for a 64-row weight stage (k-halves of 8 KB)
+__device__ __forceinline__ uint64_t wdesc(uint32_t stage, int kk) {
+  return make_smem_desc_sw128(stage + (uint32_t)(kk >> 2) * 8192 + (uint32_t)(kk & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ void sts128(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
-                     const __grid_constant__ CUtensorMap tm_w2, const FfnArgs a) {
+                     const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_hid,
+                     const __grid_constant__ CUtensorMap tm_y2, const __grid_constant__ CUtensorMap tm_out,
+                     const FfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sX = base;                         // 32 KB
-  const uint32_t sW1 = sX + TILE;                   // NST x 32 KB
-  const uint32_t sW2 = sW1 + NST * TILE;            // NST x 32 KB
-  const uint32_t sHid = sW2 + NST * TILE;           // 32 KB
-  const uint32_t bars = sHid + TILE;
-  const uint32_t x_full = bars, w_full = bars + 8, w_empty = w_full + 8 * NST, a1_full = w_empty + 8 * NST,
-                 a1_empty = a1_full + 16, h_full = a1_empty + 16, h_empty = h_full + 8, a2_full = h_empty + 8,
-                 tmem_slot = a2_full + 8;
+  const uint32_t sW1 = sX + TILE;                   // R1 x 16 KB
+  const uint32_t sW2 = sW1 + R1 * STAGE;            // R2 x 16 KB
+  const uint32_t sHid = sW2 + R2 * STAGE;           // HB x 32 KB (chunk c uses buffer c % HB)
+  const uint32_t bars = sHid + HB * TILE;
+  // local barriers
+  const uint32_t x_full = bars, r1_empty = x_full + 8, r2_empty = r1_empty + 8 * R1, a1_full = r2_empty + 8 * R2,
+                 hl_full = a1_full + 16, h_empty = hl_full + 8 * HB, hs_empty = h_empty + 8 * HB, a2_full = hs_empty + 8 * HB;
+  // barriers used in the leader only (arrivals from both CTAs)
+  const uint32_t x_pair = a2_full + 8, r1_full = x_pair + 8, r2_full = r1_full + 8 * R1, a1_empty = r2_full + 8 * R2,
+                 h_full = a1_empty + 16, tmem_slot = h_full + 8 * HB;
   const uint32_t red_off = (tmem_slot + 8 + 15u) & ~15u;   // float red[2][128] for the LayerNorm row statistics (16 B aligned)
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));   // generic pointer to `base`
   float* red = reinterpret_cast<float*>(gen + (red_off - base));
@@ -63,71 +101,139 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   // these are conflict-free broadcasts instead of a chain of dependent global loads on the per-chunk critical path
   float* sVec = red + 256;                 // b2[128], ln_g[128], ln_b[128]
   float* sB1 = sVec + 384;                 // b1[FF]
-  for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i];
+  {
+    const float s1 = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;      // dropout scale folded into the bias (see epilogue)
+    for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i] * s1;
+  }
   for (int i = threadIdx.x; i < 128; i += NTHREADS) { sVec[i] = a.b2[i]; sVec[128 + i] = a.ln_g[i]; sVec[256 + i] = a.ln_b[i]; }
   const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM;
   const int NC = a.FF / FC;
+#ifdef EGOT2_FFN_TRACE
+  if (threadIdx.x == 0 && a.trace) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    a.trace[1024 + blockIdx.x * 4] = (long long)t; a.trace[1024 + blockIdx.x * 4 + 2] = sm;
+  }
+#endif
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2);
-    mbar_init(x_full, 1);
-    for (int s = 0; s < NST; ++s) { mbar_init(w_full + 8 * s, 1); mbar_init(w_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(a1_full + 8 * s, 1); mbar_init(a1_empty + 8 * s, 8); }
-    mbar_init(h_full, 8); mbar_init(h_empty, 1); mbar_init(a2_full, 1);
+    tma_prefetch_desc(&tm_hid); tma_prefetch_desc(&tm_y2); tma_prefetch_desc(&tm_out);
+    mbar_init(x_full, 1); mbar_init(x_pair, 2); mbar_init(a2_full, 1);
+    for (int s = 0; s < R1; ++s) { mbar_init(r1_full + 8 * s, 1); mbar_init(r1_empty + 8 * s, 1); }
+    for (int s = 0; s < R2; ++s) { mbar_init(r2_full + 8 * s, 1); mbar_init(r2_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(a1_full + 8 * s, 1); mbar_init(a1_empty + 8 * s, 16); }
+    for (int s = 0; s < HB; ++s) {
+      mbar_init(h_full + 8 * s, 16); mbar_init(hl_full + 8 * s, 8); mbar_init(h_empty + 8 * s, 1); mbar_init(hs_empty + 8 * s, 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                         // both CTAs' barriers are initialised before anything targets them remotely
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t acc2 = tmem + 256;
 
   if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(x_full, TILE);
       tma_load_2d(sX, &tm_x, x_full, 0, m0);
       tma_load_2d(sX + HALF, &tm_x, x_full, 64, m0);
-      for (int c = 0; c < NC; ++c) {
-        const int s = c % NST;
-        mbar_wait(w_empty + 8 * s, ((c / NST) & 1) ^ 1);
-        mbar_expect_tx(w_full + 8 * s, 2 * TILE);
-        tma_load_2d(sW1 + s * TILE, &tm_w1, w_full + 8 * s, 0, c * FC);            // W1 rows c*128.., k 0..63
-        tma_load_2d(sW1 + s * TILE + HALF, &tm_w1, w_full + 8 * s, 64, c * FC);    //                  k 64..127
-        tma_load_2d(sW2 + s * TILE, &tm_w2, w_full + 8 * s, c * FC, 0);            // W2 all 128 rows, k = ff c*128..+63
-        tma_load_2d(sW2 + s * TILE + HALF, &tm_w2, w_full + 8 * s, c * FC + 64, 0);
+      // this CTA's 64 rows of every weight stage; the complete_tx goes to the LEADER's stage barrier, which expects the
+      // bytes of both halves.  The two rings are polled (try_wait) so that a full W2 ring never holds back W1 loads.
+      int i1 = 0, i2 = 0;
+      while (i1 < NC || i2 < NC) {
+        if (i1 < NC) {                                // W1 rows c*128 + rank*64 .., all 128 k
+          const int s = i1 % R1;
+          if (mbar_try_wait(r1_empty + 8 * s, ((i1 / R1) & 1) ^ 1)) {
+            TR(i1, 0);
+            const uint32_t bar = mapa(r1_full + 8 * s, 0);
+            if (leader) mbar_expect_tx(r1_full + 8 * s, 2 * STAGE);
+            tma_load_2d_cg2(sW1 + s * STAGE, &tm_w1, bar, 0, i1 * FC + rank * 64);
+            tma_load_2d_cg2(sW1 + s * STAGE + 8192, &tm_w1, bar, 64, i1 * FC + rank * 64);
+            ++i1;
+          }
+        }
+        if (i2 < NC && i2 < i1) {                     // W2 rows rank*64 .. (output features), k = ff c*128 ..
+          const int s = i2 % R2;
+          if (mbar_try_wait(r2_empty + 8 * s, ((i2 / R2) & 1) ^ 1)) {
+            TR(i2, 1);
+            const uint32_t bar = mapa(r2_full + 8 * s, 0);
+            if (leader) mbar_expect_tx(r2_full + 8 * s, 2 * STAGE);
+            tma_load_2d_cg2(sW2 + s * STAGE, &tm_w2, bar, i2 * FC, rank * 64);
+            tma_load_2d_cg2(sW2 + s * STAGE + 8192, &tm_w2, bar, i2 * FC + 64, rank * 64);
+            ++i2;
+          }
+        }
       }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer A (leader): GEMM1(c): acc1[c&1] = x1 . W1c^T
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, 128, false, false);
-      mbar_wait(x_full, 0);
-      for (int c = 0; c <= NC; ++c) {
-        if (c < NC) {                                   // GEMM1(c): acc1[c&1] = x1 . W1c^T
-          const int s = c % NST, bsel = c & 1;
-          mbar_wait(w_full + 8 * s, (c / NST) & 1);
+      mbar_wait(x_full, 0);                           // this CTA's x1 tile landed ...
+      mbar_arrive_cluster(mapa(x_pair, 0));           // ... tell the leader
+      if (leader) {
+        constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 128, false, false);
+        mbar_wait(x_pair, 0);
+        for (int c = 0; c < NC; ++c) {
+          const int bsel = c & 1, s = c % R1;
           mbar_wait(a1_empty + 8 * bsel, ((c >> 1) & 1) ^ 1);
+          TR(c, 3);
+          mbar_wait(r1_full + 8 * s, (c / R1) & 1);
+          TR(c, 2);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(tmem + bsel * 128, kdesc(sX, kk), kdesc(sW1 + s * TILE, kk), idesc, kk > 0 ? 1u : 0u);
-          umma_commit(a1_full + 8 * bsel);
-        }
-        if (c > 0) {                                    // GEMM2(c-1): acc2 += hid(c-1) . W2c^T
-          const int cp = c - 1, s = cp % NST;
-          mbar_wait(h_full, cp & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(acc2, kdesc(sHid, kk), kdesc(sW2 + s * TILE, kk), idesc, (cp > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(h_empty);                         // hid tile may be overwritten
-          umma_commit(w_empty + 8 * s);                 // weight stage may be refilled
+            umma_bf16_cg2(tmem + bsel * 128, kdesc(sX, kk), wdesc(sW1 + s * STAGE, kk), idesc, kk > 0 ? 1u : 0u);
+          umma_commit_cg2(r1_empty + 8 * s, 3);       // stage reusable (both CTAs) once these MMAs retire
+          umma_commit_cg2(a1_full + 8 * bsel, 3);
         }
       }
-      umma_commit(a2_full);
+    }
+  } else if (warp == 11) {
+    // ------------------------------------------------------------ MMA issuer B (leader): GEMM2(c): acc2 += hid(c) . W2c^T
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 128, false, false);
+      for (int cp = 0; cp < NC; ++cp) {
+        const int hb = cp % HB, s = cp % R2;
+        mbar_wait(h_full + 8 * hb, (cp / HB) & 1);
+        TR(cp, 5);
+        mbar_wait(r2_full + 8 * s, (cp / R2) & 1);
+        TR(cp, 4);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_cg2(acc2, kdesc(sHid + hb * TILE, kk), wdesc(sW2 + s * STAGE, kk), idesc, (cp > 0 || kk > 0) ? 1u : 0u);
+        umma_commit_cg2(r2_empty + 8 * s, 3);
+        umma_commit_cg2(h_empty + 8 * hb, 3);         // hid buffers may be overwritten (once the TMA stores have read them too)
+      }
+      umma_commit_cg2(a2_full, 3);
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ TMA store of the hidden tile (saved for backward)
+    if (lane == 0) {
+      for (int c = 0; c < NC; ++c) {
+        const int hb = c % HB;
+        mbar_wait(hl_full + 8 * hb, (c / HB) & 1);      // this CTA's epilogue wrote (and proxy-fenced) hid(c)
+        TR(c, 11);
+        if (a.save_hid) {
+          tma_store_2d(&tm_hid, sHid + hb * TILE, c * FC, m0);
+          tma_store_2d(&tm_hid, sHid + hb * TILE + HALF, c * FC + 64, m0);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        TR(c, 12);
+        mbar_arrive(hs_empty + 8 * hb);
+      }
+      tma_store_wait_all();
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
@@ -138,58 +244,75 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const bool row_ok = m < a.M;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-    const uint32_t hrow = sHid + ch * HALF + (uint32_t)r * 128;
+    const uint32_t thr = drop_threshold(a.p_drop);
+    const bool bitmode = a.p_drop == 0.5f;
+    const uint32_t a1_empty_ldr = mapa(a1_empty, 0), h_full_ldr = mapa(h_full, 0);
     for (int c = 0; c < NC; ++c) {
       const int bsel = c & 1;
+      const int hb = c % HB;
+      const uint32_t hrow = sHid + hb * TILE + ch * HALF + (uint32_t)r * 128;
       mbar_wait(a1_full + 8 * bsel, (c >> 1) & 1);
+      if (threadIdx.x == 64) TR(c, 6);
       tc_fence_after();
       uint32_t packed[32];
       uint32_t rr0[32], rr1[32];
       tmem_ld_32x32(tmem + lane_addr + bsel * 128 + ch * 64, rr0);
       tmem_ld_32x32(tmem + lane_addr + bsel * 128 + ch * 64 + 32, rr1);
       tmem_ld_wait();
+      if (threadIdx.x == 64) TR(c, 7);
+      // acc1[bsel] is in registers: hand the accumulator back (to the leader's MMA thread) before the arithmetic
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(a1_empty_ldr + 8 * bsel);
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
         const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
         const int n0 = c * FC + ch * 64 + h2 * 32;
+        const uint64_t idx0 = (uint64_t)m * a.FF + n0;          // multiple of 32: this thread owns one 32-bit mask word
+        const uint32_t mword = bitmode ? drop_bits(a.key_ffn, idx0 >> 5) : 0xFFFFFFFFu;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(sB1 + n0 + j);
-          float v0 = fmaxf(__uint_as_float(rr[j]) + b4.x, 0.f), v1 = fmaxf(__uint_as_float(rr[j + 1]) + b4.y, 0.f);
-          float v2 = fmaxf(__uint_as_float(rr[j + 2]) + b4.z, 0.f), v3 = fmaxf(__uint_as_float(rr[j + 3]) + b4.w, 0.f);
-          if (a.p_drop > 0.f) {
-            const uint64_t idx = (uint64_t)m * a.FF + n0 + j;
-            v0 *= drop_scale(a.key_ffn, idx, a.p_drop, inv_keep); v1 *= drop_scale(a.key_ffn, idx + 1, a.p_drop, inv_keep);
-            v2 *= drop_scale(a.key_ffn, idx + 2, a.p_drop, inv_keep); v3 *= drop_scale(a.key_ffn, idx + 3, a.p_drop, inv_keep);
+          // relu(acc + b) / (1-p) == relu(acc/(1-p) + b/(1-p)): sB1 holds the pre-scaled bias in training
+          float v0 = fmaxf(fmaf(__uint_as_float(rr[j]), inv_keep, b4.x), 0.f);
+          float v1 = fmaxf(fmaf(__uint_as_float(rr[j + 1]), inv_keep, b4.y), 0.f);
+          float v2 = fmaxf(fmaf(__uint_as_float(rr[j + 2]), inv_keep, b4.z), 0.f);
+          float v3 = fmaxf(fmaf(__uint_as_float(rr[j + 3]), inv_keep, b4.w), 0.f);
+          if (bitmode) {
+            v0 = (mword >> j) & 1u ? v0 : 0.f;
+            v1 = (mword >> (j + 1)) & 1u ? v1 : 0.f;
+            v2 = (mword >> (j + 2)) & 1u ? v2 : 0.f;
+            v3 = (mword >> (j + 3)) & 1u ? v3 : 0.f;
+          } else if (a.p_drop > 0.f) {
+            v0 = drop_bits(a.key_ffn, idx0 + j) >= thr ? v0 : 0.f;
+            v1 = drop_bits(a.key_ffn, idx0 + j + 1) >= thr ? v1 : 0.f;
+            v2 = drop_bits(a.key_ffn, idx0 + j + 2) >= thr ? v2 : 0.f;
+            v3 = drop_bits(a.key_ffn, idx0 + j + 3) >= thr ? v3 : 0.f;
           }
           __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
           packed[h2 * 16 + j / 2] = *reinterpret_cast<uint32_t*>(&p0);
           packed[h2 * 16 + j / 2 + 1] = *reinterpret_cast<uint32_t*>(&p1);
         }
       }
-      // acc1[bsel] fully read by this warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a1_empty + 8 * bsel);
-      // the hid tile is free once GEMM2(c-1) retired
-      if (c > 0) mbar_wait(h_empty, (c - 1) & 1);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {           // 8 x 16 B chunks = this thread's 64 columns, 128B-swizzled row
-        const uint32_t dst = hrow + (uint32_t)((j ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * j]), "r"(packed[4 * j + 1]),
-                     "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3]) : "memory");
+      // the hid buffer is free once GEMM2(c-HB) retired and the TMA store of chunk c-HB has read it
+      if (threadIdx.x == 64) TR(c, 8);
+      if (c >= HB) {
+        mbar_wait(h_empty + 8 * hb, ((c - HB) / HB) & 1);
+        mbar_wait(hs_empty + 8 * hb, ((c - HB) / HB) & 1);
       }
+      if (threadIdx.x == 64) TR(c, 9);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)             // 8 x 16 B chunks = this thread's 64 columns, 128B-swizzled row
+        sts128(hrow + (uint32_t)((j ^ (r & 7)) << 4), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(h_full);
-      if (a.hid && row_ok) {
-        uint4* gp = reinterpret_cast<uint4*>(a.hid + (size_t)m * a.FF + c * FC + ch * 64);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gp[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      }
+      if (lane == 0) { mbar_arrive_cluster(h_full_ldr + 8 * hb); mbar_arrive(hl_full + 8 * hb); }
+      if (threadIdx.x == 64) TR(c, 10);
     }
     // ------------------------------------------------------------ final: + b2, dropout2, + residual, LayerNorm2
-    mbar_wait(a2_full, 0);
+    mbar_wait(a2_full, 0);                    // every GEMM of the pair retired: sHid / sX are free to stage the outputs
+    for (int c = NC - HB; c < NC; ++c)        // the last hidden tiles have left through TMA
+      if (c >= 0) mbar_wait(hs_empty + 8 * (c % HB), (c / HB) & 1);
     tc_fence_after();
     float y[64];
     const int nb = ch * 64;
@@ -214,8 +337,8 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int j = j8 * 8 + 2 * k;
         float v0 = y[j] + sVec[nb + j], v1 = y[j + 1] + sVec[nb + j + 1];
         if (a.p_drop > 0.f) {
-          v0 *= drop_scale(a.key_drop2, (uint64_t)m * H + nb + j, a.p_drop, inv_keep);
-          v1 *= drop_scale(a.key_drop2, (uint64_t)m * H + nb + j + 1, a.p_drop, inv_keep);
+          v0 = drop_bits(a.key_drop2, (uint64_t)m * H + nb + j) >= thr ? v0 * inv_keep : 0.f;
+          v1 = drop_bits(a.key_drop2, (uint64_t)m * H + nb + j + 1) >= thr ? v1 * inv_keep : 0.f;
         }
         v0 += __uint_as_float(w[k] << 16);
         v1 += __uint_as_float(w[k] & 0xffff0000u);
@@ -236,33 +359,50 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     red[ch * 128 + r] = sq;
     named_bar_sync(1, 256);
     const float rstd = rsqrtf((red[r] + red[128 + r]) * (1.f / H) + a.eps);
-    if (row_ok) {
-      if (ch == 0) { a.stat2[2 * (size_t)m] = mean; a.stat2[2 * (size_t)m + 1] = rstd; }
-      uint4* yp = reinterpret_cast<uint4*>(a.y2 + (size_t)m * H + nb);
-      uint4* op = reinterpret_cast<uint4*>(a.x_out + (size_t)m * H + nb);
+    if (row_ok && ch == 0) { a.stat2[2 * (size_t)m] = mean; a.stat2[2 * (size_t)m + 1] = rstd; }
+    // stage y2 (pre-norm, saved) in the first hid buffer and x_out in the x1 tile (its residual reads are done: every
+    // epilogue thread passed the barriers above), then two TMA stores each
+    const uint32_t yrow = sHid + ch * HALF + (uint32_t)r * 128, orow = sX + ch * HALF + (uint32_t)r * 128;
 #pragma unroll
-      for (int j8 = 0; j8 < 8; ++j8) {
-        uint32_t yy[4], oo[4];
+    for (int j8 = 0; j8 < 8; ++j8) {
+      uint32_t yy[4], oo[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = j8 * 8 + 2 * k;
-          __nv_bfloat162 t = __floats2bfloat162_rn(y[j], y[j + 1]);
-          yy[k] = *reinterpret_cast<uint32_t*>(&t);
-          const float o0 = (y[j] - mean) * rstd * sVec[128 + nb + j] + sVec[256 + nb + j];
-          const float o1 = (y[j + 1] - mean) * rstd * sVec[128 + nb + j + 1] + sVec[256 + nb + j + 1];
-          __nv_bfloat162 u = __floats2bfloat162_rn(o0, o1);
-          oo[k] = *reinterpret_cast<uint32_t*>(&u);
-        }
-        yp[j8] = make_uint4(yy[0], yy[1], yy[2], yy[3]);
-        op[j8] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+      for (int k = 0; k < 4; ++k) {
+        const int j = j8 * 8 + 2 * k;
+        __nv_bfloat162 t = __floats2bfloat162_rn(y[j], y[j + 1]);
+        yy[k] = *reinterpret_cast<uint32_t*>(&t);
+        const float o0 = (y[j] - mean) * rstd * sVec[128 + nb + j] + sVec[256 + nb + j];
+        const float o1 = (y[j + 1] - mean) * rstd * sVec[128 + nb + j + 1] + sVec[256 + nb + j + 1];
+        __nv_bfloat162 u = __floats2bfloat162_rn(o0, o1);
+        oo[k] = *reinterpret_cast<uint32_t*>(&u);
       }
+      const uint32_t sw = (uint32_t)((j8 ^ (r & 7)) << 4);
+      sts128(yrow + sw, yy[0], yy[1], yy[2], yy[3]);
+      sts128(orow + sw, oo[0], oo[1], oo[2], oo[3]);
+    }
+    fence_proxy_async();
+    named_bar_sync(2, 256);
+    if (warp == 2 && lane == 0) {
+      tma_store_2d(&tm_y2, sHid, 0, m0);
+      tma_store_2d(&tm_y2, sHid + HALF, 64, m0);
+      tma_store_2d(&tm_out, sX, 0, m0);
+      tma_store_2d(&tm_out, sX + HALF, 64, m0);
+      tma_store_commit();
+      tma_store_wait_all();
     }
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                         // the peer may still be signalling this CTA's barriers / using the pair's TMEM
+#ifdef EGOT2_FFN_TRACE
+  if (threadIdx.x == 0 && a.trace) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[1024 + blockIdx.x * 4 + 1] = (long long)t;
+  }
+#endif
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc<512>(tmem);
+    tmem_dealloc_cg2<512>(tmem);
   }
 }
 
@@ -307,24 +447,64 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
                   const float* ln_g, const float* ln_b, float eps, void* hid, void* y2, float* stat2, void* x_out,
                   float p_drop, uint64_t key_ffn, uint64_t key_drop2, cudaStream_t st) {
   if (M == 0) return 0;
-  CUtensorMap tx, tw1, tw2;
+  CUtensorMap tx, tw1, tw2, thid, ty2, tout;
   EGOT2_TRY(kmajor_map(&tx, x1, H, M, H, 128));
-  EGOT2_TRY(kmajor_map(&tw1, W1, H, FF, H, 128));
-  EGOT2_TRY(kmajor_map(&tw2, W2, FF, H, FF, 128));
+  EGOT2_TRY(kmajor_map(&tw1, W1, H, FF, H, 64));      // each CTA of the pair fetches 64 rows of a stage
+  EGOT2_TRY(kmajor_map(&tw2, W2, FF, H, FF, 64));
+  EGOT2_TRY(kmajor_map(&thid, hid ? hid : y2, FF, M, FF, 128));    // never dereferenced when hid == nullptr
+  EGOT2_TRY(kmajor_map(&ty2, y2, H, M, H, 128));
+  EGOT2_TRY(kmajor_map(&tout, x_out, H, M, H, 128));
   FfnArgs a;
   a.M = M; a.FF = FF; a.b1 = b1; a.b2 = b2; a.ln_g = ln_g; a.ln_b = ln_b; a.eps = eps;
-  a.hid = (bf16*)hid; a.y2 = (bf16*)y2; a.stat2 = stat2; a.x_out = (bf16*)x_out;
+  a.stat2 = stat2; a.save_hid = hid != nullptr;
   a.p_drop = p_drop; a.key_ffn = key_ffn; a.key_drop2 = key_drop2;
-  const size_t smem = 1024 + (size_t)TILE * (1 + 2 * NST + 1) + 256 + (256 + 384 + (size_t)FF) * 4;
+  const size_t smem = 1024 + (size_t)TILE * (1 + HB) + (size_t)RING * STAGE + 512 + (256 + 384 + (size_t)FF) * 4;
   EGOT2_CHECK(smem <= 227 * 1024, "ffn_fused_fwd: FF=%d does not fit the bias stage in shared memory", FF);
   static size_t set_for = 0;
   if (set_for < smem) {
     EGOT2_CUDA(cudaFuncSetAttribute(ffn_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set_for = smem;
   }
-  ProfScope prof(st, "ffn_fwd_sm100 M%d H128 FF%d", M, FF);
-  ffn_fwd_sm100_kernel<<<(M + BM - 1) / BM, NTHREADS, smem, st>>>(tx, tw1, tw2, a);
-  EGOT2_LAUNCH_CHECK();
+  a.trace = nullptr;
+#ifdef EGOT2_FFN_TRACE
+  static long long* dtrace = nullptr;
+  if (!dtrace) cudaMalloc(&dtrace, (1024 + 4 * 1024) * 8);
+  cudaMemsetAsync(dtrace, 0, (1024 + 4 * 1024) * 8, st);
+  a.trace = dtrace;
+#endif
+  {
+    ProfScope prof(st, "ffn_fwd_sm100 M%d H128 FF%d", M, FF);
+    const int tiles = (M + BM - 1) / BM;
+    ffn_fwd_sm100_kernel<<<(tiles + 1) / 2 * 2, NTHREADS, smem, st>>>(tx, tw1, tw2, thid, ty2, tout, a);   // whole clusters
+    EGOT2_LAUNCH_CHECK();
+  }
+#ifdef EGOT2_FFN_TRACE
+  {
+    static int printed = 0;
+    if (printed++ == 3) {
+      static long long h[1024 + 4 * 1024];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, dtrace, sizeof(h), cudaMemcpyDeviceToHost);
+      {
+        long long g0 = h[1024];
+        const int nct = ((M + BM - 1) / BM + 1) / 2 * 2;
+        for (int b = 0; b < nct; ++b) if (h[1024 + 4 * b] < g0) g0 = h[1024 + 4 * b];
+        printf("ffn CTA timeline (ns since first start): cta sm start end\n");
+        for (int b = 0; b < nct; ++b)
+          printf("%3d sm%3lld %6lld %6lld%s", b, h[1024 + 4 * b + 2], h[1024 + 4 * b] - g0, h[1024 + 4 * b + 1] - g0, (b % 4 == 3) ? "\n" : " | ");
+        printf("\n");
+      }
+      long long t0 = h[0];
+      for (int i = 0; i < 64 * 16; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+      printf("ffn trace (cycles since first stamp): c | prod w1e w2e | mma w1f a1e w2f hf | epi a1f ldtm comp hwait hfull | st hf rd\n");
+      for (int c = 0; c < FF / FC && c < 64; ++c) {
+        printf("%2d |", c);
+        for (int k = 0; k < 13; ++k) printf(" %7lld%s", h[c * 16 + k] ? h[c * 16 + k] - t0 : -1LL, (k == 1 || k == 5 || k == 10) ? " |" : "");
+        printf("\n");
+      }
+    }
+  }
+#endif
   return 0;
 }
 

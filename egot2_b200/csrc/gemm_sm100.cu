@@ -29,7 +29,7 @@ struct EpiArgs {
   void* C; int ldc; int c_rpg, c_gstride;
   const float* bias; int relu;
   const void* mask; int ldm; float mask_scale;
-  float p_drop; uint64_t drop_key;
+  float p_drop; uint64_t drop_key; int drop_bit_mode;
   const void* residual; int ldr;
   int accumulate; int atomic;
   // grouped-K addressing for gathered MN-major operands (3-D tensor maps): 64-row k-block = kg groups x kdpad rows
@@ -238,7 +238,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
         if (e.p_drop > 0.f) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key, (uint64_t)m * e.N + nb + j, e.p_drop, inv_keep);
+          for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key, (uint64_t)m * e.N + nb + j, e.p_drop, inv_keep, e.drop_bit_mode != 0);
         }
         if (res_row) {
           if (mask_row) load32(res_row + nb, aux);
@@ -271,7 +271,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           if (bias) x += sbias[c0 + j];
           if (e.relu) x = fmaxf(x, 0.f);
           if (mask_row) x = to_f32(mask_row[n]) > 0.f ? x * e.mask_scale : 0.f;
-          if (e.p_drop > 0.f) x *= drop_scale(e.drop_key, (uint64_t)m * e.N + n, e.p_drop, inv_keep);
+          if (e.p_drop > 0.f) x *= drop_scale(e.drop_key, (uint64_t)m * e.N + n, e.p_drop, inv_keep, e.drop_bit_mode != 0);
           if (res_row) x += to_f32(res_row[n]);
           if (e.accumulate) {
             if constexpr (sizeof(TO) == 4) {
@@ -359,7 +359,7 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   EpiArgs e;
   e.M = a.M; e.N = a.N; e.C = a.C; e.ldc = a.ldc; e.c_rpg = a.c_rpg; e.c_gstride = a.c_gstride;
   e.bias = a.bias; e.relu = a.relu; e.mask = a.mask; e.ldm = a.ldm; e.mask_scale = a.mask_scale;
-  e.p_drop = a.p_drop; e.drop_key = a.drop_key; e.residual = a.residual; e.ldr = a.ldr;
+  e.p_drop = a.p_drop; e.drop_key = a.drop_key; e.drop_bit_mode = a.drop_bit_mode; e.residual = a.residual; e.ldr = a.ldr;
   e.accumulate = a.accumulate; e.atomic = a.split_k > 1;
   e.k_grouped = kg.on; e.kg = kg.g; e.kdblocks = kg.dblocks;
   const int kb_total = kg.on ? kg.kb_total : (a.K + BK - 1) / BK;

@@ -222,14 +222,27 @@ def _np_mix64(x):
     return x
 
 
-def dropout_mask_oracle(seed, site, layer, n, p):
+def dropout_mask_oracle(seed, site, layer, n, p, bit_mode=False):
     """Bit-exact restatement of csrc/common.cuh drop_scale(): multiplier (0 or 1/(1-p)) for element indices 0..n-1."""
     import numpy as np
+    M32 = np.uint64(0xFFFFFFFF)
+
+    def bits(key, idx):
+        x = (idx & M32) ^ (key & M32) ^ (((idx >> np.uint64(32)) * np.uint64(0x9E3779B1)) & M32)
+        x ^= x >> np.uint64(16)
+        x = (x * np.uint64(0x7feb352d)) & M32
+        x ^= (x >> np.uint64(15)) ^ (key >> np.uint64(32))
+        return (x * np.uint64(0x846ca68b)) & M32
+
     with np.errstate(over="ignore"):
-        key = _np_mix64(np.array([seed], dtype=np.uint64) ^ (np.uint64(0x9E3779B97F4A7C15) * np.uint64(site + 16 * layer + 1)))
-        h = _np_mix64(key + np.arange(n, dtype=np.uint64) * np.uint64(0xD6E8FEB86659FD93))
-    u = (h >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
-    return torch.from_numpy(np.where(u >= np.float32(p), np.float32(1.0 / (1.0 - p)), np.float32(0.0)))
+        key = _np_mix64(np.array([seed], dtype=np.uint64) ^ (np.uint64(0x9E3779B97F4A7C15) * np.uint64(site + 16 * layer + 1)))[0]
+        idx = np.arange(n, dtype=np.uint64)
+        if bit_mode and p == 0.5:      # FFN hidden site: one random bit per element (bit idx%32 of the hash of idx/32)
+            keep = ((bits(key, idx >> np.uint64(5)) >> (idx & np.uint64(31))) & np.uint64(1)) == 1
+        else:
+            thr = np.uint64(int(np.float32(p) * np.float32(4294967296.0) + np.float32(0.5)))
+            keep = bits(key, idx) >= thr
+    return torch.from_numpy(np.where(keep, np.float32(1.0 / (1.0 - p)), np.float32(0.0)))
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
