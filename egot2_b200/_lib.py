@@ -57,7 +57,7 @@ class LayerGrads(C.Structure):
 
 
 class LayerSaved(C.Structure):
-    _fields_ = [(n, vp) for n in ["qkv", "attn", "lse", "y1", "stat1", "x1", "hid", "y2", "stat2"]]
+    _fields_ = [(n, vp) for n in ["qkv", "attn", "lse", "y1", "stat1", "x1", "hid", "y2", "stat2", "hid_mask"]]
 
 
 class HeadDesc(C.Structure):

@@ -394,7 +394,8 @@ extern "C" int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_la
   // 5-7 fused (bf16, H = 128): the hidden activation stays on chip between the two GEMMs
   if (ffn_fused_supported(d->dtype, H, FF) && !env_is("EGOT2_FFN", "unfused"))
     return ffn_fused_fwd(M, FF, s->x1, p->lin1_w, p->lin1_b, p->lin2_w, p->lin2_b, p->norm2_g, p->norm2_b, d->ln_eps,
-                         s->hid, s->y2, s->stat2, x_out, pd, site_key(d->seed, SITE_FFN, L), site_key(d->seed, SITE_DROP2, L), st);
+                         s->hid, s->hid_mask, s->y2, s->stat2, x_out, pd, site_key(d->seed, SITE_FFN, L),
+                         site_key(d->seed, SITE_DROP2, L), st);
   // 5. hid = dropout(relu(x1 . W1^T + b1))
   {
     GemmArgs g; g.M = M; g.N = FF; g.K = H; g.A = s->x1; g.lda = H; g.B = p->lin1_w; g.ldb = H; g.trans_b = 1;
@@ -434,23 +435,22 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   const uint32_t L = (uint32_t)d->layer_index;
   const int dt = d->dtype;
 
-  // 1. through norm2: d1 = dL/dy2
+  // 1. through norm2: d1 = dL/dy2, and (same kernel) d2 = dropout2 mask applied to d1 = dL/d(linear2 out)
+  const void* d2 = w.d1;
   {
     LayerNormBwdArgs l; l.rows = M; l.H = H; l.dtype = dt; l.x = s->y2; l.stat = s->stat2; l.g = p->norm2_g;
     l.dy = dx_out; l.dx = w.d1; l.dg = g->norm2_g; l.db = g->norm2_b;
+    if (pd > 0.f) { l.dx2 = w.d2; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DROP2, L); d2 = w.d2; }
     EGOT2_TRY(layernorm_bwd(l, st));
-  }
-  // 2. dropout2 mask -> d2 = dL/d(linear2 out)
-  const void* d2 = w.d1;
-  if (pd > 0.f) {
-    EGOT2_CUDA(cudaMemcpyAsync(w.d2, w.d1, (size_t)M * H * es, cudaMemcpyDeviceToDevice, st));
-    EGOT2_TRY(dropout_inplace(dt, w.d2, (size_t)M * H, pd, site_key(d->seed, SITE_DROP2, L), st));
-    d2 = w.d2;
   }
   //    linear2: dW2 += d2^T . hid ; db2 += colsum(d2) ; dhid = (d2 . W2) * relu'(hid) * ffn-dropout scale
   EGOT2_TRY(wgrad(dt, M, H, FF, d2, H, 0, 0, s->hid, FF, 0, 0, g->lin2_w, st));
   EGOT2_TRY(colsum_accum(dt, M, H, d2, H, 0, 0, g->lin2_b, st));
-  {
+  const bool fused_dx = s->hid_mask && ffn_fused_supported(dt, H, FF) && !env_is("EGOT2_FFN", "unfused");
+  if (fused_dx) {
+    // one tcgen05 kernel: dhid = gate(d2 . W2) and d3 = dhid . W1 + d1, dhid never re-read for the second GEMM
+    EGOT2_TRY(ffn_fused_bwd_dx(M, FF, d2, pd > 0.f ? w.d1 : nullptr, s->hid_mask, p->lin1_w, p->lin2_w, pd, w.dhid, w.d3, st));
+  } else {
     GemmArgs m; m.M = M; m.N = FF; m.K = H; m.A = d2; m.lda = H; m.B = p->lin2_w; m.ldb = FF; m.trans_b = 0;
     m.C = w.dhid; m.ldc = FF; m.mask = s->hid; m.ldm = FF; m.mask_scale = inv_keep; m.in_dtype = dt; m.out_dtype = dt;
     EGOT2_TRY(gemm(m, st));
@@ -458,23 +458,19 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   // 3. linear1: dW1 += dhid^T . x1 ; db1 += colsum(dhid) ; d3 = dhid . W1 + d1 (residual branch)
   EGOT2_TRY(wgrad(dt, M, FF, H, w.dhid, FF, 0, 0, s->x1, H, 0, 0, g->lin1_w, st));
   EGOT2_TRY(colsum_accum(dt, M, FF, w.dhid, FF, 0, 0, g->lin1_b, st));
-  {
+  if (!fused_dx) {
     GemmArgs m; m.M = M; m.N = H; m.K = FF; m.A = w.dhid; m.lda = FF; m.B = p->lin1_w; m.ldb = H; m.trans_b = 0;
     m.C = w.d3; m.ldc = H; m.residual = w.d1; m.ldr = H; m.in_dtype = dt; m.out_dtype = dt;
     EGOT2_TRY(gemm(m, st));
   }
-  // 4. through norm1: d1 = dL/dy1
+  // 4. through norm1: d1 = dL/dy1, and (same kernel) d4 = dropout1 mask applied to d1 = dL/d(out_proj out)
+  //    out_proj: dWo += d4^T . attn ; dbo += colsum(d4) ; dattn = d4 . Wo
+  const void* d4 = w.d1;
   {
     LayerNormBwdArgs l; l.rows = M; l.H = H; l.dtype = dt; l.x = s->y1; l.stat = s->stat1; l.g = p->norm1_g;
     l.dy = w.d3; l.dx = w.d1; l.dg = g->norm1_g; l.db = g->norm1_b;
+    if (pd > 0.f) { l.dx2 = w.d2; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DROP1, L); d4 = w.d2; }
     EGOT2_TRY(layernorm_bwd(l, st));
-  }
-  // 5. dropout1 mask -> d4 ; out_proj: dWo += d4^T . attn ; dbo += colsum(d4) ; dattn = d4 . Wo
-  const void* d4 = w.d1;
-  if (pd > 0.f) {
-    EGOT2_CUDA(cudaMemcpyAsync(w.d2, w.d1, (size_t)M * H * es, cudaMemcpyDeviceToDevice, st));
-    EGOT2_TRY(dropout_inplace(dt, w.d2, (size_t)M * H, pd, site_key(d->seed, SITE_DROP1, L), st));
-    d4 = w.d2;
   }
   EGOT2_TRY(wgrad(dt, M, H, H, d4, H, 0, 0, s->attn, H, 0, 0, g->out_proj_w, st));
   EGOT2_TRY(colsum_accum(dt, M, H, d4, H, 0, 0, g->out_proj_b, st));

@@ -52,6 +52,8 @@ struct FfnArgs {
   const float* b1; const float* b2; const float* ln_g; const float* ln_b; float eps;
   float* stat2;
   int save_hid;
+  uint2* hmask;          // [FF/64][M] x 64 bits: hidden activation != 0 (ReLU gate x dropout keep), for ffn_bwd_dx
+  const bf16* d1;        // backward: gradient arriving through the residual branch (added to d3), (M,128)
   float p_drop; uint64_t key_ffn, key_drop2;
   long long* trace;      // EGOT2_FFN_TRACE builds only: per-chunk clock64 stamps of CTA 0
 };
@@ -68,16 +70,25 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 __device__ __forceinline__ uint64_t kdesc(uint32_t tile, int kk) {
   return make_smem_desc_sw128(tile + (uint32_t)(kk >> 2) * HALF + (uint32_t)(kk & 3) * 32, 16, 1024);
 }
-// same for a 64-row weight stage (k-halves of 8 KB)
+// weight stage = this CTA's half of the B operand.  K-major (forward): 64 n-rows x 128 k as two 8 KB k-halves.
+// MN-major (backward): 128 k-rows x 64 n (one 128 B swizzle atom wide): k16 step kk starts 16 rows further down.
+template <bool MN>
 __device__ __forceinline__ uint64_t wdesc(uint32_t stage, int kk) {
-  return make_smem_desc_sw128(stage + (uint32_t)(kk >> 2) * 8192 + (uint32_t)(kk & 3) * 32, 16, 1024);
+  return MN ? make_smem_desc_sw128(stage + (uint32_t)kk * 2048, 8192, 1024)
+            : make_smem_desc_sw128(stage + (uint32_t)(kk >> 2) * 8192 + (uint32_t)(kk & 3) * 32, 16, 1024);
 }
 __device__ __forceinline__ void sts128(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// BWD = false: the forward block described above.
+// BWD = true : the data-gradient half of its backward, same skeleton with the roles swapped -
+//     dhid_c = (d2 . W2[:, c]) * gate_c / (1-p)   (GEMM1: A = d2 tile, B = W2 columns, MN-major; gate bits from hmask)
+//     d3     = sum_c dhid_c . W1[c, :] + d1        (GEMM2: A = dhid tile, B = W1 rows, MN-major)
+//   dhid leaves through TMA (it feeds the two weight-gradient GEMMs), d3 replaces the forward's y2 output.
+template <bool BWD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
+ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_hid,
                      const __grid_constant__ CUtensorMap tm_y2, const __grid_constant__ CUtensorMap tm_out,
                      const FfnArgs a) {
@@ -101,11 +112,11 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   // these are conflict-free broadcasts instead of a chain of dependent global loads on the per-chunk critical path
   float* sVec = red + 256;                 // b2[128], ln_g[128], ln_b[128]
   float* sB1 = sVec + 384;                 // b1[FF]
-  {
+  if (!BWD) {
     const float s1 = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;      // dropout scale folded into the bias (see epilogue)
     for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i] * s1;
+    for (int i = threadIdx.x; i < 128; i += NTHREADS) { sVec[i] = a.b2[i]; sVec[128 + i] = a.ln_g[i]; sVec[256 + i] = a.ln_b[i]; }
   }
-  for (int i = threadIdx.x; i < 128; i += NTHREADS) { sVec[i] = a.b2[i]; sVec[128 + i] = a.ln_g[i]; sVec[256 + i] = a.ln_b[i]; }
   const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,8 +168,12 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             TR(i1, 0);
             const uint32_t bar = mapa(r1_full + 8 * s, 0);
             if (leader) mbar_expect_tx(r1_full + 8 * s, 2 * STAGE);
-            tma_load_2d_cg2(sW1 + s * STAGE, &tm_w1, bar, 0, i1 * FC + rank * 64);
-            tma_load_2d_cg2(sW1 + s * STAGE + 8192, &tm_w1, bar, 64, i1 * FC + rank * 64);
+            if (!BWD) {       // GEMM1 B = W1 rows (ff) c*128 + rank*64 .., K-major: two 64-k halves
+              tma_load_2d_cg2(sW1 + s * STAGE, &tm_w1, bar, 0, i1 * FC + rank * 64);
+              tma_load_2d_cg2(sW1 + s * STAGE + 8192, &tm_w1, bar, 64, i1 * FC + rank * 64);
+            } else {          // GEMM1 B = W2[:, ff], MN-major: 128 k-rows (h) x this CTA's 64 ff columns, one box
+              tma_load_2d_cg2(sW1 + s * STAGE, &tm_w2, bar, i1 * FC + rank * 64, 0);
+            }
             ++i1;
           }
         }
@@ -168,8 +183,12 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             TR(i2, 1);
             const uint32_t bar = mapa(r2_full + 8 * s, 0);
             if (leader) mbar_expect_tx(r2_full + 8 * s, 2 * STAGE);
-            tma_load_2d_cg2(sW2 + s * STAGE, &tm_w2, bar, i2 * FC, rank * 64);
-            tma_load_2d_cg2(sW2 + s * STAGE + 8192, &tm_w2, bar, i2 * FC + 64, rank * 64);
+            if (!BWD) {       // GEMM2 B = W2 rows (h) rank*64 .., K-major over ff c*128 ..
+              tma_load_2d_cg2(sW2 + s * STAGE, &tm_w2, bar, i2 * FC, rank * 64);
+              tma_load_2d_cg2(sW2 + s * STAGE + 8192, &tm_w2, bar, i2 * FC + 64, rank * 64);
+            } else {          // GEMM2 B = W1[ff, :], MN-major: 128 k-rows (ff) x this CTA's 64 h columns
+              tma_load_2d_cg2(sW2 + s * STAGE, &tm_w1, bar, rank * 64, i2 * FC);
+            }
             ++i2;
           }
         }
@@ -181,7 +200,7 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       mbar_wait(x_full, 0);                           // this CTA's x1 tile landed ...
       mbar_arrive_cluster(mapa(x_pair, 0));           // ... tell the leader
       if (leader) {
-        constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 128, false, false);
+        constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 128, false, BWD);
         mbar_wait(x_pair, 0);
         for (int c = 0; c < NC; ++c) {
           const int bsel = c & 1, s = c % R1;
@@ -192,7 +211,7 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_bf16_cg2(tmem + bsel * 128, kdesc(sX, kk), wdesc(sW1 + s * STAGE, kk), idesc, kk > 0 ? 1u : 0u);
+            umma_bf16_cg2(tmem + bsel * 128, kdesc(sX, kk), wdesc<BWD>(sW1 + s * STAGE, kk), idesc, kk > 0 ? 1u : 0u);
           umma_commit_cg2(r1_empty + 8 * s, 3);       // stage reusable (both CTAs) once these MMAs retire
           umma_commit_cg2(a1_full + 8 * bsel, 3);
         }
@@ -201,7 +220,7 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   } else if (warp == 11) {
     // ------------------------------------------------------------ MMA issuer B (leader): GEMM2(c): acc2 += hid(c) . W2c^T
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 128, false, false);
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 128, false, BWD);
       for (int cp = 0; cp < NC; ++cp) {
         const int hb = cp % HB, s = cp % R2;
         mbar_wait(h_full + 8 * hb, (cp / HB) & 1);
@@ -211,7 +230,7 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_cg2(acc2, kdesc(sHid + hb * TILE, kk), wdesc(sW2 + s * STAGE, kk), idesc, (cp > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_cg2(acc2, kdesc(sHid + hb * TILE, kk), wdesc<BWD>(sW2 + s * STAGE, kk), idesc, (cp > 0 || kk > 0) ? 1u : 0u);
         umma_commit_cg2(r2_empty + 8 * s, 3);
         umma_commit_cg2(h_empty + 8 * hb, 3);         // hid buffers may be overwritten (once the TMA stores have read them too)
       }
@@ -264,34 +283,58 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(a1_empty_ldr + 8 * bsel);
+      if (!BWD) {
+        uint32_t gate[2];
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
-        const int n0 = c * FC + ch * 64 + h2 * 32;
-        const uint64_t idx0 = (uint64_t)m * a.FF + n0;          // multiple of 32: this thread owns one 32-bit mask word
-        const uint32_t mword = bitmode ? drop_bits(a.key_ffn, idx0 >> 5) : 0xFFFFFFFFu;
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
+          const int n0 = c * FC + ch * 64 + h2 * 32;
+          const uint64_t idx0 = (uint64_t)m * a.FF + n0;          // multiple of 32: this thread owns one 32-bit mask word
+          const uint32_t mword = bitmode ? drop_bits(a.key_ffn, idx0 >> 5) : 0xFFFFFFFFu;
+          uint32_t gw = 0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(sB1 + n0 + j);
-          // relu(acc + b) / (1-p) == relu(acc/(1-p) + b/(1-p)): sB1 holds the pre-scaled bias in training
-          float v0 = fmaxf(fmaf(__uint_as_float(rr[j]), inv_keep, b4.x), 0.f);
-          float v1 = fmaxf(fmaf(__uint_as_float(rr[j + 1]), inv_keep, b4.y), 0.f);
-          float v2 = fmaxf(fmaf(__uint_as_float(rr[j + 2]), inv_keep, b4.z), 0.f);
-          float v3 = fmaxf(fmaf(__uint_as_float(rr[j + 3]), inv_keep, b4.w), 0.f);
-          if (bitmode) {
-            v0 = (mword >> j) & 1u ? v0 : 0.f;
-            v1 = (mword >> (j + 1)) & 1u ? v1 : 0.f;
-            v2 = (mword >> (j + 2)) & 1u ? v2 : 0.f;
-            v3 = (mword >> (j + 3)) & 1u ? v3 : 0.f;
-          } else if (a.p_drop > 0.f) {
-            v0 = drop_bits(a.key_ffn, idx0 + j) >= thr ? v0 : 0.f;
-            v1 = drop_bits(a.key_ffn, idx0 + j + 1) >= thr ? v1 : 0.f;
-            v2 = drop_bits(a.key_ffn, idx0 + j + 2) >= thr ? v2 : 0.f;
-            v3 = drop_bits(a.key_ffn, idx0 + j + 3) >= thr ? v3 : 0.f;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sB1 + n0 + j);
+            // relu(acc + b) / (1-p) == relu(acc/(1-p) + b/(1-p)): sB1 holds the pre-scaled bias in training
+            float v0 = fmaxf(fmaf(__uint_as_float(rr[j]), inv_keep, b4.x), 0.f);
+            float v1 = fmaxf(fmaf(__uint_as_float(rr[j + 1]), inv_keep, b4.y), 0.f);
+            float v2 = fmaxf(fmaf(__uint_as_float(rr[j + 2]), inv_keep, b4.z), 0.f);
+            float v3 = fmaxf(fmaf(__uint_as_float(rr[j + 3]), inv_keep, b4.w), 0.f);
+            if (bitmode) {
+              v0 = (mword >> j) & 1u ? v0 : 0.f;
+              v1 = (mword >> (j + 1)) & 1u ? v1 : 0.f;
+              v2 = (mword >> (j + 2)) & 1u ? v2 : 0.f;
+              v3 = (mword >> (j + 3)) & 1u ? v3 : 0.f;
+            } else if (a.p_drop > 0.f) {
+              v0 = drop_bits(a.key_ffn, idx0 + j) >= thr ? v0 : 0.f;
+              v1 = drop_bits(a.key_ffn, idx0 + j + 1) >= thr ? v1 : 0.f;
+              v2 = drop_bits(a.key_ffn, idx0 + j + 2) >= thr ? v2 : 0.f;
+              v3 = drop_bits(a.key_ffn, idx0 + j + 3) >= thr ? v3 : 0.f;
+            }
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
+            const uint32_t u0 = *reinterpret_cast<uint32_t*>(&p0), u1 = *reinterpret_cast<uint32_t*>(&p1);
+            packed[h2 * 16 + j / 2] = u0;
+            packed[h2 * 16 + j / 2 + 1] = u1;
+            // gate bit = the SAVED (bf16) activation is non-zero; values are >= 0, so "!= 0" is min(bits, 1)
+            gw += (min(u0 & 0xFFFFu, 1u) << j) + (min(u0 >> 16, 1u) << (j + 1)) + (min(u1 & 0xFFFFu, 1u) << (j + 2)) +
+                  (min(u1 >> 16, 1u) << (j + 3));
           }
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
-          packed[h2 * 16 + j / 2] = *reinterpret_cast<uint32_t*>(&p0);
-          packed[h2 * 16 + j / 2 + 1] = *reinterpret_cast<uint32_t*>(&p1);
+          gate[h2] = gw;
+        }
+        if (a.hmask && row_ok) a.hmask[(size_t)(c * 2 + ch) * a.M + m] = make_uint2(gate[0], gate[1]);
+      } else {
+        const uint2 gate = row_ok ? __ldg(a.hmask + (size_t)(c * 2 + ch) * a.M + m) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
+          const uint32_t gw = h2 ? gate.y : gate.x;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float v0 = (gw >> j) & 1u ? __uint_as_float(rr[j]) * inv_keep : 0.f;
+            const float v1 = (gw >> (j + 1)) & 1u ? __uint_as_float(rr[j + 1]) * inv_keep : 0.f;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1);
+            packed[h2 * 16 + j / 2] = *reinterpret_cast<uint32_t*>(&p0);
+          }
         }
       }
       // the hid buffer is free once GEMM2(c-HB) retired and the TMA store of chunk c-HB has read it
@@ -325,6 +368,40 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
       for (int j = 0; j < 32; ++j) y[h2 * 32 + j] = __uint_as_float(rr[j]);
     }
+    if constexpr (BWD) {
+      // d3 = acc2 + d1 (gradient through the residual branch); with no dropout2, d1 IS the d2 tile still in sX
+      const uint32_t orow = sHid + ch * HALF + (uint32_t)r * 128;
+      const bf16* d1row = (a.d1 && row_ok) ? a.d1 + (size_t)m * H + nb : nullptr;
+#pragma unroll
+      for (int j8 = 0; j8 < 8; ++j8) {
+        uint32_t w0, w1, w2, w3;
+        if (a.d1) {
+          uint4 t = make_uint4(0u, 0u, 0u, 0u);
+          if (d1row) t = __ldg(reinterpret_cast<const uint4*>(d1row) + j8);
+          w0 = t.x; w1 = t.y; w2 = t.z; w3 = t.w;
+        } else {
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                       : "r"(xrow + (uint32_t)((j8 ^ (r & 7)) << 4)));
+        }
+        const uint32_t w[4] = {w0, w1, w2, w3};
+        uint32_t oo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = j8 * 8 + 2 * k;
+          __nv_bfloat162 u = __floats2bfloat162_rn(y[j] + __uint_as_float(w[k] << 16), y[j + 1] + __uint_as_float(w[k] & 0xffff0000u));
+          oo[k] = *reinterpret_cast<uint32_t*>(&u);
+        }
+        sts128(orow + (uint32_t)((j8 ^ (r & 7)) << 4), oo[0], oo[1], oo[2], oo[3]);
+      }
+      fence_proxy_async();
+      named_bar_sync(2, 256);
+      if (warp == 2 && lane == 0) {
+        tma_store_2d(&tm_y2, sHid, 0, m0);
+        tma_store_2d(&tm_y2, sHid + HALF, 64, m0);
+        tma_store_commit();
+        tma_store_wait_all();
+      }
+    } else {
     float sum = 0.f;
 #pragma unroll
     for (int j8 = 0; j8 < 8; ++j8) {
@@ -390,6 +467,7 @@ ffn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       tma_store_commit();
       tma_store_wait_all();
     }
+    }   // !BWD
   }
   tc_fence_before();
   __syncthreads();
@@ -442,28 +520,15 @@ bool ffn_fused_supported(int dtype, int Hdim, int FF) {
   return dtype == EGOT2_BF16 && Hdim == H && FF >= FC && FF % FC == 0;
 }
 
-// x_out = LN2(x1 + drop2(drop(relu(x1 W1^T + b1)) W2^T + b2)); also writes hid (if non-null), y2, stat2
-int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1, const void* W2, const float* b2,
-                  const float* ln_g, const float* ln_b, float eps, void* hid, void* y2, float* stat2, void* x_out,
-                  float p_drop, uint64_t key_ffn, uint64_t key_drop2, cudaStream_t st) {
-  if (M == 0) return 0;
-  CUtensorMap tx, tw1, tw2, thid, ty2, tout;
-  EGOT2_TRY(kmajor_map(&tx, x1, H, M, H, 128));
-  EGOT2_TRY(kmajor_map(&tw1, W1, H, FF, H, 64));      // each CTA of the pair fetches 64 rows of a stage
-  EGOT2_TRY(kmajor_map(&tw2, W2, FF, H, FF, 64));
-  EGOT2_TRY(kmajor_map(&thid, hid ? hid : y2, FF, M, FF, 128));    // never dereferenced when hid == nullptr
-  EGOT2_TRY(kmajor_map(&ty2, y2, H, M, H, 128));
-  EGOT2_TRY(kmajor_map(&tout, x_out, H, M, H, 128));
-  FfnArgs a;
-  a.M = M; a.FF = FF; a.b1 = b1; a.b2 = b2; a.ln_g = ln_g; a.ln_b = ln_b; a.eps = eps;
-  a.stat2 = stat2; a.save_hid = hid != nullptr;
-  a.p_drop = p_drop; a.key_ffn = key_ffn; a.key_drop2 = key_drop2;
+static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2,
+                      const CUtensorMap& thid, const CUtensorMap& ty2, const CUtensorMap& tout, FfnArgs& a, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)TILE * (1 + HB) + (size_t)RING * STAGE + 512 + (256 + 384 + (size_t)FF) * 4;
-  EGOT2_CHECK(smem <= 227 * 1024, "ffn_fused_fwd: FF=%d does not fit the bias stage in shared memory", FF);
-  static size_t set_for = 0;
-  if (set_for < smem) {
-    EGOT2_CUDA(cudaFuncSetAttribute(ffn_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set_for = smem;
+  EGOT2_CHECK(smem <= 227 * 1024, "ffn_fused: FF=%d does not fit the bias stage in shared memory", FF);
+  static size_t set_for[2] = {0, 0};
+  if (set_for[bwd] < smem) {
+    if (bwd) EGOT2_CUDA(cudaFuncSetAttribute(ffn_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else EGOT2_CUDA(cudaFuncSetAttribute(ffn_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set_for[bwd] = smem;
   }
   a.trace = nullptr;
 #ifdef EGOT2_FFN_TRACE
@@ -473,9 +538,10 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
   a.trace = dtrace;
 #endif
   {
-    ProfScope prof(st, "ffn_fwd_sm100 M%d H128 FF%d", M, FF);
-    const int tiles = (M + BM - 1) / BM;
-    ffn_fwd_sm100_kernel<<<(tiles + 1) / 2 * 2, NTHREADS, smem, st>>>(tx, tw1, tw2, thid, ty2, tout, a);   // whole clusters
+    ProfScope prof(st, bwd ? "ffn_bwd_dx_sm100 M%d H128 FF%d" : "ffn_fwd_sm100 M%d H128 FF%d", M, FF);
+    const int tiles = (M + BM - 1) / BM, grid = (tiles + 1) / 2 * 2;      // whole CTA pairs
+    if (bwd) ffn_sm100_kernel<true><<<grid, NTHREADS, smem, st>>>(tx, tw1, tw2, thid, ty2, tout, a);
+    else ffn_sm100_kernel<false><<<grid, NTHREADS, smem, st>>>(tx, tw1, tw2, thid, ty2, tout, a);
     EGOT2_LAUNCH_CHECK();
   }
 #ifdef EGOT2_FFN_TRACE
@@ -485,15 +551,6 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
       static long long h[1024 + 4 * 1024];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, dtrace, sizeof(h), cudaMemcpyDeviceToHost);
-      {
-        long long g0 = h[1024];
-        const int nct = ((M + BM - 1) / BM + 1) / 2 * 2;
-        for (int b = 0; b < nct; ++b) if (h[1024 + 4 * b] < g0) g0 = h[1024 + 4 * b];
-        printf("ffn CTA timeline (ns since first start): cta sm start end\n");
-        for (int b = 0; b < nct; ++b)
-          printf("%3d sm%3lld %6lld %6lld%s", b, h[1024 + 4 * b + 2], h[1024 + 4 * b] - g0, h[1024 + 4 * b + 1] - g0, (b % 4 == 3) ? "\n" : " | ");
-        printf("\n");
-      }
       long long t0 = h[0];
       for (int i = 0; i < 64 * 16; ++i) if (h[i] && h[i] < t0) t0 = h[i];
       printf("ffn trace (cycles since first stamp): c | prod w1e w2e | mma w1f a1e w2f hf | epi a1f ldtm comp hwait hfull | st hf rd\n");
@@ -506,6 +563,44 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
   }
 #endif
   return 0;
+}
+
+// x_out = LN2(x1 + drop2(drop(relu(x1 W1^T + b1)) W2^T + b2)); also writes hid (if non-null), its non-zero gate bits
+// hmask [FF/64][M] x 64 bit (if non-null), y2 and stat2
+int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1, const void* W2, const float* b2,
+                  const float* ln_g, const float* ln_b, float eps, void* hid, void* hmask, void* y2, float* stat2, void* x_out,
+                  float p_drop, uint64_t key_ffn, uint64_t key_drop2, cudaStream_t st) {
+  if (M == 0) return 0;
+  CUtensorMap tx, tw1, tw2, thid, ty2, tout;
+  EGOT2_TRY(kmajor_map(&tx, x1, H, M, H, 128));
+  EGOT2_TRY(kmajor_map(&tw1, W1, H, FF, H, 64));      // each CTA of the pair fetches 64 rows of a stage
+  EGOT2_TRY(kmajor_map(&tw2, W2, FF, H, FF, 64));
+  EGOT2_TRY(kmajor_map(&thid, hid ? hid : y2, FF, M, FF, 128));    // never dereferenced when hid == nullptr
+  EGOT2_TRY(kmajor_map(&ty2, y2, H, M, H, 128));
+  EGOT2_TRY(kmajor_map(&tout, x_out, H, M, H, 128));
+  FfnArgs a;
+  a.M = M; a.FF = FF; a.b1 = b1; a.b2 = b2; a.ln_g = ln_g; a.ln_b = ln_b; a.eps = eps;
+  a.stat2 = stat2; a.save_hid = hid != nullptr; a.hmask = (uint2*)hmask; a.d1 = nullptr;
+  a.p_drop = p_drop; a.key_ffn = key_ffn; a.key_drop2 = key_drop2;
+  return ffn_launch(false, M, FF, tx, tw1, tw2, thid, ty2, tout, a, st);
+}
+
+// Data-gradient half of the block's backward (see the kernel comment):
+//   dhid = (d2 . W2) * gate / (1-p)  -> (M,FF) bf16;   d3 = dhid . W1 + d1  -> (M,128) bf16   (d1 == nullptr: d1 is d2)
+int ffn_fused_bwd_dx(int M, int FF, const void* d2, const void* d1, const void* hmask, const void* W1, const void* W2,
+                     float p_drop, void* dhid, void* d3, cudaStream_t st) {
+  if (M == 0) return 0;
+  CUtensorMap tx, tw1, tw2, thid, ty2;
+  EGOT2_TRY(kmajor_map(&tx, d2, H, M, H, 128));
+  EGOT2_TRY(kmajor_map(&tw1, W1, H, FF, H, 128));     // MN-major stages: 128 k-rows x 64 columns per CTA
+  EGOT2_TRY(kmajor_map(&tw2, W2, FF, H, FF, 128));
+  EGOT2_TRY(kmajor_map(&thid, dhid, FF, M, FF, 128));
+  EGOT2_TRY(kmajor_map(&ty2, d3, H, M, H, 128));
+  FfnArgs a;
+  a.M = M; a.FF = FF; a.b1 = nullptr; a.b2 = nullptr; a.ln_g = nullptr; a.ln_b = nullptr; a.eps = 0.f;
+  a.stat2 = nullptr; a.save_hid = 1; a.hmask = (uint2*)const_cast<void*>(hmask); a.d1 = (const bf16*)d1;
+  a.p_drop = p_drop; a.key_ffn = 0; a.key_drop2 = 0;
+  return ffn_launch(true, M, FF, tx, tw1, tw2, thid, ty2, ty2, a, st);
 }
 
 }  // namespace egot2

@@ -53,6 +53,10 @@ struct LayerNormBwdArgs {
   const void* dres = nullptr;    // optional (dtype): dx += dres, the gradient arriving through a residual branch
   float* dg = nullptr; float* db = nullptr;
   int x_is_f32 = 0; int dx_is_f32 = 0; int dy_is_f32 = 0;
+  // fused dropout sites (bf16 vector path; the generic path emulates them with extra launches):
+  float dy_p_drop = 0.f; uint64_t dy_drop_key = 0;       // dy *= dropmask(row*H+c)/(1-p) on load (a dropout that FOLLOWED the LN)
+  void* dx2 = nullptr; float dx2_p_drop = 0.f; uint64_t dx2_drop_key = 0;   // second output: dx * dropmask/(1-p) (a dropout that PRECEDED
+                                                                            // the residual add feeding this LN)
 };
 int layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t st);
 
@@ -89,8 +93,11 @@ int zero_f32(float* p, size_t n, cudaStream_t st);
 // fused FFN block on tcgen05 (ffn_sm100.cu): x_out = LN2(x1 + drop2(drop(relu(x1 W1^T + b1)) W2^T + b2))
 bool ffn_fused_supported(int dtype, int H, int FF);
 int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1, const void* W2, const float* b2,
-                  const float* ln_g, const float* ln_b, float eps, void* hid, void* y2, float* stat2, void* x_out,
+                  const float* ln_g, const float* ln_b, float eps, void* hid, void* hmask, void* y2, float* stat2, void* x_out,
                   float p_drop, uint64_t key_ffn, uint64_t key_drop2, cudaStream_t st);
+// dhid = (d2 . W2) * gate(hmask) / (1-p);  d3 = dhid . W1 + (d1 ? d1 : d2)
+int ffn_fused_bwd_dx(int M, int FF, const void* d2, const void* d1, const void* hmask, const void* W1, const void* W2,
+                     float p_drop, void* dhid, void* d3, cudaStream_t st);
 
 // fused small heads (head_fused.cu): pool + LN + Linear(n_out <= 32) in one kernel per direction
 bool head_fused_supported(const egot2_head_desc& d);

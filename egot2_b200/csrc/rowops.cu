@@ -159,6 +159,52 @@ __global__ void colsum_kernel(int M, int N, const T* __restrict__ x, int ldx, in
   }
 }
 
+// bf16 fast path: 128-bit loads, CW = 8 * lanes_per_row columns per CTA (N % 8 == 0, 16 B-aligned rows)
+__global__ void __launch_bounds__(256) colsum_bf16_vec_kernel(int M, int N, const bf16* __restrict__ x, int ldx, int rpg,
+                                                              int gstride, float* __restrict__ out, int rows_per_cta,
+                                                              int lanes_per_row) {
+  const int cg = threadIdx.x % lanes_per_row, rl = threadIdx.x / lanes_per_row, nrl = 256 / lanes_per_row;
+  const int n = (blockIdx.x * lanes_per_row + cg) * 8;
+  const int mbeg = blockIdx.y * rows_per_cta, mend = min(M, mbeg + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (n < N) {
+    for (int m0 = mbeg + rl; m0 < mend; m0 += 4 * nrl) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int m = m0 + u * nrl;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (m < mend) {
+          const long long r = rpg > 0 ? (long long)(m / rpg) * gstride + (m % rpg) : m;
+          v[u] = __ldg(reinterpret_cast<const uint4*>(x + r * ldx + n));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += __uint_as_float(w[k] << 16);
+          acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+        }
+      }
+    }
+  }
+  __shared__ float red[256 * 8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[(rl * lanes_per_row + cg) * 8 + i] = acc[i];
+  __syncthreads();
+  const int cw = lanes_per_row * 8;
+  for (int c = threadIdx.x; c < cw; c += 256) {
+    float t = 0.f;
+    for (int r = 0; r < nrl; ++r) t += red[r * cw + c];
+    const int nn = blockIdx.x * cw + c;
+    if (nn < N) atomicAdd(out + nn, t);
+  }
+}
+
 template <typename T>
 __global__ void dropout_kernel(T* x, size_t n, float p, float inv_keep, uint64_t key) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -275,6 +321,196 @@ __global__ void slowfast_pool_kernel(const TI* __restrict__ in, int B, int C, in
   if (lane == 0) out[((size_t)b * Tout + to) * C + c] = from_f32<TO>(s / (float)n);
 }
 
+
+// ------------------------------------------------------------------ bf16 vector LayerNorm (H in {128,256,512,1024})
+// A row is read with 128-bit loads: LPR = min(32, H/8) lanes cover one 256-column segment, so a warp holds 32/LPR rows.
+template <int HH> struct LnVec {
+  static constexpr int LPR = HH / 8 < 32 ? HH / 8 : 32;      // lanes per row
+  static constexpr int RPW = 32 / LPR;                        // rows per warp
+  static constexpr int SEG = HH / (LPR * 8);                  // 8-column segments per lane
+};
+__device__ __forceinline__ void unpack8(const uint4& v, float (&o)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { o[2 * k] = __uint_as_float(w[k] << 16); o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 o;
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+  o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+  return o;
+}
+template <int LPR> __device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int HH>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const LayerNormArgs a) {
+  typedef LnVec<HH> V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / V::LPR, cl = lane % V::LPR;
+  const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  float g[V::SEG][8], b[V::SEG][8];
+#pragma unroll
+  for (int s = 0; s < V::SEG; ++s)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int c = (s * V::LPR + cl) * 8 + i; g[s][i] = a.g[c]; b[s][i] = a.b[c]; }
+  const int rows_per_iter = gridDim.x * 8 * V::RPW;
+  for (int row = (blockIdx.x * 8 + warp) * V::RPW + sub; row < a.rows; row += rows_per_iter) {
+    const bf16* x = (const bf16*)a.x + (size_t)row * HH;
+    float v[V::SEG][8], sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x) + s * V::LPR + cl), v[s]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += v[s][i];
+    }
+    const float mean = row_sum<V::LPR>(sum) * (1.f / HH);
+    float q = 0.f;
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[s][i] - mean; q += d * d; }
+    const float rstd = rsqrtf(row_sum<V::LPR>(q) * (1.f / HH) + a.eps);
+    if (a.stat && cl == 0) { a.stat[2 * (size_t)row] = mean; a.stat[2 * (size_t)row + 1] = rstd; }
+    const float* tab = a.table ? a.table + (size_t)(row % a.table_rows) * HH : nullptr;
+    bf16* y = (bf16*)a.y + (size_t)row * HH;
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s) {
+      const int c0 = (s * V::LPR + cl) * 8;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[s][i] - mean) * rstd * g[s][i] + b[s][i];
+      if (tab) {
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(tab + c0)), t1 = __ldg(reinterpret_cast<const float4*>(tab + c0 + 4));
+        o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w; o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
+      }
+      if (a.p_drop > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= drop_scale(a.drop_key, (uint64_t)row * HH + c0 + i, a.p_drop, inv_keep);
+      }
+      reinterpret_cast<uint4*>(y)[s * V::LPR + cl] = pack8(o);
+    }
+  }
+}
+
+template <int HH>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs a) {
+  typedef LnVec<HH> V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / V::LPR, cl = lane % V::LPR;
+  __shared__ float sred[8][2][HH];
+  const float dy_keep = a.dy_p_drop > 0.f ? 1.f / (1.f - a.dy_p_drop) : 1.f;
+  const float dx2_keep = a.dx2_p_drop > 0.f ? 1.f / (1.f - a.dx2_p_drop) : 1.f;
+  float g[V::SEG][8], dg[V::SEG][8], db[V::SEG][8];
+#pragma unroll
+  for (int s = 0; s < V::SEG; ++s)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[s][i] = a.g[(s * V::LPR + cl) * 8 + i]; dg[s][i] = 0.f; db[s][i] = 0.f; }
+  const int rows_per_iter = gridDim.x * 8 * V::RPW;
+  for (int row = (blockIdx.x * 8 + warp) * V::RPW + sub; row < a.rows; row += rows_per_iter) {
+    const uint4* xp = reinterpret_cast<const uint4*>((const bf16*)a.x + (size_t)row * HH);
+    const uint4* dyp = reinterpret_cast<const uint4*>((const bf16*)a.dy + (size_t)row * HH);
+    const float mean = a.stat[2 * (size_t)row], rstd = a.stat[2 * (size_t)row + 1];
+    float xh[V::SEG][8], dyg[V::SEG][8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s) {
+      float xv[8], d[8];
+      unpack8(__ldg(xp + s * V::LPR + cl), xv);
+      unpack8(__ldg(dyp + s * V::LPR + cl), d);
+      const int c0 = (s * V::LPR + cl) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (a.dy_p_drop > 0.f) d[i] *= drop_scale(a.dy_drop_key, (uint64_t)row * HH + c0 + i, a.dy_p_drop, dy_keep);
+        xh[s][i] = (xv[i] - mean) * rstd;
+        dyg[s][i] = d[i] * g[s][i];
+        dg[s][i] += d[i] * xh[s][i];
+        db[s][i] += d[i];
+        s1 += dyg[s][i];
+        s2 += dyg[s][i] * xh[s][i];
+      }
+    }
+    s1 = row_sum<V::LPR>(s1) * (1.f / HH);
+    s2 = row_sum<V::LPR>(s2) * (1.f / HH);
+    uint4* dxp = reinterpret_cast<uint4*>((bf16*)a.dx + (size_t)row * HH);
+    const uint4* drp = a.dres ? reinterpret_cast<const uint4*>((const bf16*)a.dres + (size_t)row * HH) : nullptr;
+    uint4* dx2p = a.dx2 ? reinterpret_cast<uint4*>((bf16*)a.dx2 + (size_t)row * HH) : nullptr;
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s) {
+      const int c0 = (s * V::LPR + cl) * 8;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rstd * (dyg[s][i] - s1 - xh[s][i] * s2);
+      if (drp) {
+        float r8[8];
+        unpack8(__ldg(drp + s * V::LPR + cl), r8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += r8[i];
+      }
+      const uint4 packed = pack8(o);
+      dxp[s * V::LPR + cl] = packed;
+      if (dx2p) {
+        float o2[8];
+        unpack8(packed, o2);        // the unfused sequence masks the bf16-rounded dx
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o2[i] *= drop_scale(a.dx2_drop_key, (uint64_t)row * HH + c0 + i, a.dx2_p_drop, dx2_keep);
+        dx2p[s * V::LPR + cl] = pack8(o2);
+      }
+    }
+  }
+  if (a.dg) {
+    // fold the RPW rows a warp holds side by side, then the 8 warps through shared memory, then one atomic per column
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = V::LPR; o < 32; o <<= 1) {
+          dg[s][i] += __shfl_xor_sync(0xffffffffu, dg[s][i], o);
+          db[s][i] += __shfl_xor_sync(0xffffffffu, db[s][i], o);
+        }
+        if (sub == 0) { sred[warp][0][(s * V::LPR + cl) * 8 + i] = dg[s][i]; sred[warp][1][(s * V::LPR + cl) * 8 + i] = db[s][i]; }
+      }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * HH; c += 256) {
+      const int which = c / HH, col = c % HH;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sred[w][which][col];
+      atomicAdd((which ? a.db : a.dg) + col, t);
+    }
+  }
+}
+
+template <int HH> int ln_fwd_vec_launch(const LayerNormArgs& a, cudaStream_t st) {
+  const int rows_per_cta = 8 * LnVec<HH>::RPW;
+  int grid = (a.rows + rows_per_cta - 1) / rows_per_cta;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  ProfScope prof(st, "ln_fwd rows%d H%d", a.rows, a.H);
+  ln_fwd_vec_kernel<HH><<<grid, 256, 0, st>>>(a);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+template <int HH> int ln_bwd_vec_launch(const LayerNormBwdArgs& a, cudaStream_t st) {
+  const int rows_per_cta = 8 * LnVec<HH>::RPW;
+  int grid = (a.rows + rows_per_cta - 1) / rows_per_cta;
+  const int cap = sm_count() * 4;             // every CTA ends with 2H global atomics on the same addresses
+  if (grid > cap) grid = cap;
+  ProfScope prof(st, "ln_bwd rows%d H%d", a.rows, a.H);
+  ln_bwd_vec_kernel<HH><<<grid, 256, 0, st>>>(a);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+inline bool ln_vec_ok(int dtype, int H, const void* p0, const void* p1, const void* p2, const void* p3) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return dtype == EGOT2_BF16 && (H == 128 || H == 256 || H == 512 || H == 1024) && al(p0) && al(p1) && al(p2) && al(p3);
+}
+
 template <int NPL> int ln_fwd_dispatch(const LayerNormArgs& a, cudaStream_t st) {
   const int grid = row_grid(a.rows);
   ProfScope prof(st, "ln_fwd rows%d H%d", a.rows, a.H);
@@ -307,6 +543,14 @@ template <int NPL> int ln_bwd_dispatch(const LayerNormBwdArgs& a, cudaStream_t s
 int layernorm_fwd(const LayerNormArgs& a, cudaStream_t st) {
   EGOT2_CHECK(a.H % 32 == 0 && a.H <= 1024, "layernorm: H=%d must be a multiple of 32 and <= 1024", a.H);
   if (a.rows == 0) return 0;
+  if (!a.x_is_f32 && ln_vec_ok(a.dtype, a.H, a.x, a.y, a.table, nullptr)) {
+    switch (a.H) {
+      case 128: return ln_fwd_vec_launch<128>(a, st);
+      case 256: return ln_fwd_vec_launch<256>(a, st);
+      case 512: return ln_fwd_vec_launch<512>(a, st);
+      case 1024: return ln_fwd_vec_launch<1024>(a, st);
+    }
+  }
   switch (a.H / 32) {
     case 1: return ln_fwd_dispatch<1>(a, st);
     case 2: return ln_fwd_dispatch<2>(a, st);
@@ -321,6 +565,31 @@ int layernorm_fwd(const LayerNormArgs& a, cudaStream_t st) {
 int layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t st) {
   EGOT2_CHECK(a.H % 32 == 0 && a.H <= 1024, "layernorm_bwd: H=%d must be a multiple of 32 and <= 1024", a.H);
   if (a.rows == 0) return 0;
+  if (!a.x_is_f32 && !a.dy_is_f32 && !a.dx_is_f32 && ln_vec_ok(a.dtype, a.H, a.x, a.dy, a.dx, a.dres) &&
+      (reinterpret_cast<uintptr_t>(a.dx2) & 15) == 0) {
+    switch (a.H) {
+      case 128: return ln_bwd_vec_launch<128>(a, st);
+      case 256: return ln_bwd_vec_launch<256>(a, st);
+      case 512: return ln_bwd_vec_launch<512>(a, st);     // H = 1024 would need 64 KB of static reduction smem
+    }
+  }
+  // generic path: the fused dropout sites become separate launches around the LayerNorm kernel
+  if (a.dy_p_drop > 0.f || a.dx2) {
+    LayerNormBwdArgs b = a;
+    b.dy_p_drop = 0.f; b.dx2 = nullptr;
+    const size_t n = (size_t)a.rows * a.H;
+    if (a.dy_p_drop > 0.f) {
+      EGOT2_CHECK(!a.dy_is_f32, "layernorm_bwd: fused dy dropout needs dtype dy");
+      EGOT2_TRY(dropout_inplace(a.dtype, const_cast<void*>(a.dy), n, a.dy_p_drop, a.dy_drop_key, st));
+    }
+    EGOT2_TRY(layernorm_bwd(b, st));
+    if (a.dx2) {
+      EGOT2_CHECK(!a.dx_is_f32, "layernorm_bwd: fused dx2 dropout needs dtype dx");
+      EGOT2_CUDA(cudaMemcpyAsync(a.dx2, a.dx, n * dtype_size(a.dtype), cudaMemcpyDeviceToDevice, st));
+      EGOT2_TRY(dropout_inplace(a.dtype, a.dx2, n, a.dx2_p_drop, a.dx2_drop_key, st));
+    }
+    return 0;
+  }
   switch (a.H / 32) {
     case 1: return ln_bwd_dispatch<1>(a, st);
     case 2: return ln_bwd_dispatch<2>(a, st);
@@ -348,6 +617,20 @@ int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, cu
 
 int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int gstride, float* out, cudaStream_t st) {
   if (M == 0 || N == 0) return 0;
+  if (dtype == EGOT2_BF16 && N % 8 == 0 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int lanes_per_row = N >= 256 ? 32 : (N >= 128 ? 16 : (N >= 64 ? 8 : (N >= 32 ? 4 : (N >= 16 ? 2 : 1))));
+    const int col_blocks = (N + lanes_per_row * 8 - 1) / (lanes_per_row * 8);
+    int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
+    int rows_per_cta = (M + row_blocks - 1) / row_blocks;
+    const int min_rows = 4 * (256 / lanes_per_row);
+    if (rows_per_cta < min_rows) rows_per_cta = min_rows;
+    row_blocks = (M + rows_per_cta - 1) / rows_per_cta;
+    ProfScope prof(st, "colsum M%d N%d", M, N);
+    colsum_bf16_vec_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>(M, N, (const bf16*)x, ldx, rpg, gstride, out,
+                                                                        rows_per_cta, lanes_per_row);
+    EGOT2_LAUNCH_CHECK();
+    return 0;
+  }
   const int col_blocks = (N + 63) / 64;
   int row_blocks = (sm_count() * 8 + col_blocks - 1) / col_blocks;
   int rows_per_cta = (M + row_blocks - 1) / row_blocks;

@@ -280,6 +280,8 @@ class TranslatorEngine:
             ls.hid = buf(f"hid{i}", (M, FF), tdt).data_ptr()
             ls.y2 = buf(f"y2_{i}", (M, H), tdt).data_ptr()
             ls.stat2 = buf(f"stat2_{i}", (M, 2), torch.float32).data_ptr()
+            if self.dtype == "bf16" and H == 128 and FF % 128 == 0:     # gate bits of the fused tcgen05 FFN
+                ls.hid_mask = buf(f"hmask{i}", (FF // 64, M, 2), torch.int32).data_ptr()
             x_out = buf(f"x{i + 1}", (B, T, H), tdt)
             L.call("egot2_encoder_layer_fwd", C.byref(ld), C.byref(lp), x.data_ptr(), x_out.data_ptr(), C.byref(ls),
                    None, 0, st)

@@ -166,6 +166,9 @@ typedef struct {                      /* activations kept for backward; caller-a
   void* hid;                          /* (B*T, FF) dtype: dropout(relu(linear1(x1))) */
   void* y2;                           /* (B*T, H) dtype: x1 + dropout2(linear2(hid)), LN2 input */
   float* stat2;                       /* (B*T, 2) */
+  void* hid_mask;                     /* optional (FF/64, B*T) x 64 bit: hid != 0 (ReLU gate x dropout keep).  Written by the
+                                         fused tcgen05 FFN (bf16, H = 128, FF % 128 == 0); with it the backward runs the fused
+                                         data-gradient kernel.  NULL: unfused backward from `hid`. */
 } egot2_layer_saved;
 
 size_t egot2_encoder_layer_workspace_bytes(const egot2_layer_desc* d, int backward);
