@@ -35,7 +35,7 @@ int suggest_split_k(int M, int N, int K) {
   const int tile = (M <= 64 || N <= 64) ? 64 : 128;
   const long long tiles = (long long)((M + tile - 1) / tile) * ((N + tile - 1) / tile);
   long long want = (2LL * sm_count() + tiles - 1) / tiles;
-  long long max_by_k = K / 256;
+  long long max_by_k = K / 128;                 // at least two 64-row k-blocks per split
   if (want > max_by_k) want = max_by_k;
   if (want < 1) want = 1;
   if (want > 64) want = 64;
@@ -281,12 +281,14 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
     cast_buf = ws.take(egot2_embed_workspace_bytes(d, 1) - 256);
     EGOT2_CHECK(ws.ok(), "embed_bwd: workspace too small (%zu < %zu)", ws_bytes, ws.off);
   }
-  if (d->training && d->p_embed > 0.f)
-    EGOT2_TRY(dropout_inplace(d->dtype, dx, n, d->p_embed, site_key(d->seed, SITE_EMBED, 0), st));
-  if (g->tok_table) EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dx, g->tok_table, st));
+  // the embedding dropout's mask (applied after the LN + table add in the forward) is regenerated by both consumers of
+  // dx instead of a separate in-place pass
+  const float pe = (d->training && d->p_embed > 0.f) ? d->p_embed : 0.f;
+  const uint64_t ke = site_key(d->seed, SITE_EMBED, 0);
+  if (g->tok_table) EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dx, g->tok_table, pe, ke, st));
   LayerNormBwdArgs l;
   l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = saved->z; l.stat = saved->stat; l.g = in->ln_g;
-  l.dy = dx; l.dx = dx; l.dg = g->ln_g; l.db = g->ln_b;
+  l.dy = dx; l.dx = dx; l.dg = g->ln_g; l.db = g->ln_b; l.dy_p_drop = pe; l.dy_drop_key = ke;
   EGOT2_TRY(layernorm_bwd(l, st));
   if (d->training && d->p_feat > 0.f)
     EGOT2_TRY(dropout_inplace(d->dtype, dx, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
@@ -498,7 +500,8 @@ extern "C" int egot2_head_rows(const egot2_head_desc* d) { return d->pool ? d->B
 
 extern "C" size_t egot2_head_workspace_bytes(const egot2_head_desc* d) {
   const size_t rows = (size_t)egot2_head_rows(d), es = dtype_size(d->dtype);
-  return align_up(rows * d->n_out * es) + align_up(rows * d->H * es) + align_up(rows * d->H * 4) + 256;
+  const size_t ldl = ((size_t)d->n_out + 7) / 8 * 8;      // low-precision dlogits rows are padded to 16 B for TMA
+  return align_up(rows * ldl * es) + align_up(rows * d->H * es) + align_up(rows * d->H * 4) + 256;
 }
 
 extern "C" int egot2_head_loss_fwd(const egot2_head_desc* d, const egot2_head_in* in, const egot2_head_out* out,
@@ -544,20 +547,23 @@ extern "C" int egot2_head_loss_bwd(const egot2_head_desc* d, const egot2_head_in
   }
   EGOT2_CHECK(workspace && ws_bytes >= egot2_head_workspace_bytes(d) - 256, "head_loss_bwd: workspace too small");
   Carver ws(workspace, ws_bytes);
-  void* dl_lp = ws.take((size_t)rows * d->n_out * es);
+  const int ldl = d->dtype == EGOT2_F32 ? d->n_out : (d->n_out + 7) / 8 * 8;
+  void* dl_lp = ws.take((size_t)rows * ldl * es);
   void* dg = ws.take((size_t)rows * d->H * es);
   float* dpooled = (float*)ws.take((size_t)rows * d->H * 4);
   if (d->loss != EGOT2_LOSS_NONE)
     EGOT2_TRY(loss_bwd(*d, rows, saved->logits, in->labels, in->class_weight, saved->loss, dloss_scale, dlogits, st));
   const void* dl = dlogits;
   if (d->dtype != EGOT2_F32) {
-    EGOT2_TRY(cast_f32_to(d->dtype, dlogits, dl_lp, (size_t)rows * d->n_out, st));
+    // bf16 copy with rows padded to a multiple of 8 elements: n_out = 20 x 593 = 11860 would otherwise miss the TMA
+    // 16-byte pitch rule and push both head-gradient GEMMs onto the CUDA-core path
+    EGOT2_TRY(cast_rows_f32_to_bf16(dlogits, rows, d->n_out, dl_lp, ldl, st));
     dl = dl_lp;
   }
-  if (g->w) EGOT2_TRY(wgrad(d->dtype, rows, d->n_out, d->H, dl, d->n_out, 0, 0, saved->g, d->H, 0, 0, g->w, st));
+  if (g->w) EGOT2_TRY(wgrad(d->dtype, rows, d->n_out, d->H, dl, ldl, 0, 0, saved->g, d->H, 0, 0, g->w, st));
   if (g->b) EGOT2_TRY(colsum_accum(EGOT2_F32, rows, d->n_out, dlogits, d->n_out, 0, 0, g->b, st));
   {
-    GemmArgs m; m.M = rows; m.N = d->H; m.K = d->n_out; m.A = dl; m.lda = d->n_out; m.B = in->w; m.ldb = d->H; m.trans_b = 0;
+    GemmArgs m; m.M = rows; m.N = d->H; m.K = d->n_out; m.A = dl; m.lda = ldl; m.B = in->w; m.ldb = d->H; m.trans_b = 0;
     m.C = dg; m.ldc = d->H; m.in_dtype = d->dtype; m.out_dtype = d->dtype;
     EGOT2_TRY(gemm(m, st));
   }

@@ -418,7 +418,12 @@ int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
   if (a.accumulate && a.out_dtype != EGOT2_F32) return -1;
   if (a.split_k > 1 && (!a.accumulate || a.relu || a.mask || a.p_drop > 0.f)) return -1;
   // short-K problems are epilogue/store bound: 128-wide tiles run two CTAs per SM; long-K ones amortise A over 256 columns
-  const int bn = a.N <= 64 ? 64 : ((a.N <= 128 || a.K <= 512) ? 128 : ((a.N % 256 == 0 || a.N > 512) ? 256 : 128));
+  int bn = a.N <= 64 ? 64 : ((a.N <= 128 || a.K <= 512) ? 128 : ((a.N % 256 == 0 || a.N > 512) ? 256 : 128));
+  if (a.accumulate && a.split_k > 1) {
+    // split-K weight gradients with a small output: narrower tiles until the grid covers the SMs
+    const long long mt = (a.M + BM - 1) / BM;
+    while (bn > 64 && mt * ((a.N + bn - 1) / bn) * a.split_k < sm_count()) bn >>= 1;
+  }
   CUtensorMap ma, mb;
   // A: K-major (M,K) -> box {64 k, 128 m};  MN-major (K,M) -> box {64 m, 64 k}
   if (kg.on) {

@@ -78,7 +78,8 @@ int attention_bwd(int dtype, int B, int T, int H, int heads, const void* qkv, co
                   cudaStream_t st);
 
 // dtable[t,:] += sum_b dy[b,t,:]   (gradient of the (T,H) token table added after the embed LN)
-int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, cudaStream_t st);
+// p_drop > 0: dy has NOT had the embedding dropout's mask applied yet; the kernel applies it while reading
+int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, float p_drop, uint64_t drop_key, cudaStream_t st);
 // column sums: out[n] += sum_m x[m,n]   (bias gradients)
 int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int gstride, float* out, cudaStream_t st);
 // in-place x *= dropmask/(1-p) over n elements (idx = linear element index)
@@ -89,6 +90,8 @@ int pool_bwd(int dtype, int B, int T, int H, int pool, int row_tokens, const flo
 int cast_f32_to(int dtype, const float* src, void* dst, size_t n, cudaStream_t st);
 int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t st);
 int zero_f32(float* p, size_t n, cudaStream_t st);
+// dst[r, 0..ld) = bf16(src[r, 0..n)) followed by zeros (ld >= n)
+int cast_rows_f32_to_bf16(const float* src, int rows, int n, void* dst, int ld, cudaStream_t st);
 
 // fused FFN block on tcgen05 (ffn_sm100.cu): x_out = LN2(x1 + drop2(drop(relu(x1 W1^T + b1)) W2^T + b2))
 bool ffn_fused_supported(int dtype, int H, int FF);

@@ -101,13 +101,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) ln_bwd_kernel(const LayerNo
 // ------------------------------------------------------------------ misc elementwise / reductions
 template <typename TT>
 __global__ void table_grad_kernel(int B, int T, int H, int clips_per_cta, const TT* __restrict__ dy,
-                                  float* __restrict__ dtable) {
+                                  float* __restrict__ dtable, float p_drop, uint64_t drop_key) {
   // CTA (t, chunk): sums its chunk of clips for token t, then one atomic per column
   const int t = blockIdx.x;
   const int b0 = blockIdx.y * clips_per_cta, b1 = min(B, b0 + clips_per_cta);
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float s = 0.f;
-    for (int b = b0; b < b1; ++b) s += to_f32(dy[((size_t)b * T + t) * H + c]);
+    if (p_drop > 0.f) {       // dy is read BEFORE the embedding dropout's mask was applied: apply it on the fly
+      const float inv_keep = 1.f / (1.f - p_drop);
+      for (int b = b0; b < b1; ++b) {
+        const size_t idx = ((size_t)b * T + t) * H + c;
+        s += to_f32(dy[idx]) * drop_scale(drop_key, idx, p_drop, inv_keep);
+      }
+    } else {
+      for (int b = b0; b < b1; ++b) s += to_f32(dy[((size_t)b * T + t) * H + c]);
+    }
     atomicAdd(dtable + (size_t)t * H + c, s);
   }
 }
@@ -251,6 +259,13 @@ __global__ void cast_to_bf16_kernel(const float* __restrict__ s, bf16* __restric
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (size_t j = n & ~(size_t)3; j < n; ++j) d[j] = __float2bfloat16_rn(s[j]);
+}
+__global__ void cast_rows_kernel(const float* __restrict__ s, int rows, int n, bf16* __restrict__ d, int ld) {
+  const size_t total = (size_t)rows * ld;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / ld; const int c = (int)(i % ld);
+    d[i] = c < n ? __float2bfloat16_rn(s[r * n + c]) : __float2bfloat16_rn(0.f);
+  }
 }
 __global__ void cast_to_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -601,7 +616,7 @@ int layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t st) {
   EGOT2_CHECK(false, "layernorm_bwd: H=%d not in {32,64,128,256,512,1024}", a.H);
 }
 
-int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, cudaStream_t st) {
+int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, float p_drop, uint64_t drop_key, cudaStream_t st) {
   const int nt = H < 256 ? ((H + 31) / 32 * 32) : 256;
   int chunks = (4 * sm_count() + T - 1) / T;           // ~4 CTAs per SM
   if (chunks > B) chunks = B;
@@ -609,8 +624,8 @@ int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, cu
   const int per = (B + chunks - 1) / chunks;
   dim3 grid(T, (B + per - 1) / per);
   ProfScope prof(st, "table_grad B%d T%d H%d", B, T, H);
-  if (dtype == EGOT2_F32) table_grad_kernel<float><<<grid, nt, 0, st>>>(B, T, H, per, (const float*)dy, dtable);
-  else table_grad_kernel<bf16><<<grid, nt, 0, st>>>(B, T, H, per, (const bf16*)dy, dtable);
+  if (dtype == EGOT2_F32) table_grad_kernel<float><<<grid, nt, 0, st>>>(B, T, H, per, (const float*)dy, dtable, p_drop, drop_key);
+  else table_grad_kernel<bf16><<<grid, nt, 0, st>>>(B, T, H, per, (const bf16*)dy, dtable, p_drop, drop_key);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -700,6 +715,14 @@ int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t s
   ProfScope prof(st, "cast_to_f32 n%zu", n);
   if (dtype == EGOT2_BF16) cast_to_f32_kernel<<<ew_grid(n), 256, 0, st>>>((const bf16*)src, dst, n);
   else copy_f32_kernel<<<ew_grid(n), 256, 0, st>>>((const float*)src, dst, n);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
+int cast_rows_f32_to_bf16(const float* src, int rows, int n, void* dst, int ld, cudaStream_t st) {
+  if (rows == 0 || n == 0) return 0;
+  ProfScope prof(st, "cast_rows rows%d n%d", rows, n);
+  cast_rows_kernel<<<ew_grid((size_t)rows * ld), 256, 0, st>>>(src, rows, n, (bf16*)dst, ld);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
