@@ -12,7 +12,8 @@ all-reduce of the flat gradient arena) + one fused Adam launch.
 Lines printed by rank 0 (ONE JSON line):
   value     whole-job clips/s, features already resident in HBM (rotating pool larger than L2), CUDA-event timed,
             max over ranks;
-  e2e       same step driven from pinned HOST buffers (H2D of features+labels and D2H of the loss inside the timed region);
+  e2e       same step driven from pinned HOST buffers through TranslatorTrainer.train_stream_host: every step's H2D copy of
+            features+labels and D2H read of its loss are inside the timed region (double-buffered on a copy stream);
   roofline  the dominant kernel of the step (largest share of the summed kernel time), timed by CUDA events that the
             library records around each launch on the launch stream during a pass of eager steps after the timed region;
   cpu_baseline  the CPU oracle (torch restatement of the reference translator) on this box's host cores.
@@ -265,14 +266,13 @@ def main():
         host.append(([f[s.name].pin_memory() for s in spec.segments],
                      synth.make_labels(spec, B, seg, seed=5000 + 10 * rank + i).pin_memory()))
     e2e_steps = max(5, min(args.steps, 30))
-    for i in range(3):
-        tr.train_step_host(*host[i % 2], slot=i % 2)
+    tr.train_stream_host(host, 4)
     barrier()
     e0.record()
-    for i in range(e2e_steps):
-        tr.train_step_host(*host[i % 2], slot=i % 2)
+    losses = tr.train_stream_host(host, e2e_steps)        # returns after the last loss has been read back
     e1.record()
     barrier()
+    assert len(losses) == e2e_steps and all(l == l for l in losses), "e2e: loss read-back failed"
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)

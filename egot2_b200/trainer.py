@@ -16,6 +16,7 @@ import torch
 
 from . import _lib as L
 from .engine import Activations, TranslatorEngine
+from .parallel import allreduce_gradients
 from .specs import TranslatorSpec
 
 
@@ -104,10 +105,11 @@ class TranslatorTrainer:
 
     def _reduce_and_update(self):
         eng = self.engine
+        scale = 1.0
         if self.world > 1:
-            torch.distributed.all_reduce(eng.arena.grad, group=self.pg)     # ONE flat NCCL all-reduce (NVLink)
+            scale = allreduce_gradients(eng.arena.grad, self.pg)            # ONE flat NCCL all-reduce (NVLink)
         eng.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
-                      self.hp["weight_decay"], grad_scale=1.0 / self.world)
+                      self.hp["weight_decay"], grad_scale=scale)
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) step
     def train_step_host(self, host_feats: Sequence[torch.Tensor], host_labels: torch.Tensor, slot: int = 0) -> float:
@@ -123,6 +125,37 @@ class TranslatorTrainer:
         bufs[-1].copy_(host_labels, non_blocking=True)
         loss = self.train_step(bufs[:-1], bufs[-1], graph_key=-(slot + 1) if self.use_graphs else None)
         return float(loss.item())
+
+    def train_stream_host(self, host_batches, n_steps: int) -> List[float]:
+        """End-to-end training over a stream of pinned HOST batches [(feats..., labels)], double-buffered: the H2D
+        copy of step i+1 runs on a copy stream while step i computes, and every step's loss comes back with an
+        asynchronous D2H copy that is only read at the end.  Every step still pays its own H2D + D2H."""
+        cur = torch.cuda.current_stream(self.device)
+        ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        if not hasattr(self, "_loss_host") or self._loss_host.numel() < n_steps:
+            self._loss_host = torch.empty(max(n_steps, 1), dtype=torch.float32).pin_memory()
+        for i in range(n_steps):
+            slot = i % 2
+            host_feats, host_labels = host_batches[i % len(host_batches)]
+            bufs = self._h2d.get(slot)
+            if bufs is None:
+                bufs = [torch.empty(f.shape, device=self.device, dtype=f.dtype) for f in host_feats]
+                bufs.append(torch.empty(host_labels.shape, device=self.device, dtype=torch.int64))
+                self._h2d[slot] = bufs
+            with torch.cuda.stream(self.copy_stream):
+                if i >= 2:
+                    self.copy_stream.wait_event(ev_done[slot])      # the step that last used this slot has finished
+                for b, f in zip(bufs[:-1], host_feats):
+                    b.copy_(f, non_blocking=True)
+                bufs[-1].copy_(host_labels, non_blocking=True)
+                ev_h2d[slot].record(self.copy_stream)
+            cur.wait_event(ev_h2d[slot])
+            loss = self.train_step(bufs[:-1], bufs[-1], graph_key=-(slot + 1) if self.use_graphs else None)
+            self._loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+            ev_done[slot].record(cur)
+        cur.synchronize()
+        return self._loss_host[:n_steps].tolist()
 
     # ------------------------------------------------------------------ inference
     @torch.no_grad()

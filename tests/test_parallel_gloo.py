@@ -1,0 +1,83 @@
+"""World-size-2 gloo tests (CPU) of the data-parallel host logic: clip sharding with no data-path collective, the
+single flat gradient all-reduce, and output gathering.  The per-rank compute is the CPU oracle (test infrastructure);
+on the GPUs the same functions run over NCCL with libegot2 producing the gradients."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from egot2_b200 import parallel as par
+
+
+def test_shard_range_covers_and_balances():
+    for n in (0, 1, 7, 256, 257):
+        for world in (1, 2, 3, 8):
+            spans = [par.shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        par.shard_range(4, 2, 2)
+
+
+def _flat_grads(case_name, lo, hi):
+    """Oracle loss + flat gradient (fixed parameter order) on clips [lo, hi) of a golden case."""
+    from oracle.cases import CASES, case_inputs, oracle_forward_loss
+    case = CASES[case_name]
+    sd, feats, labels, extra = case_inputs(case)
+    feats = {k: v[lo:hi] for k, v in feats.items()}
+    extra = {k: (v[lo:hi] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == labels.shape[0] else v) for k, v in extra.items()}
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out, loss = oracle_forward_loss(case, P, feats, labels[lo:hi], extra)
+    names = sorted(P)
+    grads = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
+    flat = torch.cat([(g if g is not None else torch.zeros_like(P[k])).reshape(-1) for k, g in zip(names, grads)])
+    return out.detach(), float(loss), flat, labels[lo:hi]
+
+
+def _worker(rank, world, port, case_name, n_clips, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        lo, hi = par.shard_range(n_clips, world, rank)
+        out, loss, flat, labels = _flat_grads(case_name, lo, hi)
+        # (1) DDP semantics: mean over ranks
+        g = flat.clone()
+        scale = par.allreduce_gradients(g)
+        ddp = g * scale
+        # (2) exact full-batch gradient for the class-weighted CE: weight = the shard's summed class weights
+        cw = torch.tensor([0.266, 0.734])
+        g2 = flat.clone()
+        scale2 = par.allreduce_gradients(g2, local_weight=float(cw[labels].sum()))
+        exact = g2 * scale2
+        full_out = par.gather_outputs(out, n_clips)
+        if rank == 0:
+            q.put((ddp, exact, full_out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gradient_allreduce_matches_single_process():
+    case_name, n_clips, world = "hhi3_h128_l1", 5, 2          # 5 clips over 2 ranks: unequal shards (3 + 2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case_name, n_clips, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ddp, exact, full_out = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process references
+    out_all, _, flat_all, _ = _flat_grads(case_name, 0, n_clips)
+    parts = [_flat_grads(case_name, *par.shard_range(n_clips, world, r))[2] for r in range(world)]
+    assert torch.allclose(ddp, sum(parts) / world, rtol=1e-5, atol=1e-7)           # reference DDP: mean of rank gradients
+    assert torch.allclose(exact, flat_all, rtol=2e-4, atol=1e-6)                   # weighted: the full-batch gradient
+    assert torch.equal(full_out, out_all) or torch.allclose(full_out, out_all, rtol=1e-6, atol=1e-7)
