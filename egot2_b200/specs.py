@@ -48,6 +48,9 @@ class TranslatorSpec:
     n_task_embed: int = 0
     head_groups: Tuple[int, ...] = ()   # LTA: class-group sizes inside each of the Z heads (115, 478)
     n_heads_out: int = 1                # LTA: Z = number of independent Linear heads
+    decoder_layers: int = 0             # EgoT2-g: nn.TransformerDecoder depth (head == "decoder")
+    vocab: int = 0                      # EgoT2-g: task-prompt vocabulary size (7)
+    g_mode: str = ""                    # EgoT2-g: "lam" | "ttm" | "asd" (which forward of the shared model this spec runs)
 
     @property
     def fixed_tokens(self) -> Optional[int]:
@@ -65,7 +68,7 @@ class TranslatorSpec:
             # reference registration order: proj_lam, proj_ttm[, proj_asd], task_embed, ..., ln, linear_head
             names = [s.name for s in self.segments]
             for nm in ("lam", "ttm", "asd"):
-                if nm in names:
+                if nm in names or self.family == "hhi_g":      # EgoT2-g: one parameter set behind all three modes
                     out[f"proj_{nm}.weight"] = (H, 256)
                     out[f"proj_{nm}.bias"] = (H,)
             out["task_embed"] = (1, self.n_task_embed, H)
@@ -93,9 +96,27 @@ class TranslatorSpec:
             out[p + "norm1.bias"] = (H,)
             out[p + "norm2.weight"] = (H,)
             out[p + "norm2.bias"] = (H,)
+        for i in range(self.decoder_layers):
+            p = f"transformer_decoder.layers.{i}."
+            for att in ("self_attn", "multihead_attn"):
+                out[p + att + ".in_proj_weight"] = (3 * H, H)
+                out[p + att + ".in_proj_bias"] = (3 * H,)
+                out[p + att + ".out_proj.weight"] = (H, H)
+                out[p + att + ".out_proj.bias"] = (H,)
+            out[p + "linear1.weight"] = (FF, H)
+            out[p + "linear1.bias"] = (FF,)
+            out[p + "linear2.weight"] = (H, FF)
+            out[p + "linear2.bias"] = (H,)
+            for nrm in ("norm1", "norm2", "norm3"):
+                out[p + nrm + ".weight"] = (H,)
+                out[p + nrm + ".bias"] = (H,)
         if self.family != "hoi_pnr":
             out["ln.weight"] = (H,)
             out["ln.bias"] = (H,)
+        if self.family == "hhi_g":
+            out["embedding.weight"] = (self.vocab, H)
+            out["fc.weight"] = (self.vocab, H)
+            out["fc.bias"] = (self.vocab,)
         if self.family in ("hhi_ttm", "hhi_asd"):
             out["linear_head.0.weight"] = (H,)
             out["linear_head.0.bias"] = (H,)
@@ -158,6 +179,20 @@ def hhi_asd_spec(hidden=128, heads=4, layers=1, dropout=0.5, ffn=2048) -> Transl
             Segment("lam", 256, "proj_lam", None, 1))
     return TranslatorSpec("hhi_asd", hidden, heads, ffn, layers, segs, "task_sinusoid",
                           "transformer_encoder.", "tokens", hidden, False, dropout, 0.1, 0.0, 0.0, 3)
+
+
+def hhi_g_spec(hidden=256, heads=4, layers=3, dropout=0.1, mode="ttm", ffn=2048, vocab=7) -> TranslatorSpec:
+    """EgoT2-g TaskTranslationPromptTransformer (HHI/models/multitask/task_prompt_model.py:174-293): encoder over
+    (lam id0, ttm id1, asd id2) tokens - or the LAM tokens alone for mode "lam" (:231-234) - and an nn.TransformerDecoder
+    over the 2-token task prompt; mode "asd" regroups the memory to 3 tokens per frame (:251-257)."""
+    assert mode in ("lam", "ttm", "asd")
+    if mode == "lam":
+        segs = (Segment("lam", 256, "proj_lam", None, 0),)
+    else:
+        segs = (Segment("lam", 256, "proj_lam", None, 0), Segment("ttm", 256, "proj_ttm", None, 1),
+                Segment("asd", 256, "proj_asd", None, 2))
+    return TranslatorSpec("hhi_g", hidden, heads, ffn, layers, segs, "task_sinusoid", "transformer_encoder.", "decoder",
+                          vocab, False, dropout, 0.1, 0.0, 0.0, 3, decoder_layers=layers, vocab=vocab, g_mode=mode)
 
 
 def hoi_pnr_spec(hidden=128, layers=6, n_cls=16, feat_dropout=0.5, tr_dropout=0.1) -> TranslatorSpec:

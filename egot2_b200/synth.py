@@ -32,11 +32,11 @@ def make_state_dict(spec: TranslatorSpec, seed: int = 0) -> Dict[str, torch.Tens
     out: Dict[str, torch.Tensor] = {}
     for name, shape in spec.param_shapes().items():
         g = _gen(seed, name)
-        if name in ("task_embed", "pe"):
+        if name in ("task_embed", "pe", "embedding.weight"):
             t = torch.randn(shape, generator=g)
-        elif name.endswith("norm1.weight") or name.endswith("norm2.weight") or name in ("ln.weight", "linear_head.0.weight"):
+        elif name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("norm3.weight") or name in ("ln.weight", "linear_head.0.weight"):
             t = 1.0 + 0.1 * torch.randn(shape, generator=g)
-        elif name.endswith("norm1.bias") or name.endswith("norm2.bias") or name in ("ln.bias", "linear_head.0.bias"):
+        elif name.endswith("norm1.bias") or name.endswith("norm2.bias") or name.endswith("norm3.bias") or name in ("ln.bias", "linear_head.0.bias"):
             t = 0.1 * torch.randn(shape, generator=g)
         elif len(shape) >= 2:
             bound = 1.0 / math.sqrt(shape[-1])
@@ -74,4 +74,12 @@ def make_labels(spec: TranslatorSpec, batch: int, seg_tokens: Optional[Sequence[
         v = torch.randint(0, spec.head_groups[0], (batch, spec.n_heads_out, 1), generator=g)
         n = torch.randint(0, spec.head_groups[1], (batch, spec.n_heads_out, 1), generator=g)
         return torch.cat([v, n], dim=-1)
+    if spec.family == "hhi_g":
+        # task-prompt targets (rows, 3) = [task word, answer, answer] with the answers in {'0': 5, '1': 6}; the decoder
+        # reads target[:, :-1] and is scored on target[:, 1:] (HHI/tasks/multitask/video_tasktranslation.py:48-61).
+        # 'asd' scores every frame: rows = B * D (vocab: HHI/utils/utils.py:12-18)
+        rows = batch * seg_tokens[0] if spec.g_mode == "asd" else batch
+        task_tok = {"ttm": 2, "lam": 3, "asd": 4}[spec.g_mode]
+        ans = torch.randint(5, 7, (rows, 2), generator=g)
+        return torch.cat([torch.full((rows, 1), task_tok, dtype=torch.int64), ans], dim=1)
     raise ValueError(spec.family)

@@ -40,6 +40,11 @@ CASES = {c.name: c for c in [
     # BASELINE config 5 (scaled) and the shipped LTA config (H=1024, L=1)
     Case("hoi_lta_h512_l4", specs.hoi_lta_spec(512, 4, 8, 0.5), 3, (2, 2, 2, 2), 9),
     Case("hoi_lta_h1024_l1", specs.hoi_lta_spec(1024, 1, 8, 0.5), 2, (2, 2, 2, 2), 10),
+    # BASELINE config 3: HHI EgoT2-g (encoder + decoder over the task prompt), the three forwards of one step
+    Case("hhi_g_lam_h128_l2", specs.hhi_g_spec(128, 4, 2, 0.1, "lam"), 5, (7,), 11),
+    Case("hhi_g_ttm_h128_l2", specs.hhi_g_spec(128, 4, 2, 0.1, "ttm"), 3, (9, 9, 9), 11),
+    Case("hhi_g_asd_h128_l2", specs.hhi_g_spec(128, 4, 2, 0.1, "asd"), 2, (6, 6, 6), 11),
+    Case("hhi_g_ttm_h256_l3", specs.hhi_g_spec(256, 4, 3, 0.1, "ttm"), 2, (30, 30, 30), 12),
 ]}
 
 
@@ -83,6 +88,10 @@ def oracle_forward_loss(case: Case, P: Dict[str, torch.Tensor], feats, labels, e
     elif sp.family == "hoi_lta":
         out = O.hoi_lta_forward(P, feats["pnr"], feats["oscc"], feats["action"], feats["lta"], sp.heads)
         loss = O.lta_loss(out, labels, sp.head_groups)
+    elif sp.family == "hhi_g":
+        # HHI/tasks/multitask/video_tasktranslation.py:48-61: decoder input target[:, :-1], unweighted CE on target[:, 1:]
+        out = O.hhi_g_forward(P, feats, labels[:, :-1], sp.g_mode, sp.heads)          # (rows, V, 2)
+        loss = torch.nn.functional.cross_entropy(out, labels[:, 1:])
     else:
         raise ValueError(sp.family)
     return out, loss

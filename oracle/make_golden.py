@@ -42,6 +42,10 @@ def build_reference(case: Case, hhi, hoi):
         return hoi.lta4.TaskFusionMFTransformerLTA4Task(
             rs.hoi_lta_cfg(sp.hidden, sp.layers, sp.heads, sp.p_layer, sp.segments[0].tokens, sp.n_heads_out,
                            sp.head_groups, sp.p_head))
+    if sp.family == "hhi_g":
+        args = rs.hhi_args(sp.hidden, sp.heads, sp.layers, sp.p_layer, True)
+        vocab = {'</s>': 0, '<unk>': 1, 'ttm': 2, 'lam': 3, 'asd': 4, '0': 5, '1': 6}      # HHI/utils/utils.py:12-18
+        return hhi.multitask.TaskTranslationPromptTransformer(args, vocab)
     raise ValueError(sp.family)
 
 
@@ -61,6 +65,10 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         lav.load_state_dict({"criterion.weight": torch.tensor([1.0, 4.0]), "FC.weight": extra["FC.weight"],
                              "FC.bias": extra["FC.bias"]})
         loss = lav(out, labels)[0]
+    elif sp.family == "hhi_g":
+        # HHI/tasks/multitask/video_tasktranslation.py:48-61 (the three forwards share one model; one case = one of them)
+        out = m(*rs.hhi_inputs(feats), labels[:, :-1], sp.g_mode)                          # (rows, V, 2)
+        loss = torch.nn.CrossEntropyLoss()(out, labels[:, 1:])
     elif sp.family == "hoi_pnr":
         slow = extra["slow5"] if case.raw_slowfast else feats["slow"].permute(0, 2, 1)[..., None, None]
         fast = extra["fast5"] if case.raw_slowfast else \

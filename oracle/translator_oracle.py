@@ -218,6 +218,75 @@ def hoi_lta_forward(P: Params, pnr: Tensor, oscc: Tensor, action: Tensor, lta: T
 # --------------------------------------------------------------------------------------
 # losses
 # --------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------
+# EgoT2-g: TaskTranslationPromptTransformer — HHI/models/multitask/task_prompt_model.py:174-293
+# --------------------------------------------------------------------------------------
+def mha(q_in: Tensor, kv_in: Tensor, P: Params, pre: str, n_heads: int, mask: Optional[Tensor], p_drop: float,
+        training: bool) -> Tensor:
+    """nn.MultiheadAttention(query, key=value=kv_in), written batch-first (N,S,H) / (N,M,H) (same math as the
+    reference's seq-first call): packed in_proj rows q|k|v, softmax(q k^T / sqrt(dh) + mask), dropout on the
+    probabilities, out_proj."""
+    N, S, H = q_in.shape
+    M = kv_in.shape[1]
+    dh = H // n_heads
+    W, b = P[pre + "in_proj_weight"], P[pre + "in_proj_bias"]
+    q = linear(q_in, W[:H], b[:H]).reshape(N, S, n_heads, dh).transpose(1, 2)
+    k = linear(kv_in, W[H:2 * H], b[H:2 * H]).reshape(N, M, n_heads, dh).transpose(1, 2)
+    v = linear(kv_in, W[2 * H:], b[2 * H:]).reshape(N, M, n_heads, dh).transpose(1, 2)
+    s = (q * (1.0 / math.sqrt(dh))) @ k.transpose(-1, -2)
+    if mask is not None:
+        s = s + mask
+    p = _drop(torch.softmax(s, dim=-1), p_drop, training)
+    o = (p @ v).transpose(1, 2).reshape(N, S, H)
+    return linear(o, P[pre + "out_proj.weight"], P[pre + "out_proj.bias"])
+
+
+def decoder_layer(y: Tensor, mem: Tensor, P: Params, pre: str, n_heads: int, mask: Tensor, p_drop: float,
+                  training: bool) -> Tensor:
+    """nn.TransformerDecoderLayer, post-norm, ReLU (CustomDecoderLayer only forces need_weights=True, :163-172)."""
+    y = layer_norm(y + _drop(mha(y, y, P, pre + "self_attn.", n_heads, mask, p_drop, training), p_drop, training),
+                   P[pre + "norm1.weight"], P[pre + "norm1.bias"])
+    y = layer_norm(y + _drop(mha(y, mem, P, pre + "multihead_attn.", n_heads, None, p_drop, training), p_drop, training),
+                   P[pre + "norm2.weight"], P[pre + "norm2.bias"])
+    f = linear(_drop(torch.relu(linear(y, P[pre + "linear1.weight"], P[pre + "linear1.bias"])), p_drop, training),
+               P[pre + "linear2.weight"], P[pre + "linear2.bias"])
+    return layer_norm(y + _drop(f, p_drop, training), P[pre + "norm3.weight"], P[pre + "norm3.bias"])
+
+
+_G_TASK_ID = {"lam": 0, "ttm": 1, "asd": 2}     # task_prompt_model.py:234,247-249
+
+
+def hhi_g_forward(P: Params, feats: Dict[str, Tensor], target_in: Tensor, mode: str, n_heads: int, p_drop: float = 0.0,
+                  training: bool = False) -> Tensor:
+    """forward(video, ..., target, task) -> (rows, vocab, seq) logits (:271-275).
+    encode (:230-258): 'lam' uses the LAM tokens only (task id 0); otherwise cat(lam id0, ttm id1, asd id2);
+    'asd' regroups the encoder output to a 3-token memory per frame.  decode (:260-269): Embedding*sqrt(H) + PE(+dropout 0.1)
+    -> TransformerDecoder with the causal mask -> fc."""
+    order = ("lam",) if mode == "lam" else ("lam", "ttm", "asd")
+    H = P["ln.weight"].shape[0]
+    toks = []
+    for nm in order:
+        f = feats[nm]
+        x = linear(f, P[f"proj_{nm}.weight"], P[f"proj_{nm}.bias"])
+        x = layer_norm(x, P["ln.weight"], P["ln.bias"]) + P["task_embed"][:, _G_TASK_ID[nm], :]
+        x = x + sinusoid_table(f.shape[1], H).unsqueeze(0)
+        toks.append(_drop(x, 0.1, training))
+    x = torch.cat(toks, dim=1)                                    # (B, T, H)
+    mem = encoder(x, P, "transformer_encoder.", count_layers(P, "transformer_encoder."), n_heads, p_drop, training)
+    if mode == "asd":                                             # (B, 3T, H) -> (B*T, 3, H)
+        B, T3, _ = mem.shape
+        T = T3 // 3
+        mem = torch.stack([mem[:, 0:T].reshape(-1, H), mem[:, T:2 * T].reshape(-1, H), mem[:, 2 * T:3 * T].reshape(-1, H)], dim=1)
+    S = target_in.shape[1]
+    y = P["embedding.weight"][target_in] * math.sqrt(H)           # (rows, S, H)
+    y = _drop(y + sinusoid_table(S, H).unsqueeze(0), 0.1, training)
+    mask = torch.full((S, S), float("-inf")).triu(1)
+    for i in range(count_layers(P, "transformer_decoder.")):
+        y = decoder_layer(y, mem, P, f"transformer_decoder.layers.{i}.", n_heads, mask, p_drop, training)
+    out = linear(y, P["fc.weight"], P["fc.bias"])                 # (rows, S, V)
+    return out.transpose(1, 2)                                    # (rows, V, S) like the reference's permute(1, 2, 0)
+
+
 def ce_loss(logits: Tensor, target: Tensor, weight: Optional[Tensor] = None) -> Tensor:
     """nn.CrossEntropyLoss(weight=w), reduction='mean':  sum_b w[y_b]*nll_b / sum_b w[y_b].
     TTM weight [0.266,0.734]: HHI/configs/ttm/config.py:36, HHI/tasks/ttm/video_task.py:23-24."""
