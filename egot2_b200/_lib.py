@@ -60,6 +60,29 @@ class LayerSaved(C.Structure):
     _fields_ = [(n, vp) for n in ["qkv", "attn", "lse", "y1", "stat1", "x1", "hid", "y2", "stat2", "hid_mask"]]
 
 
+class DecoderDesc(C.Structure):
+    _fields_ = [("dtype", i32), ("rows", i32), ("S", i32), ("mem_rows", i32), ("M", i32), ("kv_inner", i32),
+                ("kv_outer", i32), ("kv_jstride", i32), ("kv_istride", i32), ("H", i32), ("FF", i32), ("heads", i32),
+                ("training", i32), ("layer_index", i32), ("p_drop", f32), ("ln_eps", f32), ("seed", u64)]
+
+
+_DEC_FIELDS = ["sa_in_w", "sa_out_w", "ca_in_w", "ca_out_w", "lin1_w", "lin2_w", "sa_in_b", "sa_out_b", "ca_in_b",
+               "ca_out_b", "lin1_b", "lin2_b", "norm1_g", "norm1_b", "norm2_g", "norm2_b", "norm3_g", "norm3_b"]
+
+
+class DecoderParams(C.Structure):
+    _fields_ = [(n, vp) for n in _DEC_FIELDS]
+
+
+class DecoderGrads(C.Structure):
+    _fields_ = [(n, vp) for n in _DEC_FIELDS]
+
+
+class DecoderSaved(C.Structure):
+    _fields_ = [(n, vp) for n in ["qkv", "a1", "y1", "stat1", "x1", "qc", "kvc", "a2", "y2", "stat2", "x2", "hid", "y3",
+                                  "stat3"]]
+
+
 class HeadDesc(C.Structure):
     _fields_ = [("dtype", i32), ("B", i32), ("T", i32), ("H", i32), ("pool", i32), ("row_tokens", i32),
                 ("use_ln", i32), ("n_out", i32), ("loss", i32), ("n_groups", i32), ("group_size", i32 * MAX_GROUPS),
@@ -97,6 +120,12 @@ SIGNATURES = {
     "egot2_encoder_layer_fwd": (C.c_int, [P(LayerDesc), P(LayerParams), vp, vp, P(LayerSaved), vp, sz, vp]),
     "egot2_encoder_layer_bwd": (C.c_int, [P(LayerDesc), P(LayerParams), vp, P(LayerSaved), vp, vp, P(LayerGrads),
                                           vp, sz, vp]),
+    "egot2_decoder_layer_workspace_bytes": (sz, [P(DecoderDesc)]),
+    "egot2_decoder_layer_fwd": (C.c_int, [P(DecoderDesc), P(DecoderParams), vp, vp, vp, P(DecoderSaved), vp]),
+    "egot2_decoder_layer_bwd": (C.c_int, [P(DecoderDesc), P(DecoderParams), vp, vp, P(DecoderSaved), vp, vp, vp,
+                                          P(DecoderGrads), vp, sz, vp]),
+    "egot2_prompt_embed_fwd": (C.c_int, [i32, i32, i32, i32, vp, vp, vp, f32, i32, u64, vp, vp]),
+    "egot2_prompt_embed_bwd": (C.c_int, [i32, i32, i32, i32, vp, vp, f32, i32, u64, vp, vp]),
     "egot2_head_rows": (C.c_int, [P(HeadDesc)]),
     "egot2_head_workspace_bytes": (sz, [P(HeadDesc)]),
     "egot2_head_loss_fwd": (C.c_int, [P(HeadDesc), P(HeadIn), P(HeadOut), vp]),

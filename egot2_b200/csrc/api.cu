@@ -52,6 +52,16 @@ bool g_prof_on = false;
 }  // namespace
 bool prof_enabled() { return g_prof_on; }
 ProfScope::ProfScope(cudaStream_t stream, const char* fmt, ...) : st(stream), slot(-1) {
+  static const bool trace = getenv("EGOT2_TRACE_LAUNCH") != nullptr;    // debugging: print every launcher tag to stderr
+  if (trace) {
+    char tag[96];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tag, sizeof(tag), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[egot2] %s\n", tag);
+    fflush(stderr);
+  }
   if (!g_prof_on || g_prof_n >= kProfMax) return;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;

@@ -80,7 +80,9 @@ __device__ __forceinline__ float warp_max(float v) {
 // mask(seed, site, idx): stateless, so forward and backward regenerate identical masks.
 // site ids (combined with layer index by the callers)
 enum DropSite : uint32_t {
-  SITE_FEAT = 1, SITE_EMBED = 2, SITE_ATTN = 3, SITE_DROP1 = 4, SITE_FFN = 5, SITE_DROP2 = 6, SITE_HEAD = 7
+  SITE_FEAT = 1, SITE_EMBED = 2, SITE_ATTN = 3, SITE_DROP1 = 4, SITE_FFN = 5, SITE_DROP2 = 6, SITE_HEAD = 7,
+  SITE_DEC_SELF = 8, SITE_DEC_CROSS = 9, SITE_DEC_DROP1 = 10, SITE_DEC_DROP2 = 11, SITE_DEC_DROP3 = 12, SITE_DEC_FFN = 13,
+  SITE_PROMPT = 14
 };
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;

@@ -77,6 +77,24 @@ int attention_bwd(int dtype, int B, int T, int H, int heads, const void* qkv, co
                   const void* dout, void* dqkv, float p_drop, uint64_t drop_key, void* ws, size_t ws_bytes,
                   cudaStream_t st);
 
+// EgoT2-g decoder attention (attention_small.cu): S query tokens per row against M keys per row
+struct SmallAttnArgs {
+  int dtype = EGOT2_F32;
+  int rows = 0, S = 0, M = 0, H = 0, heads = 0, causal = 0;
+  const void* q = nullptr; int ldq = 0;                       // (rows*S, .) queries, head h = columns h*dh..
+  const void* k = nullptr; const void* v = nullptr; int ldkv = 0;   // key/value rows, see the row mapping
+  int kv_inner = 1, kv_outer = 0, kv_jstride = 1, kv_istride = 0;
+  void* out = nullptr; int ldo = 0;                           // (rows*S, H)
+  float* lse = nullptr;                                       // (rows*heads*S) or null
+  float p_drop = 0.f; uint64_t drop_key = 0;
+  // backward
+  const void* dout = nullptr;                                 // (rows*S, .) with ldo
+  float* dq = nullptr; int ld_dq = 0;                         // fp32, += (atomics)
+  float* dk = nullptr; float* dv = nullptr; int ld_dkv = 0;   // fp32, += (atomics), indexed by kv row
+};
+int small_attn_fwd(const SmallAttnArgs& a, cudaStream_t st);
+int small_attn_bwd(const SmallAttnArgs& a, cudaStream_t st);
+
 // dtable[t,:] += sum_b dy[b,t,:]   (gradient of the (T,H) token table added after the embed LN)
 // p_drop > 0: dy has NOT had the embedding dropout's mask applied yet; the kernel applies it while reading
 int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, float p_drop, uint64_t drop_key, cudaStream_t st);

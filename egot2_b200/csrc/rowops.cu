@@ -375,8 +375,11 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const LayerNormArgs a) 
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const int c = (s * V::LPR + cl) * 8 + i; g[s][i] = a.g[c]; b[s][i] = a.b[c]; }
   const int rows_per_iter = gridDim.x * 8 * V::RPW;
-  for (int row = (blockIdx.x * 8 + warp) * V::RPW + sub; row < a.rows; row += rows_per_iter) {
-    const bf16* x = (const bf16*)a.x + (size_t)row * HH;
+  // the loop bound is warp-uniform (row0); a warp's last sub-row may be past the end: it computes on zeros and stores nothing
+  for (int row0 = (blockIdx.x * 8 + warp) * V::RPW; row0 < a.rows; row0 += rows_per_iter) {
+    const int row = row0 + sub;
+    const bool valid = row < a.rows;
+    const bf16* x = (const bf16*)a.x + (size_t)(valid ? row : row0) * HH;
     float v[V::SEG][8], sum = 0.f;
 #pragma unroll
     for (int s = 0; s < V::SEG; ++s) {
@@ -391,6 +394,7 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const LayerNormArgs a) 
 #pragma unroll
       for (int i = 0; i < 8; ++i) { const float d = v[s][i] - mean; q += d * d; }
     const float rstd = rsqrtf(row_sum<V::LPR>(q) * (1.f / HH) + a.eps);
+    if (!valid) continue;                 // no warp-level operation below this point
     if (a.stat && cl == 0) { a.stat[2 * (size_t)row] = mean; a.stat[2 * (size_t)row + 1] = rstd; }
     const float* tab = a.table ? a.table + (size_t)(row % a.table_rows) * HH : nullptr;
     bf16* y = (bf16*)a.y + (size_t)row * HH;
@@ -427,10 +431,14 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
 #pragma unroll
     for (int i = 0; i < 8; ++i) { g[s][i] = a.g[(s * V::LPR + cl) * 8 + i]; dg[s][i] = 0.f; db[s][i] = 0.f; }
   const int rows_per_iter = gridDim.x * 8 * V::RPW;
-  for (int row = (blockIdx.x * 8 + warp) * V::RPW + sub; row < a.rows; row += rows_per_iter) {
-    const uint4* xp = reinterpret_cast<const uint4*>((const bf16*)a.x + (size_t)row * HH);
-    const uint4* dyp = reinterpret_cast<const uint4*>((const bf16*)a.dy + (size_t)row * HH);
-    const float mean = a.stat[2 * (size_t)row], rstd = a.stat[2 * (size_t)row + 1];
+  // warp-uniform loop bound (row0): a sub-row past the end reads row0 again and contributes nothing
+  for (int row0 = (blockIdx.x * 8 + warp) * V::RPW; row0 < a.rows; row0 += rows_per_iter) {
+    const int row = row0 + sub;
+    const bool valid = row < a.rows;
+    const size_t rr = valid ? row : row0;
+    const uint4* xp = reinterpret_cast<const uint4*>((const bf16*)a.x + rr * HH);
+    const uint4* dyp = reinterpret_cast<const uint4*>((const bf16*)a.dy + rr * HH);
+    const float mean = a.stat[2 * rr], rstd = a.stat[2 * rr + 1];
     float xh[V::SEG][8], dyg[V::SEG][8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int s = 0; s < V::SEG; ++s) {
@@ -441,6 +449,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (a.dy_p_drop > 0.f) d[i] *= drop_scale(a.dy_drop_key, (uint64_t)row * HH + c0 + i, a.dy_p_drop, dy_keep);
+        if (!valid) d[i] = 0.f;
         xh[s][i] = (xv[i] - mean) * rstd;
         dyg[s][i] = d[i] * g[s][i];
         dg[s][i] += d[i] * xh[s][i];
@@ -451,6 +460,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
     }
     s1 = row_sum<V::LPR>(s1) * (1.f / HH);
     s2 = row_sum<V::LPR>(s2) * (1.f / HH);
+    if (!valid) continue;                 // no warp-level operation in the rest of the iteration
     uint4* dxp = reinterpret_cast<uint4*>((bf16*)a.dx + (size_t)row * HH);
     const uint4* drp = a.dres ? reinterpret_cast<const uint4*>((const bf16*)a.dres + (size_t)row * HH) : nullptr;
     uint4* dx2p = a.dx2 ? reinterpret_cast<uint4*>((bf16*)a.dx2 + (size_t)row * HH) : nullptr;

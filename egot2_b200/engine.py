@@ -129,6 +129,10 @@ class Activations:
     head_in: Optional[L.HeadIn] = None
     head_out: Optional[L.HeadOut] = None
     rows: int = 0
+    dec_desc: List[L.DecoderDesc] = field(default_factory=list)
+    dec_params: List[L.DecoderParams] = field(default_factory=list)
+    dec_saved: List[L.DecoderSaved] = field(default_factory=list)
+    prompt: Optional[torch.Tensor] = None
 
 
 class TranslatorEngine:
@@ -172,7 +176,8 @@ class TranslatorEngine:
     # ------------------------------------------------------------------ forward
     def forward(self, feats: Sequence[torch.Tensor], training: bool = False, seed: int = 0,
                 labels: Optional[torch.Tensor] = None, loss: int = L.LOSS_NONE,
-                class_weight: Optional[torch.Tensor] = None, persistent: bool = False) -> Activations:
+                class_weight: Optional[torch.Tensor] = None, persistent: bool = False,
+                prompt: Optional[torch.Tensor] = None) -> Activations:
         sp = self.spec
         assert len(feats) == len(sp.segments), f"expected {len(sp.segments)} feature streams"
         B = int(feats[0].shape[0])
@@ -197,7 +202,7 @@ class TranslatorEngine:
         if self.dtype == "bf16":
             self.arena.refresh_shadow()
 
-        key = (B, seg_tokens, bool(training), feat_dt, loss)
+        key = (B, seg_tokens, bool(training), feat_dt, loss, None if prompt is None else tuple(prompt.shape))
         act = self._persistent.get(key) if persistent else None
         fresh = act is None
         if fresh:
@@ -288,6 +293,10 @@ class TranslatorEngine:
             x = x_out
         t["x_last"] = x
 
+        # ---- EgoT2-g: task-prompt decoder over the encoder memory, then the vocabulary head
+        if sp.head == "decoder":
+            return self._decoder_forward(act, x, prompt, training, seed, labels, loss, buf)
+
         # ---- head
         if sp.head == "tokens":
             D0 = seg_tokens[0]
@@ -344,6 +353,141 @@ class TranslatorEngine:
         t["out"] = logits
         return act
 
+    # ------------------------------------------------------------------ EgoT2-g decoder
+    _DEC_NAMES = {"sa_in_w": "self_attn.in_proj_weight", "sa_out_w": "self_attn.out_proj.weight",
+                  "ca_in_w": "multihead_attn.in_proj_weight", "ca_out_w": "multihead_attn.out_proj.weight",
+                  "lin1_w": "linear1.weight", "lin2_w": "linear2.weight", "sa_in_b": "self_attn.in_proj_bias",
+                  "sa_out_b": "self_attn.out_proj.bias", "ca_in_b": "multihead_attn.in_proj_bias",
+                  "ca_out_b": "multihead_attn.out_proj.bias", "lin1_b": "linear1.bias", "lin2_b": "linear2.bias",
+                  "norm1_g": "norm1.weight", "norm1_b": "norm1.bias", "norm2_g": "norm2.weight", "norm2_b": "norm2.bias",
+                  "norm3_g": "norm3.weight", "norm3_b": "norm3.bias"}
+
+    def _fill_decoder_params(self, dp, i: int, grads_base: Optional[torch.Tensor] = None):
+        pre = f"transformer_decoder.layers.{i}."
+        for f, n in self._DEC_NAMES.items():
+            if grads_base is not None:
+                setattr(dp, f, self.arena.view(pre + n, grads_base).data_ptr())
+            elif f.endswith("_w"):
+                setattr(dp, f, self._mat(pre + n).data_ptr())
+            else:
+                setattr(dp, f, self._vec(pre + n).data_ptr())
+
+    def _decoder_forward(self, act: Activations, mem: torch.Tensor, prompt, training, seed, labels, loss, buf):
+        """decode() of TaskTranslationPromptTransformer (task_prompt_model.py:260-269) + CE over the vocabulary
+        (HHI/tasks/multitask/video_tasktranslation.py:48-61).  prompt: (rows, S) int64 decoder input tokens."""
+        sp = self.spec
+        if prompt is None:
+            raise L.Egot2Error("EgoT2-g translator: forward() needs the decoder prompt tokens")
+        if self.pe_buffer is None:
+            raise L.Egot2Error("EgoT2-g translator: call set_sinusoid(pos_embed.pe) first")
+        B, T, H, FF = act.B, act.T, sp.hidden, sp.ffn
+        dev, tdt, st = self.device, self.tdt, _stream()
+        t = act.t
+        if sp.g_mode == "asd":
+            if len(set(act.seg_tokens)) != 1:
+                raise L.Egot2Error("EgoT2-g 'asd' regroups the memory per frame: the three tasks need equal lengths")
+            Tt = act.seg_tokens[0]
+            rows, M, inner, outer, jstr, istr = B * Tt, 3, Tt, T, Tt, 1
+        else:
+            rows, M, inner, outer, jstr, istr = B, T, 1, T, 1, 0
+        prompt = prompt.to(device=dev, dtype=torch.int64).contiguous()
+        assert prompt.dim() == 2 and prompt.shape[0] == rows, f"prompt must be ({rows}, S), got {tuple(prompt.shape)}"
+        S = int(prompt.shape[1])
+        R = rows * S
+        act.prompt, act.rows = prompt, R
+        t["prompt"] = prompt
+        y = buf("dec_y0", (rows, S, H), tdt)
+        L.call("egot2_prompt_embed_fwd", self.dt, rows, S, H, prompt.data_ptr(), self._vec("embedding.weight").data_ptr(),
+               self.pe_buffer.data_ptr(), 0.1, int(training), int(seed), y.data_ptr(), st)
+        if not act.dec_desc:
+            for i in range(sp.decoder_layers):
+                dd = L.DecoderDesc()
+                dd.dtype, dd.rows, dd.S, dd.mem_rows, dd.M = self.dt, rows, S, B * T, M
+                dd.kv_inner, dd.kv_outer, dd.kv_jstride, dd.kv_istride = inner, outer, jstr, istr
+                dd.H, dd.FF, dd.heads, dd.layer_index, dd.ln_eps = H, FF, sp.heads, i, 1e-5
+                act.dec_desc.append(dd)
+                act.dec_params.append(L.DecoderParams())
+                act.dec_saved.append(L.DecoderSaved())
+        for i in range(sp.decoder_layers):
+            dd, dp, ds = act.dec_desc[i], act.dec_params[i], act.dec_saved[i]
+            dd.training, dd.p_drop, dd.seed = int(training), sp.p_layer, int(seed)
+            self._fill_decoder_params(dp, i)
+            for name, shape, dty in (("qkv", (R, 3 * H), tdt), ("a1", (R, H), tdt), ("y1", (R, H), tdt),
+                                     ("stat1", (R, 2), torch.float32), ("x1", (R, H), tdt), ("qc", (R, H), tdt),
+                                     ("kvc", (B * T, 2 * H), tdt), ("a2", (R, H), tdt), ("y2", (R, H), tdt),
+                                     ("stat2", (R, 2), torch.float32), ("x2", (R, H), tdt), ("hid", (R, FF), tdt),
+                                     ("y3", (R, H), tdt), ("stat3", (R, 2), torch.float32)):
+                setattr(ds, name, buf(f"dec{i}_{name}", shape, dty).data_ptr())
+            y_out = buf(f"dec_y{i + 1}", (rows, S, H), tdt)
+            L.call("egot2_decoder_layer_fwd", C.byref(dd), C.byref(dp), y.data_ptr(), mem.data_ptr(), y_out.data_ptr(),
+                   C.byref(ds), st)
+            y = y_out
+        t["dec_last"] = y
+        # vocabulary head on every prompt position: rows*S rows, no pooling, no LayerNorm
+        if act.head_desc is None:
+            hd = L.HeadDesc()
+            hd.dtype, hd.B, hd.T, hd.H, hd.pool, hd.row_tokens, hd.use_ln = self.dt, rows, S, H, 0, S, 0
+            hd.n_out, hd.ln_eps = sp.vocab, 1e-5
+            act.head_desc, act.head_in, act.head_out = hd, L.HeadIn(), L.HeadOut()
+        hd, hin, hout = act.head_desc, act.head_in, act.head_out
+        hd.loss, hd.training, hd.p_head, hd.seed = int(loss), int(training), 0.0, int(seed)
+        hin.x = y.data_ptr()
+        hin.w, hin.b = self._mat("fc.weight").data_ptr(), self._vec("fc.bias").data_ptr()
+        if loss != L.LOSS_NONE:
+            assert labels is not None
+            lab = labels.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+            assert lab.numel() == R, f"expected {R} target tokens, got {lab.numel()}"
+            t["labels"] = lab
+            hin.labels = lab.data_ptr()
+            hin.class_weight = None
+            hout.row_loss = buf("row_loss", (R, 2), torch.float32).data_ptr()
+            hout.loss = buf("loss", (2,), torch.float32).data_ptr()
+            hout.argmax = buf("argmax", (R,), torch.int32).data_ptr()
+        hout.pooled = buf("pooled", (R, H), torch.float32).data_ptr()
+        hout.stat = buf("stat_head", (R, 2), torch.float32).data_ptr()
+        hout.g = buf("g_head", (R, H), tdt).data_ptr()
+        logits = buf("logits", (R, sp.vocab), torch.float32)
+        hout.logits = logits.data_ptr()
+        L.call("egot2_head_loss_fwd", C.byref(hd), C.byref(hin), C.byref(hout), st)
+        t["out"] = logits
+        return act
+
+    def _decoder_backward(self, act: Activations, dout, dloss_scale, grad, gv) -> torch.Tensor:
+        """Backward of the vocabulary head, the decoder layers and the prompt embedding; returns d(loss)/d(memory) in the
+        activation dtype, i.e. the gradient entering the encoder."""
+        sp = self.spec
+        B, T, H = act.B, act.T, sp.hidden
+        dev, tdt, st = self.device, self.tdt, _stream()
+        t = act.t
+        rows, S = act.dec_desc[0].rows, act.dec_desc[0].S
+        R = rows * S
+        hd = act.head_desc
+        if hd.loss == L.LOSS_NONE:
+            assert dout is not None
+            dlogits = dout.to(device=dev, dtype=torch.float32).reshape(R, sp.vocab).contiguous().clone()
+        else:
+            dlogits = torch.empty((R, sp.vocab), device=dev, dtype=torch.float32)
+        hg = L.HeadGrads()
+        hg.w, hg.b = gv("fc.weight").data_ptr(), gv("fc.bias").data_ptr()
+        dy = torch.empty((rows, S, H), device=dev, dtype=tdt)
+        ws = self._workspace(L.load().egot2_head_workspace_bytes(C.byref(hd)))
+        L.call("egot2_head_loss_bwd", C.byref(hd), C.byref(act.head_in), C.byref(act.head_out), dlogits.data_ptr(),
+               float(dloss_scale), dy.data_ptr(), C.byref(hg), ws.data_ptr(), ws.numel(), st)
+        dmem = torch.zeros((B * T, H), device=dev, dtype=torch.float32)
+        mem = t["x_last"]
+        for i in reversed(range(sp.decoder_layers)):
+            dd = act.dec_desc[i]
+            dg = L.DecoderGrads()
+            self._fill_decoder_params(dg, i, grads_base=grad)
+            y_in = t[f"dec_y{i}"]
+            ws = self._workspace(L.load().egot2_decoder_layer_workspace_bytes(C.byref(dd)))
+            L.call("egot2_decoder_layer_bwd", C.byref(dd), C.byref(act.dec_params[i]), y_in.data_ptr(), mem.data_ptr(),
+                   C.byref(act.dec_saved[i]), dy.data_ptr(), dy.data_ptr(), dmem.data_ptr(), C.byref(dg), ws.data_ptr(),
+                   ws.numel(), st)
+        L.call("egot2_prompt_embed_bwd", self.dt, rows, S, H, act.prompt.data_ptr(), dy.data_ptr(), 0.1,
+               int(act.training), int(act.seed), gv("embedding.weight").data_ptr(), st)
+        return dmem.view(B, T, H).to(tdt)
+
     def _fill_layer_params(self, lp: L.LayerParams, i: int, grads_base: Optional[torch.Tensor] = None):
         p = f"{self.spec.encoder_prefix}layers.{i}."
         names = {"in_proj_w": "self_attn.in_proj_weight", "out_proj_w": "self_attn.out_proj.weight",
@@ -377,7 +521,9 @@ class TranslatorEngine:
         dx = torch.empty((B, T, H), device=dev, dtype=tdt)
 
         # ---- head
-        if sp.head == "tokens":
+        if sp.head == "decoder":
+            dx = self._decoder_backward(act, dout, dloss_scale, grad, gv).contiguous()
+        elif sp.head == "tokens":
             assert dout is not None
             dp = dout.to(device=dev, dtype=torch.float32).contiguous()
             L.call("egot2_pool_bwd", self.dt, B, T, H, 0, act.seg_tokens[0], dp.data_ptr(), dx.data_ptr(), st)

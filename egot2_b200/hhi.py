@@ -21,7 +21,8 @@ import torch.nn as nn
 from . import _lib
 from .engine import TranslatorEngine
 from .modules import PrecomputedFeatures, TranslatorBase
-from .specs import hhi_asd_spec, hhi_ttm_spec
+from .functional import translator_apply
+from .specs import hhi_asd_spec, hhi_g_spec, hhi_ttm_spec
 
 
 class PositionalEncoding(nn.Module):
@@ -144,6 +145,94 @@ class _ASD3Task(_HHITranslator):
             lam_out = self.lam_model(video, middle=True)
             ttm_out = self.ttm_model(video, audio, middle=True)
         return self._translate([asd_out, ttm_out, lam_out])    # token order (asd, ttm, lam)
+
+
+class TaskTranslationPromptTransformer(_HHITranslator):
+    """EgoT2-g (HHI/models/multitask/task_prompt_model.py:174-293): one model, three forwards per step
+    ('lam': LAM tokens only; 'ttm': lam+ttm+asd tokens; 'asd': same encoder, 3-token memory per frame), an
+    nn.TransformerDecoder over the task prompt and a 7-word vocabulary head.  Imported directly by
+    HHI/tasks/multitask/video_tasktranslation.py:18,35 (not through a registry)."""
+
+    def __init__(self, args, vocab, backbones: Optional[Dict[str, nn.Module]] = None):
+        super().__init__()
+        self.args = args
+        self.vocab = vocab
+        self.n_tasks = 3
+        self.dim = args.hidden_dim
+        self.n_heads = args.num_heads
+        self.num_layers = args.num_layers
+        self.dp_rate = args.dropout
+        self.max_output_length = 500
+        n_vocab = len(vocab) if vocab is not None else 7
+        # parameter containers in the reference's registration order
+        self.transformer_encoder = nn.TransformerEncoder(
+            encoder_layer=nn.TransformerEncoderLayer(d_model=self.dim, nhead=self.n_heads, dropout=self.dp_rate),
+            num_layers=self.num_layers, enable_nested_tensor=False)
+        self.transformer_decoder = nn.TransformerDecoder(
+            decoder_layer=nn.TransformerDecoderLayer(d_model=self.dim, nhead=self.n_heads, dropout=self.dp_rate),
+            num_layers=self.num_layers)
+        self.ln = nn.LayerNorm(self.dim)
+        self.task_embed = nn.Parameter(torch.randn(1, self.n_tasks, self.dim), requires_grad=True)
+        self.pos_embed = PositionalEncoding(self.dim, dropout=0.1)
+        self.embedding = nn.Embedding(n_vocab, self.dim)
+        self.proj_lam = nn.Linear(256, self.dim)
+        self.proj_ttm = nn.Linear(256, self.dim)
+        self.proj_asd = nn.Linear(256, self.dim)
+        self.fc = nn.Linear(self.dim, n_vocab)
+        self.seq_len = 2
+        for p in self.parameters():                      # _init_parameters(): xavier on every dim>1 parameter
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        if backbones is None:
+            backbones = _reference_backbones(args, True)
+        for k, m in backbones.items():
+            setattr(self, k, m)
+        self._poison_containers(self.transformer_encoder, self.transformer_decoder, self.ln, self.proj_lam, self.proj_ttm,
+                                self.proj_asd, self.fc)
+        self.embedding.forward = None
+        self._specs = {m: hhi_g_spec(self.dim, self.n_heads, self.num_layers, self.dp_rate, m, vocab=n_vocab)
+                       for m in ("lam", "ttm", "asd")}
+        self._init_translator(self._specs["ttm"])
+        self._mode_engines: Dict[str, TranslatorEngine] = {}
+
+    def _engine_for(self, mode: str, device: torch.device) -> TranslatorEngine:
+        base = self._ensure_engine(device)               # 'ttm' spec: owns the arena every parameter lives in
+        if mode == "ttm":
+            return base
+        eng = self._mode_engines.get(mode)
+        if eng is None or eng.arena is not base.arena or eng.dtype != base.dtype:
+            eng = TranslatorEngine(self._specs[mode], device, base.dtype, arena=base.arena)
+            eng.set_sinusoid(self.pos_embed.pe)
+            self._mode_engines[mode] = eng
+        return eng
+
+    def _features(self, video, video_asd, audio, audio_asd, task):
+        with torch.no_grad():
+            lam_feat = self.lam_model(video, middle=True)
+            if task == "lam":
+                return [lam_feat]
+            ttm_feat = self.ttm_model(video, audio, middle=True)
+            asd_feat = self._asd_features(video_asd, audio_asd)
+        return [lam_feat, ttm_feat, asd_feat]                 # token order (lam id0, ttm id1, asd id2)
+
+    def _decode(self, feats, tokens, task):
+        eng = self._engine_for(task, feats[0].device)
+        out = translator_apply(eng, list(feats), self._params(), self._param_names, self.training, self._next_seed(),
+                               prompt=tokens)
+        rows, S = tokens.shape
+        return out.view(rows, S, -1)                          # (rows, seq, vocab)
+
+    def forward(self, video, video_asd, audio, audio_asd, target, task):
+        assert task in ["lam", "ttm", "asd"]
+        feats = self._features(video, video_asd, audio, audio_asd, task)
+        return self._decode(feats, target, task).permute(0, 2, 1)      # (bs, vocab_size, seq_y)
+
+    def predict(self, video, video_asd, audio, audio_asd, task):
+        assert task in ["lam", "ttm", "asd"]
+        feats = self._features(video, video_asd, audio, audio_asd, task)
+        rows = feats[0].shape[0] * (feats[0].shape[1] if task == "asd" else 1)
+        y = torch.full((rows, 1), int(self.vocab[task]), dtype=torch.int64, device=feats[0].device)
+        return self._decode(feats, y, task)[:, 0, -2:]       # logits of the words '0', '1'
 
 
 def _registry(*classes):

@@ -180,6 +180,64 @@ int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_layer_params*
                             const egot2_layer_saved* s, void* dx_out, void* dx_in,
                             const egot2_layer_grads* g, void* workspace, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ EgoT2-g decoder (task-prompt transformer)
+ * One nn.TransformerDecoderLayer (post-norm, ReLU; CustomDecoderLayer only forces need_weights) over the S-token task
+ * prompt of every row, attending to that row's encoder memory:
+ *     HHI/models/multitask/task_prompt_model.py:163-172,187-194,260-269
+ * Row n, memory key j reads encoder token  (n / kv_inner) * kv_outer + j * kv_jstride + (n % kv_inner) * kv_istride :
+ *     'lam' / 'ttm' (memory = the clip's M tokens):  kv_inner 1, kv_outer M, kv_jstride 1, kv_istride 0
+ *     'asd' (:251-257, 3-token memory per frame):    kv_inner T, kv_outer 3T, kv_jstride T, kv_istride 1, rows = B*T */
+typedef struct {
+  int32_t dtype;
+  int32_t rows, S;                    /* decoder rows, prompt tokens per row */
+  int32_t mem_rows, M;                /* encoder tokens in `mem`, memory tokens per row */
+  int32_t kv_inner, kv_outer, kv_jstride, kv_istride;
+  int32_t H, FF, heads;
+  int32_t training, layer_index;
+  float p_drop, ln_eps;
+  uint64_t seed;
+} egot2_decoder_desc;
+
+typedef struct {
+  const void *sa_in_w, *sa_out_w;     /* self_attn.in_proj_weight (3H,H), out_proj.weight (H,H); dtype */
+  const void *ca_in_w, *ca_out_w;     /* multihead_attn.* */
+  const void *lin1_w, *lin2_w;        /* (FF,H), (H,FF) */
+  const float *sa_in_b, *sa_out_b, *ca_in_b, *ca_out_b, *lin1_b, *lin2_b;
+  const float *norm1_g, *norm1_b, *norm2_g, *norm2_b, *norm3_g, *norm3_b;
+} egot2_decoder_params;
+
+typedef struct {
+  float *sa_in_w, *sa_out_w, *ca_in_w, *ca_out_w, *lin1_w, *lin2_w;
+  float *sa_in_b, *sa_out_b, *ca_in_b, *ca_out_b, *lin1_b, *lin2_b;
+  float *norm1_g, *norm1_b, *norm2_g, *norm2_b, *norm3_g, *norm3_b;
+} egot2_decoder_grads;
+
+typedef struct {                      /* activations kept for backward; caller-allocated; R = rows*S */
+  void* qkv;                          /* (R, 3H) dtype */
+  void* a1;                           /* (R, H): self-attention heads, input of out_proj */
+  void* y1; float* stat1; void* x1;   /* (R, H) LN1 input, (R,2), LN1 output */
+  void* qc;                           /* (R, H): cross-attention queries */
+  void* kvc;                          /* (mem_rows, 2H): cross-attention keys | values of every encoder token */
+  void* a2;                           /* (R, H) */
+  void* y2; float* stat2; void* x2;
+  void* hid;                          /* (R, FF) */
+  void* y3; float* stat3;
+} egot2_decoder_saved;
+
+size_t egot2_decoder_layer_workspace_bytes(const egot2_decoder_desc* d);
+int egot2_decoder_layer_fwd(const egot2_decoder_desc* d, const egot2_decoder_params* p, const void* y_in /* (R,H) */,
+                            const void* mem /* (mem_rows,H) */, void* y_out, const egot2_decoder_saved* s, void* stream);
+/* dy_out is clobbered; dy_in may alias it; dmem (mem_rows,H) fp32 is ACCUMULATED (+=) over the decoder layers */
+int egot2_decoder_layer_bwd(const egot2_decoder_desc* d, const egot2_decoder_params* p, const void* y_in, const void* mem,
+                            const egot2_decoder_saved* s, void* dy_out, void* dy_in, float* dmem,
+                            const egot2_decoder_grads* g, void* workspace, size_t ws_bytes, void* stream);
+/* prompt tokens: y[n,s,:] = embedding[tok[n,s],:] * sqrt(H) + pe[s,:], then Dropout(p) (decode(), :262-264) */
+int egot2_prompt_embed_fwd(int32_t dtype, int32_t rows, int32_t S, int32_t H, const int64_t* tokens,
+                           const float* embedding, const float* pe, float p_drop, int32_t training, uint64_t seed,
+                           void* y, void* stream);
+int egot2_prompt_embed_bwd(int32_t dtype, int32_t rows, int32_t S, int32_t H, const int64_t* tokens, const void* dy,
+                           float p_drop, int32_t training, uint64_t seed, float* d_embedding /* (V,H) += */, void* stream);
+
 /* ------------------------------------------------------------------ head + loss */
 typedef struct {
   int32_t dtype;

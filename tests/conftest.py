@@ -20,7 +20,10 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     ref = os.path.isdir("/root/reference/HHI/models")
+    has_timeout = config.pluginmanager.hasplugin("timeout")
     for item in items:
+        if "gpu" in item.keywords and has_timeout and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(180))      # a GPU-side deadlock must fail the test, not hang the box
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "requires_reference" in item.keywords and not ref:

@@ -30,6 +30,8 @@ def _loss_kind(case):
         return (L.LOSS_BCE_SIGMOID if sp.n_out == 16 else L.LOSS_CE), None
     if sp.family == "hoi_lta":
         return L.LOSS_CE_GROUPS, None
+    if sp.family == "hhi_g":
+        return L.LOSS_CE, None
     return L.LOSS_NONE, None
 
 
@@ -68,8 +70,12 @@ def test_engine_matches_oracle_and_golden(name, dtype):
         eng.set_sinusoid(O.sinusoid_table(1000, sp.hidden))
     loss_kind, cw = _loss_kind(case)
     gfeats = _engine_feats(case, eng, feats, extra, dtype)
-    act = eng.forward(gfeats, training=False, labels=labels, loss=loss_kind, class_weight=cw)
-    out = act.t["out"].float().cpu()
+    if sp.family == "hhi_g":      # decoder reads target[:, :-1], CE on target[:, 1:] (video_tasktranslation.py:48-61)
+        act = eng.forward(gfeats, training=False, labels=labels[:, 1:], loss=loss_kind, prompt=labels[:, :-1])
+        out = act.t["out"].float().cpu().view(labels.shape[0], 2, -1).permute(0, 2, 1)      # (rows, V, S) like the reference
+    else:
+        act = eng.forward(gfeats, training=False, labels=labels, loss=loss_kind, class_weight=cw)
+        out = act.t["out"].float().cpu()
 
     # oracle (CPU, fp32) on the same inputs
     P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
