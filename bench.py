@@ -44,6 +44,10 @@ WORKLOADS = {
     "hoi_pnr_train_b256": dict(spec=lambda: specs.hoi_pnr_spec(128, 6, 16, 0.5, 0.1), batch=256, seg_tokens=(16, 16, 8, 8)),
     # BASELINE.json configs[4]
     "hoi_lta_train_b512": dict(spec=lambda: specs.hoi_lta_spec(512, 4, 8, 0.5), batch=512, seg_tokens=(2, 2, 2, 2)),
+    # BASELINE.json configs[2]: HHI EgoT2-g, one step = the three forwards of video_tasktranslation.py:39-66 on
+    # lam (64 clips x 7 tokens), ttm (8 clips x 3x30 tokens), asd (20 clips x 3x30 tokens -> 600 frame rows); H256 L3+3
+    "hhi_g_train": dict(spec=lambda: specs.hhi_g_spec(256, 4, 3, 0.1, "ttm"), batch=92, seg_tokens=(30, 30, 30), prompt=True,
+                        g_batches=dict(lam=(64, 7), ttm=(8, 30), asd=(20, 30))),
 }
 L2_BYTES = 126 * 2 ** 20
 
@@ -71,6 +75,29 @@ def load_ncu_traffic(tag: str):
         if not k.startswith("_") and tag.startswith(k):
             return v
     return None
+
+
+def make_g_batch(wl, seed, fdt):
+    """EgoT2-g step inputs: 7 feature tensors [lam | lam,ttm,asd | lam,ttm,asd] + concatenated (rows,3) targets."""
+    feats, labels = [], []
+    for mode in ("lam", "ttm", "asd"):
+        b, d = wl["g_batches"][mode]
+        sp = specs.hhi_g_spec(256, 4, 3, 0.1, mode)
+        seg = (d,) if mode == "lam" else (d, d, d)
+        f = synth.make_features(sp, b, seg, seed=seed * 7 + len(mode), dtype=fdt)
+        feats += [f[s_.name] for s_ in sp.segments]
+        labels.append(synth.make_labels(sp, b, seg, seed=seed * 7 + len(mode)))
+    return feats, torch.cat(labels, dim=0)
+
+
+def g_flops_per_step(wl, backward=True):
+    tot = 0.0
+    for mode in ("lam", "ttm", "asd"):
+        b, d = wl["g_batches"][mode]
+        sp = specs.hhi_g_spec(256, 4, 3, 0.1, mode)
+        seg = (d,) if mode == "lam" else (d, d, d)
+        tot += b * sp.flops_per_clip(seg, backward=backward)      # encoder + projections; the 2-token decoder is < 2 %
+    return tot
 
 
 class ClockSampler:
@@ -146,9 +173,35 @@ def cpu_oracle_step_fn(spec, batch, seg_tokens, seed=0):
     return step
 
 
-def time_cpu(spec, batch, seg_tokens, steps, warmup):
+def cpu_oracle_g_step_fn(wl, seed=0):
+    """EgoT2-g: the three forwards + summed CE + backward of the CPU oracle (train mode, dropout on)."""
+    from oracle import translator_oracle as O
+    spec = wl["spec"]()
+    sd = synth.make_state_dict(spec, seed)
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    feats, labels = make_g_batch(wl, seed, torch.float32)
+    groups = {"lam": dict(lam=feats[0]), "ttm": dict(lam=feats[1], ttm=feats[2], asd=feats[3]),
+              "asd": dict(lam=feats[4], ttm=feats[5], asd=feats[6])}
+
+    def step():
+        for p in P.values():
+            p.grad = None
+        off, loss = 0, 0.0
+        for mode in ("lam", "ttm", "asd"):
+            b, d = wl["g_batches"][mode]
+            rows = b * d if mode == "asd" else b
+            tgt = labels[off:off + rows]
+            off += rows
+            out = O.hhi_g_forward(P, groups[mode], tgt[:, :-1], mode, spec.heads, spec.p_layer, True)
+            loss = loss + torch.nn.functional.cross_entropy(out, tgt[:, 1:])
+        loss.backward()
+        return float(loss)
+    return step
+
+
+def time_cpu(spec, batch, seg_tokens, steps, warmup, wl=None):
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_oracle_step_fn(spec, batch, seg_tokens)
+    step = cpu_oracle_g_step_fn(wl) if (wl is not None and wl.get("prompt")) else cpu_oracle_step_fn(spec, batch, seg_tokens)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -166,7 +219,7 @@ def run_reference(args, wl, spec):
     steps, warm = max(1, args.steps), max(1, min(args.warmup, 2))
     # bound the run: ~2 s per 256-clip step on 8 cores -> cap the number of timed steps
     steps = min(steps, 10)
-    cps, sec = time_cpu(spec, sample_batch, wl["seg_tokens"], steps, warm)
+    cps, sec = time_cpu(spec, sample_batch, wl["seg_tokens"], steps, warm, wl)
     cores = torch.get_num_threads()
     sample = f"{steps} steps x {sample_batch} clips (fwd+loss+bwd, dropout on) of the CPU oracle, {cores} threads"
     line = {"impl": "reference", "metric": "translator fwd+bwd clips/sec", "value": cps, "unit": "clips/s",
@@ -211,14 +264,25 @@ def main():
     from egot2_b200.trainer import TranslatorTrainer
 
     B, seg = wl["batch"], wl["seg_tokens"]
-    tr = TranslatorTrainer(spec, dev, args.dtype, use_graphs=not args.no_graphs)
-    tr.load_state_dict(synth.make_state_dict(spec, 0))          # identical weights on every rank
     fdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    is_g = bool(wl.get("prompt"))
+    if is_g:
+        from egot2_b200.trainer import PromptTranslatorTrainer
+        tr = PromptTranslatorTrainer(256, 4, 3, 0.1, dev, args.dtype)
+    else:
+        tr = TranslatorTrainer(spec, dev, args.dtype, use_graphs=not args.no_graphs)
+    tr.load_state_dict(synth.make_state_dict(spec, 0))          # identical weights on every rank
     feat_bytes = spec.feature_elems_per_clip(seg) * B * (2 if args.dtype == "bf16" else 4)
+    if is_g:
+        feat_bytes = sum(t.numel() * t.element_size() for t in make_g_batch(wl, 0, fdt)[0])
     n_pool = max(3, -(-2 * L2_BYTES // feat_bytes))              # pool of distinct batches >= 2 x L2
     n_pool = min(n_pool, 64)
     pool = []
     for i in range(n_pool):
+        if is_g:
+            fe, la = make_g_batch(wl, 1000 * rank + i, fdt)
+            pool.append(([t.to(dev) for t in fe], la.to(dev)))
+            continue
         f = synth.make_features(spec, B, seg, seed=1000 * rank + i, dtype=fdt)
         pool.append(([f[s.name].to(dev) for s in spec.segments],
                      synth.make_labels(spec, B, seg, seed=1000 * rank + i).to(dev)))
@@ -262,6 +326,10 @@ def main():
     # ---- end-to-end from pinned host buffers (H2D + step + D2H of the loss inside the timed region)
     host = []
     for i in range(2):
+        if is_g:
+            fe, la = make_g_batch(wl, 5000 + 10 * rank + i, fdt)
+            host.append(([t.pin_memory() for t in fe], la.pin_memory()))
+            continue
         f = synth.make_features(spec, B, seg, seed=5000 + 10 * rank + i, dtype=fdt)
         host.append(([f[s.name].pin_memory() for s in spec.segments],
                      synth.make_labels(spec, B, seg, seed=5000 + 10 * rank + i).pin_memory()))
@@ -272,7 +340,7 @@ def main():
     losses = tr.train_stream_host(host, e2e_steps)        # returns after the last loss has been read back
     e1.record()
     barrier()
-    assert len(losses) == e2e_steps and all(l == l for l in losses), "e2e: loss read-back failed"
+    assert len(losses) == e2e_steps and all(l == l for l in losses), f"e2e: loss read-back failed: {losses}"
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
@@ -296,13 +364,13 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     cpu = None
-    if world == 1 and not args.skip_cpu_baseline:
+    if world == 1 and not args.skip_cpu_baseline and not is_g:
         sample_b = min(B, 256)
         cps, sec = time_cpu(spec, sample_b, seg, steps=5, warmup=1)
         cpu = {"value": cps, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"5 steps x {sample_b} clips (fwd+loss+bwd, dropout on) of the CPU oracle"}
 
-    flops_step = spec.flops_per_clip(seg, backward=True) * B
+    flops_step = g_flops_per_step(wl) if is_g else spec.flops_per_clip(seg, backward=True) * B
     line = {
         "metric": "translator fwd+bwd clips/sec", "value": value, "unit": "clips/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,

@@ -20,6 +20,72 @@ from .parallel import allreduce_gradients
 from .specs import TranslatorSpec
 
 
+class PromptTranslatorTrainer:
+    """EgoT2-g training step (HHI/tasks/multitask/video_tasktranslation.py:39-66): THREE forwards of one shared model
+    per step - 'lam' (LAM tokens only), 'ttm' (lam+ttm+asd tokens) and 'asd' (same encoder, 3-token memory per frame) -
+    an unweighted CE over the 7-word vocabulary at the two answer positions of each, loss = sum_i ratio_i * loss_i,
+    one backward into ONE gradient arena, [DP: one all-reduce], one fused Adam launch.
+
+    Step inputs: feats = [lam | lam, ttm, asd (ttm batch) | lam, ttm, asd (asd batch)] (7 tensors),
+                 labels = the three (rows_i, 3) target-token tensors concatenated along rows."""
+
+    def __init__(self, hidden=256, heads=4, layers=3, dropout=0.1, device="cuda:0", dtype: str = "bf16", lr: float = 5e-4,
+                 ratios=(1.0, 1.0, 1.0), process_group=None):
+        from .hhi import PositionalEncoding
+        from .specs import hhi_g_spec
+        self.device = torch.device(device)
+        self.specs = {m: hhi_g_spec(hidden, heads, layers, dropout, m) for m in ("lam", "ttm", "asd")}
+        self.spec = self.specs["ttm"]
+        self.engine = TranslatorEngine(self.specs["ttm"], self.device, dtype)
+        self.engines = {"ttm": self.engine}
+        for m in ("lam", "asd"):
+            self.engines[m] = TranslatorEngine(self.specs[m], self.device, dtype, arena=self.engine.arena)
+        pe = PositionalEncoding(hidden).pe
+        for e in self.engines.values():
+            e.set_sinusoid(pe)
+        self.ratios = ratios
+        self.hp = dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+        self.opt_state: Dict[str, torch.Tensor] = {}
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.use_graphs = False            # three engines share one workspace: eager launches
+        self._h2d: Dict[int, List[torch.Tensor]] = {}
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.loss_kind, self.class_weight = L.LOSS_CE, None
+
+    def load_state_dict(self, sd):
+        self.engine.arena.load_state_dict(sd)
+
+    def train_step(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, graph_key: Optional[int] = None):
+        self.step_count += 1
+        groups = {"lam": list(feats[0:1]), "ttm": list(feats[1:4]), "asd": list(feats[4:7])}
+        rows = {"lam": groups["lam"][0].shape[0], "ttm": groups["ttm"][0].shape[0],
+                "asd": groups["asd"][0].shape[0] * groups["asd"][0].shape[1]}
+        off, total = 0, None
+        first = True
+        for ratio, mode in zip(self.ratios, ("lam", "ttm", "asd")):
+            tgt = labels[off:off + rows[mode]]
+            off += rows[mode]
+            eng = self.engines[mode]
+            act = eng.forward(groups[mode], training=True, seed=self.step_count * 4 + len(mode), labels=tgt[:, 1:],
+                              loss=L.LOSS_CE, persistent=True, prompt=tgt[:, :-1])
+            eng.backward(act, dloss_scale=float(ratio), zero_grad=first)      # one arena, accumulated over the three
+            first = False
+            l = act.t["loss"][0] * ratio
+            total = l if total is None else total + l
+        scale = 1.0
+        if self.world > 1:
+            scale = allreduce_gradients(self.engine.arena.grad, self.pg)
+        self.engine.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
+                              self.hp["weight_decay"], grad_scale=scale)
+        return total
+
+    train_stream_host = None     # bound below to TranslatorTrainer's implementation (same double-buffered host path)
+
+
 def default_loss(spec: TranslatorSpec):
     """(loss kind, class weights) the reference task uses for this translator."""
     if spec.family == "hhi_ttm":
@@ -140,8 +206,11 @@ class TranslatorTrainer:
             host_feats, host_labels = host_batches[i % len(host_batches)]
             bufs = self._h2d.get(slot)
             if bufs is None:
-                bufs = [torch.empty(f.shape, device=self.device, dtype=f.dtype) for f in host_feats]
-                bufs.append(torch.empty(host_labels.shape, device=self.device, dtype=torch.int64))
+                # allocate ON the copy stream: a block the caching allocator recycles from the compute stream may still
+                # be in use by kernels in flight there, and the copy stream would overwrite it without waiting
+                with torch.cuda.stream(self.copy_stream):
+                    bufs = [torch.empty(f.shape, device=self.device, dtype=f.dtype) for f in host_feats]
+                    bufs.append(torch.empty(host_labels.shape, device=self.device, dtype=torch.int64))
                 self._h2d[slot] = bufs
             with torch.cuda.stream(self.copy_stream):
                 if i >= 2:
@@ -162,3 +231,6 @@ class TranslatorTrainer:
     def infer(self, feats: Sequence[torch.Tensor]) -> torch.Tensor:
         act = self.engine.forward(feats, training=False, persistent=True)
         return act.t["out"]
+
+
+PromptTranslatorTrainer.train_stream_host = TranslatorTrainer.train_stream_host
