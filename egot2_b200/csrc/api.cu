@@ -137,6 +137,43 @@ struct Carver {   // bump allocator over the caller's workspace
   bool ok() const { return off <= size && (base != nullptr || off == 0); }
 };
 
+// ---- side streams: work that only produces parameter gradients (weight-gradient GEMMs, bias column sums) is off the
+// data-gradient critical path, and the independent per-task projections do not depend on each other.  Those launches
+// are forked onto library-owned non-blocking streams with event fork/join (legal under stream capture: the CUDA graph
+// gets parallel branches), so they fill the SMs the skinny critical-path kernels leave idle.  EGOT2_STREAMS=0 disables.
+struct Side {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork[8] = {};
+  cudaEvent_t join = nullptr;
+};
+Side* get_side(int idx) {
+  static Side sides[2];
+  static int state = 0;      // 0 untried, 1 ok, -1 disabled / failed
+  if (state == 0) {
+    state = 1;
+    if (env_is("EGOT2_STREAMS", "0")) state = -1;
+    for (int i = 0; i < 2 && state == 1; ++i) {
+      if (cudaStreamCreateWithFlags(&sides[i].s, cudaStreamNonBlocking) != cudaSuccess) state = -1;
+      for (int k = 0; k < 8 && state == 1; ++k)
+        if (cudaEventCreateWithFlags(&sides[i].fork[k], cudaEventDisableTiming) != cudaSuccess) state = -1;
+      if (state == 1 && cudaEventCreateWithFlags(&sides[i].join, cudaEventDisableTiming) != cudaSuccess) state = -1;
+    }
+  }
+  return state == 1 ? &sides[idx] : nullptr;
+}
+// side stream `sd` may start once everything enqueued on `main` so far has finished; returns the stream to launch on
+cudaStream_t side_fork(cudaStream_t main, Side* sd, int k) {
+  if (!sd) return main;
+  if (cudaEventRecord(sd->fork[k], main) != cudaSuccess || cudaStreamWaitEvent(sd->s, sd->fork[k], 0) != cudaSuccess) return main;
+  return sd->s;
+}
+int side_join(cudaStream_t main, Side* sd) {
+  if (!sd) return 0;
+  EGOT2_CUDA(cudaEventRecord(sd->join, sd->s));
+  EGOT2_CUDA(cudaStreamWaitEvent(main, sd->join, 0));
+  return 0;
+}
+
 // weight-gradient GEMM: dW[N_out, K_in] += dY^T . X     (dY: (rows, N_out), X: (rows, K_in))
 int wgrad(int dtype, int rows, int n_out, int k_in, const void* dY, int ld_dy, int dy_rpg, int dy_gs, const void* X,
           int ld_x, int x_rpg, int x_gs, float* dW, cudaStream_t st) {
@@ -243,13 +280,20 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
     cast_buf = ws.take(egot2_embed_workspace_bytes(d, 0) - 256);
     EGOT2_CHECK(ws.ok(), "embed_fwd: workspace too small (%zu < %zu)", ws_bytes, ws.off);
   }
+  // the per-task projections are independent: task 0 stays on `st`, the others alternate over two side streams
+  // (not when the features need the shared fp32 -> bf16 staging buffer)
+  const bool par = d->feat_dtype == d->dtype;
+  Side* sides[2] = {par ? get_side(0) : nullptr, par ? get_side(1) : nullptr};
+  bool used[2] = {false, false};
   for (int k = 0; k < d->n_seg; ++k) {
     const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
     if (Dk == 0) continue;
+    cudaStream_t sk = st;
+    if (k > 0 && sides[(k - 1) & 1]) { sk = side_fork(st, sides[(k - 1) & 1], k & 7); used[(k - 1) & 1] = true; }
     char* zk = (char*)out->z + (size_t)d->seg_offset[k] * d->H * es;
     const void* feat = in->feat[k];
     if (d->feat_dtype != d->dtype) {
-      EGOT2_TRY(cast_f32_to(d->dtype, (const float*)feat, cast_buf, (size_t)d->B * Dk * Kk, st));
+      EGOT2_TRY(cast_f32_to(d->dtype, (const float*)feat, cast_buf, (size_t)d->B * Dk * Kk, sk));
       feat = cast_buf;
     }
     if (d->seg_has_proj[k]) {
@@ -260,12 +304,13 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
       g.C = zk; g.ldc = d->H; g.c_rpg = Dk; g.c_gstride = d->T;
       g.bias = in->proj_b[k];
       g.in_dtype = d->dtype; g.out_dtype = d->dtype;
-      EGOT2_TRY(gemm(g, st));
+      EGOT2_TRY(gemm(g, sk));
     } else {
       EGOT2_CUDA(cudaMemcpy2DAsync(zk, (size_t)d->T * d->H * es, feat, (size_t)Dk * d->H * es, (size_t)Dk * d->H * es,
-                                   d->B, cudaMemcpyDeviceToDevice, st));
+                                   d->B, cudaMemcpyDeviceToDevice, sk));
     }
   }
+  for (int i = 0; i < 2; ++i) if (used[i]) EGOT2_TRY(side_join(st, sides[i]));
   const size_t n = (size_t)d->B * d->T * d->H;
   if (d->training && d->p_feat > 0.f)
     EGOT2_TRY(dropout_inplace(d->dtype, out->z, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
@@ -302,45 +347,51 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   EGOT2_TRY(layernorm_bwd(l, st));
   if (d->training && d->p_feat > 0.f)
     EGOT2_TRY(dropout_inplace(d->dtype, dx, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+  const bool par = d->feat_dtype == d->dtype;
+  Side* sides[2] = {par ? get_side(0) : nullptr, par ? get_side(1) : nullptr};
+  bool used[2] = {false, false};
   for (int k = 0; k < d->n_seg; ++k) {
     const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
     if (Dk == 0) continue;
+    cudaStream_t sk = st;
+    if (k > 0 && sides[(k - 1) & 1]) { sk = side_fork(st, sides[(k - 1) & 1], k & 7); used[(k - 1) & 1] = true; }
     const char* dzk = (const char*)dx + (size_t)d->seg_offset[k] * d->H * es;
     if (d->seg_has_proj[k]) {
       const void* feat = in->feat[k];
       if (d->feat_dtype != d->dtype) {
-        EGOT2_TRY(cast_f32_to(d->dtype, (const float*)feat, cast_buf, (size_t)d->B * Dk * Kk, st));
+        EGOT2_TRY(cast_f32_to(d->dtype, (const float*)feat, cast_buf, (size_t)d->B * Dk * Kk, sk));
         feat = cast_buf;
       }
       if (g->proj_w[k])
-        EGOT2_TRY(wgrad(d->dtype, d->B * Dk, d->H, Kk, dzk, d->H, Dk, d->T, feat, Kk, 0, 0, g->proj_w[k], st));
-      if (g->proj_b[k]) EGOT2_TRY(colsum_accum(d->dtype, d->B * Dk, d->H, dzk, d->H, Dk, d->T, g->proj_b[k], st));
+        EGOT2_TRY(wgrad(d->dtype, d->B * Dk, d->H, Kk, dzk, d->H, Dk, d->T, feat, Kk, 0, 0, g->proj_w[k], sk));
+      if (g->proj_b[k]) EGOT2_TRY(colsum_accum(d->dtype, d->B * Dk, d->H, dzk, d->H, Dk, d->T, g->proj_b[k], sk));
       if (g->dfeat[k]) {   // dF = dZ . W   (only for a trainable backbone: HHI --nofreeze)
         GemmArgs m;
         m.M = d->B * Dk; m.N = Kk; m.K = d->H;
         m.A = dzk; m.lda = d->H; m.a_rpg = Dk; m.a_gstride = d->T;
         m.B = in->proj_w[k]; m.ldb = Kk; m.trans_b = 0;
         m.C = g->dfeat[k]; m.ldc = Kk; m.in_dtype = d->dtype; m.out_dtype = EGOT2_F32;
-        EGOT2_TRY(gemm(m, st));
+        EGOT2_TRY(gemm(m, sk));
       }
     } else if (g->dfeat[k]) {   // pass-through stream (LTA action features come from a trainable head)
       if (d->dtype == EGOT2_F32) {
         EGOT2_CUDA(cudaMemcpy2DAsync(g->dfeat[k], (size_t)Dk * d->H * 4, dzk, (size_t)d->T * d->H * 4,
-                                     (size_t)Dk * d->H * 4, d->B, cudaMemcpyDeviceToDevice, st));
+                                     (size_t)Dk * d->H * 4, d->B, cudaMemcpyDeviceToDevice, sk));
       } else {
         for (int b = 0; b < d->B; ++b)
           EGOT2_TRY(cast_to_f32(d->dtype, dzk + (size_t)b * d->T * d->H * es, g->dfeat[k] + (size_t)b * Dk * d->H,
-                                (size_t)Dk * d->H, st));
+                                (size_t)Dk * d->H, sk));
       }
     }
   }
+  for (int i = 0; i < 2; ++i) if (used[i]) EGOT2_TRY(side_join(st, sides[i]));
   return 0;
 }
 
 // =============================================================================== encoder layer
 namespace {
 struct LayerWs {
-  void *d1, *d2, *d3, *dhid, *dqkv, *attn_ws;
+  void *d1, *d2, *d3, *d4, *d5, *dhid, *dqkv, *attn_ws;
   size_t attn_ws_bytes;
 };
 size_t layer_ws_layout(const egot2_layer_desc* d, int backward, void* base, size_t bytes, LayerWs* out) {
@@ -352,6 +403,8 @@ size_t layer_ws_layout(const egot2_layer_desc* d, int backward, void* base, size
     w.d1 = ws.take(M * d->H * es);
     w.d2 = ws.take(M * d->H * es);
     w.d3 = ws.take(M * d->H * es);
+    w.d4 = ws.take(M * d->H * es);
+    w.d5 = ws.take(M * d->H * es);
     w.dhid = ws.take(M * d->FF * es);
     w.dqkv = ws.take(M * 3 * d->H * es);
     w.attn_ws_bytes = attention_bwd_workspace(d->dtype, d->B, d->T, d->H, d->heads);
@@ -447,6 +500,11 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   const uint32_t L = (uint32_t)d->layer_index;
   const int dt = d->dtype;
 
+  // Parameter-gradient work (weight-gradient GEMMs, bias column sums) runs on a side stream, forked after each producer
+  // and joined before returning; the data-gradient chain stays on `st`.  Every buffer a side launch reads is written
+  // once per call (d1..d5, dhid, dqkv), so the main chain never overwrites what the side stream may still be reading.
+  Side* sd = get_side(0);
+
   // 1. through norm2: d1 = dL/dy2, and (same kernel) d2 = dropout2 mask applied to d1 = dL/d(linear2 out)
   const void* d2 = w.d1;
   {
@@ -455,9 +513,13 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
     if (pd > 0.f) { l.dx2 = w.d2; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DROP2, L); d2 = w.d2; }
     EGOT2_TRY(layernorm_bwd(l, st));
   }
-  //    linear2: dW2 += d2^T . hid ; db2 += colsum(d2) ; dhid = (d2 . W2) * relu'(hid) * ffn-dropout scale
-  EGOT2_TRY(wgrad(dt, M, H, FF, d2, H, 0, 0, s->hid, FF, 0, 0, g->lin2_w, st));
-  EGOT2_TRY(colsum_accum(dt, M, H, d2, H, 0, 0, g->lin2_b, st));
+  //    linear2 (side): dW2 += d2^T . hid ; db2 += colsum(d2)
+  {
+    cudaStream_t ss = side_fork(st, sd, 0);
+    EGOT2_TRY(wgrad(dt, M, H, FF, d2, H, 0, 0, s->hid, FF, 0, 0, g->lin2_w, ss));
+    EGOT2_TRY(colsum_accum(dt, M, H, d2, H, 0, 0, g->lin2_b, ss));
+  }
+  //    dhid = (d2 . W2) * relu'(hid) * ffn-dropout scale ; d3 = dhid . W1 + d1 (residual branch)
   const bool fused_dx = s->hid_mask && ffn_fused_supported(dt, H, FF) && !env_is("EGOT2_FFN", "unfused");
   if (fused_dx) {
     // one tcgen05 kernel: dhid = gate(d2 . W2) and d3 = dhid . W1 + d1, dhid never re-read for the second GEMM
@@ -466,43 +528,50 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
     GemmArgs m; m.M = M; m.N = FF; m.K = H; m.A = d2; m.lda = H; m.B = p->lin2_w; m.ldb = FF; m.trans_b = 0;
     m.C = w.dhid; m.ldc = FF; m.mask = s->hid; m.ldm = FF; m.mask_scale = inv_keep; m.in_dtype = dt; m.out_dtype = dt;
     EGOT2_TRY(gemm(m, st));
+    GemmArgs n; n.M = M; n.N = H; n.K = FF; n.A = w.dhid; n.lda = FF; n.B = p->lin1_w; n.ldb = H; n.trans_b = 0;
+    n.C = w.d3; n.ldc = H; n.residual = w.d1; n.ldr = H; n.in_dtype = dt; n.out_dtype = dt;
+    EGOT2_TRY(gemm(n, st));
   }
-  // 3. linear1: dW1 += dhid^T . x1 ; db1 += colsum(dhid) ; d3 = dhid . W1 + d1 (residual branch)
-  EGOT2_TRY(wgrad(dt, M, FF, H, w.dhid, FF, 0, 0, s->x1, H, 0, 0, g->lin1_w, st));
-  EGOT2_TRY(colsum_accum(dt, M, FF, w.dhid, FF, 0, 0, g->lin1_b, st));
-  if (!fused_dx) {
-    GemmArgs m; m.M = M; m.N = H; m.K = FF; m.A = w.dhid; m.lda = FF; m.B = p->lin1_w; m.ldb = H; m.trans_b = 0;
-    m.C = w.d3; m.ldc = H; m.residual = w.d1; m.ldr = H; m.in_dtype = dt; m.out_dtype = dt;
-    EGOT2_TRY(gemm(m, st));
+  // 3. linear1 (side): dW1 += dhid^T . x1 ; db1 += colsum(dhid)
+  {
+    cudaStream_t ss = side_fork(st, sd, 1);
+    EGOT2_TRY(wgrad(dt, M, FF, H, w.dhid, FF, 0, 0, s->x1, H, 0, 0, g->lin1_w, ss));
+    EGOT2_TRY(colsum_accum(dt, M, FF, w.dhid, FF, 0, 0, g->lin1_b, ss));
   }
-  // 4. through norm1: d1 = dL/dy1, and (same kernel) d4 = dropout1 mask applied to d1 = dL/d(out_proj out)
-  //    out_proj: dWo += d4^T . attn ; dbo += colsum(d4) ; dattn = d4 . Wo
-  const void* d4 = w.d1;
+  // 4. through norm1: d4 = dL/dy1, and (same kernel) d5 = dropout1 mask applied to it = dL/d(out_proj out)
+  const void* dyo = w.d4;
   {
     LayerNormBwdArgs l; l.rows = M; l.H = H; l.dtype = dt; l.x = s->y1; l.stat = s->stat1; l.g = p->norm1_g;
-    l.dy = w.d3; l.dx = w.d1; l.dg = g->norm1_g; l.db = g->norm1_b;
-    if (pd > 0.f) { l.dx2 = w.d2; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DROP1, L); d4 = w.d2; }
+    l.dy = w.d3; l.dx = w.d4; l.dg = g->norm1_g; l.db = g->norm1_b;
+    if (pd > 0.f) { l.dx2 = w.d5; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DROP1, L); dyo = w.d5; }
     EGOT2_TRY(layernorm_bwd(l, st));
   }
-  EGOT2_TRY(wgrad(dt, M, H, H, d4, H, 0, 0, s->attn, H, 0, 0, g->out_proj_w, st));
-  EGOT2_TRY(colsum_accum(dt, M, H, d4, H, 0, 0, g->out_proj_b, st));
+  // 5. out_proj (side): dWo += dyo^T . attn ; dbo += colsum(dyo)      main: dattn = dyo . Wo  (d3 is free again)
   {
-    GemmArgs m; m.M = M; m.N = H; m.K = H; m.A = d4; m.lda = H; m.B = p->out_proj_w; m.ldb = H; m.trans_b = 0;
+    cudaStream_t ss = side_fork(st, sd, 2);
+    EGOT2_TRY(wgrad(dt, M, H, H, dyo, H, 0, 0, s->attn, H, 0, 0, g->out_proj_w, ss));
+    EGOT2_TRY(colsum_accum(dt, M, H, dyo, H, 0, 0, g->out_proj_b, ss));
+  }
+  {
+    GemmArgs m; m.M = M; m.N = H; m.K = H; m.A = dyo; m.lda = H; m.B = p->out_proj_w; m.ldb = H; m.trans_b = 0;
     m.C = w.d3; m.ldc = H; m.in_dtype = dt; m.out_dtype = dt;
     EGOT2_TRY(gemm(m, st));
   }
   // 6. attention backward -> dqkv
   EGOT2_TRY(attention_bwd(dt, d->B, d->T, H, d->heads, s->qkv, s->attn, s->lse, w.d3, w.dqkv, pd,
                           site_key(d->seed, SITE_ATTN, L), w.attn_ws, w.attn_ws_bytes, st));
-  // 7. in_proj: dWin += dqkv^T . x ; dbin += colsum(dqkv) ; dx = dqkv . Win + d1 (residual branch)
-  EGOT2_TRY(wgrad(dt, M, 3 * H, H, w.dqkv, 3 * H, 0, 0, x_in, H, 0, 0, g->in_proj_w, st));
-  EGOT2_TRY(colsum_accum(dt, M, 3 * H, w.dqkv, 3 * H, 0, 0, g->in_proj_b, st));
+  // 7. in_proj (side): dWin += dqkv^T . x ; dbin += colsum(dqkv)      main: dx = dqkv . Win + d4 (residual branch)
+  {
+    cudaStream_t ss = side_fork(st, sd, 3);
+    EGOT2_TRY(wgrad(dt, M, 3 * H, H, w.dqkv, 3 * H, 0, 0, x_in, H, 0, 0, g->in_proj_w, ss));
+    EGOT2_TRY(colsum_accum(dt, M, 3 * H, w.dqkv, 3 * H, 0, 0, g->in_proj_b, ss));
+  }
   {
     GemmArgs m; m.M = M; m.N = H; m.K = 3 * H; m.A = w.dqkv; m.lda = 3 * H; m.B = p->in_proj_w; m.ldb = H; m.trans_b = 0;
-    m.C = dx_in; m.ldc = H; m.residual = w.d1; m.ldr = H; m.in_dtype = dt; m.out_dtype = dt;
+    m.C = dx_in; m.ldc = H; m.residual = w.d4; m.ldr = H; m.in_dtype = dt; m.out_dtype = dt;
     EGOT2_TRY(gemm(m, st));
   }
-  return 0;
+  return side_join(st, sd);
 }
 
 // =============================================================================== head + loss
