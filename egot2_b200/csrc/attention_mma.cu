@@ -117,6 +117,13 @@ __device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, i
   }
 }
 
+// p == 0.5: the 32-key mask words of one query row (common.cuh attn_drop_keep)
+template <int NW>
+__device__ __forceinline__ void mask_words(uint64_t key, uint64_t row, int wpr, uint32_t (&w)[NW]) {
+#pragma unroll
+  for (int k = 0; k < NW; ++k) w[k] = k < wpr ? drop_bits(key, row * (uint64_t)wpr + k) : 0u;
+}
+
 // ------------------------------------------------------------------ forward
 template <int DH, int TK16>
 __global__ void __launch_bounds__(TK16 * 32) attn_mma_fwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv,
@@ -158,18 +165,31 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_fwd_kernel(int T, int H, i
   float sum0 = 0.f, sum1 = 0.f;
   const int q0 = r0 + (lane >> 2), q1 = q0 + 8;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const bool bitmode = p_drop == 0.5f;
+  constexpr int NW = (TK16 + 1) / 2;           // 32-key mask words per query row
+  uint32_t w0[NW], w1[NW];
+  if (bitmode) {
+    mask_words<NW>(drop_key, (uint64_t)bh * T + q0, (T + 31) >> 5, w0);
+    mask_words<NW>(drop_key, (uint64_t)bh * T + q1, (T + 31) >> 5, w1);
+  }
   uint32_t p[NT / 2][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     float e0 = exp2f((s[nt][0] - mx0) * sc), e1 = exp2f((s[nt][1] - mx0) * sc);
     float e2 = exp2f((s[nt][2] - mx1) * sc), e3 = exp2f((s[nt][3] - mx1) * sc);
     sum0 += e0 + e1; sum1 += e2 + e3;
-    if (p_drop > 0.f) {
+    if (bitmode) {
+      const int bit = (nt & 3) * 8 + 2 * (lane & 3);
+      e0 = (w0[nt >> 2] >> bit) & 1u ? e0 * 2.f : 0.f;
+      e1 = (w0[nt >> 2] >> (bit + 1)) & 1u ? e1 * 2.f : 0.f;
+      e2 = (w1[nt >> 2] >> bit) & 1u ? e2 * 2.f : 0.f;
+      e3 = (w1[nt >> 2] >> (bit + 1)) & 1u ? e3 * 2.f : 0.f;
+    } else if (p_drop > 0.f) {
       const int c = nt * 8 + 2 * (lane & 3);
-      e0 *= drop_scale(drop_key, ((uint64_t)bh * T + q0) * T + c, p_drop, inv_keep);
-      e1 *= drop_scale(drop_key, ((uint64_t)bh * T + q0) * T + c + 1, p_drop, inv_keep);
-      e2 *= drop_scale(drop_key, ((uint64_t)bh * T + q1) * T + c, p_drop, inv_keep);
-      e3 *= drop_scale(drop_key, ((uint64_t)bh * T + q1) * T + c + 1, p_drop, inv_keep);
+      e0 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q0, T, c, p_drop, inv_keep);
+      e1 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q0, T, c + 1, p_drop, inv_keep);
+      e2 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q1, T, c, p_drop, inv_keep);
+      e3 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q1, T, c + 1, p_drop, inv_keep);
     }
     p[nt >> 1][(nt & 1) * 2] = pack_bf16(e0, e1);
     p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(e2, e3);
@@ -237,6 +257,8 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
   const float scn = rsqrtf((float)DH);
   const float sc2 = scn * 1.4426950408889634f, l2e = 1.4426950408889634f;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const bool bitmode = p_drop == 0.5f;
+  constexpr int NW = (TK16 + 1) / 2;                       // 32-key (or 32-query) blocks of the clip
   const int ra = r0 + (lane >> 2), rb = ra + 8;            // this thread's two tile rows
   const uint32_t uQ = (uint32_t)__cvta_generic_to_shared(sQ), uK = (uint32_t)__cvta_generic_to_shared(sK);
   const uint32_t uV = (uint32_t)__cvta_generic_to_shared(sV), udO = (uint32_t)__cvta_generic_to_shared(sdO);
@@ -248,6 +270,11 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
     load_a<DH>(uQ, r0, a1);
     load_a<DH>(udO, r0, a2);
     const float la = sL[ra] * l2e, lb = sL[rb] * l2e, da = sD[ra], db = sD[rb];
+    uint32_t wa[NW], wb[NW];
+    if (bitmode) {
+      mask_words<NW>(drop_key, (uint64_t)bh * T + ra, (T + 31) >> 5, wa);
+      mask_words<NW>(drop_key, (uint64_t)bh * T + rb, (T + 31) >> 5, wb);
+    }
     float o[Tile<DH>::ND][4];
 #pragma unroll
     for (int i = 0; i < Tile<DH>::ND; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
@@ -264,11 +291,17 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
         float p0 = c < T ? exp2f(s[h2][0] * sc2 - la) : 0.f, p1 = c + 1 < T ? exp2f(s[h2][1] * sc2 - la) : 0.f;
         float p2 = c < T ? exp2f(s[h2][2] * sc2 - lb) : 0.f, p3 = c + 1 < T ? exp2f(s[h2][3] * sc2 - lb) : 0.f;
         float g0 = dp[h2][0], g1 = dp[h2][1], g2 = dp[h2][2], g3 = dp[h2][3];
-        if (p_drop > 0.f) {
-          g0 *= drop_scale(drop_key, ((uint64_t)bh * T + ra) * T + c, p_drop, inv_keep);
-          g1 *= drop_scale(drop_key, ((uint64_t)bh * T + ra) * T + c + 1, p_drop, inv_keep);
-          g2 *= drop_scale(drop_key, ((uint64_t)bh * T + rb) * T + c, p_drop, inv_keep);
-          g3 *= drop_scale(drop_key, ((uint64_t)bh * T + rb) * T + c + 1, p_drop, inv_keep);
+        if (bitmode) {
+          const int bit = (kb & 1) * 16 + h2 * 8 + 2 * (lane & 3);
+          g0 = (wa[kb >> 1] >> bit) & 1u ? g0 * 2.f : 0.f;
+          g1 = (wa[kb >> 1] >> (bit + 1)) & 1u ? g1 * 2.f : 0.f;
+          g2 = (wb[kb >> 1] >> bit) & 1u ? g2 * 2.f : 0.f;
+          g3 = (wb[kb >> 1] >> (bit + 1)) & 1u ? g3 * 2.f : 0.f;
+        } else if (p_drop > 0.f) {
+          g0 *= attn_drop_scale(drop_key, (uint64_t)bh * T + ra, T, c, p_drop, inv_keep);
+          g1 *= attn_drop_scale(drop_key, (uint64_t)bh * T + ra, T, c + 1, p_drop, inv_keep);
+          g2 *= attn_drop_scale(drop_key, (uint64_t)bh * T + rb, T, c, p_drop, inv_keep);
+          g3 *= attn_drop_scale(drop_key, (uint64_t)bh * T + rb, T, c + 1, p_drop, inv_keep);
         }
         ds[h2 * 2] = pack_bf16(p0 * (g0 - da), p1 * (g1 - da));
         ds[h2 * 2 + 1] = pack_bf16(p2 * (g2 - db), p3 * (g3 - db));
@@ -287,6 +320,16 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
     uint32_t a1[Tile<DH>::KS][4], a2[Tile<DH>::KS][4];
     load_a<DH>(uK, r0, a1);
     load_a<DH>(uV, r0, a2);
+    // p == 0.5: the mask word of (query c, this warp's 32-key block) serves all 16 key rows of the warp: lane L hashes
+    // the words of queries L, L+32, ... once and every element fetches its word with a shuffle
+    uint32_t wq[NW];
+    if (bitmode) {
+#pragma unroll
+      for (int j = 0; j < NW; ++j) {
+        const int qy = lane + 32 * j;
+        wq[j] = qy < T ? drop_bits(drop_key, ((uint64_t)bh * T + qy) * (uint64_t)((T + 31) >> 5) + (uint32_t)(r0 >> 5)) : 0u;
+      }
+    }
     float ov[Tile<DH>::ND][4], ok[Tile<DH>::ND][4];
 #pragma unroll
     for (int i = 0; i < Tile<DH>::ND; ++i) { ov[i][0] = ov[i][1] = ov[i][2] = ov[i][3] = 0.f; ok[i][0] = ok[i][1] = ok[i][2] = ok[i][3] = 0.f; }
@@ -304,11 +347,17 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
         float p0 = c < T ? exp2f(s[h2][0] * sc2 - l0) : 0.f, p1 = c + 1 < T ? exp2f(s[h2][1] * sc2 - l1) : 0.f;
         float p2 = c < T ? exp2f(s[h2][2] * sc2 - l0) : 0.f, p3 = c + 1 < T ? exp2f(s[h2][3] * sc2 - l1) : 0.f;
         float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
-        if (p_drop > 0.f) {
-          m0 = drop_scale(drop_key, ((uint64_t)bh * T + c) * T + ra, p_drop, inv_keep);
-          m1 = drop_scale(drop_key, ((uint64_t)bh * T + c + 1) * T + ra, p_drop, inv_keep);
-          m2 = drop_scale(drop_key, ((uint64_t)bh * T + c) * T + rb, p_drop, inv_keep);
-          m3 = drop_scale(drop_key, ((uint64_t)bh * T + c + 1) * T + rb, p_drop, inv_keep);
+        if (bitmode) {
+          const uint32_t u0 = __shfl_sync(0xffffffffu, wq[kb >> 1], c & 31), u1 = __shfl_sync(0xffffffffu, wq[kb >> 1], (c + 1) & 31);
+          m0 = (u0 >> (ra & 31)) & 1u ? 2.f : 0.f;
+          m1 = (u1 >> (ra & 31)) & 1u ? 2.f : 0.f;
+          m2 = (u0 >> (rb & 31)) & 1u ? 2.f : 0.f;
+          m3 = (u1 >> (rb & 31)) & 1u ? 2.f : 0.f;
+        } else if (p_drop > 0.f) {
+          m0 = attn_drop_scale(drop_key, (uint64_t)bh * T + c, T, ra, p_drop, inv_keep);
+          m1 = attn_drop_scale(drop_key, (uint64_t)bh * T + c + 1, T, ra, p_drop, inv_keep);
+          m2 = attn_drop_scale(drop_key, (uint64_t)bh * T + c, T, rb, p_drop, inv_keep);
+          m3 = attn_drop_scale(drop_key, (uint64_t)bh * T + c + 1, T, rb, p_drop, inv_keep);
         }
         pf[h2 * 2] = pack_bf16(p0 * m0, p1 * m1);
         pf[h2 * 2 + 1] = pack_bf16(p2 * m2, p3 * m3);

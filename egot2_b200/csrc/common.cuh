@@ -116,6 +116,16 @@ __host__ __device__ __forceinline__ bool drop_keep(uint64_t key, uint64_t idx, f
   if (bit_mode && p == 0.5f) return (drop_bits(key, idx >> 5) >> (uint32_t)(idx & 31)) & 1u;
   return drop_bits(key, idx) >= thr;
 }
+// Attention-probability dropout for one (query row, key) pair; row = (b*heads + h)*T + query.
+// p == 0.5 (the HHI default) takes ONE random bit per pair: bit key%32 of the hash of (row * ceil(T/32) + key/32), so a
+// thread that owns several keys of one query row pays one hash per 32 keys (attention_mma.cu); other p: one hash per pair.
+__host__ __device__ __forceinline__ bool attn_drop_keep(uint64_t key, uint64_t row, int T, int c, float p, uint32_t thr) {
+  if (p == 0.5f) return (drop_bits(key, row * (uint64_t)((T + 31) >> 5) + (uint32_t)(c >> 5)) >> (c & 31)) & 1u;
+  return drop_bits(key, row * (uint64_t)T + (uint32_t)c) >= thr;
+}
+__device__ __forceinline__ float attn_drop_scale(uint64_t key, uint64_t row, int T, int c, float p, float inv_keep) {
+  return attn_drop_keep(key, row, T, c, p, drop_threshold(p)) ? inv_keep : 0.0f;
+}
 // returns the multiplier: 0 if dropped, 1/(1-p) if kept
 __device__ __forceinline__ float drop_scale(uint64_t key, uint64_t idx, float p, float inv_keep, bool bit_mode = false) {
   return drop_keep(key, idx, p, drop_threshold(p), bit_mode) ? inv_keep : 0.0f;

@@ -228,7 +228,7 @@ def _np_mix64(x):
     return x
 
 
-def dropout_mask_oracle(seed, site, layer, n, p, bit_mode=False):
+def dropout_mask_oracle(seed, site, layer, n, p, bit_mode=False, raw_bits=False):
     """Bit-exact restatement of csrc/common.cuh drop_scale(): multiplier (0 or 1/(1-p)) for element indices 0..n-1."""
     import numpy as np
     M32 = np.uint64(0xFFFFFFFF)
@@ -243,12 +243,28 @@ def dropout_mask_oracle(seed, site, layer, n, p, bit_mode=False):
     with np.errstate(over="ignore"):
         key = _np_mix64(np.array([seed], dtype=np.uint64) ^ (np.uint64(0x9E3779B97F4A7C15) * np.uint64(site + 16 * layer + 1)))[0]
         idx = np.arange(n, dtype=np.uint64)
+        if raw_bits:
+            return bits(key, idx)
         if bit_mode and p == 0.5:      # FFN hidden site: one random bit per element (bit idx%32 of the hash of idx/32)
             keep = ((bits(key, idx >> np.uint64(5)) >> (idx & np.uint64(31))) & np.uint64(1)) == 1
         else:
             thr = np.uint64(int(np.float32(p) * np.float32(4294967296.0) + np.float32(0.5)))
             keep = bits(key, idx) >= thr
     return torch.from_numpy(np.where(keep, np.float32(1.0 / (1.0 - p)), np.float32(0.0)))
+
+
+def attn_mask_oracle(seed, n_bh, T, p):
+    """csrc/common.cuh attn_drop_keep() for every (b*heads+h, query, key): multiplier 0 or 1/(1-p), shape (n_bh*T*T,)."""
+    import numpy as np
+    if p != 0.5:
+        return dropout_mask_oracle(seed, 3, 0, n_bh * T * T, p)              # SITE_ATTN = 3, idx = row*T + key
+    wpr = (T + 31) // 32
+    words = dropout_mask_oracle(seed, 3, 0, n_bh * T * wpr, 0.25, raw_bits=True)      # hash of row*wpr + key//32
+    rows = np.arange(n_bh * T, dtype=np.int64)[:, None]
+    keys = np.arange(T, dtype=np.int64)[None, :]
+    w = words[rows * wpr + keys // 32]
+    keep = (w >> (keys % 32).astype(np.uint64)) & np.uint64(1)
+    return torch.from_numpy(np.where(keep == 1, np.float32(2.0), np.float32(0.0)).reshape(-1))
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
@@ -258,7 +274,8 @@ def test_attention_dropout_mask_is_exact(dtype, T, H, heads):
     the documented counter-based generator — checked against a torch reference fed the same mask."""
     from egot2_b200 import engine as E
     torch.manual_seed(4)
-    B, p, seed = 2, 0.25, 99
+    B, seed = 2, 99
+    p = 0.5 if T in (48, 128, 150) else 0.25     # p == 0.5: one random bit per (query, key) pair, 32 keys per hash
     tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
     qkv = (torch.randn(B, T, 3 * H, device="cuda") * 0.7).to(tdt)
     dout = torch.randn(B, T, H, device="cuda").to(tdt)
@@ -271,7 +288,7 @@ def test_attention_dropout_mask_is_exact(dtype, T, H, heads):
     ws = torch.empty(max(nws, 16), device="cuda", dtype=torch.uint8)
     L.call("egot2_attention_bwd", E._dt(dtype), B, T, H, heads, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(),
            dout.data_ptr(), dqkv.data_ptr(), p, 1, seed, ws.data_ptr(), nws, E._stream())
-    mask = dropout_mask_oracle(seed, 3, 0, B * heads * T * T, p).reshape(B, heads, T, T).cuda().double()   # SITE_ATTN = 3
+    mask = attn_mask_oracle(seed, B * heads, T, p).reshape(B, heads, T, T).cuda().double()
     q = qkv.double().requires_grad_(True)
     dh = H // heads
     qq, kk, vv = q.split(H, dim=-1)
