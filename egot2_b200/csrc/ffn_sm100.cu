@@ -27,6 +27,8 @@
 // TMEM (per CTA): acc1 double-buffered (2 x 128 columns) + acc2 (128 columns).
 // Barriers that the leader's MMA threads wait on (operands of BOTH CTAs ready, accumulators drained by BOTH epilogues)
 // live in the leader and receive remote arrivals; completion barriers are signalled in both CTAs by multicast commits.
+#include <stdlib.h>
+
 #include "ops.h"
 #include "sm100.cuh"
 
@@ -52,6 +54,7 @@ struct FfnArgs {
   const float* b1; const float* b2; const float* ln_g; const float* ln_b; float eps;
   float* stat2;
   int save_hid;
+  int hid_tiled;         // hidden tensor layout: 0 = row-major (M, FF); 1 = tile-major [M/128][FF/64][128][64] (16 KB contiguous per TMA box)
   uint2* hmask;          // [FF/64][M] x 64 bits: hidden activation != 0 (ReLU gate x dropout keep), for ffn_bwd_dx
   const bf16* d1;        // backward: gradient arriving through the residual branch (added to d3), (M,128)
   float p_drop; uint64_t key_ffn, key_drop2;
@@ -86,7 +89,10 @@ __device__ __forceinline__ void sts128(uint32_t dst, uint32_t a, uint32_t b, uin
 //     dhid_c = (d2 . W2[:, c]) * gate_c / (1-p)   (GEMM1: A = d2 tile, B = W2 columns, MN-major; gate bits from hmask)
 //     d3     = sum_c dhid_c . W1[c, :] + d1        (GEMM2: A = dhid tile, B = W1 rows, MN-major)
 //   dhid leaves through TMA (it feeds the two weight-gradient GEMMs), d3 replaces the forward's y2 output.
-template <bool BWD>
+// DROP: 0 = no dropout (inference), 1 = p == 0.5 (one random bit per hidden element), 2 = general p (hash per element).
+// A template parameter, not a runtime branch: the three variants of the fully unrolled per-chunk epilogue would triple a
+// body that already exceeds the 32 KB L1.5 instruction cache.
+template <bool BWD, int DROP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_hid,
@@ -110,7 +116,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   float* red = reinterpret_cast<float*>(gen + (red_off - base));
   // bias / LayerNorm vectors live in shared memory: every lane of an epilogue warp reads the same column values, so
   // these are conflict-free broadcasts instead of a chain of dependent global loads on the per-chunk critical path
-  float* sVec = red + 256;                 // b2[128], ln_g[128], ln_b[128]
+  float* sVec = red + 512;                 // b2[128], ln_g[128], ln_b[128]   (red: sum[2][128], sumsq[2][128])
   float* sB1 = sVec + 384;                 // b1[FF]
   if (!BWD) {
     const float s1 = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;      // dropout scale folded into the bias (see epilogue)
@@ -131,6 +137,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #endif
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  if (threadIdx.x == 64) TR(60, 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2);
@@ -151,6 +158,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t acc2 = tmem + 256;
+  if (threadIdx.x == 64) TR(60, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -244,8 +252,14 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         mbar_wait(hl_full + 8 * hb, (c / HB) & 1);      // this CTA's epilogue wrote (and proxy-fenced) hid(c)
         TR(c, 11);
         if (a.save_hid) {
-          tma_store_2d(&tm_hid, sHid + hb * TILE, c * FC, m0);
-          tma_store_2d(&tm_hid, sHid + hb * TILE + HALF, c * FC + 64, m0);
+          if (a.hid_tiled) {      // box (tile, ff-half) is one contiguous 16 KB block
+            const int row = ((int)blockIdx.x * (a.FF / 64) + c * 2) * 128;
+            tma_store_2d(&tm_hid, sHid + hb * TILE, 0, row);
+            tma_store_2d(&tm_hid, sHid + hb * TILE + HALF, 0, row + 128);
+          } else {
+            tma_store_2d(&tm_hid, sHid + hb * TILE, c * FC, m0);
+            tma_store_2d(&tm_hid, sHid + hb * TILE + HALF, c * FC + 64, m0);
+          }
           tma_store_commit();
           tma_store_wait_read();
         }
@@ -264,7 +278,6 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
     const uint32_t thr = drop_threshold(a.p_drop);
-    const bool bitmode = a.p_drop == 0.5f;
     const uint32_t a1_empty_ldr = mapa(a1_empty, 0), h_full_ldr = mapa(h_full, 0);
     for (int c = 0; c < NC; ++c) {
       const int bsel = c & 1;
@@ -290,7 +303,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
           const int n0 = c * FC + ch * 64 + h2 * 32;
           const uint64_t idx0 = (uint64_t)m * a.FF + n0;          // multiple of 32: this thread owns one 32-bit mask word
-          const uint32_t mword = bitmode ? drop_bits(a.key_ffn, idx0 >> 5) : 0xFFFFFFFFu;
+          const uint32_t mword = DROP == 1 ? drop_bits(a.key_ffn, idx0 >> 5) : 0xFFFFFFFFu;
           uint32_t gw = 0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -300,12 +313,12 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             float v1 = fmaxf(fmaf(__uint_as_float(rr[j + 1]), inv_keep, b4.y), 0.f);
             float v2 = fmaxf(fmaf(__uint_as_float(rr[j + 2]), inv_keep, b4.z), 0.f);
             float v3 = fmaxf(fmaf(__uint_as_float(rr[j + 3]), inv_keep, b4.w), 0.f);
-            if (bitmode) {
+            if constexpr (DROP == 1) {
               v0 = (mword >> j) & 1u ? v0 : 0.f;
               v1 = (mword >> (j + 1)) & 1u ? v1 : 0.f;
               v2 = (mword >> (j + 2)) & 1u ? v2 : 0.f;
               v3 = (mword >> (j + 3)) & 1u ? v3 : 0.f;
-            } else if (a.p_drop > 0.f) {
+            } else if constexpr (DROP == 2) {
               v0 = drop_bits(a.key_ffn, idx0 + j) >= thr ? v0 : 0.f;
               v1 = drop_bits(a.key_ffn, idx0 + j + 1) >= thr ? v1 : 0.f;
               v2 = drop_bits(a.key_ffn, idx0 + j + 2) >= thr ? v2 : 0.f;
@@ -354,44 +367,43 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
     // ------------------------------------------------------------ final: + b2, dropout2, + residual, LayerNorm2
     mbar_wait(a2_full, 0);                    // every GEMM of the pair retired: sHid / sX are free to stage the outputs
+    if (threadIdx.x == 64) TR(60, 2);
     for (int c = NC - HB; c < NC; ++c)        // the last hidden tiles have left through TMA
       if (c >= 0) mbar_wait(hs_empty + 8 * (c % HB), (c / HB) & 1);
     tc_fence_after();
-    float y[64];
+    if (threadIdx.x == 64) TR(60, 3);
+    // The final epilogue runs ONCE per CTA: fully unrolled over 64 columns it was ~2k straight-line instructions whose
+    // cold instruction-cache misses cost ~20k cycles per CTA (stall_no_inst in ncu).  It is therefore written as two
+    // compact loops over 8-column groups (8-column TMEM loads, nothing indexed dynamically).
     const int nb = ch * 64;
     const uint32_t xrow = sX + ch * HALF + (uint32_t)r * 128;
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      uint32_t rr[32];
-      tmem_ld_32x32(acc2 + lane_addr + nb + h2 * 32, rr);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) y[h2 * 32 + j] = __uint_as_float(rr[j]);
-    }
+    const uint32_t yrow = sHid + ch * HALF + (uint32_t)r * 128;
     if constexpr (BWD) {
       // d3 = acc2 + d1 (gradient through the residual branch); with no dropout2, d1 IS the d2 tile still in sX
-      const uint32_t orow = sHid + ch * HALF + (uint32_t)r * 128;
       const bf16* d1row = (a.d1 && row_ok) ? a.d1 + (size_t)m * H + nb : nullptr;
-#pragma unroll
+#pragma unroll 1
       for (int j8 = 0; j8 < 8; ++j8) {
+        uint32_t rr[8];
+        tmem_ld_32x8(acc2 + lane_addr + nb + j8 * 8, rr);
+        const uint32_t sw = (uint32_t)((j8 ^ (r & 7)) << 4);
         uint32_t w0, w1, w2, w3;
         if (a.d1) {
           uint4 t = make_uint4(0u, 0u, 0u, 0u);
           if (d1row) t = __ldg(reinterpret_cast<const uint4*>(d1row) + j8);
           w0 = t.x; w1 = t.y; w2 = t.z; w3 = t.w;
         } else {
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                       : "r"(xrow + (uint32_t)((j8 ^ (r & 7)) << 4)));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(xrow + sw));
         }
+        tmem_ld_wait();
         const uint32_t w[4] = {w0, w1, w2, w3};
         uint32_t oo[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int j = j8 * 8 + 2 * k;
-          __nv_bfloat162 u = __floats2bfloat162_rn(y[j] + __uint_as_float(w[k] << 16), y[j + 1] + __uint_as_float(w[k] & 0xffff0000u));
+          __nv_bfloat162 u = __floats2bfloat162_rn(__uint_as_float(rr[2 * k]) + __uint_as_float(w[k] << 16),
+                                                   __uint_as_float(rr[2 * k + 1]) + __uint_as_float(w[k] & 0xffff0000u));
           oo[k] = *reinterpret_cast<uint32_t*>(&u);
         }
-        sts128(orow + (uint32_t)((j8 ^ (r & 7)) << 4), oo[0], oo[1], oo[2], oo[3]);
+        sts128(yrow + sw, oo[0], oo[1], oo[2], oo[3]);
       }
       fence_proxy_async();
       named_bar_sync(2, 256);
@@ -402,75 +414,80 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         tma_store_wait_all();
       }
     } else {
-    float sum = 0.f;
+      // pass 1: y = acc2 + b2 -> dropout2 -> + x1, rounded to bf16 (what LayerNorm2 sees and what is saved); staged in the
+      // first hid buffer; row sum / sum of squares on the rounded values
+      float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+      for (int j8 = 0; j8 < 8; ++j8) {
+        uint32_t rr[8];
+        tmem_ld_32x8(acc2 + lane_addr + nb + j8 * 8, rr);
+        const uint32_t sw = (uint32_t)((j8 ^ (r & 7)) << 4);
+        uint32_t w0, w1, w2, w3;                  // residual: 8 bf16 of x1 from the swizzled smem tile
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(xrow + sw));
+        tmem_ld_wait();
+        const uint32_t w[4] = {w0, w1, w2, w3};
+        uint32_t yy[4];
 #pragma unroll
-    for (int j8 = 0; j8 < 8; ++j8) {
-      uint32_t w0, w1, w2, w3;                  // residual: 8 bf16 of x1 from the swizzled smem tile
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                   : "r"(xrow + (uint32_t)((j8 ^ (r & 7)) << 4)));
-      const uint32_t w[4] = {w0, w1, w2, w3};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = j8 * 8 + 2 * k;
-        float v0 = y[j] + sVec[nb + j], v1 = y[j + 1] + sVec[nb + j + 1];
-        if (a.p_drop > 0.f) {
-          v0 = drop_bits(a.key_drop2, (uint64_t)m * H + nb + j) >= thr ? v0 * inv_keep : 0.f;
-          v1 = drop_bits(a.key_drop2, (uint64_t)m * H + nb + j + 1) >= thr ? v1 * inv_keep : 0.f;
+        for (int k = 0; k < 4; ++k) {
+          const int j = j8 * 8 + 2 * k;
+          float v0 = __uint_as_float(rr[2 * k]) + sVec[nb + j], v1 = __uint_as_float(rr[2 * k + 1]) + sVec[nb + j + 1];
+          if constexpr (DROP != 0) {
+            v0 = drop_bits(a.key_drop2, (uint64_t)m * H + nb + j) >= thr ? v0 * inv_keep : 0.f;
+            v1 = drop_bits(a.key_drop2, (uint64_t)m * H + nb + j + 1) >= thr ? v1 * inv_keep : 0.f;
+          }
+          v0 += __uint_as_float(w[k] << 16);
+          v1 += __uint_as_float(w[k] & 0xffff0000u);
+          __nv_bfloat162 t = __floats2bfloat162_rn(v0, v1);
+          yy[k] = *reinterpret_cast<uint32_t*>(&t);
+          v0 = __uint_as_float(yy[k] << 16);
+          v1 = __uint_as_float(yy[k] & 0xffff0000u);
+          sum += v0 + v1;
+          sq = fmaf(v0, v0, fmaf(v1, v1, sq));
         }
-        v0 += __uint_as_float(w[k] << 16);
-        v1 += __uint_as_float(w[k] & 0xffff0000u);
-        // LayerNorm sees the bf16-rounded pre-norm activation, exactly what is saved for backward
-        v0 = __bfloat162float(__float2bfloat16_rn(v0));
-        v1 = __bfloat162float(__float2bfloat16_rn(v1));
-        y[j] = v0; y[j + 1] = v1;
-        sum += v0 + v1;
+        sts128(yrow + sw, yy[0], yy[1], yy[2], yy[3]);
+      }
+      red[ch * 128 + r] = sum;
+      red[256 + ch * 128 + r] = sq;
+      named_bar_sync(1, 256);
+      const float mean = (red[r] + red[128 + r]) * (1.f / H);
+      const float var = fmaxf((red[256 + r] + red[384 + r]) * (1.f / H) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + a.eps);
+      if (row_ok && ch == 0) { a.stat2[2 * (size_t)m] = mean; a.stat2[2 * (size_t)m + 1] = rstd; }
+      // pass 2: x_out = (y - mean) * rstd * g + b, staged in the x1 tile (its residual reads are done)
+      const uint32_t orow = xrow;
+#pragma unroll 1
+      for (int j8 = 0; j8 < 8; ++j8) {
+        const uint32_t sw = (uint32_t)((j8 ^ (r & 7)) << 4);
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(yrow + sw));
+        const uint32_t w[4] = {w0, w1, w2, w3};
+        uint32_t oo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = nb + j8 * 8 + 2 * k;
+          const float o0 = (__uint_as_float(w[k] << 16) - mean) * rstd * sVec[128 + j] + sVec[256 + j];
+          const float o1 = (__uint_as_float(w[k] & 0xffff0000u) - mean) * rstd * sVec[128 + j + 1] + sVec[256 + j + 1];
+          __nv_bfloat162 u = __floats2bfloat162_rn(o0, o1);
+          oo[k] = *reinterpret_cast<uint32_t*>(&u);
+        }
+        sts128(orow + sw, oo[0], oo[1], oo[2], oo[3]);
+      }
+      fence_proxy_async();
+      named_bar_sync(2, 256);
+      if (warp == 2 && lane == 0) {
+        tma_store_2d(&tm_y2, sHid, 0, m0);
+        tma_store_2d(&tm_y2, sHid + HALF, 64, m0);
+        tma_store_2d(&tm_out, sX, 0, m0);
+        tma_store_2d(&tm_out, sX + HALF, 64, m0);
+        tma_store_commit();
+        tma_store_wait_all();
       }
     }
-    red[ch * 128 + r] = sum;
-    named_bar_sync(1, 256);
-    const float mean = (red[r] + red[128 + r]) * (1.f / H);
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < 64; ++j) { const float d = y[j] - mean; sq += d * d; }
-    named_bar_sync(2, 256);
-    red[ch * 128 + r] = sq;
-    named_bar_sync(1, 256);
-    const float rstd = rsqrtf((red[r] + red[128 + r]) * (1.f / H) + a.eps);
-    if (row_ok && ch == 0) { a.stat2[2 * (size_t)m] = mean; a.stat2[2 * (size_t)m + 1] = rstd; }
-    // stage y2 (pre-norm, saved) in the first hid buffer and x_out in the x1 tile (its residual reads are done: every
-    // epilogue thread passed the barriers above), then two TMA stores each
-    const uint32_t yrow = sHid + ch * HALF + (uint32_t)r * 128, orow = sX + ch * HALF + (uint32_t)r * 128;
-#pragma unroll
-    for (int j8 = 0; j8 < 8; ++j8) {
-      uint32_t yy[4], oo[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = j8 * 8 + 2 * k;
-        __nv_bfloat162 t = __floats2bfloat162_rn(y[j], y[j + 1]);
-        yy[k] = *reinterpret_cast<uint32_t*>(&t);
-        const float o0 = (y[j] - mean) * rstd * sVec[128 + nb + j] + sVec[256 + nb + j];
-        const float o1 = (y[j + 1] - mean) * rstd * sVec[128 + nb + j + 1] + sVec[256 + nb + j + 1];
-        __nv_bfloat162 u = __floats2bfloat162_rn(o0, o1);
-        oo[k] = *reinterpret_cast<uint32_t*>(&u);
-      }
-      const uint32_t sw = (uint32_t)((j8 ^ (r & 7)) << 4);
-      sts128(yrow + sw, yy[0], yy[1], yy[2], yy[3]);
-      sts128(orow + sw, oo[0], oo[1], oo[2], oo[3]);
-    }
-    fence_proxy_async();
-    named_bar_sync(2, 256);
-    if (warp == 2 && lane == 0) {
-      tma_store_2d(&tm_y2, sHid, 0, m0);
-      tma_store_2d(&tm_y2, sHid + HALF, 64, m0);
-      tma_store_2d(&tm_out, sX, 0, m0);
-      tma_store_2d(&tm_out, sX + HALF, 64, m0);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
-    }   // !BWD
   }
+  if (threadIdx.x == 64) TR(60, 4);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 64) TR(60, 5);
   cluster_sync_all();                         // the peer may still be signalling this CTA's barriers / using the pair's TMEM
 #ifdef EGOT2_FFN_TRACE
   if (threadIdx.x == 0 && a.trace) {
@@ -522,13 +539,17 @@ bool ffn_fused_supported(int dtype, int Hdim, int FF) {
 
 static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2,
                       const CUtensorMap& thid, const CUtensorMap& ty2, const CUtensorMap& tout, FfnArgs& a, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)TILE * (1 + HB) + (size_t)RING * STAGE + 512 + (256 + 384 + (size_t)FF) * 4;
+  const size_t smem = 1024 + (size_t)TILE * (1 + HB) + (size_t)RING * STAGE + 512 + (512 + 384 + (size_t)FF) * 4;
   EGOT2_CHECK(smem <= 227 * 1024, "ffn_fused: FF=%d does not fit the bias stage in shared memory", FF);
-  static size_t set_for[2] = {0, 0};
-  if (set_for[bwd] < smem) {
-    if (bwd) EGOT2_CUDA(cudaFuncSetAttribute(ffn_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else EGOT2_CUDA(cudaFuncSetAttribute(ffn_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set_for[bwd] = smem;
+  const int drop = bwd ? 0 : (a.p_drop <= 0.f ? 0 : (a.p_drop == 0.5f ? 1 : 2));
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FfnArgs);
+  static const KernelFn kernels[4] = {ffn_sm100_kernel<false, 0>, ffn_sm100_kernel<false, 1>, ffn_sm100_kernel<false, 2>,
+                                      ffn_sm100_kernel<true, 0>};
+  const int ki = bwd ? 3 : drop;
+  static size_t set_for[4] = {0, 0, 0, 0};
+  if (set_for[ki] < smem) {
+    EGOT2_CUDA(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set_for[ki] = smem;
   }
   a.trace = nullptr;
 #ifdef EGOT2_FFN_TRACE
@@ -540,8 +561,7 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
   {
     ProfScope prof(st, bwd ? "ffn_bwd_dx_sm100 M%d H128 FF%d" : "ffn_fwd_sm100 M%d H128 FF%d", M, FF);
     const int tiles = (M + BM - 1) / BM, grid = (tiles + 1) / 2 * 2;      // whole CTA pairs
-    if (bwd) ffn_sm100_kernel<true><<<grid, NTHREADS, smem, st>>>(tx, tw1, tw2, thid, ty2, tout, a);
-    else ffn_sm100_kernel<false><<<grid, NTHREADS, smem, st>>>(tx, tw1, tw2, thid, ty2, tout, a);
+    kernels[ki]<<<grid, NTHREADS, smem, st>>>(tx, tw1, tw2, thid, ty2, tout, a);
     EGOT2_LAUNCH_CHECK();
   }
 #ifdef EGOT2_FFN_TRACE
@@ -552,8 +572,9 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
       cudaStreamSynchronize(st);
       cudaMemcpy(h, dtrace, sizeof(h), cudaMemcpyDeviceToHost);
       long long t0 = h[0];
-      for (int i = 0; i < 64 * 16; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+      for (int i = 0; i < 64 * 16; ++i) if (h[i] > 0 && h[i] < t0) t0 = h[i];
       printf("ffn trace (cycles since first stamp): c | prod w1e w2e | mma w1f a1e w2f hf | epi a1f ldtm comp hwait hfull | st hf rd\n");
+      printf("ffn stamps: entry %lld setup %lld a2_full %lld hs_done %lld | resid+sum %lld bar1 %lld staged %lld bar2 %lld tma_issued %lld | epi_done %lld cta_sync %lld\n", h[60*16+0]-t0, h[60*16+1]-t0, h[60*16+2]-t0, h[60*16+3]-t0, h[60*16+6]-t0, h[60*16+7]-t0, h[60*16+8]-t0, h[60*16+9]-t0, h[60*16+10]-t0, h[60*16+4]-t0, h[60*16+5]-t0);
       for (int c = 0; c < FF / FC && c < 64; ++c) {
         printf("%2d |", c);
         for (int k = 0; k < 13; ++k) printf(" %7lld%s", h[c * 16 + k] ? h[c * 16 + k] - t0 : -1LL, (k == 1 || k == 5 || k == 10) ? " |" : "");
@@ -575,12 +596,16 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
   EGOT2_TRY(kmajor_map(&tx, x1, H, M, H, 128));
   EGOT2_TRY(kmajor_map(&tw1, W1, H, FF, H, 64));      // each CTA of the pair fetches 64 rows of a stage
   EGOT2_TRY(kmajor_map(&tw2, W2, FF, H, FF, 64));
-  EGOT2_TRY(kmajor_map(&thid, hid ? hid : y2, FF, M, FF, 128));    // never dereferenced when hid == nullptr
+  if (getenv("EGOT2_FFN_NOHID")) hid = nullptr;                 // EXPERIMENT: how much of the kernel is the hidden-tensor write?
+  const bool tiled = getenv("EGOT2_HID_TILED") != nullptr;      // EXPERIMENT: tile-major hidden layout (consumers not adapted)
+  const int tiles128 = (M + 127) / 128;
+  if (tiled && hid) EGOT2_TRY(kmajor_map(&thid, hid, 64, tiles128 * (FF / 64) * 128, 64, 128));
+  else EGOT2_TRY(kmajor_map(&thid, hid ? hid : y2, FF, M, FF, 128));    // never dereferenced when hid == nullptr
   EGOT2_TRY(kmajor_map(&ty2, y2, H, M, H, 128));
   EGOT2_TRY(kmajor_map(&tout, x_out, H, M, H, 128));
   FfnArgs a;
   a.M = M; a.FF = FF; a.b1 = b1; a.b2 = b2; a.ln_g = ln_g; a.ln_b = ln_b; a.eps = eps;
-  a.stat2 = stat2; a.save_hid = hid != nullptr; a.hmask = (uint2*)hmask; a.d1 = nullptr;
+  a.stat2 = stat2; a.save_hid = hid != nullptr; a.hmask = (uint2*)hmask; a.d1 = nullptr; a.hid_tiled = tiled && hid;
   a.p_drop = p_drop; a.key_ffn = key_ffn; a.key_drop2 = key_drop2;
   return ffn_launch(false, M, FF, tx, tw1, tw2, thid, ty2, tout, a, st);
 }
@@ -598,7 +623,7 @@ int ffn_fused_bwd_dx(int M, int FF, const void* d2, const void* d1, const void* 
   EGOT2_TRY(kmajor_map(&ty2, d3, H, M, H, 128));
   FfnArgs a;
   a.M = M; a.FF = FF; a.b1 = nullptr; a.b2 = nullptr; a.ln_g = nullptr; a.ln_b = nullptr; a.eps = 0.f;
-  a.stat2 = nullptr; a.save_hid = 1; a.hmask = (uint2*)const_cast<void*>(hmask); a.d1 = (const bf16*)d1;
+  a.stat2 = nullptr; a.save_hid = 1; a.hmask = (uint2*)const_cast<void*>(hmask); a.d1 = (const bf16*)d1; a.hid_tiled = 0;
   a.p_drop = p_drop; a.key_ffn = 0; a.key_drop2 = 0;
   return ffn_launch(true, M, FF, tx, tw1, tw2, thid, ty2, ty2, a, st);
 }
