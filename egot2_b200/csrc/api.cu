@@ -18,6 +18,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static const bool on = !(getenv("EGOT2_PDL") && atoi(getenv("EGOT2_PDL")) == 0);
+  return on;
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;

@@ -13,6 +13,10 @@
 
 #include "ops.h"
 
+#ifndef EGOT2_ATTN_MINB
+#define EGOT2_ATTN_MINB 4      // resident CTAs per SM the register allocation aims at (T <= 96 variants)
+#endif
+
 namespace egot2 {
 
 namespace {
@@ -105,58 +109,80 @@ __device__ __forceinline__ void gemm_pv_kb(float (&o)[Tile<DH>::ND][4], const ui
   }
 }
 
-// stage rows [0,T) x DH of a strided global matrix into smem [Tpad][LD]; rows >= T are zero
-template <int DH>
-__device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, int ld_src, int T, int Tpad) {
+// stage rows [0,T) x DH of a strided global matrix into smem [TK16*16][LD]; rows >= T are zero.  Asynchronous (cp.async,
+// 16 B per request, zero-fill for the padding rows): a thread's requests for ALL staged matrices are in flight together,
+// so the CTA pays one global round trip, not one per matrix; the caller commits and waits (stage_wait) before its
+// barrier.  The CTA has exactly TK16*32 threads, so the trip count (DH/16 chunks per thread) is a compile-time constant.
+template <int DH, int TK16>
+__device__ __forceinline__ void stage(uint32_t dst, const bf16* __restrict__ src, int ld_src, int T) {
   constexpr int CH = DH / 8;                 // 16-byte chunks per row
-  for (int e = threadIdx.x; e < Tpad * CH; e += blockDim.x) {
-    const int r = e / CH, c = (e % CH) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < T) v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld_src + c);
-    *reinterpret_cast<uint4*>(dst + r * Tile<DH>::LD + c) = v;
+  constexpr int RPI = TK16 * 32 / CH;        // rows covered by one pass of the CTA
+  const int r0 = threadIdx.x / CH, c = (threadIdx.x % CH) * 8;
+#pragma unroll
+  for (int i = 0; i < DH / 16; ++i) {
+    const int r = r0 + i * RPI;
+    const bool ok = r < T;
+    const bf16* g = src + (size_t)(ok ? r : 0) * ld_src + c;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)((r * Tile<DH>::LD + c) * 2)), "l"(g),
+                 "r"(ok ? 16 : 0) : "memory");
   }
 }
-
-// p == 0.5: the 32-key mask words of one query row (common.cuh attn_drop_keep)
-template <int NW>
-__device__ __forceinline__ void mask_words(uint64_t key, uint64_t row, int wpr, uint32_t (&w)[NW]) {
-#pragma unroll
-  for (int k = 0; k < NW; ++k) w[k] = k < wpr ? drop_bits(key, row * (uint64_t)wpr + k) : 0u;
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// 2^x on the SFU, one instruction (the arguments here are <= 0 up to rounding; -inf -> 0)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
+// p == 0.5: the 32-key mask words of one query row (common.cuh attn_drop_keep), pre-shifted by `sh` so that the bit
+// of a thread's element sits at a compile-time position
+template <int NW>
+__device__ __forceinline__ void mask_words(uint64_t key, uint64_t row, int wpr, int sh, uint32_t (&w)[NW]) {
+#pragma unroll
+  for (int k = 0; k < NW; ++k) w[k] = k < wpr ? drop_bits(key, row * (uint64_t)wpr + k) >> sh : 0u;
+}
+
+// Dropout handling is a template parameter (the three variants share nothing on the per-element path and the unused ones
+// would only dilute the instruction cache): MODE 0 no dropout, 1 p == 0.5 (one random bit per pair), 2 general p.
 // ------------------------------------------------------------------ forward
-template <int DH, int TK16>
-__global__ void __launch_bounds__(TK16 * 32) attn_mma_fwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv,
+template <int DH, int TK16, int MODE>
+__global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) attn_mma_fwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv,
                                                                  bf16* __restrict__ out, float* __restrict__ lse,
                                                                  float p_drop, uint64_t drop_key) {
   constexpr int NT = TK16 * 2, LD = Tile<DH>::LD, TP = TK16 * 16;
   extern __shared__ __align__(16) uint8_t smem[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem);
-  bf16* sK = sQ + TP * LD;
-  bf16* sV = sK + TP * LD;
+  const uint32_t uQ = (uint32_t)__cvta_generic_to_shared(smem), uK = uQ + TP * LD * 2, uV = uK + TP * LD * 2;
   const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bf16* base = qkv + (size_t)b * T * 3 * H + h * DH;
-  stage<DH>(sQ, base, 3 * H, T, TP);
-  stage<DH>(sK, base + H, 3 * H, T, TP);
-  stage<DH>(sV, base + 2 * H, 3 * H, T, TP);
+  EGOT2_PDL_ENTER();
+  stage<DH, TK16>(uQ, base, 3 * H, T);
+  stage<DH, TK16>(uK, base + H, 3 * H, T);
+  stage<DH, TK16>(uV, base + 2 * H, 3 * H, T);
+  stage_wait();
   __syncthreads();
   const int r0 = warp * 16;
   if (r0 >= T) return;
   uint32_t aq[Tile<DH>::KS][4];
-  load_a<DH>((uint32_t)__cvta_generic_to_shared(sQ), r0, aq);
+  load_a<DH>(uQ, r0, aq);
   float s[NT][4];
 #pragma unroll
   for (int i = 0; i < NT; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-  gemm_rc<DH, NT>(s, aq, (uint32_t)__cvta_generic_to_shared(sK));
+  gemm_rc<DH, NT>(s, aq, uK);
   // softmax over keys; thread holds rows (lane/4) and (lane/4 + 8), columns nt*8 + 2*(lane%4) + {0,1}
   const float sc = rsqrtf((float)DH) * 1.4426950408889634f;        // scale * log2(e)
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
-    const int c = nt * 8 + 2 * (lane & 3);
-    if (c >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-    if (c + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    if (nt * 8 + 8 > T) {                      // warp-uniform: only the last tile(s) hold padded keys
+      const int c = nt * 8 + 2 * (lane & 3);
+      if (c >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (c + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    }
     mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
     mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
   }
@@ -164,27 +190,26 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_fwd_kernel(int T, int H, i
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
   float sum0 = 0.f, sum1 = 0.f;
   const int q0 = r0 + (lane >> 2), q1 = q0 + 8;
-  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  const bool bitmode = p_drop == 0.5f;
+  const float ms0 = mx0 * sc, ms1 = mx1 * sc;
   constexpr int NW = (TK16 + 1) / 2;           // 32-key mask words per query row
   uint32_t w0[NW], w1[NW];
-  if (bitmode) {
-    mask_words<NW>(drop_key, (uint64_t)bh * T + q0, (T + 31) >> 5, w0);
-    mask_words<NW>(drop_key, (uint64_t)bh * T + q1, (T + 31) >> 5, w1);
+  if (MODE == 1) {
+    mask_words<NW>(drop_key, (uint64_t)bh * T + q0, (T + 31) >> 5, 2 * (lane & 3), w0);
+    mask_words<NW>(drop_key, (uint64_t)bh * T + q1, (T + 31) >> 5, 2 * (lane & 3), w1);
   }
+  // MODE 1 keeps e or zeroes it; the 1/(1-p) = 2 of the kept entries is folded into the final row scale (exact: power of 2)
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   uint32_t p[NT / 2][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
-    float e0 = exp2f((s[nt][0] - mx0) * sc), e1 = exp2f((s[nt][1] - mx0) * sc);
-    float e2 = exp2f((s[nt][2] - mx1) * sc), e3 = exp2f((s[nt][3] - mx1) * sc);
+    float e0 = ex2(fmaf(s[nt][0], sc, -ms0)), e1 = ex2(fmaf(s[nt][1], sc, -ms0));
+    float e2 = ex2(fmaf(s[nt][2], sc, -ms1)), e3 = ex2(fmaf(s[nt][3], sc, -ms1));
     sum0 += e0 + e1; sum1 += e2 + e3;
-    if (bitmode) {
-      const int bit = (nt & 3) * 8 + 2 * (lane & 3);
-      e0 = (w0[nt >> 2] >> bit) & 1u ? e0 * 2.f : 0.f;
-      e1 = (w0[nt >> 2] >> (bit + 1)) & 1u ? e1 * 2.f : 0.f;
-      e2 = (w1[nt >> 2] >> bit) & 1u ? e2 * 2.f : 0.f;
-      e3 = (w1[nt >> 2] >> (bit + 1)) & 1u ? e3 * 2.f : 0.f;
-    } else if (p_drop > 0.f) {
+    if (MODE == 1) {
+      const uint32_t m0 = w0[nt >> 2] >> ((nt & 3) * 8), m1 = w1[nt >> 2] >> ((nt & 3) * 8);
+      e0 = (m0 & 1u) ? e0 : 0.f; e1 = (m0 & 2u) ? e1 : 0.f;
+      e2 = (m1 & 1u) ? e2 : 0.f; e3 = (m1 & 2u) ? e3 : 0.f;
+    } else if (MODE == 2) {
       const int c = nt * 8 + 2 * (lane & 3);
       e0 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q0, T, c, p_drop, inv_keep);
       e1 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q0, T, c + 1, p_drop, inv_keep);
@@ -199,8 +224,9 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_fwd_kernel(int T, int H, i
   float o[Tile<DH>::ND][4];
 #pragma unroll
   for (int i = 0; i < Tile<DH>::ND; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-  gemm_pv<DH, NT>(o, p, (uint32_t)__cvta_generic_to_shared(sV));
-  const float i0 = 1.f / sum0, i1 = 1.f / sum1;
+  gemm_pv<DH, NT>(o, p, uV);
+  const float fold = MODE == 1 ? 2.f : 1.f;
+  const float i0 = fold / sum0, i1 = fold / sum1;
   bf16* ob = out + (size_t)b * T * H + h * DH;
 #pragma unroll
   for (int nd = 0; nd < Tile<DH>::ND; ++nd) {
@@ -216,52 +242,62 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_fwd_kernel(int T, int H, i
 }
 
 // ------------------------------------------------------------------ backward
-template <int DH, int TK16>
-__global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv,
+template <int DH, int TK16, int MODE>
+__global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) attn_mma_bwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv,
                                                                  const bf16* __restrict__ out, const float* __restrict__ lse,
                                                                  const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
                                                                  float p_drop, uint64_t drop_key) {
-  constexpr int NT = TK16 * 2, LD = Tile<DH>::LD, TP = TK16 * 16;
+  constexpr int LD = Tile<DH>::LD, TP = TK16 * 16;
   extern __shared__ __align__(16) uint8_t smem[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem);
-  bf16* sK = sQ + TP * LD;
-  bf16* sV = sK + TP * LD;
-  bf16* sdO = sV + TP * LD;
-  float* sL = reinterpret_cast<float*>(sdO + TP * LD);      // lse per query
-  float* sD = sL + TP;                                      // D = rowsum(dO * O) per query
+  const uint32_t uQ = (uint32_t)__cvta_generic_to_shared(smem), uK = uQ + TP * LD * 2, uV = uK + TP * LD * 2,
+                 udO = uV + TP * LD * 2;
+  float* sL = reinterpret_cast<float*>(smem + (size_t)4 * TP * LD * 2);      // lse * log2(e) per query
+  float* sD = sL + TP;                                                       // D = rowsum(dO * O) per query
   const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bf16* base = qkv + (size_t)b * T * 3 * H + h * DH;
   const bf16* ob = out + (size_t)b * T * H + h * DH;
   const bf16* dob = dout + (size_t)b * T * H + h * DH;
-  stage<DH>(sQ, base, 3 * H, T, TP);
-  stage<DH>(sK, base + H, 3 * H, T, TP);
-  stage<DH>(sV, base + 2 * H, 3 * H, T, TP);
-  stage<DH>(sdO, dob, H, T, TP);
-  // D_i and lse_i: 4 lanes per query row
-  for (int r = (threadIdx.x >> 2); r < TP; r += (blockDim.x >> 2)) {
-    float d = 0.f;
-    if (r < T)
-      for (int c = (threadIdx.x & 3) * 2; c < DH; c += 8) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dob + (size_t)r * H + c));
-        const float2 o2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + (size_t)r * H + c));
-        d += a.x * o2.x + a.y * o2.y;
+  constexpr float l2e = 1.4426950408889634f;
+  EGOT2_PDL_ENTER();
+  stage<DH, TK16>(uQ, base, 3 * H, T);
+  stage<DH, TK16>(uK, base + H, 3 * H, T);
+  stage<DH, TK16>(uV, base + 2 * H, 3 * H, T);
+  stage<DH, TK16>(udO, dob, H, T);
+  // D_i and lse_i while the copies are in flight: 4 lanes per query row, 16 B loads
+  {
+    constexpr int RPI = TK16 * 8;              // rows per pass (4 lanes each)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = (threadIdx.x >> 2) + i * RPI;
+      float d = 0.f;
+      if (r < T) {
+#pragma unroll
+        for (int c = (threadIdx.x & 3) * 8; c < DH; c += 32) {
+          const uint4 a4 = *reinterpret_cast<const uint4*>(dob + (size_t)r * H + c);
+          const uint4 o4 = *reinterpret_cast<const uint4*>(ob + (size_t)r * H + c);
+          const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, ow[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            d = fmaf(__uint_as_float(aw[k] << 16), __uint_as_float(ow[k] << 16), d);
+            d = fmaf(__uint_as_float(aw[k] & 0xffff0000u), __uint_as_float(ow[k] & 0xffff0000u), d);
+          }
+        }
       }
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    d += __shfl_xor_sync(0xffffffffu, d, 2);
-    if ((threadIdx.x & 3) == 0) { sD[r] = d; sL[r] = r < T ? lse[(size_t)bh * T + r] : 0.f; }
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      if ((threadIdx.x & 3) == 0) { sD[r] = d; sL[r] = r < T ? lse[(size_t)bh * T + r] * l2e : 0.f; }
+    }
   }
+  stage_wait();
   __syncthreads();
   const int r0 = warp * 16;
   if (r0 >= T) return;
   const float scn = rsqrtf((float)DH);
-  const float sc2 = scn * 1.4426950408889634f, l2e = 1.4426950408889634f;
+  const float sc2 = scn * l2e;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  const bool bitmode = p_drop == 0.5f;
   constexpr int NW = (TK16 + 1) / 2;                       // 32-key (or 32-query) blocks of the clip
   const int ra = r0 + (lane >> 2), rb = ra + 8;            // this thread's two tile rows
-  const uint32_t uQ = (uint32_t)__cvta_generic_to_shared(sQ), uK = (uint32_t)__cvta_generic_to_shared(sK);
-  const uint32_t uV = (uint32_t)__cvta_generic_to_shared(sV), udO = (uint32_t)__cvta_generic_to_shared(sdO);
   bf16* dq = dqkv + (size_t)b * T * 3 * H + h * DH;
 
   // ---------------- pass 1: rows = queries -> dQ   (streamed over 16-key blocks: nothing T-wide stays in registers)
@@ -269,11 +305,11 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
     uint32_t a1[Tile<DH>::KS][4], a2[Tile<DH>::KS][4];
     load_a<DH>(uQ, r0, a1);
     load_a<DH>(udO, r0, a2);
-    const float la = sL[ra] * l2e, lb = sL[rb] * l2e, da = sD[ra], db = sD[rb];
+    const float la = sL[ra], lb = sL[rb], da = sD[ra], db = sD[rb];
     uint32_t wa[NW], wb[NW];
-    if (bitmode) {
-      mask_words<NW>(drop_key, (uint64_t)bh * T + ra, (T + 31) >> 5, wa);
-      mask_words<NW>(drop_key, (uint64_t)bh * T + rb, (T + 31) >> 5, wb);
+    if (MODE == 1) {
+      mask_words<NW>(drop_key, (uint64_t)bh * T + ra, (T + 31) >> 5, 2 * (lane & 3), wa);
+      mask_words<NW>(drop_key, (uint64_t)bh * T + rb, (T + 31) >> 5, 2 * (lane & 3), wb);
     }
     float o[Tile<DH>::ND][4];
 #pragma unroll
@@ -287,17 +323,20 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
       uint32_t ds[4];
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
-        const int c = kb * 16 + h2 * 8 + 2 * (lane & 3);
-        float p0 = c < T ? exp2f(s[h2][0] * sc2 - la) : 0.f, p1 = c + 1 < T ? exp2f(s[h2][1] * sc2 - la) : 0.f;
-        float p2 = c < T ? exp2f(s[h2][2] * sc2 - lb) : 0.f, p3 = c + 1 < T ? exp2f(s[h2][3] * sc2 - lb) : 0.f;
+        float p0 = ex2(fmaf(s[h2][0], sc2, -la)), p1 = ex2(fmaf(s[h2][1], sc2, -la));
+        float p2 = ex2(fmaf(s[h2][2], sc2, -lb)), p3 = ex2(fmaf(s[h2][3], sc2, -lb));
+        if (kb * 16 + 16 > T) {                // warp-uniform: padded keys only exist in the last block
+          const int c = kb * 16 + h2 * 8 + 2 * (lane & 3);
+          if (c >= T) { p0 = 0.f; p2 = 0.f; }
+          if (c + 1 >= T) { p1 = 0.f; p3 = 0.f; }
+        }
         float g0 = dp[h2][0], g1 = dp[h2][1], g2 = dp[h2][2], g3 = dp[h2][3];
-        if (bitmode) {
-          const int bit = (kb & 1) * 16 + h2 * 8 + 2 * (lane & 3);
-          g0 = (wa[kb >> 1] >> bit) & 1u ? g0 * 2.f : 0.f;
-          g1 = (wa[kb >> 1] >> (bit + 1)) & 1u ? g1 * 2.f : 0.f;
-          g2 = (wb[kb >> 1] >> bit) & 1u ? g2 * 2.f : 0.f;
-          g3 = (wb[kb >> 1] >> (bit + 1)) & 1u ? g3 * 2.f : 0.f;
-        } else if (p_drop > 0.f) {
+        if (MODE == 1) {
+          const uint32_t m0 = wa[kb >> 1] >> ((kb & 1) * 16 + h2 * 8), m1 = wb[kb >> 1] >> ((kb & 1) * 16 + h2 * 8);
+          g0 = (m0 & 1u) ? g0 + g0 : 0.f; g1 = (m0 & 2u) ? g1 + g1 : 0.f;
+          g2 = (m1 & 1u) ? g2 + g2 : 0.f; g3 = (m1 & 2u) ? g3 + g3 : 0.f;
+        } else if (MODE == 2) {
+          const int c = kb * 16 + h2 * 8 + 2 * (lane & 3);
           g0 *= attn_drop_scale(drop_key, (uint64_t)bh * T + ra, T, c, p_drop, inv_keep);
           g1 *= attn_drop_scale(drop_key, (uint64_t)bh * T + ra, T, c + 1, p_drop, inv_keep);
           g2 *= attn_drop_scale(drop_key, (uint64_t)bh * T + rb, T, c, p_drop, inv_keep);
@@ -323,7 +362,7 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
     // p == 0.5: the mask word of (query c, this warp's 32-key block) serves all 16 key rows of the warp: lane L hashes
     // the words of queries L, L+32, ... once and every element fetches its word with a shuffle
     uint32_t wq[NW];
-    if (bitmode) {
+    if (MODE == 1) {
 #pragma unroll
       for (int j = 0; j < NW; ++j) {
         const int qy = lane + 32 * j;
@@ -343,17 +382,22 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
         const int c = kb * 16 + h2 * 8 + 2 * (lane & 3);
-        const float l0 = sL[c] * l2e, l1 = sL[c + 1] * l2e, d0 = sD[c], d1 = sD[c + 1];
-        float p0 = c < T ? exp2f(s[h2][0] * sc2 - l0) : 0.f, p1 = c + 1 < T ? exp2f(s[h2][1] * sc2 - l1) : 0.f;
-        float p2 = c < T ? exp2f(s[h2][2] * sc2 - l0) : 0.f, p3 = c + 1 < T ? exp2f(s[h2][3] * sc2 - l1) : 0.f;
+        const float2 l01 = *reinterpret_cast<const float2*>(sL + c), d01 = *reinterpret_cast<const float2*>(sD + c);
+        float p0 = ex2(fmaf(s[h2][0], sc2, -l01.x)), p1 = ex2(fmaf(s[h2][1], sc2, -l01.y));
+        float p2 = ex2(fmaf(s[h2][2], sc2, -l01.x)), p3 = ex2(fmaf(s[h2][3], sc2, -l01.y));
+        if (kb * 16 + 16 > T) {                // warp-uniform: padded queries only exist in the last block
+          if (c >= T) { p0 = 0.f; p2 = 0.f; }
+          if (c + 1 >= T) { p1 = 0.f; p3 = 0.f; }
+        }
         float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
-        if (bitmode) {
-          const uint32_t u0 = __shfl_sync(0xffffffffu, wq[kb >> 1], c & 31), u1 = __shfl_sync(0xffffffffu, wq[kb >> 1], (c + 1) & 31);
-          m0 = (u0 >> (ra & 31)) & 1u ? 2.f : 0.f;
-          m1 = (u1 >> (ra & 31)) & 1u ? 2.f : 0.f;
-          m2 = (u0 >> (rb & 31)) & 1u ? 2.f : 0.f;
-          m3 = (u1 >> (rb & 31)) & 1u ? 2.f : 0.f;
-        } else if (p_drop > 0.f) {
+        if (MODE == 1) {
+          const uint32_t u0 = __shfl_sync(0xffffffffu, wq[kb >> 1], c & 31) >> (ra & 31);   // bit 0: key ra, bit 8: key rb
+          const uint32_t u1 = __shfl_sync(0xffffffffu, wq[kb >> 1], (c + 1) & 31) >> (ra & 31);
+          m0 = (u0 & 1u) ? 2.f : 0.f;
+          m1 = (u1 & 1u) ? 2.f : 0.f;
+          m2 = (u0 & 0x100u) ? 2.f : 0.f;
+          m3 = (u1 & 0x100u) ? 2.f : 0.f;
+        } else if (MODE == 2) {
           m0 = attn_drop_scale(drop_key, (uint64_t)bh * T + c, T, ra, p_drop, inv_keep);
           m1 = attn_drop_scale(drop_key, (uint64_t)bh * T + c + 1, T, ra, p_drop, inv_keep);
           m2 = attn_drop_scale(drop_key, (uint64_t)bh * T + c, T, rb, p_drop, inv_keep);
@@ -361,8 +405,8 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
         }
         pf[h2 * 2] = pack_bf16(p0 * m0, p1 * m1);
         pf[h2 * 2 + 1] = pack_bf16(p2 * m2, p3 * m3);
-        ds[h2 * 2] = pack_bf16(p0 * (dp[h2][0] * m0 - d0), p1 * (dp[h2][1] * m1 - d1));
-        ds[h2 * 2 + 1] = pack_bf16(p2 * (dp[h2][2] * m2 - d0), p3 * (dp[h2][3] * m3 - d1));
+        ds[h2 * 2] = pack_bf16(p0 * fmaf(dp[h2][0], m0, -d01.x), p1 * fmaf(dp[h2][1], m1, -d01.y));
+        ds[h2 * 2 + 1] = pack_bf16(p2 * fmaf(dp[h2][2], m2, -d01.x), p3 * fmaf(dp[h2][3], m3, -d01.y));
       }
       gemm_pv_kb<DH>(ov, pf, udO, kb);
       gemm_pv_kb<DH>(ok, ds, uQ, kb);
@@ -382,14 +426,20 @@ __global__ void __launch_bounds__(TK16 * 32) attn_mma_bwd_kernel(int T, int H, i
   }
 }
 
+inline int drop_mode(float p) { return p <= 0.f ? 0 : (p == 0.5f ? 1 : 2); }
+
 template <int DH, int TK16>
 int launch_fwd(int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p, uint64_t key, cudaStream_t st) {
   constexpr size_t smem = (size_t)3 * TK16 * 16 * Tile<DH>::LD * 2;
-  auto kern = attn_mma_fwd_kernel<DH, TK16>;
+  typedef void (*Kern)(int, int, int, const bf16*, bf16*, float*, float, uint64_t);
+  static const Kern kerns[3] = {attn_mma_fwd_kernel<DH, TK16, 0>, attn_mma_fwd_kernel<DH, TK16, 1>, attn_mma_fwd_kernel<DH, TK16, 2>};
   static bool set = false;
-  if (!set) { EGOT2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+  if (!set) {
+    for (int i = 0; i < 3; ++i) EGOT2_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = true;
+  }
   ProfScope prof(st, "attn_mma_fwd<dh%d,tk%d> B%d T%d H%d", DH, TK16 * 16, B, T, H);
-  kern<<<B * heads, TK16 * 32, smem, st>>>(T, H, heads, (const bf16*)qkv, (bf16*)out, lse, p, key);
+  launch(kerns[drop_mode(p)], dim3(B * heads), dim3(TK16 * 32), smem, st, T, H, heads, (const bf16*)qkv, (bf16*)out, lse, p, key);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -397,12 +447,16 @@ template <int DH, int TK16>
 int launch_bwd(int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse, const void* dout,
                void* dqkv, float p, uint64_t key, cudaStream_t st) {
   constexpr size_t smem = (size_t)4 * TK16 * 16 * Tile<DH>::LD * 2 + 2 * TK16 * 16 * 4;
-  auto kern = attn_mma_bwd_kernel<DH, TK16>;
+  typedef void (*Kern)(int, int, int, const bf16*, const bf16*, const float*, const bf16*, bf16*, float, uint64_t);
+  static const Kern kerns[3] = {attn_mma_bwd_kernel<DH, TK16, 0>, attn_mma_bwd_kernel<DH, TK16, 1>, attn_mma_bwd_kernel<DH, TK16, 2>};
   static bool set = false;
-  if (!set) { EGOT2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+  if (!set) {
+    for (int i = 0; i < 3; ++i) EGOT2_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = true;
+  }
   ProfScope prof(st, "attn_mma_bwd<dh%d,tk%d> B%d T%d H%d", DH, TK16 * 16, B, T, H);
-  kern<<<B * heads, TK16 * 32, smem, st>>>(T, H, heads, (const bf16*)qkv, (const bf16*)out, lse, (const bf16*)dout,
-                                          (bf16*)dqkv, p, key);
+  launch(kerns[drop_mode(p)], dim3(B * heads), dim3(TK16 * 32), smem, st, T, H, heads, (const bf16*)qkv, (const bf16*)out, lse,
+         (const bf16*)dout, (bf16*)dqkv, p, key);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

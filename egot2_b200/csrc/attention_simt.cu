@@ -41,6 +41,7 @@ template <typename T, int DH>
 __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(int Tn, int H, int heads, const T* __restrict__ qkv,
                                                            T* __restrict__ out, float* __restrict__ lse, float p_drop,
                                                            uint64_t drop_key) {
+  EGOT2_PDL_ENTER();
   constexpr int NC = Cols<DH>::N;
   constexpr int KB = Cfg<DH>::KB, RPW = Cfg<DH>::RPW, RB = Cfg<DH>::RB;
   __shared__ float Ks[KB][DH + 1];
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_dq_kernel(int Tn, int H, int
                                                               const T* __restrict__ out, const float* __restrict__ lse,
                                                               const T* __restrict__ dout, T* __restrict__ dqkv,
                                                               float* __restrict__ Dvec, float p_drop, uint64_t drop_key) {
+  EGOT2_PDL_ENTER();
   constexpr int NC = Cols<DH>::N;
   constexpr int KB = Cfg<DH>::KB, RPW = Cfg<DH>::RPW, RB = Cfg<DH>::RB;
   __shared__ float Ks[KB][DH + 1];
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_dkv_kernel(int Tn, int H, in
                                                                const float* __restrict__ lse, const T* __restrict__ dout,
                                                                T* __restrict__ dqkv, const float* __restrict__ Dvec,
                                                                float p_drop, uint64_t drop_key) {
+  EGOT2_PDL_ENTER();
   constexpr int NC = Cols<DH>::N;
   constexpr int KB = Cfg<DH>::KB, RPW = Cfg<DH>::RPW, RB = Cfg<DH>::RB;
   __shared__ float Qs[KB][DH + 1];     // streamed: scaled queries
@@ -340,7 +343,7 @@ int fwd_launch(int B, int Tn, int H, int heads, const void* qkv, void* out, floa
   constexpr int RB = Cfg<DH>::RB;
   dim3 grid(B * heads, (Tn + RB - 1) / RB);
   ProfScope prof(st, "attn_simt_fwd<dh%d> B%d T%d H%d", DH, B, Tn, H);
-  attn_fwd_kernel<T, DH><<<grid, NW * 32, 0, st>>>(Tn, H, heads, (const T*)qkv, (T*)out, lse, p, key);
+  launch(attn_fwd_kernel<T, DH>, dim3(grid), dim3(NW * 32), 0, st, Tn, H, heads, (const T*)qkv, (T*)out, lse, p, key);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -350,10 +353,10 @@ int bwd_launch(int B, int Tn, int H, int heads, const void* qkv, const void* out
   constexpr int RB = Cfg<DH>::RB;
   dim3 grid(B * heads, (Tn + RB - 1) / RB);
   ProfScope prof(st, "attn_simt_bwd<dh%d> B%d T%d H%d (2 kernels)", DH, B, Tn, H);
-  attn_bwd_dq_kernel<T, DH><<<grid, NW * 32, 0, st>>>(Tn, H, heads, (const T*)qkv, (const T*)out, lse, (const T*)dout,
+  launch(attn_bwd_dq_kernel<T, DH>, dim3(grid), dim3(NW * 32), 0, st, Tn, H, heads, (const T*)qkv, (const T*)out, lse, (const T*)dout,
                                                       (T*)dqkv, Dvec, p, key);
   EGOT2_LAUNCH_CHECK();
-  attn_bwd_dkv_kernel<T, DH><<<grid, NW * 32, 0, st>>>(Tn, H, heads, (const T*)qkv, lse, (const T*)dout, (T*)dqkv, Dvec,
+  launch(attn_bwd_dkv_kernel<T, DH>, dim3(grid), dim3(NW * 32), 0, st, Tn, H, heads, (const T*)qkv, lse, (const T*)dout, (T*)dqkv, Dvec,
                                                        p, key);
   EGOT2_LAUNCH_CHECK();
   return 0;

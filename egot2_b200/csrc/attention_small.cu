@@ -20,6 +20,7 @@ constexpr int MAXK = 1024;          // keys per row (scores live in shared memor
 
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32) small_attn_fwd_kernel(const SmallAttnArgs a) {
+  EGOT2_PDL_ENTER();
   __shared__ float sc[WARPS][MAXK];
   __shared__ float sq[WARPS][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(WARPS * 32) small_attn_fwd_kernel(const SmallA
 // dq (rows*S, ldq) / dk, dv (kv rows, ldkv): fp32, ACCUMULATED with atomics (several queries / heads / rows share keys)
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32) small_attn_bwd_kernel(const SmallAttnArgs a) {
+  EGOT2_PDL_ENTER();
   __shared__ float sp[WARPS][MAXK];      // raw probabilities, then ds
   __shared__ float spd[WARPS][MAXK];     // dropped probabilities (what multiplied V)
   __shared__ float sq[WARPS][128];
@@ -156,8 +158,8 @@ int small_attn_fwd(const SmallAttnArgs& a, cudaStream_t st) {
   if (total == 0) return 0;
   ProfScope prof(st, "small_attn_fwd rows%d S%d M%d H%d", a.rows, a.S, a.M, a.H);
   const int grid = (int)((total + WARPS - 1) / WARPS);
-  if (a.dtype == EGOT2_F32) small_attn_fwd_kernel<float><<<grid, WARPS * 32, 0, st>>>(a);
-  else small_attn_fwd_kernel<bf16><<<grid, WARPS * 32, 0, st>>>(a);
+  if (a.dtype == EGOT2_F32) launch(small_attn_fwd_kernel<float>, dim3(grid), dim3(WARPS * 32), 0, st, a);
+  else launch(small_attn_fwd_kernel<bf16>, dim3(grid), dim3(WARPS * 32), 0, st, a);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -169,8 +171,8 @@ int small_attn_bwd(const SmallAttnArgs& a, cudaStream_t st) {
   if (total == 0) return 0;
   ProfScope prof(st, "small_attn_bwd rows%d S%d M%d H%d", a.rows, a.S, a.M, a.H);
   const int grid = (int)((total + WARPS - 1) / WARPS);
-  if (a.dtype == EGOT2_F32) small_attn_bwd_kernel<float><<<grid, WARPS * 32, 0, st>>>(a);
-  else small_attn_bwd_kernel<bf16><<<grid, WARPS * 32, 0, st>>>(a);
+  if (a.dtype == EGOT2_F32) launch(small_attn_bwd_kernel<float>, dim3(grid), dim3(WARPS * 32), 0, st, a);
+  else launch(small_attn_bwd_kernel<bf16>, dim3(grid), dim3(WARPS * 32), 0, st, a);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

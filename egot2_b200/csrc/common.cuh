@@ -44,6 +44,29 @@ extern unsigned long long g_launch_count;
 
 int sm_count();
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the library starts with pdl_launch_dependents() - the NEXT kernel on the stream may become resident
+// and run its prologue (barrier init, TMEM alloc, tensormap prefetch) while this one is still running - and executes
+// pdl_wait() before its first global-memory access: griddepcontrol.wait returns only when every earlier grid has
+// completed and flushed, so data hazards are exactly those of plain stream order.  Because the chain is only
+// transitive when EVERY kernel waits, launch() (which sets the stream-serialization attribute) must only be used with
+// kernels that call pdl_wait(); nothing before the wait may read memory another kernel of the step writes.
+// EGOT2_PDL=0 launches without the attribute (griddepcontrol.* are then no-ops).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define EGOT2_PDL_ENTER() do { ::egot2::pdl_launch_dependents(); ::egot2::pdl_wait(); } while (0)
+bool pdl_enabled();
+template <typename... Params, typename... Args>
+inline void launch(void (*kern)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);      // errors surface through EGOT2_LAUNCH_CHECK()
+}
+
 // ---------------------------------------------------------------- per-launcher CUDA-event timing (egot2_prof_*)
 // When profiling is enabled (egot2_prof_enable(1); eager launches only, never during graph capture) every launcher
 // brackets the kernels it enqueues with a pair of CUDA events recorded on the launch stream.

@@ -70,6 +70,7 @@ int wgrad2(int dt, int rows, int n_out, int k_in, const void* dY, int ld_dy, con
 template <typename T>
 __global__ void prompt_embed_fwd_kernel(int rows, int S, int H, const int64_t* __restrict__ tok, const float* __restrict__ emb,
                                         const float* __restrict__ pe, float p, uint64_t key, T* __restrict__ y) {
+  EGOT2_PDL_ENTER();
   const int r = blockIdx.x, s = r % S;
   const float sc = sqrtf((float)H), inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const float* e = emb + (size_t)tok[r] * H;
@@ -82,6 +83,7 @@ __global__ void prompt_embed_fwd_kernel(int rows, int S, int H, const int64_t* _
 template <typename T>
 __global__ void prompt_embed_bwd_kernel(int rows, int S, int H, const int64_t* __restrict__ tok, const T* __restrict__ dy,
                                         float p, uint64_t key, float* __restrict__ demb) {
+  EGOT2_PDL_ENTER();
   const int r = blockIdx.x;
   const float sc = sqrtf((float)H), inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   float* e = demb + (size_t)tok[r] * H;
@@ -262,8 +264,8 @@ extern "C" int egot2_prompt_embed_fwd(int32_t dtype, int32_t rows, int32_t S, in
   const float p = training ? p_drop : 0.f;
   const uint64_t key = site_key(seed, SITE_PROMPT, 0);
   ProfScope prof(st, "prompt_embed_fwd rows%d S%d H%d", rows, S, H);
-  if (dtype == EGOT2_F32) prompt_embed_fwd_kernel<float><<<rows * S, 128, 0, st>>>(rows, S, H, tokens, embedding, pe, p, key, (float*)y);
-  else prompt_embed_fwd_kernel<bf16><<<rows * S, 128, 0, st>>>(rows, S, H, tokens, embedding, pe, p, key, (bf16*)y);
+  if (dtype == EGOT2_F32) launch(prompt_embed_fwd_kernel<float>, dim3(rows * S), dim3(128), 0, st, rows, S, H, tokens, embedding, pe, p, key, (float*)y);
+  else launch(prompt_embed_fwd_kernel<bf16>, dim3(rows * S), dim3(128), 0, st, rows, S, H, tokens, embedding, pe, p, key, (bf16*)y);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -276,8 +278,8 @@ extern "C" int egot2_prompt_embed_bwd(int32_t dtype, int32_t rows, int32_t S, in
   const float p = training ? p_drop : 0.f;
   const uint64_t key = site_key(seed, SITE_PROMPT, 0);
   ProfScope prof(st, "prompt_embed_bwd rows%d S%d H%d", rows, S, H);
-  if (dtype == EGOT2_F32) prompt_embed_bwd_kernel<float><<<rows * S, 128, 0, st>>>(rows, S, H, tokens, (const float*)dy, p, key, d_embedding);
-  else prompt_embed_bwd_kernel<bf16><<<rows * S, 128, 0, st>>>(rows, S, H, tokens, (const bf16*)dy, p, key, d_embedding);
+  if (dtype == EGOT2_F32) launch(prompt_embed_bwd_kernel<float>, dim3(rows * S), dim3(128), 0, st, rows, S, H, tokens, (const float*)dy, p, key, d_embedding);
+  else launch(prompt_embed_bwd_kernel<bf16>, dim3(rows * S), dim3(128), 0, st, rows, S, H, tokens, (const bf16*)dy, p, key, d_embedding);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

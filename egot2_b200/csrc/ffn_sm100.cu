@@ -118,11 +118,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   // these are conflict-free broadcasts instead of a chain of dependent global loads on the per-chunk critical path
   float* sVec = red + 512;                 // b2[128], ln_g[128], ln_b[128]   (red: sum[2][128], sumsq[2][128])
   float* sB1 = sVec + 384;                 // b1[FF]
-  if (!BWD) {
-    const float s1 = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;      // dropout scale folded into the bias (see epilogue)
-    for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i] * s1;
-    for (int i = threadIdx.x; i < 128; i += NTHREADS) { sVec[i] = a.b2[i]; sVec[128 + i] = a.ln_g[i]; sVec[256 + i] = a.ln_b[i]; }
-  }
+  pdl_launch_dependents();       // the next kernel may become resident and run its prologue under this one
   const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -152,6 +148,12 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
+  pdl_wait();                    // first global-memory access of the kernel is below
+  if (!BWD) {
+    const float s1 = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;      // dropout scale folded into the bias (see epilogue)
+    for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i] * s1;
+    for (int i = threadIdx.x; i < 128; i += NTHREADS) { sVec[i] = a.b2[i]; sVec[128 + i] = a.ln_g[i]; sVec[256 + i] = a.ln_b[i]; }
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                         // both CTAs' barriers are initialised before anything targets them remotely
@@ -561,7 +563,7 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
   {
     ProfScope prof(st, bwd ? "ffn_bwd_dx_sm100 M%d H128 FF%d" : "ffn_fwd_sm100 M%d H128 FF%d", M, FF);
     const int tiles = (M + BM - 1) / BM, grid = (tiles + 1) / 2 * 2;      // whole CTA pairs
-    kernels[ki]<<<grid, NTHREADS, smem, st>>>(tx, tw1, tw2, thid, ty2, tout, a);
+    launch(kernels[ki], dim3(grid), dim3(NTHREADS), smem, st, tx, tw1, tw2, thid, ty2, tout, a);
     EGOT2_LAUNCH_CHECK();
   }
 #ifdef EGOT2_FFN_TRACE

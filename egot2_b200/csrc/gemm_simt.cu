@@ -21,6 +21,7 @@ __device__ __forceinline__ long long remap(int r, int rpg, int gstride) {
 
 template <typename TI, typename TO, int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs a) {
+  EGOT2_PDL_ENTER();
   constexpr int NT = 256;
   static_assert((BM / TM) * (BN / TN) == NT, "thread tiling");
   __shared__ float As[BK][BM + 4];
@@ -139,10 +140,10 @@ int launch(const GemmArgs& a, cudaStream_t st) {
                  a.trans_b, a.split_k);
   if (small) {
     dim3 grid((a.N + 63) / 64, (a.M + 63) / 64, a.split_k);
-    gemm_simt_kernel<TI, TO, 64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(a);
+    launch(gemm_simt_kernel<TI, TO, 64, 64, 16, 4, 4>, dim3(grid), dim3(256), 0, st, a);
   } else {
     dim3 grid((a.N + 127) / 128, (a.M + 127) / 128, a.split_k);
-    gemm_simt_kernel<TI, TO, 128, 128, 16, 8, 8><<<grid, 256, 0, st>>>(a);
+    launch(gemm_simt_kernel<TI, TO, 128, 128, 16, 8, 8>, dim3(grid), dim3(256), 0, st, a);
   }
   EGOT2_LAUNCH_CHECK();
   return 0;

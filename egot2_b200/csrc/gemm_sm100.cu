@@ -112,6 +112,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int kb_end = min(k_blocks_total, kb_begin + k_blocks_per_split);
   const int nkb = kb_end - kb_begin;
 
+  pdl_launch_dependents();      // the next kernel's prologue may overlap this one's main loop
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -120,6 +121,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  pdl_wait();                   // everything above touched only kernel parameters, shared memory and TMEM
   float* sbias = reinterpret_cast<float*>(smem_raw + (bias_off - smem_u32(smem_raw)));
   if (warp >= 2) {
     const bool has_bias = e.bias != nullptr && blockIdx.z == 0;
@@ -371,7 +373,7 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, splits);
   ProfScope prof(st, "gemm_sm100<bn%d,%s%s,%s> M%d N%d K%d sk%d%s", BN, A_MN ? "mn" : "k", B_MN ? "mn" : "k",
                  sizeof(TO) == 4 ? "f32" : "bf16", a.M, a.N, a.K, splits, a.mask ? " +mask" : (a.residual ? " +res" : ""));
-  kern<<<grid, NTHREADS, smem, st>>>(ma, mb, e, kb_total, kb_per);
+  ::egot2::launch(kern, grid, dim3(NTHREADS), smem, st, ma, mb, e, kb_total, kb_per);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

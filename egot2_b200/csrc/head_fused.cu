@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(NT) head_fwd_kernel(int T, int H, int n_out, c
                                                       float p_drop, uint64_t drop_key, float* __restrict__ pooled,
                                                       float* __restrict__ stat, TT* __restrict__ g_out,
                                                       float* __restrict__ logits) {
+  EGOT2_PDL_ENTER();
   extern __shared__ float sm[];
   float* ps = sm;            // pooled (H)
   float* gs = sm + H;        // LN output (H)
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(int T, int H, int n_out, c
                                                       TT* __restrict__ dx, float* __restrict__ d_ln_g,
                                                       float* __restrict__ d_ln_b, float* __restrict__ dW,
                                                       float* __restrict__ db) {
+  EGOT2_PDL_ENTER();
   extern __shared__ float sm[];
   float* dgs = sm;           // d(LN output) (H)
   float* dps = sm + H;       // d(pooled) (H)
@@ -133,10 +135,10 @@ int head_fused_fwd(const egot2_head_desc& d, const egot2_head_in& in, const egot
   const size_t smem = 2 * (size_t)d.H * sizeof(float);
   ProfScope prof(st, "head_fwd B%d T%d H%d n%d", d.B, d.T, d.H, d.n_out);
   if (d.dtype == EGOT2_F32)
-    head_fwd_kernel<float><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, (const float*)in.x, in.ln_g, in.ln_b, (const float*)in.w,
+    launch(head_fwd_kernel<float>, dim3(d.B), dim3(NT), smem, st, d.T, d.H, d.n_out, (const float*)in.x, in.ln_g, in.ln_b, (const float*)in.w,
                                                   in.b, d.ln_eps, ph, key, out.pooled, out.stat, (float*)out.g, out.logits);
   else
-    head_fwd_kernel<bf16><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, (const bf16*)in.x, in.ln_g, in.ln_b, (const bf16*)in.w,
+    launch(head_fwd_kernel<bf16>, dim3(d.B), dim3(NT), smem, st, d.T, d.H, d.n_out, (const bf16*)in.x, in.ln_g, in.ln_b, (const bf16*)in.w,
                                                  in.b, d.ln_eps, ph, key, out.pooled, out.stat, (bf16*)out.g, out.logits);
   EGOT2_LAUNCH_CHECK();
   return 0;
@@ -149,10 +151,10 @@ int head_fused_bwd(const egot2_head_desc& d, const egot2_head_in& in, const egot
   const size_t smem = 2 * (size_t)d.H * sizeof(float);
   ProfScope prof(st, "head_bwd B%d T%d H%d n%d", d.B, d.T, d.H, d.n_out);
   if (d.dtype == EGOT2_F32)
-    head_bwd_kernel<float><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, dlogits, saved.pooled, saved.stat, (const float*)saved.g,
+    launch(head_bwd_kernel<float>, dim3(d.B), dim3(NT), smem, st, d.T, d.H, d.n_out, dlogits, saved.pooled, saved.stat, (const float*)saved.g,
                                                   in.ln_g, (const float*)in.w, ph, key, (float*)dx, g.ln_g, g.ln_b, g.w, g.b);
   else
-    head_bwd_kernel<bf16><<<d.B, NT, smem, st>>>(d.T, d.H, d.n_out, dlogits, saved.pooled, saved.stat, (const bf16*)saved.g,
+    launch(head_bwd_kernel<bf16>, dim3(d.B), dim3(NT), smem, st, d.T, d.H, d.n_out, dlogits, saved.pooled, saved.stat, (const bf16*)saved.g,
                                                  in.ln_g, (const bf16*)in.w, ph, key, (bf16*)dx, g.ln_g, g.ln_b, g.w, g.b);
   EGOT2_LAUNCH_CHECK();
   return 0;

@@ -44,6 +44,7 @@ __device__ __forceinline__ void seg_locate(const SegGeom& g, long long seg, long
 __global__ void ce_fwd_kernel(SegGeom g, long long segs, const float* __restrict__ logits,
                               const int64_t* __restrict__ labels, const float* __restrict__ cw,
                               float* __restrict__ seg_loss, int32_t* __restrict__ argmax) {
+  EGOT2_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const long long seg = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (seg >= segs) return;
@@ -75,6 +76,7 @@ __global__ void ce_fwd_kernel(SegGeom g, long long segs, const float* __restrict
 __global__ void ce_bwd_kernel(SegGeom g, long long segs, const float* __restrict__ logits,
                               const int64_t* __restrict__ labels, const float* __restrict__ cw,
                               const float* __restrict__ loss2, float scale, float* __restrict__ dlogits) {
+  EGOT2_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const long long seg = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (seg >= segs) return;
@@ -97,6 +99,7 @@ __global__ void ce_bwd_kernel(SegGeom g, long long segs, const float* __restrict
 // sigmoid + BCE against a one-hot row; one warp per row
 __global__ void bce_fwd_kernel(int rows, int n, const float* __restrict__ logits, const int64_t* __restrict__ labels,
                                float* __restrict__ seg_loss, int32_t* __restrict__ argmax) {
+  EGOT2_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -125,6 +128,7 @@ __global__ void bce_fwd_kernel(int rows, int n, const float* __restrict__ logits
 }
 __global__ void bce_bwd_kernel(long long total, int n, const float* __restrict__ logits,
                                const int64_t* __restrict__ labels, float scale, float* __restrict__ dlogits) {
+  EGOT2_PDL_ENTER();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long row = i / n; const int j = (int)(i % n);
@@ -135,6 +139,7 @@ __global__ void bce_bwd_kernel(long long total, int n, const float* __restrict__
 // loss2[0] = sum(wnll) / (sum(w) / denom_div);  loss2[1] = sum(w) / denom_div
 __global__ void loss_reduce_kernel(long long segs, const float* __restrict__ seg_loss, float denom_div,
                                    float* __restrict__ loss2) {
+  EGOT2_PDL_ENTER();
   __shared__ float s0[32], s1[32];
   float a = 0.f, b = 0.f;
   for (long long i = threadIdx.x; i < segs; i += blockDim.x) { a += seg_loss[2 * i]; b += seg_loss[2 * i + 1]; }
@@ -163,12 +168,12 @@ int loss_fwd(const egot2_head_desc& d, int rows, const float* logits, const int6
   const int grid = (int)((segs * 32 + 255) / 256);
   ProfScope prof(st, "loss_fwd kind%d rows%d n%d (2 kernels)", d.loss, rows, d.n_out);
   if (d.loss == EGOT2_LOSS_BCE_SIGMOID)
-    bce_fwd_kernel<<<grid, 256, 0, st>>>(rows, d.n_out, logits, labels, row_loss, argmax);
+    launch(bce_fwd_kernel, dim3(grid), dim3(256), 0, st, rows, d.n_out, logits, labels, row_loss, argmax);
   else
-    ce_fwd_kernel<<<grid, 256, 0, st>>>(g, segs, logits, labels, class_weight, row_loss, argmax);
+    launch(ce_fwd_kernel, dim3(grid), dim3(256), 0, st, g, segs, logits, labels, class_weight, row_loss, argmax);
   EGOT2_LAUNCH_CHECK();
   const float denom_div = d.loss == EGOT2_LOSS_CE_GROUPS ? (float)(g.sub_rows * g.n_groups) : 1.f;
-  loss_reduce_kernel<<<1, 1024, 0, st>>>(segs, row_loss, denom_div, loss);
+  launch(loss_reduce_kernel, dim3(1), dim3(1024), 0, st, segs, row_loss, denom_div, loss);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -180,10 +185,10 @@ int loss_bwd(const egot2_head_desc& d, int rows, const float* logits, const int6
   ProfScope prof(st, "loss_bwd kind%d rows%d n%d", d.loss, rows, d.n_out);
   if (d.loss == EGOT2_LOSS_BCE_SIGMOID) {
     const long long total = (long long)rows * d.n_out;
-    bce_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(total, d.n_out, logits, labels, dloss_scale, dlogits);
+    launch(bce_bwd_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, total, d.n_out, logits, labels, dloss_scale, dlogits);
   } else {
     const long long segs = (long long)rows * g.sub_rows * g.n_groups;
-    ce_bwd_kernel<<<(int)((segs * 32 + 255) / 256), 256, 0, st>>>(g, segs, logits, labels, class_weight, loss2,
+    launch(ce_bwd_kernel, dim3((int)((segs * 32 + 255) / 256)), dim3(256), 0, st, g, segs, logits, labels, class_weight, loss2,
                                                                    dloss_scale, dlogits);
   }
   EGOT2_LAUNCH_CHECK();

@@ -21,6 +21,7 @@ inline int row_grid(int rows) {
 // ------------------------------------------------------------------ LayerNorm forward
 template <typename TX, typename TY, int NPL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) ln_fwd_kernel(const LayerNormArgs a) {
+  EGOT2_PDL_ENTER();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int H = NPL * 32;
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) ln_fwd_kernel(const LayerNo
 // ------------------------------------------------------------------ LayerNorm backward
 template <typename TX, typename TDY, typename TDX, typename TR, int NPL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) ln_bwd_kernel(const LayerNormBwdArgs a) {
+  EGOT2_PDL_ENTER();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int H = NPL * 32;
   __shared__ float sdg[NPL * 32], sdb[NPL * 32];
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) ln_bwd_kernel(const LayerNo
 template <typename TT>
 __global__ void table_grad_kernel(int B, int T, int H, int clips_per_cta, const TT* __restrict__ dy,
                                   float* __restrict__ dtable, float p_drop, uint64_t drop_key) {
+  EGOT2_PDL_ENTER();
   // CTA (t, chunk): sums its chunk of clips for token t, then one atomic per column
   const int t = blockIdx.x;
   const int b0 = blockIdx.y * clips_per_cta, b1 = min(B, b0 + clips_per_cta);
@@ -129,6 +132,7 @@ __device__ __forceinline__ float2 pair_f32(__nv_bfloat162 v) { return __bfloat16
 template <typename T>
 __global__ void colsum_kernel(int M, int N, const T* __restrict__ x, int ldx, int rpg, int gstride,
                               float* __restrict__ out, int rows_per_cta) {
+  EGOT2_PDL_ENTER();
   // blockDim = (32 column pairs, 8 row lanes): a warp reads 64 consecutive columns of one row per load
   typedef typename Pair<T>::type P2;
   const int n = (blockIdx.x * 32 + threadIdx.x) * 2;
@@ -171,6 +175,7 @@ __global__ void colsum_kernel(int M, int N, const T* __restrict__ x, int ldx, in
 __global__ void __launch_bounds__(256) colsum_bf16_vec_kernel(int M, int N, const bf16* __restrict__ x, int ldx, int rpg,
                                                               int gstride, float* __restrict__ out, int rows_per_cta,
                                                               int lanes_per_row) {
+  EGOT2_PDL_ENTER();
   const int cg = threadIdx.x % lanes_per_row, rl = threadIdx.x / lanes_per_row, nrl = 256 / lanes_per_row;
   const int n = (blockIdx.x * lanes_per_row + cg) * 8;
   const int mbeg = blockIdx.y * rows_per_cta, mend = min(M, mbeg + rows_per_cta);
@@ -215,6 +220,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_vec_kernel(int M, int N, cons
 
 template <typename T>
 __global__ void dropout_kernel(T* x, size_t n, float p, float inv_keep, uint64_t key) {
+  EGOT2_PDL_ENTER();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     x[i] = from_f32<T>(to_f32(x[i]) * drop_scale(key, i, p, inv_keep));
 }
@@ -222,6 +228,7 @@ __global__ void dropout_kernel(T* x, size_t n, float p, float inv_keep, uint64_t
 template <typename TT>
 __global__ void pool_fwd_kernel(int B, int T, int H, int pool, int row_tokens, const TT* __restrict__ x,
                                 float* __restrict__ pooled) {
+  EGOT2_PDL_ENTER();
   if (pool) {
     const int b = blockIdx.x;
     for (int c = threadIdx.x; c < H; c += blockDim.x) {
@@ -239,6 +246,7 @@ __global__ void pool_fwd_kernel(int B, int T, int H, int pool, int row_tokens, c
 template <typename TT>
 __global__ void pool_bwd_kernel(int B, int T, int H, int pool, int row_tokens, const float* __restrict__ dpooled,
                                 TT* __restrict__ dx) {
+  EGOT2_PDL_ENTER();
   const int r = blockIdx.x, b = r / T, t = r % T;     // one CTA per token row of dx
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float v;
@@ -249,6 +257,7 @@ __global__ void pool_bwd_kernel(int B, int T, int H, int pool, int row_tokens, c
 }
 
 __global__ void cast_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, size_t n) {
+  EGOT2_PDL_ENTER();
   size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
   for (; i + 3 < n; i += stride) {
@@ -261,6 +270,7 @@ __global__ void cast_to_bf16_kernel(const float* __restrict__ s, bf16* __restric
     for (size_t j = n & ~(size_t)3; j < n; ++j) d[j] = __float2bfloat16_rn(s[j]);
 }
 __global__ void cast_rows_kernel(const float* __restrict__ s, int rows, int n, bf16* __restrict__ d, int ld) {
+  EGOT2_PDL_ENTER();
   const size_t total = (size_t)rows * ld;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / ld; const int c = (int)(i % ld);
@@ -268,19 +278,23 @@ __global__ void cast_rows_kernel(const float* __restrict__ s, int rows, int n, b
   }
 }
 __global__ void cast_to_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, size_t n) {
+  EGOT2_PDL_ENTER();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     d[i] = __bfloat162float(s[i]);
 }
 __global__ void copy_f32_kernel(const float* __restrict__ s, float* __restrict__ d, size_t n) {
+  EGOT2_PDL_ENTER();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
 }
 __global__ void zero_kernel(float* p, size_t n) {
+  EGOT2_PDL_ENTER();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
                             float bc1, float bc2_sqrt, float gscale) {
+  EGOT2_PDL_ENTER();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float grad = g[i] * gscale;
     const float w = p[i];
@@ -297,6 +311,7 @@ struct SegList { int n; int tokens[EGOT2_MAX_SEG]; int task[EGOT2_MAX_SEG]; };
 
 __global__ void hhi_tok_table_fwd_kernel(const float* __restrict__ task_embed, const float* __restrict__ pe,
                                          SegList s, int H, float* __restrict__ table) {
+  EGOT2_PDL_ENTER();
   // one CTA per token; d restarts at 0 for every task (PositionalEncoding applied per task before the concat)
   int t = blockIdx.x, seg = 0, d = t;
   while (seg < s.n - 1 && d >= s.tokens[seg]) { d -= s.tokens[seg]; ++seg; }
@@ -305,6 +320,7 @@ __global__ void hhi_tok_table_fwd_kernel(const float* __restrict__ task_embed, c
 }
 __global__ void hhi_tok_table_bwd_kernel(const float* __restrict__ dtable, SegList s, int H,
                                          float* __restrict__ d_task_embed) {
+  EGOT2_PDL_ENTER();
   // one CTA per segment: d_task_embed[task] += sum over the segment's tokens
   const int seg = blockIdx.x;
   int off = 0;
@@ -321,6 +337,7 @@ __global__ void hhi_tok_table_bwd_kernel(const float* __restrict__ dtable, SegLi
 template <typename TI, typename TO>
 __global__ void slowfast_pool_kernel(const TI* __restrict__ in, int B, int C, int Tin, int hw, int Tout,
                                      TO* __restrict__ out) {
+  EGOT2_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
   const size_t total = (size_t)B * C * Tout;
@@ -365,6 +382,7 @@ template <int LPR> __device__ __forceinline__ float row_sum(float v) {
 
 template <int HH>
 __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const LayerNormArgs a) {
+  EGOT2_PDL_ENTER();
   typedef LnVec<HH> V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / V::LPR, cl = lane % V::LPR;
@@ -419,6 +437,7 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const LayerNormArgs a) 
 
 template <int HH>
 __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs a) {
+  EGOT2_PDL_ENTER();
   typedef LnVec<HH> V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / V::LPR, cl = lane % V::LPR;
@@ -517,7 +536,7 @@ template <int HH> int ln_fwd_vec_launch(const LayerNormArgs& a, cudaStream_t st)
   const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
   ProfScope prof(st, "ln_fwd rows%d H%d", a.rows, a.H);
-  ln_fwd_vec_kernel<HH><<<grid, 256, 0, st>>>(a);
+  launch(ln_fwd_vec_kernel<HH>, dim3(grid), dim3(256), 0, st, a);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -527,7 +546,7 @@ template <int HH> int ln_bwd_vec_launch(const LayerNormBwdArgs& a, cudaStream_t 
   const int cap = sm_count() * 4;             // every CTA ends with 2H global atomics on the same addresses
   if (grid > cap) grid = cap;
   ProfScope prof(st, "ln_bwd rows%d H%d", a.rows, a.H);
-  ln_bwd_vec_kernel<HH><<<grid, 256, 0, st>>>(a);
+  launch(ln_bwd_vec_kernel<HH>, dim3(grid), dim3(256), 0, st, a);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -539,9 +558,9 @@ inline bool ln_vec_ok(int dtype, int H, const void* p0, const void* p1, const vo
 template <int NPL> int ln_fwd_dispatch(const LayerNormArgs& a, cudaStream_t st) {
   const int grid = row_grid(a.rows);
   ProfScope prof(st, "ln_fwd rows%d H%d", a.rows, a.H);
-  if (a.dtype == EGOT2_F32) ln_fwd_kernel<float, float, NPL><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
-  else if (a.x_is_f32) ln_fwd_kernel<float, bf16, NPL><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
-  else ln_fwd_kernel<bf16, bf16, NPL><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+  if (a.dtype == EGOT2_F32) launch(ln_fwd_kernel<float, float, NPL>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, a);
+  else if (a.x_is_f32) launch(ln_fwd_kernel<float, bf16, NPL>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, a);
+  else launch(ln_fwd_kernel<bf16, bf16, NPL>, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, a);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -551,12 +570,12 @@ template <int NPL> int ln_bwd_dispatch(const LayerNormBwdArgs& a, cudaStream_t s
   const int nt = kWarpsPerCta * 32;
   ProfScope prof(st, "ln_bwd rows%d H%d", a.rows, a.H);
   if (a.dtype == EGOT2_F32) {
-    ln_bwd_kernel<float, float, float, float, NPL><<<grid, nt, 0, st>>>(a);
+    launch(ln_bwd_kernel<float, float, float, float, NPL>, dim3(grid), dim3(nt), 0, st, a);
   } else {
     // bf16 activations; the pooled-vector LN of the head runs with fp32 x / dy / dx
-    if (a.x_is_f32 && a.dy_is_f32 && a.dx_is_f32) ln_bwd_kernel<float, float, float, bf16, NPL><<<grid, nt, 0, st>>>(a);
-    else if (a.x_is_f32 && !a.dy_is_f32 && a.dx_is_f32) ln_bwd_kernel<float, bf16, float, bf16, NPL><<<grid, nt, 0, st>>>(a);
-    else if (!a.x_is_f32 && !a.dy_is_f32 && !a.dx_is_f32) ln_bwd_kernel<bf16, bf16, bf16, bf16, NPL><<<grid, nt, 0, st>>>(a);
+    if (a.x_is_f32 && a.dy_is_f32 && a.dx_is_f32) launch(ln_bwd_kernel<float, float, float, bf16, NPL>, dim3(grid), dim3(nt), 0, st, a);
+    else if (a.x_is_f32 && !a.dy_is_f32 && a.dx_is_f32) launch(ln_bwd_kernel<float, bf16, float, bf16, NPL>, dim3(grid), dim3(nt), 0, st, a);
+    else if (!a.x_is_f32 && !a.dy_is_f32 && !a.dx_is_f32) launch(ln_bwd_kernel<bf16, bf16, bf16, bf16, NPL>, dim3(grid), dim3(nt), 0, st, a);
     else EGOT2_CHECK(false, "layernorm_bwd: unsupported dtype mix");
   }
   EGOT2_LAUNCH_CHECK();
@@ -634,8 +653,8 @@ int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, fl
   const int per = (B + chunks - 1) / chunks;
   dim3 grid(T, (B + per - 1) / per);
   ProfScope prof(st, "table_grad B%d T%d H%d", B, T, H);
-  if (dtype == EGOT2_F32) table_grad_kernel<float><<<grid, nt, 0, st>>>(B, T, H, per, (const float*)dy, dtable, p_drop, drop_key);
-  else table_grad_kernel<bf16><<<grid, nt, 0, st>>>(B, T, H, per, (const bf16*)dy, dtable, p_drop, drop_key);
+  if (dtype == EGOT2_F32) launch(table_grad_kernel<float>, dim3(grid), dim3(nt), 0, st, B, T, H, per, (const float*)dy, dtable, p_drop, drop_key);
+  else launch(table_grad_kernel<bf16>, dim3(grid), dim3(nt), 0, st, B, T, H, per, (const bf16*)dy, dtable, p_drop, drop_key);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -651,7 +670,7 @@ int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int g
     if (rows_per_cta < min_rows) rows_per_cta = min_rows;
     row_blocks = (M + rows_per_cta - 1) / rows_per_cta;
     ProfScope prof(st, "colsum M%d N%d", M, N);
-    colsum_bf16_vec_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>(M, N, (const bf16*)x, ldx, rpg, gstride, out,
+    launch(colsum_bf16_vec_kernel, dim3(col_blocks, row_blocks), dim3(256), 0, st, M, N, (const bf16*)x, ldx, rpg, gstride, out,
                                                                         rows_per_cta, lanes_per_row);
     EGOT2_LAUNCH_CHECK();
     return 0;
@@ -663,8 +682,8 @@ int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int g
   row_blocks = (M + rows_per_cta - 1) / rows_per_cta;
   dim3 grid(col_blocks, row_blocks), block(32, 8);
   ProfScope prof(st, "colsum M%d N%d", M, N);
-  if (dtype == EGOT2_F32) colsum_kernel<float><<<grid, block, 0, st>>>(M, N, (const float*)x, ldx, rpg, gstride, out, rows_per_cta);
-  else colsum_kernel<bf16><<<grid, block, 0, st>>>(M, N, (const bf16*)x, ldx, rpg, gstride, out, rows_per_cta);
+  if (dtype == EGOT2_F32) launch(colsum_kernel<float>, dim3(grid), dim3(block), 0, st, M, N, (const float*)x, ldx, rpg, gstride, out, rows_per_cta);
+  else launch(colsum_kernel<bf16>, dim3(grid), dim3(block), 0, st, M, N, (const bf16*)x, ldx, rpg, gstride, out, rows_per_cta);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -680,8 +699,8 @@ int dropout_inplace(int dtype, void* x, size_t n, float p, uint64_t key, cudaStr
   if (p <= 0.f || n == 0) return 0;
   const float inv_keep = 1.f / (1.f - p);
   ProfScope prof(st, "dropout_inplace n%zu", n);
-  if (dtype == EGOT2_F32) dropout_kernel<float><<<ew_grid(n), 256, 0, st>>>((float*)x, n, p, inv_keep, key);
-  else dropout_kernel<bf16><<<ew_grid(n), 256, 0, st>>>((bf16*)x, n, p, inv_keep, key);
+  if (dtype == EGOT2_F32) launch(dropout_kernel<float>, dim3(ew_grid(n)), dim3(256), 0, st, (float*)x, n, p, inv_keep, key);
+  else launch(dropout_kernel<bf16>, dim3(ew_grid(n)), dim3(256), 0, st, (bf16*)x, n, p, inv_keep, key);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -691,8 +710,8 @@ int pool_fwd(int dtype, int B, int T, int H, int pool, int row_tokens, const voi
   if (rows == 0) return 0;
   const int nt = H < 256 ? ((H + 31) / 32 * 32) : 256;
   ProfScope prof(st, "pool_fwd B%d T%d H%d", B, T, H);
-  if (dtype == EGOT2_F32) pool_fwd_kernel<float><<<rows, nt, 0, st>>>(B, T, H, pool, row_tokens, (const float*)x, pooled);
-  else pool_fwd_kernel<bf16><<<rows, nt, 0, st>>>(B, T, H, pool, row_tokens, (const bf16*)x, pooled);
+  if (dtype == EGOT2_F32) launch(pool_fwd_kernel<float>, dim3(rows), dim3(nt), 0, st, B, T, H, pool, row_tokens, (const float*)x, pooled);
+  else launch(pool_fwd_kernel<bf16>, dim3(rows), dim3(nt), 0, st, B, T, H, pool, row_tokens, (const bf16*)x, pooled);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -701,8 +720,8 @@ int pool_bwd(int dtype, int B, int T, int H, int pool, int row_tokens, const flo
   if (B * T == 0) return 0;
   const int nt = H < 256 ? ((H + 31) / 32 * 32) : 256;
   ProfScope prof(st, "pool_bwd B%d T%d H%d", B, T, H);
-  if (dtype == EGOT2_F32) pool_bwd_kernel<float><<<B * T, nt, 0, st>>>(B, T, H, pool, row_tokens, dpooled, (float*)dx);
-  else pool_bwd_kernel<bf16><<<B * T, nt, 0, st>>>(B, T, H, pool, row_tokens, dpooled, (bf16*)dx);
+  if (dtype == EGOT2_F32) launch(pool_bwd_kernel<float>, dim3(B * T), dim3(nt), 0, st, B, T, H, pool, row_tokens, dpooled, (float*)dx);
+  else launch(pool_bwd_kernel<bf16>, dim3(B * T), dim3(nt), 0, st, B, T, H, pool, row_tokens, dpooled, (bf16*)dx);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -712,9 +731,9 @@ int cast_f32_to(int dtype, const float* src, void* dst, size_t n, cudaStream_t s
   ProfScope prof(st, "cast_f32_to n%zu", n);
   if (dtype == EGOT2_BF16) {
     EGOT2_CHECK(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0), "cast: unaligned buffers");
-    cast_to_bf16_kernel<<<ew_grid(n, 4), 256, 0, st>>>(src, (bf16*)dst, n);
+    launch(cast_to_bf16_kernel, dim3(ew_grid(n, 4)), dim3(256), 0, st, src, (bf16*)dst, n);
   } else {
-    copy_f32_kernel<<<ew_grid(n), 256, 0, st>>>(src, (float*)dst, n);
+    launch(copy_f32_kernel, dim3(ew_grid(n)), dim3(256), 0, st, src, (float*)dst, n);
   }
   EGOT2_LAUNCH_CHECK();
   return 0;
@@ -723,8 +742,8 @@ int cast_f32_to(int dtype, const float* src, void* dst, size_t n, cudaStream_t s
 int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
   ProfScope prof(st, "cast_to_f32 n%zu", n);
-  if (dtype == EGOT2_BF16) cast_to_f32_kernel<<<ew_grid(n), 256, 0, st>>>((const bf16*)src, dst, n);
-  else copy_f32_kernel<<<ew_grid(n), 256, 0, st>>>((const float*)src, dst, n);
+  if (dtype == EGOT2_BF16) launch(cast_to_f32_kernel, dim3(ew_grid(n)), dim3(256), 0, st, (const bf16*)src, dst, n);
+  else launch(copy_f32_kernel, dim3(ew_grid(n)), dim3(256), 0, st, (const float*)src, dst, n);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -732,7 +751,7 @@ int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t s
 int cast_rows_f32_to_bf16(const float* src, int rows, int n, void* dst, int ld, cudaStream_t st) {
   if (rows == 0 || n == 0) return 0;
   ProfScope prof(st, "cast_rows rows%d n%d", rows, n);
-  cast_rows_kernel<<<ew_grid((size_t)rows * ld), 256, 0, st>>>(src, rows, n, (bf16*)dst, ld);
+  launch(cast_rows_kernel, dim3(ew_grid((size_t)rows * ld)), dim3(256), 0, st, src, rows, n, (bf16*)dst, ld);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -753,7 +772,7 @@ extern "C" int egot2_cast_f32_to_bf16(const float* src, void* dst, size_t n, voi
 }
 extern "C" int egot2_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream) {
   if (n == 0) return 0;
-  cast_to_f32_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+  launch(cast_to_f32_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)src, dst, n);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -766,7 +785,7 @@ extern "C" int egot2_adam_step(float* param, const float* grad, float* exp_avg, 
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   ProfScope prof((cudaStream_t)stream, "adam n%zu", n);
-  adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+  launch(adam_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                            weight_decay, bc1, sqrtf(bc2), grad_scale);
   EGOT2_LAUNCH_CHECK();
   return 0;
@@ -783,7 +802,7 @@ extern "C" int egot2_hhi_tok_table_fwd(const float* task_embed, const float* pe,
   }
   if (T == 0) return 0;
   ProfScope prof((cudaStream_t)stream, "hhi_tok_table_fwd T%d H%d", T, H);
-  hhi_tok_table_fwd_kernel<<<T, 128, 0, (cudaStream_t)stream>>>(task_embed, pe, s, H, tok_table);
+  launch(hhi_tok_table_fwd_kernel, dim3(T), dim3(128), 0, (cudaStream_t)stream, task_embed, pe, s, H, tok_table);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -793,7 +812,7 @@ extern "C" int egot2_hhi_tok_table_bwd(const float* d_tok_table, int32_t n_seg, 
   SegList s; s.n = n_seg;
   for (int i = 0; i < n_seg; ++i) { s.tokens[i] = seg_tokens[i]; s.task[i] = seg_task_id[i]; }
   ProfScope prof((cudaStream_t)stream, "hhi_tok_table_bwd H%d", H);
-  hhi_tok_table_bwd_kernel<<<n_seg, 128, 0, (cudaStream_t)stream>>>(d_tok_table, s, H, d_task_embed);
+  launch(hhi_tok_table_bwd_kernel, dim3(n_seg), dim3(128), 0, (cudaStream_t)stream, d_tok_table, s, H, d_task_embed);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -807,11 +826,11 @@ extern "C" int egot2_slowfast_pool_fwd(const void* in, int32_t in_dtype, int32_t
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(st, "slowfast_pool B%d C%d Tin%d hw%d", B, C, Tin, hw);
   if (in_dtype == EGOT2_F32 && out_dtype == EGOT2_F32)
-    slowfast_pool_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, B, C, Tin, hw, Tout, (float*)out);
+    launch(slowfast_pool_kernel<float, float>, dim3(grid), dim3(256), 0, st, (const float*)in, B, C, Tin, hw, Tout, (float*)out);
   else if (in_dtype == EGOT2_F32 && out_dtype == EGOT2_BF16)
-    slowfast_pool_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)in, B, C, Tin, hw, Tout, (bf16*)out);
+    launch(slowfast_pool_kernel<float, bf16>, dim3(grid), dim3(256), 0, st, (const float*)in, B, C, Tin, hw, Tout, (bf16*)out);
   else if (in_dtype == EGOT2_BF16 && out_dtype == EGOT2_BF16)
-    slowfast_pool_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)in, B, C, Tin, hw, Tout, (bf16*)out);
+    launch(slowfast_pool_kernel<bf16, bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)in, B, C, Tin, hw, Tout, (bf16*)out);
   else EGOT2_CHECK(false, "slowfast_pool: unsupported dtypes %d -> %d", in_dtype, out_dtype);
   EGOT2_LAUNCH_CHECK();
   return 0;
