@@ -152,12 +152,12 @@ struct Side {
   cudaEvent_t join = nullptr;
 };
 Side* get_side(int idx) {
-  static Side sides[2];
+  static Side sides[3];
   static int state = 0;      // 0 untried, 1 ok, -1 disabled / failed
   if (state == 0) {
     state = 1;
     if (env_is("EGOT2_STREAMS", "0")) state = -1;
-    for (int i = 0; i < 2 && state == 1; ++i) {
+    for (int i = 0; i < 3 && state == 1; ++i) {
       if (cudaStreamCreateWithFlags(&sides[i].s, cudaStreamNonBlocking) != cudaSuccess) state = -1;
       for (int k = 0; k < 8 && state == 1; ++k)
         if (cudaEventCreateWithFlags(&sides[i].fork[k], cudaEventDisableTiming) != cudaSuccess) state = -1;
@@ -255,6 +255,7 @@ extern "C" size_t egot2_embed_workspace_bytes(const egot2_embed_desc* d, int bac
     }
     n += align_up(mx * dtype_size(d->dtype));
   }
+  if (backward) n += align_up((size_t)d->B * d->T * d->H * dtype_size(d->dtype));   // LN-backward output (dx stays intact for the table gradient)
   return n;
 }
 
@@ -338,20 +339,33 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   Carver ws(workspace, ws_bytes);
   void* cast_buf = nullptr;
   if (d->feat_dtype != d->dtype) {
-    cast_buf = ws.take(egot2_embed_workspace_bytes(d, 1) - 256);
-    EGOT2_CHECK(ws.ok(), "embed_bwd: workspace too small (%zu < %zu)", ws_bytes, ws.off);
+    size_t mx = 0;
+    for (int k = 0; k < d->n_seg; ++k) {
+      const size_t e = (size_t)d->B * d->seg_tokens[k] * d->seg_in_dim[k];
+      if (e > mx) mx = e;
+    }
+    cast_buf = ws.take(mx * es);
   }
+  void* dz = ws.take(n * es);
+  EGOT2_CHECK(ws.ok(), "embed_bwd: workspace too small (%zu < %zu)", ws_bytes, ws.off);
   // the embedding dropout's mask (applied after the LN + table add in the forward) is regenerated by both consumers of
   // dx instead of a separate in-place pass
   const float pe = (d->training && d->p_embed > 0.f) ? d->p_embed : 0.f;
   const uint64_t ke = site_key(d->seed, SITE_EMBED, 0);
-  if (g->tok_table) EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dx, g->tok_table, pe, ke, st));
+  // token-table gradient (column sums of dx per token / per task): a side stream, beside the LayerNorm backward, which
+  // therefore writes to the workspace instead of in place
+  SegOut so;
+  so.n = d->n_seg;
+  bool want_table = g->tok_table != nullptr;
+  for (int k = 0; k < d->n_seg; ++k) { so.tokens[k] = d->seg_tokens[k]; so.out[k] = g->seg_embed[k]; want_table |= g->seg_embed[k] != nullptr; }
+  Side* tside = want_table ? get_side(2) : nullptr;
+  if (want_table) EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dx, g->tok_table, so, pe, ke, side_fork(st, tside, 0)));
   LayerNormBwdArgs l;
   l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = saved->z; l.stat = saved->stat; l.g = in->ln_g;
-  l.dy = dx; l.dx = dx; l.dg = g->ln_g; l.db = g->ln_b; l.dy_p_drop = pe; l.dy_drop_key = ke;
+  l.dy = dx; l.dx = dz; l.dg = g->ln_g; l.db = g->ln_b; l.dy_p_drop = pe; l.dy_drop_key = ke;
   EGOT2_TRY(layernorm_bwd(l, st));
   if (d->training && d->p_feat > 0.f)
-    EGOT2_TRY(dropout_inplace(d->dtype, dx, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+    EGOT2_TRY(dropout_inplace(d->dtype, dz, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
   const bool par = d->feat_dtype == d->dtype;
   Side* sides[2] = {par ? get_side(0) : nullptr, par ? get_side(1) : nullptr};
   bool used[2] = {false, false};
@@ -360,7 +374,7 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
     if (Dk == 0) continue;
     cudaStream_t sk = st;
     if (k > 0 && sides[(k - 1) & 1]) { sk = side_fork(st, sides[(k - 1) & 1], k & 7); used[(k - 1) & 1] = true; }
-    const char* dzk = (const char*)dx + (size_t)d->seg_offset[k] * d->H * es;
+    const char* dzk = (const char*)dz + (size_t)d->seg_offset[k] * d->H * es;
     if (d->seg_has_proj[k]) {
       const void* feat = in->feat[k];
       if (d->feat_dtype != d->dtype) {
@@ -390,6 +404,7 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
     }
   }
   for (int i = 0; i < 2; ++i) if (used[i]) EGOT2_TRY(side_join(st, sides[i]));
+  if (tside) EGOT2_TRY(side_join(st, tside));
   return 0;
 }
 

@@ -281,9 +281,15 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
     const uint32_t thr = drop_threshold(a.p_drop);
     const uint32_t a1_empty_ldr = mapa(a1_empty, 0), h_full_ldr = mapa(h_full, 0);
+    // backward: the ReLU/dropout gate bits of chunk c+1 are fetched while chunk c is processed (a dependent global
+    // load in front of every chunk's arithmetic was ~1 us of exposed latency per chunk)
+    uint2 gate_next = make_uint2(0u, 0u);
+    if (BWD && row_ok) gate_next = __ldg(a.hmask + (size_t)ch * a.M + m);
     for (int c = 0; c < NC; ++c) {
       const int bsel = c & 1;
       const int hb = c % HB;
+      const uint2 gate_cur = gate_next;
+      if (BWD && row_ok && c + 1 < NC) gate_next = __ldg(a.hmask + (size_t)((c + 1) * 2 + ch) * a.M + m);
       const uint32_t hrow = sHid + hb * TILE + ch * HALF + (uint32_t)r * 128;
       mbar_wait(a1_full + 8 * bsel, (c >> 1) & 1);
       if (threadIdx.x == 64) TR(c, 6);
@@ -305,40 +311,46 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
           const int n0 = c * FC + ch * 64 + h2 * 32;
           const uint64_t idx0 = (uint64_t)m * a.FF + n0;          // multiple of 32: this thread owns one 32-bit mask word
-          const uint32_t mword = DROP == 1 ? drop_bits(a.key_ffn, idx0 >> 5) : 0xFFFFFFFFu;
-          uint32_t gw = 0;
+          // pre-activations (dropout scale folded in: relu(acc + b) / (1-p) == relu(acc/(1-p) + b/(1-p)), sB1 holds the
+          // pre-scaled bias in training), and the word of their sign bits gathered with one funnel shift per element
+          float v[32];
+          uint32_t neg = 0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(sB1 + n0 + j);
-            // relu(acc + b) / (1-p) == relu(acc/(1-p) + b/(1-p)): sB1 holds the pre-scaled bias in training
-            float v0 = fmaxf(fmaf(__uint_as_float(rr[j]), inv_keep, b4.x), 0.f);
-            float v1 = fmaxf(fmaf(__uint_as_float(rr[j + 1]), inv_keep, b4.y), 0.f);
-            float v2 = fmaxf(fmaf(__uint_as_float(rr[j + 2]), inv_keep, b4.z), 0.f);
-            float v3 = fmaxf(fmaf(__uint_as_float(rr[j + 3]), inv_keep, b4.w), 0.f);
-            if constexpr (DROP == 1) {
-              v0 = (mword >> j) & 1u ? v0 : 0.f;
-              v1 = (mword >> (j + 1)) & 1u ? v1 : 0.f;
-              v2 = (mword >> (j + 2)) & 1u ? v2 : 0.f;
-              v3 = (mword >> (j + 3)) & 1u ? v3 : 0.f;
-            } else if constexpr (DROP == 2) {
-              v0 = drop_bits(a.key_ffn, idx0 + j) >= thr ? v0 : 0.f;
-              v1 = drop_bits(a.key_ffn, idx0 + j + 1) >= thr ? v1 : 0.f;
-              v2 = drop_bits(a.key_ffn, idx0 + j + 2) >= thr ? v2 : 0.f;
-              v3 = drop_bits(a.key_ffn, idx0 + j + 3) >= thr ? v3 : 0.f;
-            }
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
-            const uint32_t u0 = *reinterpret_cast<uint32_t*>(&p0), u1 = *reinterpret_cast<uint32_t*>(&p1);
+            v[j] = fmaf(__uint_as_float(rr[j]), inv_keep, b4.x);
+            v[j + 1] = fmaf(__uint_as_float(rr[j + 1]), inv_keep, b4.y);
+            v[j + 2] = fmaf(__uint_as_float(rr[j + 2]), inv_keep, b4.z);
+            v[j + 3] = fmaf(__uint_as_float(rr[j + 3]), inv_keep, b4.w);
+          }
+#pragma unroll
+          for (int j = 31; j >= 0; --j) neg = __funnelshift_l(__float_as_uint(v[j]), neg, 1);     // bit j = sign of v[j]
+          // gate bit = positive pre-activation that survives the dropout, i.e. the saved activation is non-zero (bf16 has
+          // fp32's exponent range, so a positive normal value never rounds to zero; an exactly-zero pre-activation has
+          // its bit set and the value 0, which only matters for the measure-zero relu'(0) convention)
+          uint32_t keep;
+          if constexpr (DROP == 1) {
+            keep = drop_bits(a.key_ffn, idx0 >> 5);
+          } else if constexpr (DROP == 2) {
+            keep = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) keep |= (drop_bits(a.key_ffn, idx0 + j) >= thr ? 1u : 0u) << j;
+          } else {
+            keep = 0xFFFFFFFFu;
+          }
+          uint32_t gw = ~neg & keep;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float v0 = (gw >> j) & 1u ? v[j] : 0.f, v1 = (gw >> (j + 1)) & 1u ? v[j + 1] : 0.f;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1);
+            const uint32_t u0 = *reinterpret_cast<uint32_t*>(&p0);
             packed[h2 * 16 + j / 2] = u0;
-            packed[h2 * 16 + j / 2 + 1] = u1;
-            // gate bit = the SAVED (bf16) activation is non-zero; values are >= 0, so "!= 0" is min(bits, 1)
-            gw += (min(u0 & 0xFFFFu, 1u) << j) + (min(u0 >> 16, 1u) << (j + 1)) + (min(u1 & 0xFFFFu, 1u) << (j + 2)) +
-                  (min(u1 >> 16, 1u) << (j + 3));
           }
           gate[h2] = gw;
         }
         if (a.hmask && row_ok) a.hmask[(size_t)(c * 2 + ch) * a.M + m] = make_uint2(gate[0], gate[1]);
       } else {
-        const uint2 gate = row_ok ? __ldg(a.hmask + (size_t)(c * 2 + ch) * a.M + m) : make_uint2(0u, 0u);
+        const uint2 gate = gate_cur;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const uint32_t (&rr)[32] = h2 ? rr1 : rr0;

@@ -38,12 +38,39 @@ __global__ void __launch_bounds__(NT) head_fwd_kernel(int T, int H, int n_out, c
   __shared__ float red[NT / 32];
   const int row = blockIdx.x;
   const TT* xb = x + (size_t)row * T * H;
-  for (int c = threadIdx.x; c < H; c += NT) {
-    float s = 0.f;
-    for (int t = 0; t < T; ++t) s += to_f32(xb[(size_t)t * H + c]);
-    s /= (float)T;
-    ps[c] = s;
-    pooled[(size_t)row * H + c] = s;
+  if (sizeof(TT) == 2 && H == 128) {
+    // bf16, H = 128: 16 lanes x 16 B cover a token row, the CTA's 16 lane groups take tokens t, t+16, ... (all loads
+    // independent and in flight together), then the 16 partial rows are summed through shared memory
+    __shared__ float part[16][128 + 4];
+    const int cg = threadIdx.x & 15, tg = threadIdx.x >> 4;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int t = tg; t < T; t += 16) {
+      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(xb) + (size_t)t * H + cg * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc[2 * k] += __uint_as_float(w[k] << 16); acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[tg][cg * 8 + i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) s += part[g][threadIdx.x];
+      s /= (float)T;
+      ps[threadIdx.x] = s;
+      pooled[(size_t)row * H + threadIdx.x] = s;
+    }
+  } else {
+    for (int c = threadIdx.x; c < H; c += NT) {
+      float s = 0.f;
+      for (int t = 0; t < T; ++t) s += to_f32(xb[(size_t)t * H + c]);
+      s /= (float)T;
+      ps[c] = s;
+      pooled[(size_t)row * H + c] = s;
+    }
   }
   __syncthreads();
   float part = 0.f;
@@ -119,7 +146,20 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(int T, int H, int n_out, c
   }
   __syncthreads();
   TT* dxb = dx + (size_t)row * T * H;
-  for (int e = threadIdx.x; e < T * H; e += NT) dxb[e] = from_f32<TT>(dps[e % H]);
+  if (sizeof(TT) == 2 && H % 8 == 0) {          // 16 B stores: every token row of the clip receives the same H values
+    const int cpr = H / 8;                       // chunks per row
+    for (int e = threadIdx.x; e < T * cpr; e += NT) {
+      const int c = (e % cpr) * 8;
+      uint4 o;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(dps[c], dps[c + 1]), p1 = __floats2bfloat162_rn(dps[c + 2], dps[c + 3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(dps[c + 4], dps[c + 5]), p3 = __floats2bfloat162_rn(dps[c + 6], dps[c + 7]);
+      o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+      o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(dxb) + (size_t)e * 8) = o;
+    }
+  } else {
+    for (int e = threadIdx.x; e < T * H; e += NT) dxb[e] = from_f32<TT>(dps[e % H]);
+  }
 }
 
 }  // namespace

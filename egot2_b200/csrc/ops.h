@@ -97,7 +97,10 @@ int small_attn_bwd(const SmallAttnArgs& a, cudaStream_t st);
 
 // dtable[t,:] += sum_b dy[b,t,:]   (gradient of the (T,H) token table added after the embed LN)
 // p_drop > 0: dy has NOT had the embedding dropout's mask applied yet; the kernel applies it while reading
-int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, float p_drop, uint64_t drop_key, cudaStream_t st);
+// dtable[t,:] += sum_b dy[b,t,:] (dtable may be null); seg_out[k][:] += the same sums over segment k's tokens (null entries skipped)
+struct SegOut { int n = 0; int tokens[EGOT2_MAX_SEG] = {}; float* out[EGOT2_MAX_SEG] = {}; };
+int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, const SegOut& so, float p_drop, uint64_t drop_key,
+               cudaStream_t st);
 // column sums: out[n] += sum_m x[m,n]   (bias gradients)
 int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int gstride, float* out, cudaStream_t st);
 // in-place x *= dropmask/(1-p) over n elements (idx = linear element index)

@@ -101,13 +101,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) ln_bwd_kernel(const LayerNo
 }
 
 // ------------------------------------------------------------------ misc elementwise / reductions
+__device__ __forceinline__ float* seg_target(const SegOut& so, int t) {
+  int seg = 0, d = t;
+  while (seg < so.n - 1 && d >= so.tokens[seg]) { d -= so.tokens[seg]; ++seg; }
+  return seg < so.n ? so.out[seg] : nullptr;
+}
 template <typename TT>
 __global__ void table_grad_kernel(int B, int T, int H, int clips_per_cta, const TT* __restrict__ dy,
-                                  float* __restrict__ dtable, float p_drop, uint64_t drop_key) {
+                                  float* __restrict__ dtable, const SegOut so, float p_drop, uint64_t drop_key) {
   EGOT2_PDL_ENTER();
   // CTA (t, chunk): sums its chunk of clips for token t, then one atomic per column
   const int t = blockIdx.x;
   const int b0 = blockIdx.y * clips_per_cta, b1 = min(B, b0 + clips_per_cta);
+  float* seg_out = seg_target(so, t);
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float s = 0.f;
     if (p_drop > 0.f) {       // dy is read BEFORE the embedding dropout's mask was applied: apply it on the fly
@@ -119,7 +125,49 @@ __global__ void table_grad_kernel(int B, int T, int H, int clips_per_cta, const 
     } else {
       for (int b = b0; b < b1; ++b) s += to_f32(dy[((size_t)b * T + t) * H + c]);
     }
-    atomicAdd(dtable + (size_t)t * H + c, s);
+    if (dtable) atomicAdd(dtable + (size_t)t * H + c, s);
+    if (seg_out) atomicAdd(seg_out + c, s);
+  }
+}
+// bf16, H = 8 * LPR with LPR a power of two <= 128: LPR lanes x 16 B cover a token row, the CTA's 128 / LPR lane groups
+// stride over the clips (independent 16 B loads), the partial rows meet in shared memory
+__global__ void __launch_bounds__(128) table_grad_vec_kernel(int B, int T, int H, int clips_per_cta, const bf16* __restrict__ dy,
+                                                             float* __restrict__ dtable, const SegOut so, float p_drop,
+                                                             uint64_t drop_key) {
+  EGOT2_PDL_ENTER();
+  __shared__ float part[1024];
+  const int lpr = H >> 3, groups = 128 / lpr;
+  const int cg = threadIdx.x % lpr, g = threadIdx.x / lpr;
+  const int t = blockIdx.x;
+  const int b0 = blockIdx.y * clips_per_cta, b1 = min(B, b0 + clips_per_cta);
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const uint32_t thr = drop_threshold(p_drop);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int b = b0 + g; b < b1; b += groups) {
+    const size_t idx = ((size_t)b * T + t) * H + cg * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(dy + idx);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
+      if (p_drop > 0.f) {
+        lo = drop_bits(drop_key, idx + 2 * k) >= thr ? lo * inv_keep : 0.f;
+        hi = drop_bits(drop_key, idx + 2 * k + 1) >= thr ? hi * inv_keep : 0.f;
+      }
+      acc[2 * k] += lo; acc[2 * k + 1] += hi;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[g * H + cg * 8 + i] = acc[i];
+  __syncthreads();
+  float* seg_out = seg_target(so, t);
+  for (int c = threadIdx.x; c < H; c += 128) {
+    float s = 0.f;
+    for (int k = 0; k < groups; ++k) s += part[k * H + c];
+    if (dtable) atomicAdd(dtable + (size_t)t * H + c, s);
+    if (seg_out) atomicAdd(seg_out + c, s);
   }
 }
 
@@ -291,9 +339,9 @@ __global__ void zero_kernel(float* p, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                            float bc1, float bc2_sqrt, float gscale) {
+                            float bc1, float bc2_sqrt, float gscale, bf16* __restrict__ shadow, int zero_grad) {
   EGOT2_PDL_ENTER();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float grad = g[i] * gscale;
@@ -303,7 +351,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
     m[i] = mi; v[i] = vi;
     // torch.optim.Adam: denom = sqrt(v)/sqrt(bias_correction2) + eps ; step = lr / bias_correction1
-    p[i] = w - (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    const float wn = w - (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    p[i] = wn;
+    if (shadow) shadow[i] = __float2bfloat16_rn(wn);     // the bf16 copy the next forward's GEMMs read
+    if (zero_grad) g[i] = 0.f;                           // the next backward accumulates into a clean arena
   }
 }
 
@@ -645,7 +696,8 @@ int layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t st) {
   EGOT2_CHECK(false, "layernorm_bwd: H=%d not in {32,64,128,256,512,1024}", a.H);
 }
 
-int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, float p_drop, uint64_t drop_key, cudaStream_t st) {
+int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, const SegOut& so, float p_drop, uint64_t drop_key,
+               cudaStream_t st) {
   const int nt = H < 256 ? ((H + 31) / 32 * 32) : 256;
   int chunks = (4 * sm_count() + T - 1) / T;           // ~4 CTAs per SM
   if (chunks > B) chunks = B;
@@ -653,8 +705,11 @@ int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, fl
   const int per = (B + chunks - 1) / chunks;
   dim3 grid(T, (B + per - 1) / per);
   ProfScope prof(st, "table_grad B%d T%d H%d", B, T, H);
-  if (dtype == EGOT2_F32) launch(table_grad_kernel<float>, dim3(grid), dim3(nt), 0, st, B, T, H, per, (const float*)dy, dtable, p_drop, drop_key);
-  else launch(table_grad_kernel<bf16>, dim3(grid), dim3(nt), 0, st, B, T, H, per, (const bf16*)dy, dtable, p_drop, drop_key);
+  const int lpr = H / 8;
+  if (dtype == EGOT2_BF16 && H % 8 == 0 && lpr <= 128 && (lpr & (lpr - 1)) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0)
+    launch(table_grad_vec_kernel, grid, dim3(128), 0, st, B, T, H, per, (const bf16*)dy, dtable, so, p_drop, drop_key);
+  else if (dtype == EGOT2_F32) launch(table_grad_kernel<float>, grid, dim3(nt), 0, st, B, T, H, per, (const float*)dy, dtable, so, p_drop, drop_key);
+  else launch(table_grad_kernel<bf16>, grid, dim3(nt), 0, st, B, T, H, per, (const bf16*)dy, dtable, so, p_drop, drop_key);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -777,18 +832,30 @@ extern "C" int egot2_cast_bf16_to_f32(const void* src, float* dst, size_t n, voi
   return 0;
 }
 
-extern "C" int egot2_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
-                               float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
-                               void* stream) {
+static int adam_launch(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* shadow,
+                       int zero_grad, void* stream) {
   EGOT2_CHECK(step >= 1, "adam: step must be >= 1");
   if (n == 0) return 0;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   ProfScope prof((cudaStream_t)stream, "adam n%zu", n);
-  launch(adam_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                           weight_decay, bc1, sqrtf(bc2), grad_scale);
+  launch(adam_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+         beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, (bf16*)shadow, zero_grad);
   EGOT2_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int egot2_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                               void* stream) {
+  return adam_launch(param, const_cast<float*>(grad), exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step,
+                     grad_scale, nullptr, 0, stream);
+}
+extern "C" int egot2_adam_step_fused(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                                     float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                                     float grad_scale, void* shadow_bf16, int32_t zero_grad, void* stream) {
+  return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, shadow_bf16,
+                     zero_grad, stream);
 }
 
 extern "C" int egot2_hhi_tok_table_fwd(const float* task_embed, const float* pe, int32_t pe_len, int32_t n_seg,

@@ -70,6 +70,10 @@ class ParamArena:
         self.param = torch.zeros(self.numel, device=self.device, dtype=torch.float32)
         self.grad = torch.zeros(self.numel, device=self.device, dtype=torch.float32)
         self.shadow: Optional[torch.Tensor] = None
+        # True while `shadow` is known to equal bf16(param): set by the fused Adam (which writes both), cleared by
+        # anything else that may change the parameters.  The drop-in nn.Module path never sets it (a torch optimizer
+        # updates the arena views behind our back), so there every forward re-casts.
+        self.shadow_fresh = False
         self.head_w_names, self.head_b_names = head_w, head_b
 
     def view(self, name: str, base: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -91,6 +95,7 @@ class ParamArena:
         with torch.no_grad():
             for name in self.shapes:
                 self.view(name).copy_(sd[name].to(device=self.device, dtype=torch.float32))
+        self.shadow_fresh = False
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {name: self.view(name).clone() for name in self.shapes}
@@ -99,6 +104,9 @@ class ParamArena:
         """fp32 -> bf16 shadow of the whole arena (one launch)."""
         if self.shadow is None:
             self.shadow = torch.empty(self.numel, device=self.device, dtype=torch.bfloat16)
+            self.shadow_fresh = False
+        if self.shadow_fresh:
+            return
         L.call("egot2_cast_f32_to_bf16", self.param.data_ptr(), self.shadow.data_ptr(), self.numel, _stream())
 
 
@@ -568,28 +576,41 @@ class TranslatorEngine:
                 eg.dfeat[k] = dfeats[k].data_ptr()
         eg.ln_g, eg.ln_b = gv("ln.weight").data_ptr(), gv("ln.bias").data_ptr()
         if sp.embed == "task_sinusoid":
-            dtable = torch.zeros((T, H), device=dev, dtype=torch.float32)
+            # table row = task_embed[task_k] + fixed sinusoid: the column sums of each segment go straight into
+            # d(task_embed[task_k]) (no (T,H) table gradient, no second reduction pass)
+            te = gv("task_embed").view(-1, H)
+            for k, s in enumerate(sp.segments):
+                eg.seg_embed[k] = te[s.task_id].data_ptr()
         else:
-            dtable = gv("pe").view(T, H)
-        eg.tok_table = dtable.data_ptr()
+            eg.tok_table = gv("pe").view(T, H).data_ptr()
         d = act.embed_desc
         ws = self._workspace(L.load().egot2_embed_workspace_bytes(C.byref(d), 1))
         L.call("egot2_embed_bwd", C.byref(d), C.byref(act.embed_in), C.byref(act.embed_out), dx.data_ptr(), C.byref(eg),
                ws.data_ptr(), ws.numel(), st)
-        if sp.embed == "task_sinusoid":
-            segs = (C.c_int32 * len(act.seg_tokens))(*act.seg_tokens)
-            ids = (C.c_int32 * len(act.seg_tokens))(*[s.task_id for s in sp.segments])
-            L.call("egot2_hhi_tok_table_bwd", dtable.data_ptr(), len(act.seg_tokens), segs, ids, H,
-                   gv("task_embed").data_ptr(), st)
         return grad, dfeats
 
     # ------------------------------------------------------------------ fused optimizer
     def adam_step(self, state: Dict[str, torch.Tensor], step: int, lr: float = 5e-4, betas=(0.9, 0.999),
-                  eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0):
-        """torch.optim.Adam over the whole arena in one launch (HHI/tasks/ttm/video_task.py:64-66: lr 5e-4)."""
+                  eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0, fused: bool = False):
+        """torch.optim.Adam over the whole arena in one launch (HHI/tasks/ttm/video_task.py:64-66: lr 5e-4).
+        fused: the same launch also writes the bf16 shadow of the updated parameters (bf16 engines) and clears the
+        gradient arena, so the next step needs neither the cast launch nor a fill (callers then pass
+        zero_grad=False to backward())."""
         if "m" not in state:
             state["m"] = torch.zeros_like(self.arena.param)
             state["v"] = torch.zeros_like(self.arena.param)
+        if fused:
+            shadow = None
+            if self.dtype == "bf16":
+                if self.arena.shadow is None:
+                    self.arena.refresh_shadow()
+                shadow = self.arena.shadow.data_ptr()
+            L.call("egot2_adam_step_fused", self.arena.param.data_ptr(), self.arena.grad.data_ptr(), state["m"].data_ptr(),
+                   state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps, weight_decay, int(step),
+                   float(grad_scale), shadow, 1, _stream())
+            self.arena.shadow_fresh = shadow is not None
+            return
         L.call("egot2_adam_step", self.arena.param.data_ptr(), self.arena.grad.data_ptr(), state["m"].data_ptr(),
                state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps, weight_decay, int(step),
                float(grad_scale), _stream())
+        self.arena.shadow_fresh = False

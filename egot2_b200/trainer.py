@@ -119,6 +119,7 @@ class TranslatorTrainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.use_graphs = use_graphs
+        self._grad_clean = False           # True right after the fused Adam: the gradient arena is all zeros
         self._graphs: Dict[int, tuple] = {}
         self._h2d: Dict[int, List[torch.Tensor]] = {}
         self.copy_stream = torch.cuda.Stream(device=self.device)
@@ -134,7 +135,9 @@ class TranslatorTrainer:
     def _fwd_bwd(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, seed: int) -> Activations:
         act = self.engine.forward(feats, training=True, seed=seed, labels=labels, loss=self.loss_kind,
                                   class_weight=self.class_weight, persistent=True)
-        self.engine.backward(act)
+        # the fused Adam of the previous step left the gradient arena cleared (and the bf16 shadow current)
+        self.engine.backward(act, zero_grad=not self._grad_clean)
+        self._grad_clean = False
         return act
 
     def train_step(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, graph_key: Optional[int] = None):
@@ -148,7 +151,12 @@ class TranslatorTrainer:
             if entry is None:
                 entry = self._capture(feats, labels, graph_key)
             graph, act = entry
+            if not self._grad_clean:                      # e.g. the first graphed step after eager ones
+                self.engine.arena.grad.zero_()
+            if self.engine.dtype == "bf16" and not self.engine.arena.shadow_fresh:
+                self.engine.arena.refresh_shadow()
             graph.replay()
+            self._grad_clean = False
         else:
             act = self._fwd_bwd(feats, labels, seed=self.step_count)
         self._reduce_and_update()
@@ -162,6 +170,13 @@ class TranslatorTrainer:
         with torch.cuda.stream(s):
             self._fwd_bwd(feats, labels, seed=1 + key)
         torch.cuda.current_stream().wait_stream(s)
+        # the captured sequence is the steady state: shadow current and gradient arena cleared by the previous step's
+        # fused Adam, so neither the cast nor the fill is part of the graph
+        self.engine.arena.grad.zero_()
+        if self.engine.dtype == "bf16":
+            self.engine.arena.refresh_shadow()
+            self.engine.arena.shadow_fresh = True
+        self._grad_clean = True
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -175,7 +190,8 @@ class TranslatorTrainer:
         if self.world > 1:
             scale = allreduce_gradients(eng.arena.grad, self.pg)            # ONE flat NCCL all-reduce (NVLink)
         eng.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
-                      self.hp["weight_decay"], grad_scale=scale)
+                      self.hp["weight_decay"], grad_scale=scale, fused=True)
+        self._grad_clean = True
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) step
     def train_step_host(self, host_feats: Sequence[torch.Tensor], host_labels: torch.Tensor, slot: int = 0) -> float:

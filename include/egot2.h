@@ -111,15 +111,18 @@ typedef struct {
   float* proj_b[EGOT2_MAX_SEG];
   float* ln_g;
   float* ln_b;
-  float* tok_table;                   /* (T,H) */
+  float* tok_table;                   /* (T,H); may be NULL when the table itself is not a parameter (HHI: use seg_embed) */
   float* dfeat[EGOT2_MAX_SEG];        /* optional (B,D_k,K_k) fp32 gradient w.r.t. a feature stream; NULL = frozen */
+  float* seg_embed[EGOT2_MAX_SEG];    /* optional (H) +=: sum over clips and over segment k's tokens of the gradient that
+                                       * reaches the token table, i.e. d(task_embed[task_k]) of the HHI translators whose
+                                       * table rows are task_embed[task_k] + a fixed sinusoid (no (T,H) detour) */
 } egot2_embed_grads;
 
 size_t egot2_embed_workspace_bytes(const egot2_embed_desc* d, int backward);
 int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* in, const egot2_embed_out* out,
                     void* workspace, size_t ws_bytes, void* stream);
 int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* in, const egot2_embed_out* saved,
-                    const void* dx /* (B,T,H) dtype; clobbered */, const egot2_embed_grads* g,
+                    const void* dx /* (B,T,H) dtype; left intact */, const egot2_embed_grads* g,
                     void* workspace, size_t ws_bytes, void* stream);
 
 /* HHI: tok_table[off_k + d, :] = task_embed[task_id_k, :] + pe[d, :]  (d restarts per task; `pe` is the module's
@@ -300,6 +303,11 @@ int egot2_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);
 int egot2_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                     void* stream);
+/* Same update, and in the same pass: the bf16 shadow of the updated parameters (shadow_bf16, n elements; NULL = skip) and,
+ * if zero_grad, the gradient arena is cleared for the next step's accumulation (replaces a cast launch and a fill). */
+int egot2_adam_step_fused(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                          void* shadow_bf16, int32_t zero_grad, void* stream);
 
 /* ------------------------------------------------------------------ op-level entry points (diagnostics / unit tests) */
 /* C[M,N] = op(A)[M,K] . op(B)[K,N] (+bias[N]) ; A stored (M,K) or, if trans_a, (K,M); B stored (K,N) or, if
