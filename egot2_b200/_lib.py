@@ -57,7 +57,7 @@ class LayerGrads(C.Structure):
 
 
 class LayerSaved(C.Structure):
-    _fields_ = [(n, vp) for n in ["qkv", "attn", "lse", "y1", "stat1", "x1", "hid", "y2", "stat2", "hid_mask"]]
+    _fields_ = [(n, vp) for n in ["qkv", "attn", "lse", "y1", "stat1", "x1", "hid", "y2", "stat2", "hid_mask", "ffn_scratch"]]
 
 
 class DecoderDesc(C.Structure):
@@ -116,6 +116,7 @@ SIGNATURES = {
     "egot2_embed_bwd": (C.c_int, [P(EmbedDesc), P(EmbedIn), P(EmbedOut), vp, P(EmbedGrads), vp, sz, vp]),
     "egot2_hhi_tok_table_fwd": (C.c_int, [vp, vp, i32, i32, P(i32), P(i32), i32, vp, vp]),
     "egot2_hhi_tok_table_bwd": (C.c_int, [vp, i32, P(i32), P(i32), i32, vp, vp]),
+    "egot2_ffn_scratch_bytes": (sz, [i32]),
     "egot2_encoder_layer_workspace_bytes": (sz, [P(LayerDesc), C.c_int]),
     "egot2_encoder_layer_fwd": (C.c_int, [P(LayerDesc), P(LayerParams), vp, vp, P(LayerSaved), vp, sz, vp]),
     "egot2_encoder_layer_bwd": (C.c_int, [P(LayerDesc), P(LayerParams), vp, P(LayerSaved), vp, vp, P(LayerGrads),

@@ -441,6 +441,8 @@ int layer_check(const egot2_layer_desc* d) {
 }
 }  // namespace
 
+extern "C" size_t egot2_ffn_scratch_bytes(int32_t M) { return M > 0 ? ffn_scratch_bytes(M) : 0; }
+
 extern "C" size_t egot2_encoder_layer_workspace_bytes(const egot2_layer_desc* d, int backward) {
   return layer_ws_layout(d, backward, nullptr, 0, nullptr);
 }
@@ -480,7 +482,7 @@ extern "C" int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_la
   if (ffn_fused_supported(d->dtype, H, FF) && !env_is("EGOT2_FFN", "unfused"))
     return ffn_fused_fwd(M, FF, s->x1, p->lin1_w, p->lin1_b, p->lin2_w, p->lin2_b, p->norm2_g, p->norm2_b, d->ln_eps,
                          s->hid, s->hid_mask, s->y2, s->stat2, x_out, pd, site_key(d->seed, SITE_FFN, L),
-                         site_key(d->seed, SITE_DROP2, L), st);
+                         site_key(d->seed, SITE_DROP2, L), s->ffn_scratch, st);
   // 5. hid = dropout(relu(x1 . W1^T + b1))
   {
     GemmArgs g; g.M = M; g.N = FF; g.K = H; g.A = s->x1; g.lda = H; g.B = p->lin1_w; g.ldb = H; g.trans_b = 1;
@@ -543,7 +545,7 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   const bool fused_dx = s->hid_mask && ffn_fused_supported(dt, H, FF) && !env_is("EGOT2_FFN", "unfused");
   if (fused_dx) {
     // one tcgen05 kernel: dhid = gate(d2 . W2) and d3 = dhid . W1 + d1, dhid never re-read for the second GEMM
-    EGOT2_TRY(ffn_fused_bwd_dx(M, FF, d2, pd > 0.f ? w.d1 : nullptr, s->hid_mask, p->lin1_w, p->lin2_w, pd, w.dhid, w.d3, st));
+    EGOT2_TRY(ffn_fused_bwd_dx(M, FF, d2, pd > 0.f ? w.d1 : nullptr, s->hid_mask, p->lin1_w, p->lin2_w, pd, w.dhid, w.d3, s->ffn_scratch, st));
   } else {
     GemmArgs m; m.M = M; m.N = FF; m.K = H; m.A = d2; m.lda = H; m.B = p->lin2_w; m.ldb = FF; m.trans_b = 0;
     m.C = w.dhid; m.ldc = FF; m.mask = s->hid; m.ldm = FF; m.mask_scale = inv_keep; m.in_dtype = dt; m.out_dtype = dt;

@@ -58,6 +58,11 @@ struct FfnArgs {
   uint2* hmask;          // [FF/64][M] x 64 bits: hidden activation != 0 (ReLU gate x dropout keep), for ffn_bwd_dx
   const bf16* d1;        // backward: gradient arriving through the residual branch (added to d3), (M,128)
   float p_drop; uint64_t key_ffn, key_drop2;
+  // FF-split tail (see ffn_launch): CTA pairs >= split_pair0 each own 1/S of the FF range of a tail token tile and add
+  // their partial GEMM2 accumulator into `partial` (fp32, rows relative to token split_pair0*256); a fix-up kernel finishes
+  int split_pair0, S;
+  float* partial;
+  const bf16* fix_x1; const bf16* fix_d1; bf16* fix_y2; bf16* fix_out;     // global tensors the fix-up kernel reads / writes
   long long* trace;      // EGOT2_FFN_TRACE builds only: per-chunk clock64 stamps of CTA 0
 };
 
@@ -79,6 +84,9 @@ template <bool MN>
 __device__ __forceinline__ uint64_t wdesc(uint32_t stage, int kk) {
   return MN ? make_smem_desc_sw128(stage + (uint32_t)kk * 2048, 8192, 1024)
             : make_smem_desc_sw128(stage + (uint32_t)(kk >> 2) * 8192 + (uint32_t)(kk & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -122,8 +130,17 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
-  const int NC = a.FF / FC;
+  // which token tile and which chunk range [c_begin, c_begin + NC) of the FF loop this pair owns (NC = all of it for a
+  // regular pair; the loops below count LOCAL chunks, cg = c_begin + c is the chunk's position in FF)
+  int tile_pair = (int)blockIdx.x >> 1, c_begin = 0, NC = a.FF / FC;
+  const bool split = tile_pair >= a.split_pair0;
+  if (split) {
+    const int u = tile_pair - a.split_pair0;
+    tile_pair = a.split_pair0 + u / a.S;
+    NC /= a.S;
+    c_begin = (u % a.S) * NC;
+  }
+  const int m0 = (tile_pair * 2 + ((int)blockIdx.x & 1)) * BM;
 #ifdef EGOT2_FFN_TRACE
   if (threadIdx.x == 0 && a.trace) {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -179,10 +196,10 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const uint32_t bar = mapa(r1_full + 8 * s, 0);
             if (leader) mbar_expect_tx(r1_full + 8 * s, 2 * STAGE);
             if (!BWD) {       // GEMM1 B = W1 rows (ff) c*128 + rank*64 .., K-major: two 64-k halves
-              tma_load_2d_cg2(sW1 + s * STAGE, &tm_w1, bar, 0, i1 * FC + rank * 64);
-              tma_load_2d_cg2(sW1 + s * STAGE + 8192, &tm_w1, bar, 64, i1 * FC + rank * 64);
+              tma_load_2d_cg2(sW1 + s * STAGE, &tm_w1, bar, 0, (c_begin + i1) * FC + rank * 64);
+              tma_load_2d_cg2(sW1 + s * STAGE + 8192, &tm_w1, bar, 64, (c_begin + i1) * FC + rank * 64);
             } else {          // GEMM1 B = W2[:, ff], MN-major: 128 k-rows (h) x this CTA's 64 ff columns, one box
-              tma_load_2d_cg2(sW1 + s * STAGE, &tm_w2, bar, i1 * FC + rank * 64, 0);
+              tma_load_2d_cg2(sW1 + s * STAGE, &tm_w2, bar, (c_begin + i1) * FC + rank * 64, 0);
             }
             ++i1;
           }
@@ -194,10 +211,10 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const uint32_t bar = mapa(r2_full + 8 * s, 0);
             if (leader) mbar_expect_tx(r2_full + 8 * s, 2 * STAGE);
             if (!BWD) {       // GEMM2 B = W2 rows (h) rank*64 .., K-major over ff c*128 ..
-              tma_load_2d_cg2(sW2 + s * STAGE, &tm_w2, bar, i2 * FC, rank * 64);
-              tma_load_2d_cg2(sW2 + s * STAGE + 8192, &tm_w2, bar, i2 * FC + 64, rank * 64);
+              tma_load_2d_cg2(sW2 + s * STAGE, &tm_w2, bar, (c_begin + i2) * FC, rank * 64);
+              tma_load_2d_cg2(sW2 + s * STAGE + 8192, &tm_w2, bar, (c_begin + i2) * FC + 64, rank * 64);
             } else {          // GEMM2 B = W1[ff, :], MN-major: 128 k-rows (ff) x this CTA's 64 h columns
-              tma_load_2d_cg2(sW2 + s * STAGE, &tm_w1, bar, rank * 64, i2 * FC);
+              tma_load_2d_cg2(sW2 + s * STAGE, &tm_w1, bar, rank * 64, (c_begin + i2) * FC);
             }
             ++i2;
           }
@@ -255,12 +272,12 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         TR(c, 11);
         if (a.save_hid) {
           if (a.hid_tiled) {      // box (tile, ff-half) is one contiguous 16 KB block
-            const int row = ((int)blockIdx.x * (a.FF / 64) + c * 2) * 128;
+            const int row = ((m0 / BM) * (a.FF / 64) + (c_begin + c) * 2) * 128;
             tma_store_2d(&tm_hid, sHid + hb * TILE, 0, row);
             tma_store_2d(&tm_hid, sHid + hb * TILE + HALF, 0, row + 128);
           } else {
-            tma_store_2d(&tm_hid, sHid + hb * TILE, c * FC, m0);
-            tma_store_2d(&tm_hid, sHid + hb * TILE + HALF, c * FC + 64, m0);
+            tma_store_2d(&tm_hid, sHid + hb * TILE, (c_begin + c) * FC, m0);
+            tma_store_2d(&tm_hid, sHid + hb * TILE + HALF, (c_begin + c) * FC + 64, m0);
           }
           tma_store_commit();
           tma_store_wait_read();
@@ -284,12 +301,13 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // backward: the ReLU/dropout gate bits of chunk c+1 are fetched while chunk c is processed (a dependent global
     // load in front of every chunk's arithmetic was ~1 us of exposed latency per chunk)
     uint2 gate_next = make_uint2(0u, 0u);
-    if (BWD && row_ok) gate_next = __ldg(a.hmask + (size_t)ch * a.M + m);
+    if (BWD && row_ok) gate_next = __ldg(a.hmask + (size_t)(c_begin * 2 + ch) * a.M + m);
     for (int c = 0; c < NC; ++c) {
       const int bsel = c & 1;
       const int hb = c % HB;
       const uint2 gate_cur = gate_next;
-      if (BWD && row_ok && c + 1 < NC) gate_next = __ldg(a.hmask + (size_t)((c + 1) * 2 + ch) * a.M + m);
+      const int cg = c_begin + c;
+      if (BWD && row_ok && c + 1 < NC) gate_next = __ldg(a.hmask + (size_t)((cg + 1) * 2 + ch) * a.M + m);
       const uint32_t hrow = sHid + hb * TILE + ch * HALF + (uint32_t)r * 128;
       mbar_wait(a1_full + 8 * bsel, (c >> 1) & 1);
       if (threadIdx.x == 64) TR(c, 6);
@@ -309,7 +327,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
-          const int n0 = c * FC + ch * 64 + h2 * 32;
+          const int n0 = cg * FC + ch * 64 + h2 * 32;
           const uint64_t idx0 = (uint64_t)m * a.FF + n0;          // multiple of 32: this thread owns one 32-bit mask word
           // pre-activations (dropout scale folded in: relu(acc + b) / (1-p) == relu(acc/(1-p) + b/(1-p)), sB1 holds the
           // pre-scaled bias in training), and the word of their sign bits gathered with one funnel shift per element
@@ -348,7 +366,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
           gate[h2] = gw;
         }
-        if (a.hmask && row_ok) a.hmask[(size_t)(c * 2 + ch) * a.M + m] = make_uint2(gate[0], gate[1]);
+        if (a.hmask && row_ok) a.hmask[(size_t)(cg * 2 + ch) * a.M + m] = make_uint2(gate[0], gate[1]);
       } else {
         const uint2 gate = gate_cur;
 #pragma unroll
@@ -392,7 +410,21 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int nb = ch * 64;
     const uint32_t xrow = sX + ch * HALF + (uint32_t)r * 128;
     const uint32_t yrow = sHid + ch * HALF + (uint32_t)r * 128;
-    if constexpr (BWD) {
+    if (split) {
+      // FF-split tail unit: this pair's partial sum over its chunk range joins the others' in fp32; the fix-up kernel
+      // applies everything that follows the second GEMM once all S partials are in
+      float* prow = a.partial + ((size_t)(m - a.split_pair0 * 2 * BM)) * H + nb;
+#pragma unroll 1
+      for (int j8 = 0; j8 < 8; ++j8) {
+        uint32_t rr[8];
+        tmem_ld_32x8(acc2 + lane_addr + nb + j8 * 8, rr);
+        tmem_ld_wait();
+        if (row_ok) {
+          red_add_v4(prow + j8 * 8, __uint_as_float(rr[0]), __uint_as_float(rr[1]), __uint_as_float(rr[2]), __uint_as_float(rr[3]));
+          red_add_v4(prow + j8 * 8 + 4, __uint_as_float(rr[4]), __uint_as_float(rr[5]), __uint_as_float(rr[6]), __uint_as_float(rr[7]));
+        }
+      }
+    } else if constexpr (BWD) {
       // d3 = acc2 + d1 (gradient through the residual branch); with no dropout2, d1 IS the d2 tile still in sX
       const bf16* d1row = (a.d1 && row_ok) ? a.d1 + (size_t)m * H + nb : nullptr;
 #pragma unroll 1
@@ -515,6 +547,70 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------- fix-up of the FF-split tail tiles
+// One warp per token row (4 columns per lane).  Reads the summed fp32 partials, finishes the block exactly like the main
+// kernel's final epilogue does for a regular tile, and leaves the scratch rows zeroed for the next launch.
+__global__ void __launch_bounds__(256) ffn_fixup_fwd_kernel(int rows, int m_base, float* __restrict__ partial,
+                                                            const bf16* __restrict__ x1, const float* __restrict__ b2,
+                                                            const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                            float eps, float p_drop, uint64_t key_drop2,
+                                                            bf16* __restrict__ y2, float* __restrict__ stat2,
+                                                            bf16* __restrict__ x_out) {
+  EGOT2_PDL_ENTER();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int m = m_base + r, c0 = lane * 4;
+  float4* pp = reinterpret_cast<float4*>(partial + (size_t)r * H + c0);
+  const float4 acc = *pp;
+  *pp = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint2 xw = *reinterpret_cast<const uint2*>(x1 + (size_t)m * H + c0);
+  const float4 bb = *reinterpret_cast<const float4*>(b2 + c0);
+  float v[4] = {acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w};
+  if (p_drop > 0.f) {
+    const float inv_keep = 1.f / (1.f - p_drop);
+    const uint32_t thr = drop_threshold(p_drop);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = drop_bits(key_drop2, (uint64_t)m * H + c0 + i) >= thr ? v[i] * inv_keep : 0.f;
+  }
+  v[0] += __uint_as_float(xw.x << 16); v[1] += __uint_as_float(xw.x & 0xffff0000u);
+  v[2] += __uint_as_float(xw.y << 16); v[3] += __uint_as_float(xw.y & 0xffff0000u);
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 yw; yw.x = *reinterpret_cast<uint32_t*>(&t0); yw.y = *reinterpret_cast<uint32_t*>(&t1);
+  *reinterpret_cast<uint2*>(y2 + (size_t)m * H + c0) = yw;
+  v[0] = __uint_as_float(yw.x << 16); v[1] = __uint_as_float(yw.x & 0xffff0000u);
+  v[2] = __uint_as_float(yw.y << 16); v[3] = __uint_as_float(yw.y & 0xffff0000u);
+  float sum = (v[0] + v[1]) + (v[2] + v[3]);
+  float sq = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
+  sum = warp_sum(sum); sq = warp_sum(sq);
+  const float mean = sum * (1.f / H);
+  const float var = fmaxf(sq * (1.f / H) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  if (lane == 0) { stat2[2 * (size_t)m] = mean; stat2[2 * (size_t)m + 1] = rstd; }
+  const float4 g4 = *reinterpret_cast<const float4*>(ln_g + c0), e4 = *reinterpret_cast<const float4*>(ln_b + c0);
+  __nv_bfloat162 o0 = __floats2bfloat162_rn((v[0] - mean) * rstd * g4.x + e4.x, (v[1] - mean) * rstd * g4.y + e4.y);
+  __nv_bfloat162 o1 = __floats2bfloat162_rn((v[2] - mean) * rstd * g4.z + e4.z, (v[3] - mean) * rstd * g4.w + e4.w);
+  uint2 ow; ow.x = *reinterpret_cast<uint32_t*>(&o0); ow.y = *reinterpret_cast<uint32_t*>(&o1);
+  *reinterpret_cast<uint2*>(x_out + (size_t)m * H + c0) = ow;
+}
+// d3 = partial + d1 (the gradient arriving through the residual branch)
+__global__ void __launch_bounds__(256) ffn_fixup_bwd_kernel(int rows, int m_base, float* __restrict__ partial,
+                                                            const bf16* __restrict__ d1, bf16* __restrict__ d3) {
+  EGOT2_PDL_ENTER();
+  const int i = blockIdx.x * 256 + threadIdx.x;          // one thread per 4 columns
+  if (i >= rows * (H / 4)) return;
+  const int r = i / (H / 4), c0 = (i % (H / 4)) * 4;
+  const size_t g = (size_t)(m_base + r) * H + c0;
+  float4* pp = reinterpret_cast<float4*>(partial + (size_t)r * H + c0);
+  const float4 acc = *pp;
+  *pp = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint2 dw = *reinterpret_cast<const uint2*>(d1 + g);
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(acc.x + __uint_as_float(dw.x << 16), acc.y + __uint_as_float(dw.x & 0xffff0000u));
+  __nv_bfloat162 t1 = __floats2bfloat162_rn(acc.z + __uint_as_float(dw.y << 16), acc.w + __uint_as_float(dw.y & 0xffff0000u));
+  uint2 ow; ow.x = *reinterpret_cast<uint32_t*>(&t0); ow.y = *reinterpret_cast<uint32_t*>(&t1);
+  *reinterpret_cast<uint2*>(d3 + g) = ow;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -547,6 +643,15 @@ int kmajor_map(CUtensorMap* map, const void* basep, int inner, int rows, int ld,
 
 }  // namespace
 
+static bool env_off(const char* name) { const char* v = getenv(name); return v && v[0] == '0'; }
+
+size_t ffn_scratch_bytes(int M) {
+  // the tail is always shorter than one wave of pairs, whatever the occupancy query says at launch time
+  const int pairs = (M + 2 * BM - 1) / (2 * BM), slots = sm_count() / 2;
+  const int tail = pairs < slots ? pairs : slots;
+  return pairs > 1 ? (size_t)tail * 2 * BM * H * sizeof(float) : 0;
+}
+
 bool ffn_fused_supported(int dtype, int Hdim, int FF) {
   return dtype == EGOT2_BF16 && Hdim == H && FF >= FC && FF % FC == 0;
 }
@@ -574,9 +679,45 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
 #endif
   {
     ProfScope prof(st, bwd ? "ffn_bwd_dx_sm100 M%d H128 FF%d" : "ffn_fwd_sm100 M%d H128 FF%d", M, FF);
-    const int tiles = (M + BM - 1) / BM, grid = (tiles + 1) / 2 * 2;      // whole CTA pairs
-    launch(kernels[ki], dim3(grid), dim3(NTHREADS), smem, st, tx, tw1, tw2, thid, ty2, tout, a);
+    const int tiles = (M + BM - 1) / BM, pairs = (tiles + 1) / 2;         // whole CTA pairs
+    // Wave quantisation: `slots` pairs are resident at once (one CTA per SM); the pairs of the last, partial wave would
+    // each run a full-length tile on a mostly idle GPU.  Instead each tail tile is cut into S slices of the FF loop
+    // (S * tail <= slots, S | FF/128) that run side by side and meet in an fp32 scratch; a small fix-up kernel applies
+    // what follows the second GEMM (ffn_fixup_*).  HHI b256: 90 pairs on 74 slots -> 74 full + 16 x 4 quarter units.
+    static int slots_cached[4] = {0, 0, 0, 0};
+    if (slots_cached[ki] == 0) {
+      int n = 0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * sm_count()); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&n, kernels[ki], &cfg) != cudaSuccess || n <= 0) { n = sm_count() / 2; (void)cudaGetLastError(); }
+      slots_cached[ki] = n;
+    }
+    int slots = slots_cached[ki];
+    if (getenv("EGOT2_FFN_SLOTS") && atoi(getenv("EGOT2_FFN_SLOTS")) > 0) slots = atoi(getenv("EGOT2_FFN_SLOTS"));   // tests: force a tail at small M
+    const int NCH = FF / FC;
+    int S = 1, tail = pairs % slots;
+    if (a.partial && pairs > slots && tail > 0 && !env_off("EGOT2_FFN_SPLIT")) {
+      for (int cand = 2; cand <= NCH && cand * tail <= slots; cand *= 2)
+        if (NCH % cand == 0) S = cand;
+    }
+    a.S = S;
+    a.split_pair0 = S > 1 ? pairs - tail : pairs;
+    const int grid_pairs = S > 1 ? (pairs - tail) + tail * S : pairs;
+    launch(kernels[ki], dim3(2 * grid_pairs), dim3(NTHREADS), smem, st, tx, tw1, tw2, thid, ty2, tout, a);
     EGOT2_LAUNCH_CHECK();
+    if (S > 1) {
+      const int m_base = a.split_pair0 * 2 * BM, rows = M - m_base;
+      if (bwd)
+        launch(ffn_fixup_bwd_kernel, dim3((rows * (H / 4) + 255) / 256), dim3(256), 0, st, rows, m_base, a.partial, a.fix_d1, a.fix_out);
+      else
+        launch(ffn_fixup_fwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, rows, m_base, a.partial, a.fix_x1, a.b2, a.ln_g, a.ln_b,
+               a.eps, a.p_drop, a.key_drop2, a.fix_y2, a.stat2, a.fix_out);
+      EGOT2_LAUNCH_CHECK();
+    }
   }
 #ifdef EGOT2_FFN_TRACE
   {
@@ -604,7 +745,7 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
 // hmask [FF/64][M] x 64 bit (if non-null), y2 and stat2
 int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1, const void* W2, const float* b2,
                   const float* ln_g, const float* ln_b, float eps, void* hid, void* hmask, void* y2, float* stat2, void* x_out,
-                  float p_drop, uint64_t key_ffn, uint64_t key_drop2, cudaStream_t st) {
+                  float p_drop, uint64_t key_ffn, uint64_t key_drop2, float* scratch, cudaStream_t st) {
   if (M == 0) return 0;
   CUtensorMap tx, tw1, tw2, thid, ty2, tout;
   EGOT2_TRY(kmajor_map(&tx, x1, H, M, H, 128));
@@ -621,13 +762,14 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
   a.M = M; a.FF = FF; a.b1 = b1; a.b2 = b2; a.ln_g = ln_g; a.ln_b = ln_b; a.eps = eps;
   a.stat2 = stat2; a.save_hid = hid != nullptr; a.hmask = (uint2*)hmask; a.d1 = nullptr; a.hid_tiled = tiled && hid;
   a.p_drop = p_drop; a.key_ffn = key_ffn; a.key_drop2 = key_drop2;
+  a.partial = scratch; a.fix_x1 = (const bf16*)x1; a.fix_d1 = nullptr; a.fix_y2 = (bf16*)y2; a.fix_out = (bf16*)x_out;
   return ffn_launch(false, M, FF, tx, tw1, tw2, thid, ty2, tout, a, st);
 }
 
 // Data-gradient half of the block's backward (see the kernel comment):
 //   dhid = (d2 . W2) * gate / (1-p)  -> (M,FF) bf16;   d3 = dhid . W1 + d1  -> (M,128) bf16   (d1 == nullptr: d1 is d2)
 int ffn_fused_bwd_dx(int M, int FF, const void* d2, const void* d1, const void* hmask, const void* W1, const void* W2,
-                     float p_drop, void* dhid, void* d3, cudaStream_t st) {
+                     float p_drop, void* dhid, void* d3, float* scratch, cudaStream_t st) {
   if (M == 0) return 0;
   CUtensorMap tx, tw1, tw2, thid, ty2;
   EGOT2_TRY(kmajor_map(&tx, d2, H, M, H, 128));
@@ -639,6 +781,7 @@ int ffn_fused_bwd_dx(int M, int FF, const void* d2, const void* d1, const void* 
   a.M = M; a.FF = FF; a.b1 = nullptr; a.b2 = nullptr; a.ln_g = nullptr; a.ln_b = nullptr; a.eps = 0.f;
   a.stat2 = nullptr; a.save_hid = 1; a.hmask = (uint2*)const_cast<void*>(hmask); a.d1 = (const bf16*)d1; a.hid_tiled = 0;
   a.p_drop = p_drop; a.key_ffn = 0; a.key_drop2 = 0;
+  a.partial = scratch; a.fix_x1 = nullptr; a.fix_d1 = (const bf16*)(d1 ? d1 : d2); a.fix_y2 = nullptr; a.fix_out = (bf16*)d3;
   return ffn_launch(true, M, FF, tx, tw1, tw2, thid, ty2, ty2, a, st);
 }
 

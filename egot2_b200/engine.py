@@ -295,6 +295,11 @@ class TranslatorEngine:
             ls.stat2 = buf(f"stat2_{i}", (M, 2), torch.float32).data_ptr()
             if self.dtype == "bf16" and H == 128 and FF % 128 == 0:     # gate bits of the fused tcgen05 FFN
                 ls.hid_mask = buf(f"hmask{i}", (FF // 64, M, 2), torch.int32).data_ptr()
+                nscr = int(L.load().egot2_ffn_scratch_bytes(M)) // 4
+                if nscr > 0:            # zeroed once; the fused FFN kernels leave it zeroed (see include/egot2.h)
+                    if "ffn_scratch" not in t:
+                        t["ffn_scratch"] = torch.zeros(nscr, device=dev, dtype=torch.float32)
+                    ls.ffn_scratch = t["ffn_scratch"].data_ptr()
             x_out = buf(f"x{i + 1}", (B, T, H), tdt)
             L.call("egot2_encoder_layer_fwd", C.byref(ld), C.byref(lp), x.data_ptr(), x_out.data_ptr(), C.byref(ls),
                    None, 0, st)

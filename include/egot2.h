@@ -172,8 +172,12 @@ typedef struct {                      /* activations kept for backward; caller-a
   void* hid_mask;                     /* optional (FF/64, B*T) x 64 bit: hid != 0 (ReLU gate x dropout keep).  Written by the
                                          fused tcgen05 FFN (bf16, H = 128, FF % 128 == 0); with it the backward runs the fused
                                          data-gradient kernel.  NULL: unfused backward from `hid`. */
+  float* ffn_scratch;                 /* optional, egot2_ffn_scratch_bytes(B*T) bytes, ALL ZERO on entry and left all zero on
+                                         exit: lets the fused FFN kernels cut the token tiles of their last, partial wave
+                                         into FF slices that meet here (fp32).  NULL: tiles are never split. */
 } egot2_layer_saved;
 
+size_t egot2_ffn_scratch_bytes(int32_t M /* B*T tokens */);
 size_t egot2_encoder_layer_workspace_bytes(const egot2_layer_desc* d, int backward);
 int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_layer_params* p, const void* x_in,
                             void* x_out, const egot2_layer_saved* s, void* workspace, size_t ws_bytes,

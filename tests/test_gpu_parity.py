@@ -328,3 +328,40 @@ def test_fused_ffn_matches_unfused_with_dropout(name, monkeypatch):
         frac_zero_a, frac_zero_b = float((a == 0).float().mean()), float((b == 0).float().mean())
         assert abs(frac_zero_a - frac_zero_b) < 2e-3, k              # same dropout pattern
         assert float((a - b).abs().max()) <= 2e-2 * scale, k
+
+
+@pytest.mark.parametrize("batch,slots", [(8, 2), (24, 4), (13, 4)])
+def test_ffn_tail_split_matches_unsplit(batch, slots, monkeypatch):
+    """The FF-split of the last partial wave (ffn_sm100.cu: tail tiles cut into FF slices that meet in an fp32 scratch,
+    finished by the fix-up kernel) against the same kernels with whole tiles, forward and backward, in training mode.
+    EGOT2_FFN_SLOTS shrinks the wave so that a few hundred tokens already have a tail (batch 13: a ragged last tile)."""
+    from egot2_b200 import synth
+    from egot2_b200.engine import TranslatorEngine
+    from oracle import translator_oracle as O
+    case = CASES["hhi3_h128_d30"]
+    sp = case.spec
+    sd = synth.make_state_dict(sp, 3)
+    feats = synth.make_features(sp, batch, case.seg_tokens, 3)
+    labels = synth.make_labels(sp, batch, case.seg_tokens, 3).cuda()
+    loss_kind, cw = _loss_kind(case)
+    monkeypatch.setenv("EGOT2_FFN_SLOTS", str(slots))
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("EGOT2_FFN_SPLIT", mode)
+        eng = TranslatorEngine(sp, "cuda:0", "bf16")
+        eng.arena.load_state_dict(sd)
+        eng.set_sinusoid(O.sinusoid_table(1000, sp.hidden))
+        gf = [feats[s.name].cuda().bfloat16() for s in sp.segments]
+        act = eng.forward(gf, training=True, seed=5, labels=labels, loss=loss_kind, class_weight=cw)
+        eng.backward(act)
+        torch.cuda.synchronize()
+        res[mode] = {k: act.t[k].float().clone() for k in ("hid0", "y2_0", "x_last", "out", "loss")}
+        res[mode]["grad"] = eng.arena.grad.clone()
+        if mode == "1":
+            assert float(act.t["ffn_scratch"].abs().max()) == 0.0          # left clean for the next launch
+    for k in res["0"]:
+        a, b = res["1"][k], res["0"][k]
+        scale = float(b.abs().max()) + 1e-12
+        assert float((a - b).abs().max()) <= 2e-2 * scale, k
+        if k not in ("grad", "loss"):            # bf16 activations: only the fp32 summation order of GEMM2 differs
+            assert float((a != b).float().mean()) < 0.05, k
