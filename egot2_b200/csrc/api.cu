@@ -525,7 +525,12 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   // Parameter-gradient work (weight-gradient GEMMs, bias column sums) runs on a side stream, forked after each producer
   // and joined before returning; the data-gradient chain stays on `st`.  Every buffer a side launch reads is written
   // once per call (d1..d5, dhid, dqkv), so the main chain never overwrites what the side stream may still be reading.
-  Side* sd = get_side(0);
+  // Three side streams: the four parameter-gradient groups total more kernel time than the data-gradient chain they hang
+  // off, so on one stream the join at the end of the layer stalled the main chain; spread out, every group finishes
+  // before the chain does.
+  Side* sd0 = get_side(0);
+  Side* sd1 = get_side(1);
+  Side* sd2 = get_side(2);
 
   // 1. through norm2: d1 = dL/dy2, and (same kernel) d2 = dropout2 mask applied to d1 = dL/d(linear2 out)
   const void* d2 = w.d1;
@@ -537,7 +542,7 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   }
   //    linear2 (side): dW2 += d2^T . hid ; db2 += colsum(d2)
   {
-    cudaStream_t ss = side_fork(st, sd, 0);
+    cudaStream_t ss = side_fork(st, sd0, 0);
     EGOT2_TRY(wgrad(dt, M, H, FF, d2, H, 0, 0, s->hid, FF, 0, 0, g->lin2_w, ss));
     EGOT2_TRY(colsum_accum(dt, M, H, d2, H, 0, 0, g->lin2_b, ss));
   }
@@ -556,9 +561,10 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   }
   // 3. linear1 (side): dW1 += dhid^T . x1 ; db1 += colsum(dhid)
   {
-    cudaStream_t ss = side_fork(st, sd, 1);
+    cudaStream_t ss = side_fork(st, sd1, 1);
     EGOT2_TRY(wgrad(dt, M, FF, H, w.dhid, FF, 0, 0, s->x1, H, 0, 0, g->lin1_w, ss));
-    EGOT2_TRY(colsum_accum(dt, M, FF, w.dhid, FF, 0, 0, g->lin1_b, ss));
+    cudaStream_t s2 = side_fork(st, sd2, 1);      // the bias sum reads dhid beside the GEMM (both mostly from L2)
+    EGOT2_TRY(colsum_accum(dt, M, FF, w.dhid, FF, 0, 0, g->lin1_b, s2));
   }
   // 4. through norm1: d4 = dL/dy1, and (same kernel) d5 = dropout1 mask applied to it = dL/d(out_proj out)
   const void* dyo = w.d4;
@@ -570,7 +576,7 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   }
   // 5. out_proj (side): dWo += dyo^T . attn ; dbo += colsum(dyo)      main: dattn = dyo . Wo  (d3 is free again)
   {
-    cudaStream_t ss = side_fork(st, sd, 2);
+    cudaStream_t ss = side_fork(st, sd2, 2);
     EGOT2_TRY(wgrad(dt, M, H, H, dyo, H, 0, 0, s->attn, H, 0, 0, g->out_proj_w, ss));
     EGOT2_TRY(colsum_accum(dt, M, H, dyo, H, 0, 0, g->out_proj_b, ss));
   }
@@ -584,16 +590,19 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
                           site_key(d->seed, SITE_ATTN, L), w.attn_ws, w.attn_ws_bytes, st));
   // 7. in_proj (side): dWin += dqkv^T . x ; dbin += colsum(dqkv)      main: dx = dqkv . Win + d4 (residual branch)
   {
-    cudaStream_t ss = side_fork(st, sd, 3);
+    cudaStream_t ss = side_fork(st, sd0, 3);
     EGOT2_TRY(wgrad(dt, M, 3 * H, H, w.dqkv, 3 * H, 0, 0, x_in, H, 0, 0, g->in_proj_w, ss));
-    EGOT2_TRY(colsum_accum(dt, M, 3 * H, w.dqkv, 3 * H, 0, 0, g->in_proj_b, ss));
+    cudaStream_t s2 = side_fork(st, sd2, 3);
+    EGOT2_TRY(colsum_accum(dt, M, 3 * H, w.dqkv, 3 * H, 0, 0, g->in_proj_b, s2));
   }
   {
     GemmArgs m; m.M = M; m.N = H; m.K = 3 * H; m.A = w.dqkv; m.lda = 3 * H; m.B = p->in_proj_w; m.ldb = H; m.trans_b = 0;
     m.C = dx_in; m.ldc = H; m.residual = w.d4; m.ldr = H; m.in_dtype = dt; m.out_dtype = dt;
     EGOT2_TRY(gemm(m, st));
   }
-  return side_join(st, sd);
+  EGOT2_TRY(side_join(st, sd0));
+  EGOT2_TRY(side_join(st, sd1));
+  return side_join(st, sd2);
 }
 
 // =============================================================================== head + loss

@@ -11,6 +11,8 @@
 //   K-major  (row-major, K contiguous; activations (M,K) / nn.Linear weights (N,K)): one TMA box {64 k, rows}
 //   MN-major (K rows, M|N contiguous; used by dX = dY.W and dW = dY^T.X):            boxes of {64 mn, 64 k}
 // gridDim.z > 1 = split-K for the weight-gradient GEMMs (K = every token of the batch): fp32 atomics into C.
+#include <stdlib.h>
+
 #include "ops.h"
 #include "sm100.cuh"
 
@@ -32,6 +34,7 @@ struct EpiArgs {
   float p_drop; uint64_t drop_key; int drop_bit_mode;
   const void* residual; int ldr;
   int accumulate; int atomic;
+  int tma_store;     // bf16 C, plain rows: the tile leaves through shared memory + TMA (coalesced) instead of per-row stores
   // grouped-K addressing for gathered MN-major operands (3-D tensor maps): 64-row k-block = kg groups x kdpad rows
   int k_grouped, kg, kdblocks;
 };
@@ -85,14 +88,26 @@ __device__ __forceinline__ void store32(bf16* p, const float (&v)[32]) {
 }
 
 template <int BN> struct TileCfg {            // stages chosen so that BN<=128 tiles fit two CTAs per SM
-  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int STAGES = BN == 128 ? 2 : (BN == 64 ? 3 : 4);
   static constexpr int MIN_CTAS = BN == 256 ? 1 : 2;
+  // bf16 output tile staged in shared memory for the TMA-store epilogue (BN <= 128 only: 128 rows x BN x 2 B)
+  static constexpr uint32_t OUT_BYTES = BN <= 128 ? 128 * BN * 2 : 0;
 };
+__device__ __forceinline__ void sts128(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Persistent over output tiles: CTA b takes tiles b, b + gridDim.x, ... (n fastest, so neighbouring CTAs share A rows in
+// L2).  The smem ring keeps running across tiles and the accumulator is double-buffered in TMEM (2 x BN columns), so the
+// TMA fill and the MMAs of tile i+1 overlap the epilogue of tile i - for the short-K GEMMs of this model (K = 128..384)
+// the per-tile fill + epilogue latency is several times the MMA time.  Split-K launches (gridDim.z > 1) give every
+// CTA exactly one tile.
 template <int BN, bool A_MN, bool B_MN, typename TO>
 __global__ void __launch_bounds__(NTHREADS, TileCfg<BN>::MIN_CTAS)
-gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const EpiArgs e,
-                  const int k_blocks_total, const int k_blocks_per_split) {
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const __grid_constant__ CUtensorMap tma_c, const EpiArgs e, const int k_blocks_total, const int k_blocks_per_split, const int tiles_n, const int num_tiles) {
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr int STAGES = TileCfg<BN>::STAGES;
@@ -100,14 +115,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024 B alignment
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + STAGES * A_BYTES;
-  const uint32_t bars = sB + STAGES * B_BYTES;                            // full[STAGES], empty[STAGES], tmem_full
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES;
-  const uint32_t tmem_slot = tmem_full + 8;
-  const uint32_t bias_off = (tmem_slot + 8 + 15u) & ~15u;        // float sbias[BN]: this tile's bias columns (broadcast reads in the epilogue)
+  const uint32_t sOut = sB + STAGES * B_BYTES;                            // [BN/64][128 rows][128 B], 128B-swizzled (TMA-store epilogue)
+  const uint32_t bars = sOut + TileCfg<BN>::OUT_BYTES;                          // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES, tmem_empty = tmem_full + 16;
+  const uint32_t tmem_slot = tmem_empty + 16;
+  const uint32_t bias_off = (tmem_slot + 8 + 15u) & ~15u;        // float sbias[2][BN]: the tile's bias columns (broadcast reads in the epilogue)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kb_begin = blockIdx.z * k_blocks_per_split;
   const int kb_end = min(k_blocks_total, kb_begin + k_blocks_per_split);
   const int nkb = kb_end - kb_begin;
@@ -116,18 +131,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (e.tma_store) tma_prefetch_desc(&tma_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
   pdl_wait();                   // everything above touched only kernel parameters, shared memory and TMEM
   float* sbias = reinterpret_cast<float*>(smem_raw + (bias_off - smem_u32(smem_raw)));
-  if (warp >= 2) {
-    const bool has_bias = e.bias != nullptr && blockIdx.z == 0;
-    for (int i = threadIdx.x - 64; i < BN; i += NTHREADS - 64)
-      sbias[i] = (has_bias && n0 + i < e.N) ? __ldg(e.bias + n0 + i) : 0.f;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -136,34 +147,38 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
-        const int kb = kb_begin + i;
-        const int k = kb * BK;
-        if (A_MN && B_MN && e.k_grouped) {
-          // token rows live in (clip, frame) groups inside a (B,T,H) tensor: one k-block = kg clips x kdpad frames,
-          // frames beyond the segment are zero-filled by TMA (they contribute nothing to dW)
-          const int grp = (kb / e.kdblocks) * e.kg, d0 = (kb % e.kdblocks) * 64;
+      int it = 0;                                                   // ring position, continuous across tiles
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+          const int kb = kb_begin + i;
+          const int k = kb * BK;
+          if (A_MN && B_MN && e.k_grouped) {
+            // token rows live in (clip, frame) groups inside a (B,T,H) tensor: one k-block = kg clips x kdpad frames,
+            // frames beyond the segment are zero-filled by TMA (they contribute nothing to dW)
+            const int grp = (kb / e.kdblocks) * e.kg, d0 = (kb % e.kdblocks) * 64;
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_3d(sA + s * A_BYTES + j * 8192, &tma_a, full0 + 8 * s, m0 + 64 * j, d0, grp);
+            for (int j = 0; j < BM / 64; ++j) tma_load_3d(sA + s * A_BYTES + j * 8192, &tma_a, full0 + 8 * s, m0 + 64 * j, d0, grp);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_3d(sB + s * B_BYTES + j * 8192, &tma_b, full0 + 8 * s, n0 + 64 * j, d0, grp);
-          continue;
-        }
-        if (!A_MN) {
-          tma_load_2d(sA + s * A_BYTES, &tma_a, full0 + 8 * s, k, m0);
-        } else {
+            for (int j = 0; j < BN / 64; ++j) tma_load_3d(sB + s * B_BYTES + j * 8192, &tma_b, full0 + 8 * s, n0 + 64 * j, d0, grp);
+            continue;
+          }
+          if (!A_MN) {
+            tma_load_2d(sA + s * A_BYTES, &tma_a, full0 + 8 * s, k, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + s * A_BYTES + j * 8192, &tma_a, full0 + 8 * s, m0 + 64 * j, k);
-        }
-        if (!B_MN) {
-          tma_load_2d(sB + s * B_BYTES, &tma_b, full0 + 8 * s, k, n0);
-        } else {
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + s * A_BYTES + j * 8192, &tma_a, full0 + 8 * s, m0 + 64 * j, k);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB + s * B_BYTES, &tma_b, full0 + 8 * s, k, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + s * B_BYTES + j * 8192, &tma_b, full0 + 8 * s, n0 + 64 * j, k);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + s * B_BYTES + j * 8192, &tma_b, full0 + 8 * s, n0 + 64 * j, k);
+          }
         }
       }
     }
@@ -171,23 +186,29 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     // ================================================================ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(tmem_empty + 8 * buf, ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator (tile lt-2)
         tc_fence_after();
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          // K-major: 16 k = 32 B inside the 128 B swizzle row; MN-major: 16 k = 16 rows of 128 B
-          const uint64_t ad = A_MN ? make_smem_desc_sw128(sA + s * A_BYTES + kk * 2048, 8192, 1024)
-                                   : make_smem_desc_sw128(sA + s * A_BYTES + kk * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc_sw128(sB + s * B_BYTES + kk * 2048, 8192, 1024)
-                                   : make_smem_desc_sw128(sB + s * B_BYTES + kk * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // K-major: 16 k = 32 B inside the 128 B swizzle row; MN-major: 16 k = 16 rows of 128 B
+            const uint64_t ad = A_MN ? make_smem_desc_sw128(sA + s * A_BYTES + kk * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(sA + s * A_BYTES + kk * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_smem_desc_sw128(sB + s * B_BYTES + kk * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(sB + s * B_BYTES + kk * 32, 16, 1024);
+            umma_bf16(tmem_base + buf * BN, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);          // smem slot reusable once these MMAs retire
         }
-        umma_commit(empty0 + 8 * s);          // smem slot reusable once these MMAs retire
+        umma_commit(tmem_full + 8 * buf);       // accumulator complete
       }
-      umma_commit(tmem_full);                 // accumulator complete
     }
   } else {
     // ================================================================ epilogue (warps 2..5)
@@ -195,103 +216,152 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     // a 128-bit vector, the one large auxiliary operand (ReLU gate or residual) is fetched while the TMEM load is
     // in flight, and there is no per-element control flow.  Edge chunks take the scalar path.
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
-    const int m = m0 + q * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const float inv_keep = e.p_drop > 0.f ? 1.f / (1.f - e.p_drop) : 1.f;
-    const bool row_ok = (m < e.M) && nkb > 0;
-    const long long crow = row_ok ? remap(m, e.c_rpg, e.c_gstride) : 0;
-    TO* __restrict__ crow_ptr = (TO*)e.C + crow * e.ldc;
     const bool first_split = blockIdx.z == 0;
     const float* bias = first_split ? e.bias : nullptr;
-    const TO* mask_row = e.mask ? (const TO*)e.mask + (long long)(row_ok ? m : 0) * e.ldm : nullptr;
-    const TO* res_row = (e.residual && first_split) ? (const TO*)e.residual + (long long)(row_ok ? m : 0) * e.ldr : nullptr;
-    const bool vec_ok = aligned16(crow_ptr) && aligned16(mask_row) && aligned16(res_row);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      const int nb = n0 + c0;
-      const bool active = row_ok && nb < e.N;
-      const bool fast = active && vec_ok && (nb + 32 <= e.N);
-      float aux[32];
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int m = m0 + q * 32 + lane;
+      float* sb = sbias + buf * BN;
+      if (bias) {
+        for (int i = threadIdx.x - 64; i < BN; i += NTHREADS - 64) sb[i] = n0 + i < e.N ? __ldg(bias + n0 + i) : 0.f;
+        named_bar_sync(1, NTHREADS - 64);
+      }
+      const bool row_ok = (m < e.M) && nkb > 0;
+      const long long crow = row_ok ? remap(m, e.c_rpg, e.c_gstride) : 0;
+      TO* __restrict__ crow_ptr = (TO*)e.C + crow * e.ldc;
+      const TO* mask_row = e.mask ? (const TO*)e.mask + (long long)(row_ok ? m : 0) * e.ldm : nullptr;
+      const TO* res_row = (e.residual && first_split) ? (const TO*)e.residual + (long long)(row_ok ? m : 0) * e.ldr : nullptr;
+      const bool vec_ok = aligned16(crow_ptr) && aligned16(mask_row) && aligned16(res_row);
       const TO* aux_row = mask_row ? mask_row : res_row;
-      if (fast && aux_row) load32(aux_row + nb, aux);
-      tmem_ld_wait();
-      if (!active) continue;
-      float v[32];
+      // the first chunk's auxiliary operand is requested BEFORE waiting for the accumulator, every later chunk's one
+      // chunk ahead: its global-load latency hides behind the MMAs / the previous chunk instead of in front of each chunk
+      float aux[32], aux_next[32];
+      const bool aux_vec = row_ok && vec_ok && aux_row != nullptr;
+      if (aux_vec && n0 + 32 <= e.N) load32(aux_row + n0, aux_next);
+      if (e.tma_store && lt > 0) {              // the previous tile's TMA store has finished reading the staged tile
+        if (warp == 2 && lane == 0) tma_store_wait_read();
+        named_bar_sync(3, NTHREADS - 64);
+      }
+      mbar_wait(tmem_full + 8 * buf, (lt >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+        const int nb = n0 + c0;
+        const bool active = row_ok && nb < e.N;
+        const bool fast = active && vec_ok && (nb + 32 <= e.N);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (fast) {
-        if (bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
+        for (int j = 0; j < 32; ++j) aux[j] = aux_next[j];
+        if (aux_vec && c0 + 32 < BN && nb + 64 <= e.N) load32(aux_row + nb + 32, aux_next);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {                    // the whole accumulator of this tile is in registers: release the buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
         }
-        if (e.relu) {
+        if (!active) continue;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (mask_row) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (fast) {
+          if (bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = aux[j] > 0.f ? v[j] * e.mask_scale : 0.f;
-        }
-        if (e.p_drop > 0.f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key, (uint64_t)m * e.N + nb + j, e.p_drop, inv_keep, e.drop_bit_mode != 0);
-        }
-        if (res_row) {
-          if (mask_row) load32(res_row + nb, aux);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += aux[j];
-        }
-        if (e.accumulate) {
-          if constexpr (sizeof(TO) == 4) {
-            float* dst = (float*)crow_ptr + nb;
-            if (e.atomic) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              float old[32];
-              load32(dst, old);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += old[j];
-              store32(dst, v);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + j);
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
           }
-        } else {
-          store32(crow_ptr + nb, v);
-        }
-      } else {
+          if (e.relu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = nb + j;
-          if (n >= e.N) continue;
-          float x = v[j];
-          if (bias) x += sbias[c0 + j];
-          if (e.relu) x = fmaxf(x, 0.f);
-          if (mask_row) x = to_f32(mask_row[n]) > 0.f ? x * e.mask_scale : 0.f;
-          if (e.p_drop > 0.f) x *= drop_scale(e.drop_key, (uint64_t)m * e.N + n, e.p_drop, inv_keep, e.drop_bit_mode != 0);
-          if (res_row) x += to_f32(res_row[n]);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (mask_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = aux[j] > 0.f ? v[j] * e.mask_scale : 0.f;
+          }
+          if (e.p_drop > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key, (uint64_t)m * e.N + nb + j, e.p_drop, inv_keep, e.drop_bit_mode != 0);
+          }
+          if (res_row) {
+            if (mask_row) load32(res_row + nb, aux);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += aux[j];
+          }
           if (e.accumulate) {
             if constexpr (sizeof(TO) == 4) {
-              if (e.atomic) atomicAdd((float*)crow_ptr + n, x);
-              else ((float*)crow_ptr)[n] += x;
+              float* dst = (float*)crow_ptr + nb;
+              if (e.atomic) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+                float old[32];
+                load32(dst, old);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += old[j];
+                store32(dst, v);
+              }
+            }
+          } else if (BN <= 128 && sizeof(TO) == 2 && e.tma_store) {
+            // this thread's 32 columns = 4 x 16 B chunks of its 128 B swizzle row in the staged tile
+            const int r = q * 32 + lane;
+            const uint32_t srow = sOut + (uint32_t)(c0 >> 6) * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+                w[k] = *reinterpret_cast<uint32_t*>(&t);
+              }
+              sts128(srow + (uint32_t)(((((c0 & 63) >> 3) + j) ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
             }
           } else {
-            crow_ptr[n] = from_f32<TO>(x);
+            store32(crow_ptr + nb, v);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (n >= e.N) continue;
+            float x = v[j];
+            if (bias) x += sb[c0 + j];
+            if (e.relu) x = fmaxf(x, 0.f);
+            if (mask_row) x = to_f32(mask_row[n]) > 0.f ? x * e.mask_scale : 0.f;
+            if (e.p_drop > 0.f) x *= drop_scale(e.drop_key, (uint64_t)m * e.N + n, e.p_drop, inv_keep, e.drop_bit_mode != 0);
+            if (res_row) x += to_f32(res_row[n]);
+            if (e.accumulate) {
+              if constexpr (sizeof(TO) == 4) {
+                if (e.atomic) atomicAdd((float*)crow_ptr + n, x);
+                else ((float*)crow_ptr)[n] += x;
+              }
+            } else {
+              crow_ptr[n] = from_f32<TO>(x);
+            }
           }
         }
       }
+      if (BN <= 128 && e.tma_store) {
+        fence_proxy_async();                      // the generic-proxy smem writes become visible to the TMA engine
+        named_bar_sync(2, NTHREADS - 64);
+        if (warp == 2 && lane == 0) {
+#pragma unroll
+          for (int h = 0; h < BN / 64; ++h) tma_store_2d(&tma_c, sOut + h * 16384, n0 + h * 64, m0);
+          tma_store_commit();
+        }
+      }
     }
+    if (e.tma_store && warp == 2 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -347,11 +417,12 @@ int make_map3(CUtensorMap* map, const void* base, int inner, int rpg, int groups
 }
 
 struct KGroup { int on = 0, g = 1, dblocks = 1, kb_total = 0; };
+static bool host_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int BN, bool A_MN, bool B_MN, typename TO>
 int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, const KGroup& kg, cudaStream_t st) {
   constexpr int STAGES = TileCfg<BN>::STAGES;
-  constexpr size_t smem = 1024 + STAGES * (BM * BK * 2 + BN * BK * 2) + 16 * STAGES + 64 + BN * 4;
+  constexpr size_t smem = 1024 + STAGES * (BM * BK * 2 + BN * BK * 2) + TileCfg<BN>::OUT_BYTES + 16 * STAGES + 96 + 2 * BN * 4;
   static bool attr_set = false;
   auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, TO>;
   if (!attr_set) {
@@ -364,16 +435,34 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   e.p_drop = a.p_drop; e.drop_key = a.drop_key; e.drop_bit_mode = a.drop_bit_mode; e.residual = a.residual; e.ldr = a.ldr;
   e.accumulate = a.accumulate; e.atomic = a.split_k > 1;
   e.k_grouped = kg.on; e.kg = kg.g; e.kdblocks = kg.dblocks;
+  // TMA-store epilogue: bf16 output in plain row order, whole 32-column chunks, every per-row operand 16 B aligned (the
+  // vector path then never falls back to direct stores that would race with the tile store)
+  CUtensorMap mc = ma;
+  e.tma_store = 0;
+  if (BN <= 128 && sizeof(TO) == 2 && !a.accumulate && a.c_rpg == 0 && a.N % 32 == 0 && a.ldc % 8 == 0 && host_al16(a.C) &&
+      (!a.mask || (host_al16(a.mask) && a.ldm % 8 == 0)) && (!a.residual || (host_al16(a.residual) && a.ldr % 8 == 0)) &&
+      !(getenv("EGOT2_GEMM_TMASTORE") && getenv("EGOT2_GEMM_TMASTORE")[0] == '0')) {
+    EGOT2_TRY(make_map(&mc, a.C, a.N, a.M, a.ldc, 64, 128));
+    e.tma_store = 1;
+  }
   const int kb_total = kg.on ? kg.kb_total : (a.K + BK - 1) / BK;
   int splits = a.split_k < 1 ? 1 : a.split_k;
   if (splits > kb_total) splits = kb_total;
   const int kb_per = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per - 1) / kb_per;
   e.atomic = splits > 1;
-  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, splits);
+  const int tiles_n = (a.N + BN - 1) / BN, num_tiles = tiles_n * ((a.M + BM - 1) / BM);
+  // persistent CTAs: as many as are resident at once, evened out so that every CTA walks the same number of tiles
+  int ctas = num_tiles;
+  if (splits == 1) {
+    const int slots = sm_count() * TileCfg<BN>::MIN_CTAS;
+    const int rounds = (num_tiles + slots - 1) / slots;
+    ctas = (num_tiles + rounds - 1) / rounds;
+  }
+  dim3 grid(ctas, 1, splits);
   ProfScope prof(st, "gemm_sm100<bn%d,%s%s,%s> M%d N%d K%d sk%d%s", BN, A_MN ? "mn" : "k", B_MN ? "mn" : "k",
                  sizeof(TO) == 4 ? "f32" : "bf16", a.M, a.N, a.K, splits, a.mask ? " +mask" : (a.residual ? " +res" : ""));
-  ::egot2::launch(kern, grid, dim3(NTHREADS), smem, st, ma, mb, e, kb_total, kb_per);
+  ::egot2::launch(kern, grid, dim3(NTHREADS), smem, st, ma, mb, mc, e, kb_total, kb_per, tiles_n, num_tiles);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
