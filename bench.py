@@ -407,6 +407,10 @@ def launcher_cost(tag: str, es: int):
         M, FF = ints(r"M(\d+) H128 FF(\d+)")
         H = 128          # x1 in, W1+W2, hid saved for backward, y2 + x_out out
         return 4.0 * M * H * FF, (M * H + 2 * H * FF + M * FF + 2 * M * H) * es
+    if tag.startswith("ffn_bwd_dx_sm100"):
+        M, FF = ints(r"M(\d+) H128 FF(\d+)")
+        H = 128          # dhid = gate(d2 . W2), d3 = dhid . W1 + d1; reads d2, d1, gate bits, W1+W2; writes dhid and d3
+        return 4.0 * M * H * FF, (3 * M * H + 2 * H * FF + M * FF) * es + M * FF // 8
     if tag.startswith("ffn_bwd_sm100"):
         M, FF = ints(r"M(\d+) H128 FF(\d+)")
         H = 128          # dX GEMMs (2) + dW GEMMs (2); reads d2, x1, hid, W1, W2; writes d3 + fp32 dW1/dW2

@@ -166,14 +166,29 @@ Side* get_side(int idx) {
   }
   return state == 1 ? &sides[idx] : nullptr;
 }
+}  // namespace
+int launch_priority(cudaStream_t st) {
+  static int state = 0, lo = 0, hi = 0;      // 0 untried, 1 on, -1 off
+  if (state == 0) {
+    state = 1;
+    if (env_is("EGOT2_PRIO", "0") || cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess || lo == hi) state = -1;
+  }
+  if (state != 1) return INT_MIN;
+  for (int i = 0; i < 3; ++i) {
+    Side* sd = get_side(i);
+    if (sd && sd->s == st) return lo;          // numerically largest = least urgent
+  }
+  return hi;
+}
+namespace {
 // side stream `sd` may start once everything enqueued on `main` so far has finished; returns the stream to launch on
 cudaStream_t side_fork(cudaStream_t main, Side* sd, int k) {
-  if (!sd) return main;
+  if (!sd || prof_enabled()) return main;      // launcher profiling: one stream, so that every launcher is timed alone
   if (cudaEventRecord(sd->fork[k], main) != cudaSuccess || cudaStreamWaitEvent(sd->s, sd->fork[k], 0) != cudaSuccess) return main;
   return sd->s;
 }
 int side_join(cudaStream_t main, Side* sd) {
-  if (!sd) return 0;
+  if (!sd || prof_enabled()) return 0;
   EGOT2_CUDA(cudaEventRecord(sd->join, sd->s));
   EGOT2_CUDA(cudaStreamWaitEvent(main, sd->join, 0));
   return 0;

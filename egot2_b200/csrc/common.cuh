@@ -3,6 +3,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -56,14 +57,28 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #define EGOT2_PDL_ENTER() do { ::egot2::pdl_launch_dependents(); ::egot2::pdl_wait(); } while (0)
 bool pdl_enabled();
+// Launch priority: kernels on the caller's stream (the data-gradient / forward chain, i.e. the critical path) outrank the
+// library's side-stream kernels (parameter gradients), so when both have CTAs waiting for an SM the chain goes first and
+// the side work fills what is left.  Returns INT_MIN when priorities are disabled (EGOT2_PRIO=0) or unavailable.
+int launch_priority(cudaStream_t st);
 template <typename... Params, typename... Args>
 inline void launch(void (*kern)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  const int prio = launch_priority(st);
+  if (prio != INT_MIN) {
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = prio;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
   (void)cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);      // errors surface through EGOT2_LAUNCH_CHECK()
 }
 
