@@ -13,7 +13,8 @@ MAX_GROUPS = 4
 F32, BF16 = 0, 1
 LOSS_NONE, LOSS_CE, LOSS_BCE_SIGMOID, LOSS_CE_GROUPS = 0, 1, 2, 3
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libegot2.so")
+# EGOT2_LIB: an alternative build of the same library (instrumented / experimental variants for tools/); never a fallback
+_LIB_PATH = os.environ.get("EGOT2_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libegot2.so")
 
 i32, u64, f32, vp, sz = C.c_int32, C.c_uint64, C.c_float, C.c_void_p, C.c_size_t
 

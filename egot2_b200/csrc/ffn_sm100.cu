@@ -24,7 +24,7 @@
 //               MMAs - tools/ubench/umma_issue.cu - so one stream's synchronisation overlaps the other stream's MMAs)
 //   warps 2-9   epilogue (both CTAs): two warps per TMEM lane quadrant, 64 hidden columns each
 //   warp 10     TMA store of the hidden tile (both CTAs)
-// TMEM (per CTA): acc1 double-buffered (2 x 128 columns) + acc2 (128 columns).
+// TMEM (per CTA): acc1 double-buffered (AB x 128 columns) + acc2 (128 columns).
 // Barriers that the leader's MMA threads wait on (operands of BOTH CTAs ready, accumulators drained by BOTH epilogues)
 // live in the leader and receive remote arrivals; completion barriers are signalled in both CTAs by multicast commits.
 #include <stdlib.h>
@@ -41,9 +41,23 @@ namespace {
 constexpr int H = 128;
 constexpr int BM = 128;                    // tokens per CTA (256 per pair)
 constexpr int FC = 128;                    // hidden columns per chunk
-constexpr int R1 = 4, R2 = 3;              // W1 / W2 ring stages (16 KB: this CTA's 64 rows x 128 k, two 8 KB k-halves)
+// Pipeline depths (compile-time knobs for experiments).  Measured on B200 (HHI b256): 2/2/4/3, 3/2/4/3 and 3/3/3/2 (acc1
+// buffers / hidden buffers / W1 ring / W2 ring) all run the forward in 53-55 us - the chunk period (~2.3k cycles for 16
+// M=256 x N=128 x K=16 MMAs) is not set by the depth of the GEMM1 -> epilogue -> GEMM2 loop but by SHARED-MEMORY BANDWIDTH:
+// per chunk and CTA the SS-mode MMAs read 96 KB of operands (x tile 32, hidden tile 32, weight halves 32), the epilogue
+// writes the 32 KB hidden tile, TMA reads it back for the saved activation and writes 32 KB of weight stages: 192 KB at
+// 128 B/clk = 1.5k cycles before bank conflicts.  Going further needs operands in TMEM (tcgen05 TS mode), not more stages.
+#ifndef EGOT2_FFN_AB
+#define EGOT2_FFN_AB 2
+#define EGOT2_FFN_HB 2
+#define EGOT2_FFN_R1 4
+#define EGOT2_FFN_R2 3
+#endif
+constexpr int R1 = EGOT2_FFN_R1, R2 = EGOT2_FFN_R2;   // W1 / W2 ring stages (16 KB: this CTA's 64 rows x 128 k, two 8 KB k-halves)
 constexpr int RING = R1 + R2;
-constexpr int HB = 2;                      // hidden-tile buffers in shared memory
+constexpr int HB = EGOT2_FFN_HB;           // hidden-tile buffers in shared memory
+constexpr int AB = EGOT2_FFN_AB;           // acc1 buffers in TMEM (acc2 follows them)
+static_assert(AB * 128 + 128 <= 512, "TMEM: acc1 buffers + acc2 must fit 512 columns");
 constexpr int NTHREADS = 384;
 constexpr uint32_t TILE = 128 * 128 * 2;   // one 128x128 bf16 operand tile = two 16 KB K-halves
 constexpr uint32_t HALF = 16384;
@@ -115,10 +129,10 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const uint32_t bars = sHid + HB * TILE;
   // local barriers
   const uint32_t x_full = bars, r1_empty = x_full + 8, r2_empty = r1_empty + 8 * R1, a1_full = r2_empty + 8 * R2,
-                 hl_full = a1_full + 16, h_empty = hl_full + 8 * HB, hs_empty = h_empty + 8 * HB, a2_full = hs_empty + 8 * HB;
+                 hl_full = a1_full + 8 * AB, h_empty = hl_full + 8 * HB, hs_empty = h_empty + 8 * HB, a2_full = hs_empty + 8 * HB;
   // barriers used in the leader only (arrivals from both CTAs)
   const uint32_t x_pair = a2_full + 8, r1_full = x_pair + 8, r2_full = r1_full + 8 * R1, a1_empty = r2_full + 8 * R2,
-                 h_full = a1_empty + 16, tmem_slot = h_full + 8 * HB;
+                 h_full = a1_empty + 8 * AB, tmem_slot = h_full + 8 * HB;
   const uint32_t red_off = (tmem_slot + 8 + 15u) & ~15u;   // float red[2][128] for the LayerNorm row statistics (16 B aligned)
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));   // generic pointer to `base`
   float* red = reinterpret_cast<float*>(gen + (red_off - base));
@@ -158,7 +172,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     mbar_init(x_full, 1); mbar_init(x_pair, 2); mbar_init(a2_full, 1);
     for (int s = 0; s < R1; ++s) { mbar_init(r1_full + 8 * s, 1); mbar_init(r1_empty + 8 * s, 1); }
     for (int s = 0; s < R2; ++s) { mbar_init(r2_full + 8 * s, 1); mbar_init(r2_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(a1_full + 8 * s, 1); mbar_init(a1_empty + 8 * s, 16); }
+    for (int s = 0; s < AB; ++s) { mbar_init(a1_full + 8 * s, 1); mbar_init(a1_empty + 8 * s, 16); }
     for (int s = 0; s < HB; ++s) {
       mbar_init(h_full + 8 * s, 16); mbar_init(hl_full + 8 * s, 8); mbar_init(h_empty + 8 * s, 1); mbar_init(hs_empty + 8 * s, 1);
     }
@@ -176,7 +190,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   cluster_sync_all();                         // both CTAs' barriers are initialised before anything targets them remotely
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t acc2 = tmem + 256;
+  const uint32_t acc2 = tmem + AB * 128;
   if (threadIdx.x == 64) TR(60, 1);
 
   if (warp == 0) {
@@ -230,8 +244,8 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 128, false, BWD);
         mbar_wait(x_pair, 0);
         for (int c = 0; c < NC; ++c) {
-          const int bsel = c & 1, s = c % R1;
-          mbar_wait(a1_empty + 8 * bsel, ((c >> 1) & 1) ^ 1);
+          const int bsel = c % AB, s = c % R1;
+          mbar_wait(a1_empty + 8 * bsel, ((c / AB) & 1) ^ 1);
           TR(c, 3);
           mbar_wait(r1_full + 8 * s, (c / R1) & 1);
           TR(c, 2);
@@ -303,13 +317,13 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     uint2 gate_next = make_uint2(0u, 0u);
     if (BWD && row_ok) gate_next = __ldg(a.hmask + (size_t)(c_begin * 2 + ch) * a.M + m);
     for (int c = 0; c < NC; ++c) {
-      const int bsel = c & 1;
+      const int bsel = c % AB;
       const int hb = c % HB;
       const uint2 gate_cur = gate_next;
       const int cg = c_begin + c;
       if (BWD && row_ok && c + 1 < NC) gate_next = __ldg(a.hmask + (size_t)((cg + 1) * 2 + ch) * a.M + m);
       const uint32_t hrow = sHid + hb * TILE + ch * HALF + (uint32_t)r * 128;
-      mbar_wait(a1_full + 8 * bsel, (c >> 1) & 1);
+      mbar_wait(a1_full + 8 * bsel, (c / AB) & 1);
       if (threadIdx.x == 64) TR(c, 6);
       tc_fence_after();
       uint32_t packed[32];
@@ -722,7 +736,8 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
 #ifdef EGOT2_FFN_TRACE
   {
     static int printed = 0;
-    if (printed++ == 3) {
+    static const int trace_at = getenv("EGOT2_FFN_TRACE_AT") ? atoi(getenv("EGOT2_FFN_TRACE_AT")) : 3;
+    if (printed++ == trace_at) {
       static long long h[1024 + 4 * 1024];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, dtrace, sizeof(h), cudaMemcpyDeviceToHost);

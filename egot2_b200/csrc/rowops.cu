@@ -444,17 +444,31 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const LayerNormArgs a) 
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const int c = (s * V::LPR + cl) * 8 + i; g[s][i] = a.g[c]; b[s][i] = a.b[c]; }
   const int rows_per_iter = gridDim.x * 8 * V::RPW;
-  // the loop bound is warp-uniform (row0); a warp's last sub-row may be past the end: it computes on zeros and stores nothing
-  for (int row0 = (blockIdx.x * 8 + warp) * V::RPW; row0 < a.rows; row0 += rows_per_iter) {
+  // the loop bound is warp-uniform (row0); a warp's last sub-row may be past the end: it computes on zeros and stores nothing.
+  // The next iteration's row is requested before this one is processed (a warp only walks a few rows; without the
+  // prefetch every iteration starts with an exposed global-load round trip).
+  int row0 = (blockIdx.x * 8 + warp) * V::RPW;
+  uint4 xq[V::SEG];
+  if (row0 < a.rows) {
+    const bf16* x = (const bf16*)a.x + (size_t)(row0 + sub < a.rows ? row0 + sub : row0) * HH;
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s) xq[s] = __ldg(reinterpret_cast<const uint4*>(x) + s * V::LPR + cl);
+  }
+  for (; row0 < a.rows; row0 += rows_per_iter) {
     const int row = row0 + sub;
     const bool valid = row < a.rows;
-    const bf16* x = (const bf16*)a.x + (size_t)(valid ? row : row0) * HH;
     float v[V::SEG][8], sum = 0.f;
 #pragma unroll
     for (int s = 0; s < V::SEG; ++s) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x) + s * V::LPR + cl), v[s]);
+      unpack8(xq[s], v[s]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sum += v[s][i];
+    }
+    if (row0 + rows_per_iter < a.rows) {
+      const int rn = row0 + rows_per_iter;
+      const bf16* x = (const bf16*)a.x + (size_t)(rn + sub < a.rows ? rn + sub : rn) * HH;
+#pragma unroll
+      for (int s = 0; s < V::SEG; ++s) xq[s] = __ldg(reinterpret_cast<const uint4*>(x) + s * V::LPR + cl);
     }
     const float mean = row_sum<V::LPR>(sum) * (1.f / HH);
     float q = 0.f;
@@ -502,19 +516,42 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
     for (int i = 0; i < 8; ++i) { g[s][i] = a.g[(s * V::LPR + cl) * 8 + i]; dg[s][i] = 0.f; db[s][i] = 0.f; }
   const int rows_per_iter = gridDim.x * 8 * V::RPW;
   // warp-uniform loop bound (row0): a sub-row past the end reads row0 again and contributes nothing
-  for (int row0 = (blockIdx.x * 8 + warp) * V::RPW; row0 < a.rows; row0 += rows_per_iter) {
+  // x, dy and the row statistics of the NEXT iteration are requested before this one is processed (see ln_fwd_vec_kernel)
+  int row0 = (blockIdx.x * 8 + warp) * V::RPW;
+  uint4 xq[V::SEG], dq[V::SEG];
+  float2 stq = make_float2(0.f, 0.f);
+  if (row0 < a.rows) {
+    const size_t rr = row0 + sub < a.rows ? row0 + sub : row0;
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s) {
+      xq[s] = __ldg(reinterpret_cast<const uint4*>((const bf16*)a.x + rr * HH) + s * V::LPR + cl);
+      dq[s] = __ldg(reinterpret_cast<const uint4*>((const bf16*)a.dy + rr * HH) + s * V::LPR + cl);
+    }
+    stq = __ldg(reinterpret_cast<const float2*>(a.stat) + rr);
+  }
+  for (; row0 < a.rows; row0 += rows_per_iter) {
     const int row = row0 + sub;
     const bool valid = row < a.rows;
-    const size_t rr = valid ? row : row0;
-    const uint4* xp = reinterpret_cast<const uint4*>((const bf16*)a.x + rr * HH);
-    const uint4* dyp = reinterpret_cast<const uint4*>((const bf16*)a.dy + rr * HH);
-    const float mean = a.stat[2 * rr], rstd = a.stat[2 * rr + 1];
+    const float mean = stq.x, rstd = stq.y;
+    uint4 xc[V::SEG], dc[V::SEG];
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s) { xc[s] = xq[s]; dc[s] = dq[s]; }
+    if (row0 + rows_per_iter < a.rows) {
+      const int rn = row0 + rows_per_iter;
+      const size_t rr = rn + sub < a.rows ? rn + sub : rn;
+#pragma unroll
+      for (int s = 0; s < V::SEG; ++s) {
+        xq[s] = __ldg(reinterpret_cast<const uint4*>((const bf16*)a.x + rr * HH) + s * V::LPR + cl);
+        dq[s] = __ldg(reinterpret_cast<const uint4*>((const bf16*)a.dy + rr * HH) + s * V::LPR + cl);
+      }
+      stq = __ldg(reinterpret_cast<const float2*>(a.stat) + rr);
+    }
     float xh[V::SEG][8], dyg[V::SEG][8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int s = 0; s < V::SEG; ++s) {
       float xv[8], d[8];
-      unpack8(__ldg(xp + s * V::LPR + cl), xv);
-      unpack8(__ldg(dyp + s * V::LPR + cl), d);
+      unpack8(xc[s], xv);
+      unpack8(dc[s], d);
       const int c0 = (s * V::LPR + cl) * 8;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -584,7 +621,9 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
 template <int HH> int ln_fwd_vec_launch(const LayerNormArgs& a, cudaStream_t st) {
   const int rows_per_cta = 8 * LnVec<HH>::RPW;
   int grid = (a.rows + rows_per_cta - 1) / rows_per_cta;
-  const int cap = sm_count() * 8;
+  static int occ = 0;                         // resident CTAs per SM: the grid is ONE wave of them (grid-stride loop inside)
+  if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_fwd_vec_kernel<HH>, 256, 0) != cudaSuccess || occ < 1)) occ = 4;
+  const int cap = sm_count() * occ;
   if (grid > cap) grid = cap;
   ProfScope prof(st, "ln_fwd rows%d H%d", a.rows, a.H);
   launch(ln_fwd_vec_kernel<HH>, dim3(grid), dim3(256), 0, st, a);
@@ -594,7 +633,12 @@ template <int HH> int ln_fwd_vec_launch(const LayerNormArgs& a, cudaStream_t st)
 template <int HH> int ln_bwd_vec_launch(const LayerNormBwdArgs& a, cudaStream_t st) {
   const int rows_per_cta = 8 * LnVec<HH>::RPW;
   int grid = (a.rows + rows_per_cta - 1) / rows_per_cta;
-  const int cap = sm_count() * 4;             // every CTA ends with 2H global atomics on the same addresses
+  static int occ = 0;                         // one wave of resident CTAs, at most 4 per SM: every CTA ends with 2H global
+  if (occ == 0) {                             // atomics on the same addresses
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_vec_kernel<HH>, 256, 0) != cudaSuccess || occ < 1) occ = 2;
+    if (occ > 4) occ = 4;
+  }
+  const int cap = sm_count() * occ;
   if (grid > cap) grid = cap;
   ProfScope prof(st, "ln_bwd rows%d H%d", a.rows, a.H);
   launch(ln_bwd_vec_kernel<HH>, dim3(grid), dim3(256), 0, st, a);
