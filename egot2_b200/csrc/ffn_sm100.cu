@@ -57,7 +57,16 @@ constexpr int R1 = EGOT2_FFN_R1, R2 = EGOT2_FFN_R2;   // W1 / W2 ring stages (16
 constexpr int RING = R1 + R2;
 constexpr int HB = EGOT2_FFN_HB;           // hidden-tile buffers in shared memory
 constexpr int AB = EGOT2_FFN_AB;           // acc1 buffers in TMEM (acc2 follows them)
-static_assert(AB * 128 + 128 <= 512, "TMEM: acc1 buffers + acc2 must fit 512 columns");
+// EGOT2_FFN_TS=1: GEMM1's A operand (the x1 / d2 token tile, the same for every chunk) lives in TENSOR MEMORY - the epilogue
+// warps copy it there once per tile (64 columns of packed bf16 pairs, tcgen05.st) and the per-chunk MMAs take A from TMEM
+// (tcgen05.mma TS form) instead of re-reading 32 KB of shared memory.  Parity-green on B200 but no faster (53.4 vs 52.9 us
+// forward), so the SS form stays the default; kept as the starting point for moving the hidden tile to TMEM as well.
+#ifndef EGOT2_FFN_TS
+#define EGOT2_FFN_TS 0
+#endif
+constexpr bool TS = EGOT2_FFN_TS != 0;
+constexpr int XB = AB * 128 + 128;         // TMEM column of the A tile (after acc1 buffers and acc2)
+static_assert(AB * 128 + 128 + (TS ? 64 : 0) <= 512, "TMEM: acc1 buffers + acc2 (+ A tile) must fit 512 columns");
 constexpr int NTHREADS = 384;
 constexpr uint32_t TILE = 128 * 128 * 2;   // one 128x128 bf16 operand tile = two 16 KB K-halves
 constexpr uint32_t HALF = 16384;
@@ -132,7 +141,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                  hl_full = a1_full + 8 * AB, h_empty = hl_full + 8 * HB, hs_empty = h_empty + 8 * HB, a2_full = hs_empty + 8 * HB;
   // barriers used in the leader only (arrivals from both CTAs)
   const uint32_t x_pair = a2_full + 8, r1_full = x_pair + 8, r2_full = r1_full + 8 * R1, a1_empty = r2_full + 8 * R2,
-                 h_full = a1_empty + 8 * AB, tmem_slot = h_full + 8 * HB;
+                 h_full = a1_empty + 8 * AB, xt_full = h_full + 8 * HB, tmem_slot = xt_full + 8;
   const uint32_t red_off = (tmem_slot + 8 + 15u) & ~15u;   // float red[2][128] for the LayerNorm row statistics (16 B aligned)
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));   // generic pointer to `base`
   float* red = reinterpret_cast<float*>(gen + (red_off - base));
@@ -169,7 +178,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2);
     tma_prefetch_desc(&tm_hid); tma_prefetch_desc(&tm_y2); tma_prefetch_desc(&tm_out);
-    mbar_init(x_full, 1); mbar_init(x_pair, 2); mbar_init(a2_full, 1);
+    mbar_init(x_full, 1); mbar_init(x_pair, 2); mbar_init(a2_full, 1); mbar_init(xt_full, 16);
     for (int s = 0; s < R1; ++s) { mbar_init(r1_full + 8 * s, 1); mbar_init(r1_empty + 8 * s, 1); }
     for (int s = 0; s < R2; ++s) { mbar_init(r2_full + 8 * s, 1); mbar_init(r2_empty + 8 * s, 1); }
     for (int s = 0; s < AB; ++s) { mbar_init(a1_full + 8 * s, 1); mbar_init(a1_empty + 8 * s, 16); }
@@ -243,6 +252,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       if (leader) {
         constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 128, false, BWD);
         mbar_wait(x_pair, 0);
+        if (TS) { mbar_wait(xt_full, 0); tc_fence_after(); }      // both CTAs' A tiles are in tensor memory
         for (int c = 0; c < NC; ++c) {
           const int bsel = c % AB, s = c % R1;
           mbar_wait(a1_empty + 8 * bsel, ((c / AB) & 1) ^ 1);
@@ -251,8 +261,10 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           TR(c, 2);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16_cg2(tmem + bsel * 128, kdesc(sX, kk), wdesc<BWD>(sW1 + s * STAGE, kk), idesc, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk) {
+            if (TS) umma_bf16_cg2_ts(tmem + bsel * 128, tmem + XB + kk * 8, wdesc<BWD>(sW1 + s * STAGE, kk), idesc, kk > 0 ? 1u : 0u);
+            else umma_bf16_cg2(tmem + bsel * 128, kdesc(sX, kk), wdesc<BWD>(sW1 + s * STAGE, kk), idesc, kk > 0 ? 1u : 0u);
+          }
           umma_commit_cg2(r1_empty + 8 * s, 3);       // stage reusable (both CTAs) once these MMAs retire
           umma_commit_cg2(a1_full + 8 * bsel, 3);
         }
@@ -314,6 +326,21 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t a1_empty_ldr = mapa(a1_empty, 0), h_full_ldr = mapa(h_full, 0);
     // backward: the ReLU/dropout gate bits of chunk c+1 are fetched while chunk c is processed (a dependent global
     // load in front of every chunk's arithmetic was ~1 us of exposed latency per chunk)
+    if (TS) {
+      // this thread's half row of the A tile (64 bf16 = 32 packed words, k ascending) from the swizzled smem tile into TMEM
+      mbar_wait(x_full, 0);
+      uint32_t xw[32];
+      const uint32_t xr = sX + ch * HALF + (uint32_t)r * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(xw[4 * j]), "=r"(xw[4 * j + 1]), "=r"(xw[4 * j + 2]), "=r"(xw[4 * j + 3]) : "r"(xr + (uint32_t)((j ^ (r & 7)) << 4)));
+      tmem_st_32x32(tmem + lane_addr + XB + ch * 32, xw);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(xt_full, 0));
+    }
     uint2 gate_next = make_uint2(0u, 0u);
     if (BWD && row_ok) gate_next = __ldg(a.hmask + (size_t)(c_begin * 2 + ch) * a.M + m);
     for (int c = 0; c < NC; ++c) {
