@@ -341,8 +341,14 @@ __global__ void zero_kernel(float* p, size_t n) {
 
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                            float bc1, float bc2_sqrt, float gscale, bf16* __restrict__ shadow, int zero_grad) {
+                            float bc1, float bc2_sqrt, float gscale, bf16* __restrict__ shadow, int zero_grad,
+                            const int32_t* __restrict__ step_dev) {
   EGOT2_PDL_ENTER();
+  if (step_dev) {            // step count kept on the device (whole-step CUDA graphs): bias corrections computed here
+    const float t = (float)*step_dev;
+    bc1 = 1.f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float grad = g[i] * gscale;
     const float w = p[i];
@@ -878,14 +884,14 @@ extern "C" int egot2_cast_bf16_to_f32(const void* src, float* dst, size_t n, voi
 
 static int adam_launch(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                        float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* shadow,
-                       int zero_grad, void* stream) {
-  EGOT2_CHECK(step >= 1, "adam: step must be >= 1");
+                       int zero_grad, void* stream, const int32_t* step_dev = nullptr) {
+  EGOT2_CHECK(step >= 1 || step_dev, "adam: step must be >= 1");
   if (n == 0) return 0;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   ProfScope prof((cudaStream_t)stream, "adam n%zu", n);
   launch(adam_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
-         beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, (bf16*)shadow, zero_grad);
+         beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, (bf16*)shadow, zero_grad, step_dev);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -900,6 +906,15 @@ extern "C" int egot2_adam_step_fused(float* param, float* grad, float* exp_avg, 
                                      float grad_scale, void* shadow_bf16, int32_t zero_grad, void* stream) {
   return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, shadow_bf16,
                      zero_grad, stream);
+}
+
+extern "C" int egot2_adam_step_fused_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                                         float beta1, float beta2, float eps, float weight_decay,
+                                         const int32_t* step_dev, float grad_scale, void* shadow_bf16, int32_t zero_grad,
+                                         void* stream) {
+  EGOT2_CHECK(step_dev != nullptr, "adam: step_dev is null");
+  return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, 1, grad_scale, shadow_bf16,
+                     zero_grad, stream, step_dev);
 }
 
 extern "C" int egot2_hhi_tok_table_fwd(const float* task_embed, const float* pe, int32_t pe_len, int32_t n_seg,

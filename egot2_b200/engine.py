@@ -596,7 +596,8 @@ class TranslatorEngine:
 
     # ------------------------------------------------------------------ fused optimizer
     def adam_step(self, state: Dict[str, torch.Tensor], step: int, lr: float = 5e-4, betas=(0.9, 0.999),
-                  eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0, fused: bool = False):
+                  eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0, fused: bool = False,
+                  step_dev: Optional[torch.Tensor] = None):
         """torch.optim.Adam over the whole arena in one launch (HHI/tasks/ttm/video_task.py:64-66: lr 5e-4).
         fused: the same launch also writes the bf16 shadow of the updated parameters (bf16 engines) and clears the
         gradient arena, so the next step needs neither the cast launch nor a fill (callers then pass
@@ -610,9 +611,14 @@ class TranslatorEngine:
                 if self.arena.shadow is None:
                     self.arena.refresh_shadow()
                 shadow = self.arena.shadow.data_ptr()
-            L.call("egot2_adam_step_fused", self.arena.param.data_ptr(), self.arena.grad.data_ptr(), state["m"].data_ptr(),
-                   state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps, weight_decay, int(step),
-                   float(grad_scale), shadow, 1, _stream())
+            if step_dev is not None:        # step count read on the device (graph-resident update)
+                L.call("egot2_adam_step_fused_dev", self.arena.param.data_ptr(), self.arena.grad.data_ptr(),
+                       state["m"].data_ptr(), state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps,
+                       weight_decay, step_dev.data_ptr(), float(grad_scale), shadow, 1, _stream())
+            else:
+                L.call("egot2_adam_step_fused", self.arena.param.data_ptr(), self.arena.grad.data_ptr(),
+                       state["m"].data_ptr(), state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps,
+                       weight_decay, int(step), float(grad_scale), shadow, 1, _stream())
             self.arena.shadow_fresh = shadow is not None
             return
         L.call("egot2_adam_step", self.arena.param.data_ptr(), self.arena.grad.data_ptr(), state["m"].data_ptr(),

@@ -120,6 +120,18 @@ class TranslatorTrainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.use_graphs = use_graphs
         self._grad_clean = False           # True right after the fused Adam: the gradient arena is all zeros
+        # Whole-step graphs (single GPU): the fused Adam is captured behind forward+backward, with the optimizer's step
+        # count kept ON THE DEVICE (a counter kernel on a side branch of the graph advances it, the Adam kernel reads
+        # it), so one graph launch is one optimisation step.  EGOT2_GRAPH_UPDATE=0 keeps Adam as an eager launch after
+        # the replay.
+        import os
+        gu = os.environ.get("EGOT2_GRAPH_UPDATE", "1")
+        # N > 1: capturing torch.distributed's NCCL all-reduce hung on the 2xB200 box (round 1), so the data-parallel step
+        # keeps [graph: forward+backward] -> eager all-reduce -> eager fused Adam unless forced with EGOT2_GRAPH_UPDATE=force
+        self.graph_update = gu == "force" or (gu != "0" and self.world == 1)
+        self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self._step_dev_val = 0
+        self._bump_stream = torch.cuda.Stream(device=self.device)
         self._graphs: Dict[int, tuple] = {}
         self._h2d: Dict[int, List[torch.Tensor]] = {}
         self.copy_stream = torch.cuda.Stream(device=self.device)
@@ -155,7 +167,14 @@ class TranslatorTrainer:
                 self.engine.arena.grad.zero_()
             if self.engine.dtype == "bf16" and not self.engine.arena.shadow_fresh:
                 self.engine.arena.refresh_shadow()
+            if self.graph_update and self._step_dev_val != self.step_count - 1:
+                self._step_dev.fill_(self.step_count - 1)
             graph.replay()
+            if self.graph_update:                         # the graph ended with [all-reduce +] fused Adam
+                self._step_dev_val = self.step_count
+                self._grad_clean = True
+                self.engine.arena.shadow_fresh = self.engine.dtype == "bf16"
+                return act.t["loss"][0]
             self._grad_clean = False
         else:
             act = self._fwd_bwd(feats, labels, seed=self.step_count)
@@ -177,20 +196,36 @@ class TranslatorTrainer:
             self.engine.arena.refresh_shadow()
             self.engine.arena.shadow_fresh = True
         self._grad_clean = True
+        if self.graph_update:
+            if "m" not in self.opt_state:                 # optimizer state must exist before capture
+                self.opt_state["m"] = torch.zeros_like(self.engine.arena.param)
+                self.opt_state["v"] = torch.zeros_like(self.engine.arena.param)
+            if self.world > 1:                            # communicator warm-up outside the capture (grad arena is zero)
+                allreduce_gradients(self.engine.arena.grad, self.pg)
+            self._step_dev.fill_(self.step_count - 1)
+            self._step_dev_val = self.step_count - 1
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
+            cur = torch.cuda.current_stream(self.device)
+            if self.graph_update:                         # side branch: advance the device-resident step count
+                self._bump_stream.wait_stream(cur)
+                with torch.cuda.stream(self._bump_stream):
+                    self._step_dev.add_(1)
             act = self._fwd_bwd(feats, labels, seed=1 + key)
+            if self.graph_update:
+                cur.wait_stream(self._bump_stream)
+                self._reduce_and_update(step_dev=self._step_dev)
         self._graphs[key] = (g, act)
         return g, act
 
-    def _reduce_and_update(self):
+    def _reduce_and_update(self, step_dev: Optional[torch.Tensor] = None):
         eng = self.engine
         scale = 1.0
         if self.world > 1:
             scale = allreduce_gradients(eng.arena.grad, self.pg)            # ONE flat NCCL all-reduce (NVLink)
         eng.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
-                      self.hp["weight_decay"], grad_scale=scale, fused=True)
+                      self.hp["weight_decay"], grad_scale=scale, fused=True, step_dev=step_dev)
         self._grad_clean = True
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) step

@@ -312,6 +312,11 @@ int egot2_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
 int egot2_adam_step_fused(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                           float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                           void* shadow_bf16, int32_t zero_grad, void* stream);
+/* Same, with the step count t >= 1 read from DEVICE memory at execution time (bias corrections 1 - beta^t computed in the
+ * kernel): the launch can sit inside a CUDA graph that is replayed every step while a counter kernel advances *step_dev. */
+int egot2_adam_step_fused_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, const int32_t* step_dev,
+                              float grad_scale, void* shadow_bf16, int32_t zero_grad, void* stream);
 
 /* ------------------------------------------------------------------ op-level entry points (diagnostics / unit tests) */
 /* C[M,N] = op(A)[M,K] . op(B)[K,N] (+bias[N]) ; A stored (M,K) or, if trans_a, (K,M); B stored (K,N) or, if
