@@ -111,6 +111,7 @@ SIGNATURES = {
     "egot2_sm_count": (C.c_int, []),
     "egot2_launch_count": (C.c_uint64, []),
     "egot2_prof_enable": (C.c_int, [C.c_int]),
+    "egot2_timeline_set": (C.c_int, [vp]),
     "egot2_prof_report": (C.c_int, [C.c_char_p, sz]),
     "egot2_embed_workspace_bytes": (sz, [P(EmbedDesc), C.c_int]),
     "egot2_embed_fwd": (C.c_int, [P(EmbedDesc), P(EmbedIn), P(EmbedOut), vp, sz, vp]),

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define EGOT2_FILE_ID 11
 #include "ops.h"
 
 namespace egot2 {
@@ -17,6 +18,12 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+#ifdef EGOT2_TIMELINE
+static void (*g_tl_setters[32])(unsigned long long*);
+static int g_tl_n = 0;
+void tl_register(void (*setter)(unsigned long long*)) { if (g_tl_n < 32) g_tl_setters[g_tl_n++] = setter; }
+#endif
 
 bool pdl_enabled() {
   static const bool on = !(getenv("EGOT2_PDL") && atoi(getenv("EGOT2_PDL")) == 0);
@@ -216,6 +223,17 @@ extern "C" const char* egot2_last_error(void) { return g_err; }
 extern "C" int egot2_sm_count(void) { return sm_count(); }
 extern "C" uint64_t egot2_launch_count(void) { return g_launch_count; }
 
+// EGOT2_TIMELINE builds: device buffer of 1 + 2*2000 u64 ([0] = count, then (globaltimer ns, file*100000+line) pairs); NULL = off
+extern "C" int egot2_timeline_set(void* dev_buf) {
+#ifdef EGOT2_TIMELINE
+  for (int i = 0; i < g_tl_n; ++i) g_tl_setters[i]((unsigned long long*)dev_buf);
+  return 0;
+#else
+  (void)dev_buf;
+  EGOT2_CHECK(false, "this build has no timeline support (compile with -DEGOT2_TIMELINE)");
+#endif
+}
+
 extern "C" int egot2_prof_enable(int on) {
   if (on && !g_prof) {
     g_prof = (ProfRec*)calloc(kProfMax, sizeof(ProfRec));
@@ -306,11 +324,15 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   const bool par = d->feat_dtype == d->dtype;
   Side* sides[2] = {par ? get_side(0) : nullptr, par ? get_side(1) : nullptr};
   bool used[2] = {false, false};
+  // fork BOTH side streams before anything of this stage is enqueued on `st`: a fork event recorded after segment 0's
+  // launch would make the other segments wait for it (seen in the in-graph timeline: they started when it had finished)
+  cudaStream_t side_st[2] = {st, st};
+  for (int i = 0; i < 2 && i + 1 < d->n_seg; ++i)
+    if (sides[i]) { side_st[i] = side_fork(st, sides[i], 0); used[i] = side_st[i] != st; }
   for (int k = 0; k < d->n_seg; ++k) {
     const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
     if (Dk == 0) continue;
-    cudaStream_t sk = st;
-    if (k > 0 && sides[(k - 1) & 1]) { sk = side_fork(st, sides[(k - 1) & 1], k & 7); used[(k - 1) & 1] = true; }
+    cudaStream_t sk = k > 0 ? side_st[(k - 1) & 1] : st;
     char* zk = (char*)out->z + (size_t)d->seg_offset[k] * d->H * es;
     const void* feat = in->feat[k];
     if (d->feat_dtype != d->dtype) {
@@ -384,11 +406,15 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   const bool par = d->feat_dtype == d->dtype;
   Side* sides[2] = {par ? get_side(0) : nullptr, par ? get_side(1) : nullptr};
   bool used[2] = {false, false};
+  // fork BOTH side streams before anything of this stage is enqueued on `st`: a fork event recorded after segment 0's
+  // launch would make the other segments wait for it (seen in the in-graph timeline: they started when it had finished)
+  cudaStream_t side_st[2] = {st, st};
+  for (int i = 0; i < 2 && i + 1 < d->n_seg; ++i)
+    if (sides[i]) { side_st[i] = side_fork(st, sides[i], 0); used[i] = side_st[i] != st; }
   for (int k = 0; k < d->n_seg; ++k) {
     const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
     if (Dk == 0) continue;
-    cudaStream_t sk = st;
-    if (k > 0 && sides[(k - 1) & 1]) { sk = side_fork(st, sides[(k - 1) & 1], k & 7); used[(k - 1) & 1] = true; }
+    cudaStream_t sk = k > 0 ? side_st[(k - 1) & 1] : st;
     const char* dzk = (const char*)dz + (size_t)d->seg_offset[k] * d->H * es;
     if (d->seg_has_proj[k]) {
       const void* feat = in->feat[k];
@@ -636,8 +662,10 @@ extern "C" int egot2_head_loss_fwd(const egot2_head_desc* d, const egot2_head_in
   if (rows == 0) return 0;
   EGOT2_CHECK(d->pool || (d->row_tokens > 0 && d->row_tokens <= d->T), "head: row_tokens=%d out of range", d->row_tokens);
   if (head_fused_supported(*d)) {
-    EGOT2_TRY(head_fused_fwd(*d, *in, *out, st));
-    return loss_fwd(*d, rows, out->logits, in->labels, in->class_weight, out->row_loss, out->loss, out->argmax, st);
+    if (d->loss != EGOT2_LOSS_NONE)
+      EGOT2_CHECK(in->labels && out->row_loss && out->loss, "head_loss_fwd: labels/row_loss/loss buffers required");
+    EGOT2_TRY(head_fused_fwd(*d, *in, *out, st));          // logits + per-row loss terms + argmax in one kernel
+    return loss_reduce(*d, rows, out->row_loss, out->loss, st);
   }
   EGOT2_TRY(pool_fwd(d->dtype, d->B, d->T, d->H, d->pool, d->row_tokens, in->x, out->pooled, st));
   const float ph = d->training ? d->p_head : 0.f;
@@ -665,11 +693,8 @@ extern "C" int egot2_head_loss_bwd(const egot2_head_desc* d, const egot2_head_in
   const int rows = egot2_head_rows(d);
   if (rows == 0) return 0;
   const size_t es = dtype_size(d->dtype);
-  if (head_fused_supported(*d)) {
-    if (d->loss != EGOT2_LOSS_NONE)
-      EGOT2_TRY(loss_bwd(*d, rows, saved->logits, in->labels, in->class_weight, saved->loss, dloss_scale, dlogits, st));
-    return head_fused_bwd(*d, *in, *saved, dlogits, dx, *g, st);
-  }
+  if (head_fused_supported(*d))       // d(loss)/d(logits) is derived inside the kernel (and written to `dlogits`)
+    return head_fused_bwd(*d, *in, *saved, dlogits, dloss_scale, dx, *g, st);
   EGOT2_CHECK(workspace && ws_bytes >= egot2_head_workspace_bytes(d) - 256, "head_loss_bwd: workspace too small");
   Carver ws(workspace, ws_bytes);
   const int ldl = d->dtype == EGOT2_F32 ? d->n_out : (d->n_out + 7) / 8 * 8;

@@ -11,6 +11,7 @@
 // shape-general kernels of attention_simt.cu.  Dropout masks are regenerated from (key, b, h, query, key index).
 #include <math.h>
 
+#define EGOT2_FILE_ID 6
 #include "ops.h"
 
 #ifndef EGOT2_ATTN_MINB

@@ -8,6 +8,7 @@
 // Layout: qkv (B, T, 3H) with q|k|v packed along the last dim, head h = columns h*dh..(h+1)*dh.
 #include <math.h>
 
+#define EGOT2_FILE_ID 9
 #include "ops.h"
 
 namespace egot2 {

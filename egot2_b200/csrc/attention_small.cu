@@ -9,6 +9,7 @@
 //   'asd' regrouping (:251-257): inner = T, outer = 3T, jstride = T, istride = 1  (row n = b*T + t sees tokens t, T+t, 2T+t)
 #include <math.h>
 
+#define EGOT2_FILE_ID 8
 #include "ops.h"
 
 namespace egot2 {

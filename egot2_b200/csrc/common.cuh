@@ -53,9 +53,37 @@ int sm_count();
 // transitive when EVERY kernel waits, launch() (which sets the stream-serialization attribute) must only be used with
 // kernels that call pdl_wait(); nothing before the wait may read memory another kernel of the step writes.
 // EGOT2_PDL=0 launches without the attribute (griddepcontrol.* are then no-ops).
+// ---- in-graph timeline (EGOT2_TIMELINE builds only; tools/timeline.py).  Block 0 / thread 0 of every kernel stamps
+// %globaltimer right after its griddepcontrol.wait, i.e. when everything before it on the stream has finished; consecutive
+// stamps of the chain therefore give each kernel's in-graph duration including launch gaps.  Each translation unit owns a
+// copy of the buffer pointer (no relocatable device code); tl_register collects their setters.
+#ifdef EGOT2_TIMELINE
+void tl_register(void (*setter)(unsigned long long*));
+static __device__ unsigned long long* tl_buf_dev = nullptr;
+namespace {
+struct TlReg {
+  TlReg() { tl_register([](unsigned long long* p) { cudaMemcpyToSymbol(tl_buf_dev, &p, sizeof(p)); }); }
+};
+static TlReg tl_reg_instance;
+}  // namespace
+__device__ __forceinline__ void tl_stamp(unsigned loc) {
+  if (tl_buf_dev && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned i = atomicAdd(reinterpret_cast<unsigned*>(tl_buf_dev), 1u);
+    if (i < 2000) { tl_buf_dev[1 + 2 * i] = t; tl_buf_dev[2 + 2 * i] = loc; }
+  }
+}
+#define EGOT2_TL(id) ::egot2::tl_stamp((unsigned)(id) * 100000u + (unsigned)__LINE__)
+#else
+#define EGOT2_TL(id) do { } while (0)
+#endif
+#ifndef EGOT2_FILE_ID
+#define EGOT2_FILE_ID 0
+#endif
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#define EGOT2_PDL_ENTER() do { ::egot2::pdl_launch_dependents(); ::egot2::pdl_wait(); } while (0)
+#define EGOT2_PDL_ENTER() do { ::egot2::pdl_launch_dependents(); ::egot2::pdl_wait(); EGOT2_TL(EGOT2_FILE_ID); } while (0)
 bool pdl_enabled();
 // Launch priority: kernels on the caller's stream (the data-gradient / forward chain, i.e. the critical path) outrank the
 // library's side-stream kernels (parameter gradients), so when both have CTAs waiting for an SM the chain goes first and

@@ -5,6 +5,7 @@
 // only 2 tokens per row, so attention uses the small-query kernels of attention_small.cu.
 #include <math.h>
 
+#define EGOT2_FILE_ID 7
 #include "ops.h"
 
 namespace egot2 {

@@ -29,6 +29,7 @@
 // live in the leader and receive remote arrivals; completion barriers are signalled in both CTAs by multicast commits.
 #include <stdlib.h>
 
+#define EGOT2_FILE_ID 5
 #include "ops.h"
 #include "sm100.cuh"
 
@@ -189,6 +190,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   }
   if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
   pdl_wait();                    // first global-memory access of the kernel is below
+  EGOT2_TL(EGOT2_FILE_ID);
   if (!BWD) {
     const float s1 = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;      // dropout scale folded into the bias (see epilogue)
     for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i] * s1;

@@ -7,6 +7,7 @@
 // outputs per thread, 256 threads.  Handles all four operand orientations, storage-row
 // remapping (segment scatter inside (B,T,H) tensors), the fused epilogue of ops.h and split-K
 // with fp32 atomics for the weight-gradient GEMMs (K = all tokens of the batch).
+#define EGOT2_FILE_ID 10
 #include "ops.h"
 
 namespace egot2 {

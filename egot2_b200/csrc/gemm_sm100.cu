@@ -13,6 +13,7 @@
 // gridDim.z > 1 = split-K for the weight-gradient GEMMs (K = every token of the batch): fp32 atomics into C.
 #include <stdlib.h>
 
+#define EGOT2_FILE_ID 4
 #include "ops.h"
 #include "sm100.cuh"
 
@@ -87,11 +88,12 @@ __device__ __forceinline__ void store32(bf16* p, const float (&v)[32]) {
   }
 }
 
-template <int BN> struct TileCfg {            // stages chosen so that BN<=128 tiles fit two CTAs per SM
-  static constexpr int STAGES = BN == 128 ? 2 : (BN == 64 ? 3 : 4);
+template <int BN, typename TO> struct TileCfg {   // stages chosen so that BN<=128 tiles fit two CTAs per SM
+  // bf16 output tile staged in shared memory for the TMA-store epilogue (bf16 C, BN <= 128 only: 128 rows x BN x 2 B);
+  // fp32 outputs (split-K weight gradients: long K loops) spend that shared memory on a deeper operand ring instead
+  static constexpr uint32_t OUT_BYTES = (BN <= 128 && sizeof(TO) == 2) ? 128 * BN * 2 : 0;
+  static constexpr int STAGES = BN == 128 ? (OUT_BYTES ? 2 : 3) : (BN == 64 ? (OUT_BYTES ? 3 : 4) : 4);
   static constexpr int MIN_CTAS = BN == 256 ? 1 : 2;
-  // bf16 output tile staged in shared memory for the TMA-store epilogue (BN <= 128 only: 128 rows x BN x 2 B)
-  static constexpr uint32_t OUT_BYTES = BN <= 128 ? 128 * BN * 2 : 0;
 };
 __device__ __forceinline__ void sts128(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -105,18 +107,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 // the per-tile fill + epilogue latency is several times the MMA time.  Split-K launches (gridDim.z > 1) give every
 // CTA exactly one tile.
 template <int BN, bool A_MN, bool B_MN, typename TO>
-__global__ void __launch_bounds__(NTHREADS, TileCfg<BN>::MIN_CTAS)
+__global__ void __launch_bounds__(NTHREADS, TileCfg<BN, TO>::MIN_CTAS)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_c, const EpiArgs e, const int k_blocks_total, const int k_blocks_per_split, const int tiles_n, const int num_tiles) {
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
-  constexpr int STAGES = TileCfg<BN>::STAGES;
+  constexpr int STAGES = TileCfg<BN, TO>::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024 B alignment
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + STAGES * A_BYTES;
   const uint32_t sOut = sB + STAGES * B_BYTES;                            // [BN/64][128 rows][128 B], 128B-swizzled (TMA-store epilogue)
-  const uint32_t bars = sOut + TileCfg<BN>::OUT_BYTES;                          // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+  const uint32_t bars = sOut + TileCfg<BN, TO>::OUT_BYTES;                          // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES, tmem_empty = tmem_full + 16;
   const uint32_t tmem_slot = tmem_empty + 16;
   const uint32_t bias_off = (tmem_slot + 8 + 15u) & ~15u;        // float sbias[2][BN]: the tile's bias columns (broadcast reads in the epilogue)
@@ -138,6 +140,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
   pdl_wait();                   // everything above touched only kernel parameters, shared memory and TMEM
+  EGOT2_TL(EGOT2_FILE_ID);
   float* sbias = reinterpret_cast<float*>(smem_raw + (bias_off - smem_u32(smem_raw)));
   tc_fence_before();
   __syncthreads();
@@ -421,8 +424,8 @@ static bool host_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 template <int BN, bool A_MN, bool B_MN, typename TO>
 int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, const KGroup& kg, cudaStream_t st) {
-  constexpr int STAGES = TileCfg<BN>::STAGES;
-  constexpr size_t smem = 1024 + STAGES * (BM * BK * 2 + BN * BK * 2) + TileCfg<BN>::OUT_BYTES + 16 * STAGES + 96 + 2 * BN * 4;
+  constexpr int STAGES = TileCfg<BN, TO>::STAGES;
+  constexpr size_t smem = 1024 + STAGES * (BM * BK * 2 + BN * BK * 2) + TileCfg<BN, TO>::OUT_BYTES + 16 * STAGES + 96 + 2 * BN * 4;
   static bool attr_set = false;
   auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, TO>;
   if (!attr_set) {
@@ -448,6 +451,12 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   const int kb_total = kg.on ? kg.kb_total : (a.K + BK - 1) / BK;
   int splits = a.split_k < 1 ? 1 : a.split_k;
   if (splits > kb_total) splits = kb_total;
+  {
+    // split-K grids are ONE wave: tiles x splits <= resident CTAs (19 splits x 16 tiles = 304 CTAs on 296 slots ran the
+    // weight-gradient GEMMs in two waves, the second one 3 % full)
+    const int nt = ((a.N + BN - 1) / BN) * ((a.M + BM - 1) / BM), slots = sm_count() * TileCfg<BN, TO>::MIN_CTAS;
+    if (splits > 1 && nt * splits > slots) splits = slots / nt > 0 ? slots / nt : 1;
+  }
   const int kb_per = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per - 1) / kb_per;
   e.atomic = splits > 1;
@@ -455,7 +464,7 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   // persistent CTAs: as many as are resident at once, evened out so that every CTA walks the same number of tiles
   int ctas = num_tiles;
   if (splits == 1) {
-    const int slots = sm_count() * TileCfg<BN>::MIN_CTAS;
+    const int slots = sm_count() * TileCfg<BN, TO>::MIN_CTAS;
     const int rounds = (num_tiles + slots - 1) / slots;
     ctas = (num_tiles + rounds - 1) / rounds;
   }

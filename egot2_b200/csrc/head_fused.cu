@@ -4,6 +4,7 @@
 //             plus d(gamma, beta, W, b) accumulated with one atomic per (clip, element)
 // Replaces pool + LN + cast + GEMM (+ colsum + wgrad + dgrad + LN-bwd + pool-bwd): ~15 tiny launches -> 2.
 // HHI TTM head (2 logits) and HOI PNR / OSCC heads (16 / 2 logits; LayerNorm shared with the token LN).
+#define EGOT2_FILE_ID 3
 #include "ops.h"
 
 namespace egot2 {
@@ -30,12 +31,15 @@ __global__ void __launch_bounds__(NT) head_fwd_kernel(int T, int H, int n_out, c
                                                       const TT* __restrict__ W, const float* __restrict__ bias, float eps,
                                                       float p_drop, uint64_t drop_key, float* __restrict__ pooled,
                                                       float* __restrict__ stat, TT* __restrict__ g_out,
-                                                      float* __restrict__ logits) {
+                                                      float* __restrict__ logits, int loss_kind,
+                                                      const int64_t* __restrict__ labels, const float* __restrict__ cw,
+                                                      float* __restrict__ seg_loss, int32_t* __restrict__ argmax) {
   EGOT2_PDL_ENTER();
   extern __shared__ float sm[];
   float* ps = sm;            // pooled (H)
   float* gs = sm + H;        // LN output (H)
   __shared__ float red[NT / 32];
+  __shared__ float slog[32];
   const int row = blockIdx.x;
   const TT* xb = x + (size_t)row * T * H;
   if (sizeof(TT) == 2 && H == 128) {
@@ -94,8 +98,40 @@ __global__ void __launch_bounds__(NT) head_fwd_kernel(int T, int H, int n_out, c
     float d = 0.f;
     for (int c = lane; c < H; c += 32) d += gs[c] * to_f32(W[(size_t)j * H + c]);
     d = warp_sum(d);
-    if (lane == 0) logits[(size_t)row * n_out + j] = d + bias[j];
+    if (lane == 0) { logits[(size_t)row * n_out + j] = d + bias[j]; slog[j] = d + bias[j]; }
   }
+  if (loss_kind == EGOT2_LOSS_NONE) return;
+  // fused per-row loss (same arithmetic and reduction order as loss.cu's ce_fwd_kernel / bce_fwd_kernel: one warp per row)
+  __syncthreads();
+  if (warp != 0) return;
+  const int y = (int)labels[row];
+  const float z = lane < n_out ? slog[lane] : -INFINITY;
+  float mx = z; int am = lane < n_out ? lane : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+  }
+  if (loss_kind == EGOT2_LOSS_BCE_SIGMOID) {
+    float acc = 0.f;
+    if (lane < n_out) {
+      const float p = 1.f / (1.f + expf(-z));
+      const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);   // BCELoss clamps at -100
+      acc = -((lane == y) ? lp : l1p);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) { seg_loss[2 * (size_t)row] = acc; seg_loss[2 * (size_t)row + 1] = (float)n_out; }
+  } else {
+    float s = lane < n_out ? expf(z - mx) : 0.f;
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float w = cw ? cw[y] : 1.f;
+      seg_loss[2 * (size_t)row] = w * ((mx + logf(s)) - slog[y]);
+      seg_loss[2 * (size_t)row + 1] = w;
+    }
+  }
+  if (lane == 0 && argmax) argmax[row] = am;
 }
 
 template <typename TT>
@@ -105,7 +141,10 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(int T, int H, int n_out, c
                                                       const TT* __restrict__ W, float p_drop, uint64_t drop_key,
                                                       TT* __restrict__ dx, float* __restrict__ d_ln_g,
                                                       float* __restrict__ d_ln_b, float* __restrict__ dW,
-                                                      float* __restrict__ db) {
+                                                      float* __restrict__ db, int loss_kind, int rows,
+                                                      const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                      const float* __restrict__ cw, float dloss_scale,
+                                                      float* __restrict__ dlogits_out) {
   EGOT2_PDL_ENTER();
   extern __shared__ float sm[];
   float* dgs = sm;           // d(LN output) (H)
@@ -113,10 +152,42 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(int T, int H, int n_out, c
   __shared__ float dl[32];
   __shared__ float red[NT / 32];
   const int row = blockIdx.x;
-  if (threadIdx.x < n_out) {
-    const float v = dlogits[(size_t)row * n_out + threadIdx.x];
-    dl[threadIdx.x] = v;
-    if (db) atomicAdd(db + threadIdx.x, v);
+  if (loss_kind == EGOT2_LOSS_NONE) {
+    if (threadIdx.x < n_out) {
+      const float v = dlogits[(size_t)row * n_out + threadIdx.x];
+      dl[threadIdx.x] = v;
+      if (db) atomicAdd(db + threadIdx.x, v);
+    }
+  } else {
+    // fused d(loss)/d(logits) of this clip (loss.cu ce_bwd_kernel / bce_bwd_kernel).  The normaliser of the weighted mean
+    // (sum of the class weights over ALL rows) is recomputed by every CTA - a few hundred L2-resident loads - so that the
+    // backward does not wait for a separate kernel.
+    float wsum = 0.f;
+    if (loss_kind == EGOT2_LOSS_CE) {
+      float part = 0.f;
+      for (int i = threadIdx.x; i < rows; i += NT) part += cw ? cw[(int)labels[i]] : 1.f;
+      wsum = block_sum(part, red);
+    }
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x, y = (int)labels[row];
+      const float z = lane < n_out ? logits[(size_t)row * n_out + lane] : -INFINITY;
+      float v = 0.f;
+      if (loss_kind == EGOT2_LOSS_BCE_SIGMOID) {
+        const float p = 1.f / (1.f + expf(-z));
+        v = dloss_scale * (p - (lane == y ? 1.f : 0.f)) / ((float)rows * (float)n_out);
+      } else {
+        const float mx = warp_max(z);
+        const float e = lane < n_out ? expf(z - mx) : 0.f;
+        const float s = warp_sum(e);
+        const float w = (cw ? cw[y] : 1.f) * dloss_scale / wsum;
+        v = w * (e * (1.f / s) - (lane == y ? 1.f : 0.f));
+      }
+      if (lane < n_out) {
+        dl[lane] = v;
+        if (dlogits_out) dlogits_out[(size_t)row * n_out + lane] = v;
+        if (db) atomicAdd(db + lane, v);
+      }
+    }
   }
   __syncthreads();
   const float mean = stat[2 * (size_t)row], rstd = stat[2 * (size_t)row + 1];
@@ -176,26 +247,30 @@ int head_fused_fwd(const egot2_head_desc& d, const egot2_head_in& in, const egot
   ProfScope prof(st, "head_fwd B%d T%d H%d n%d", d.B, d.T, d.H, d.n_out);
   if (d.dtype == EGOT2_F32)
     launch(head_fwd_kernel<float>, dim3(d.B), dim3(NT), smem, st, d.T, d.H, d.n_out, (const float*)in.x, in.ln_g, in.ln_b, (const float*)in.w,
-                                                  in.b, d.ln_eps, ph, key, out.pooled, out.stat, (float*)out.g, out.logits);
+                                                  in.b, d.ln_eps, ph, key, out.pooled, out.stat, (float*)out.g, out.logits,
+           d.loss, in.labels, in.class_weight, out.row_loss, out.argmax);
   else
     launch(head_fwd_kernel<bf16>, dim3(d.B), dim3(NT), smem, st, d.T, d.H, d.n_out, (const bf16*)in.x, in.ln_g, in.ln_b, (const bf16*)in.w,
-                                                 in.b, d.ln_eps, ph, key, out.pooled, out.stat, (bf16*)out.g, out.logits);
+                                                 in.b, d.ln_eps, ph, key, out.pooled, out.stat, (bf16*)out.g, out.logits,
+           d.loss, in.labels, in.class_weight, out.row_loss, out.argmax);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
 
-int head_fused_bwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& saved, const float* dlogits,
-                   void* dx, const egot2_head_grads& g, cudaStream_t st) {
+int head_fused_bwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& saved, float* dlogits,
+                   float dloss_scale, void* dx, const egot2_head_grads& g, cudaStream_t st) {
   const float ph = d.training ? d.p_head : 0.f;
   const uint64_t key = site_key(d.seed, SITE_HEAD, 0);
   const size_t smem = 2 * (size_t)d.H * sizeof(float);
   ProfScope prof(st, "head_bwd B%d T%d H%d n%d", d.B, d.T, d.H, d.n_out);
   if (d.dtype == EGOT2_F32)
     launch(head_bwd_kernel<float>, dim3(d.B), dim3(NT), smem, st, d.T, d.H, d.n_out, dlogits, saved.pooled, saved.stat, (const float*)saved.g,
-                                                  in.ln_g, (const float*)in.w, ph, key, (float*)dx, g.ln_g, g.ln_b, g.w, g.b);
+                                                  in.ln_g, (const float*)in.w, ph, key, (float*)dx, g.ln_g, g.ln_b, g.w, g.b,
+           d.loss, d.B, saved.logits, in.labels, in.class_weight, dloss_scale, dlogits);
   else
     launch(head_bwd_kernel<bf16>, dim3(d.B), dim3(NT), smem, st, d.T, d.H, d.n_out, dlogits, saved.pooled, saved.stat, (const bf16*)saved.g,
-                                                 in.ln_g, (const bf16*)in.w, ph, key, (bf16*)dx, g.ln_g, g.ln_b, g.w, g.b);
+                                                 in.ln_g, (const bf16*)in.w, ph, key, (bf16*)dx, g.ln_g, g.ln_b, g.w, g.b,
+           d.loss, d.B, saved.logits, in.labels, in.class_weight, dloss_scale, dlogits);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

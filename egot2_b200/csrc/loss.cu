@@ -7,6 +7,7 @@
 // deterministic (no atomics).  argmax (first maximal index, as torch.argmax) is emitted per segment.
 #include <math.h>
 
+#define EGOT2_FILE_ID 2
 #include "ops.h"
 
 namespace egot2 {
@@ -174,6 +175,16 @@ int loss_fwd(const egot2_head_desc& d, int rows, const float* logits, const int6
   EGOT2_LAUNCH_CHECK();
   const float denom_div = d.loss == EGOT2_LOSS_CE_GROUPS ? (float)(g.sub_rows * g.n_groups) : 1.f;
   launch(loss_reduce_kernel, dim3(1), dim3(1024), 0, st, segs, row_loss, denom_div, loss);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
+// only the tree reduction of per-row (weighted nll, weight) pairs that a fused head kernel already produced
+int loss_reduce(const egot2_head_desc& d, int rows, const float* row_loss, float* loss, cudaStream_t st) {
+  if (d.loss == EGOT2_LOSS_NONE || rows == 0) return 0;
+  EGOT2_CHECK(d.loss != EGOT2_LOSS_CE_GROUPS && row_loss && loss, "loss_reduce: single-segment losses only");
+  ProfScope prof(st, "loss_reduce kind%d rows%d", d.loss, rows);
+  launch(loss_reduce_kernel, dim3(1), dim3(1024), 0, st, (long long)rows, row_loss, 1.f, loss);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

@@ -127,7 +127,10 @@ int ffn_fused_bwd_dx(int M, int FF, const void* d2, const void* d1, const void* 
 // fused small heads (head_fused.cu): pool + LN + Linear(n_out <= 32) in one kernel per direction
 bool head_fused_supported(const egot2_head_desc& d);
 int head_fused_fwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& out, cudaStream_t st);
-int head_fused_bwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& saved, const float* dlogits,
+// fwd also emits the per-row loss terms + argmax when d.loss != NONE; bwd then derives d(loss)/d(logits) itself (written to
+// `dlogits`, which is only READ when d.loss == NONE)
+int loss_reduce(const egot2_head_desc& d, int rows, const float* row_loss, float* loss, cudaStream_t st);
+int head_fused_bwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& saved, float* dlogits, float dloss_scale,
                    void* dx, const egot2_head_grads& g, cudaStream_t st);
 
 // losses on fp32 logits (rows, n_out)

@@ -4,6 +4,7 @@
 // Loads/stores are coalesced (lane-strided columns); grids are sized to a multiple of the SM count.
 #include <math.h>
 
+#define EGOT2_FILE_ID 1
 #include "ops.h"
 
 namespace egot2 {

@@ -72,6 +72,10 @@ uint64_t egot2_launch_count(void);
  * enqueues with CUDA events on the launch stream (eager launches only; ignored during stream capture).
  * egot2_prof_report writes "<launcher tag>\t<launches>\t<total microseconds>\n" lines (host buffer). */
 int egot2_prof_enable(int on);
+/* Diagnostics, -DEGOT2_TIMELINE builds only (otherwise returns an error): every kernel stamps %globaltimer when it starts
+ * (after its programmatic-dependent-launch wait) into dev_buf: u64[0] = number of stamps, then (ns, file_id*100000+line)
+ * pairs, at most 2000.  Works inside CUDA-graph replays; NULL switches it off.  See tools/timeline.py. */
+int egot2_timeline_set(void* dev_buf);
 int egot2_prof_report(char* buf_host, size_t buf_bytes);
 
 /* ------------------------------------------------------------------ embed stage */
