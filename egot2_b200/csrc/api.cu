@@ -202,14 +202,17 @@ int side_join(cudaStream_t main, Side* sd) {
 }
 
 // weight-gradient GEMM: dW[N_out, K_in] += dY^T . X     (dY: (rows, N_out), X: (rows, K_in))
+// share: how many sibling weight-gradient GEMMs run side by side (the per-task projections): each takes 1/share of the
+// resident CTA slots so that all of them fit ONE wave together instead of queueing behind each other
 int wgrad(int dtype, int rows, int n_out, int k_in, const void* dY, int ld_dy, int dy_rpg, int dy_gs, const void* X,
-          int ld_x, int x_rpg, int x_gs, float* dW, cudaStream_t st) {
+          int ld_x, int x_rpg, int x_gs, float* dW, cudaStream_t st, int share = 1) {
   GemmArgs g;
   g.M = n_out; g.N = k_in; g.K = rows;
   g.A = dY; g.lda = ld_dy; g.trans_a = 1; g.a_rpg = dy_rpg; g.a_gstride = dy_gs;
   g.B = X; g.ldb = ld_x; g.trans_b = 0; g.b_rpg = x_rpg; g.b_gstride = x_gs;
   g.C = dW; g.ldc = k_in; g.in_dtype = dtype; g.out_dtype = EGOT2_F32; g.accumulate = 1;
   g.split_k = suggest_split_k(g.M, g.N, g.K);
+  if (share > 1) g.split_k = g.split_k / share > 0 ? g.split_k / share : 1;
   return gemm(g, st);
 }
 
@@ -411,6 +414,8 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   cudaStream_t side_st[2] = {st, st};
   for (int i = 0; i < 2 && i + 1 < d->n_seg; ++i)
     if (sides[i]) { side_st[i] = side_fork(st, sides[i], 0); used[i] = side_st[i] != st; }
+  int n_proj = 0;
+  for (int k = 0; k < d->n_seg; ++k) n_proj += (d->seg_has_proj[k] && d->seg_tokens[k] > 0) ? 1 : 0;
   for (int k = 0; k < d->n_seg; ++k) {
     const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
     if (Dk == 0) continue;
@@ -423,7 +428,7 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
         feat = cast_buf;
       }
       if (g->proj_w[k])
-        EGOT2_TRY(wgrad(d->dtype, d->B * Dk, d->H, Kk, dzk, d->H, Dk, d->T, feat, Kk, 0, 0, g->proj_w[k], sk));
+        EGOT2_TRY(wgrad(d->dtype, d->B * Dk, d->H, Kk, dzk, d->H, Dk, d->T, feat, Kk, 0, 0, g->proj_w[k], sk, par ? n_proj : 1));
       if (g->proj_b[k]) EGOT2_TRY(colsum_accum(d->dtype, d->B * Dk, d->H, dzk, d->H, Dk, d->T, g->proj_b[k], sk));
       if (g->dfeat[k]) {   // dF = dZ . W   (only for a trainable backbone: HHI --nofreeze)
         GemmArgs m;
@@ -591,7 +596,8 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   const bool fused_dx = s->hid_mask && ffn_fused_supported(dt, H, FF) && !env_is("EGOT2_FFN", "unfused");
   if (fused_dx) {
     // one tcgen05 kernel: dhid = gate(d2 . W2) and d3 = dhid . W1 + d1, dhid never re-read for the second GEMM
-    EGOT2_TRY(ffn_fused_bwd_dx(M, FF, d2, pd > 0.f ? w.d1 : nullptr, s->hid_mask, p->lin1_w, p->lin2_w, pd, w.dhid, w.d3, s->ffn_scratch, st));
+    EGOT2_TRY(ffn_fused_bwd_dx(M, FF, d2, pd > 0.f ? w.d1 : nullptr, s->hid_mask, p->lin1_w, p->lin2_w, pd, w.dhid, w.d3, s->ffn_scratch,
+                               g->lin1_b, st));          // + db1: the bias gradient comes out of the same pass over dhid
   } else {
     GemmArgs m; m.M = M; m.N = FF; m.K = H; m.A = d2; m.lda = H; m.B = p->lin2_w; m.ldb = FF; m.trans_b = 0;
     m.C = w.dhid; m.ldc = FF; m.mask = s->hid; m.ldm = FF; m.mask_scale = inv_keep; m.in_dtype = dt; m.out_dtype = dt;
@@ -604,8 +610,10 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   {
     cudaStream_t ss = side_fork(st, sd1, 1);
     EGOT2_TRY(wgrad(dt, M, FF, H, w.dhid, FF, 0, 0, s->x1, H, 0, 0, g->lin1_w, ss));
-    cudaStream_t s2 = side_fork(st, sd2, 1);      // the bias sum reads dhid beside the GEMM (both mostly from L2)
-    EGOT2_TRY(colsum_accum(dt, M, FF, w.dhid, FF, 0, 0, g->lin1_b, s2));
+    if (!fused_dx) {
+      cudaStream_t s2 = side_fork(st, sd2, 1);    // the bias sum reads dhid beside the GEMM (both mostly from L2)
+      EGOT2_TRY(colsum_accum(dt, M, FF, w.dhid, FF, 0, 0, g->lin1_b, s2));
+    }
   }
   // 4. through norm1: d4 = dL/dy1, and (same kernel) d5 = dropout1 mask applied to it = dL/d(out_proj out)
   const void* dyo = w.d4;

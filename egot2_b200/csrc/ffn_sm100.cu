@@ -81,6 +81,8 @@ struct FfnArgs {
   int hid_tiled;         // hidden tensor layout: 0 = row-major (M, FF); 1 = tile-major [M/128][FF/64][128][64] (16 KB contiguous per TMA box)
   uint2* hmask;          // [FF/64][M] x 64 bits: hidden activation != 0 (ReLU gate x dropout keep), for ffn_bwd_dx
   const bf16* d1;        // backward: gradient arriving through the residual branch (added to d3), (M,128)
+  float* db1;            // backward, optional: db1[FF] += column sums of dhid (the linear1 bias gradient), so that no
+                         // separate kernel has to re-read the (M,FF) dhid tensor for it
   float p_drop; uint64_t key_ffn, key_drop2;
   // FF-split tail (see ffn_launch): CTA pairs >= split_pair0 each own 1/S of the FF range of a tail token tile and add
   // their partial GEMM2 accumulator into `partial` (fp32, rows relative to token split_pair0*256); a fix-up kernel finishes
@@ -191,6 +193,9 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
   pdl_wait();                    // first global-memory access of the kernel is below
   EGOT2_TL(EGOT2_FILE_ID);
+  if (BWD) {                     // sB1 doubles as this CTA's db1 accumulator (the forward's bias stage is not needed)
+    for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = 0.f;
+  }
   if (!BWD) {
     const float s1 = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;      // dropout scale folded into the bias (see epilogue)
     for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i] * s1;
@@ -416,12 +421,32 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         for (int h2 = 0; h2 < 2; ++h2) {
           const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
           const uint32_t gw = h2 ? gate.y : gate.x;
+          float cs[32];          // this row's 32 dhid values; reduced over the warp's 32 rows below
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const float v0 = (gw >> j) & 1u ? __uint_as_float(rr[j]) * inv_keep : 0.f;
             const float v1 = (gw >> (j + 1)) & 1u ? __uint_as_float(rr[j + 1]) * inv_keep : 0.f;
             __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1);
             packed[h2 * 16 + j / 2] = *reinterpret_cast<uint32_t*>(&p0);
+            cs[j] = v0; cs[j + 1] = v1;
+          }
+          if (a.db1) {
+            // db1 (linear1 bias gradient) = column sums of dhid, taken here so that no other kernel re-reads the (M,FF)
+            // tensor: a transposing butterfly over the warp's 32 rows - 31 shuffles for 32 columns - after which lane L
+            // holds the sum of column L (rows past M have zero gate bits and contribute nothing).  Costs the kernel ~9 us
+            // (HHI b256) against a 17 us separate pass; summing the staged tile in the idle TMA-store warp instead was
+            // slower still (it delays the hidden-buffer hand-back).
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+              const bool up = (lane & s) != 0;
+#pragma unroll
+              for (int i = 0; i < s; ++i) {
+                const float send = up ? cs[i] : cs[i + s];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+                cs[i] = (up ? cs[i + s] : cs[i]) + recv;
+              }
+            }
+            atomicAdd(sB1 + cg * FC + ch * 64 + h2 * 32 + lane, cs[0]);
           }
         }
       }
@@ -576,6 +601,12 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (threadIdx.x == 64) TR(60, 4);
   tc_fence_before();
   __syncthreads();
+  if (BWD && a.db1) {            // this CTA's column sums of its chunk range -> global (one reduction per column)
+    for (int i = threadIdx.x; i < NC * FC; i += NTHREADS) {
+      const float v = sB1[c_begin * FC + i];
+      if (v != 0.f) atomicAdd(a.db1 + c_begin * FC + i, v);
+    }
+  }
   if (threadIdx.x == 64) TR(60, 5);
   cluster_sync_all();                         // the peer may still be signalling this CTA's barriers / using the pair's TMEM
 #ifdef EGOT2_FFN_TRACE
@@ -805,6 +836,7 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
   FfnArgs a;
   a.M = M; a.FF = FF; a.b1 = b1; a.b2 = b2; a.ln_g = ln_g; a.ln_b = ln_b; a.eps = eps;
   a.stat2 = stat2; a.save_hid = hid != nullptr; a.hmask = (uint2*)hmask; a.d1 = nullptr; a.hid_tiled = tiled && hid;
+  a.db1 = nullptr;
   a.p_drop = p_drop; a.key_ffn = key_ffn; a.key_drop2 = key_drop2;
   a.partial = scratch; a.fix_x1 = (const bf16*)x1; a.fix_d1 = nullptr; a.fix_y2 = (bf16*)y2; a.fix_out = (bf16*)x_out;
   return ffn_launch(false, M, FF, tx, tw1, tw2, thid, ty2, tout, a, st);
@@ -813,7 +845,7 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
 // Data-gradient half of the block's backward (see the kernel comment):
 //   dhid = (d2 . W2) * gate / (1-p)  -> (M,FF) bf16;   d3 = dhid . W1 + d1  -> (M,128) bf16   (d1 == nullptr: d1 is d2)
 int ffn_fused_bwd_dx(int M, int FF, const void* d2, const void* d1, const void* hmask, const void* W1, const void* W2,
-                     float p_drop, void* dhid, void* d3, float* scratch, cudaStream_t st) {
+                     float p_drop, void* dhid, void* d3, float* scratch, float* db1, cudaStream_t st) {
   if (M == 0) return 0;
   CUtensorMap tx, tw1, tw2, thid, ty2;
   EGOT2_TRY(kmajor_map(&tx, d2, H, M, H, 128));
@@ -824,6 +856,7 @@ int ffn_fused_bwd_dx(int M, int FF, const void* d2, const void* d1, const void* 
   FfnArgs a;
   a.M = M; a.FF = FF; a.b1 = nullptr; a.b2 = nullptr; a.ln_g = nullptr; a.ln_b = nullptr; a.eps = 0.f;
   a.stat2 = nullptr; a.save_hid = 1; a.hmask = (uint2*)const_cast<void*>(hmask); a.d1 = (const bf16*)d1; a.hid_tiled = 0;
+  a.db1 = db1;
   a.p_drop = p_drop; a.key_ffn = 0; a.key_drop2 = 0;
   a.partial = scratch; a.fix_x1 = nullptr; a.fix_d1 = (const bf16*)(d1 ? d1 : d2); a.fix_y2 = nullptr; a.fix_out = (bf16*)d3;
   return ffn_launch(true, M, FF, tx, tw1, tw2, thid, ty2, ty2, a, st);

@@ -120,9 +120,9 @@ int ffn_fused_fwd(int M, int FF, const void* x1, const void* W1, const float* b1
                   const float* ln_g, const float* ln_b, float eps, void* hid, void* hmask, void* y2, float* stat2, void* x_out,
                   float p_drop, uint64_t key_ffn, uint64_t key_drop2, float* scratch, cudaStream_t st);
 size_t ffn_scratch_bytes(int M);      // zeroed fp32 scratch that enables the FF-split of the last partial wave (may be 0)
-// dhid = (d2 . W2) * gate(hmask) / (1-p);  d3 = dhid . W1 + (d1 ? d1 : d2)
+// dhid = (d2 . W2) * gate(hmask) / (1-p);  d3 = dhid . W1 + (d1 ? d1 : d2);  db1 (optional) += column sums of dhid
 int ffn_fused_bwd_dx(int M, int FF, const void* d2, const void* d1, const void* hmask, const void* W1, const void* W2,
-                     float p_drop, void* dhid, void* d3, float* scratch, cudaStream_t st);
+                     float p_drop, void* dhid, void* d3, float* scratch, float* db1, cudaStream_t st);
 
 // fused small heads (head_fused.cu): pool + LN + Linear(n_out <= 32) in one kernel per direction
 bool head_fused_supported(const egot2_head_desc& d);
