@@ -416,6 +416,23 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
     if (sides[i]) { side_st[i] = side_fork(st, sides[i], 0); used[i] = side_st[i] != st; }
   int n_proj = 0;
   for (int k = 0; k < d->n_seg; ++k) n_proj += (d->seg_has_proj[k] && d->seg_tokens[k] > 0) ? 1 : 0;
+  {
+    // every projection's bias gradient (column sums of its segment's rows of dz) in ONE launch of the per-segment
+    // column-sum kernel instead of one strided column-sum launch per task
+    SegOut sb;
+    sb.n = d->n_seg;
+    bool any = false;
+    for (int k = 0; k < d->n_seg; ++k) {
+      sb.tokens[k] = d->seg_tokens[k];
+      sb.out[k] = (d->seg_has_proj[k] && d->seg_tokens[k] > 0) ? g->proj_b[k] : nullptr;
+      any |= sb.out[k] != nullptr;
+    }
+    Side* bside = get_side(2);
+    if (any) {
+      EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dz, nullptr, sb, 0.f, 0, side_fork(st, bside, 1)));
+      if (bside && !tside) tside = bside;       // joined below
+    }
+  }
   for (int k = 0; k < d->n_seg; ++k) {
     const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
     if (Dk == 0) continue;
@@ -429,7 +446,6 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
       }
       if (g->proj_w[k])
         EGOT2_TRY(wgrad(d->dtype, d->B * Dk, d->H, Kk, dzk, d->H, Dk, d->T, feat, Kk, 0, 0, g->proj_w[k], sk, par ? n_proj : 1));
-      if (g->proj_b[k]) EGOT2_TRY(colsum_accum(d->dtype, d->B * Dk, d->H, dzk, d->H, Dk, d->T, g->proj_b[k], sk));
       if (g->dfeat[k]) {   // dF = dZ . W   (only for a trainable backbone: HHI --nofreeze)
         GemmArgs m;
         m.M = d->B * Dk; m.N = Kk; m.K = d->H;
@@ -584,13 +600,13 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
     LayerNormBwdArgs l; l.rows = M; l.H = H; l.dtype = dt; l.x = s->y2; l.stat = s->stat2; l.g = p->norm2_g;
     l.dy = dx_out; l.dx = w.d1; l.dg = g->norm2_g; l.db = g->norm2_b;
     if (pd > 0.f) { l.dx2 = w.d2; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DROP2, L); d2 = w.d2; }
+    l.dcol = g->lin2_b;            // db2 = colsum(d2) comes out of the same pass
     EGOT2_TRY(layernorm_bwd(l, st));
   }
-  //    linear2 (side): dW2 += d2^T . hid ; db2 += colsum(d2)
+  //    linear2 (side): dW2 += d2^T . hid
   {
     cudaStream_t ss = side_fork(st, sd0, 0);
     EGOT2_TRY(wgrad(dt, M, H, FF, d2, H, 0, 0, s->hid, FF, 0, 0, g->lin2_w, ss));
-    EGOT2_TRY(colsum_accum(dt, M, H, d2, H, 0, 0, g->lin2_b, ss));
   }
   //    dhid = (d2 . W2) * relu'(hid) * ffn-dropout scale ; d3 = dhid . W1 + d1 (residual branch)
   const bool fused_dx = s->hid_mask && ffn_fused_supported(dt, H, FF) && !env_is("EGOT2_FFN", "unfused");
@@ -621,13 +637,13 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
     LayerNormBwdArgs l; l.rows = M; l.H = H; l.dtype = dt; l.x = s->y1; l.stat = s->stat1; l.g = p->norm1_g;
     l.dy = w.d3; l.dx = w.d4; l.dg = g->norm1_g; l.db = g->norm1_b;
     if (pd > 0.f) { l.dx2 = w.d5; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DROP1, L); dyo = w.d5; }
+    l.dcol = g->out_proj_b;        // dbo = colsum(dyo) comes out of the same pass
     EGOT2_TRY(layernorm_bwd(l, st));
   }
   // 5. out_proj (side): dWo += dyo^T . attn ; dbo += colsum(dyo)      main: dattn = dyo . Wo  (d3 is free again)
   {
     cudaStream_t ss = side_fork(st, sd2, 2);
     EGOT2_TRY(wgrad(dt, M, H, H, dyo, H, 0, 0, s->attn, H, 0, 0, g->out_proj_w, ss));
-    EGOT2_TRY(colsum_accum(dt, M, H, dyo, H, 0, 0, g->out_proj_b, ss));
   }
   {
     GemmArgs m; m.M = M; m.N = H; m.K = H; m.A = dyo; m.lda = H; m.B = p->out_proj_w; m.ldb = H; m.trans_b = 0;

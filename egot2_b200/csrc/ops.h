@@ -55,6 +55,8 @@ struct LayerNormBwdArgs {
   int x_is_f32 = 0; int dx_is_f32 = 0; int dy_is_f32 = 0;
   // fused dropout sites (bf16 vector path; the generic path emulates them with extra launches):
   float dy_p_drop = 0.f; uint64_t dy_drop_key = 0;       // dy *= dropmask(row*H+c)/(1-p) on load (a dropout that FOLLOWED the LN)
+  float* dcol = nullptr;         // optional (H) +=: column sums of the gradient handed on (dx2 if given, else dx) = the bias
+                                 // gradient of the Linear layer that produced the LN input's residual branch
   void* dx2 = nullptr; float dx2_p_drop = 0.f; uint64_t dx2_drop_key = 0;   // second output: dx * dropmask/(1-p) (a dropout that PRECEDED
                                                                             // the residual add feeding this LN)
 };

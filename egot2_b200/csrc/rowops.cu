@@ -516,11 +516,11 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
   __shared__ float sred[8][2][HH];
   const float dy_keep = a.dy_p_drop > 0.f ? 1.f / (1.f - a.dy_p_drop) : 1.f;
   const float dx2_keep = a.dx2_p_drop > 0.f ? 1.f / (1.f - a.dx2_p_drop) : 1.f;
-  float g[V::SEG][8], dg[V::SEG][8], db[V::SEG][8];
+  float g[V::SEG][8], dg[V::SEG][8], db[V::SEG][8], dcs[V::SEG][8];
 #pragma unroll
   for (int s = 0; s < V::SEG; ++s)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { g[s][i] = a.g[(s * V::LPR + cl) * 8 + i]; dg[s][i] = 0.f; db[s][i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { g[s][i] = a.g[(s * V::LPR + cl) * 8 + i]; dg[s][i] = 0.f; db[s][i] = 0.f; dcs[s][i] = 0.f; }
   const int rows_per_iter = gridDim.x * 8 * V::RPW;
   // warp-uniform loop bound (row0): a sub-row past the end reads row0 again and contributes nothing
   // x, dy and the row statistics of the NEXT iteration are requested before this one is processed (see ln_fwd_vec_kernel)
@@ -597,7 +597,18 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
         unpack8(packed, o2);        // the unfused sequence masks the bf16-rounded dx
 #pragma unroll
         for (int i = 0; i < 8; ++i) o2[i] *= drop_scale(a.dx2_drop_key, (uint64_t)row * HH + c0 + i, a.dx2_p_drop, dx2_keep);
-        dx2p[s * V::LPR + cl] = pack8(o2);
+        const uint4 packed2 = pack8(o2);
+        dx2p[s * V::LPR + cl] = packed2;
+        if (a.dcol) {               // column sums of what the next Linear's backward sees (the rounded values)
+          unpack8(packed2, o2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dcs[s][i] += o2[i];
+        }
+      } else if (a.dcol) {
+        float o1[8];
+        unpack8(packed, o1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dcs[s][i] += o1[i];
       }
     }
   }
@@ -621,6 +632,24 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += sred[w][which][col];
       atomicAdd((which ? a.db : a.dg) + col, t);
+    }
+  }
+  if (a.dcol) {
+    __syncthreads();                           // sred is reused
+#pragma unroll
+    for (int s = 0; s < V::SEG; ++s)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = V::LPR; o < 32; o <<= 1) dcs[s][i] += __shfl_xor_sync(0xffffffffu, dcs[s][i], o);
+        if (sub == 0) sred[warp][0][(s * V::LPR + cl) * 8 + i] = dcs[s][i];
+      }
+    __syncthreads();
+    for (int col = threadIdx.x; col < HH; col += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sred[w][0][col];
+      atomicAdd(a.dcol + col, t);
     }
   }
 }
@@ -719,7 +748,14 @@ int layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t st) {
       case 512: return ln_bwd_vec_launch<512>(a, st);     // H = 1024 would need 64 KB of static reduction smem
     }
   }
-  // generic path: the fused dropout sites become separate launches around the LayerNorm kernel
+  // generic path: the fused dropout sites / column sums become separate launches around the LayerNorm kernel
+  if (a.dcol) {
+    LayerNormBwdArgs b = a;
+    b.dcol = nullptr;
+    EGOT2_TRY(layernorm_bwd(b, st));
+    EGOT2_CHECK(!a.dx_is_f32, "layernorm_bwd: fused column sums need dtype dx");
+    return colsum_accum(a.dtype, a.rows, a.H, a.dx2 ? a.dx2 : a.dx, a.H, 0, 0, a.dcol, st);
+  }
   if (a.dy_p_drop > 0.f || a.dx2) {
     LayerNormBwdArgs b = a;
     b.dy_p_drop = 0.f; b.dx2 = nullptr;
