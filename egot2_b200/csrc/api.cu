@@ -604,10 +604,15 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
     EGOT2_TRY(layernorm_bwd(l, st));
   }
   //    linear2 (side): dW2 += d2^T . hid
-  {
+  // EGOT2_LATE_WGRAD=1 forks the two big weight-gradient GEMMs only after the LayerNorm1 backward instead of right after
+  // their producers (their long-lived CTAs cannot be pre-empted and slow the short chain kernels behind the fused FFN
+  // backward).  Measured: 333.6 vs 330.5 us per step - the work only moves into the backlog before the join - so off.
+  static const bool late_wgrad = env_is("EGOT2_LATE_WGRAD", "1");
+  auto fork_dw2 = [&]() -> int {
     cudaStream_t ss = side_fork(st, sd0, 0);
-    EGOT2_TRY(wgrad(dt, M, H, FF, d2, H, 0, 0, s->hid, FF, 0, 0, g->lin2_w, ss));
-  }
+    return wgrad(dt, M, H, FF, d2, H, 0, 0, s->hid, FF, 0, 0, g->lin2_w, ss);
+  };
+  if (!late_wgrad) EGOT2_TRY(fork_dw2());
   //    dhid = (d2 . W2) * relu'(hid) * ffn-dropout scale ; d3 = dhid . W1 + d1 (residual branch)
   const bool fused_dx = s->hid_mask && ffn_fused_supported(dt, H, FF) && !env_is("EGOT2_FFN", "unfused");
   if (fused_dx) {
@@ -623,14 +628,16 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
     EGOT2_TRY(gemm(n, st));
   }
   // 3. linear1 (side): dW1 += dhid^T . x1 ; db1 += colsum(dhid)
-  {
+  auto fork_dw1 = [&]() -> int {
     cudaStream_t ss = side_fork(st, sd1, 1);
     EGOT2_TRY(wgrad(dt, M, FF, H, w.dhid, FF, 0, 0, s->x1, H, 0, 0, g->lin1_w, ss));
     if (!fused_dx) {
       cudaStream_t s2 = side_fork(st, sd2, 1);    // the bias sum reads dhid beside the GEMM (both mostly from L2)
       EGOT2_TRY(colsum_accum(dt, M, FF, w.dhid, FF, 0, 0, g->lin1_b, s2));
     }
-  }
+    return 0;
+  };
+  if (!late_wgrad) EGOT2_TRY(fork_dw1());
   // 4. through norm1: d4 = dL/dy1, and (same kernel) d5 = dropout1 mask applied to it = dL/d(out_proj out)
   const void* dyo = w.d4;
   {
@@ -640,6 +647,7 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
     l.dcol = g->out_proj_b;        // dbo = colsum(dyo) comes out of the same pass
     EGOT2_TRY(layernorm_bwd(l, st));
   }
+  if (late_wgrad) { EGOT2_TRY(fork_dw2()); EGOT2_TRY(fork_dw1()); }
   // 5. out_proj (side): dWo += dyo^T . attn ; dbo += colsum(dyo)      main: dattn = dyo . Wo  (d3 is free again)
   {
     cudaStream_t ss = side_fork(st, sd2, 2);
