@@ -58,8 +58,19 @@ class ParamArena:
 
         head_w = [n for n in shapes if re.fullmatch(r"head\.projections\.\d+\.weight", n)]
         head_b = [n for n in shapes if re.fullmatch(r"head\.projections\.\d+\.bias", n)]
+        # The embedding-stage parameters (per-task projections, task/positional embeddings, the shared LayerNorm) come
+        # FIRST and contiguous: their gradients are the last ones backward produces, so under data parallelism the rest
+        # of the arena [embed_numel:] can be all-reduced while the embedding backward still runs (trainer.py).
+        proj_names = {s.proj for s in spec.segments if s.proj is not None}
+        def _is_embed(n):
+            return n.rsplit(".", 1)[0] in proj_names or n in ("task_embed", "pe", "ln.weight", "ln.bias")
         for name, shp in shapes.items():
-            if name in head_w or name in head_b:
+            if _is_embed(name):
+                place(name, _numel(shp))
+        self.embed_numel = (off + _ALIGN - 1) // _ALIGN * _ALIGN
+        off = self.embed_numel
+        for name, shp in shapes.items():
+            if name in head_w or name in head_b or _is_embed(name):
                 continue
             place(name, _numel(shp))
         for i, name in enumerate(head_w):      # contiguous block, no padding between heads
@@ -518,20 +529,32 @@ class TranslatorEngine:
     # ------------------------------------------------------------------ backward
     def backward(self, act: Activations, dout: Optional[torch.Tensor] = None, dloss_scale: float = 1.0,
                  grad: Optional[torch.Tensor] = None, zero_grad: bool = True,
-                 want_dfeat: Sequence[bool] = ()) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+                 want_dfeat: Sequence[bool] = (), stage: str = "all") -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
         """Gradients of every translator parameter, accumulated into `grad` (a flat fp32 buffer with the
         arena layout; default: arena.grad).  `dout`: gradient w.r.t. the forward output when the loss was
         computed outside (drop-in autograd path); with a fused loss pass dloss_scale instead."""
         sp = self.spec
         B, T, H = act.B, act.T, sp.hidden
         grad = self.arena.grad if grad is None else grad
-        if zero_grad:
+        assert stage in ("all", "pre_embed", "embed")
+        if zero_grad and stage != "embed":
             grad.zero_()
         st = _stream()
         tdt, dev = self.tdt, self.device
         t = act.t
         gv = lambda name: self.arena.view(name, grad)
-        dx = torch.empty((B, T, H), device=dev, dtype=tdt)
+        # stage = "pre_embed" | "embed": the two halves of backward as separate calls (separate CUDA graphs in the
+        # data-parallel trainer, so that most of the gradient all-reduce overlaps the embedding backward); the gradient
+        # w.r.t. the encoder input then lives in a persistent buffer between the two
+        if stage == "all":
+            dx = torch.empty((B, T, H), device=dev, dtype=tdt)
+        else:
+            assert sp.head != "decoder", "staged backward is not wired for the EgoT2-g decoder head"
+            if "dx_chain" not in t:
+                t["dx_chain"] = torch.empty((B, T, H), device=dev, dtype=tdt)
+            dx = t["dx_chain"]
+        if stage == "embed":
+            return self._embed_backward(act, dx, grad, gv, want_dfeat)
 
         # ---- head
         if sp.head == "decoder":
@@ -569,6 +592,14 @@ class TranslatorEngine:
             L.call("egot2_encoder_layer_bwd", C.byref(ld), C.byref(act.layer_params[i]), x_in.data_ptr(),
                    C.byref(act.layer_saved[i]), dx.data_ptr(), dx.data_ptr(), C.byref(lg), ws.data_ptr(), ws.numel(), st)
 
+        if stage == "pre_embed":
+            return grad, [None] * len(sp.segments)
+        return self._embed_backward(act, dx, grad, gv, want_dfeat)
+
+    def _embed_backward(self, act: Activations, dx: torch.Tensor, grad: torch.Tensor, gv, want_dfeat):
+        sp = self.spec
+        B, T, H = act.B, act.T, sp.hidden
+        dev, st = self.device, _stream()
         # ---- embed
         eg = L.EmbedGrads()
         dfeats: List[Optional[torch.Tensor]] = [None] * len(sp.segments)

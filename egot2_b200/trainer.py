@@ -129,6 +129,14 @@ class TranslatorTrainer:
         # N > 1: capturing torch.distributed's NCCL all-reduce hung on the 2xB200 box (round 1), so the data-parallel step
         # keeps [graph: forward+backward] -> eager all-reduce -> eager fused Adam unless forced with EGOT2_GRAPH_UPDATE=force
         self.graph_update = gu == "force" or (gu != "0" and self.world == 1)
+        # N > 1 with graphs: the step is TWO graphs - [forward + backward down to the encoder input] and [embedding
+        # backward] - so that the all-reduce of everything but the embedding-stage gradients (arena[embed_numel:],
+        # most of the bytes) runs on NCCL's stream WHILE the second graph executes; only the small embedding bucket is
+        # reduced after it.  EGOT2_DP_OVERLAP=0: one graph, one all-reduce behind it.
+        ov = os.environ.get("EGOT2_DP_OVERLAP", "1")       # "force": also with one rank (tests; needs an initialised group)
+        self.dp_overlap = ((self.world > 1 and ov != "0") or ov == "force") and spec.head != "decoder"
+        if self.dp_overlap:
+            self.graph_update = False
         self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
         self._step_dev_val = 0
         self._bump_stream = torch.cuda.Stream(device=self.device)
@@ -144,11 +152,11 @@ class TranslatorTrainer:
         return self.engine.arena.state_dict()
 
     # ------------------------------------------------------------------ device-resident step
-    def _fwd_bwd(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, seed: int) -> Activations:
+    def _fwd_bwd(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, seed: int, stage: str = "all") -> Activations:
         act = self.engine.forward(feats, training=True, seed=seed, labels=labels, loss=self.loss_kind,
                                   class_weight=self.class_weight, persistent=True)
         # the fused Adam of the previous step left the gradient arena cleared (and the bf16 shadow current)
-        self.engine.backward(act, zero_grad=not self._grad_clean)
+        self.engine.backward(act, zero_grad=not self._grad_clean, stage=stage)
         self._grad_clean = False
         return act
 
@@ -162,6 +170,8 @@ class TranslatorTrainer:
             entry = self._graphs.get(graph_key)
             if entry is None:
                 entry = self._capture(feats, labels, graph_key)
+            if len(entry) == 3:                           # data-parallel, two graphs with the all-reduce in between
+                return self._dp_overlap_step(entry)
             graph, act = entry
             if not self._grad_clean:                      # e.g. the first graphed step after eager ones
                 self.engine.arena.grad.zero_()
@@ -179,6 +189,25 @@ class TranslatorTrainer:
         else:
             act = self._fwd_bwd(feats, labels, seed=self.step_count)
         self._reduce_and_update()
+        return act.t["loss"][0]
+
+    def _dp_overlap_step(self, entry):
+        import torch.distributed as dist
+        g1, g2, act = entry
+        eng = self.engine
+        if not self._grad_clean:
+            eng.arena.grad.zero_()
+        if eng.dtype == "bf16" and not eng.arena.shadow_fresh:
+            eng.arena.refresh_shadow()
+        nb = eng.arena.embed_numel
+        g1.replay()                                       # forward + backward of head and encoder layers
+        work = dist.all_reduce(eng.arena.grad[nb:], group=self.pg, async_op=True)      # overlaps the embedding backward
+        g2.replay()
+        dist.all_reduce(eng.arena.grad[:nb], group=self.pg)
+        work.wait()
+        eng.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
+                      self.hp["weight_decay"], grad_scale=1.0 / self.world, fused=True)
+        self._grad_clean = True
         return act.t["loss"][0]
 
     def _capture(self, feats, labels, key):
@@ -204,6 +233,15 @@ class TranslatorTrainer:
                 allreduce_gradients(self.engine.arena.grad, self.pg)
             self._step_dev.fill_(self.step_count - 1)
             self._step_dev_val = self.step_count - 1
+        if self.dp_overlap and not self.graph_update:
+            torch.cuda.synchronize(self.device)
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                act = self._fwd_bwd(feats, labels, seed=1 + key, stage="pre_embed")
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self.engine.backward(act, zero_grad=False, stage="embed")
+            self._graphs[key] = (g1, g2, act)
+            return self._graphs[key]
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
