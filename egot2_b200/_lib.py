@@ -110,6 +110,10 @@ SIGNATURES = {
     "egot2_last_error": (C.c_char_p, []),
     "egot2_sm_count": (C.c_int, []),
     "egot2_launch_count": (C.c_uint64, []),
+    "egot2_dropout_epoch_enable": (C.c_int, [C.c_int]),
+    "egot2_dropout_epoch_set": (C.c_int, [u64, vp]),
+    "egot2_dropout_epoch_advance": (C.c_int, [vp]),
+    "egot2_dropout_epoch_host": (C.c_int, [u64]),
     "egot2_prof_enable": (C.c_int, [C.c_int]),
     "egot2_timeline_set": (C.c_int, [vp]),
     "egot2_prof_report": (C.c_int, [C.c_char_p, sz]),

@@ -25,6 +25,19 @@ static int g_tl_n = 0;
 void tl_register(void (*setter)(unsigned long long*)) { if (g_tl_n < 32) g_tl_setters[g_tl_n++] = setter; }
 #endif
 
+// ---- dropout epoch (common.cuh): registry of the per-translation-unit slot pointers + the library-owned slot
+unsigned long long g_host_epoch = 0;
+static void (*g_epoch_setters[32])(const unsigned long long*);
+static int g_epoch_n = 0;
+void epoch_register(void (*setter)(const unsigned long long*)) { if (g_epoch_n < 32) g_epoch_setters[g_epoch_n++] = setter; }
+namespace {
+__global__ void epoch_advance_kernel(unsigned long long* slot, unsigned long long add) {
+  EGOT2_PDL_ENTER();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *slot += add;
+}
+unsigned long long* g_epoch_slot = nullptr;
+}  // namespace
+
 bool pdl_enabled() {
   static const bool on = !(getenv("EGOT2_PDL") && atoi(getenv("EGOT2_PDL")) == 0);
   return on;
@@ -236,6 +249,33 @@ extern "C" int egot2_timeline_set(void* dev_buf) {
   EGOT2_CHECK(false, "this build has no timeline support (compile with -DEGOT2_TIMELINE)");
 #endif
 }
+
+extern "C" int egot2_dropout_epoch_enable(int on) {
+  if (on && !g_epoch_slot) {
+    EGOT2_CUDA(cudaMalloc(&g_epoch_slot, sizeof(unsigned long long)));
+    EGOT2_CUDA(cudaMemset(g_epoch_slot, 0, sizeof(unsigned long long)));
+  }
+  const unsigned long long* p = on ? g_epoch_slot : nullptr;
+  for (int i = 0; i < g_epoch_n; ++i) g_epoch_setters[i](p);       // cudaMemcpyToSymbol: not under stream capture
+  EGOT2_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int egot2_dropout_epoch_set(uint64_t value, void* stream) {
+  EGOT2_CHECK(g_epoch_slot != nullptr, "dropout epoch: call egot2_dropout_epoch_enable(1) first");
+  EGOT2_CUDA(cudaMemsetAsync(g_epoch_slot, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+  if (value) {
+    launch(epoch_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, g_epoch_slot, (unsigned long long)value);
+    EGOT2_LAUNCH_CHECK();
+  }
+  return 0;
+}
+extern "C" int egot2_dropout_epoch_advance(void* stream) {
+  EGOT2_CHECK(g_epoch_slot != nullptr, "dropout epoch: call egot2_dropout_epoch_enable(1) first");
+  launch(epoch_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, g_epoch_slot, 1ull);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int egot2_dropout_epoch_host(uint64_t value) { g_host_epoch = value; return 0; }
 
 extern "C" int egot2_prof_enable(int on) {
   if (on && !g_prof) {

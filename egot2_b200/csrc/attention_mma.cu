@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
   constexpr int NW = (TK16 + 1) / 2;           // 32-key mask words per query row
   uint32_t w0[NW], w1[NW];
   if (MODE == 1) {
-    mask_words<NW>(drop_key, (uint64_t)bh * T + q0, (T + 31) >> 5, 2 * (lane & 3), w0);
-    mask_words<NW>(drop_key, (uint64_t)bh * T + q1, (T + 31) >> 5, 2 * (lane & 3), w1);
+    mask_words<NW>(drop_key ^ egot2_ep, (uint64_t)bh * T + q0, (T + 31) >> 5, 2 * (lane & 3), w0);
+    mask_words<NW>(drop_key ^ egot2_ep, (uint64_t)bh * T + q1, (T + 31) >> 5, 2 * (lane & 3), w1);
   }
   // MODE 1 keeps e or zeroes it; the 1/(1-p) = 2 of the kept entries is folded into the final row scale (exact: power of 2)
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -212,10 +212,10 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
       e2 = (m1 & 1u) ? e2 : 0.f; e3 = (m1 & 2u) ? e3 : 0.f;
     } else if (MODE == 2) {
       const int c = nt * 8 + 2 * (lane & 3);
-      e0 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q0, T, c, p_drop, inv_keep);
-      e1 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q0, T, c + 1, p_drop, inv_keep);
-      e2 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q1, T, c, p_drop, inv_keep);
-      e3 *= attn_drop_scale(drop_key, (uint64_t)bh * T + q1, T, c + 1, p_drop, inv_keep);
+      e0 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q0, T, c, p_drop, inv_keep);
+      e1 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q0, T, c + 1, p_drop, inv_keep);
+      e2 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q1, T, c, p_drop, inv_keep);
+      e3 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q1, T, c + 1, p_drop, inv_keep);
     }
     p[nt >> 1][(nt & 1) * 2] = pack_bf16(e0, e1);
     p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(e2, e3);
@@ -309,8 +309,8 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
     const float la = sL[ra], lb = sL[rb], da = sD[ra], db = sD[rb];
     uint32_t wa[NW], wb[NW];
     if (MODE == 1) {
-      mask_words<NW>(drop_key, (uint64_t)bh * T + ra, (T + 31) >> 5, 2 * (lane & 3), wa);
-      mask_words<NW>(drop_key, (uint64_t)bh * T + rb, (T + 31) >> 5, 2 * (lane & 3), wb);
+      mask_words<NW>(drop_key ^ egot2_ep, (uint64_t)bh * T + ra, (T + 31) >> 5, 2 * (lane & 3), wa);
+      mask_words<NW>(drop_key ^ egot2_ep, (uint64_t)bh * T + rb, (T + 31) >> 5, 2 * (lane & 3), wb);
     }
     float o[Tile<DH>::ND][4];
 #pragma unroll
@@ -338,10 +338,10 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
           g2 = (m1 & 1u) ? g2 + g2 : 0.f; g3 = (m1 & 2u) ? g3 + g3 : 0.f;
         } else if (MODE == 2) {
           const int c = kb * 16 + h2 * 8 + 2 * (lane & 3);
-          g0 *= attn_drop_scale(drop_key, (uint64_t)bh * T + ra, T, c, p_drop, inv_keep);
-          g1 *= attn_drop_scale(drop_key, (uint64_t)bh * T + ra, T, c + 1, p_drop, inv_keep);
-          g2 *= attn_drop_scale(drop_key, (uint64_t)bh * T + rb, T, c, p_drop, inv_keep);
-          g3 *= attn_drop_scale(drop_key, (uint64_t)bh * T + rb, T, c + 1, p_drop, inv_keep);
+          g0 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + ra, T, c, p_drop, inv_keep);
+          g1 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + ra, T, c + 1, p_drop, inv_keep);
+          g2 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + rb, T, c, p_drop, inv_keep);
+          g3 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + rb, T, c + 1, p_drop, inv_keep);
         }
         ds[h2 * 2] = pack_bf16(p0 * (g0 - da), p1 * (g1 - da));
         ds[h2 * 2 + 1] = pack_bf16(p2 * (g2 - db), p3 * (g3 - db));
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
 #pragma unroll
       for (int j = 0; j < NW; ++j) {
         const int qy = lane + 32 * j;
-        wq[j] = qy < T ? drop_bits(drop_key, ((uint64_t)bh * T + qy) * (uint64_t)((T + 31) >> 5) + (uint32_t)(r0 >> 5)) : 0u;
+        wq[j] = qy < T ? drop_bits(drop_key ^ egot2_ep, ((uint64_t)bh * T + qy) * (uint64_t)((T + 31) >> 5) + (uint32_t)(r0 >> 5)) : 0u;
       }
     }
     float ov[Tile<DH>::ND][4], ok[Tile<DH>::ND][4];
@@ -399,10 +399,10 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
           m2 = (u0 & 0x100u) ? 2.f : 0.f;
           m3 = (u1 & 0x100u) ? 2.f : 0.f;
         } else if (MODE == 2) {
-          m0 = attn_drop_scale(drop_key, (uint64_t)bh * T + c, T, ra, p_drop, inv_keep);
-          m1 = attn_drop_scale(drop_key, (uint64_t)bh * T + c + 1, T, ra, p_drop, inv_keep);
-          m2 = attn_drop_scale(drop_key, (uint64_t)bh * T + c, T, rb, p_drop, inv_keep);
-          m3 = attn_drop_scale(drop_key, (uint64_t)bh * T + c + 1, T, rb, p_drop, inv_keep);
+          m0 = attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + c, T, ra, p_drop, inv_keep);
+          m1 = attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + c + 1, T, ra, p_drop, inv_keep);
+          m2 = attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + c, T, rb, p_drop, inv_keep);
+          m3 = attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + c + 1, T, rb, p_drop, inv_keep);
         }
         pf[h2 * 2] = pack_bf16(p0 * m0, p1 * m1);
         pf[h2 * 2 + 1] = pack_bf16(p2 * m2, p3 * m3);

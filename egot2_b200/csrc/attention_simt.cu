@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(int Tn, int H, int he
         float p = j < nk ? expf(s[jj] - m_new) : 0.f;
         psum += p;
         if (p_drop > 0.f)
-          p *= attn_drop_scale(drop_key, (uint64_t)bh * Tn + qi, Tn, k0 + j, p_drop, inv_keep);
+          p *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * Tn + qi, Tn, k0 + j, p_drop, inv_keep);
         Ps[warp][j] = p;
       }
       l[r] = l[r] * corr + warp_sum(psum);
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_dq_kernel(int Tn, int H, int
         if (j < nk) {
           const float p = expf(s - L[r]);
           if (p_drop > 0.f)
-            dp *= attn_drop_scale(drop_key, (uint64_t)bh * Tn + qi, Tn, k0 + j, p_drop, inv_keep);
+            dp *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * Tn + qi, Tn, k0 + j, p_drop, inv_keep);
           ds = p * (dp - Di[r]);
         }
         Ps[warp][j] = ds;
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_dkv_kernel(int Tn, int H, in
         if (i < nq) {
           const float p = expf(s - Ls[i]);
           float mk = 1.f;
-          if (p_drop > 0.f) mk = attn_drop_scale(drop_key, (uint64_t)bh * Tn + (i0 + i), Tn, kj, p_drop, inv_keep);
+          if (p_drop > 0.f) mk = attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * Tn + (i0 + i), Tn, kj, p_drop, inv_keep);
           pd = p * mk;
           ds = p * (dp * mk - Ds[i]);
         }

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(WARPS * 32) small_attn_fwd_kernel(const SmallA
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   for (int j = lane; j < nk; j += 32) {
     float p = sc[warp][j] * inv;
-    if (a.p_drop > 0.f) p *= drop_scale(a.drop_key, (uint64_t)qid * a.M + j, a.p_drop, inv_keep);
+    if (a.p_drop > 0.f) p *= drop_scale(a.drop_key ^ egot2_ep, (uint64_t)qid * a.M + j, a.p_drop, inv_keep);
     sc[warp][j] = p;
   }
   if (lane == 0 && a.lse) a.lse[qid] = mx + logf(sum);
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(WARPS * 32) small_attn_bwd_kernel(const SmallA
     float dp = 0.f;
     for (int c = 0; c < dh; ++c) dp = fmaf(sdo[warp][c], to_f32(v[c]), dp);
     const float p = sp[warp][j] * inv;
-    const float mk = a.p_drop > 0.f ? drop_scale(a.drop_key, (uint64_t)qid * a.M + j, a.p_drop, inv_keep) : 1.f;
+    const float mk = a.p_drop > 0.f ? drop_scale(a.drop_key ^ egot2_ep, (uint64_t)qid * a.M + j, a.p_drop, inv_keep) : 1.f;
     spd[warp][j] = p * mk;
     dsum += p * dp * mk;                   // dp * mk = gradient w.r.t. the un-dropped probability
     sp[warp][j] = p;

@@ -81,9 +81,32 @@ __device__ __forceinline__ void tl_stamp(unsigned loc) {
 #ifndef EGOT2_FILE_ID
 #define EGOT2_FILE_ID 0
 #endif
+// ---- dropout epoch: a device-resident counter folded into every dropout key at execution time, so that a CUDA graph that
+// is replayed step after step draws a fresh mask each time although its kernels' key arguments are frozen at capture.
+// effective key = key ^ (epoch * golden ratio); the epoch lives in a library-owned 8-byte slot (egot2_dropout_epoch_*):
+// advanced by a one-thread kernel (graph-capturable), or, for tests, emulated on the host side (the launchers then fold
+// the same term into the keys they pass).  Off (pointer null) unless enabled: keys are then exactly the host-computed ones.
+// Each translation unit holds its own copy of the slot pointer (no relocatable device code), set through epoch_register.
+void epoch_register(void (*setter)(const unsigned long long*));
+static __device__ const unsigned long long* epoch_slot_dev = nullptr;
+namespace {
+struct EpochReg {
+  EpochReg() { epoch_register([](const unsigned long long* p) { cudaMemcpyToSymbol(epoch_slot_dev, &p, sizeof(p)); }); }
+};
+static EpochReg epoch_reg_instance;
+}  // namespace
+constexpr unsigned long long kEpochMul = 0x9E3779B97F4A7C15ULL;
+__device__ __forceinline__ unsigned long long epoch_xor() {
+  const unsigned long long* p = epoch_slot_dev;
+  return p ? *p * kEpochMul : 0ull;
+}
+extern unsigned long long g_host_epoch;      // host-side emulation (tests): folded into site_key() on the host
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#define EGOT2_PDL_ENTER() do { ::egot2::pdl_launch_dependents(); ::egot2::pdl_wait(); EGOT2_TL(EGOT2_FILE_ID); } while (0)
+// first statement(s) of every kernel; also defines egot2_ep, the dropout-epoch term every key use is XORed with
+#define EGOT2_PDL_ENTER()                                                                    \
+  ::egot2::pdl_launch_dependents(); ::egot2::pdl_wait(); EGOT2_TL(EGOT2_FILE_ID);            \
+  const unsigned long long egot2_ep = ::egot2::epoch_xor(); (void)egot2_ep
 bool pdl_enabled();
 // Launch priority: kernels on the caller's stream (the data-gradient / forward chain, i.e. the critical path) outrank the
 // library's side-stream kernels (parameter gradients), so when both have CTAs waiting for an SM the chain goes first and
@@ -157,7 +180,12 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 __host__ __device__ __forceinline__ uint64_t site_key(uint64_t seed, uint32_t site, uint32_t layer) {
-  return mix64(seed ^ (0x9E3779B97F4A7C15ULL * (uint64_t)(site + 16u * layer + 1u)));
+  const uint64_t k = mix64(seed ^ (0x9E3779B97F4A7C15ULL * (uint64_t)(site + 16u * layer + 1u)));
+#ifndef __CUDA_ARCH__
+  return k ^ (g_host_epoch * kEpochMul);     // host-side epoch emulation (0 unless a test sets it)
+#else
+  return k;
+#endif
 }
 // 32 random bits for element `idx` of the dropout site `key`: a two-multiply xorshift hash (lowbias32-style) of the
 // 32-bit element index, keyed by both halves of the 64-bit site key.  ~7 integer instructions per element.

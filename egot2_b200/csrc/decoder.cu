@@ -77,7 +77,7 @@ __global__ void prompt_embed_fwd_kernel(int rows, int S, int H, const int64_t* _
   const float* e = emb + (size_t)tok[r] * H;
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float v = e[c] * sc + pe[(size_t)s * H + c];
-    if (p > 0.f) v *= drop_scale(key, (uint64_t)r * H + c, p, inv_keep);
+    if (p > 0.f) v *= drop_scale(key ^ egot2_ep, (uint64_t)r * H + c, p, inv_keep);
     y[(size_t)r * H + c] = from_f32<T>(v);
   }
 }
@@ -90,7 +90,7 @@ __global__ void prompt_embed_bwd_kernel(int rows, int S, int H, const int64_t* _
   float* e = demb + (size_t)tok[r] * H;
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float v = to_f32(dy[(size_t)r * H + c]) * sc;
-    if (p > 0.f) v *= drop_scale(key, (uint64_t)r * H + c, p, inv_keep);
+    if (p > 0.f) v *= drop_scale(key ^ egot2_ep, (uint64_t)r * H + c, p, inv_keep);
     atomicAdd(e + c, v);
   }
 }

@@ -193,6 +193,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
   pdl_wait();                    // first global-memory access of the kernel is below
   EGOT2_TL(EGOT2_FILE_ID);
+  const unsigned long long egot2_ep = epoch_xor();
   if (BWD) {                     // sB1 doubles as this CTA's db1 accumulator (the forward's bias stage is not needed)
     for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = 0.f;
   }
@@ -396,11 +397,11 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           // its bit set and the value 0, which only matters for the measure-zero relu'(0) convention)
           uint32_t keep;
           if constexpr (DROP == 1) {
-            keep = drop_bits(a.key_ffn, idx0 >> 5);
+            keep = drop_bits(a.key_ffn ^ egot2_ep, idx0 >> 5);
           } else if constexpr (DROP == 2) {
             keep = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) keep |= (drop_bits(a.key_ffn, idx0 + j) >= thr ? 1u : 0u) << j;
+            for (int j = 0; j < 32; ++j) keep |= (drop_bits(a.key_ffn ^ egot2_ep, idx0 + j) >= thr ? 1u : 0u) << j;
           } else {
             keep = 0xFFFFFFFFu;
           }
@@ -546,8 +547,8 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const int j = j8 * 8 + 2 * k;
           float v0 = __uint_as_float(rr[2 * k]) + sVec[nb + j], v1 = __uint_as_float(rr[2 * k + 1]) + sVec[nb + j + 1];
           if constexpr (DROP != 0) {
-            v0 = drop_bits(a.key_drop2, (uint64_t)m * H + nb + j) >= thr ? v0 * inv_keep : 0.f;
-            v1 = drop_bits(a.key_drop2, (uint64_t)m * H + nb + j + 1) >= thr ? v1 * inv_keep : 0.f;
+            v0 = drop_bits(a.key_drop2 ^ egot2_ep, (uint64_t)m * H + nb + j) >= thr ? v0 * inv_keep : 0.f;
+            v1 = drop_bits(a.key_drop2 ^ egot2_ep, (uint64_t)m * H + nb + j + 1) >= thr ? v1 * inv_keep : 0.f;
           }
           v0 += __uint_as_float(w[k] << 16);
           v1 += __uint_as_float(w[k] & 0xffff0000u);
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(256) ffn_fixup_fwd_kernel(int rows, int m_base
     const float inv_keep = 1.f / (1.f - p_drop);
     const uint32_t thr = drop_threshold(p_drop);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = drop_bits(key_drop2, (uint64_t)m * H + c0 + i) >= thr ? v[i] * inv_keep : 0.f;
+    for (int i = 0; i < 4; ++i) v[i] = drop_bits(key_drop2 ^ egot2_ep, (uint64_t)m * H + c0 + i) >= thr ? v[i] * inv_keep : 0.f;
   }
   v[0] += __uint_as_float(xw.x << 16); v[1] += __uint_as_float(xw.x & 0xffff0000u);
   v[2] += __uint_as_float(xw.y << 16); v[3] += __uint_as_float(xw.y & 0xffff0000u);

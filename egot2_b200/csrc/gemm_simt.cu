@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs a) {
       if (a.bias && first_split) v += __ldg(a.bias + n);
       if (a.relu) v = fmaxf(v, 0.f);
       if (a.mask) v = to_f32(((const TO*)a.mask)[(long long)m * a.ldm + n]) > 0.f ? v * a.mask_scale : 0.f;
-      if (a.p_drop > 0.f) v *= drop_scale(a.drop_key, (uint64_t)m * a.N + n, a.p_drop, inv_keep, a.drop_bit_mode != 0);
+      if (a.p_drop > 0.f) v *= drop_scale(a.drop_key ^ egot2_ep, (uint64_t)m * a.N + n, a.p_drop, inv_keep, a.drop_bit_mode != 0);
       if (a.residual && first_split) v += to_f32(((const TO*)a.residual)[(long long)m * a.ldr + n]);
       TO* dst = C + crow * a.ldc + n;
       if (a.accumulate) {

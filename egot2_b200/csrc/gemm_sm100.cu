@@ -141,6 +141,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
   pdl_wait();                   // everything above touched only kernel parameters, shared memory and TMEM
   EGOT2_TL(EGOT2_FILE_ID);
+  const unsigned long long egot2_ep = epoch_xor();
   float* sbias = reinterpret_cast<float*>(smem_raw + (bias_off - smem_u32(smem_raw)));
   tc_fence_before();
   __syncthreads();
@@ -288,7 +289,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           }
           if (e.p_drop > 0.f) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key, (uint64_t)m * e.N + nb + j, e.p_drop, inv_keep, e.drop_bit_mode != 0);
+            for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key ^ egot2_ep, (uint64_t)m * e.N + nb + j, e.p_drop, inv_keep, e.drop_bit_mode != 0);
           }
           if (res_row) {
             if (mask_row) load32(res_row + nb, aux);
@@ -335,7 +336,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             if (bias) x += sb[c0 + j];
             if (e.relu) x = fmaxf(x, 0.f);
             if (mask_row) x = to_f32(mask_row[n]) > 0.f ? x * e.mask_scale : 0.f;
-            if (e.p_drop > 0.f) x *= drop_scale(e.drop_key, (uint64_t)m * e.N + n, e.p_drop, inv_keep, e.drop_bit_mode != 0);
+            if (e.p_drop > 0.f) x *= drop_scale(e.drop_key ^ egot2_ep, (uint64_t)m * e.N + n, e.p_drop, inv_keep, e.drop_bit_mode != 0);
             if (res_row) x += to_f32(res_row[n]);
             if (e.accumulate) {
               if constexpr (sizeof(TO) == 4) {

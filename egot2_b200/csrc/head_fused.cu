@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NT) head_fwd_kernel(int T, int H, int n_out, c
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   for (int c = threadIdx.x; c < H; c += NT) {
     float g = (ps[c] - mean) * rstd * ln_g[c] + ln_b[c];
-    if (p_drop > 0.f) g *= drop_scale(drop_key, (uint64_t)row * H + c, p_drop, inv_keep);
+    if (p_drop > 0.f) g *= drop_scale(drop_key ^ egot2_ep, (uint64_t)row * H + c, p_drop, inv_keep);
     const TT gr = from_f32<TT>(g);
     g_out[(size_t)row * H + c] = gr;
     gs[c] = to_f32(gr);
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(int T, int H, int n_out, c
       dg += dl[j] * to_f32(W[(size_t)j * H + c]);
       if (dW) atomicAdd(dW + (size_t)j * H + c, dl[j] * gsv);
     }
-    if (p_drop > 0.f) dg *= drop_scale(drop_key, (uint64_t)row * H + c, p_drop, inv_keep);
+    if (p_drop > 0.f) dg *= drop_scale(drop_key ^ egot2_ep, (uint64_t)row * H + c, p_drop, inv_keep);
     const float xh = (pooled[(size_t)row * H + c] - mean) * rstd;
     if (d_ln_g) { atomicAdd(d_ln_g + c, dg * xh); atomicAdd(d_ln_b + c, dg); }
     const float dyg = dg * ln_g[c];

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) ln_fwd_kernel(const LayerNo
       const int c = lane + 32 * i;
       float o = (v[i] - mean) * rstd * g[i] + b[i];
       if (tab) o += tab[c];
-      if (a.p_drop > 0.f) o *= drop_scale(a.drop_key, (uint64_t)row * H + c, a.p_drop, inv_keep);
+      if (a.p_drop > 0.f) o *= drop_scale(a.drop_key ^ egot2_ep, (uint64_t)row * H + c, a.p_drop, inv_keep);
       y[c] = from_f32<TY>(o);
     }
   }
@@ -121,7 +121,7 @@ __global__ void table_grad_kernel(int B, int T, int H, int clips_per_cta, const 
       const float inv_keep = 1.f / (1.f - p_drop);
       for (int b = b0; b < b1; ++b) {
         const size_t idx = ((size_t)b * T + t) * H + c;
-        s += to_f32(dy[idx]) * drop_scale(drop_key, idx, p_drop, inv_keep);
+        s += to_f32(dy[idx]) * drop_scale(drop_key ^ egot2_ep, idx, p_drop, inv_keep);
       }
     } else {
       for (int b = b0; b < b1; ++b) s += to_f32(dy[((size_t)b * T + t) * H + c]);
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(128) table_grad_vec_kernel(int B, int T, int H
     for (int k = 0; k < 4; ++k) {
       float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
       if (p_drop > 0.f) {
-        lo = drop_bits(drop_key, idx + 2 * k) >= thr ? lo * inv_keep : 0.f;
-        hi = drop_bits(drop_key, idx + 2 * k + 1) >= thr ? hi * inv_keep : 0.f;
+        lo = drop_bits(drop_key ^ egot2_ep, idx + 2 * k) >= thr ? lo * inv_keep : 0.f;
+        hi = drop_bits(drop_key ^ egot2_ep, idx + 2 * k + 1) >= thr ? hi * inv_keep : 0.f;
       }
       acc[2 * k] += lo; acc[2 * k + 1] += hi;
     }
@@ -271,7 +271,7 @@ template <typename T>
 __global__ void dropout_kernel(T* x, size_t n, float p, float inv_keep, uint64_t key) {
   EGOT2_PDL_ENTER();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    x[i] = from_f32<T>(to_f32(x[i]) * drop_scale(key, i, p, inv_keep));
+    x[i] = from_f32<T>(to_f32(x[i]) * drop_scale(key ^ egot2_ep, i, p, inv_keep));
 }
 
 template <typename TT>
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const LayerNormArgs a) 
       }
       if (a.p_drop > 0.f) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] *= drop_scale(a.drop_key, (uint64_t)row * HH + c0 + i, a.p_drop, inv_keep);
+        for (int i = 0; i < 8; ++i) o[i] *= drop_scale(a.drop_key ^ egot2_ep, (uint64_t)row * HH + c0 + i, a.p_drop, inv_keep);
       }
       reinterpret_cast<uint4*>(y)[s * V::LPR + cl] = pack8(o);
     }
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
       const int c0 = (s * V::LPR + cl) * 8;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (a.dy_p_drop > 0.f) d[i] *= drop_scale(a.dy_drop_key, (uint64_t)row * HH + c0 + i, a.dy_p_drop, dy_keep);
+        if (a.dy_p_drop > 0.f) d[i] *= drop_scale(a.dy_drop_key ^ egot2_ep, (uint64_t)row * HH + c0 + i, a.dy_p_drop, dy_keep);
         if (!valid) d[i] = 0.f;
         xh[s][i] = (xv[i] - mean) * rstd;
         dyg[s][i] = d[i] * g[s][i];
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
         float o2[8];
         unpack8(packed, o2);        // the unfused sequence masks the bf16-rounded dx
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o2[i] *= drop_scale(a.dx2_drop_key, (uint64_t)row * HH + c0 + i, a.dx2_p_drop, dx2_keep);
+        for (int i = 0; i < 8; ++i) o2[i] *= drop_scale(a.dx2_drop_key ^ egot2_ep, (uint64_t)row * HH + c0 + i, a.dx2_p_drop, dx2_keep);
         const uint4 packed2 = pack8(o2);
         dx2p[s * V::LPR + cl] = packed2;
         if (a.dcol) {               // column sums of what the next Linear's backward sees (the rounded values)

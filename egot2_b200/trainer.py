@@ -137,6 +137,13 @@ class TranslatorTrainer:
         self.dp_overlap = ((self.world > 1 and ov != "0") or ov == "force") and spec.head != "decoder"
         if self.dp_overlap:
             self.graph_update = False
+        # Graph replays re-run kernels whose dropout keys were frozen at capture: the library's device-resident dropout
+        # epoch (advanced once per step, XORed into every key at execution time) gives every replay fresh masks.
+        self.dropout_epoch = bool(use_graphs) and os.environ.get("EGOT2_DROPOUT_EPOCH", "1") != "0"
+        if self.dropout_epoch:
+            with torch.cuda.device(self.device):
+                L.call("egot2_dropout_epoch_enable", 1)
+                L.call("egot2_dropout_epoch_set", 0, torch.cuda.current_stream(self.device).cuda_stream)
         self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
         self._step_dev_val = 0
         self._bump_stream = torch.cuda.Stream(device=self.device)
@@ -163,8 +170,9 @@ class TranslatorTrainer:
     def train_step(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, graph_key: Optional[int] = None):
         """One optimisation step on device-resident features.  Returns the (device) loss tensor.
         graph_key: a stable id for this exact set of input buffers; its launch sequence is captured into a CUDA
-        graph on first use (dropout then reuses the captured seed — fine for benchmarking, for real training
-        leave graph_key=None)."""
+        graph on first use.  The captured kernels keep the dropout seed they were captured with; the device-resident
+        dropout epoch (advanced once per step, folded into every key at execution time) makes each replay draw fresh
+        masks all the same."""
         self.step_count += 1
         if graph_key is not None and self.use_graphs:
             entry = self._graphs.get(graph_key)
@@ -180,7 +188,7 @@ class TranslatorTrainer:
             if self.graph_update and self._step_dev_val != self.step_count - 1:
                 self._step_dev.fill_(self.step_count - 1)
             graph.replay()
-            if self.graph_update:                         # the graph ended with [all-reduce +] fused Adam
+            if self.graph_update:                         # the graph ended with fused Adam (+ the epoch advance)
                 self._step_dev_val = self.step_count
                 self._grad_clean = True
                 self.engine.arena.shadow_fresh = self.engine.dtype == "bf16"
@@ -189,6 +197,7 @@ class TranslatorTrainer:
         else:
             act = self._fwd_bwd(feats, labels, seed=self.step_count)
         self._reduce_and_update()
+        self._advance_epoch()
         return act.t["loss"][0]
 
     def _dp_overlap_step(self, entry):
@@ -208,6 +217,7 @@ class TranslatorTrainer:
         eng.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
                       self.hp["weight_decay"], grad_scale=1.0 / self.world, fused=True)
         self._grad_clean = True
+        self._advance_epoch()
         return act.t["loss"][0]
 
     def _capture(self, feats, labels, key):
@@ -253,9 +263,19 @@ class TranslatorTrainer:
             act = self._fwd_bwd(feats, labels, seed=1 + key)
             if self.graph_update:
                 cur.wait_stream(self._bump_stream)
+                # every dropout consumer of this step has been enqueued before this point: the epoch advances for the
+                # NEXT replay on the side branch, beside the Adam launch (which reads no dropout key)
+                self._bump_stream.wait_stream(cur)
+                with torch.cuda.stream(self._bump_stream):
+                    self._advance_epoch()
                 self._reduce_and_update(step_dev=self._step_dev)
+                cur.wait_stream(self._bump_stream)
         self._graphs[key] = (g, act)
         return g, act
+
+    def _advance_epoch(self):
+        if self.dropout_epoch:
+            L.call("egot2_dropout_epoch_advance", torch.cuda.current_stream(self.device).cuda_stream)      # current = the stream in effect
 
     def _reduce_and_update(self, step_dev: Optional[torch.Tensor] = None):
         eng = self.engine

@@ -71,6 +71,16 @@ uint64_t egot2_launch_count(void);
 /* Launcher timing for the benchmark's roofline: while enabled, every launcher of the library brackets the kernels it
  * enqueues with CUDA events on the launch stream (eager launches only; ignored during stream capture).
  * egot2_prof_report writes "<launcher tag>\t<launches>\t<total microseconds>\n" lines (host buffer). */
+/* Dropout epoch: a device-resident counter XORed (times a constant) into every dropout key when the kernels EXECUTE, so
+ * that a CUDA graph replayed every step draws fresh masks although its kernel arguments (the keys derived from `seed`)
+ * were frozen at capture.  enable(1) allocates the 8-byte slot and switches all kernels to it (call outside stream
+ * capture; single GPU context per process); set/advance enqueue on `stream` and are graph-capturable;
+ * egot2_dropout_epoch_host(v) folds the same term into the keys on the HOST side instead (tests: host epoch v with the
+ * device epoch off must reproduce device epoch v bit for bit). */
+int egot2_dropout_epoch_enable(int on);
+int egot2_dropout_epoch_set(uint64_t value, void* stream);
+int egot2_dropout_epoch_advance(void* stream);
+int egot2_dropout_epoch_host(uint64_t value);
 int egot2_prof_enable(int on);
 /* Diagnostics, -DEGOT2_TIMELINE builds only (otherwise returns an error): every kernel stamps %globaltimer when it starts
  * (after its programmatic-dependent-launch wait) into dev_buf: u64[0] = number of stamps, then (ns, file_id*100000+line)
