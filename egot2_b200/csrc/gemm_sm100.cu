@@ -138,7 +138,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  // split-K CTAs own exactly one tile: a single accumulator (BN columns) - the double buffer would only keep other
+  // tensor-core kernels' CTAs (the data-gradient chain beside these weight-gradient GEMMs) from allocating TMEM on this SM
+  const bool one_tile = gridDim.z > 1;
+  if (warp == 1) { if (one_tile) tmem_alloc<BN>(tmem_slot); else tmem_alloc<2 * BN>(tmem_slot); }
   pdl_wait();                   // everything above touched only kernel parameters, shared memory and TMEM
   EGOT2_TL(EGOT2_FILE_ID);
   const unsigned long long egot2_ep = epoch_xor();
@@ -365,7 +368,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc<2 * BN>(tmem_base);
+    if (one_tile) tmem_dealloc<BN>(tmem_base); else tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
