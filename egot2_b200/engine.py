@@ -348,6 +348,8 @@ class TranslatorEngine:
             ln_name = "ln" if sp.head_ln_shared else "linear_head.0"
             hin.ln_g, hin.ln_b = self._vec(ln_name + ".weight").data_ptr(), self._vec(ln_name + ".bias").data_ptr()
             hin.w, hin.b = self._mat("linear_head.1.weight").data_ptr(), self._vec("linear_head.1.bias").data_ptr()
+        elif sp.head == "pool_linear":
+            hin.w, hin.b = self._mat("linear_head.weight").data_ptr(), self._vec("linear_head.bias").data_ptr()
         else:
             base = self.arena.shadow if self.dtype == "bf16" else self.arena.param
             w, _ = self.arena.stacked_head(base)
@@ -575,6 +577,8 @@ class TranslatorEngine:
                 ln_name = "ln" if sp.head_ln_shared else "linear_head.0"
                 hg.ln_g, hg.ln_b = gv(ln_name + ".weight").data_ptr(), gv(ln_name + ".bias").data_ptr()
                 hg.w, hg.b = gv("linear_head.1.weight").data_ptr(), gv("linear_head.1.bias").data_ptr()
+            elif sp.head == "pool_linear":
+                hg.w, hg.b = gv("linear_head.weight").data_ptr(), gv("linear_head.bias").data_ptr()
             else:
                 w, bvec = self.arena.stacked_head(grad)
                 hg.w, hg.b = w.data_ptr(), bvec.data_ptr()

@@ -21,7 +21,7 @@ from torch.distributions.categorical import Categorical
 from . import _lib as L
 from .engine import _stream
 from .modules import PrecomputedFeatures, TranslatorBase
-from .specs import hoi_lta_spec, hoi_pnr_spec
+from .specs import hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
 
 
 def slowfast_pool(x5: torch.Tensor, t_out: int, out_dtype: torch.dtype) -> torch.Tensor:
@@ -89,7 +89,49 @@ class _PNR3TaskDropout(TranslatorBase):
         return out.unsqueeze(self.unsqueeze_dim)
 
 
-def _reference_pnr_backbones(self, cfg):  # pragma: no cover - needs an EgoT2 checkout + checkpoints
+class _PNR2TaskDropout(TranslatorBase):
+    """2-task sibling (HOI/models/pnr/video_model_transfer.py:70-105): PNR + OSCC -> keyframe logits (B,1,16) / OSCC
+    (B,2,1); H=256, 3 layers, 32 tokens, head = bare Linear on the mean token."""
+
+    def __init__(self, cfg, backbones: Optional[Dict[str, nn.Module]] = None):
+        super().__init__()
+        self.cfg_recognition = None
+        if backbones is None:
+            backbones = _reference_pnr_backbones(self, cfg, with_recognition=False)
+        for k, m in backbones.items():
+            setattr(self, k, m)
+        self.num_classes = 16 if cfg.DATA.TASK == "keyframe_localization" else 2
+        self.unsqueeze_dim = 1 if cfg.DATA.TASK == "keyframe_localization" else 2
+        self.sequence_len = 32
+        self.feature_dim = 256
+        self.proj1 = nn.Linear(8192, self.feature_dim)
+        self.proj2 = nn.Linear(8192, self.feature_dim)
+        self.pe = nn.Parameter(torch.randn(1, self.sequence_len, self.feature_dim), requires_grad=True)
+        self.ln = nn.LayerNorm(self.feature_dim)
+        self.dpmode = cfg.MODEL.FEAT_DROPOUT_MODE
+        self.transformer = nn.TransformerEncoder(
+            encoder_layer=nn.TransformerEncoderLayer(d_model=self.feature_dim, nhead=8,
+                                                     dropout=cfg.MODEL.TRANSFORMER_DROPOUT_RATE,
+                                                     dim_feedforward=self.feature_dim * 2, batch_first=True),
+            num_layers=3, enable_nested_tensor=False)
+        self.linear_head = nn.Linear(self.feature_dim, self.num_classes)
+        self._poison_containers(self.proj1, self.proj2, self.transformer, self.linear_head, self.ln)
+        self._init_translator(hoi_pnr2_spec(self.num_classes, cfg.MODEL.TRANSFORMER_DROPOUT_RATE))
+
+    def forward(self, x):
+        if self.dpmode > 0 and self.training:
+            # reference :95-98 then drops the PNR segment's projected features only; the embed stage has one
+            # feature-dropout switch for all segments, so this (non-default) mode is refused rather than approximated
+            raise L.Egot2Error("TaskFusionMFTransformerDropout: FEAT_DROPOUT_MODE > 0 (per-segment feature dropout) is "
+                               "not built; the shipped default is 0")
+        x2 = x.copy()
+        pnr_feat = self.pnr_model(x, middle=True)                        # (bs, 16, 8192)
+        oscc_feat = self.oscc_model(x2, middle=True)                     # (bs, 16, 8192)
+        out = self._translate([pnr_feat, oscc_feat])                     # token order (pnr, oscc)
+        return out.unsqueeze(self.unsqueeze_dim)
+
+
+def _reference_pnr_backbones(self, cfg, with_recognition=True):  # pragma: no cover - needs an EgoT2 checkout + checkpoints
     try:
         from models.pnr.video_model_builder import KeyframeLocalizationResNet, StateChangeClsResNet  # type: ignore
         from models.lta.video_model_builder import SlowFast                                        # type: ignore
@@ -113,6 +155,8 @@ def _reference_pnr_backbones(self, cfg):  # pragma: no cover - needs an EgoT2 ch
     load_checkpoint(out["oscc_model"], cfg_oscc.MISC.CHECKPOINT_FILE_PATH)
     if cfg.PRETRAIN.OSCC_FT:
         out["oscc_model"].eval(); freeze_params(out["oscc_model"])
+    if not with_recognition:
+        return out
     cfg_rec = load_lta_config(cfg.PRETRAIN.ACTION_CFG)
     cfg_rec.MODEL.NUM_CLASSES = [cfg.MODEL.TRANSLATION_INPUT_FEATURES]
     cfg_rec.MODEL.HEAD_ACT = None
@@ -240,9 +284,11 @@ def _reference_lta_backbones(self, cfg):  # pragma: no cover - needs an EgoT2 ch
     return out
 
 
-pnr = SimpleNamespace(TaskFusionMFTransformer3TaskDropout=_PNR3TaskDropout)
+pnr = SimpleNamespace(TaskFusionMFTransformer3TaskDropout=_PNR3TaskDropout, TaskFusionMFTransformerDropout=_PNR2TaskDropout)
 _PNR3TaskDropout.__name__ = _PNR3TaskDropout.__qualname__ = "TaskFusionMFTransformer3TaskDropout"
-pnr.MODEL_REGISTRY = {"TaskFusionMFTransformer3TaskDropout": _PNR3TaskDropout}
+_PNR2TaskDropout.__name__ = _PNR2TaskDropout.__qualname__ = "TaskFusionMFTransformerDropout"
+pnr.MODEL_REGISTRY = {"TaskFusionMFTransformer3TaskDropout": _PNR3TaskDropout,
+                      "TaskFusionMFTransformerDropout": _PNR2TaskDropout}
 pnr.build_model = lambda cfg, **kw: pnr.MODEL_REGISTRY[cfg.MODEL.MODEL_NAME](cfg, **kw)
 
 lta = SimpleNamespace(TaskFusionMFTransformerLTA4Task=_LTA4Task)

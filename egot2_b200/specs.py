@@ -122,6 +122,9 @@ class TranslatorSpec:
             out["linear_head.0.bias"] = (H,)
             out["linear_head.1.weight"] = (2, H)
             out["linear_head.1.bias"] = (2,)
+        elif self.family == "hoi_pnr" and self.head == "pool_linear":
+            out["linear_head.weight"] = (self.n_out, H)       # 2-task variant: a bare nn.Linear head
+            out["linear_head.bias"] = (self.n_out,)
         elif self.family == "hoi_pnr":
             # linear_head.0.* alias ln.* in the reference state_dict (same tensor)
             out["linear_head.1.weight"] = (self.n_out, H)
@@ -201,6 +204,15 @@ def hoi_pnr_spec(hidden=128, layers=6, n_cls=16, feat_dropout=0.5, tr_dropout=0.
             Segment("slow", 2048, "proj3_slow", 8), Segment("fast", 256, "proj3_fast", 8))
     return TranslatorSpec("hoi_pnr", hidden, 8, 2 * hidden, layers, segs, "learned_pe", "transformer.",
                           "pool_ln_linear", n_cls, True, tr_dropout, 0.0, feat_dropout, 0.0)
+
+
+def hoi_pnr2_spec(n_cls=16, tr_dropout=0.1) -> TranslatorSpec:
+    """2-task PNR/OSCC sibling `TaskFusionMFTransformerDropout` (HOI/models/pnr/video_model_transfer.py:70-105): tokens
+    (pnr16, oscc16), H=256, nh=8, FF=2H, 3 layers, shared-nothing head = a bare Linear(H, n_cls) on the mean token (no
+    LayerNorm).  FEAT_DROPOUT_MODE = 0 (the shipped default, configs/pnr/defaults.py:240) = no feature dropout."""
+    segs = (Segment("pnr", 8192, "proj1", 16), Segment("oscc", 8192, "proj2", 16))
+    return TranslatorSpec("hoi_pnr", 256, 8, 512, 3, segs, "learned_pe", "transformer.", "pool_linear", n_cls, False,
+                          tr_dropout, 0.0, 0.0, 0.0)
 
 
 def hoi_lta_spec(hidden=512, layers=4, heads=8, dropout=0.5, num_input_clips=2, num_actions=20,

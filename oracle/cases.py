@@ -37,6 +37,8 @@ CASES = {c.name: c for c in [
     Case("hoi_pnr_h128_l6", specs.hoi_pnr_spec(128, 6, 16, 0.5, 0.1), 6, (16, 16, 8, 8), 6),
     Case("hoi_pnr_raw_maps", specs.hoi_pnr_spec(128, 6, 16, 0.5, 0.1), 2, (16, 16, 8, 8), 7, raw_slowfast=True),
     Case("hoi_oscc_h256_l5", specs.hoi_pnr_spec(256, 5, 2, 0.1, 0.1), 4, (16, 16, 8, 8), 8),
+    # SURVEY 8a-F sibling: the 2-task PNR translator (H=256, 3 layers, 32 tokens, bare Linear head)
+    Case("hoi_pnr2_h256_l3", specs.hoi_pnr2_spec(16, 0.1), 5, (16, 16), 13),
     # BASELINE config 5 (scaled) and the shipped LTA config (H=1024, L=1)
     Case("hoi_lta_h512_l4", specs.hoi_lta_spec(512, 4, 8, 0.5), 3, (2, 2, 2, 2), 9),
     Case("hoi_lta_h1024_l1", specs.hoi_lta_spec(1024, 1, 8, 0.5), 2, (2, 2, 2, 2), 10),
@@ -76,6 +78,10 @@ def oracle_forward_loss(case: Case, P: Dict[str, torch.Tensor], feats, labels, e
     elif sp.family == "hhi_asd":
         out = O.hhi_asd_forward(P, feats, sp.heads)
         loss = O.loss_av(extra, out, labels)[0]
+    elif sp.family == "hoi_pnr" and sp.head == "pool_linear":
+        out = O.hoi_pnr2_forward(P, feats["pnr"], feats["oscc"], sp.heads)
+        loss = (O.bce_sigmoid_loss(out, torch.nn.functional.one_hot(labels, 16).float()) if sp.n_out == 16
+                else O.ce_loss(out, labels))
     elif sp.family == "hoi_pnr":
         if case.raw_slowfast:
             out = O.hoi_pnr_forward(P, feats["pnr"], feats["oscc"], extra["slow5"], extra["fast5"], sp.heads)

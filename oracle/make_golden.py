@@ -34,6 +34,12 @@ def build_reference(case: Case, hhi, hoi):
         return cls(rs.hhi_args(sp.hidden, sp.heads, sp.layers, sp.p_layer, three))
     if sp.family == "hhi_asd":
         return hhi.asd.TaskFusionMFTransformer3Task(rs.hhi_args(sp.hidden, sp.heads, sp.layers, sp.p_layer, True))
+    if sp.family == "hoi_pnr" and sp.head == "pool_linear":
+        cfg = rs.hoi_pnr_cfg(sp.hidden, sp.layers, 0.5, sp.p_layer,
+                             "keyframe_localization" if sp.n_out == 16 else "state_change_detection")
+        cfg.MODEL.FEAT_DROPOUT_MODE = 0                      # HOI/configs/pnr/defaults.py:240
+        cfg.PRETRAIN.PNR_FT = cfg.PRETRAIN.OSCC_FT = True
+        return hoi.pnr2.TaskFusionMFTransformerDropout(cfg)
     if sp.family == "hoi_pnr":
         task = "keyframe_localization_2loader" if sp.n_out == 16 else "state_change_detection"
         m = hoi.pnr3.TaskFusionMFTransformer3TaskDropout(rs.hoi_pnr_cfg(sp.hidden, sp.layers, sp.p_feat, sp.p_layer, task))
@@ -69,6 +75,16 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         # HHI/tasks/multitask/video_tasktranslation.py:48-61 (the three forwards share one model; one case = one of them)
         out = m(*rs.hhi_inputs(feats), labels[:, :-1], sp.g_mode)                          # (rows, V, 2)
         loss = torch.nn.CrossEntropyLoss()(out, labels[:, 1:])
+    elif sp.family == "hoi_pnr" and sp.head == "pool_linear":
+        m.pnr_model = rs.FeatureBackbone(); m.pnr_model.slot = "pnr"
+        m.oscc_model = rs.FeatureBackbone(); m.oscc_model.slot = "oscc"
+        out = m([{"pnr": feats["pnr"], "oscc": feats["oscc"]}])
+        if sp.n_out == 16:
+            out = out.squeeze(1)
+            loss = torch.nn.BCELoss()(torch.sigmoid(out), torch.nn.functional.one_hot(labels, 16).float())
+        else:
+            out = out.squeeze(2)
+            loss = torch.nn.functional.cross_entropy(out, labels)
     elif sp.family == "hoi_pnr":
         slow = extra["slow5"] if case.raw_slowfast else feats["slow"].permute(0, 2, 1)[..., None, None]
         fast = extra["fast5"] if case.raw_slowfast else \

@@ -190,6 +190,17 @@ def hoi_pnr_forward(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: Te
     return linear(g, P["linear_head.1.weight"], P["linear_head.1.bias"])
 
 
+def hoi_pnr2_forward(P: Params, pnr: Tensor, oscc: Tensor, n_heads: int = 8, p_drop: float = 0.0,
+                     training: bool = False) -> Tensor:
+    """TaskFusionMFTransformerDropout (the 2-task sibling) -> (B, n_cls) logits before the unsqueeze.
+    HOI/models/pnr/video_model_transfer.py:91-105 with FEAT_DROPOUT_MODE = 0 (configs/pnr/defaults.py:240): tokens
+    (pnr, oscc) -> ln + learned pe -> 3-layer encoder -> mean over tokens -> bare Linear head (no LayerNorm)."""
+    z = torch.cat([linear(pnr, P["proj1.weight"], P["proj1.bias"]), linear(oscc, P["proj2.weight"], P["proj2.bias"])], dim=1)
+    x = layer_norm(z, P["ln.weight"], P["ln.bias"]) + P["pe"]
+    x = encoder(x, P, "transformer.", count_layers(P, "transformer."), n_heads, p_drop, training)
+    return linear(x.mean(dim=1), P["linear_head.weight"], P["linear_head.bias"])
+
+
 def hoi_lta_forward(P: Params, pnr: Tensor, oscc: Tensor, action: Tensor, lta: Tensor, n_heads: int = 8,
                     p_drop: float = 0.0, p_head: float = 0.0, training: bool = False,
                     eval_softmax: bool = False) -> Tensor:

@@ -54,6 +54,11 @@ def build_ours(case, backbones=True):
         vocab = {'</s>': 0, '<unk>': 1, 'ttm': 2, 'lam': 3, 'asd': 4, '0': 5, '1': 6}
         bb = {"lam_model": PrecomputedFeatures("lam"), "ttm_model": PrecomputedFeatures("ttm"), "asd_model": _TalkNetFeatures()}
         return hhi.TaskTranslationPromptTransformer(args, vocab, backbones=bb)
+    if sp.family == "hoi_pnr" and sp.head == "pool_linear":      # the 2-task sibling
+        cfg = CfgNode(DATA=CfgNode(TASK="keyframe_localization" if sp.n_out == 16 else "state_change"),
+                      MODEL=CfgNode(FEAT_DROPOUT_RATE=0.5, FEAT_DROPOUT_MODE=0, TRANSFORMER_DROPOUT_RATE=sp.p_layer))
+        bb = {"pnr_model": PrecomputedFeatures("pnr"), "oscc_model": PrecomputedFeatures("oscc")}
+        return hoi.pnr.TaskFusionMFTransformerDropout(cfg, backbones=bb)
     if sp.family == "hoi_pnr":
         cfg = CfgNode(DATA=CfgNode(TASK="keyframe_localization_2loader" if sp.n_out == 16 else "state_change"),
                       MODEL=CfgNode(TRANSLATION_INPUT_FEATURES=sp.hidden, TRANSLATION_LAYERS=sp.layers,
@@ -82,6 +87,9 @@ def run_ours(case, m, feats, extra, dev, labels=None):
     if sp.family in ("hhi_ttm", "hhi_asd"):
         v = _Feats(f)
         return m(v, v, None, None)
+    if sp.family == "hoi_pnr" and sp.head == "pool_linear":
+        out = m([{"pnr": f["pnr"], "oscc": f["oscc"]}])
+        return out.squeeze(1) if sp.n_out == 16 else out.squeeze(2)
     if sp.family == "hoi_pnr":
         if case.raw_slowfast:
             sf = [extra["slow5"].to(dev), extra["fast5"].to(dev)]
@@ -116,7 +124,7 @@ def test_container_forward_is_poisoned():
 
 @pytest.mark.requires_reference
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_l1", "hhi_asd_h128_l1", "hoi_pnr_h128_l6", "hoi_lta_h512_l4",
-                                  "hhi_g_ttm_h128_l2"])
+                                  "hhi_g_ttm_h128_l2", "hoi_pnr2_h256_l3"])
 def test_same_seed_same_init_as_reference(name):
     """ctor parity: under the same torch seed our module draws exactly the reference's initial weights."""
     from oracle import ref_shims as rs
@@ -139,7 +147,7 @@ def test_same_seed_same_init_as_reference(name):
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_d30", "hhi_asd_h128_l1", "hoi_pnr_h128_l6",
                                   "hoi_pnr_raw_maps", "hoi_lta_h512_l4", "hhi_g_lam_h128_l2", "hhi_g_ttm_h128_l2",
-                                  "hhi_g_asd_h128_l2"])
+                                  "hhi_g_asd_h128_l2", "hoi_pnr2_h256_l3"])
 def test_module_forward_backward_vs_oracle(name, dtype):
     from oracle import translator_oracle as O
     warnings.filterwarnings("ignore")
