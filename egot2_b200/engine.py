@@ -56,8 +56,9 @@ class ParamArena:
             self.offsets[name] = off
             off += numel
 
-        head_w = [n for n in shapes if re.fullmatch(r"head\.projections\.\d+\.weight", n)]
-        head_b = [n for n in shapes if re.fullmatch(r"head\.projections\.\d+\.bias", n)]
+        # stacked heads (LTA: head.projections.z ; AR: linear_head1.1 / linear_head2.1): contiguous, no padding between
+        head_w = [n for n in shapes if re.fullmatch(r"head\.projections\.\d+\.weight|linear_head\d\.1\.weight", n)]
+        head_b = [n for n in shapes if re.fullmatch(r"head\.projections\.\d+\.bias|linear_head\d\.1\.bias", n)]
         # The embedding-stage parameters (per-task projections, task/positional embeddings, the shared LayerNorm) come
         # FIRST and contiguous: their gradients are the last ones backward produces, so under data parallelism the rest
         # of the arena [embed_numel:] can be all-reduced while the embedding backward still runs (trainer.py).
@@ -94,13 +95,13 @@ class ParamArena:
         return base[o:o + _numel(shp)].view(shp)
 
     def stacked_head(self, base: Optional[torch.Tensor] = None):
-        """(Z*per, H) weight and (Z*per,) bias views of the LTA head."""
+        """(sum of head rows, H) weight and (sum of head rows,) bias views of the stacked heads (LTA / AR)."""
         base = self.param if base is None else base
         w0, b0 = self.head_w_names[0], self.head_b_names[0]
-        per, H = self.shapes[w0]
-        Z = len(self.head_w_names)
+        H = self.shapes[w0][1]
+        rows = sum(self.shapes[n][0] for n in self.head_w_names)
         ow, ob = self.offsets[w0], self.offsets[b0]
-        return base[ow:ow + Z * per * H].view(Z * per, H), base[ob:ob + Z * per]
+        return base[ow:ow + rows * H].view(rows, H), base[ob:ob + rows]
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
         with torch.no_grad():
@@ -332,9 +333,9 @@ class TranslatorEngine:
         if fresh or act.head_desc is None:
             hd = L.HeadDesc()
             hd.dtype, hd.B, hd.T, hd.H, hd.pool, hd.row_tokens = self.dt, B, T, H, 1, 0
-            hd.use_ln = 1 if sp.head == "pool_ln_linear" else 0
+            hd.use_ln = 1 if sp.head in ("pool_ln_linear", "pool_ln_multilinear") else 0
             hd.n_out, hd.ln_eps = sp.n_out, 1e-5
-            if sp.head == "pool_multilinear":
+            if sp.head in ("pool_multilinear", "pool_ln_multilinear"):
                 hd.n_groups, hd.sub_rows = len(sp.head_groups), sp.n_heads_out
                 for gi, gs in enumerate(sp.head_groups):
                     hd.group_size[gi] = gs
@@ -355,6 +356,8 @@ class TranslatorEngine:
             w, _ = self.arena.stacked_head(base)
             _, bvec = self.arena.stacked_head(self.arena.param)
             hin.w, hin.b = w.data_ptr(), bvec.data_ptr()
+            if sp.head == "pool_ln_multilinear":      # AR: the shared ln in front of both heads
+                hin.ln_g, hin.ln_b = self._vec("ln.weight").data_ptr(), self._vec("ln.bias").data_ptr()
         if loss != L.LOSS_NONE:
             assert labels is not None
             lab = labels.to(device=dev, dtype=torch.int64).contiguous()
@@ -366,7 +369,8 @@ class TranslatorEngine:
                 hin.class_weight = cw.data_ptr()
             else:
                 hin.class_weight = None
-            segs = rows * (sp.n_heads_out * len(sp.head_groups) if sp.head == "pool_multilinear" else 1)
+            segs = rows * (sp.n_heads_out * len(sp.head_groups)
+                           if sp.head in ("pool_multilinear", "pool_ln_multilinear") else 1)
             hout.row_loss = buf("row_loss", (segs, 2), torch.float32).data_ptr()
             hout.loss = buf("loss", (2,), torch.float32).data_ptr()
             hout.argmax = buf("argmax", (segs,), torch.int32).data_ptr()
@@ -582,6 +586,8 @@ class TranslatorEngine:
             else:
                 w, bvec = self.arena.stacked_head(grad)
                 hg.w, hg.b = w.data_ptr(), bvec.data_ptr()
+                if sp.head == "pool_ln_multilinear":
+                    hg.ln_g, hg.ln_b = gv("ln.weight").data_ptr(), gv("ln.bias").data_ptr()
             ws = self._workspace(L.load().egot2_head_workspace_bytes(C.byref(hd)))
             L.call("egot2_head_loss_bwd", C.byref(hd), C.byref(act.head_in), C.byref(act.head_out), dlogits.data_ptr(),
                    float(dloss_scale), dx.data_ptr(), C.byref(hg), ws.data_ptr(), ws.numel(), st)

@@ -3,6 +3,8 @@
 Reference (relative to /root/reference):
   pnr.TaskFusionMFTransformer3TaskDropout   HOI/models/pnr/video_model_transfer_3task.py:212-258
   lta.TaskFusionMFTransformerLTA4Task       HOI/models/lta/lta_models_lta_transfer.py:257-377
+  pnr.TaskFusionMFTransformerDropout        HOI/models/pnr/video_model_transfer.py:70-105   (2-task sibling)
+  lta.TaskFusionMFTransformer3Task          HOI/models/lta/lta_models_transfer.py:96-137    (action-recognition sibling)
   MultiTaskHead (LTA head)                  HOI/models/lta/head_helper.py:218-291
 The frozen PNR/OSCC/SlowFast/LTA backbones are not part of this package: inside an EgoT2 checkout
 they are built by the reference's own loaders; otherwise pass `backbones={...}`.
@@ -21,7 +23,7 @@ from torch.distributions.categorical import Categorical
 from . import _lib as L
 from .engine import _stream
 from .modules import PrecomputedFeatures, TranslatorBase
-from .specs import hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
+from .specs import hoi_ar_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
 
 
 def slowfast_pool(x5: torch.Tensor, t_out: int, out_dtype: torch.dtype) -> torch.Tensor:
@@ -129,6 +131,54 @@ class _PNR2TaskDropout(TranslatorBase):
         oscc_feat = self.oscc_model(x2, middle=True)                     # (bs, 16, 8192)
         out = self._translate([pnr_feat, oscc_feat])                     # token order (pnr, oscc)
         return out.unsqueeze(self.unsqueeze_dim)
+
+
+class _AR3Task(TranslatorBase):
+    """Action-recognition sibling (HOI/models/lta/lta_models_transfer.py:96-137): AR(slow,fast) + PNR + OSCC ->
+    [verb logits (B,115), noun logits (B,478)]; one LayerNorm shared by the token LN and both heads."""
+
+    def __init__(self, cfg, backbones: Optional[Dict[str, nn.Module]] = None):
+        super().__init__()
+        self.cfg_pnr = None
+        self.cfg_recognition = None
+        if backbones is None:
+            backbones = _reference_pnr_backbones(self, cfg)
+        for k, m in backbones.items():
+            setattr(self, k, m)
+        num_cls1, num_cls2 = cfg.MODEL.NUM_CLASSES
+        self.num_classes = (num_cls1, num_cls2)
+        self.sequence_len = 48
+        self.num_heads = cfg.MODEL.TRANSLATION_HEADS
+        self.num_layers = cfg.MODEL.TRANSLATION_LAYERS
+        self.feature_dim = cfg.MODEL.TRANSLATION_INPUT_FEATURES
+        self.dp_rate = cfg.MODEL.TRANSLATION_DROPOUT
+        self.proj1 = nn.Linear(8192, self.feature_dim)
+        self.proj2 = nn.Linear(8192, self.feature_dim)
+        self.proj3_slow = nn.Linear(2048, self.feature_dim)
+        self.proj3_fast = nn.Linear(256, self.feature_dim)
+        self.pe = nn.Parameter(torch.randn(1, self.sequence_len, self.feature_dim), requires_grad=True)
+        self.transformer = nn.TransformerEncoder(
+            encoder_layer=nn.TransformerEncoderLayer(d_model=self.feature_dim, nhead=self.num_heads,
+                                                     dropout=self.dp_rate, batch_first=True),
+            num_layers=self.num_layers, enable_nested_tensor=False)
+        self.ln = nn.LayerNorm(self.feature_dim)
+        self.linear_head1 = nn.Sequential(self.ln, nn.Linear(self.feature_dim, num_cls1))     # shared ln
+        self.linear_head2 = nn.Sequential(self.ln, nn.Linear(self.feature_dim, num_cls2))
+        self._poison_containers(self.proj1, self.proj2, self.proj3_slow, self.proj3_fast, self.transformer,
+                                self.linear_head1, self.linear_head2)
+        self._init_translator(hoi_ar_spec(self.feature_dim, self.num_layers, self.num_heads, self.dp_rate,
+                                          (num_cls1, num_cls2)))
+
+    def forward(self, x_action, x_pnr):
+        x_oscc = x_pnr.copy()
+        pnr_feat = self.pnr_model(x_pnr, middle=True)                    # (bs, 16, 8192)
+        oscc_feat = self.oscc_model(x_oscc, middle=True)                 # (bs, 16, 8192)
+        slow5, fast5 = self.recognition_model(x_action, middle=True)     # (bs,2048,8,7,7), (bs,256,32,7,7)
+        dt = torch.float32 if self.compute_dtype == "fp32" else torch.bfloat16
+        slow = slowfast_pool(slow5, slow5.shape[2], dt) if slow5.dim() == 5 else slow5
+        fast = slowfast_pool(fast5, 8, dt) if fast5.dim() == 5 else fast5
+        out = self._translate([slow, fast, pnr_feat, oscc_feat])         # token order (slow, fast, pnr, oscc)
+        return list(torch.split(out, list(self.num_classes), dim=-1))
 
 
 def _reference_pnr_backbones(self, cfg, with_recognition=True):  # pragma: no cover - needs an EgoT2 checkout + checkpoints
@@ -291,7 +341,8 @@ pnr.MODEL_REGISTRY = {"TaskFusionMFTransformer3TaskDropout": _PNR3TaskDropout,
                       "TaskFusionMFTransformerDropout": _PNR2TaskDropout}
 pnr.build_model = lambda cfg, **kw: pnr.MODEL_REGISTRY[cfg.MODEL.MODEL_NAME](cfg, **kw)
 
-lta = SimpleNamespace(TaskFusionMFTransformerLTA4Task=_LTA4Task)
+lta = SimpleNamespace(TaskFusionMFTransformerLTA4Task=_LTA4Task, TaskFusionMFTransformer3Task=_AR3Task)
 _LTA4Task.__name__ = _LTA4Task.__qualname__ = "TaskFusionMFTransformerLTA4Task"
-lta.MODEL_REGISTRY = {"TaskFusionMFTransformerLTA4Task": _LTA4Task}
+_AR3Task.__name__ = _AR3Task.__qualname__ = "TaskFusionMFTransformer3Task"
+lta.MODEL_REGISTRY = {"TaskFusionMFTransformerLTA4Task": _LTA4Task, "TaskFusionMFTransformer3Task": _AR3Task}
 lta.build_model = lambda cfg, **kw: lta.MODEL_REGISTRY[cfg.MODEL.MODEL_NAME](cfg, **kw)

@@ -129,6 +129,11 @@ class TranslatorSpec:
             # linear_head.0.* alias ln.* in the reference state_dict (same tensor)
             out["linear_head.1.weight"] = (self.n_out, H)
             out["linear_head.1.bias"] = (self.n_out,)
+        elif self.family == "hoi_ar":
+            # linear_head{1,2}.0.* alias ln.* in the reference state_dict (one LayerNorm, three uses)
+            for gi, n_cls in enumerate(self.head_groups):
+                out[f"linear_head{gi + 1}.1.weight"] = (n_cls, H)
+                out[f"linear_head{gi + 1}.1.bias"] = (n_cls,)
         elif self.family == "hoi_lta":
             per = sum(self.head_groups)
             for z in range(self.n_heads_out):
@@ -213,6 +218,16 @@ def hoi_pnr2_spec(n_cls=16, tr_dropout=0.1) -> TranslatorSpec:
     segs = (Segment("pnr", 8192, "proj1", 16), Segment("oscc", 8192, "proj2", 16))
     return TranslatorSpec("hoi_pnr", 256, 8, 512, 3, segs, "learned_pe", "transformer.", "pool_linear", n_cls, False,
                           tr_dropout, 0.0, 0.0, 0.0)
+
+
+def hoi_ar_spec(hidden=128, layers=3, heads=8, dropout=0.1, num_classes=(115, 478), ffn=2048) -> TranslatorSpec:
+    """Action-recognition EgoT2-s sibling `TaskFusionMFTransformer3Task` (HOI/models/lta/lta_models_transfer.py:96-137):
+    tokens (slow8, fast8, pnr16, oscc16), FF = 2048 (torch default), `ln` shared by the token LayerNorm and BOTH heads
+    (linear_head1 -> verbs, linear_head2 -> nouns); shipped: H=128, L=3, p=0.1 (configs/recognition/ts_ar.yaml:53-55)."""
+    segs = (Segment("slow", 2048, "proj3_slow", 8), Segment("fast", 256, "proj3_fast", 8),
+            Segment("pnr", 8192, "proj1", 16), Segment("oscc", 8192, "proj2", 16))
+    return TranslatorSpec("hoi_ar", hidden, heads, ffn, layers, segs, "learned_pe", "transformer.",
+                          "pool_ln_multilinear", sum(num_classes), True, dropout, 0.0, 0.0, 0.0, 0, tuple(num_classes), 1)
 
 
 def hoi_lta_spec(hidden=512, layers=4, heads=8, dropout=0.5, num_input_clips=2, num_actions=20,

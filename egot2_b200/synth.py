@@ -70,6 +70,10 @@ def make_labels(spec: TranslatorSpec, batch: int, seg_tokens: Optional[Sequence[
         return torch.randint(0, 2, (batch * d,), generator=g)
     if spec.family == "hoi_pnr":
         return torch.randint(0, spec.n_out, (batch,), generator=g)
+    if spec.family == "hoi_ar":        # (B, 2): verb id, noun id (RecognitionTask2Loader labels[:, 0] / labels[:, 1])
+        v = torch.randint(0, spec.head_groups[0], (batch, 1), generator=g)
+        n = torch.randint(0, spec.head_groups[1], (batch, 1), generator=g)
+        return torch.cat([v, n], dim=-1)
     if spec.family == "hoi_lta":
         v = torch.randint(0, spec.head_groups[0], (batch, spec.n_heads_out, 1), generator=g)
         n = torch.randint(0, spec.head_groups[1], (batch, spec.n_heads_out, 1), generator=g)

@@ -92,7 +92,7 @@ def default_loss(spec: TranslatorSpec):
         return L.LOSS_CE, torch.tensor([0.266, 0.734])
     if spec.family == "hoi_pnr":
         return (L.LOSS_BCE_SIGMOID if spec.n_out == 16 else L.LOSS_CE), None
-    if spec.family == "hoi_lta":
+    if spec.family in ("hoi_lta", "hoi_ar"):
         return L.LOSS_CE_GROUPS, None
     raise ValueError(f"{spec.family}: the loss lives outside the translator (use the nn.Module API)")
 

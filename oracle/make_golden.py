@@ -44,6 +44,12 @@ def build_reference(case: Case, hhi, hoi):
         task = "keyframe_localization_2loader" if sp.n_out == 16 else "state_change_detection"
         m = hoi.pnr3.TaskFusionMFTransformer3TaskDropout(rs.hoi_pnr_cfg(sp.hidden, sp.layers, sp.p_feat, sp.p_layer, task))
         return m
+    if sp.family == "hoi_ar":
+        cfg = rs.CfgNode(MODEL=rs.CfgNode(NUM_CLASSES=list(sp.head_groups), TRANSLATION_HEADS=sp.heads,
+                                          TRANSLATION_LAYERS=sp.layers, TRANSLATION_INPUT_FEATURES=sp.hidden,
+                                          TRANSLATION_DROPOUT=sp.p_layer),
+                         PRETRAIN=rs.CfgNode(PNR_CFG=None, OSCC_CFG=None, ACTION_CFG=None))
+        return hoi.lta3.TaskFusionMFTransformer3Task(cfg)
     if sp.family == "hoi_lta":
         return hoi.lta4.TaskFusionMFTransformerLTA4Task(
             rs.hoi_lta_cfg(sp.hidden, sp.layers, sp.heads, sp.p_layer, sp.segments[0].tokens, sp.n_heads_out,
@@ -104,6 +110,20 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         else:
             out = out.squeeze(2)                                   # (B,2,1) -> (B,2)
             loss = torch.nn.functional.cross_entropy(out, labels)  # :143-146
+    elif sp.family == "hoi_ar":
+        slow = feats["slow"].permute(0, 2, 1)[..., None, None]
+        fast = feats["fast"].permute(0, 2, 1).repeat_interleave(4, dim=2)[..., None, None]   # (B,256,32,1,1)
+        m.pnr_model = rs.FeatureBackbone(); m.pnr_model.slot = "pnr"
+        m.oscc_model = rs.FeatureBackbone(); m.oscc_model.slot = "oscc"
+
+        class _SF(torch.nn.Module):
+            def forward(self, x, middle=False):
+                return [slow, fast]
+        m.recognition_model = _SF()
+        preds = m(None, [{"pnr": feats["pnr"], "oscc": feats["oscc"]}])
+        out = torch.cat(preds, dim=-1)
+        # HOI/tasks/lta/long_term_anticipation_taskspecfic.py:31-33
+        loss = torch.nn.functional.cross_entropy(preds[0], labels[:, 0]) + torch.nn.functional.cross_entropy(preds[1], labels[:, 1])
     elif sp.family == "hoi_lta":
         # forward() lines 355-358 run the backbones; we enter at the projections (359-363)
         feat = torch.cat((m.proj_pnr(feats["pnr"]), m.proj_oscc(feats["oscc"]), feats["action"],
@@ -141,7 +161,7 @@ def main():
         m = build_reference(case, hhi, hoi)
         missing, unexpected = m.load_state_dict(sd, strict=False)
         # everything we do not set must be a buffer / alias / backbone, never a translator weight
-        allowed = ("pos_embed.pe", "linear_head.0.", "lam_model", "ttm_model", "asd_model")
+        allowed = ("pos_embed.pe", "linear_head.0.", "linear_head1.0.", "linear_head2.0.", "lam_model", "ttm_model", "asd_model")
         assert not unexpected, unexpected
         assert all(k.startswith(allowed) for k in missing), missing
         m.eval()

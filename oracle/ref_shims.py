@@ -289,9 +289,10 @@ def load_hoi():
         pnr2 = importlib.import_module("models.pnr.video_model_transfer")
         head = importlib.import_module("models.lta.head_helper")
         lta4 = importlib.import_module("models.lta.lta_models_lta_transfer")
+        lta3 = importlib.import_module("models.lta.lta_models_transfer")       # AR 3-task / 2TaskAR siblings
         # skip backbone construction in the 3-task base class
         pnr3.TaskFusion3Task.__init__ = lambda self, cfg, *a, **k: nn.Module.__init__(self)
-    return SimpleNamespace(pnr3=pnr3, pnr2=pnr2, lta4=lta4, head=head)
+    return SimpleNamespace(pnr3=pnr3, pnr2=pnr2, lta4=lta4, lta3=lta3, head=head)
 
 
 def hoi_pnr_cfg(hidden=128, layers=6, feat_dropout=0.5, tr_dropout=0.1, task="keyframe_localization_2loader"):

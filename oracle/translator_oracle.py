@@ -201,6 +201,32 @@ def hoi_pnr2_forward(P: Params, pnr: Tensor, oscc: Tensor, n_heads: int = 8, p_d
     return linear(x.mean(dim=1), P["linear_head.weight"], P["linear_head.bias"])
 
 
+def hoi_ar_forward(P: Params, slow: Tensor, fast: Tensor, pnr: Tensor, oscc: Tensor, n_heads: int = 8,
+                   p_drop: float = 0.0, training: bool = False) -> Tensor:
+    """Action-recognition TaskFusionMFTransformer3Task -> (B, 115 + 478) = [verb logits | noun logits].
+    HOI/models/lta/lta_models_transfer.py:124-137.  Token order (slow, fast, pnr, oscc); learned pe; the ONE LayerNorm
+    `ln` normalises the tokens and sits in front of both heads (linear_head{1,2} = Sequential(self.ln, Linear), :119-121).
+    slow/fast may be the raw 5-D SlowFast maps or the already pooled (B,8,C) features."""
+    if slow.dim() == 5:
+        slow, fast = pool_slowfast(slow, fast)
+    z = torch.cat([linear(slow, P["proj3_slow.weight"], P["proj3_slow.bias"]),
+                   linear(fast, P["proj3_fast.weight"], P["proj3_fast.bias"]),
+                   linear(pnr, P["proj1.weight"], P["proj1.bias"]),
+                   linear(oscc, P["proj2.weight"], P["proj2.bias"])], dim=1)
+    x = layer_norm(z, P["ln.weight"], P["ln.bias"]) + P["pe"]
+    x = encoder(x, P, "transformer.", count_layers(P, "transformer."), n_heads, p_drop, training)
+    g = layer_norm(x.mean(dim=1), P["ln.weight"], P["ln.bias"])
+    return torch.cat([linear(g, P["linear_head1.1.weight"], P["linear_head1.1.bias"]),
+                      linear(g, P["linear_head2.1.weight"], P["linear_head2.1.bias"])], dim=-1)
+
+
+def ar_loss(stacked: Tensor, labels: Tensor, num_classes=(115, 478)) -> Tensor:
+    """RecognitionTask2Loader.training_step (HOI/tasks/lta/long_term_anticipation_taskspecfic.py:26-33):
+    CE(verb logits, labels[:, 0]) + CE(noun logits, labels[:, 1])."""
+    v, n = torch.split(stacked, list(num_classes), dim=-1)
+    return torch.nn.functional.cross_entropy(v, labels[:, 0]) + torch.nn.functional.cross_entropy(n, labels[:, 1])
+
+
 def hoi_lta_forward(P: Params, pnr: Tensor, oscc: Tensor, action: Tensor, lta: Tensor, n_heads: int = 8,
                     p_drop: float = 0.0, p_head: float = 0.0, training: bool = False,
                     eval_softmax: bool = False) -> Tensor:
