@@ -172,7 +172,6 @@ class TranslatorEngine:
         self.lossav: Optional[Dict[str, torch.Tensor]] = None
         self._ws: Optional[torch.Tensor] = None
         self._persistent: Dict[Tuple, Activations] = {}
-        self.shadow_valid = False
 
     # ------------------------------------------------------------------ helpers
     def _mat(self, name: str) -> torch.Tensor:
