@@ -5,6 +5,7 @@ Reference (relative to /root/reference):
   lta.TaskFusionMFTransformerLTA4Task       HOI/models/lta/lta_models_lta_transfer.py:257-377
   pnr.TaskFusionMFTransformerDropout        HOI/models/pnr/video_model_transfer.py:70-105   (2-task sibling)
   lta.TaskFusionMFTransformer3Task          HOI/models/lta/lta_models_transfer.py:96-137    (action-recognition sibling)
+  lta.TaskFusionMFTransformer2TaskAR        HOI/models/lta/lta_models_transfer.py:169-235   (AR from recognition + LTA features)
   MultiTaskHead (LTA head)                  HOI/models/lta/head_helper.py:218-291
 The frozen PNR/OSCC/SlowFast/LTA backbones are not part of this package: inside an EgoT2 checkout
 they are built by the reference's own loaders; otherwise pass `backbones={...}`.
@@ -23,7 +24,7 @@ from torch.distributions.categorical import Categorical
 from . import _lib as L
 from .engine import _stream
 from .modules import PrecomputedFeatures, TranslatorBase
-from .specs import hoi_ar_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
+from .specs import hoi_ar2_spec, hoi_ar_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
 
 
 def slowfast_pool(x5: torch.Tensor, t_out: int, out_dtype: torch.dtype) -> torch.Tensor:
@@ -179,6 +180,86 @@ class _AR3Task(TranslatorBase):
         fast = slowfast_pool(fast5, 8, dt) if fast5.dim() == 5 else fast5
         out = self._translate([slow, fast, pnr_feat, oscc_feat])         # token order (slow, fast, pnr, oscc)
         return list(torch.split(out, list(self.num_classes), dim=-1))
+
+
+class _AR2Task(TranslatorBase):
+    """`TaskFusionMFTransformer2TaskAR` (HOI/models/lta/lta_models_transfer.py:169-235): the last input clip through the
+    recognition backbone (slow/fast maps) + the first NUM_INPUT_CLIPS clips through the LTA backbone -> [verbs, nouns]."""
+
+    def __init__(self, cfg, backbones: Optional[Dict[str, nn.Module]] = None):
+        super().__init__()
+        self.cfg = cfg
+        self.num_input = cfg.FORECASTING.NUM_INPUT_CLIPS
+        self.input_offset = cfg.FORECASTING.INPUT_OFFSET
+        num_cls1, num_cls2 = cfg.MODEL.NUM_CLASSES
+        self.num_classes = (num_cls1, num_cls2)
+        self.sequence_len = 18
+        self.num_heads = cfg.MODEL.TRANSLATION_HEADS
+        self.num_layers = cfg.MODEL.TRANSLATION_LAYERS
+        self.feature_dim = cfg.MODEL.TRANSLATION_INPUT_FEATURES
+        self.dp_rate = cfg.MODEL.TRANSLATION_DROPOUT
+        self.proj_lta = nn.Linear(2048, self.feature_dim)
+        self.proj_slow = nn.Linear(2048, self.feature_dim)
+        self.proj_fast = nn.Linear(256, self.feature_dim)
+        self.pe = nn.Parameter(torch.randn(1, self.sequence_len, self.feature_dim), requires_grad=True)
+        self.transformer = nn.TransformerEncoder(
+            encoder_layer=nn.TransformerEncoderLayer(d_model=self.feature_dim, nhead=self.num_heads,
+                                                     dropout=self.dp_rate, batch_first=True),
+            num_layers=self.num_layers, enable_nested_tensor=False)
+        self.ln = nn.LayerNorm(self.feature_dim)
+        self.linear_head1 = nn.Sequential(self.ln, nn.Linear(self.feature_dim, num_cls1))
+        self.linear_head2 = nn.Sequential(self.ln, nn.Linear(self.feature_dim, num_cls2))
+        for p in self.parameters():                       # reference _init_parameters (:211-214), before the backbones exist
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self._poison_containers(self.proj_lta, self.proj_slow, self.proj_fast, self.transformer, self.linear_head1,
+                                self.linear_head2)
+        if backbones is None:
+            backbones = _reference_ar2_backbones(cfg)
+        for k, m in backbones.items():
+            setattr(self, k, m)
+        self._init_translator(hoi_ar2_spec(self.feature_dim, self.num_layers, self.num_heads, self.dp_rate,
+                                           (num_cls1, num_cls2)))
+
+    def forward(self, x):
+        x1 = x.copy()
+        x_action = [x1[0][:, -1, ...], x1[1][:, -1, ...]]
+        x_lta = [x[0][:, 0:self.num_input, ...], x[1][:, 0:self.num_input, ...]]
+        with torch.no_grad():
+            slow5, fast5 = self.action_model(x_action, middle=True)      # (bs,2048,8,7,7), (bs,256,32,7,7)
+            feat_lta = self.lta_model(x_lta, middle=True).transpose(0, 1)   # (bs, num_input, 2048)
+        return self.translate(slow5, fast5, feat_lta)
+
+    def translate(self, slow5, fast5, feat_lta):
+        dt = torch.float32 if self.compute_dtype == "fp32" else torch.bfloat16
+        slow = slowfast_pool(slow5, slow5.shape[2], dt) if slow5.dim() == 5 else slow5
+        fast = slowfast_pool(fast5, 8, dt) if fast5.dim() == 5 else fast5
+        out = self._translate([slow, fast, feat_lta.contiguous()])       # token order (slow, fast, lta)
+        return list(torch.split(out, list(self.num_classes), dim=-1))
+
+
+def _reference_ar2_backbones(cfg):  # pragma: no cover - needs an EgoT2 checkout + checkpoints
+    """lta_models_transfer.py:216-227: recognition SlowFast trunk (no head) + LTA encoder (no decoder), both frozen."""
+    try:
+        from models.lta.video_model_builder import SlowFast                                        # type: ignore
+        from models.lta.lta_models import ForecastingEncoderDecoder                                # type: ignore
+        from utils.lta.parser import load_config_from_file as load_lta_config                      # type: ignore
+        from utils.multitask.load_model import load_lta_backbone, freeze_backbone_params, freeze_params  # type: ignore
+    except Exception as e:
+        raise L.Egot2Error("the frozen SlowFast/LTA backbones are not part of egot2_b200: run inside an EgoT2 checkout "
+                           "or pass backbones={'action_model':..., 'lta_model':...}") from e
+    out = {}
+    cfg_rec = load_lta_config(cfg.PRETRAIN.ACTION_CFG)
+    cfg_rec.MODEL.NUM_CLASSES = [cfg.MODEL.TRANSLATION_INPUT_FEATURES]
+    cfg_rec.MODEL.HEAD_ACT = None
+    out["action_model"] = SlowFast(cfg_rec, with_head=False)
+    load_lta_backbone(out["action_model"], cfg_rec.CHECKPOINT_FILE_PATH, True, True)
+    freeze_backbone_params(out["action_model"])
+    cfg_lta = load_lta_config(cfg.PRETRAIN.LTA_CFG)
+    out["lta_model"] = ForecastingEncoderDecoder(cfg_lta, build_decoder=False)
+    load_lta_backbone(out["lta_model"], cfg_lta.CHECKPOINT_FILE_PATH)
+    freeze_params(out["lta_model"])
+    return out
 
 
 def _reference_pnr_backbones(self, cfg, with_recognition=True):  # pragma: no cover - needs an EgoT2 checkout + checkpoints
@@ -341,8 +422,11 @@ pnr.MODEL_REGISTRY = {"TaskFusionMFTransformer3TaskDropout": _PNR3TaskDropout,
                       "TaskFusionMFTransformerDropout": _PNR2TaskDropout}
 pnr.build_model = lambda cfg, **kw: pnr.MODEL_REGISTRY[cfg.MODEL.MODEL_NAME](cfg, **kw)
 
-lta = SimpleNamespace(TaskFusionMFTransformerLTA4Task=_LTA4Task, TaskFusionMFTransformer3Task=_AR3Task)
+lta = SimpleNamespace(TaskFusionMFTransformerLTA4Task=_LTA4Task, TaskFusionMFTransformer3Task=_AR3Task,
+                      TaskFusionMFTransformer2TaskAR=_AR2Task)
+_AR2Task.__name__ = _AR2Task.__qualname__ = "TaskFusionMFTransformer2TaskAR"
 _LTA4Task.__name__ = _LTA4Task.__qualname__ = "TaskFusionMFTransformerLTA4Task"
 _AR3Task.__name__ = _AR3Task.__qualname__ = "TaskFusionMFTransformer3Task"
-lta.MODEL_REGISTRY = {"TaskFusionMFTransformerLTA4Task": _LTA4Task, "TaskFusionMFTransformer3Task": _AR3Task}
+lta.MODEL_REGISTRY = {"TaskFusionMFTransformerLTA4Task": _LTA4Task, "TaskFusionMFTransformer3Task": _AR3Task,
+                      "TaskFusionMFTransformer2TaskAR": _AR2Task}
 lta.build_model = lambda cfg, **kw: lta.MODEL_REGISTRY[cfg.MODEL.MODEL_NAME](cfg, **kw)

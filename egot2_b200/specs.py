@@ -230,6 +230,15 @@ def hoi_ar_spec(hidden=128, layers=3, heads=8, dropout=0.1, num_classes=(115, 47
                           "pool_ln_multilinear", sum(num_classes), True, dropout, 0.0, 0.0, 0.0, 0, tuple(num_classes), 1)
 
 
+def hoi_ar2_spec(hidden=128, layers=3, heads=8, dropout=0.1, num_classes=(115, 478), ffn=2048) -> TranslatorSpec:
+    """`TaskFusionMFTransformer2TaskAR` (HOI/models/lta/lta_models_transfer.py:169-235): AR from the recognition backbone's
+    (slow8, fast8) tokens plus the LTA backbone's 2 clip features = 18 tokens; same shared-ln two-head output as the
+    3-task AR translator; all dim>1 parameters xavier-initialised (:211-214)."""
+    segs = (Segment("slow", 2048, "proj_slow", 8), Segment("fast", 256, "proj_fast", 8), Segment("lta", 2048, "proj_lta", 2))
+    return TranslatorSpec("hoi_ar", hidden, heads, ffn, layers, segs, "learned_pe", "transformer.",
+                          "pool_ln_multilinear", sum(num_classes), True, dropout, 0.0, 0.0, 0.0, 0, tuple(num_classes), 1)
+
+
 def hoi_lta_spec(hidden=512, layers=4, heads=8, dropout=0.5, num_input_clips=2, num_actions=20,
                  num_classes=(115, 478), head_dropout=0.5, ffn=2048) -> TranslatorSpec:
     """LTA EgoT2-s: tokens (pnr, oscc, action, lta) x num_input_clips, FF=2048 (torch default),

@@ -41,6 +41,7 @@ CASES = {c.name: c for c in [
     Case("hoi_pnr2_h256_l3", specs.hoi_pnr2_spec(16, 0.1), 5, (16, 16), 13),
     # SURVEY 8a-F sibling: the action-recognition translator (48 tokens (slow,fast,pnr,oscc), FF 2048, shared ln, 2 heads)
     Case("hoi_ar_h128_l3", specs.hoi_ar_spec(128, 3, 8, 0.1), 4, (8, 8, 16, 16), 14),
+    Case("hoi_ar2_h128_l2", specs.hoi_ar2_spec(128, 2, 8, 0.1), 6, (8, 8, 2), 15),
     # BASELINE config 5 (scaled) and the shipped LTA config (H=1024, L=1)
     Case("hoi_lta_h512_l4", specs.hoi_lta_spec(512, 4, 8, 0.5), 3, (2, 2, 2, 2), 9),
     Case("hoi_lta_h1024_l1", specs.hoi_lta_spec(1024, 1, 8, 0.5), 2, (2, 2, 2, 2), 10),
@@ -93,6 +94,9 @@ def oracle_forward_loss(case: Case, P: Dict[str, torch.Tensor], feats, labels, e
             loss = O.bce_sigmoid_loss(out, torch.nn.functional.one_hot(labels, 16).float())
         else:
             loss = O.ce_loss(out, labels)
+    elif sp.family == "hoi_ar" and len(sp.segments) == 3:
+        out = O.hoi_ar2_forward(P, feats["slow"], feats["fast"], feats["lta"], sp.heads)
+        loss = O.ar_loss(out, labels, sp.head_groups)
     elif sp.family == "hoi_ar":
         out = O.hoi_ar_forward(P, feats["slow"], feats["fast"], feats["pnr"], feats["oscc"], sp.heads)
         loss = O.ar_loss(out, labels, sp.head_groups)

@@ -44,6 +44,15 @@ def build_reference(case: Case, hhi, hoi):
         task = "keyframe_localization_2loader" if sp.n_out == 16 else "state_change_detection"
         m = hoi.pnr3.TaskFusionMFTransformer3TaskDropout(rs.hoi_pnr_cfg(sp.hidden, sp.layers, sp.p_feat, sp.p_layer, task))
         return m
+    if sp.family == "hoi_ar" and len(sp.segments) == 3:
+        cfg = rs.CfgNode(MODEL=rs.CfgNode(NUM_CLASSES=list(sp.head_groups), TRANSLATION_HEADS=sp.heads,
+                                          TRANSLATION_LAYERS=sp.layers, TRANSLATION_INPUT_FEATURES=sp.hidden,
+                                          TRANSLATION_DROPOUT=sp.p_layer),
+                         FORECASTING=rs.CfgNode(NUM_INPUT_CLIPS=2, INPUT_OFFSET=0),
+                         PRETRAIN=rs.CfgNode(ACTION_CFG="x", LTA_CFG="x"))
+        # the backbone section of the ctor (:216-227) only needs a config object from the (stubbed) loader
+        hoi.lta3.load_lta_config = lambda f: rs.CfgNode(MODEL=rs.CfgNode(), CHECKPOINT_FILE_PATH=None)
+        return hoi.lta3.TaskFusionMFTransformer2TaskAR(cfg)
     if sp.family == "hoi_ar":
         cfg = rs.CfgNode(MODEL=rs.CfgNode(NUM_CLASSES=list(sp.head_groups), TRANSLATION_HEADS=sp.heads,
                                           TRANSLATION_LAYERS=sp.layers, TRANSLATION_INPUT_FEATURES=sp.hidden,
@@ -110,6 +119,14 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         else:
             out = out.squeeze(2)                                   # (B,2,1) -> (B,2)
             loss = torch.nn.functional.cross_entropy(out, labels)  # :143-146
+    elif sp.family == "hoi_ar" and len(sp.segments) == 3:
+        # forward() lines 229-236 run the frozen backbones under no_grad; we enter at the projections (:240-246)
+        feat = torch.cat((m.proj_slow(feats["slow"]), m.proj_fast(feats["fast"]), m.proj_lta(feats["lta"])), dim=1)
+        feat = m.ln(feat) + m.pe
+        out_t = m.transformer(feat).mean(dim=1)
+        preds = [m.linear_head1(out_t), m.linear_head2(out_t)]
+        out = torch.cat(preds, dim=-1)
+        loss = torch.nn.functional.cross_entropy(preds[0], labels[:, 0]) + torch.nn.functional.cross_entropy(preds[1], labels[:, 1])
     elif sp.family == "hoi_ar":
         slow = feats["slow"].permute(0, 2, 1)[..., None, None]
         fast = feats["fast"].permute(0, 2, 1).repeat_interleave(4, dim=2)[..., None, None]   # (B,256,32,1,1)
@@ -161,7 +178,8 @@ def main():
         m = build_reference(case, hhi, hoi)
         missing, unexpected = m.load_state_dict(sd, strict=False)
         # everything we do not set must be a buffer / alias / backbone, never a translator weight
-        allowed = ("pos_embed.pe", "linear_head.0.", "linear_head1.0.", "linear_head2.0.", "lam_model", "ttm_model", "asd_model")
+        allowed = ("pos_embed.pe", "linear_head.0.", "linear_head1.0.", "linear_head2.0.", "lam_model", "ttm_model", "asd_model",
+                   "action_model", "lta_model")
         assert not unexpected, unexpected
         assert all(k.startswith(allowed) for k in missing), missing
         m.eval()

@@ -220,6 +220,22 @@ def hoi_ar_forward(P: Params, slow: Tensor, fast: Tensor, pnr: Tensor, oscc: Ten
                       linear(g, P["linear_head2.1.weight"], P["linear_head2.1.bias"])], dim=-1)
 
 
+def hoi_ar2_forward(P: Params, slow: Tensor, fast: Tensor, lta: Tensor, n_heads: int = 8, p_drop: float = 0.0,
+                    training: bool = False) -> Tensor:
+    """TaskFusionMFTransformer2TaskAR -> (B, 115 + 478).  HOI/models/lta/lta_models_transfer.py:227-235: tokens
+    (slow8, fast8, lta2) -> ln + pe -> encoder -> mean -> shared ln -> two Linear heads."""
+    if slow.dim() == 5:
+        slow, fast = pool_slowfast(slow, fast)
+    z = torch.cat([linear(slow, P["proj_slow.weight"], P["proj_slow.bias"]),
+                   linear(fast, P["proj_fast.weight"], P["proj_fast.bias"]),
+                   linear(lta, P["proj_lta.weight"], P["proj_lta.bias"])], dim=1)
+    x = layer_norm(z, P["ln.weight"], P["ln.bias"]) + P["pe"]
+    x = encoder(x, P, "transformer.", count_layers(P, "transformer."), n_heads, p_drop, training)
+    g = layer_norm(x.mean(dim=1), P["ln.weight"], P["ln.bias"])
+    return torch.cat([linear(g, P["linear_head1.1.weight"], P["linear_head1.1.bias"]),
+                      linear(g, P["linear_head2.1.weight"], P["linear_head2.1.bias"])], dim=-1)
+
+
 def ar_loss(stacked: Tensor, labels: Tensor, num_classes=(115, 478)) -> Tensor:
     """RecognitionTask2Loader.training_step (HOI/tasks/lta/long_term_anticipation_taskspecfic.py:26-33):
     CE(verb logits, labels[:, 0]) + CE(noun logits, labels[:, 1])."""

@@ -66,6 +66,11 @@ def build_ours(case, backbones=True):
         bb = {"pnr_model": PrecomputedFeatures("pnr"), "oscc_model": PrecomputedFeatures("oscc"),
               "recognition_model": PrecomputedFeatures("slowfast")}
         return hoi.pnr.TaskFusionMFTransformer3TaskDropout(cfg, backbones=bb)
+    if sp.family == "hoi_ar" and len(sp.segments) == 3:
+        cfg = CfgNode(MODEL=CfgNode(NUM_CLASSES=list(sp.head_groups), TRANSLATION_HEADS=sp.heads, TRANSLATION_LAYERS=sp.layers,
+                                    TRANSLATION_INPUT_FEATURES=sp.hidden, TRANSLATION_DROPOUT=sp.p_layer),
+                      FORECASTING=CfgNode(NUM_INPUT_CLIPS=2, INPUT_OFFSET=0))
+        return hoi.lta.TaskFusionMFTransformer2TaskAR(cfg, backbones={})
     if sp.family == "hoi_ar":
         cfg = CfgNode(MODEL=CfgNode(NUM_CLASSES=list(sp.head_groups), TRANSLATION_HEADS=sp.heads, TRANSLATION_LAYERS=sp.layers,
                                     TRANSLATION_INPUT_FEATURES=sp.hidden, TRANSLATION_DROPOUT=sp.p_layer))
@@ -103,6 +108,8 @@ def run_ours(case, m, feats, extra, dev, labels=None):
             sf = [f["slow"], f["fast"]]
         out = m([{"pnr": f["pnr"], "oscc": f["oscc"]}], {"slowfast": sf})
         return out.squeeze(1) if sp.n_out == 16 else out.squeeze(2)
+    if sp.family == "hoi_ar" and len(sp.segments) == 3:
+        return torch.cat(m.translate(f["slow"], f["fast"], f["lta"]), dim=-1)
     if sp.family == "hoi_ar":
         return torch.cat(m({"slowfast": [f["slow"], f["fast"]]}, [{"pnr": f["pnr"], "oscc": f["oscc"]}]), dim=-1)
     if sp.family == "hoi_lta":
@@ -132,7 +139,7 @@ def test_container_forward_is_poisoned():
 
 @pytest.mark.requires_reference
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_l1", "hhi_asd_h128_l1", "hoi_pnr_h128_l6", "hoi_lta_h512_l4",
-                                  "hhi_g_ttm_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3"])
+                                  "hhi_g_ttm_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2"])
 def test_same_seed_same_init_as_reference(name):
     """ctor parity: under the same torch seed our module draws exactly the reference's initial weights."""
     from oracle import ref_shims as rs
@@ -155,7 +162,7 @@ def test_same_seed_same_init_as_reference(name):
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_d30", "hhi_asd_h128_l1", "hoi_pnr_h128_l6",
                                   "hoi_pnr_raw_maps", "hoi_lta_h512_l4", "hhi_g_lam_h128_l2", "hhi_g_ttm_h128_l2",
-                                  "hhi_g_asd_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3"])
+                                  "hhi_g_asd_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2"])
 def test_module_forward_backward_vs_oracle(name, dtype):
     from oracle import translator_oracle as O
     warnings.filterwarnings("ignore")
