@@ -277,6 +277,14 @@ extern "C" int egot2_dropout_epoch_advance(void* stream) {
 }
 extern "C" int egot2_dropout_epoch_host(uint64_t value) { g_host_epoch = value; return 0; }
 
+extern "C" int egot2_pnr_metrics(int32_t B, int32_t n, const float* logits, const int64_t* label_idx,
+                                 const float* label_onehot, const int64_t* sc_label, const double* fps,
+                                 const int64_t* start_frame, const int64_t* end_frame, const int64_t* pnr_frame,
+                                 double* err_sec, int64_t* out_counts, double* out_dist_sum, void* stream) {
+  return pnr_metrics(B, n, logits, label_idx, label_onehot, sc_label, fps, start_frame, end_frame, pnr_frame, err_sec,
+                     (long long*)out_counts, out_dist_sum, (cudaStream_t)stream);
+}
+
 extern "C" int egot2_prof_enable(int on) {
   if (on && !g_prof) {
     g_prof = (ProfRec*)calloc(kProfMax, sizeof(ProfRec));

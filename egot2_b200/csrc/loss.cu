@@ -155,7 +155,78 @@ __global__ void loss_reduce_kernel(long long segs, const float* __restrict__ seg
   }
 }
 
+// Batched PNR / OSCC evaluation metrics (HOI/evaluation/pnr/metrics.py:11-80), one thread per clip + one block-wide
+// reduction in a fixed order (deterministic).  out_i64 = [correct, total]; out_f64 = [sum of keyframe time errors (s)].
+//   pred   = first arg-max of the clip's logits (torch.argmax)
+//   label  = label_idx[b] if given, else the first arg-max of the clip's one-hot row
+//   clips with sc_label != 1 are skipped (sc_label == nullptr: every clip counts - state_change_accuracy)
+//   time error (only if fps != nullptr): | float32((end - start) / 16 * pred) - (pnr - start) | / fps
+__global__ void __launch_bounds__(1024) pnr_metrics_kernel(int B, int n, const float* __restrict__ logits,
+                                                           const int64_t* __restrict__ label_idx,
+                                                           const float* __restrict__ label_onehot,
+                                                           const int64_t* __restrict__ sc_label, const double* __restrict__ fps,
+                                                           const int64_t* __restrict__ start, const int64_t* __restrict__ end,
+                                                           const int64_t* __restrict__ pnr, double* __restrict__ err_sec,
+                                                           long long* __restrict__ out_i64, double* __restrict__ out_f64) {
+  EGOT2_PDL_ENTER();
+  __shared__ long long s_c[32], s_t[32];
+  __shared__ double s_d[32];
+  long long c = 0, t = 0;
+  double dsum = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {        // fixed assignment clip -> thread: deterministic sums
+    const float* z = logits + (size_t)b * n;
+    int am = 0; float mx = z[0];
+    for (int j = 1; j < n; ++j) if (z[j] > mx) { mx = z[j]; am = j; }
+    long long lab;
+    if (label_idx) lab = label_idx[b];
+    else {
+      const float* y = label_onehot + (size_t)b * n;
+      int la = 0; float lm = y[0];
+      for (int j = 1; j < n; ++j) if (y[j] > lm) { lm = y[j]; la = j; }
+      lab = la;
+    }
+    const bool counted = sc_label == nullptr || sc_label[b] == 1;
+    double e = 0.0;
+    if (counted) {
+      ++t;
+      if ((long long)am == lab) ++c;
+      if (fps) {
+        const float mapped = ((float)(end[b] - start[b]) / 16.0f) * (float)am;     // the reference's float32 tensor arithmetic
+        e = fabs((double)mapped - (double)(pnr[b] - start[b])) / fps[b];
+        dsum += e;
+      }
+    }
+    if (err_sec) err_sec[b] = counted ? e : -1.0;
+  }
+  // warp + block reduction in lane / warp order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_down_sync(0xffffffffu, c, o);
+    t += __shfl_down_sync(0xffffffffu, t, o);
+    dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = c; s_t[threadIdx.x >> 5] = t; s_d[threadIdx.x >> 5] = dsum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long cc = 0, tt = 0; double dd = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { cc += s_c[w]; tt += s_t[w]; dd += s_d[w]; }
+    out_i64[0] = cc; out_i64[1] = tt; out_f64[0] = dd;
+  }
+}
+
 }  // namespace
+
+int pnr_metrics(int B, int n, const float* logits, const int64_t* label_idx, const float* label_onehot,
+                const int64_t* sc_label, const double* fps, const int64_t* start, const int64_t* end, const int64_t* pnr,
+                double* err_sec, long long* out_i64, double* out_f64, cudaStream_t st) {
+  EGOT2_CHECK(B >= 0 && n >= 1 && logits && (label_idx || label_onehot) && out_i64 && out_f64, "pnr_metrics: bad arguments");
+  EGOT2_CHECK(!fps || (start && end && pnr), "pnr_metrics: the time error needs start/end/pnr frames");
+  ProfScope prof(st, "pnr_metrics B%d n%d", B, n);
+  launch(pnr_metrics_kernel, dim3(1), dim3(1024), 0, st, B, n, logits, label_idx, label_onehot, sc_label, fps, start, end, pnr,
+         err_sec, out_i64, out_f64);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
 
 int loss_fwd(const egot2_head_desc& d, int rows, const float* logits, const int64_t* labels, const float* class_weight,
              float* row_loss, float* loss, int32_t* argmax, cudaStream_t st) {

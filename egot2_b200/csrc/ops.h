@@ -135,6 +135,10 @@ int loss_reduce(const egot2_head_desc& d, int rows, const float* row_loss, float
 int head_fused_bwd(const egot2_head_desc& d, const egot2_head_in& in, const egot2_head_out& saved, float* dlogits, float dloss_scale,
                    void* dx, const egot2_head_grads& g, cudaStream_t st);
 
+// batched PNR / OSCC evaluation metrics on the device (loss.cu)
+int pnr_metrics(int B, int n, const float* logits, const int64_t* label_idx, const float* label_onehot,
+                const int64_t* sc_label, const double* fps, const int64_t* start, const int64_t* end, const int64_t* pnr,
+                double* err_sec, long long* out_i64, double* out_f64, cudaStream_t st);
 // losses on fp32 logits (rows, n_out)
 int loss_fwd(const egot2_head_desc& d, int rows, const float* logits, const int64_t* labels, const float* class_weight,
              float* row_loss, float* loss, int32_t* argmax, cudaStream_t st);

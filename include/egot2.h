@@ -332,6 +332,16 @@ int egot2_adam_step_fused_dev(float* param, float* grad, float* exp_avg, float* 
                               float beta1, float beta2, float eps, float weight_decay, const int32_t* step_dev,
                               float grad_scale, void* shadow_bf16, int32_t zero_grad, void* stream);
 
+/* Batched PNR / OSCC evaluation metrics in one launch (replaces the per-clip `.item()` loops of
+ * HOI/evaluation/pnr/metrics.py:11-80: state_change_accuracy, keyframe_accuracy, keyframe_distance).
+ * logits (B,n) fp32; label_idx (B) int64 OR label_onehot (B,n) fp32; sc_label (B) int64 or NULL (every clip counts);
+ * fps (B) f64 + start/end/pnr frames (B) int64, or fps NULL to skip the time error.
+ * out_counts[2] = {correct, total}; out_dist_sum[1] = sum over counted clips of
+ * |float32((end-start)/16 * argmax) - (pnr-start)| / fps; err_sec (B, optional) = per-clip error, -1 for skipped clips. */
+int egot2_pnr_metrics(int32_t B, int32_t n, const float* logits, const int64_t* label_idx, const float* label_onehot,
+                      const int64_t* sc_label, const double* fps, const int64_t* start_frame, const int64_t* end_frame,
+                      const int64_t* pnr_frame, double* err_sec, int64_t* out_counts, double* out_dist_sum, void* stream);
+
 /* ------------------------------------------------------------------ op-level entry points (diagnostics / unit tests) */
 /* C[M,N] = op(A)[M,K] . op(B)[K,N] (+bias[N]) ; A stored (M,K) or, if trans_a, (K,M); B stored (K,N) or, if
  * trans_b, (N,K) [nn.Linear weight layout]; relu optional; C fp32 or bf16 per `dtype` (A,B in `dtype`). */
