@@ -225,7 +225,11 @@ def run_reference(args, wl, spec):
     line = {"impl": "reference", "metric": "translator fwd+bwd clips/sec", "value": cps, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "clips_per_step": sample_batch, "tokens_per_clip": sum(wl["seg_tokens"])},
+            "config": {"workload": args.workload, "translator": spec.family, "hidden": spec.hidden, "layers": spec.layers,
+                       "heads": spec.heads, "ffn": spec.ffn, "clips_per_gpu": sample_batch,
+                       "tokens_per_clip": sum(wl["seg_tokens"]),
+                       "step": "fwd + loss + bwd (all translator grads) of the CPU oracle (torch restatement of the "
+                               "reference translator), fp32, all host threads; one bounded sample of the same workload"},
             "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
