@@ -290,9 +290,17 @@ def load_hoi():
         head = importlib.import_module("models.lta.head_helper")
         lta4 = importlib.import_module("models.lta.lta_models_lta_transfer")
         lta3 = importlib.import_module("models.lta.lta_models_transfer")       # AR 3-task / 2TaskAR siblings
+        _mod("models.multitask").__path__ = [os.path.join(root, "models/multitask")]
+        multitask = importlib.import_module("models.multitask.video_model_builder")   # HOI EgoT2-g (oracle/next_rows.py)
+
+        # torch>=2 passes is_causal to _mha_block; the reference override predates it (same shim as for HHI)
+        def _mha_block_g(self, x, mem, attn_mask, key_padding_mask, is_causal=False):
+            x = self.multihead_attn(x, mem, mem, attn_mask=attn_mask, key_padding_mask=key_padding_mask, need_weights=True)[0]
+            return self.dropout2(x)
+        multitask.CustomDecoderLayer._mha_block = _mha_block_g
         # skip backbone construction in the 3-task base class
         pnr3.TaskFusion3Task.__init__ = lambda self, cfg, *a, **k: nn.Module.__init__(self)
-    return SimpleNamespace(pnr3=pnr3, pnr2=pnr2, lta4=lta4, lta3=lta3, head=head)
+    return SimpleNamespace(pnr3=pnr3, pnr2=pnr2, lta4=lta4, lta3=lta3, head=head, multitask=multitask)
 
 
 def hoi_pnr_cfg(hidden=128, layers=6, feat_dropout=0.5, tr_dropout=0.1, task="keyframe_localization_2loader"):

@@ -340,6 +340,64 @@ def hhi_g_forward(P: Params, feats: Dict[str, Tensor], target_in: Tensor, mode: 
     return out.transpose(1, 2)                                    # (rows, V, S) like the reference's permute(1, 2, 0)
 
 
+# --------------------------------------------------------------------------------------
+# HOI EgoT2-g (oracle only so far: the CUDA path is a round-2 row)
+# --------------------------------------------------------------------------------------
+def hoi_g_encode(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: Tensor, n_heads: int, p_drop: float = 0.0,
+                 training: bool = False) -> Tensor:
+    """TaskTranslationPromptTransformer.encode (HOI/models/multitask/video_model_builder.py:228-246) -> memory (B,48,H).
+    Three TASKS: pnr (id 0), oscc (id 1) and action (id 2) = cat(proj_action_slow(slow8), proj_action_fast(fast8)); every
+    task gets ln + task_embed[id] + sinusoid restarting at 0 PER TASK (encode_prepare :144-148; the action task's 16 tokens
+    share one position run) + Dropout(0.1); concat (pnr, oscc, action) -> nn.TransformerEncoder."""
+    if slow.dim() == 5:
+        slow, fast = pool_slowfast(slow, fast)
+    H = P["ln.weight"].shape[0]
+    tasks = [linear(pnr, P["proj_pnr.weight"], P["proj_pnr.bias"]),
+             linear(oscc, P["proj_oscc.weight"], P["proj_oscc.bias"]),
+             torch.cat([linear(slow, P["proj_action_slow.weight"], P["proj_action_slow.bias"]),
+                        linear(fast, P["proj_action_fast.weight"], P["proj_action_fast.bias"])], dim=1)]
+    toks = []
+    for k, f in enumerate(tasks):
+        x = layer_norm(f, P["ln.weight"], P["ln.bias"]) + P["task_embed"][:, k, :]
+        x = x + sinusoid_table(f.shape[1], H).unsqueeze(0)
+        toks.append(_drop(x, 0.1, training))
+    x = torch.cat(toks, dim=1)
+    return encoder(x, P, "transformer_encoder.", count_layers(P, "transformer_encoder."), n_heads, p_drop, training)
+
+
+def hoi_g_decode(P: Params, mem: Tensor, target_in: Tensor, n_heads: int, p_drop: float = 0.0, training: bool = False) -> Tensor:
+    """decode (:150-160): Embedding * sqrt(H) + PE (+ dropout 0.1) -> TransformerDecoder with the causal mask -> fc.
+    Returns (B, S, V)."""
+    H = P["ln.weight"].shape[0]
+    S = target_in.shape[1]
+    y = P["embedding.weight"][target_in] * math.sqrt(H)
+    y = _drop(y + sinusoid_table(S, H).unsqueeze(0), 0.1, training)
+    mask = torch.full((S, S), float("-inf")).triu(1)
+    for i in range(count_layers(P, "transformer_decoder.")):
+        y = decoder_layer(y, mem, P, f"transformer_decoder.layers.{i}.", n_heads, mask, p_drop, training)
+    return linear(y, P["fc.weight"], P["fc.bias"])
+
+
+def hoi_g_forward(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: Tensor, target_in: Tensor, n_heads: int,
+                  p_drop: float = 0.0, training: bool = False) -> Tensor:
+    """forward(video_pnr, video_ac, target) -> (B, V, S) logits (:248-251)."""
+    mem = hoi_g_encode(P, pnr, oscc, slow, fast, n_heads, p_drop, training)
+    return hoi_g_decode(P, mem, target_in, n_heads, p_drop, training).transpose(1, 2)
+
+
+def hoi_g_predict_ac(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: Tensor, start_token: int, n_heads: int) -> Tensor:
+    """predict_ac (:264-275): greedy autoregressive decoding of a fixed 3-token sequence [action, verb, noun]; returns the two
+    generated vocabulary indices (B, 2)."""
+    mem = hoi_g_encode(P, pnr, oscc, slow, fast, n_heads)
+    B = pnr.shape[0]
+    toks = torch.ones((B, 3), dtype=torch.int64)
+    toks[:, 0] = start_token
+    for sy in range(1, 3):
+        out = hoi_g_decode(P, mem, toks[:, :sy], n_heads)            # (B, sy, V)
+        toks[:, sy] = out[:, -1].argmax(dim=-1)
+    return toks[:, 1:]
+
+
 def ce_loss(logits: Tensor, target: Tensor, weight: Optional[Tensor] = None) -> Tensor:
     """nn.CrossEntropyLoss(weight=w), reduction='mean':  sum_b w[y_b]*nll_b / sum_b w[y_b].
     TTM weight [0.266,0.734]: HHI/configs/ttm/config.py:36, HHI/tasks/ttm/video_task.py:23-24."""
