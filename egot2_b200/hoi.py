@@ -24,7 +24,7 @@ from torch.distributions.categorical import Categorical
 from . import _lib as L
 from .engine import _stream
 from .modules import PrecomputedFeatures, TranslatorBase
-from .specs import hoi_ar2_spec, hoi_ar_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
+from .specs import hoi_ar2_spec, hoi_ar_spec, hoi_lta2_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
 
 
 def slowfast_pool(x5: torch.Tensor, t_out: int, out_dtype: torch.dtype) -> torch.Tensor:
@@ -383,6 +383,94 @@ class _LTA4Task(TranslatorBase):
         return results
 
 
+class _LTA2Task(TranslatorBase):
+    """LTA 2-task sibling (HOI/models/lta/lta_models_lta_transfer.py:429-526): AR + LTA features of the input clips ->
+    20 future (verb, noun) distributions.  TRANSLATION_INPUT_FEATURES == 2048 (proj_lta = Identity) is not built."""
+
+    def __init__(self, cfg, backbones: Optional[Dict[str, nn.Module]] = None):
+        super().__init__()
+        self.cfg = cfg
+        self.sequence_len = cfg.FORECASTING.NUM_INPUT_CLIPS * 2
+        self.num_heads = cfg.MODEL.TRANSLATION_HEADS
+        self.num_layers = cfg.MODEL.TRANSLATION_LAYERS
+        self.feature_dim = cfg.MODEL.TRANSLATION_INPUT_FEATURES
+        if self.feature_dim == 2048:
+            raise L.Egot2Error("TaskFusionMFTransformer2Task with TRANSLATION_INPUT_FEATURES = 2048 (proj_lta = Identity) "
+                               "is not built: the LayerNorm kernels stop at H = 1024")
+        self.proj_lta = nn.Linear(2048, self.feature_dim)
+        self.dp_rate = cfg.MODEL.TRANSLATION_DROPOUT
+        self.pe = nn.Parameter(torch.randn(1, self.sequence_len, self.feature_dim), requires_grad=True)
+        self.transformer = nn.TransformerEncoder(
+            encoder_layer=nn.TransformerEncoderLayer(d_model=self.feature_dim, nhead=self.num_heads,
+                                                     dropout=self.dp_rate, batch_first=True),
+            num_layers=self.num_layers, enable_nested_tensor=False)
+        self.ln = nn.LayerNorm(self.feature_dim)
+        for p in self.parameters():                      # _init_parameters(): xavier on every dim>1 translator param
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        if backbones is None:
+            backbones = _reference_lta2_backbones(cfg)
+        for k, m in backbones.items():
+            setattr(self, k, m)
+        self.num_classes = list(cfg.MODEL.NUM_CLASSES)
+        per_head = reduce(lambda a, b: a + b, self.num_classes)
+        Z = cfg.FORECASTING.NUM_ACTIONS_TO_PREDICT
+        self.head = _HeadContainer(self.feature_dim, [per_head] * Z)     # default nn.Linear init, like the reference
+        self.test_noact = bool(cfg.TEST.NO_ACT)
+        self._poison_containers(self.proj_lta, self.transformer, self.ln, self.head)
+        self._init_translator(hoi_lta2_spec(self.feature_dim, self.num_layers, self.num_heads, self.dp_rate,
+                                            cfg.FORECASTING.NUM_INPUT_CLIPS, Z, tuple(self.num_classes),
+                                            cfg.MODEL.DROPOUT_RATE))
+
+    encode_clips = _LTA4Task.encode_clips
+
+    def translate(self, action, lta):
+        out = self._translate([action, lta])                   # (B, Z*593) logits
+        B = out.shape[0]
+        out = out.view(B, len(self.head.projections), -1)
+        if not self.training and not self.test_noact:
+            out = torch.softmax(out, dim=-1)                   # MultiTaskHead eval activation (head_helper.py:284-286)
+        return list(torch.split(out, self.num_classes, dim=-1))
+
+    def forward(self, x, tgts=None):
+        action = self.encode_clips(self.action_model, x)                 # (bs, num_input, d)
+        lta = self.lta_model(x, None, middle=True).transpose(0, 1)       # (bs, num_input, 2048)
+        return self.translate(action, lta)
+
+    def generate(self, x, k=1):
+        results = []
+        for head_x in self.forward(x):
+            if k > 1:
+                dist = Categorical(logits=head_x)
+                preds = [dist.sample() for _ in range(k)]
+            elif k == 1:
+                preds = [head_x.argmax(2)]
+            results.append(torch.stack(preds, dim=1))
+        return results
+
+
+def _reference_lta2_backbones(cfg):  # pragma: no cover - needs an EgoT2 checkout + checkpoints
+    import copy
+    try:
+        from models.lta.video_model_builder import SlowFast                                        # type: ignore
+        from models.lta.lta_models import ForecastingEncoderDecoder                                # type: ignore
+        from utils.multitask.load_model import load_lta_backbone, freeze_backbone_params, freeze_params  # type: ignore
+    except Exception as e:
+        raise L.Egot2Error("the frozen SlowFast/LTA backbones are not part of egot2_b200: run inside an EgoT2 checkout "
+                           "or pass backbones={'action_model':..., 'lta_model':...}") from e
+    out = {}
+    bcfg = copy.deepcopy(cfg)
+    bcfg.MODEL.NUM_CLASSES = [cfg.MODEL.TRANSLATION_INPUT_FEATURES]
+    bcfg.MODEL.HEAD_ACT = None
+    out["action_model"] = SlowFast(bcfg, with_head=True)
+    load_lta_backbone(out["action_model"], cfg.CHECKPOINT_FILE_PATH_AR, True, True)
+    freeze_backbone_params(out["action_model"])
+    out["lta_model"] = ForecastingEncoderDecoder(cfg, build_decoder=False)
+    load_lta_backbone(out["lta_model"], cfg.CHECKPOINT_FILE_PATH_LTA)
+    freeze_params(out["lta_model"])
+    return out
+
+
 def _reference_lta_backbones(self, cfg):  # pragma: no cover - needs an EgoT2 checkout + checkpoints
     import copy
     try:
@@ -423,10 +511,11 @@ pnr.MODEL_REGISTRY = {"TaskFusionMFTransformer3TaskDropout": _PNR3TaskDropout,
 pnr.build_model = lambda cfg, **kw: pnr.MODEL_REGISTRY[cfg.MODEL.MODEL_NAME](cfg, **kw)
 
 lta = SimpleNamespace(TaskFusionMFTransformerLTA4Task=_LTA4Task, TaskFusionMFTransformer3Task=_AR3Task,
-                      TaskFusionMFTransformer2TaskAR=_AR2Task)
+                      TaskFusionMFTransformer2TaskAR=_AR2Task, TaskFusionMFTransformer2Task=_LTA2Task)
+_LTA2Task.__name__ = _LTA2Task.__qualname__ = "TaskFusionMFTransformer2Task"
 _AR2Task.__name__ = _AR2Task.__qualname__ = "TaskFusionMFTransformer2TaskAR"
 _LTA4Task.__name__ = _LTA4Task.__qualname__ = "TaskFusionMFTransformerLTA4Task"
 _AR3Task.__name__ = _AR3Task.__qualname__ = "TaskFusionMFTransformer3Task"
 lta.MODEL_REGISTRY = {"TaskFusionMFTransformerLTA4Task": _LTA4Task, "TaskFusionMFTransformer3Task": _AR3Task,
-                      "TaskFusionMFTransformer2TaskAR": _AR2Task}
+                      "TaskFusionMFTransformer2TaskAR": _AR2Task, "TaskFusionMFTransformer2Task": _LTA2Task}
 lta.build_model = lambda cfg, **kw: lta.MODEL_REGISTRY[cfg.MODEL.MODEL_NAME](cfg, **kw)

@@ -239,6 +239,20 @@ def hoi_ar2_spec(hidden=128, layers=3, heads=8, dropout=0.1, num_classes=(115, 4
                           "pool_ln_multilinear", sum(num_classes), True, dropout, 0.0, 0.0, 0.0, 0, tuple(num_classes), 1)
 
 
+def hoi_lta2_spec(hidden=512, layers=1, heads=4, dropout=0.5, num_input_clips=2, num_actions=20,
+                  num_classes=(115, 478), head_dropout=0.5, ffn=2048) -> TranslatorSpec:
+    """LTA 2-task sibling `TaskFusionMFTransformer2Task` (HOI/models/lta/lta_models_lta_transfer.py:429-526): tokens
+    (action, lta) x num_input_clips, the action features arrive `hidden` wide from the SlowFast head, `proj_lta` is a
+    Linear(2048, hidden) (nn.Identity when hidden == 2048 - the shipped ts_lta_2task.yaml - which is beyond the
+    H <= 1024 LayerNorm kernels and not built), same MultiTaskHead as the 4-task translator."""
+    assert hidden != 2048, "hidden == 2048 (proj_lta = Identity) needs LayerNorm kernels beyond H = 1024: not built"
+    n = num_input_clips
+    segs = (Segment("action", hidden, None, n), Segment("lta", 2048, "proj_lta", n))
+    return TranslatorSpec("hoi_lta", hidden, heads, ffn, layers, segs, "learned_pe", "transformer.",
+                          "pool_multilinear", num_actions * sum(num_classes), False, dropout, 0.0, 0.0,
+                          head_dropout, 0, tuple(num_classes), num_actions)
+
+
 def hoi_lta_spec(hidden=512, layers=4, heads=8, dropout=0.5, num_input_clips=2, num_actions=20,
                  num_classes=(115, 478), head_dropout=0.5, ffn=2048) -> TranslatorSpec:
     """LTA EgoT2-s: tokens (pnr, oscc, action, lta) x num_input_clips, FF=2048 (torch default),

@@ -44,6 +44,8 @@ CASES = {c.name: c for c in [
     Case("hoi_ar2_h128_l2", specs.hoi_ar2_spec(128, 2, 8, 0.1), 6, (8, 8, 2), 15),
     # BASELINE config 5 (scaled) and the shipped LTA config (H=1024, L=1)
     Case("hoi_lta_h512_l4", specs.hoi_lta_spec(512, 4, 8, 0.5), 3, (2, 2, 2, 2), 9),
+    # SURVEY 8a-F sibling: LTA 2-task (tokens (action, lta) x 2); see UNVALIDATED_ON_GPU below
+    Case("hoi_lta2_h512_l1", specs.hoi_lta2_spec(512, 1, 4, 0.5), 3, (2, 2), 16),
     Case("hoi_lta_h1024_l1", specs.hoi_lta_spec(1024, 1, 8, 0.5), 2, (2, 2, 2, 2), 10),
     # BASELINE config 3: HHI EgoT2-g (encoder + decoder over the task prompt), the three forwards of one step
     Case("hhi_g_lam_h128_l2", specs.hhi_g_spec(128, 4, 2, 0.1, "lam"), 5, (7,), 11),
@@ -51,6 +53,12 @@ CASES = {c.name: c for c in [
     Case("hhi_g_asd_h128_l2", specs.hhi_g_spec(128, 4, 2, 0.1, "asd"), 2, (6, 6, 6), 11),
     Case("hhi_g_ttm_h256_l3", specs.hhi_g_spec(256, 4, 3, 0.1, "ttm"), 2, (30, 30, 30), 12),
 ]}
+
+
+#: cases added after the round's GPU budget was spent: CPU-side checks (state_dict keys, same-seed init, oracle pinned
+#: against the reference class, golden) are green, the GPU parity tests for them are marked xfail(strict=False) until
+#: they have run on hardware once (tests/test_zz_unvalidated_gpu.py)
+UNVALIDATED_ON_GPU = {"hoi_lta2_h512_l1"}
 
 
 def case_inputs(case: Case):
@@ -100,6 +108,9 @@ def oracle_forward_loss(case: Case, P: Dict[str, torch.Tensor], feats, labels, e
     elif sp.family == "hoi_ar":
         out = O.hoi_ar_forward(P, feats["slow"], feats["fast"], feats["pnr"], feats["oscc"], sp.heads)
         loss = O.ar_loss(out, labels, sp.head_groups)
+    elif sp.family == "hoi_lta" and len(sp.segments) == 2:
+        out = O.hoi_lta2_forward(P, feats["action"], feats["lta"], sp.heads)
+        loss = O.lta_loss(out, labels, sp.head_groups)
     elif sp.family == "hoi_lta":
         out = O.hoi_lta_forward(P, feats["pnr"], feats["oscc"], feats["action"], feats["lta"], sp.heads)
         loss = O.lta_loss(out, labels, sp.head_groups)

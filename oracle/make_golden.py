@@ -59,6 +59,10 @@ def build_reference(case: Case, hhi, hoi):
                                           TRANSLATION_DROPOUT=sp.p_layer),
                          PRETRAIN=rs.CfgNode(PNR_CFG=None, OSCC_CFG=None, ACTION_CFG=None))
         return hoi.lta3.TaskFusionMFTransformer3Task(cfg)
+    if sp.family == "hoi_lta" and len(sp.segments) == 2:
+        return hoi.lta4.TaskFusionMFTransformer2Task(
+            rs.hoi_lta_cfg(sp.hidden, sp.layers, sp.heads, sp.p_layer, sp.segments[0].tokens, sp.n_heads_out,
+                           sp.head_groups, sp.p_head))
     if sp.family == "hoi_lta":
         return hoi.lta4.TaskFusionMFTransformerLTA4Task(
             rs.hoi_lta_cfg(sp.hidden, sp.layers, sp.heads, sp.p_layer, sp.segments[0].tokens, sp.n_heads_out,
@@ -141,6 +145,20 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         out = torch.cat(preds, dim=-1)
         # HOI/tasks/lta/long_term_anticipation_taskspecfic.py:31-33
         loss = torch.nn.functional.cross_entropy(preds[0], labels[:, 0]) + torch.nn.functional.cross_entropy(preds[1], labels[:, 1])
+    elif sp.family == "hoi_lta" and len(sp.segments) == 2:
+        # forward() lines 510-512 run the backbones; we enter at the projection (:513-518)
+        feat = torch.cat((feats["action"], m.proj_lta(feats["lta"])), dim=1)
+        feat = m.ln(feat) + m.pe
+        out_t = m.transformer(feat).mean(dim=1)
+        m.head.training = True                                     # raw logits (train-mode head), dropout is p=0 below
+        if hasattr(m.head, "dropout"):
+            m.head.dropout.p = 0.0
+        preds = m.decode(out_t)
+        out = torch.cat(preds, dim=-1)
+        loss = 0
+        for h, head_x in enumerate(preds):
+            for z in range(head_x.shape[1]):
+                loss = loss + torch.nn.functional.cross_entropy(head_x[:, z], labels[:, z, h])
     elif sp.family == "hoi_lta":
         # forward() lines 355-358 run the backbones; we enter at the projections (359-363)
         feat = torch.cat((m.proj_pnr(feats["pnr"]), m.proj_oscc(feats["oscc"]), feats["action"],

@@ -340,6 +340,24 @@ def hhi_g_forward(P: Params, feats: Dict[str, Tensor], target_in: Tensor, mode: 
     return out.transpose(1, 2)                                    # (rows, V, S) like the reference's permute(1, 2, 0)
 
 
+def hoi_lta2_forward(P: Params, action: Tensor, lta: Tensor, n_heads: int = 4, p_drop: float = 0.0, p_head: float = 0.0,
+                     training: bool = False, eval_softmax: bool = False) -> Tensor:
+    """LTA TaskFusionMFTransformer2Task -> stacked head logits (B, Z, 593).
+    HOI/models/lta/lta_models_lta_transfer.py:510-518: tokens (action x n, proj_lta(lta) x n) -> ln + pe -> encoder ->
+    mean -> MultiTaskHead (Z x [Dropout -> Linear(H, 593)], softmax over 593 in eval unless TEST.NO_ACT)."""
+    z = torch.cat([action, linear(lta, P["proj_lta.weight"], P["proj_lta.bias"])], dim=1)
+    x = layer_norm(z, P["ln.weight"], P["ln.bias"]) + P["pe"]
+    x = encoder(x, P, "transformer.", count_layers(P, "transformer."), n_heads, p_drop, training)
+    g = x.mean(dim=1)
+    outs = []
+    zi = 0
+    while f"head.projections.{zi}.weight" in P:
+        outs.append(linear(_drop(g, p_head, training), P[f"head.projections.{zi}.weight"], P[f"head.projections.{zi}.bias"]))
+        zi += 1
+    out = torch.stack(outs, dim=1)
+    return torch.softmax(out, dim=-1) if eval_softmax else out
+
+
 # --------------------------------------------------------------------------------------
 # HOI EgoT2-g (SURVEY 8f-2; oracle only so far: the CUDA path is a round-2 row)
 # --------------------------------------------------------------------------------------

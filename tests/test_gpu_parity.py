@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from egot2_b200 import _lib as L
-from oracle.cases import CASES, case_inputs, grad_digest, oracle_forward_loss
+from oracle.cases import CASES, UNVALIDATED_ON_GPU, case_inputs, grad_digest, oracle_forward_loss
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -54,7 +54,7 @@ def _engine_feats(case, eng, feats, extra, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if n not in UNVALIDATED_ON_GPU])
 def test_engine_matches_oracle_and_golden(name, dtype):
     from egot2_b200.engine import TranslatorEngine
     from oracle import translator_oracle as O

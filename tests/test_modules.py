@@ -77,6 +77,13 @@ def build_ours(case, backbones=True):
         bb = {"pnr_model": PrecomputedFeatures("pnr"), "oscc_model": PrecomputedFeatures("oscc"),
               "recognition_model": PrecomputedFeatures("slowfast")}
         return hoi.lta.TaskFusionMFTransformer3Task(cfg, backbones=bb)
+    if sp.family == "hoi_lta" and len(sp.segments) == 2:
+        cfg = CfgNode(MODEL=CfgNode(TRANSLATION_INPUT_FEATURES=sp.hidden, TRANSLATION_LAYERS=sp.layers,
+                                    TRANSLATION_HEADS=sp.heads, TRANSLATION_DROPOUT=sp.p_layer,
+                                    NUM_CLASSES=list(sp.head_groups), DROPOUT_RATE=sp.p_head, HEAD_ACT="softmax"),
+                      FORECASTING=CfgNode(NUM_INPUT_CLIPS=sp.segments[0].tokens, NUM_ACTIONS_TO_PREDICT=sp.n_heads_out),
+                      TEST=CfgNode(NO_ACT=True))
+        return hoi.lta.TaskFusionMFTransformer2Task(cfg, backbones={})
     if sp.family == "hoi_lta":
         cfg = CfgNode(MODEL=CfgNode(TRANSLATION_INPUT_FEATURES=sp.hidden, TRANSLATION_LAYERS=sp.layers,
                                     TRANSLATION_HEADS=sp.heads, TRANSLATION_DROPOUT=sp.p_layer,
@@ -112,6 +119,8 @@ def run_ours(case, m, feats, extra, dev, labels=None):
         return torch.cat(m.translate(f["slow"], f["fast"], f["lta"]), dim=-1)
     if sp.family == "hoi_ar":
         return torch.cat(m({"slowfast": [f["slow"], f["fast"]]}, [{"pnr": f["pnr"], "oscc": f["oscc"]}]), dim=-1)
+    if sp.family == "hoi_lta" and len(sp.segments) == 2:
+        return torch.cat(m.translate(f["action"], f["lta"]), dim=-1)
     if sp.family == "hoi_lta":
         return torch.cat(m.translate(f["pnr"], f["oscc"], f["action"], f["lta"]), dim=-1)
 
@@ -139,7 +148,7 @@ def test_container_forward_is_poisoned():
 
 @pytest.mark.requires_reference
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_l1", "hhi_asd_h128_l1", "hoi_pnr_h128_l6", "hoi_lta_h512_l4",
-                                  "hhi_g_ttm_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2"])
+                                  "hhi_g_ttm_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2", "hoi_lta2_h512_l1"])
 def test_same_seed_same_init_as_reference(name):
     """ctor parity: under the same torch seed our module draws exactly the reference's initial weights."""
     from oracle import ref_shims as rs

@@ -18,7 +18,7 @@ def ref():
     return rs.load_hhi(), rs.load_hoi()
 
 
-@pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_l1", "hhi_asd_h128_l1", "hoi_pnr_h128_l6", "hoi_lta_h512_l4", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2"])
+@pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_l1", "hhi_asd_h128_l1", "hoi_pnr_h128_l6", "hoi_lta_h512_l4", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2", "hoi_lta2_h512_l1"])
 def test_restatement_equals_reference_fresh_seed(ref, name):
     from oracle.make_golden import build_reference, reference_forward_loss
     hhi, hoi = ref
