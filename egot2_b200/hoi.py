@@ -6,6 +6,7 @@ Reference (relative to /root/reference):
   pnr.TaskFusionMFTransformerDropout        HOI/models/pnr/video_model_transfer.py:70-105   (2-task sibling)
   lta.TaskFusionMFTransformer3Task          HOI/models/lta/lta_models_transfer.py:96-137    (action-recognition sibling)
   lta.TaskFusionMFTransformer2TaskAR        HOI/models/lta/lta_models_transfer.py:169-235   (AR from recognition + LTA features)
+  lta.TaskFusionMFTransformer2Task          HOI/models/lta/lta_models_lta_transfer.py:429-526 (LTA 2-task sibling, H <= 1024)
   MultiTaskHead (LTA head)                  HOI/models/lta/head_helper.py:218-291
 The frozen PNR/OSCC/SlowFast/LTA backbones are not part of this package: inside an EgoT2 checkout
 they are built by the reference's own loaders; otherwise pass `backbones={...}`.

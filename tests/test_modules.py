@@ -171,7 +171,8 @@ def test_same_seed_same_init_as_reference(name):
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_d30", "hhi_asd_h128_l1", "hoi_pnr_h128_l6",
                                   "hoi_pnr_raw_maps", "hoi_lta_h512_l4", "hhi_g_lam_h128_l2", "hhi_g_ttm_h128_l2",
-                                  "hhi_g_asd_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2"])
+                                  "hhi_g_asd_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2",
+                                  "hoi_lta2_h512_l1"])
 def test_module_forward_backward_vs_oracle(name, dtype):
     from oracle import translator_oracle as O
     warnings.filterwarnings("ignore")
