@@ -416,6 +416,54 @@ def hoi_g_predict_ac(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: T
     return toks[:, 1:]
 
 
+# --------------------------------------------------------------------------------------
+# simple_vit translators (oracle only so far: pre-norm / GELU kernels are a round-2 row)
+# --------------------------------------------------------------------------------------
+def simple_vit_transformer(x: Tensor, P: Params, pre: str, heads: int = 8) -> Tensor:
+    """HOI/models/pnr/simple_vit.py:55-107 `Transformer`: depth x [x = Attention(x) + x ; x = FeedForward(x) + x], both
+    PRE-norm; Attention = LayerNorm -> bias-free to_qkv (dim -> 3*heads*dim_head, dim_head independent of dim) ->
+    softmax(q k^T * dim_head^-0.5) v -> bias-free to_out; FeedForward = LayerNorm -> Linear -> exact (erf) GELU -> Linear.
+    No dropout anywhere, no final norm.  State_dict keys: `{pre}layers.{i}.0.{norm,to_qkv,to_out}`, `{pre}layers.{i}.1.net.{0,1,3}`."""
+    i = 0
+    while f"{pre}layers.{i}.0.norm.weight" in P:
+        a, f = f"{pre}layers.{i}.0.", f"{pre}layers.{i}.1.net."
+        h = layer_norm(x, P[a + "norm.weight"], P[a + "norm.bias"])
+        qkv = linear(h, P[a + "to_qkv.weight"], None)
+        B, N, inner3 = qkv.shape
+        dh = inner3 // 3 // heads
+        q, k, v = (t.reshape(B, N, heads, dh).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+        p = torch.softmax((q @ k.transpose(-1, -2)) * dh ** -0.5, dim=-1)
+        o = (p @ v).transpose(1, 2).reshape(B, N, heads * dh)
+        x = linear(o, P[a + "to_out.weight"], None) + x
+        h = layer_norm(x, P[f + "0.weight"], P[f + "0.bias"])
+        h = torch.nn.functional.gelu(linear(h, P[f + "1.weight"], P[f + "1.bias"]))
+        x = linear(h, P[f + "3.weight"], P[f + "3.bias"]) + x
+        i += 1
+    return x
+
+
+def hoi_pnr_vit_forward(P: Params, pnr: Tensor, oscc: Tensor, slow: Optional[Tensor] = None, fast: Optional[Tensor] = None) -> Tensor:
+    """simple_vit siblings -> (B, n_cls) logits before the unsqueeze.
+    3-task `TaskFusionMFTransformer3Task` (HOI/models/pnr/video_model_transfer_3task.py:128-164): tokens (pnr, oscc, slow, fast)
+    -> ln + pe -> simple_vit Transformer(dim 256, depth 3, heads 8, dim_head 128, mlp 512) -> mean -> Sequential(self.ln, Linear)
+    (the SAME ln as the token LayerNorm).  2-task `TaskFusionMFTransformer` (video_model_transfer.py:44-67): tokens (pnr, oscc),
+    NO token LayerNorm (feat = cat(proj1, proj2) + pe), head = Sequential(its own LayerNorm, Linear)."""
+    if slow is not None:
+        if slow.dim() == 5:
+            slow, fast = pool_slowfast(slow, fast)
+        z = torch.cat([linear(pnr, P["proj1.weight"], P["proj1.bias"]), linear(oscc, P["proj2.weight"], P["proj2.bias"]),
+                       linear(slow, P["proj3_slow.weight"], P["proj3_slow.bias"]),
+                       linear(fast, P["proj3_fast.weight"], P["proj3_fast.bias"])], dim=1)
+        x = layer_norm(z, P["ln.weight"], P["ln.bias"]) + P["pe"]
+        x = simple_vit_transformer(x, P, "transformer.")
+        g = layer_norm(x.mean(dim=1), P["ln.weight"], P["ln.bias"])
+    else:
+        z = torch.cat([linear(pnr, P["proj1.weight"], P["proj1.bias"]), linear(oscc, P["proj2.weight"], P["proj2.bias"])], dim=1)
+        x = simple_vit_transformer(z + P["pe"], P, "transformer.")
+        g = layer_norm(x.mean(dim=1), P["linear_head.0.weight"], P["linear_head.0.bias"])
+    return linear(g, P["linear_head.1.weight"], P["linear_head.1.bias"])
+
+
 def ce_loss(logits: Tensor, target: Tensor, weight: Optional[Tensor] = None) -> Tensor:
     """nn.CrossEntropyLoss(weight=w), reduction='mean':  sum_b w[y_b]*nll_b / sum_b w[y_b].
     TTM weight [0.266,0.734]: HHI/configs/ttm/config.py:36, HHI/tasks/ttm/video_task.py:23-24."""

@@ -52,3 +52,32 @@ def test_hoi_g_oracle_matches_reference_live():
     gold = np.load(NR.GOLDEN)
     assert np.allclose(rec["output"], gold["output"], atol=2e-5, rtol=1e-4)
     assert np.array_equal(rec["predict_ac"], gold["predict_ac"])
+
+
+@pytest.mark.parametrize("three_task", [False, True])
+def test_simple_vit_oracle_matches_golden(three_task):
+    """simple_vit siblings (pre-norm, GELU, bias-free qkv/out with dim_head 128 x 8 heads on a 256-wide model): the
+    restatement against the golden made from the reference classes (oracle/next_rows.py main_vit)."""
+    gold = np.load(NR.GOLDEN_VIT)
+    tag = "3task" if three_task else "2task"
+    sd, feats, labels = NR.vit_inputs(three_task)
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out, loss = NR.vit_oracle(P, feats, labels, three_task)
+    ref = torch.from_numpy(gold[tag + "/output"])
+    assert float((out.detach() - ref).abs().max()) <= 2e-5 + 1e-4 * float(ref.abs().max())
+    assert abs(float(loss) - float(gold[tag + "/loss"])) <= 1e-4 * abs(float(gold[tag + "/loss"]))
+    names = [k[len(tag + "/grad/"):] for k in gold.files if k.startswith(tag + "/grad/")]
+    grads = torch.autograd.grad(loss, [P[k] for k in names])
+    for k, g in zip(names, grads):
+        d, r = grad_digest(g), torch.from_numpy(gold[tag + "/grad/" + k])
+        assert float((d - r).abs().max()) <= 2e-4 * (float(r.abs().max()) + 1e-6) + 1e-6, k
+    assert torch.equal(out.argmax(-1), ref.argmax(-1))          # keyframe index
+
+
+@pytest.mark.requires_reference
+@pytest.mark.skipif(not os.path.exists("/root/reference/HOI/models/pnr/simple_vit.py"), reason="reference tree not present")
+def test_simple_vit_oracle_matches_reference_live():
+    rec = NR.main_vit(write=False)
+    gold = np.load(NR.GOLDEN_VIT)
+    for tag in ("2task", "3task"):
+        assert np.allclose(rec[tag + "/output"], gold[tag + "/output"], atol=2e-5, rtol=1e-4)
