@@ -2,6 +2,7 @@
 
     python -m egot2_b200.build            # incremental
     python -m egot2_b200.build --force
+    EGOT2_BUILD_TAG=timeline EGOT2_CFLAGS=-DEGOT2_TIMELINE python -m egot2_b200.build    # -> lib/libegot2_timeline.so
 
 The library lands in egot2_b200/lib/libegot2.so (git-ignored, shipped to the GPU box by gpurun).
 """
@@ -15,8 +16,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "libegot2.so")
+# EGOT2_BUILD_TAG=<tag>: an instrumented / experimental variant (e.g. EGOT2_CFLAGS=-DEGOT2_TIMELINE) gets its own object
+# directory and library name (lib/libegot2_<tag>.so, loaded with EGOT2_LIB=...), so the product build is never disturbed
+_TAG = os.environ.get("EGOT2_BUILD_TAG", "")
+OBJDIR = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(LIBDIR, "libegot2" + ("_" + _TAG if _TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]

@@ -3,8 +3,8 @@
 every kernel stamps %globaltimer when it starts; the stamps of one CUDA-graph replay, sorted by time, show the real
 start order / gaps of the main chain and the side streams.
 
-  EGOT2_CFLAGS=-DEGOT2_TIMELINE python -m egot2_b200.build --force   (then copy the .so aside and rebuild normally)
-  EGOT2_LIB=/path/libegot2_timeline.so python tools/timeline.py
+  EGOT2_BUILD_TAG=timeline EGOT2_CFLAGS=-DEGOT2_TIMELINE python -m egot2_b200.build      (-> egot2_b200/lib/libegot2_timeline.so)
+  EGOT2_LIB=$PWD/egot2_b200/lib/libegot2_timeline.so python tools/timeline.py
 """
 import argparse
 import os
