@@ -242,10 +242,11 @@ class TranslatorEngine:
             if self.pe_buffer is None:
                 raise L.Egot2Error("HHI translator: call set_sinusoid(pos_embed.pe) first")
             table = buf("tok_table", (T, H), torch.float32)
-            segs = (C.c_int32 * len(seg_tokens))(*seg_tokens)
-            ids = (C.c_int32 * len(seg_tokens))(*[s.task_id for s in sp.segments])
+            runs = sp.table_runs(seg_tokens)          # one position run per segment (HOI EgoT2-g: slow|fast share one)
+            segs = (C.c_int32 * len(runs))(*[r[0] for r in runs])
+            ids = (C.c_int32 * len(runs))(*[r[1] for r in runs])
             L.call("egot2_hhi_tok_table_fwd", self._vec("task_embed").data_ptr(), self.pe_buffer.data_ptr(),
-                   int(self.pe_buffer.shape[0]), len(seg_tokens), segs, ids, H, table.data_ptr(), st)
+                   int(self.pe_buffer.shape[0]), len(runs), segs, ids, H, table.data_ptr(), st)
         else:
             table = self._vec("pe").view(T, H)
 
@@ -480,6 +481,22 @@ class TranslatorEngine:
         L.call("egot2_head_loss_fwd", C.byref(hd), C.byref(hin), C.byref(hout), st)
         t["out"] = logits
         return act
+
+    def decode_again(self, act: Activations, prompt: torch.Tensor) -> Activations:
+        """Greedy decoding step of EgoT2-g (predict_ac, HOI/models/multitask/video_model_builder.py:264-275): only the
+        decoder and the vocabulary head run, for a new (longer) prompt, over the encoder memory `act` already holds.
+        Inference only; the returned activations own their decoder buffers and share the memory."""
+        if self.spec.head != "decoder" or "x_last" not in act.t:
+            raise L.Egot2Error("decode_again: needs the activations of an EgoT2-g forward")
+        act2 = Activations(act.B, act.seg_tokens, act.T, False, 0)
+        t, dev = act2.t, self.device
+        t["x_last"] = act.t["x_last"]
+
+        def buf(name, shape, dtype):
+            if name not in t:
+                t[name] = torch.empty(shape, device=dev, dtype=dtype)
+            return t[name]
+        return self._decoder_forward(act2, t["x_last"], prompt, False, 0, None, L.LOSS_NONE, buf)
 
     def _decoder_backward(self, act: Activations, dout, dloss_scale, grad, gv) -> torch.Tensor:
         """Backward of the vocabulary head, the decoder layers and the prompt embedding; returns d(loss)/d(memory) in the

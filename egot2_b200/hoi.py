@@ -8,6 +8,8 @@ Reference (relative to /root/reference):
   lta.TaskFusionMFTransformer2TaskAR        HOI/models/lta/lta_models_transfer.py:169-235   (AR from recognition + LTA features)
   lta.TaskFusionMFTransformer2Task          HOI/models/lta/lta_models_lta_transfer.py:429-526 (LTA 2-task sibling, H <= 1024)
   MultiTaskHead (LTA head)                  HOI/models/lta/head_helper.py:218-291
+  multitask.TaskTranslationPromptTransformer       HOI/models/multitask/video_model_builder.py:223-275 (HOI EgoT2-g)
+  multitask.TaskTranslationPromptTransformer6Task  HOI/models/multitask/video_model_builder.py:279-383
 The frozen PNR/OSCC/SlowFast/LTA backbones are not part of this package: inside an EgoT2 checkout
 they are built by the reference's own loaders; otherwise pass `backbones={...}`.
 """
@@ -23,9 +25,10 @@ import torch.nn as nn
 from torch.distributions.categorical import Categorical
 
 from . import _lib as L
-from .engine import _stream
+from .engine import TranslatorEngine, _stream
+from .functional import translator_apply
 from .modules import PrecomputedFeatures, TranslatorBase
-from .specs import hoi_ar2_spec, hoi_ar_spec, hoi_lta2_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
+from .specs import hoi_ar2_spec, hoi_ar_spec, hoi_g_spec, hoi_lta2_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
 
 
 def slowfast_pool(x5: torch.Tensor, t_out: int, out_dtype: torch.dtype) -> torch.Tensor:
@@ -503,6 +506,257 @@ def _reference_lta_backbones(self, cfg):  # pragma: no cover - needs an EgoT2 ch
     load_lta_backbone(out["lta_model"], cfg.CHECKPOINT_FILE_PATH_LTA); freeze_params(out["lta_model"])
     return out
 
+
+# ------------------------------------------------------------------------------------------------ HOI EgoT2-g
+class _PromptTranslator(TranslatorBase):
+    """HOI EgoT2-g `TaskTranslationPromptTransformer` (HOI/models/multitask/video_model_builder.py:223-275 on the
+    TaskPromptTransformer base, :54-160): PNR + OSCC + action (slow | fast) tokens -> nn.TransformerEncoder -> memory;
+    an nn.TransformerDecoder over the task prompt ([task word, answer, ...]) and a vocabulary head.  Imported directly by
+    HOI/tasks/multitask/video_task.py:20,176 (not through a registry)."""
+
+    _n_tasks = 3
+
+    def __init__(self, args, vocab, oscc_no_temp_pool=True, backbones: Optional[Dict[str, nn.Module]] = None):
+        super().__init__()
+        from .hhi import PositionalEncoding
+        self.args = args
+        self.vocab = vocab
+        self.dim = args.hidden_dim
+        self.n_tasks = 3
+        self.task_dict = {"pnr": 0, "oscc": 1, "action": 2}
+        self.n_heads = args.num_heads
+        self.num_layers = args.num_layers
+        self.dp_rate = args.dropout
+        n_vocab = len(vocab)
+        # parameter containers in the reference's registration order (:70-90): same RNG draws, same state_dict keys
+        self.transformer_encoder = nn.TransformerEncoder(
+            encoder_layer=nn.TransformerEncoderLayer(d_model=self.dim, nhead=self.n_heads, dropout=self.dp_rate),
+            num_layers=self.num_layers, enable_nested_tensor=False)
+        self.transformer_decoder = nn.TransformerDecoder(
+            decoder_layer=nn.TransformerDecoderLayer(d_model=self.dim, nhead=self.n_heads, dropout=self.dp_rate),
+            num_layers=self.num_layers)
+        self.proj_pnr = nn.Linear(8192, self.dim)
+        self.proj_oscc = nn.Linear(8192, self.dim)
+        self.proj_action_slow = nn.Linear(2048, self.dim)
+        self.proj_action_fast = nn.Linear(256, self.dim)
+        self.fc = nn.Linear(self.dim, n_vocab)
+        self.ln = nn.LayerNorm(self.dim)
+        self.task_embed = nn.Parameter(torch.randn(1, self.n_tasks, self.dim), requires_grad=True)
+        self.pos_embed = PositionalEncoding(self.dim, dropout=0.1, max_len=200)
+        self.embedding = nn.Embedding(n_vocab, self.dim)
+        self.seq_len = 5
+        self.y_mask = self.get_tgt_mask(self.seq_len)
+        for p in self.parameters():                      # _init_parameters (:121-124), before the backbones exist
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        if backbones is None:
+            backbones = _reference_multitask_backbones(self, args, oscc_no_temp_pool)
+        for k, m in backbones.items():
+            setattr(self, k, m)
+        self._finish()
+
+    def _finish(self):
+        self._poison_containers(self.transformer_encoder, self.transformer_decoder, self.ln, self.proj_pnr, self.proj_oscc,
+                                self.proj_action_slow, self.proj_action_fast, self.fc)
+        self.embedding.forward = None
+        self._specs = {"clip": hoi_g_spec(self.dim, self.n_heads, self.num_layers, self.dp_rate, len(self.vocab), "clip",
+                                          self._n_tasks)}
+        self._init_translator(self._specs["clip"])
+        self._mode_engines: Dict[str, TranslatorEngine] = {}
+
+    def get_tgt_mask(self, size) -> torch.Tensor:
+        """(:127-142) kept for API parity; the decoder kernels apply the causal mask themselves."""
+        mask = torch.tril(torch.ones(size, size) == 1).float()
+        return mask.masked_fill(mask == 0, float("-inf")).masked_fill(mask == 1, 0.0)
+
+    def _configure_engine(self, eng: TranslatorEngine):
+        eng.set_sinusoid(self.pos_embed.pe)
+
+    def _engine_for(self, mode: str, device: torch.device) -> TranslatorEngine:
+        base = self._ensure_engine(device)               # the 'clip' spec owns the arena every parameter lives in
+        if mode == "clip":
+            return base
+        eng = self._mode_engines.get(mode)
+        if eng is None or eng.arena is not base.arena or eng.dtype != base.dtype:
+            eng = TranslatorEngine(self._specs[mode], device, base.dtype, arena=base.arena)
+            eng.set_sinusoid(self.pos_embed.pe)
+            self._mode_engines[mode] = eng
+        return eng
+
+    def _clip_features(self, video_pnr, video_ac) -> List[torch.Tensor]:
+        """The frozen backbones of encode() (:229-233) + the adaptive pooling of the SlowFast maps (:237-238)."""
+        video_oscc = video_pnr.copy()
+        with torch.no_grad():
+            feat_pnr = self.pnr_model(video_pnr, middle=True)              # (bs, 16, 8192)
+            feat_oscc = self.oscc_model(video_oscc, middle=True)           # (bs, 16, 8192)
+            slow5, fast5 = self.recognition_model(video_ac, middle=True)   # (bs,2048,8,7,7), (bs,256,32,7,7)
+        dt = torch.float32 if self.compute_dtype == "fp32" else torch.bfloat16
+        slow = slowfast_pool(slow5, slow5.shape[2], dt) if slow5.dim() == 5 else slow5
+        fast = slowfast_pool(fast5, 8, dt) if fast5.dim() == 5 else fast5
+        return [feat_pnr, feat_oscc, slow, fast]                           # token order (pnr, oscc, slow | fast)
+
+    def _decode(self, feats, tokens, mode="clip"):
+        eng = self._engine_for(mode, feats[0].device)
+        out = translator_apply(eng, list(feats), self._params(), self._param_names, self.training, self._next_seed(),
+                               prompt=tokens)
+        rows, S = tokens.shape
+        return out.view(rows, S, -1)                                       # (bs, seq, vocab)
+
+    def _start(self, feats, word) -> torch.Tensor:
+        return torch.full((feats[0].shape[0], 1), int(self.vocab[word]), dtype=torch.int64, device=feats[0].device)
+
+    def forward(self, video_pnr, video_ac, target):
+        feats = self._clip_features(video_pnr, video_ac)
+        return self._decode(feats, target).permute(0, 2, 1)                # (bs, vocab_size, seq_y)
+
+    def predict(self, video_pnr, video_ac, task):
+        assert task in ["pnr", "oscc", "action_verb", "action_noun"]
+        feats = self._clip_features(video_pnr, video_ac)
+        out = self._decode(feats, self._start(feats, task))[:, 0]          # (bs, vocab)
+        return torch.argmax(out, dim=-1) if "action" in task else out
+
+    def _greedy(self, feats, start_word: str, seq_len: int = 3, mode: str = "clip") -> torch.Tensor:
+        """Greedy decoding of a fixed-length answer (:264-275): one encoder pass, then the decoder alone per new token."""
+        B, dev = feats[0].shape[0], feats[0].device
+        toks = torch.ones((B, seq_len), dtype=torch.int64, device=dev)
+        toks[:, 0] = int(self.vocab[start_word])
+        if self.training:                                                  # dropout on: the regular (autograd) path
+            for sy in range(1, seq_len):
+                toks[:, sy] = self._decode(feats, toks[:, :sy].contiguous(), mode)[:, -1].argmax(dim=-1)
+            return toks[:, 1:]
+        eng = self._engine_for(mode, dev)
+        with torch.no_grad():
+            act = None
+            for sy in range(1, seq_len):
+                y = toks[:, :sy].contiguous()
+                act = eng.forward(list(feats), training=False, prompt=y) if act is None else eng.decode_again(act, y)
+                toks[:, sy] = act.t["out"].view(B, sy, -1)[:, -1].argmax(dim=-1)
+        return toks[:, 1:]                                                 # idx in vocab
+
+    def predict_ac(self, video_pnr, video_ac):
+        return self._greedy(self._clip_features(video_pnr, video_ac), "action")
+
+
+class _PromptTranslator6Task(_PromptTranslator):
+    """`TaskTranslationPromptTransformer6Task` (:279-383): the same clip encode for the pnr / oscc / action prompts with
+    a 4-row task_embed, plus an 'lta' encode over (pnr, oscc, action, lta) features of the input clips (:325-339)."""
+
+    _n_tasks = 4
+
+    def __init__(self, args, vocab, backbones: Optional[Dict[str, nn.Module]] = None):
+        super().__init__(args, vocab, backbones=backbones)
+
+    def _finish(self):
+        # registered after the base class is complete (:282-283): plain randn / default Linear init, no xavier
+        self.task_embed = nn.Parameter(torch.randn(1, 4, self.dim), requires_grad=True)
+        self.proj_lta = nn.Linear(2048, self.dim)
+        if not hasattr(self, "lta_model"):
+            self.lta_model = _reference_multitask_lta_backbone(self, self.args)
+        super()._finish()
+        self._poison_containers(self.proj_lta)                             # 'lta' specs: built on first use (num_input
+                                                                           # comes with the data), see _features()
+
+    encode_clips = None          # bound below (same loops as the LTA translators)
+    encode_clips_pnr = None
+
+    def _features(self, video_pnr, video_ac, task):
+        if "lta" not in task:
+            return self._clip_features(video_pnr, video_ac), "clip"
+        import copy
+        with torch.no_grad():
+            video_oscc = copy.deepcopy(video_pnr)
+            feat_pnr = self.encode_clips_pnr(self.pnr_model, video_pnr)    # (bs, num_input, 8192)
+            feat_oscc = self.encode_clips_pnr(self.oscc_model, video_oscc)
+            feat_action = self.encode_clips(self.recognition_model, video_ac)          # (bs, num_input, dim)
+            feat_lta = self.lta_model(video_ac, None, middle=True).transpose(0, 1)     # (bs, num_input, 2048)
+        n = feat_pnr.shape[1]
+        key = f"lta{n}"
+        if self._specs.get(key) is None:
+            self._specs[key] = hoi_g_spec(self.dim, self.n_heads, self.num_layers, self.dp_rate, len(self.vocab), "lta", 4, n)
+        return [feat_pnr.contiguous(), feat_oscc.contiguous(), feat_action.contiguous(), feat_lta.contiguous()], key
+
+    def forward(self, video_pnr, video_ac, target, task):
+        feats, mode = self._features(video_pnr, video_ac, task)
+        return self._decode(feats, target, mode).permute(0, 2, 1)          # (bs, vocab_size, seq_y)
+
+    def predict(self, video_pnr, video_ac, task, predict_verb_only=False, predict_noun_only=False):
+        assert task in ["pnr", "oscc", "action", "lta"]
+        feats, mode = self._features(video_pnr, video_ac, task)
+        if task in ["action", "lta"]:
+            if not predict_noun_only:
+                out_verb = self._decode(feats, self._start(feats, task + "_verb"), mode)[:, 0]
+            if predict_verb_only:
+                return
+            out_noun = self._decode(feats, self._start(feats, task + "_noun"), mode)[:, 0]
+            if predict_noun_only:
+                return
+            return torch.stack((out_verb.argmax(dim=-1), out_noun.argmax(dim=-1)), dim=1)      # (bs, 2)
+        return self._decode(feats, self._start(feats, task), mode)[:, 0]
+
+    def predict_ac(self, video_pnr, video_ac):
+        raise AttributeError("TaskTranslationPromptTransformer6Task has no predict_ac (the reference class predicts verb "
+                             "and noun with two one-token prompts: predict(..., 'action'))")
+
+
+_PromptTranslator6Task.encode_clips = _LTA4Task.encode_clips
+_PromptTranslator6Task.encode_clips_pnr = _LTA4Task.encode_clips_pnr
+
+
+def _reference_multitask_backbones(self, args, oscc_no_temp_pool=True):  # pragma: no cover - needs an EgoT2 checkout
+    """video_model_builder.py:96-119: PNR / OSCC ResNets (frozen) and the recognition SlowFast with a hidden_dim head."""
+    try:
+        from models.pnr.video_model_builder import KeyframeLocalizationResNet, StateChangeClsResNet  # type: ignore
+        from models.lta.video_model_builder import SlowFast                                        # type: ignore
+        from utils.pnr.parser import load_config_file                                              # type: ignore
+        from utils.lta.parser import load_config_from_file as load_lta_config                      # type: ignore
+        from utils.multitask.load_model import (load_checkpoint, freeze_params,                   # type: ignore
+                                                load_recognition_backbone, freeze_backbone_params)
+    except Exception as e:
+        raise L.Egot2Error("the frozen PNR/OSCC/SlowFast backbones are not part of egot2_b200: run inside an EgoT2 "
+                           "checkout or pass backbones={'pnr_model':..., 'oscc_model':..., 'recognition_model':...}") from e
+    out = {}
+    cfg_pnr = load_config_file(args.pnr_cfg_file)
+    out["pnr_model"] = KeyframeLocalizationResNet(cfg_pnr)
+    load_checkpoint(out["pnr_model"], cfg_pnr.MISC.CHECKPOINT_FILE_PATH)
+    freeze_params(out["pnr_model"])
+    cfg_oscc = load_config_file(args.oscc_cfg_file)
+    cfg_oscc.MODEL.NO_TEMP_POOL = oscc_no_temp_pool
+    out["oscc_model"] = StateChangeClsResNet(cfg_oscc)
+    load_checkpoint(out["oscc_model"], cfg_oscc.MISC.CHECKPOINT_FILE_PATH)
+    freeze_params(out["oscc_model"])
+    cfg_rec = load_lta_config(args.action_cfg_file)
+    cfg_rec.MODEL.NUM_CLASSES = [self.dim]
+    cfg_rec.MODEL.HEAD_ACT = None
+    out["recognition_model"] = SlowFast(cfg_rec, with_head=True)
+    load_recognition_backbone(out["recognition_model"], cfg_rec.CHECKPOINT_FILE_PATH)
+    freeze_backbone_params(out["recognition_model"])                       # the head stays trainable
+    self.cfg_pnr, self.cfg_oscc, self.cfg_action = cfg_pnr, cfg_oscc, cfg_rec
+    return out
+
+
+def _reference_multitask_lta_backbone(self, args):  # pragma: no cover - needs an EgoT2 checkout
+    """video_model_builder.py:285-290: the LTA encoder (no decoder), frozen."""
+    import copy
+    try:
+        from models.lta.lta_models import ForecastingEncoderDecoder                                # type: ignore
+        from utils.lta.parser import load_config_from_file as load_lta_config                      # type: ignore
+        from utils.multitask.load_model import load_lta_backbone, freeze_params                    # type: ignore
+    except Exception as e:
+        raise L.Egot2Error("the frozen LTA backbone is not part of egot2_b200: run inside an EgoT2 checkout or pass "
+                           "backbones={..., 'lta_model': ...}") from e
+    cfg_lta = load_lta_config(args.lta_cfg_file)
+    self.cfg_lta = copy.deepcopy(cfg_lta)
+    cfg_lta.FORECASTING.NUM_ACTIONS_TO_PREDICT = 20
+    m = ForecastingEncoderDecoder(cfg_lta, build_decoder=False)
+    load_lta_backbone(m, cfg_lta.CHECKPOINT_FILE_PATH_LTA)
+    freeze_params(m)
+    return m
+
+
+_PromptTranslator.__name__ = _PromptTranslator.__qualname__ = "TaskTranslationPromptTransformer"
+_PromptTranslator6Task.__name__ = _PromptTranslator6Task.__qualname__ = "TaskTranslationPromptTransformer6Task"
+multitask = SimpleNamespace(TaskTranslationPromptTransformer=_PromptTranslator,
+                            TaskTranslationPromptTransformer6Task=_PromptTranslator6Task)
 
 pnr = SimpleNamespace(TaskFusionMFTransformer3TaskDropout=_PNR3TaskDropout, TaskFusionMFTransformerDropout=_PNR2TaskDropout)
 _PNR3TaskDropout.__name__ = _PNR3TaskDropout.__qualname__ = "TaskFusionMFTransformer3TaskDropout"

@@ -43,6 +43,12 @@ class PrecomputedFeatures(nn.Module):
         return x
 
 
+def _require_cuda(device: torch.device):
+    if device.type != "cuda":
+        raise _lib.Egot2Error("egot2_b200 translators run on CUDA only (no CPU fallback); move the module and "
+                              "its inputs to a B200")
+
+
 class TranslatorBase(nn.Module):
     """Holds the spec, the engine and the parameter <-> arena binding."""
 
@@ -73,9 +79,7 @@ class TranslatorBase(nn.Module):
         return [self.get_parameter(n) for n in self._param_names]
 
     def _ensure_engine(self, device: torch.device) -> TranslatorEngine:
-        if device.type != "cuda":
-            raise _lib.Egot2Error("egot2_b200 translators run on CUDA only (no CPU fallback); move the module and "
-                                  "its inputs to a B200")
+        _require_cuda(device)
         eng = self._engine
         if eng is None or eng.device != device or eng.dtype != self.compute_dtype:
             eng = TranslatorEngine(self._spec, device, self.compute_dtype)

@@ -25,7 +25,9 @@ class Segment:
     in_dim: int                   # feature width K of this task's frozen backbone
     proj: Optional[str]           # state_dict prefix of its nn.Linear(K, hidden); None = already `hidden` wide
     tokens: Optional[int] = None  # tokens per clip if fixed by the model (HOI); None = taken from the input (HHI)
-    task_id: Optional[int] = None # row of `task_embed` added to these tokens (HHI only)
+    task_id: Optional[int] = None # row of `task_embed` added to these tokens (task_sinusoid embedding only)
+    pos_run: bool = False         # the sinusoid positions CONTINUE the previous segment's run instead of restarting at 0
+                                  # (HOI EgoT2-g: the action task = slow8 | fast8 sharing positions 0..15)
 
 
 @dataclass(frozen=True)
@@ -58,13 +60,32 @@ class TranslatorSpec:
             return None
         return sum(s.tokens for s in self.segments)
 
+    def table_runs(self, seg_tokens) -> List[Tuple[int, int]]:
+        """(tokens, task_id) of every position run of the task_sinusoid token table: one run per segment, except that a
+        segment flagged `pos_run` extends the run of the segment before it (same task row, positions carry on)."""
+        runs: List[Tuple[int, int]] = []
+        for s, d in zip(self.segments, seg_tokens):
+            if s.pos_run and runs:
+                assert runs[-1][1] == s.task_id, f"{s.name}: a continued position run keeps its task row"
+                runs[-1] = (runs[-1][0] + int(d), runs[-1][1])
+            else:
+                runs.append((int(d), s.task_id))
+        return runs
+
     # ---- parameter inventory: reference state_dict key -> shape ------------------------
     def param_shapes(self, tokens: Optional[int] = None) -> Dict[str, Tuple[int, ...]]:
         H, FF = self.hidden, self.ffn
         out: Dict[str, Tuple[int, ...]] = {}
-        if self.embed == "task_sinusoid":
-            for s in self.segments:
-                pass
+        if self.embed == "task_sinusoid" and self.family == "hoi_g":
+            # one parameter set behind both modes of the 6-task model (n_task_embed == 4 adds proj_lta)
+            out["proj_pnr.weight"], out["proj_pnr.bias"] = (H, 8192), (H,)
+            out["proj_oscc.weight"], out["proj_oscc.bias"] = (H, 8192), (H,)
+            out["proj_action_slow.weight"], out["proj_action_slow.bias"] = (H, 2048), (H,)
+            out["proj_action_fast.weight"], out["proj_action_fast.bias"] = (H, 256), (H,)
+            if self.n_task_embed == 4:
+                out["proj_lta.weight"], out["proj_lta.bias"] = (H, 2048), (H,)
+            out["task_embed"] = (1, self.n_task_embed, H)
+        elif self.embed == "task_sinusoid":
             # reference registration order: proj_lam, proj_ttm[, proj_asd], task_embed, ..., ln, linear_head
             names = [s.name for s in self.segments]
             for nm in ("lam", "ttm", "asd"):
@@ -113,7 +134,7 @@ class TranslatorSpec:
         if self.family != "hoi_pnr":
             out["ln.weight"] = (H,)
             out["ln.bias"] = (H,)
-        if self.family == "hhi_g":
+        if self.family in ("hhi_g", "hoi_g"):
             out["embedding.weight"] = (self.vocab, H)
             out["fc.weight"] = (self.vocab, H)
             out["fc.bias"] = (self.vocab,)
@@ -201,6 +222,25 @@ def hhi_g_spec(hidden=256, heads=4, layers=3, dropout=0.1, mode="ttm", ffn=2048,
                 Segment("asd", 256, "proj_asd", None, 2))
     return TranslatorSpec("hhi_g", hidden, heads, ffn, layers, segs, "task_sinusoid", "transformer_encoder.", "decoder",
                           vocab, False, dropout, 0.1, 0.0, 0.0, 3, decoder_layers=layers, vocab=vocab, g_mode=mode)
+
+
+def hoi_g_spec(hidden=256, heads=4, layers=3, dropout=0.1, vocab=600, mode="clip", n_tasks=3, num_input=2,
+               ffn=2048) -> TranslatorSpec:
+    """HOI EgoT2-g `TaskTranslationPromptTransformer` (HOI/models/multitask/video_model_builder.py:223-275) and the
+    `...6Task` sibling (:279-383).  mode "clip" (pnr / oscc / action prompts): encoder over (pnr16 id0, oscc16 id1,
+    action id2 = slow8 | fast8 with ONE position run 0..15, encode() :236-243), decoder memory = the clip's 48 tokens.
+    mode "lta" (6Task only, n_tasks = 4, :325-345): tokens (pnr, oscc, action [already `hidden` wide], lta) x num_input
+    clips with task rows 0..3.  Positional dropout 0.1 (PositionalEncoding, :56), FF 2048 (torch default), xavier init."""
+    assert mode in ("clip", "lta") and n_tasks in (3, 4) and (mode == "clip" or n_tasks == 4)
+    if mode == "clip":
+        segs = (Segment("pnr", 8192, "proj_pnr", 16, 0), Segment("oscc", 8192, "proj_oscc", 16, 1),
+                Segment("slow", 2048, "proj_action_slow", 8, 2), Segment("fast", 256, "proj_action_fast", 8, 2, True))
+    else:
+        n = num_input
+        segs = (Segment("pnr", 8192, "proj_pnr", n, 0), Segment("oscc", 8192, "proj_oscc", n, 1),
+                Segment("action", hidden, None, n, 2), Segment("lta", 2048, "proj_lta", n, 3))
+    return TranslatorSpec("hoi_g", hidden, heads, ffn, layers, segs, "task_sinusoid", "transformer_encoder.", "decoder",
+                          vocab, False, dropout, 0.1, 0.0, 0.0, n_tasks, decoder_layers=layers, vocab=vocab, g_mode=mode)
 
 
 def hoi_pnr_spec(hidden=128, layers=6, n_cls=16, feat_dropout=0.5, tr_dropout=0.1) -> TranslatorSpec:

@@ -61,7 +61,7 @@ def make_features(spec: TranslatorSpec, batch: int, seg_tokens: Optional[Sequenc
 
 def make_labels(spec: TranslatorSpec, batch: int, seg_tokens: Optional[Sequence[int]] = None, seed: int = 0):
     """Task labels: TTM (B,) in {0,1}; ASD (B*D,) in {0,1}; PNR keyframe (B,) in [0,16) or OSCC (B,) in {0,1};
-    LTA (B,Z,2) verb/noun ids."""
+    LTA (B,Z,2) verb/noun ids; EgoT2-g (rows,3) task-prompt target tokens."""
     g = _gen(seed, "labels")
     if spec.family == "hhi_ttm":
         return torch.randint(0, 2, (batch,), generator=g)
@@ -86,4 +86,9 @@ def make_labels(spec: TranslatorSpec, batch: int, seg_tokens: Optional[Sequence[
         task_tok = {"ttm": 2, "lam": 3, "asd": 4}[spec.g_mode]
         ans = torch.randint(5, 7, (rows, 2), generator=g)
         return torch.cat([torch.full((rows, 1), task_tok, dtype=torch.int64), ans], dim=1)
+    if spec.family == "hoi_g":
+        # (B, 3) = [task word, answer, answer] drawn from the whole vocabulary past the task words, e.g. ['action', verb,
+        # noun] (HOI/tasks/multitask/video_task.py:182-199: decoder input target[:, :-1], CE on target[:, 1:])
+        ans = torch.randint(5, spec.vocab, (batch, 2), generator=g)
+        return torch.cat([torch.full((batch, 1), 4, dtype=torch.int64), ans], dim=1)
     raise ValueError(spec.family)

@@ -86,6 +86,64 @@ class PromptTranslatorTrainer:
     train_stream_host = None     # bound below to TranslatorTrainer's implementation (same double-buffered host path)
 
 
+class HoiPromptTranslatorTrainer:
+    """HOI EgoT2-g training step (Unified3TaskTranslation, HOI/tasks/multitask/video_task.py:182-204): THREE forwards of
+    one model per step - a PNR batch, an OSCC batch and an action batch, each the (pnr16, oscc16, slow8, fast8) features
+    of its clips plus (B_i, 3) target tokens [task word, answer, answer] - an unweighted CE over the vocabulary at the two
+    answer positions, loss = sum_i ratio_i * loss_i, one backward into ONE gradient arena, [DP: one all-reduce], AdamW
+    (lr 1e-4, weight decay 1e-4, :265-268; defaults hidden 512 / 8 heads / 3 layers, HOI/configs/multitask/config.py:49-53).
+
+    Step inputs: feats = 3 x [pnr, oscc, slow, fast] (12 tensors), labels = the three target tensors concatenated."""
+
+    def __init__(self, hidden=512, heads=8, layers=3, dropout=0.1, vocab=600, device="cuda:0", dtype: str = "bf16",
+                 lr: float = 1e-4, weight_decay: float = 1e-4, ratios=(1.0, 1.0, 1.0), n_tasks: int = 3, process_group=None):
+        from .hhi import PositionalEncoding
+        from .specs import hoi_g_spec
+        self.device = torch.device(device)
+        self.spec = hoi_g_spec(hidden, heads, layers, dropout, vocab, "clip", n_tasks)
+        self.engine = TranslatorEngine(self.spec, self.device, dtype)
+        self.engine.set_sinusoid(PositionalEncoding(hidden, max_len=200).pe)
+        self.ratios = ratios
+        self.hp = dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay)
+        self.opt_state: Dict[str, torch.Tensor] = {}
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.use_graphs = False
+        self._h2d: Dict[int, List[torch.Tensor]] = {}
+        self.copy_stream = None if self.device.type != "cuda" else torch.cuda.Stream(device=self.device)
+        self.loss_kind, self.class_weight = L.LOSS_CE, None
+
+    def load_state_dict(self, sd):
+        self.engine.arena.load_state_dict(sd)
+
+    def train_step(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, graph_key: Optional[int] = None):
+        assert len(feats) == 12, "three batches x (pnr, oscc, slow, fast)"
+        self.step_count += 1
+        eng = self.engine
+        off, total = 0, None
+        for i, ratio in enumerate(self.ratios):
+            group = list(feats[4 * i:4 * i + 4])
+            rows = group[0].shape[0]
+            tgt = labels[off:off + rows]
+            off += rows
+            act = eng.forward(group, training=True, seed=self.step_count * 4 + i, labels=tgt[:, 1:], loss=L.LOSS_CE,
+                              persistent=True, prompt=tgt[:, :-1])
+            eng.backward(act, dloss_scale=float(ratio), zero_grad=(i == 0))    # one arena, accumulated over the three
+            l = act.t["loss"][0] * ratio
+            total = l if total is None else total + l
+        scale = 1.0
+        if self.world > 1:
+            scale = allreduce_gradients(eng.arena.grad, self.pg)
+        # AdamW = decoupled decay: p *= 1 - lr * wd, then the plain Adam update (which does not read p)
+        if self.hp["weight_decay"]:
+            eng.arena.param.mul_(1.0 - self.hp["lr"] * self.hp["weight_decay"])
+        eng.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"], 0.0, grad_scale=scale)
+        return total
+
+
 def default_loss(spec: TranslatorSpec):
     """(loss kind, class weights) the reference task uses for this translator."""
     if spec.family == "hhi_ttm":
@@ -343,3 +401,4 @@ class TranslatorTrainer:
 
 
 PromptTranslatorTrainer.train_stream_host = TranslatorTrainer.train_stream_host
+HoiPromptTranslatorTrainer.train_stream_host = TranslatorTrainer.train_stream_host

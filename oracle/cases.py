@@ -52,13 +52,19 @@ CASES = {c.name: c for c in [
     Case("hhi_g_ttm_h128_l2", specs.hhi_g_spec(128, 4, 2, 0.1, "ttm"), 3, (9, 9, 9), 11),
     Case("hhi_g_asd_h128_l2", specs.hhi_g_spec(128, 4, 2, 0.1, "asd"), 2, (6, 6, 6), 11),
     Case("hhi_g_ttm_h256_l3", specs.hhi_g_spec(256, 4, 3, 0.1, "ttm"), 2, (30, 30, 30), 12),
+    # HOI EgoT2-g (48-token memory, slow|fast share one position run, 40-word stand-in vocabulary) and the
+    # 6-task sibling: same clip encode with a 4-row task_embed, and its 'lta' encode (4 tasks x 2 input clips)
+    Case("hoi_g_h128_l2", specs.hoi_g_spec(128, 4, 2, 0.1, vocab=40), 3, (16, 16, 8, 8), 17),
+    Case("hoi_g6_clip_h128_l1", specs.hoi_g_spec(128, 8, 1, 0.1, vocab=40, n_tasks=4), 2, (16, 16, 8, 8), 18),
+    Case("hoi_g6_lta_h128_l2", specs.hoi_g_spec(128, 4, 2, 0.1, vocab=40, mode="lta", n_tasks=4), 4, (2, 2, 2, 2), 19),
 ]}
 
 
 #: cases added after the round's GPU budget was spent: CPU-side checks (state_dict keys, same-seed init, oracle pinned
 #: against the reference class, golden) are green, the GPU parity tests for them are marked xfail(strict=False) until
 #: they have run on hardware once (tests/test_zz_unvalidated_gpu.py)
-UNVALIDATED_ON_GPU = set()          # hoi_lta2_h512_l1 passed on a B200 (4 x XPASS) at the end of round 1 and moved out
+# (hoi_lta2_h512_l1 went this way: 4 x XPASS on a B200 at the end of round 1, then moved into the regular lists)
+UNVALIDATED_ON_GPU = {"hoi_g_h128_l2", "hoi_g6_clip_h128_l1", "hoi_g6_lta_h128_l2"}
 
 
 def case_inputs(case: Case):
@@ -118,6 +124,13 @@ def oracle_forward_loss(case: Case, P: Dict[str, torch.Tensor], feats, labels, e
         # HHI/tasks/multitask/video_tasktranslation.py:48-61: decoder input target[:, :-1], unweighted CE on target[:, 1:]
         out = O.hhi_g_forward(P, feats, labels[:, :-1], sp.g_mode, sp.heads)          # (rows, V, 2)
         loss = torch.nn.functional.cross_entropy(out, labels[:, 1:])
+    elif sp.family == "hoi_g":
+        # HOI/tasks/multitask/video_task.py:182-199: decoder input target[:, :-1], unweighted CE on target[:, 1:]
+        if sp.g_mode == "lta":
+            out = O.hoi_g_lta_forward(P, feats["pnr"], feats["oscc"], feats["action"], feats["lta"], labels[:, :-1], sp.heads)
+        else:
+            out = O.hoi_g_forward(P, feats["pnr"], feats["oscc"], feats["slow"], feats["fast"], labels[:, :-1], sp.heads)
+        loss = torch.nn.functional.cross_entropy(out, labels[:, 1:])                  # out (B, V, 2)
     else:
         raise ValueError(sp.family)
     return out, loss

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the REAL reference classes.
 
-Run in the build container (needs /root/reference):   python -m oracle.make_golden
+Run in the build container (needs /root/reference):   python -m oracle.make_golden [case names ...]
 For each case in `oracle/cases.py` the reference translator class (verbatim code, backbones
 stubbed — see ref_shims.py) is constructed, the seeded synthetic state_dict is loaded, and in
 eval mode (dropout off; torch MHA fast path disabled so the documented slow-path math runs)
@@ -71,7 +71,51 @@ def build_reference(case: Case, hhi, hoi):
         args = rs.hhi_args(sp.hidden, sp.heads, sp.layers, sp.p_layer, True)
         vocab = {'</s>': 0, '<unk>': 1, 'ttm': 2, 'lam': 3, 'asd': 4, '0': 5, '1': 6}      # HHI/utils/utils.py:12-18
         return hhi.multitask.TaskTranslationPromptTransformer(args, vocab)
+    if sp.family == "hoi_g":
+        from types import SimpleNamespace
+        mt = hoi.multitask
+        mt.load_lta_config = lambda f: rs.CfgNode(MODEL=rs.CfgNode(), FORECASTING=rs.CfgNode(), CHECKPOINT_FILE_PATH=None,
+                                                  CHECKPOINT_FILE_PATH_LTA=None)
+        args = SimpleNamespace(hidden_dim=sp.hidden, num_heads=sp.heads, num_layers=sp.layers, dropout=sp.p_layer,
+                               pnr_cfg_file=None, oscc_cfg_file=None, action_cfg_file=None, lta_cfg_file=None)
+        vocab = {("action" if i == 4 else f"w{i}"): i for i in range(sp.vocab)}      # only len(vocab) and the start word matter
+        cls = mt.TaskTranslationPromptTransformer6Task if sp.n_task_embed == 4 else mt.TaskTranslationPromptTransformer
+        return cls(args, vocab)
     raise ValueError(sp.family)
+
+
+class _Const(torch.nn.Module):
+    """A frozen backbone whose output is already known."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, x, *a, middle=False, **k):
+        return self.fn(x)
+
+
+def hoi_g_reference_forward(sp, m, feats, target_in):
+    """Drive the real HOI EgoT2-g forward() with stand-in backbones that return this case's features."""
+    if sp.g_mode == "lta":
+        # 6Task.encode 'lta' (:325-331): encode_clips_pnr averages each clip's (B, 16, 8192) map over time, encode_clips
+        # stacks one recognition feature per clip, lta_model returns (num_input, B, 2048)
+        m.recognition_model = _Const(lambda x: x[0])
+        m.lta_model = _Const(lambda x: feats["lta"].transpose(0, 1))
+        # video_pnr stands for the PNR clip tensor AND (deep-copied, :327) the OSCC one: give the two stubs different
+        # features by stacking them on a trailing axis the stubs pick from
+        m.pnr_model = _Const(lambda x: x[0][..., 0].unsqueeze(1))
+        m.oscc_model = _Const(lambda x: x[0][..., 1].unsqueeze(1))
+        video_pnr = torch.stack([feats["pnr"], feats["oscc"]], dim=-1)                      # (B, n, 8192, 2)
+        return m(video_pnr, [feats["action"]], target_in, "lta_verb")
+    slow5 = feats["slow"].permute(0, 2, 1)[..., None, None]
+    fast5 = feats["fast"].permute(0, 2, 1).repeat_interleave(4, dim=2)[..., None, None]     # (B,256,32,1,1)
+    m.pnr_model, m.oscc_model = _Const(lambda x: feats["pnr"]), _Const(lambda x: feats["oscc"])
+    m.recognition_model = _Const(lambda x: [slow5, fast5])
+    vid = [torch.zeros(feats["pnr"].shape[0], 1)]
+    if sp.n_task_embed == 4:
+        return m(vid, None, target_in, "action")
+    return m(vid, None, target_in)
 
 
 def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
@@ -94,6 +138,9 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         # HHI/tasks/multitask/video_tasktranslation.py:48-61 (the three forwards share one model; one case = one of them)
         out = m(*rs.hhi_inputs(feats), labels[:, :-1], sp.g_mode)                          # (rows, V, 2)
         loss = torch.nn.CrossEntropyLoss()(out, labels[:, 1:])
+    elif sp.family == "hoi_g":
+        out = hoi_g_reference_forward(sp, m, feats, labels[:, :-1])                         # (B, V, 2)
+        loss = torch.nn.CrossEntropyLoss()(out, labels[:, 1:])                              # HOI/tasks/multitask/video_task.py:177,185
     elif sp.family == "hoi_pnr" and sp.head == "pool_linear":
         m.pnr_model = rs.FeatureBackbone(); m.pnr_model.slot = "pnr"
         m.oscc_model = rs.FeatureBackbone(); m.oscc_model.slot = "oscc"
@@ -178,7 +225,8 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
     return out, loss
 
 
-def main():
+def main(only=()):
+    """only: case names to (re)generate; default = every case.  state_dict_keys.json always covers all cases."""
     warnings.filterwarnings("ignore")
     torch.backends.mha.set_fastpath_enabled(False)
     torch.set_num_threads(8)
@@ -192,12 +240,14 @@ def main():
     with open(os.path.join(GOLDEN_DIR, "state_dict_keys.json"), "w") as f:
         json.dump(ref_keys, f, indent=0, sort_keys=True)
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         sd, feats, labels, extra = case_inputs(case)
         m = build_reference(case, hhi, hoi)
         missing, unexpected = m.load_state_dict(sd, strict=False)
         # everything we do not set must be a buffer / alias / backbone, never a translator weight
         allowed = ("pos_embed.pe", "linear_head.0.", "linear_head1.0.", "linear_head2.0.", "lam_model", "ttm_model", "asd_model",
-                   "action_model", "lta_model")
+                   "action_model", "lta_model", "pnr_model", "oscc_model", "recognition_model")
         assert not unexpected, unexpected
         assert all(k.startswith(allowed) for k in missing), missing
         m.eval()
@@ -227,4 +277,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(tuple(sys.argv[1:]))

@@ -361,19 +361,10 @@ def hoi_lta2_forward(P: Params, action: Tensor, lta: Tensor, n_heads: int = 4, p
 # --------------------------------------------------------------------------------------
 # HOI EgoT2-g (oracle only so far: the CUDA path is a round-2 row)
 # --------------------------------------------------------------------------------------
-def hoi_g_encode(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: Tensor, n_heads: int, p_drop: float = 0.0,
-                 training: bool = False) -> Tensor:
-    """TaskTranslationPromptTransformer.encode (HOI/models/multitask/video_model_builder.py:228-246) -> memory (B,48,H).
-    Three TASKS: pnr (id 0), oscc (id 1) and action (id 2) = cat(proj_action_slow(slow8), proj_action_fast(fast8)); every
-    task gets ln + task_embed[id] + sinusoid restarting at 0 PER TASK (encode_prepare :144-148; the action task's 16 tokens
-    share one position run) + Dropout(0.1); concat (pnr, oscc, action) -> nn.TransformerEncoder."""
-    if slow.dim() == 5:
-        slow, fast = pool_slowfast(slow, fast)
+def _hoi_g_tokens(P: Params, tasks: Sequence[Tensor], n_heads: int, p_drop: float, training: bool) -> Tensor:
+    """encode_prepare per TASK (HOI/models/multitask/video_model_builder.py:144-148: ln + task_embed[id] + sinusoid that
+    restarts at 0 for every task + Dropout(0.1)), concat along tokens, nn.TransformerEncoder."""
     H = P["ln.weight"].shape[0]
-    tasks = [linear(pnr, P["proj_pnr.weight"], P["proj_pnr.bias"]),
-             linear(oscc, P["proj_oscc.weight"], P["proj_oscc.bias"]),
-             torch.cat([linear(slow, P["proj_action_slow.weight"], P["proj_action_slow.bias"]),
-                        linear(fast, P["proj_action_fast.weight"], P["proj_action_fast.bias"])], dim=1)]
     toks = []
     for k, f in enumerate(tasks):
         x = layer_norm(f, P["ln.weight"], P["ln.bias"]) + P["task_embed"][:, k, :]
@@ -381,6 +372,40 @@ def hoi_g_encode(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: Tenso
         toks.append(_drop(x, 0.1, training))
     x = torch.cat(toks, dim=1)
     return encoder(x, P, "transformer_encoder.", count_layers(P, "transformer_encoder."), n_heads, p_drop, training)
+
+
+def hoi_g_encode(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: Tensor, n_heads: int, p_drop: float = 0.0,
+                 training: bool = False) -> Tensor:
+    """TaskTranslationPromptTransformer.encode (HOI/models/multitask/video_model_builder.py:228-246; same lines of the
+    6-task class for the pnr / oscc / action prompts, :333-343) -> memory (B,48,H).  Three TASKS: pnr (id 0), oscc (id 1)
+    and action (id 2) = cat(proj_action_slow(slow8), proj_action_fast(fast8)): the action task's 16 tokens share one
+    position run."""
+    if slow.dim() == 5:
+        slow, fast = pool_slowfast(slow, fast)
+    tasks = [linear(pnr, P["proj_pnr.weight"], P["proj_pnr.bias"]),
+             linear(oscc, P["proj_oscc.weight"], P["proj_oscc.bias"]),
+             torch.cat([linear(slow, P["proj_action_slow.weight"], P["proj_action_slow.bias"]),
+                        linear(fast, P["proj_action_fast.weight"], P["proj_action_fast.bias"])], dim=1)]
+    return _hoi_g_tokens(P, tasks, n_heads, p_drop, training)
+
+
+def hoi_g_lta_encode(P: Params, pnr: Tensor, oscc: Tensor, action: Tensor, lta: Tensor, n_heads: int, p_drop: float = 0.0,
+                     training: bool = False) -> Tensor:
+    """TaskTranslationPromptTransformer6Task.encode for the 'lta' prompts (:325-339): per input clip one temporal-mean
+    PNR and OSCC feature (8192), one recognition feature (already H wide: the SlowFast head projects to hidden_dim) and
+    one LTA backbone feature (2048); four tasks (ids 0..3) of num_input tokens each -> memory (B, 4*num_input, H)."""
+    tasks = [linear(pnr, P["proj_pnr.weight"], P["proj_pnr.bias"]),
+             linear(oscc, P["proj_oscc.weight"], P["proj_oscc.bias"]),
+             action,
+             linear(lta, P["proj_lta.weight"], P["proj_lta.bias"])]
+    return _hoi_g_tokens(P, tasks, n_heads, p_drop, training)
+
+
+def hoi_g_lta_forward(P: Params, pnr: Tensor, oscc: Tensor, action: Tensor, lta: Tensor, target_in: Tensor, n_heads: int,
+                      p_drop: float = 0.0, training: bool = False) -> Tensor:
+    """6Task forward(video_pnr, video_ac, target, 'lta*') -> (B, V, S) logits (:347-350)."""
+    mem = hoi_g_lta_encode(P, pnr, oscc, action, lta, n_heads, p_drop, training)
+    return hoi_g_decode(P, mem, target_in, n_heads, p_drop, training).transpose(1, 2)
 
 
 def hoi_g_decode(P: Params, mem: Tensor, target_in: Tensor, n_heads: int, p_drop: float = 0.0, training: bool = False) -> Tensor:

@@ -12,6 +12,9 @@ SPECS = {
     "hhi3": specs.hhi_ttm_spec(128, 4, 1, 0.5, True),
     "hhi_asd": specs.hhi_asd_spec(128, 4, 1, 0.5),
     "hhi_g": specs.hhi_g_spec(256, 4, 3, 0.1, "ttm"),
+    "hoi_g": specs.hoi_g_spec(256, 4, 3, 0.1, 600),
+    "hoi_g6": specs.hoi_g_spec(256, 4, 3, 0.1, 600, "clip", 4),
+    "hoi_g6_lta": specs.hoi_g_spec(256, 4, 3, 0.1, 600, "lta", 4),
     "pnr": specs.hoi_pnr_spec(128, 6, 16, 0.5, 0.1),
     "pnr2": specs.hoi_pnr2_spec(16, 0.1),
     "ar": specs.hoi_ar_spec(128, 3, 8, 0.1),

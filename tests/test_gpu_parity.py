@@ -30,7 +30,7 @@ def _loss_kind(case):
         return (L.LOSS_BCE_SIGMOID if sp.n_out == 16 else L.LOSS_CE), None
     if sp.family in ("hoi_lta", "hoi_ar"):
         return L.LOSS_CE_GROUPS, None
-    if sp.family == "hhi_g":
+    if sp.family in ("hhi_g", "hoi_g"):
         return L.LOSS_CE, None
     return L.LOSS_NONE, None
 
@@ -70,7 +70,7 @@ def test_engine_matches_oracle_and_golden(name, dtype):
         eng.set_sinusoid(O.sinusoid_table(1000, sp.hidden))
     loss_kind, cw = _loss_kind(case)
     gfeats = _engine_feats(case, eng, feats, extra, dtype)
-    if sp.family == "hhi_g":      # decoder reads target[:, :-1], CE on target[:, 1:] (video_tasktranslation.py:48-61)
+    if sp.family in ("hhi_g", "hoi_g"):      # decoder reads target[:, :-1], CE on target[:, 1:] (video_tasktranslation.py:48-61)
         act = eng.forward(gfeats, training=False, labels=labels[:, 1:], loss=loss_kind, prompt=labels[:, :-1])
         out = act.t["out"].float().cpu().view(labels.shape[0], 2, -1).permute(0, 2, 1)      # (rows, V, S) like the reference
     else:

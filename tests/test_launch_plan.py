@@ -1,0 +1,151 @@
+"""Host-side launch plan of every parity case, checked WITHOUT a GPU: the C-ABI entry points are replaced by a recorder
+(nothing is computed, buffers stay uninitialised), so what runs here is exactly the Python sequencing of the product
+path - descriptor filling, buffer shapes, the order of `egot2_*` calls in forward, backward and greedy decoding - through
+the public drop-in modules.  It catches host-logic errors (wrong segment geometry, a missing buffer, a mode that is not
+wired) before a case reaches hardware; the arithmetic itself is covered by the `-m gpu` parity tests."""
+import ctypes as C
+import warnings
+
+import pytest
+import torch
+
+from egot2_b200 import _lib as L
+from egot2_b200 import engine as E
+from egot2_b200 import modules as M
+from oracle.cases import CASES, case_inputs
+
+import test_modules as tm
+
+
+@pytest.fixture
+def recorder(monkeypatch):
+    calls = []
+
+    def fake_call(name, *args):
+        calls.append((name, args))
+        return 0
+    monkeypatch.setattr(L, "call", fake_call)
+    monkeypatch.setattr(E, "_stream", lambda: 0)
+    monkeypatch.setattr(M, "_require_cuda", lambda device: None)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    return calls
+
+
+def _names(calls):
+    return [c[0] for c in calls]
+
+
+def _build(name, dtype="fp32"):
+    warnings.filterwarnings("ignore")
+    case = CASES[name]
+    sd, feats, labels, extra = case_inputs(case)
+    m = tm.build_ours(case)
+    m.load_state_dict(sd, strict=False)
+    m.set_compute_dtype(dtype).eval()
+    return case, m, feats, labels, extra
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if not CASES[n].raw_slowfast])
+def test_forward_backward_plan(name, dtype, recorder):
+    case, m, feats, labels, extra = _build(name, dtype)
+    sp = case.spec
+    out = tm.run_ours(case, m, feats, extra, torch.device("cpu"), labels)
+    fwd = _names(recorder)
+    assert fwd.count("egot2_embed_fwd") == 1
+    assert fwd.count("egot2_encoder_layer_fwd") == sp.layers
+    assert fwd.count("egot2_decoder_layer_fwd") == sp.decoder_layers
+    if sp.embed == "task_sinusoid":
+        assert fwd.index("egot2_hhi_tok_table_fwd") < fwd.index("egot2_embed_fwd")
+    if sp.head == "decoder":
+        assert fwd.index("egot2_prompt_embed_fwd") < fwd.index("egot2_decoder_layer_fwd") < fwd.index("egot2_head_loss_fwd")
+        assert tuple(out.shape) == (labels.shape[0], sp.vocab, labels.shape[1] - 1)
+    del recorder[:]
+    out.float().sum().backward()
+    bwd = _names(recorder)
+    assert bwd.count("egot2_encoder_layer_bwd") == sp.layers
+    assert bwd.count("egot2_decoder_layer_bwd") == sp.decoder_layers
+    assert bwd[-1] == "egot2_embed_bwd"
+    for k in m._param_names:
+        assert m.get_parameter(k).grad is not None, k
+
+
+def _tok_table_runs(calls):
+    (args,) = [a for n, a in calls if n == "egot2_hhi_tok_table_fwd"]
+    n = args[3]
+    return list(args[4][:n]), list(args[5][:n])
+
+
+def test_hoi_g_action_tokens_share_one_position_run(recorder):
+    """encode() :236-243: slow8 | fast8 are ONE task (row 2 of task_embed) with positions 0..15, while the projection
+    stage still sees four feature streams."""
+    case, m, feats, labels, extra = _build("hoi_g_h128_l2")
+    tm.run_ours(case, m, feats, extra, torch.device("cpu"), labels)
+    assert _tok_table_runs(recorder) == ([16, 16, 16], [0, 1, 2])
+    (eargs,) = [a for n, a in recorder if n == "egot2_embed_fwd"]
+    d = C.cast(eargs[0], C.POINTER(L.EmbedDesc)).contents
+    assert d.n_seg == 4 and list(d.seg_tokens[:4]) == [16, 16, 8, 8] and list(d.seg_offset[:4]) == [0, 16, 32, 40]
+    assert list(d.seg_in_dim[:4]) == [8192, 8192, 2048, 256] and d.T == 48
+
+
+def test_hoi_g6_lta_mode_uses_four_task_rows(recorder):
+    case, m, feats, labels, extra = _build("hoi_g6_lta_h128_l2")
+    tm.run_ours(case, m, feats, extra, torch.device("cpu"), labels)
+    assert _tok_table_runs(recorder) == ([2, 2, 2, 2], [0, 1, 2, 3])
+    (eargs,) = [a for n, a in recorder if n == "egot2_embed_fwd"]
+    d = C.cast(eargs[0], C.POINTER(L.EmbedDesc)).contents
+    assert list(d.seg_has_proj[:4]) == [1, 1, 0, 1] and d.T == 8          # the action features arrive hidden-wide
+    # both modes of the 6-task model live in ONE arena
+    assert m._mode_engines["lta2"].arena is m._engine.arena
+
+
+def test_hoi_g_greedy_decoding_encodes_once(recorder):
+    """predict_ac (:264-275): the encoder runs once, the decoder + vocabulary head once per generated token with a
+    prompt that grows by one."""
+    case, m, feats, labels, extra = _build("hoi_g_h128_l2")
+    vid, ac = [{"pnr": feats["pnr"], "oscc": feats["oscc"]}], {"slowfast": [feats["slow"], feats["fast"]]}
+    toks = m.predict_ac(vid, ac)
+    assert tuple(toks.shape) == (case.batch, 2) and toks.dtype == torch.int64
+    names = _names(recorder)
+    assert names.count("egot2_embed_fwd") == 1 and names.count("egot2_encoder_layer_fwd") == case.spec.layers
+    assert names.count("egot2_prompt_embed_fwd") == 2 and names.count("egot2_head_loss_fwd") == 2
+    assert names.count("egot2_decoder_layer_fwd") == 2 * case.spec.decoder_layers
+    S = [a[2] for n, a in recorder if n == "egot2_prompt_embed_fwd"]
+    assert S == [1, 2]
+    # predict: one-token prompt; 'action_*' returns indices, 'pnr' / 'oscc' the vocabulary logits
+    assert tuple(m.predict(vid, ac, "action_verb").shape) == (case.batch,)
+    assert tuple(m.predict(vid, ac, "pnr").shape) == (case.batch, case.spec.vocab)
+
+
+def test_hoi_g6_predict_returns_verb_noun_pairs(recorder):
+    case, m, feats, labels, extra = _build("hoi_g6_clip_h128_l1")
+    vid, ac = [{"pnr": feats["pnr"], "oscc": feats["oscc"]}], {"slowfast": [feats["slow"], feats["fast"]]}
+    assert tuple(m.predict(vid, ac, "action").shape) == (case.batch, 2)
+    assert tuple(m.predict(vid, ac, "oscc").shape) == (case.batch, case.spec.vocab)
+    assert m.predict(vid, ac, "action", predict_verb_only=True) is None
+
+
+def test_hoi_g_training_step_plan(recorder):
+    """Unified3TaskTranslation.training_step (HOI/tasks/multitask/video_task.py:182-204): three forward/backward passes
+    into one gradient arena (cleared by the first only), decoupled weight decay, one Adam launch."""
+    from egot2_b200 import synth
+    from egot2_b200.trainer import HoiPromptTranslatorTrainer
+    tr = HoiPromptTranslatorTrainer(hidden=128, heads=4, layers=2, vocab=40, device="cpu", dtype="fp32")
+    sp = tr.spec
+    tr.engine.arena.param.fill_(1.0)
+    feats, labels = [], []
+    for i, B in enumerate((2, 3, 4)):
+        f = synth.make_features(sp, B, seed=50 + i)
+        feats += [f[s.name] for s in sp.segments]
+        labels.append(synth.make_labels(sp, B, seed=50 + i))
+    tr.train_step(feats, torch.cat(labels))
+    names = _names(recorder)
+    assert names.count("egot2_embed_fwd") == 3 and names.count("egot2_embed_bwd") == 3
+    assert names.count("egot2_encoder_layer_fwd") == 3 * sp.layers == names.count("egot2_encoder_layer_bwd")
+    assert names.count("egot2_decoder_layer_fwd") == 3 * sp.decoder_layers == names.count("egot2_decoder_layer_bwd")
+    assert names.count("egot2_adam_step") == 1 and names[-1] == "egot2_adam_step"
+    rows = [a[1] for n, a in recorder if n == "egot2_prompt_embed_fwd"]
+    assert rows == [2, 3, 4]
+    assert float(tr.engine.arena.param[0]) == pytest.approx(1.0 - 1e-4 * 1e-4)          # AdamW's decoupled decay
+    (adam,) = [a for n, a in recorder if n == "egot2_adam_step"]
+    assert adam[9] == 0.0                                                               # no L2 term inside the Adam launch

@@ -36,6 +36,31 @@ class _Feats(dict):
         return (n, d, 1, 1)
 
 
+#: stand-in vocabulary of the HOI EgoT2-g cases: only its size and the start words matter (index 4 = the task word the
+#: synthetic targets start with, oracle/make_golden.py)
+HOI_G_WORDS = ["</s>", "<unk>", "pnr", "oscc", "action", "action_verb", "action_noun", "lta", "lta_verb", "lta_noun"]
+
+
+class _LtaFeatures(torch.nn.Module):
+    """ForecastingEncoderDecoder stand-in: returns (num_input, B, 2048) like the reference's middle=True path."""
+    feats = None
+
+    def forward(self, x, tgts=None, middle=False):
+        return self.feats.transpose(0, 1)
+
+
+class _PerClip(torch.nn.Module):
+    """PNR / OSCC / recognition stand-in for the per-input-clip loops (encode_clips / encode_clips_pnr): the "video" is
+    the feature tensor itself; pick >= 0 selects PNR (0) or OSCC (1) features stacked on a trailing axis and adds the
+    time axis encode_clips_pnr averages over."""
+    def __init__(self, pick=-1):
+        super().__init__()
+        self.pick = pick
+
+    def forward(self, x, middle=False):
+        return x[0][..., self.pick].unsqueeze(1) if self.pick >= 0 else x[0]
+
+
 def build_ours(case, backbones=True):
     sp = case.spec
     if sp.family in ("hhi_ttm", "hhi_asd"):
@@ -54,6 +79,16 @@ def build_ours(case, backbones=True):
         vocab = {'</s>': 0, '<unk>': 1, 'ttm': 2, 'lam': 3, 'asd': 4, '0': 5, '1': 6}
         bb = {"lam_model": PrecomputedFeatures("lam"), "ttm_model": PrecomputedFeatures("ttm"), "asd_model": _TalkNetFeatures()}
         return hhi.TaskTranslationPromptTransformer(args, vocab, backbones=bb)
+    if sp.family == "hoi_g":
+        args = SimpleNamespace(hidden_dim=sp.hidden, num_heads=sp.heads, num_layers=sp.layers, dropout=sp.p_layer)
+        vocab = {w: i for i, w in enumerate(HOI_G_WORDS)}
+        vocab.update({f"w{i}": i for i in range(len(HOI_G_WORDS), sp.vocab)})
+        bb = {"pnr_model": PrecomputedFeatures("pnr"), "oscc_model": PrecomputedFeatures("oscc"),
+              "recognition_model": PrecomputedFeatures("slowfast")}
+        if sp.n_task_embed == 4:
+            bb["lta_model"] = _LtaFeatures()
+            return hoi.multitask.TaskTranslationPromptTransformer6Task(args, vocab, backbones=bb)
+        return hoi.multitask.TaskTranslationPromptTransformer(args, vocab, backbones=bb)
     if sp.family == "hoi_pnr" and sp.head == "pool_linear":      # the 2-task sibling
         cfg = CfgNode(DATA=CfgNode(TASK="keyframe_localization" if sp.n_out == 16 else "state_change"),
                       MODEL=CfgNode(FEAT_DROPOUT_RATE=0.5, FEAT_DROPOUT_MODE=0, TRANSFORMER_DROPOUT_RATE=sp.p_layer))
@@ -100,6 +135,16 @@ def run_ours(case, m, feats, extra, dev, labels=None):
     if sp.family == "hhi_g":
         v = _Feats(f)
         return m(v, v, None, None, labels[:, :-1].to(dev), sp.g_mode)
+    if sp.family == "hoi_g" and sp.g_mode == "lta":
+        # encode_clips_pnr slices video_pnr[:, i] and averages over time; encode_clips slices every pathway[:, i]
+        m.pnr_model, m.oscc_model, m.recognition_model = _PerClip(0), _PerClip(1), _PerClip()
+        m.lta_model.feats = f["lta"]
+        return m(torch.stack([f["pnr"], f["oscc"]], dim=-1), [f["action"]], labels[:, :-1].to(dev), "lta_verb")
+    if sp.family == "hoi_g":
+        vid, ac = [{"pnr": f["pnr"], "oscc": f["oscc"]}], {"slowfast": [f["slow"], f["fast"]]}
+        if sp.n_task_embed == 4:
+            return m(vid, ac, labels[:, :-1].to(dev), "action")
+        return m(vid, ac, labels[:, :-1].to(dev))
     if sp.family == "hhi_ttm" and len(sp.segments) == 2:
         return m(_Feats(f), None)
     if sp.family in ("hhi_ttm", "hhi_asd"):
@@ -148,7 +193,8 @@ def test_container_forward_is_poisoned():
 
 @pytest.mark.requires_reference
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_l1", "hhi_asd_h128_l1", "hoi_pnr_h128_l6", "hoi_lta_h512_l4",
-                                  "hhi_g_ttm_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2", "hoi_lta2_h512_l1"])
+                                  "hhi_g_ttm_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2", "hoi_lta2_h512_l1",
+                                  "hoi_g_h128_l2", "hoi_g6_lta_h128_l2"])
 def test_same_seed_same_init_as_reference(name):
     """ctor parity: under the same torch seed our module draws exactly the reference's initial weights."""
     from oracle import ref_shims as rs
@@ -205,7 +251,7 @@ def test_module_forward_backward_vs_oracle(name, dtype):
         assert float((score.cpu() - o_score).abs().max()) < (1e-4 if dtype == "fp32" else 2e-2)
     elif sp.family == "hoi_pnr":
         loss = torch.nn.BCELoss()(torch.sigmoid(out), torch.nn.functional.one_hot(lab, 16).float())
-    elif sp.family == "hhi_g":      # HHI/tasks/multitask/video_tasktranslation.py:36,48-61
+    elif sp.family in ("hhi_g", "hoi_g"):      # HHI/tasks/multitask/video_tasktranslation.py:36,48-61; HOI/tasks/multitask/video_task.py:177,185
         loss = torch.nn.CrossEntropyLoss()(out, lab[:, 1:])
     elif sp.family == "hoi_ar":
         loss = O.ar_loss(out, lab, sp.head_groups)

@@ -21,3 +21,40 @@ def test_engine_parity_unvalidated(name, dtype):
 def test_module_parity_unvalidated(name, dtype):
     import test_modules as tm
     tm.test_module_forward_backward_vs_oracle(name, dtype)
+
+
+def test_hoi_g_greedy_predict_ac_matches_reference_golden():
+    """HOI EgoT2-g greedy decoding (predict_ac, HOI/models/multitask/video_model_builder.py:264-275) through the drop-in
+    module: the generated [verb, noun] vocabulary indices equal the real reference class's (tests/golden/next_hoi_g.npz),
+    and decoding over the kept encoder memory equals a full forward with the same prompt."""
+    import warnings
+    from types import SimpleNamespace
+
+    import numpy as np
+    import torch
+
+    from egot2_b200 import hoi
+    from egot2_b200.modules import PrecomputedFeatures
+    from oracle import next_rows as NR
+    warnings.filterwarnings("ignore")
+    dev = torch.device("cuda:0")
+    sd, feats, target = NR.inputs()
+    gold = np.load(NR.GOLDEN)
+    args = SimpleNamespace(hidden_dim=NR.H, num_heads=NR.HEADS, num_layers=NR.LAYERS, dropout=0.1)
+    vocab = {("action" if i == 4 else f"w{i}"): i for i in range(NR.VOCAB)}
+    bb = {"pnr_model": PrecomputedFeatures("pnr"), "oscc_model": PrecomputedFeatures("oscc"),
+          "recognition_model": PrecomputedFeatures("slowfast")}
+    m = hoi.multitask.TaskTranslationPromptTransformer(args, vocab, backbones=bb)
+    m.load_state_dict(sd, strict=False)
+    m.to(dev).set_compute_dtype("fp32").eval()
+    f = {k: v.to(dev) for k, v in feats.items()}
+    vid, ac = [{"pnr": f["pnr"], "oscc": f["oscc"]}], {"slowfast": [f["slow"], f["fast"]]}
+    out = m(vid, ac, target[:, :-1].to(dev)).float().cpu()
+    ref = torch.from_numpy(gold["output"])
+    assert float((out - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+    toks = m.predict_ac(vid, ac).cpu()
+    assert torch.equal(toks, torch.from_numpy(gold["predict_ac"]))
+    # the decoder-only second step == a full forward on the two-token prompt
+    start = torch.full((NR.B, 1), 4, dtype=torch.int64)
+    full = m(vid, ac, torch.cat([start, toks[:, :1]], dim=1).to(dev))          # (B, V, 2)
+    assert torch.equal(full[:, :, -1].argmax(dim=1).cpu(), toks[:, 1])
