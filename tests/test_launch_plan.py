@@ -149,3 +149,14 @@ def test_hoi_g_training_step_plan(recorder):
     assert float(tr.engine.arena.param[0]) == pytest.approx(1.0 - 1e-4 * 1e-4)          # AdamW's decoupled decay
     (adam,) = [a for n, a in recorder if n == "egot2_adam_step"]
     assert adam[9] == 0.0                                                               # no L2 term inside the Adam launch
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n].spec.embed == "task_sinusoid"])
+def test_table_runs_default_to_one_run_per_segment(name):
+    case = CASES[name]
+    sp = case.spec
+    runs = sp.table_runs(case.seg_tokens)
+    if any(s.pos_run for s in sp.segments):
+        assert sum(r[0] for r in runs) == sum(case.seg_tokens) and len(runs) < len(sp.segments)
+    else:
+        assert runs == [(d, s.task_id) for s, d in zip(sp.segments, case.seg_tokens)]

@@ -81,3 +81,49 @@ def test_two_rank_gradient_allreduce_matches_single_process():
     assert torch.allclose(ddp, sum(parts) / world, rtol=1e-5, atol=1e-7)           # reference DDP: mean of rank gradients
     assert torch.allclose(exact, flat_all, rtol=2e-4, atol=1e-6)                   # weighted: the full-batch gradient
     assert torch.equal(full_out, out_all) or torch.allclose(full_out, out_all, rtol=1e-6, atol=1e-7)
+
+
+def _overlap_worker(rank, world, port, q):
+    """The trainer's overlapped schedule (trainer._dp_overlap_step) on the real arena layout: the tail
+    [embed_numel:] (head + encoder-layer gradients, complete after the first backward stage) is all-reduced
+    asynchronously while the embedding stage still writes the prefix [0, embed_numel), which is reduced afterwards."""
+    from egot2_b200 import specs
+    from egot2_b200.engine import ParamArena
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        arena = ParamArena(specs.hhi_ttm_spec(128, 4, 1, 0.5, True), torch.device("cpu"))
+        g = torch.Generator().manual_seed(100 + rank)
+        full = torch.randn(arena.numel, generator=g)
+        nb = arena.embed_numel
+        arena.grad[nb:] = full[nb:]                       # stage 1 done: everything behind the embedding stage
+        work = dist.all_reduce(arena.grad[nb:], async_op=True)
+        arena.grad[:nb] = full[:nb]                       # stage 2 (embedding backward) lands while the tail is in flight
+        dist.all_reduce(arena.grad[:nb])
+        work.wait()
+        whole = full.clone()
+        dist.all_reduce(whole)                            # the single-bucket schedule
+        if rank == 0:
+            q.put((arena.grad.clone(), whole, nb, arena.numel))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_piece_overlapped_allreduce_equals_single_bucket():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    two_piece, whole, nb, numel = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert 0 < nb < numel
+    assert torch.equal(two_piece, whole)                  # the two slices tile the arena exactly; same sums
+    expect = sum(torch.randn(numel, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
+    assert torch.allclose(whole, expect, rtol=0, atol=1e-6)
