@@ -102,6 +102,26 @@ class HeadGrads(C.Structure):
     _fields_ = [(n, vp) for n in ["ln_g", "ln_b", "w", "b"]]
 
 
+class VitDesc(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("T", i32), ("D", i32), ("heads", i32), ("dim_head", i32), ("mlp", i32),
+                ("layer_index", i32), ("ln_eps", f32)]
+
+
+_VIT_PARAM_FIELDS = ["qkv_w", "out_w", "ff1_w", "ff2_w", "norm_a_g", "norm_a_b", "norm_f_g", "norm_f_b", "ff1_b", "ff2_b"]
+
+
+class VitParams(C.Structure):
+    _fields_ = [(n, vp) for n in _VIT_PARAM_FIELDS]
+
+
+class VitGrads(C.Structure):
+    _fields_ = [(n, vp) for n in _VIT_PARAM_FIELDS]
+
+
+class VitSaved(C.Structure):
+    _fields_ = [(n, vp) for n in ["h", "stat_a", "qkv", "attn", "lse", "x1", "h2", "stat_f", "u", "act"]]
+
+
 P = C.POINTER
 
 # name -> (restype, argtypes); every symbol declared in include/egot2.h must be listed here
@@ -132,6 +152,9 @@ SIGNATURES = {
     "egot2_decoder_layer_fwd": (C.c_int, [P(DecoderDesc), P(DecoderParams), vp, vp, vp, P(DecoderSaved), vp]),
     "egot2_decoder_layer_bwd": (C.c_int, [P(DecoderDesc), P(DecoderParams), vp, vp, P(DecoderSaved), vp, vp, vp,
                                           P(DecoderGrads), vp, sz, vp]),
+    "egot2_vit_layer_workspace_bytes": (sz, [P(VitDesc)]),
+    "egot2_vit_layer_fwd": (C.c_int, [P(VitDesc), P(VitParams), vp, vp, P(VitSaved), vp]),
+    "egot2_vit_layer_bwd": (C.c_int, [P(VitDesc), P(VitParams), vp, P(VitSaved), vp, vp, P(VitGrads), vp, sz, vp]),
     "egot2_prompt_embed_fwd": (C.c_int, [i32, i32, i32, i32, vp, vp, vp, f32, i32, u64, vp, vp]),
     "egot2_prompt_embed_bwd": (C.c_int, [i32, i32, i32, i32, vp, vp, f32, i32, u64, vp, vp]),
     "egot2_head_rows": (C.c_int, [P(HeadDesc)]),

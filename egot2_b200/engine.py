@@ -283,7 +283,12 @@ class TranslatorEngine:
         L.call("egot2_embed_fwd", C.byref(d), C.byref(ein), C.byref(eout), ws.data_ptr(), ws.numel(), st)
 
         # ---- encoder layers
-        if fresh or not act.layer_desc:
+        if sp.encoder == "simple_vit":
+            x = self._vit_forward(act, x, buf)
+            n_torch_layers = 0
+        else:
+            n_torch_layers = sp.layers
+        if n_torch_layers and (fresh or not act.layer_desc):
             act.layer_desc, act.layer_params, act.layer_saved = [], [], []
             for i in range(sp.layers):
                 ld = L.LayerDesc()
@@ -292,7 +297,7 @@ class TranslatorEngine:
                 act.layer_desc.append(ld)
                 act.layer_params.append(L.LayerParams())
                 act.layer_saved.append(L.LayerSaved())
-        for i in range(sp.layers):
+        for i in range(n_torch_layers):
             ld, lp, ls = act.layer_desc[i], act.layer_params[i], act.layer_saved[i]
             ld.training, ld.p_drop, ld.seed = int(training), sp.p_layer, int(seed)
             self._fill_layer_params(lp, i)
@@ -382,6 +387,58 @@ class TranslatorEngine:
         L.call("egot2_head_loss_fwd", C.byref(hd), C.byref(hin), C.byref(hout), st)
         t["out"] = logits
         return act
+
+    # ------------------------------------------------------------------ simple_vit encoder (HOI PNR "simple_vit" sibling)
+    _VIT_NAMES = {"qkv_w": "0.to_qkv.weight", "out_w": "0.to_out.weight", "ff1_w": "1.net.1.weight", "ff2_w": "1.net.3.weight",
+                  "norm_a_g": "0.norm.weight", "norm_a_b": "0.norm.bias", "norm_f_g": "1.net.0.weight",
+                  "norm_f_b": "1.net.0.bias", "ff1_b": "1.net.1.bias", "ff2_b": "1.net.3.bias"}
+
+    def _fill_vit_params(self, vp, i: int, grads_base: Optional[torch.Tensor] = None):
+        pre = f"{self.spec.encoder_prefix}layers.{i}."
+        for f, n in self._VIT_NAMES.items():
+            if grads_base is not None:
+                setattr(vp, f, self.arena.view(pre + n, grads_base).data_ptr())
+            elif f.endswith("_w"):
+                setattr(vp, f, self._mat(pre + n).data_ptr())
+            else:
+                setattr(vp, f, self._vec(pre + n).data_ptr())
+
+    def _vit_forward(self, act: Activations, x: torch.Tensor, buf) -> torch.Tensor:
+        """depth x egot2_vit_layer_fwd (HOI/models/pnr/simple_vit.py:93-107); x: (B, T, D) tokens after ln + pe."""
+        sp = self.spec
+        B, T, D, tdt, st = act.B, act.T, sp.hidden, self.tdt, _stream()
+        M, inner = B * T, sp.heads * sp.dim_head
+        if not act.layer_desc:
+            for i in range(sp.layers):
+                vd = L.VitDesc()
+                vd.dtype, vd.B, vd.T, vd.D, vd.heads, vd.dim_head, vd.mlp = self.dt, B, T, D, sp.heads, sp.dim_head, sp.ffn
+                vd.layer_index, vd.ln_eps = i, 1e-5
+                act.layer_desc.append(vd)
+                act.layer_params.append(L.VitParams())
+                act.layer_saved.append(L.VitSaved())
+        for i in range(sp.layers):
+            vd, vp, vs = act.layer_desc[i], act.layer_params[i], act.layer_saved[i]
+            self._fill_vit_params(vp, i)
+            for name, shape, dty in (("h", (M, D), tdt), ("stat_a", (M, 2), torch.float32), ("qkv", (M, 3 * inner), tdt),
+                                     ("attn", (M, inner), tdt), ("lse", (B, sp.heads, T), torch.float32), ("x1", (M, D), tdt),
+                                     ("h2", (M, D), tdt), ("stat_f", (M, 2), torch.float32), ("u", (M, sp.ffn), tdt),
+                                     ("act", (M, sp.ffn), tdt)):
+                setattr(vs, name, buf(f"vit{i}_{name}", shape, dty).data_ptr())
+            x_out = buf(f"x{i + 1}", (B, T, D), tdt)
+            L.call("egot2_vit_layer_fwd", C.byref(vd), C.byref(vp), x.data_ptr(), x_out.data_ptr(), C.byref(vs), st)
+            x = x_out
+        return x
+
+    def _vit_backward(self, act: Activations, dx: torch.Tensor, grad: torch.Tensor):
+        sp, t, st = self.spec, act.t, _stream()
+        for i in reversed(range(sp.layers)):
+            vd = act.layer_desc[i]
+            vg = L.VitGrads()
+            self._fill_vit_params(vg, i, grads_base=grad)
+            x_in = t["x0"] if i == 0 else t[f"x{i}"]
+            ws = self._workspace(L.load().egot2_vit_layer_workspace_bytes(C.byref(vd)))
+            L.call("egot2_vit_layer_bwd", C.byref(vd), C.byref(act.layer_params[i]), x_in.data_ptr(),
+                   C.byref(act.layer_saved[i]), dx.data_ptr(), dx.data_ptr(), C.byref(vg), ws.data_ptr(), ws.numel(), st)
 
     # ------------------------------------------------------------------ EgoT2-g decoder
     _DEC_NAMES = {"sa_in_w": "self_attn.in_proj_weight", "sa_out_w": "self_attn.out_proj.weight",
@@ -609,7 +666,9 @@ class TranslatorEngine:
                    float(dloss_scale), dx.data_ptr(), C.byref(hg), ws.data_ptr(), ws.numel(), st)
 
         # ---- encoder layers (reverse)
-        for i in reversed(range(sp.layers)):
+        if sp.encoder == "simple_vit":
+            self._vit_backward(act, dx, grad)
+        for i in reversed(range(sp.layers if sp.encoder == "torch" else 0)):
             ld = act.layer_desc[i]
             lg = L.LayerGrads()
             self._fill_layer_params(lg, i, grads_base=grad)

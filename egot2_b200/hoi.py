@@ -4,6 +4,7 @@ Reference (relative to /root/reference):
   pnr.TaskFusionMFTransformer3TaskDropout   HOI/models/pnr/video_model_transfer_3task.py:212-258
   lta.TaskFusionMFTransformerLTA4Task       HOI/models/lta/lta_models_lta_transfer.py:257-377
   pnr.TaskFusionMFTransformerDropout        HOI/models/pnr/video_model_transfer.py:70-105   (2-task sibling)
+  pnr.TaskFusionMFTransformer3Task          HOI/models/pnr/video_model_transfer_3task.py:128-164 (simple_vit sibling)
   lta.TaskFusionMFTransformer3Task          HOI/models/lta/lta_models_transfer.py:96-137    (action-recognition sibling)
   lta.TaskFusionMFTransformer2TaskAR        HOI/models/lta/lta_models_transfer.py:169-235   (AR from recognition + LTA features)
   lta.TaskFusionMFTransformer2Task          HOI/models/lta/lta_models_lta_transfer.py:429-526 (LTA 2-task sibling, H <= 1024)
@@ -28,7 +29,8 @@ from . import _lib as L
 from .engine import TranslatorEngine, _stream
 from .functional import translator_apply
 from .modules import PrecomputedFeatures, TranslatorBase
-from .specs import hoi_ar2_spec, hoi_ar_spec, hoi_g_spec, hoi_lta2_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec
+from .specs import (hoi_ar2_spec, hoi_ar_spec, hoi_g_spec, hoi_lta2_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec,
+                    hoi_pnr_vit_spec)
 
 
 def slowfast_pool(x5: torch.Tensor, t_out: int, out_dtype: torch.dtype) -> torch.Tensor:
@@ -94,6 +96,63 @@ class _PNR3TaskDropout(TranslatorBase):
         fast = slowfast_pool(fast5, 8, dt) if fast5.dim() == 5 else fast5
         out = self._translate([pnr_feat, oscc_feat, slow, fast])         # token order (pnr, oscc, slow, fast)
         return out.unsqueeze(self.unsqueeze_dim)
+
+
+class _VitAttention(nn.Module):
+    """Parameter container with simple_vit Attention's keys (`norm`, bias-free `to_qkv` / `to_out`; simple_vit.py:67-78)."""
+
+    def __init__(self, dim, heads, dim_head):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.to_qkv = nn.Linear(dim, heads * dim_head * 3, bias=False)
+        self.to_out = nn.Linear(heads * dim_head, dim, bias=False)
+
+
+class _VitFeedForward(nn.Module):
+    """Parameter container with simple_vit FeedForward's keys (`net.0` LayerNorm, `net.1` / `net.3` Linear; :55-63)."""
+
+    def __init__(self, dim, hidden_dim):
+        super().__init__()
+        self.net = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, hidden_dim), nn.GELU(), nn.Linear(hidden_dim, dim))
+
+
+class _VitTransformer(nn.Module):
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim):
+        super().__init__()
+        self.layers = nn.ModuleList([nn.ModuleList([_VitAttention(dim, heads, dim_head), _VitFeedForward(dim, mlp_dim)])
+                                     for _ in range(depth)])
+
+
+class _PNR3TaskVit(TranslatorBase):
+    """simple_vit sibling (HOI/models/pnr/video_model_transfer_3task.py:128-164): the 48 tokens of the Dropout variant
+    through a pre-norm / GELU simple_vit Transformer(dim 256, depth 3, heads 8, dim_head 128, mlp_dim 512); the head shares
+    `ln` with the token LayerNorm; no dropout."""
+
+    def __init__(self, cfg, backbones: Optional[Dict[str, nn.Module]] = None):
+        super().__init__()
+        self.cfg_pnr = None
+        self.cfg_recognition = None
+        if backbones is None:
+            backbones = _reference_pnr_backbones(self, cfg)
+        for k, m in backbones.items():
+            setattr(self, k, m)
+        self.num_classes = 16 if "keyframe_localization" in cfg.DATA.TASK else 2
+        self.unsqueeze_dim = 1 if "keyframe_localization" in cfg.DATA.TASK else 2
+        self.sequence_len = 48
+        self.feature_dim = 256
+        self.proj1 = nn.Linear(8192, self.feature_dim)
+        self.proj2 = nn.Linear(8192, self.feature_dim)
+        self.proj3_slow = nn.Linear(2048, self.feature_dim)
+        self.proj3_fast = nn.Linear(256, self.feature_dim)
+        self.pe = nn.Parameter(torch.randn(1, self.sequence_len, self.feature_dim), requires_grad=True)
+        self.transformer = _VitTransformer(dim=self.feature_dim, depth=3, heads=8, dim_head=128, mlp_dim=512)
+        self.ln = nn.LayerNorm(self.feature_dim)
+        self.linear_head = nn.Sequential(self.ln, nn.Linear(self.feature_dim, self.num_classes))   # shared ln
+        self._poison_containers(self.proj1, self.proj2, self.proj3_slow, self.proj3_fast, self.transformer,
+                                self.linear_head)
+        self._init_translator(hoi_pnr_vit_spec(self.num_classes))
+
+    forward = _PNR3TaskDropout.forward
 
 
 class _PNR2TaskDropout(TranslatorBase):
@@ -758,11 +817,14 @@ _PromptTranslator6Task.__name__ = _PromptTranslator6Task.__qualname__ = "TaskTra
 multitask = SimpleNamespace(TaskTranslationPromptTransformer=_PromptTranslator,
                             TaskTranslationPromptTransformer6Task=_PromptTranslator6Task)
 
-pnr = SimpleNamespace(TaskFusionMFTransformer3TaskDropout=_PNR3TaskDropout, TaskFusionMFTransformerDropout=_PNR2TaskDropout)
+pnr = SimpleNamespace(TaskFusionMFTransformer3TaskDropout=_PNR3TaskDropout, TaskFusionMFTransformerDropout=_PNR2TaskDropout,
+                      TaskFusionMFTransformer3Task=_PNR3TaskVit)
 _PNR3TaskDropout.__name__ = _PNR3TaskDropout.__qualname__ = "TaskFusionMFTransformer3TaskDropout"
 _PNR2TaskDropout.__name__ = _PNR2TaskDropout.__qualname__ = "TaskFusionMFTransformerDropout"
+_PNR3TaskVit.__name__ = _PNR3TaskVit.__qualname__ = "TaskFusionMFTransformer3Task"
 pnr.MODEL_REGISTRY = {"TaskFusionMFTransformer3TaskDropout": _PNR3TaskDropout,
-                      "TaskFusionMFTransformerDropout": _PNR2TaskDropout}
+                      "TaskFusionMFTransformerDropout": _PNR2TaskDropout,
+                      "TaskFusionMFTransformer3Task": _PNR3TaskVit}
 pnr.build_model = lambda cfg, **kw: pnr.MODEL_REGISTRY[cfg.MODEL.MODEL_NAME](cfg, **kw)
 
 lta = SimpleNamespace(TaskFusionMFTransformerLTA4Task=_LTA4Task, TaskFusionMFTransformer3Task=_AR3Task,

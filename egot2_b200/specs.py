@@ -53,6 +53,9 @@ class TranslatorSpec:
     decoder_layers: int = 0             # EgoT2-g: nn.TransformerDecoder depth (head == "decoder")
     vocab: int = 0                      # EgoT2-g: task-prompt vocabulary size (7)
     g_mode: str = ""                    # EgoT2-g: "lam" | "ttm" | "asd" (which forward of the shared model this spec runs)
+    encoder: str = "torch"              # "torch": nn.TransformerEncoderLayer (post-norm, ReLU) | "simple_vit": pre-norm, GELU,
+                                        # bias-free attention with `dim_head` independent of `hidden` (HOI/models/pnr/simple_vit.py)
+    dim_head: int = 0                   # simple_vit only: inner = heads * dim_head
 
     @property
     def fixed_tokens(self) -> Optional[int]:
@@ -103,7 +106,16 @@ class TranslatorSpec:
         if self.family == "hoi_pnr":
             out["ln.weight"] = (H,)
             out["ln.bias"] = (H,)
-        for i in range(self.layers):
+        for i in range(self.layers if self.encoder == "simple_vit" else 0):
+            a, f = f"{self.encoder_prefix}layers.{i}.0.", f"{self.encoder_prefix}layers.{i}.1.net."
+            inner = self.heads * self.dim_head
+            out[a + "norm.weight"], out[a + "norm.bias"] = (H,), (H,)
+            out[a + "to_qkv.weight"] = (3 * inner, H)
+            out[a + "to_out.weight"] = (H, inner)
+            out[f + "0.weight"], out[f + "0.bias"] = (H,), (H,)
+            out[f + "1.weight"], out[f + "1.bias"] = (FF, H), (FF,)
+            out[f + "3.weight"], out[f + "3.bias"] = (H, FF), (H,)
+        for i in range(self.layers if self.encoder == "torch" else 0):
             p = f"{self.encoder_prefix}layers.{i}."
             out[p + "self_attn.in_proj_weight"] = (3 * H, H)
             out[p + "self_attn.in_proj_bias"] = (3 * H,)
@@ -249,6 +261,17 @@ def hoi_pnr_spec(hidden=128, layers=6, n_cls=16, feat_dropout=0.5, tr_dropout=0.
             Segment("slow", 2048, "proj3_slow", 8), Segment("fast", 256, "proj3_fast", 8))
     return TranslatorSpec("hoi_pnr", hidden, 8, 2 * hidden, layers, segs, "learned_pe", "transformer.",
                           "pool_ln_linear", n_cls, True, tr_dropout, 0.0, feat_dropout, 0.0)
+
+
+def hoi_pnr_vit_spec(n_cls=16) -> TranslatorSpec:
+    """simple_vit sibling of the PNR/OSCC translator, `TaskFusionMFTransformer3Task` of the pnr registry
+    (HOI/models/pnr/video_model_transfer_3task.py:128-164): the same 48 tokens and the same shared-ln head as the Dropout
+    variant, H = 256 fixed, encoder = simple_vit Transformer(dim 256, depth 3, heads 8, dim_head 128, mlp_dim 512); no
+    dropout anywhere."""
+    segs = (Segment("pnr", 8192, "proj1", 16), Segment("oscc", 8192, "proj2", 16),
+            Segment("slow", 2048, "proj3_slow", 8), Segment("fast", 256, "proj3_fast", 8))
+    return TranslatorSpec("hoi_pnr", 256, 8, 512, 3, segs, "learned_pe", "transformer.", "pool_ln_linear", n_cls, True,
+                          0.0, 0.0, 0.0, 0.0, encoder="simple_vit", dim_head=128)
 
 
 def hoi_pnr2_spec(n_cls=16, tr_dropout=0.1) -> TranslatorSpec:

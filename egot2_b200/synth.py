@@ -34,9 +34,9 @@ def make_state_dict(spec: TranslatorSpec, seed: int = 0) -> Dict[str, torch.Tens
         g = _gen(seed, name)
         if name in ("task_embed", "pe", "embedding.weight"):
             t = torch.randn(shape, generator=g)
-        elif name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("norm3.weight") or name in ("ln.weight", "linear_head.0.weight"):
+        elif name.endswith(("norm1.weight", "norm2.weight", "norm3.weight", ".0.norm.weight", ".1.net.0.weight")) or name in ("ln.weight", "linear_head.0.weight"):
             t = 1.0 + 0.1 * torch.randn(shape, generator=g)
-        elif name.endswith("norm1.bias") or name.endswith("norm2.bias") or name.endswith("norm3.bias") or name in ("ln.bias", "linear_head.0.bias"):
+        elif name.endswith(("norm1.bias", "norm2.bias", "norm3.bias", ".0.norm.bias", ".1.net.0.bias")) or name in ("ln.bias", "linear_head.0.bias"):
             t = 0.1 * torch.randn(shape, generator=g)
         elif len(shape) >= 2:
             bound = 1.0 / math.sqrt(shape[-1])

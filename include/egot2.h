@@ -28,6 +28,8 @@
  *                                HOI/tasks/lta/long_term_anticipation_taskspecfic.py:177-183 (sum of 40 CE)
  *   egot2_slowfast_pool_fwd      AdaptiveAvgPool3d of the raw SlowFast maps
  *                                HOI/models/pnr/video_model_transfer_3task.py:226-227,245-247
+ *   egot2_vit_layer_fwd/bwd      one simple_vit Transformer layer (pre-norm, GELU, bias-free attention)
+ *                                HOI/models/pnr/simple_vit.py:55-107, HOI/models/pnr/video_model_transfer_3task.py:128-164
  *   egot2_adam_step              torch.optim.Adam over the flat translator parameter arena
  *                                HHI/tasks/ttm/video_task.py:64-66
  *
@@ -200,6 +202,51 @@ int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_layer_params*
 int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_layer_params* p, const void* x_in,
                             const egot2_layer_saved* s, void* dx_out, void* dx_in,
                             const egot2_layer_grads* g, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ simple_vit layer (HOI PNR "simple_vit" siblings)
+ * One layer of the simple_vit Transformer (HOI/models/pnr/simple_vit.py:55-107; used by
+ * HOI/models/pnr/video_model_transfer_3task.py:128-164 with dim 256, depth 3, heads 8, dim_head 128, mlp_dim 512):
+ *     x1 = to_out(softmax(q k^T * dim_head^-0.5) v) + x,  [q|k|v] = to_qkv(LayerNorm(x))     (pre-norm, bias-free)
+ *     x2 = W2 gelu(W1 LayerNorm(x1) + b1) + b2 + x1                                         (exact erf GELU)
+ * no dropout; dim_head is independent of the model width D (inner = heads * dim_head). */
+typedef struct {
+  int32_t dtype;
+  int32_t B, T, D;                    /* clips, tokens per clip, model width */
+  int32_t heads, dim_head;
+  int32_t mlp;                        /* hidden width of the FeedForward */
+  int32_t layer_index;
+  float ln_eps;
+} egot2_vit_desc;
+
+typedef struct {
+  const void *qkv_w, *out_w;          /* layers.i.0.to_qkv.weight (3*inner, D), layers.i.0.to_out.weight (D, inner); dtype */
+  const void *ff1_w, *ff2_w;          /* layers.i.1.net.1.weight (mlp, D), layers.i.1.net.3.weight (D, mlp); dtype */
+  const float *norm_a_g, *norm_a_b;   /* layers.i.0.norm */
+  const float *norm_f_g, *norm_f_b;   /* layers.i.1.net.0 */
+  const float *ff1_b, *ff2_b;
+} egot2_vit_params;
+
+typedef struct {                      /* fp32, accumulated (+=) */
+  float *qkv_w, *out_w, *ff1_w, *ff2_w;
+  float *norm_a_g, *norm_a_b, *norm_f_g, *norm_f_b, *ff1_b, *ff2_b;
+} egot2_vit_grads;
+
+typedef struct {                      /* activations kept for backward; caller-allocated; M = B*T, inner = heads*dim_head */
+  void* h; float* stat_a;             /* (M, D) LayerNorm_a output, (M, 2) */
+  void* qkv;                          /* (M, 3*inner) */
+  void* attn; float* lse;             /* (M, inner), (B, heads, T) */
+  void* x1;                           /* (M, D) */
+  void* h2; float* stat_f;            /* (M, D), (M, 2) */
+  void* u; void* act;                 /* (M, mlp) pre-activation and gelu(u) */
+} egot2_vit_saved;
+
+size_t egot2_vit_layer_workspace_bytes(const egot2_vit_desc* d);
+int egot2_vit_layer_fwd(const egot2_vit_desc* d, const egot2_vit_params* p, const void* x_in /* (M,D) */, void* x_out,
+                        const egot2_vit_saved* s, void* stream);
+/* dx_in may alias dx_out */
+int egot2_vit_layer_bwd(const egot2_vit_desc* d, const egot2_vit_params* p, const void* x_in, const egot2_vit_saved* s,
+                        const void* dx_out, void* dx_in, const egot2_vit_grads* g, void* workspace, size_t ws_bytes,
+                        void* stream);
 
 /* ------------------------------------------------------------------ EgoT2-g decoder (task-prompt transformer)
  * One nn.TransformerDecoderLayer (post-norm, ReLU; CustomDecoderLayer only forces need_weights) over the S-token task

@@ -40,6 +40,8 @@ def build_reference(case: Case, hhi, hoi):
         cfg.MODEL.FEAT_DROPOUT_MODE = 0                      # HOI/configs/pnr/defaults.py:240
         cfg.PRETRAIN.PNR_FT = cfg.PRETRAIN.OSCC_FT = True
         return hoi.pnr2.TaskFusionMFTransformerDropout(cfg)
+    if sp.family == "hoi_pnr" and sp.encoder == "simple_vit":
+        return hoi.pnr3.TaskFusionMFTransformer3Task(rs.hoi_pnr_cfg(256, 3, 0.5, 0.1, "keyframe_localization_2loader"))
     if sp.family == "hoi_pnr":
         task = "keyframe_localization_2loader" if sp.n_out == 16 else "state_change_detection"
         m = hoi.pnr3.TaskFusionMFTransformer3TaskDropout(rs.hoi_pnr_cfg(sp.hidden, sp.layers, sp.p_feat, sp.p_layer, task))

@@ -53,7 +53,8 @@ def test_forward_backward_plan(name, dtype, recorder):
     out = tm.run_ours(case, m, feats, extra, torch.device("cpu"), labels)
     fwd = _names(recorder)
     assert fwd.count("egot2_embed_fwd") == 1
-    assert fwd.count("egot2_encoder_layer_fwd") == sp.layers
+    layer = "egot2_vit_layer" if sp.encoder == "simple_vit" else "egot2_encoder_layer"
+    assert fwd.count(layer + "_fwd") == sp.layers
     assert fwd.count("egot2_decoder_layer_fwd") == sp.decoder_layers
     if sp.embed == "task_sinusoid":
         assert fwd.index("egot2_hhi_tok_table_fwd") < fwd.index("egot2_embed_fwd")
@@ -63,7 +64,7 @@ def test_forward_backward_plan(name, dtype, recorder):
     del recorder[:]
     out.float().sum().backward()
     bwd = _names(recorder)
-    assert bwd.count("egot2_encoder_layer_bwd") == sp.layers
+    assert bwd.count(layer + "_bwd") == sp.layers
     assert bwd.count("egot2_decoder_layer_bwd") == sp.decoder_layers
     assert bwd[-1] == "egot2_embed_bwd"
     for k in m._param_names:
@@ -160,3 +161,23 @@ def test_table_runs_default_to_one_run_per_segment(name):
         assert sum(r[0] for r in runs) == sum(case.seg_tokens) and len(runs) < len(sp.segments)
     else:
         assert runs == [(d, s.task_id) for s, d in zip(sp.segments, case.seg_tokens)]
+
+
+def test_simple_vit_layers_replace_the_torch_encoder(recorder):
+    """HOI PNR simple_vit sibling: the embed stage and the shared-ln head are those of the Dropout variant, the encoder is
+    depth x egot2_vit_layer_fwd/bwd with dim_head independent of the model width."""
+    case, m, feats, labels, extra = _build("hoi_pnr_vit_h256_l3")
+    out = tm.run_ours(case, m, feats, extra, torch.device("cpu"), labels)
+    names = _names(recorder)
+    assert names.count("egot2_vit_layer_fwd") == 3 and "egot2_encoder_layer_fwd" not in names
+    assert names.index("egot2_embed_fwd") < names.index("egot2_vit_layer_fwd") < names.index("egot2_head_loss_fwd")
+    (a0, a1, a2) = [a for n, a in recorder if n == "egot2_vit_layer_fwd"]
+    d = C.cast(a0[0], C.POINTER(L.VitDesc)).contents
+    assert (d.B, d.T, d.D, d.heads, d.dim_head, d.mlp) == (case.batch, 48, 256, 8, 128, 512)
+    assert a0[3] == a1[2] and a1[3] == a2[2]                      # layer i's output buffer is layer i+1's input
+    del recorder[:]
+    out.float().sum().backward()
+    names = _names(recorder)
+    assert names.count("egot2_vit_layer_bwd") == 3 and names[-1] == "egot2_embed_bwd"
+    for k in m._param_names:
+        assert m.get_parameter(k).grad is not None, k
