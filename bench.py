@@ -48,6 +48,10 @@ WORKLOADS = {
     # lam (64 clips x 7 tokens), ttm (8 clips x 3x30 tokens), asd (20 clips x 3x30 tokens -> 600 frame rows); H256 L3+3
     "hhi_g_train": dict(spec=lambda: specs.hhi_g_spec(256, 4, 3, 0.1, "ttm"), batch=92, seg_tokens=(30, 30, 30), prompt=True,
                         g_batches=dict(lam=(64, 7), ttm=(8, 30), asd=(20, 30))),
+    # HOI EgoT2-g at the reference defaults (hidden 512, 8 heads, 3+3 layers, HOI/configs/multitask/config.py:49-53),
+    # one step = the three forwards of Unified3TaskTranslation.training_step (pnr, oscc and action batches of 32 clips x 48 tokens)
+    "hoi_g_train": dict(spec=lambda: specs.hoi_g_spec(512, 8, 3, 0.1, 600), batch=96, seg_tokens=(16, 16, 8, 8), prompt=True,
+                        g_kind="hoi", g_batches=dict(pnr=32, oscc=32, action=32)),
 }
 L2_BYTES = 126 * 2 ** 20
 
@@ -80,6 +84,14 @@ def load_ncu_traffic(tag: str):
 def make_g_batch(wl, seed, fdt):
     """EgoT2-g step inputs: 7 feature tensors [lam | lam,ttm,asd | lam,ttm,asd] + concatenated (rows,3) targets."""
     feats, labels = [], []
+    if wl.get("g_kind") == "hoi":          # 12 feature tensors = 3 x [pnr, oscc, slow, fast] + concatenated (clips,3) targets
+        sp = wl["spec"]()
+        for i, task in enumerate(("pnr", "oscc", "action")):
+            b = wl["g_batches"][task]
+            f = synth.make_features(sp, b, seed=seed * 7 + i, dtype=fdt)
+            feats += [f[s_.name] for s_ in sp.segments]
+            labels.append(synth.make_labels(sp, b, seed=seed * 7 + i))
+        return feats, torch.cat(labels, dim=0)
     for mode in ("lam", "ttm", "asd"):
         b, d = wl["g_batches"][mode]
         sp = specs.hhi_g_spec(256, 4, 3, 0.1, mode)
@@ -92,6 +104,8 @@ def make_g_batch(wl, seed, fdt):
 
 def g_flops_per_step(wl, backward=True):
     tot = 0.0
+    if wl.get("g_kind") == "hoi":
+        return sum(wl["g_batches"].values()) * wl["spec"]().flops_per_clip(wl["seg_tokens"], backward=backward)
     for mode in ("lam", "ttm", "asd"):
         b, d = wl["g_batches"][mode]
         sp = specs.hhi_g_spec(256, 4, 3, 0.1, mode)
@@ -180,6 +194,21 @@ def cpu_oracle_g_step_fn(wl, seed=0):
     sd = synth.make_state_dict(spec, seed)
     P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     feats, labels = make_g_batch(wl, seed, torch.float32)
+    if wl.get("g_kind") == "hoi":
+
+        def hoi_step():
+            for p in P.values():
+                p.grad = None
+            off, loss = 0, 0.0
+            for i in range(3):
+                pnr, oscc, slow, fast = feats[4 * i:4 * i + 4]
+                tgt = labels[off:off + pnr.shape[0]]
+                off += pnr.shape[0]
+                out = O.hoi_g_forward(P, pnr, oscc, slow, fast, tgt[:, :-1], spec.heads, spec.p_layer, True)
+                loss = loss + torch.nn.functional.cross_entropy(out, tgt[:, 1:])
+            loss.backward()
+            return float(loss)
+        return hoi_step
     groups = {"lam": dict(lam=feats[0]), "ttm": dict(lam=feats[1], ttm=feats[2], asd=feats[3]),
               "asd": dict(lam=feats[4], ttm=feats[5], asd=feats[6])}
 
@@ -270,7 +299,10 @@ def main():
     B, seg = wl["batch"], wl["seg_tokens"]
     fdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     is_g = bool(wl.get("prompt"))
-    if is_g:
+    if is_g and wl.get("g_kind") == "hoi":
+        from egot2_b200.trainer import HoiPromptTranslatorTrainer
+        tr = HoiPromptTranslatorTrainer(spec.hidden, spec.heads, spec.layers, spec.p_layer, spec.vocab, dev, args.dtype)
+    elif is_g:
         from egot2_b200.trainer import PromptTranslatorTrainer
         tr = PromptTranslatorTrainer(256, 4, 3, 0.1, dev, args.dtype)
     else:
