@@ -166,6 +166,7 @@ SIGNATURES = {
     "egot2_cast_bf16_to_f32": (C.c_int, [vp, vp, sz, vp]),
     "egot2_adam_step": (C.c_int, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp]),
     "egot2_adam_step_fused": (C.c_int, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp, i32, vp]),
+    "egot2_adamw_step_fused": (C.c_int, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp, i32, vp]),
     "egot2_adam_step_fused_dev": (C.c_int, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp, f32, vp, i32, vp]),
     "egot2_gemm": (C.c_int, [i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, vp]),
     "egot2_gemm_last_impl": (C.c_char_p, []),

@@ -340,6 +340,8 @@ __global__ void zero_kernel(float* p, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
+// DECOUPLED = torch.optim.AdamW: the weight decay scales the parameter (p *= 1 - lr*wd) instead of joining the gradient
+template <bool DECOUPLED>
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
                             float bc1, float bc2_sqrt, float gscale, bf16* __restrict__ shadow, int zero_grad,
@@ -352,8 +354,9 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   }
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float grad = g[i] * gscale;
-    const float w = p[i];
-    if (wd != 0.f) grad += wd * w;
+    float w = p[i];
+    if (DECOUPLED) w *= 1.f - lr * wd;
+    else if (wd != 0.f) grad += wd * w;
     const float mi = b1 * m[i] + (1.f - b1) * grad;
     const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
     m[i] = mi; v[i] = vi;
@@ -921,14 +924,18 @@ extern "C" int egot2_cast_bf16_to_f32(const void* src, float* dst, size_t n, voi
 
 static int adam_launch(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                        float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* shadow,
-                       int zero_grad, void* stream, const int32_t* step_dev = nullptr) {
+                       int zero_grad, void* stream, const int32_t* step_dev = nullptr, bool decoupled = false) {
   EGOT2_CHECK(step >= 1 || step_dev, "adam: step must be >= 1");
   if (n == 0) return 0;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   ProfScope prof((cudaStream_t)stream, "adam n%zu", n);
-  launch(adam_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
-         beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, (bf16*)shadow, zero_grad, step_dev);
+  if (decoupled)
+    launch(adam_kernel<true>, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr,
+           beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, (bf16*)shadow, zero_grad, step_dev);
+  else
+    launch(adam_kernel<false>, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr,
+           beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, (bf16*)shadow, zero_grad, step_dev);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
@@ -943,6 +950,14 @@ extern "C" int egot2_adam_step_fused(float* param, float* grad, float* exp_avg, 
                                      float grad_scale, void* shadow_bf16, int32_t zero_grad, void* stream) {
   return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, shadow_bf16,
                      zero_grad, stream);
+}
+
+// torch.optim.AdamW (HOI EgoT2-g: lr 1e-4, weight decay 1e-4, HOI/tasks/multitask/video_task.py:265-268), same fusions
+extern "C" int egot2_adamw_step_fused(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                                      float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                                      float grad_scale, void* shadow_bf16, int32_t zero_grad, void* stream) {
+  return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, shadow_bf16,
+                     zero_grad, stream, nullptr, true);
 }
 
 extern "C" int egot2_adam_step_fused_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,

@@ -713,7 +713,7 @@ class TranslatorEngine:
     # ------------------------------------------------------------------ fused optimizer
     def adam_step(self, state: Dict[str, torch.Tensor], step: int, lr: float = 5e-4, betas=(0.9, 0.999),
                   eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0, fused: bool = False,
-                  step_dev: Optional[torch.Tensor] = None):
+                  step_dev: Optional[torch.Tensor] = None, decoupled: bool = False):
         """torch.optim.Adam over the whole arena in one launch (HHI/tasks/ttm/video_task.py:64-66: lr 5e-4).
         fused: the same launch also writes the bf16 shadow of the updated parameters (bf16 engines) and clears the
         gradient arena, so the next step needs neither the cast launch nor a fill (callers then pass
@@ -731,12 +731,18 @@ class TranslatorEngine:
                 L.call("egot2_adam_step_fused_dev", self.arena.param.data_ptr(), self.arena.grad.data_ptr(),
                        state["m"].data_ptr(), state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps,
                        weight_decay, step_dev.data_ptr(), float(grad_scale), shadow, 1, _stream())
+            elif decoupled:                 # torch.optim.AdamW (HOI EgoT2-g)
+                L.call("egot2_adamw_step_fused", self.arena.param.data_ptr(), self.arena.grad.data_ptr(),
+                       state["m"].data_ptr(), state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps,
+                       weight_decay, int(step), float(grad_scale), shadow, 1, _stream())
             else:
                 L.call("egot2_adam_step_fused", self.arena.param.data_ptr(), self.arena.grad.data_ptr(),
                        state["m"].data_ptr(), state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps,
                        weight_decay, int(step), float(grad_scale), shadow, 1, _stream())
             self.arena.shadow_fresh = shadow is not None
             return
+        if decoupled:
+            raise L.Egot2Error("adam_step: decoupled weight decay (AdamW) is only built into the fused launch")
         L.call("egot2_adam_step", self.arena.param.data_ptr(), self.arena.grad.data_ptr(), state["m"].data_ptr(),
                state["v"].data_ptr(), self.arena.numel, lr, betas[0], betas[1], eps, weight_decay, int(step),
                float(grad_scale), _stream())

@@ -115,6 +115,7 @@ class HoiPromptTranslatorTrainer:
         self._h2d: Dict[int, List[torch.Tensor]] = {}
         self.copy_stream = None if self.device.type != "cuda" else torch.cuda.Stream(device=self.device)
         self.loss_kind, self.class_weight = L.LOSS_CE, None
+        self._grad_clean = False           # True after a fused AdamW launch (it clears the gradient arena)
 
     def load_state_dict(self, sd):
         self.engine.arena.load_state_dict(sd)
@@ -131,16 +132,17 @@ class HoiPromptTranslatorTrainer:
             off += rows
             act = eng.forward(group, training=True, seed=self.step_count * 4 + i, labels=tgt[:, 1:], loss=L.LOSS_CE,
                               persistent=True, prompt=tgt[:, :-1])
-            eng.backward(act, dloss_scale=float(ratio), zero_grad=(i == 0))    # one arena, accumulated over the three
+            # one arena, accumulated over the three; cleared here only if the previous step's optimizer did not
+            eng.backward(act, dloss_scale=float(ratio), zero_grad=(i == 0 and not self._grad_clean))
             l = act.t["loss"][0] * ratio
             total = l if total is None else total + l
         scale = 1.0
         if self.world > 1:
             scale = allreduce_gradients(eng.arena.grad, self.pg)
-        # AdamW = decoupled decay: p *= 1 - lr * wd, then the plain Adam update (which does not read p)
-        if self.hp["weight_decay"]:
-            eng.arena.param.mul_(1.0 - self.hp["lr"] * self.hp["weight_decay"])
-        eng.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"], 0.0, grad_scale=scale)
+        # AdamW (decoupled decay) + bf16 shadow + gradient clear in one launch
+        eng.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
+                      self.hp["weight_decay"], grad_scale=scale, fused=True, decoupled=True)
+        self._grad_clean = True
         return total
 
 

@@ -378,6 +378,11 @@ int egot2_adam_step_fused(float* param, float* grad, float* exp_avg, float* exp_
 int egot2_adam_step_fused_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                               float beta1, float beta2, float eps, float weight_decay, const int32_t* step_dev,
                               float grad_scale, void* shadow_bf16, int32_t zero_grad, void* stream);
+/* torch.optim.AdamW: decoupled weight decay (param *= 1 - lr*weight_decay before the Adam update); otherwise as
+ * egot2_adam_step_fused (HOI EgoT2-g optimizer: HOI/tasks/multitask/video_task.py:265-268) */
+int egot2_adamw_step_fused(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                           float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                           void* shadow_bf16, int32_t zero_grad, void* stream);
 
 /* Batched PNR / OSCC evaluation metrics in one launch (replaces the per-clip `.item()` loops of
  * HOI/evaluation/pnr/metrics.py:11-80: state_change_accuracy, keyframe_accuracy, keyframe_distance).

@@ -128,7 +128,7 @@ def test_hoi_g6_predict_returns_verb_noun_pairs(recorder):
 
 def test_hoi_g_training_step_plan(recorder):
     """Unified3TaskTranslation.training_step (HOI/tasks/multitask/video_task.py:182-204): three forward/backward passes
-    into one gradient arena (cleared by the first only), decoupled weight decay, one Adam launch."""
+    into one gradient arena (cleared by the first only), one fused AdamW launch."""
     from egot2_b200 import synth
     from egot2_b200.trainer import HoiPromptTranslatorTrainer
     tr = HoiPromptTranslatorTrainer(hidden=128, heads=4, layers=2, vocab=40, device="cpu", dtype="fp32")
@@ -144,12 +144,13 @@ def test_hoi_g_training_step_plan(recorder):
     assert names.count("egot2_embed_fwd") == 3 and names.count("egot2_embed_bwd") == 3
     assert names.count("egot2_encoder_layer_fwd") == 3 * sp.layers == names.count("egot2_encoder_layer_bwd")
     assert names.count("egot2_decoder_layer_fwd") == 3 * sp.decoder_layers == names.count("egot2_decoder_layer_bwd")
-    assert names.count("egot2_adam_step") == 1 and names[-1] == "egot2_adam_step"
+    assert names.count("egot2_adamw_step_fused") == 1 and names[-1] == "egot2_adamw_step_fused"
     rows = [a[1] for n, a in recorder if n == "egot2_prompt_embed_fwd"]
     assert rows == [2, 3, 4]
-    assert float(tr.engine.arena.param[0]) == pytest.approx(1.0 - 1e-4 * 1e-4)          # AdamW's decoupled decay
-    (adam,) = [a for n, a in recorder if n == "egot2_adam_step"]
-    assert adam[9] == 0.0                                                               # no L2 term inside the Adam launch
+    (adam,) = [a for n, a in recorder if n == "egot2_adamw_step_fused"]
+    assert adam[5] == pytest.approx(1e-4) and adam[9] == pytest.approx(1e-4)          # lr, decoupled weight decay (:265-268)
+    assert float(tr.engine.arena.param[0]) == 1.0                                      # nothing touches the arena on the host
+    assert tr._grad_clean
 
 
 @pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n].spec.embed == "task_sinusoid"])

@@ -58,3 +58,28 @@ def test_hoi_g_greedy_predict_ac_matches_reference_golden():
     start = torch.full((NR.B, 1), 4, dtype=torch.int64)
     full = m(vid, ac, torch.cat([start, toks[:, :1]], dim=1).to(dev))          # (B, V, 2)
     assert torch.equal(full[:, :, -1].argmax(dim=1).cpu(), toks[:, 1])
+
+
+def test_fused_adamw_matches_torch():
+    """egot2_adamw_step_fused == torch.optim.AdamW (decoupled decay) over a flat arena, incl. the bf16 shadow it writes and
+    the gradient clear."""
+    import torch
+
+    from egot2_b200 import _lib as L
+    torch.manual_seed(0)
+    n = 4096 + 37
+    p = torch.randn(n, device="cuda")
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    shadow = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda")
+        ref.grad = g.clone()
+        opt.step()
+        L.call("egot2_adamw_step_fused", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-2, 0.9, 0.999, 1e-8, 0.1,
+               step, 1.0, shadow.data_ptr(), 1, st)
+        assert float((p - ref.detach()).abs().max()) < 1e-6
+        assert float(g.abs().max()) == 0.0
+        assert torch.equal(shadow, p.to(torch.bfloat16))
