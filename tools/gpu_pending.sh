@@ -1,0 +1,23 @@
+#!/bin/bash
+# First GPU round-trip for code that was written without hardware: the xfail(non-strict) parity tests of
+# oracle.cases.UNVALIDATED_ON_GPU (+ greedy decoding, fused AdamW) with full tracebacks, then the bench lines of the new
+# workloads.  Usage (under gpurun): tools/gpu_pending.sh [tag]      -> gpurun_out/pending_<tag>.log, bench_*_<tag>.json
+tag=${1:-run}
+mkdir -p gpurun_out
+# --runxfail: report real pass / fail (with tracebacks) instead of XPASS / XFAIL
+timeout 900 python -m pytest tests/test_zz_unvalidated_gpu.py -m gpu -q --runxfail -rA --tb=short \
+  > gpurun_out/pending_$tag.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pending_$tag.log
+grep -E "PASSED|FAILED|ERROR|passed|failed|rc=" gpurun_out/pending_$tag.log | tail -40
+for wl in hoi_g_train hhi_g_train; do
+  timeout 300 python bench.py --workload $wl --skip-cpu-baseline --steps 20 --warmup 3 \
+    > gpurun_out/bench_${wl}_$tag.json 2> gpurun_out/bench_${wl}_$tag.err
+  tail -c 400 gpurun_out/bench_${wl}_$tag.err
+  python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/bench_${wl}_$tag.json").read().strip().splitlines()[-1])
+    print("$wl", "value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], "launches", d.get("gpu_launches"))
+except Exception as e:
+    print("$wl bench parse failed", e)
+PY
+done
