@@ -137,6 +137,8 @@ static bool force_simt_attention() {   // diagnostics: EGOT2_ATTN=simt
 
 int attention_fwd(int dtype, int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p_drop,
                   uint64_t drop_key, cudaStream_t st) {
+  if (heads > 0 && H % heads == 0 && H / heads > 128)
+    return attention_wide_fwd(dtype, B, T, H, heads, qkv, out, lse, p_drop, drop_key, st);
   if (attention_mma_supported(dtype, T, H, heads) && !force_simt_attention())
     return attention_mma_fwd(B, T, H, heads, qkv, out, lse, p_drop, drop_key, st);
   return attention_simt_fwd(dtype, B, T, H, heads, qkv, out, lse, p_drop, drop_key, st);
@@ -144,6 +146,8 @@ int attention_fwd(int dtype, int B, int T, int H, int heads, const void* qkv, vo
 int attention_bwd(int dtype, int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse,
                   const void* dout, void* dqkv, float p_drop, uint64_t drop_key, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
+  if (heads > 0 && H % heads == 0 && H / heads > 128)
+    return attention_wide_bwd(dtype, B, T, H, heads, qkv, out, lse, dout, dqkv, p_drop, drop_key, st);
   if (attention_mma_supported(dtype, T, H, heads) && !force_simt_attention())
     return attention_mma_bwd(B, T, H, heads, qkv, out, lse, dout, dqkv, p_drop, drop_key, st);
   return attention_simt_bwd(dtype, B, T, H, heads, qkv, out, lse, dout, dqkv, p_drop, drop_key, ws, ws_bytes, st);

@@ -1,6 +1,6 @@
 // rowops.cu — HBM-bound row-wise kernels: LayerNorm fwd/bwd, token pooling, column reductions,
 // dropout, casts, Adam, token-table helpers, SlowFast map pooling.
-// One warp owns one row of H (H = 32*NPL, NPL in {1,2,4,8,16,32}); all statistics in fp32.
+// One warp owns one row of H (H = 32*NPL, NPL in {1,2,4,8,16,32,64}); all statistics in fp32.
 // Loads/stores are coalesced (lane-strided columns); grids are sized to a multiple of the SM count.
 #include <math.h>
 
@@ -719,7 +719,7 @@ template <int NPL> int ln_bwd_dispatch(const LayerNormBwdArgs& a, cudaStream_t s
 }  // namespace
 
 int layernorm_fwd(const LayerNormArgs& a, cudaStream_t st) {
-  EGOT2_CHECK(a.H % 32 == 0 && a.H <= 1024, "layernorm: H=%d must be a multiple of 32 and <= 1024", a.H);
+  EGOT2_CHECK(a.H % 32 == 0 && a.H <= 2048, "layernorm: H=%d must be a multiple of 32 and <= 2048", a.H);
   if (a.rows == 0) return 0;
   if (!a.x_is_f32 && ln_vec_ok(a.dtype, a.H, a.x, a.y, a.table, nullptr)) {
     switch (a.H) {
@@ -736,12 +736,13 @@ int layernorm_fwd(const LayerNormArgs& a, cudaStream_t st) {
     case 8: return ln_fwd_dispatch<8>(a, st);
     case 16: return ln_fwd_dispatch<16>(a, st);
     case 32: return ln_fwd_dispatch<32>(a, st);
+    case 64: return ln_fwd_dispatch<64>(a, st);       // H = 2048: the LTA 2-task translator's shipped width
   }
-  EGOT2_CHECK(false, "layernorm: H=%d not in {32,64,128,256,512,1024}", a.H);
+  EGOT2_CHECK(false, "layernorm: H=%d not in {32,64,128,256,512,1024,2048}", a.H);
 }
 
 int layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t st) {
-  EGOT2_CHECK(a.H % 32 == 0 && a.H <= 1024, "layernorm_bwd: H=%d must be a multiple of 32 and <= 1024", a.H);
+  EGOT2_CHECK(a.H % 32 == 0 && a.H <= 2048, "layernorm_bwd: H=%d must be a multiple of 32 and <= 2048", a.H);
   if (a.rows == 0) return 0;
   if (!a.x_is_f32 && !a.dy_is_f32 && !a.dx_is_f32 && ln_vec_ok(a.dtype, a.H, a.x, a.dy, a.dx, a.dres) &&
       (reinterpret_cast<uintptr_t>(a.dx2) & 15) == 0) {
@@ -782,8 +783,9 @@ int layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t st) {
     case 8: return ln_bwd_dispatch<8>(a, st);
     case 16: return ln_bwd_dispatch<16>(a, st);
     case 32: return ln_bwd_dispatch<32>(a, st);
+    case 64: return ln_bwd_dispatch<64>(a, st);
   }
-  EGOT2_CHECK(false, "layernorm_bwd: H=%d not in {32,64,128,256,512,1024}", a.H);
+  EGOT2_CHECK(false, "layernorm_bwd: H=%d not in {32,64,128,256,512,1024,2048}", a.H);
 }
 
 int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, const SegOut& so, float p_drop, uint64_t drop_key,

@@ -7,7 +7,7 @@ Reference (relative to /root/reference):
   pnr.TaskFusionMFTransformer3Task          HOI/models/pnr/video_model_transfer_3task.py:128-164 (simple_vit sibling)
   lta.TaskFusionMFTransformer3Task          HOI/models/lta/lta_models_transfer.py:96-137    (action-recognition sibling)
   lta.TaskFusionMFTransformer2TaskAR        HOI/models/lta/lta_models_transfer.py:169-235   (AR from recognition + LTA features)
-  lta.TaskFusionMFTransformer2Task          HOI/models/lta/lta_models_lta_transfer.py:429-526 (LTA 2-task sibling, H <= 1024)
+  lta.TaskFusionMFTransformer2Task          HOI/models/lta/lta_models_lta_transfer.py:429-526 (LTA 2-task sibling)
   MultiTaskHead (LTA head)                  HOI/models/lta/head_helper.py:218-291
   multitask.TaskTranslationPromptTransformer       HOI/models/multitask/video_model_builder.py:223-275 (HOI EgoT2-g)
   multitask.TaskTranslationPromptTransformer6Task  HOI/models/multitask/video_model_builder.py:279-383
@@ -448,7 +448,7 @@ class _LTA4Task(TranslatorBase):
 
 class _LTA2Task(TranslatorBase):
     """LTA 2-task sibling (HOI/models/lta/lta_models_lta_transfer.py:429-526): AR + LTA features of the input clips ->
-    20 future (verb, noun) distributions.  TRANSLATION_INPUT_FEATURES == 2048 (proj_lta = Identity) is not built."""
+    20 future (verb, noun) distributions; at TRANSLATION_INPUT_FEATURES == 2048 (the shipped config) proj_lta = Identity."""
 
     def __init__(self, cfg, backbones: Optional[Dict[str, nn.Module]] = None):
         super().__init__()
@@ -457,10 +457,8 @@ class _LTA2Task(TranslatorBase):
         self.num_heads = cfg.MODEL.TRANSLATION_HEADS
         self.num_layers = cfg.MODEL.TRANSLATION_LAYERS
         self.feature_dim = cfg.MODEL.TRANSLATION_INPUT_FEATURES
-        if self.feature_dim == 2048:
-            raise L.Egot2Error("TaskFusionMFTransformer2Task with TRANSLATION_INPUT_FEATURES = 2048 (proj_lta = Identity) "
-                               "is not built: the LayerNorm kernels stop at H = 1024")
-        self.proj_lta = nn.Linear(2048, self.feature_dim)
+        # :441-444 - at the shipped width 2048 the LTA features enter as they are
+        self.proj_lta = nn.Identity() if self.feature_dim == 2048 else nn.Linear(2048, self.feature_dim)
         self.dp_rate = cfg.MODEL.TRANSLATION_DROPOUT
         self.pe = nn.Parameter(torch.randn(1, self.sequence_len, self.feature_dim), requires_grad=True)
         self.transformer = nn.TransformerEncoder(

@@ -306,11 +306,10 @@ def hoi_lta2_spec(hidden=512, layers=1, heads=4, dropout=0.5, num_input_clips=2,
                   num_classes=(115, 478), head_dropout=0.5, ffn=2048) -> TranslatorSpec:
     """LTA 2-task sibling `TaskFusionMFTransformer2Task` (HOI/models/lta/lta_models_lta_transfer.py:429-526): tokens
     (action, lta) x num_input_clips, the action features arrive `hidden` wide from the SlowFast head, `proj_lta` is a
-    Linear(2048, hidden) (nn.Identity when hidden == 2048 - the shipped ts_lta_2task.yaml - which is beyond the
-    H <= 1024 LayerNorm kernels and not built), same MultiTaskHead as the 4-task translator."""
-    assert hidden != 2048, "hidden == 2048 (proj_lta = Identity) needs LayerNorm kernels beyond H = 1024: not built"
+    Linear(2048, hidden) - or nn.Identity when hidden == 2048 (:441-444; the shipped ts_lta_2task.yaml: H 2048, 4 heads =
+    head dim 512, served by the wide-head attention kernels) - same MultiTaskHead as the 4-task translator."""
     n = num_input_clips
-    segs = (Segment("action", hidden, None, n), Segment("lta", 2048, "proj_lta", n))
+    segs = (Segment("action", hidden, None, n), Segment("lta", 2048, None if hidden == 2048 else "proj_lta", n))
     return TranslatorSpec("hoi_lta", hidden, heads, ffn, layers, segs, "learned_pe", "transformer.",
                           "pool_multilinear", num_actions * sum(num_classes), False, dropout, 0.0, 0.0,
                           head_dropout, 0, tuple(num_classes), num_actions)

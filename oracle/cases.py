@@ -47,6 +47,8 @@ CASES = {c.name: c for c in [
     # SURVEY 8a-F sibling: LTA 2-task (tokens (action, lta) x 2)
     Case("hoi_lta2_h512_l1", specs.hoi_lta2_spec(512, 1, 4, 0.5), 3, (2, 2), 16),
     Case("hoi_lta_h1024_l1", specs.hoi_lta_spec(1024, 1, 8, 0.5), 2, (2, 2, 2, 2), 10),
+    # the LTA 2-task sibling at its SHIPPED width (ts_lta_2task.yaml: H 2048, 4 heads = head dim 512, proj_lta = Identity)
+    Case("hoi_lta2_h2048_l1", specs.hoi_lta2_spec(2048, 1, 4, 0.5), 2, (2, 2), 21),
     # BASELINE config 3: HHI EgoT2-g (encoder + decoder over the task prompt), the three forwards of one step
     Case("hhi_g_lam_h128_l2", specs.hhi_g_spec(128, 4, 2, 0.1, "lam"), 5, (7,), 11),
     Case("hhi_g_ttm_h128_l2", specs.hhi_g_spec(128, 4, 2, 0.1, "ttm"), 3, (9, 9, 9), 11),
@@ -66,7 +68,7 @@ CASES = {c.name: c for c in [
 #: against the reference class, golden) are green, the GPU parity tests for them are marked xfail(strict=False) until
 #: they have run on hardware once (tests/test_zz_unvalidated_gpu.py)
 # (hoi_lta2_h512_l1 went this way: 4 x XPASS on a B200 at the end of round 1, then moved into the regular lists)
-UNVALIDATED_ON_GPU = {"hoi_g_h128_l2", "hoi_g6_clip_h128_l1", "hoi_g6_lta_h128_l2", "hoi_pnr_vit_h256_l3"}
+UNVALIDATED_ON_GPU = {"hoi_g_h128_l2", "hoi_g6_clip_h128_l1", "hoi_g6_lta_h128_l2", "hoi_pnr_vit_h256_l3", "hoi_lta2_h2048_l1"}
 
 
 def case_inputs(case: Case):

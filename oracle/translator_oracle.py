@@ -345,7 +345,8 @@ def hoi_lta2_forward(P: Params, action: Tensor, lta: Tensor, n_heads: int = 4, p
     """LTA TaskFusionMFTransformer2Task -> stacked head logits (B, Z, 593).
     HOI/models/lta/lta_models_lta_transfer.py:510-518: tokens (action x n, proj_lta(lta) x n) -> ln + pe -> encoder ->
     mean -> MultiTaskHead (Z x [Dropout -> Linear(H, 593)], softmax over 593 in eval unless TEST.NO_ACT)."""
-    z = torch.cat([action, linear(lta, P["proj_lta.weight"], P["proj_lta.bias"])], dim=1)
+    # :441-444 - proj_lta is nn.Identity when the translator is 2048 wide (no proj_lta.* in the state_dict)
+    z = torch.cat([action, linear(lta, P["proj_lta.weight"], P["proj_lta.bias"]) if "proj_lta.weight" in P else lta], dim=1)
     x = layer_norm(z, P["ln.weight"], P["ln.bias"]) + P["pe"]
     x = encoder(x, P, "transformer.", count_layers(P, "transformer."), n_heads, p_drop, training)
     g = x.mean(dim=1)

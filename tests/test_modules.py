@@ -199,7 +199,7 @@ def test_container_forward_is_poisoned():
 @pytest.mark.requires_reference
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_l1", "hhi_asd_h128_l1", "hoi_pnr_h128_l6", "hoi_lta_h512_l4",
                                   "hhi_g_ttm_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2", "hoi_lta2_h512_l1",
-                                  "hoi_g_h128_l2", "hoi_g6_lta_h128_l2", "hoi_pnr_vit_h256_l3"])
+                                  "hoi_g_h128_l2", "hoi_g6_lta_h128_l2", "hoi_pnr_vit_h256_l3", "hoi_lta2_h2048_l1"])
 def test_same_seed_same_init_as_reference(name):
     """ctor parity: under the same torch seed our module draws exactly the reference's initial weights."""
     from oracle import ref_shims as rs
