@@ -359,6 +359,8 @@ static int embed_check(const egot2_embed_desc* d) {
     tot += d->seg_tokens[k];
   }
   EGOT2_CHECK(tot == d->T, "embed: segments cover %d tokens, T=%d", tot, d->T);
+  EGOT2_CHECK(!d->no_ln || !d->training || (d->p_feat == 0.f && d->p_embed == 0.f),
+              "embed: the LayerNorm-free variant has no dropout sites (p_feat=%f p_embed=%f)", d->p_feat, d->p_embed);
   return 0;
 }
 
@@ -412,6 +414,7 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   const size_t n = (size_t)d->B * d->T * d->H;
   if (d->training && d->p_feat > 0.f)
     EGOT2_TRY(dropout_inplace(d->dtype, out->z, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+  if (d->no_ln) return add_table(d->dtype, n, (size_t)d->T * d->H, out->z, in->tok_table, out->x, st);
   LayerNormArgs l;
   l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = out->z; l.g = in->ln_g; l.b = in->ln_b; l.eps = d->ln_eps;
   l.y = out->x; l.stat = out->stat; l.table = in->tok_table; l.table_rows = d->T;
@@ -452,12 +455,16 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   for (int k = 0; k < d->n_seg; ++k) { so.tokens[k] = d->seg_tokens[k]; so.out[k] = g->seg_embed[k]; want_table |= g->seg_embed[k] != nullptr; }
   Side* tside = want_table ? get_side(2) : nullptr;
   if (want_table) EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dx, g->tok_table, so, pe, ke, side_fork(st, tside, 0)));
-  LayerNormBwdArgs l;
-  l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = saved->z; l.stat = saved->stat; l.g = in->ln_g;
-  l.dy = dx; l.dx = dz; l.dg = g->ln_g; l.db = g->ln_b; l.dy_p_drop = pe; l.dy_drop_key = ke;
-  EGOT2_TRY(layernorm_bwd(l, st));
-  if (d->training && d->p_feat > 0.f)
-    EGOT2_TRY(dropout_inplace(d->dtype, dz, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+  if (d->no_ln) {
+    dz = dx;                              // x = z + table: the token gradient IS the projection-output gradient
+  } else {
+    LayerNormBwdArgs l;
+    l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = saved->z; l.stat = saved->stat; l.g = in->ln_g;
+    l.dy = dx; l.dx = dz; l.dg = g->ln_g; l.db = g->ln_b; l.dy_p_drop = pe; l.dy_drop_key = ke;
+    EGOT2_TRY(layernorm_bwd(l, st));
+    if (d->training && d->p_feat > 0.f)
+      EGOT2_TRY(dropout_inplace(d->dtype, dz, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+  }
   const bool par = d->feat_dtype == d->dtype;
   Side* sides[2] = {par ? get_side(0) : nullptr, par ? get_side(1) : nullptr};
   bool used[2] = {false, false};

@@ -272,7 +272,9 @@ class TranslatorEngine:
             if s.proj is not None:
                 ein.proj_w[k] = self._mat(s.proj + ".weight").data_ptr()
                 ein.proj_b[k] = self._vec(s.proj + ".bias").data_ptr()
-        ein.ln_g, ein.ln_b = self._vec("ln.weight").data_ptr(), self._vec("ln.bias").data_ptr()
+        d.no_ln = 0 if sp.embed_ln else 1
+        if sp.embed_ln:
+            ein.ln_g, ein.ln_b = self._vec("ln.weight").data_ptr(), self._vec("ln.bias").data_ptr()
         ein.tok_table = table.data_ptr()
         eout.z = buf("z", (B, T, H), tdt).data_ptr()
         eout.stat = buf("stat0", (M, 2), torch.float32).data_ptr()
@@ -695,7 +697,8 @@ class TranslatorEngine:
             if k < len(want_dfeat) and want_dfeat[k]:
                 dfeats[k] = torch.empty((B, act.seg_tokens[k], s.in_dim), device=dev, dtype=torch.float32)
                 eg.dfeat[k] = dfeats[k].data_ptr()
-        eg.ln_g, eg.ln_b = gv("ln.weight").data_ptr(), gv("ln.bias").data_ptr()
+        if sp.embed_ln:
+            eg.ln_g, eg.ln_b = gv("ln.weight").data_ptr(), gv("ln.bias").data_ptr()
         if sp.embed == "task_sinusoid":
             # table row = task_embed[task_k] + fixed sinusoid: the column sums of each segment go straight into
             # d(task_embed[task_k]) (no (T,H) table gradient, no second reduction pass)

@@ -5,6 +5,7 @@ Reference (relative to /root/reference):
   lta.TaskFusionMFTransformerLTA4Task       HOI/models/lta/lta_models_lta_transfer.py:257-377
   pnr.TaskFusionMFTransformerDropout        HOI/models/pnr/video_model_transfer.py:70-105   (2-task sibling)
   pnr.TaskFusionMFTransformer3Task          HOI/models/pnr/video_model_transfer_3task.py:128-164 (simple_vit sibling)
+  pnr.TaskFusionMFTransformer               HOI/models/pnr/video_model_transfer.py:44-67       (2-task simple_vit sibling)
   lta.TaskFusionMFTransformer3Task          HOI/models/lta/lta_models_transfer.py:96-137    (action-recognition sibling)
   lta.TaskFusionMFTransformer2TaskAR        HOI/models/lta/lta_models_transfer.py:169-235   (AR from recognition + LTA features)
   lta.TaskFusionMFTransformer2Task          HOI/models/lta/lta_models_lta_transfer.py:429-526 (LTA 2-task sibling)
@@ -29,8 +30,8 @@ from . import _lib as L
 from .engine import TranslatorEngine, _stream
 from .functional import translator_apply
 from .modules import PrecomputedFeatures, TranslatorBase
-from .specs import (hoi_ar2_spec, hoi_ar_spec, hoi_g_spec, hoi_lta2_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr_spec,
-                    hoi_pnr_vit_spec)
+from .specs import (hoi_ar2_spec, hoi_ar_spec, hoi_g_spec, hoi_lta2_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr2_vit_spec,
+                    hoi_pnr_spec, hoi_pnr_vit_spec)
 
 
 def slowfast_pool(x5: torch.Tensor, t_out: int, out_dtype: torch.dtype) -> torch.Tensor:
@@ -153,6 +154,37 @@ class _PNR3TaskVit(TranslatorBase):
         self._init_translator(hoi_pnr_vit_spec(self.num_classes))
 
     forward = _PNR3TaskDropout.forward
+
+
+class _PNR2TaskVit(TranslatorBase):
+    """2-task simple_vit sibling (HOI/models/pnr/video_model_transfer.py:44-67): PNR + OSCC projections + pe (no token
+    LayerNorm) -> simple_vit Transformer -> mean -> Sequential(LayerNorm, Linear)."""
+
+    def __init__(self, cfg, backbones: Optional[Dict[str, nn.Module]] = None):
+        super().__init__()
+        self.cfg_recognition = None
+        if backbones is None:
+            backbones = _reference_pnr_backbones(self, cfg, with_recognition=False)
+        for k, m in backbones.items():
+            setattr(self, k, m)
+        self.num_classes = 16 if cfg.DATA.TASK == "keyframe_localization" else 2
+        self.unsqueeze_dim = 1 if cfg.DATA.TASK == "keyframe_localization" else 2
+        self.sequence_len = 32
+        self.feature_dim = 256
+        self.proj1 = nn.Linear(8192, self.feature_dim)
+        self.proj2 = nn.Linear(8192, self.feature_dim)
+        self.pe = nn.Parameter(torch.randn(1, self.sequence_len, self.feature_dim), requires_grad=True)
+        self.transformer = _VitTransformer(dim=self.feature_dim, depth=3, heads=8, dim_head=128, mlp_dim=512)
+        self.linear_head = nn.Sequential(nn.LayerNorm(self.feature_dim), nn.Linear(self.feature_dim, self.num_classes))
+        self._poison_containers(self.proj1, self.proj2, self.transformer, self.linear_head)
+        self._init_translator(hoi_pnr2_vit_spec(self.num_classes))
+
+    def forward(self, x):
+        x2 = x.copy()
+        pnr_feat = self.pnr_model(x, middle=True)                        # (bs, 16, 8192)
+        oscc_feat = self.oscc_model(x2, middle=True)                     # (bs, 16, 8192)
+        out = self._translate([pnr_feat, oscc_feat])                     # token order (pnr, oscc)
+        return out.unsqueeze(self.unsqueeze_dim)
 
 
 class _PNR2TaskDropout(TranslatorBase):
@@ -816,13 +848,15 @@ multitask = SimpleNamespace(TaskTranslationPromptTransformer=_PromptTranslator,
                             TaskTranslationPromptTransformer6Task=_PromptTranslator6Task)
 
 pnr = SimpleNamespace(TaskFusionMFTransformer3TaskDropout=_PNR3TaskDropout, TaskFusionMFTransformerDropout=_PNR2TaskDropout,
-                      TaskFusionMFTransformer3Task=_PNR3TaskVit)
+                      TaskFusionMFTransformer3Task=_PNR3TaskVit, TaskFusionMFTransformer=_PNR2TaskVit)
 _PNR3TaskDropout.__name__ = _PNR3TaskDropout.__qualname__ = "TaskFusionMFTransformer3TaskDropout"
 _PNR2TaskDropout.__name__ = _PNR2TaskDropout.__qualname__ = "TaskFusionMFTransformerDropout"
 _PNR3TaskVit.__name__ = _PNR3TaskVit.__qualname__ = "TaskFusionMFTransformer3Task"
+_PNR2TaskVit.__name__ = _PNR2TaskVit.__qualname__ = "TaskFusionMFTransformer"
 pnr.MODEL_REGISTRY = {"TaskFusionMFTransformer3TaskDropout": _PNR3TaskDropout,
                       "TaskFusionMFTransformerDropout": _PNR2TaskDropout,
-                      "TaskFusionMFTransformer3Task": _PNR3TaskVit}
+                      "TaskFusionMFTransformer3Task": _PNR3TaskVit,
+                      "TaskFusionMFTransformer": _PNR2TaskVit}
 pnr.build_model = lambda cfg, **kw: pnr.MODEL_REGISTRY[cfg.MODEL.MODEL_NAME](cfg, **kw)
 
 lta = SimpleNamespace(TaskFusionMFTransformerLTA4Task=_LTA4Task, TaskFusionMFTransformer3Task=_AR3Task,

@@ -56,6 +56,7 @@ class TranslatorSpec:
     encoder: str = "torch"              # "torch": nn.TransformerEncoderLayer (post-norm, ReLU) | "simple_vit": pre-norm, GELU,
                                         # bias-free attention with `dim_head` independent of `hidden` (HOI/models/pnr/simple_vit.py)
     dim_head: int = 0                   # simple_vit only: inner = heads * dim_head
+    embed_ln: bool = True               # False: tokens = projected features + pe, no LayerNorm (2-task simple_vit sibling)
 
     @property
     def fixed_tokens(self) -> Optional[int]:
@@ -103,7 +104,7 @@ class TranslatorSpec:
                 if s.proj is not None:
                     out[f"{s.proj}.weight"] = (H, s.in_dim)
                     out[f"{s.proj}.bias"] = (H,)
-        if self.family == "hoi_pnr":
+        if self.family == "hoi_pnr" and (self.embed_ln or self.head_ln_shared):
             out["ln.weight"] = (H,)
             out["ln.bias"] = (H,)
         for i in range(self.layers if self.encoder == "simple_vit" else 0):
@@ -159,7 +160,10 @@ class TranslatorSpec:
             out["linear_head.weight"] = (self.n_out, H)       # 2-task variant: a bare nn.Linear head
             out["linear_head.bias"] = (self.n_out,)
         elif self.family == "hoi_pnr":
-            # linear_head.0.* alias ln.* in the reference state_dict (same tensor)
+            # linear_head.0.* alias ln.* in the reference state_dict (same tensor) unless the head owns its LayerNorm
+            if not self.head_ln_shared:
+                out["linear_head.0.weight"] = (H,)
+                out["linear_head.0.bias"] = (H,)
             out["linear_head.1.weight"] = (self.n_out, H)
             out["linear_head.1.bias"] = (self.n_out,)
         elif self.family == "hoi_ar":
@@ -272,6 +276,15 @@ def hoi_pnr_vit_spec(n_cls=16) -> TranslatorSpec:
             Segment("slow", 2048, "proj3_slow", 8), Segment("fast", 256, "proj3_fast", 8))
     return TranslatorSpec("hoi_pnr", 256, 8, 512, 3, segs, "learned_pe", "transformer.", "pool_ln_linear", n_cls, True,
                           0.0, 0.0, 0.0, 0.0, encoder="simple_vit", dim_head=128)
+
+
+def hoi_pnr2_vit_spec(n_cls=16) -> TranslatorSpec:
+    """2-task simple_vit sibling `TaskFusionMFTransformer` (HOI/models/pnr/video_model_transfer.py:44-67): tokens (pnr16,
+    oscc16) = projections + pe with NO token LayerNorm (:63), the same simple_vit Transformer(256, depth 3, 8 x 128, mlp 512),
+    head = Sequential(its own LayerNorm, Linear)."""
+    segs = (Segment("pnr", 8192, "proj1", 16), Segment("oscc", 8192, "proj2", 16))
+    return TranslatorSpec("hoi_pnr", 256, 8, 512, 3, segs, "learned_pe", "transformer.", "pool_ln_linear", n_cls, False,
+                          0.0, 0.0, 0.0, 0.0, encoder="simple_vit", dim_head=128, embed_ln=False)
 
 
 def hoi_pnr2_spec(n_cls=16, tr_dropout=0.1) -> TranslatorSpec:

@@ -105,6 +105,8 @@ typedef struct {
   float p_embed;                      /* dropout AFTER the embedding add (HHI PositionalEncoding.dropout) */
   float ln_eps;
   uint64_t seed;
+  int32_t no_ln;                      /* 1: no LayerNorm - tokens = projected features + tok_table (the 2-task simple_vit
+                                       * sibling, HOI/models/pnr/video_model_transfer.py:63); needs p_feat = p_embed = 0 */
 } egot2_embed_desc;
 
 typedef struct {

@@ -40,6 +40,10 @@ def build_reference(case: Case, hhi, hoi):
         cfg.MODEL.FEAT_DROPOUT_MODE = 0                      # HOI/configs/pnr/defaults.py:240
         cfg.PRETRAIN.PNR_FT = cfg.PRETRAIN.OSCC_FT = True
         return hoi.pnr2.TaskFusionMFTransformerDropout(cfg)
+    if sp.family == "hoi_pnr" and sp.encoder == "simple_vit" and len(sp.segments) == 2:
+        cfg = rs.hoi_pnr_cfg(256, 3, 0.5, 0.1, "keyframe_localization")
+        cfg.PRETRAIN.PNR_FT = cfg.PRETRAIN.OSCC_FT = True
+        return hoi.pnr2.TaskFusionMFTransformer(cfg)
     if sp.family == "hoi_pnr" and sp.encoder == "simple_vit":
         return hoi.pnr3.TaskFusionMFTransformer3Task(rs.hoi_pnr_cfg(256, 3, 0.5, 0.1, "keyframe_localization_2loader"))
     if sp.family == "hoi_pnr":
@@ -143,7 +147,7 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
     elif sp.family == "hoi_g":
         out = hoi_g_reference_forward(sp, m, feats, labels[:, :-1])                         # (B, V, 2)
         loss = torch.nn.CrossEntropyLoss()(out, labels[:, 1:])                              # HOI/tasks/multitask/video_task.py:177,185
-    elif sp.family == "hoi_pnr" and sp.head == "pool_linear":
+    elif sp.family == "hoi_pnr" and len(sp.segments) == 2:
         m.pnr_model = rs.FeatureBackbone(); m.pnr_model.slot = "pnr"
         m.oscc_model = rs.FeatureBackbone(); m.oscc_model.slot = "oscc"
         out = m([{"pnr": feats["pnr"], "oscc": feats["oscc"]}])

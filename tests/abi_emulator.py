@@ -64,7 +64,8 @@ def embed_fwd(desc, ein, eout, ws, ws_bytes, st):
             z[:, off:off + Dk] = O.linear(f, _f32(i.proj_w[k], d.H, Kk), _f32(i.proj_b[k], d.H))
         else:
             z[:, off:off + Dk] = f
-    x = O.layer_norm(z, _f32(i.ln_g, d.H), _f32(i.ln_b, d.H), d.ln_eps) + _f32(i.tok_table, d.T, d.H)
+    table = _f32(i.tok_table, d.T, d.H)
+    x = z + table if d.no_ln else O.layer_norm(z, _f32(i.ln_g, d.H), _f32(i.ln_b, d.H), d.ln_eps) + table
     _f32(o.x, d.B, d.T, d.H).copy_(x)
 
 
@@ -328,10 +329,11 @@ def embed_bwd(desc, ein, esaved, dx, grads, ws, ws_bytes, st):
     feats = [_leaf(_f32(i.feat[k], B, d.seg_tokens[k], d.seg_in_dim[k])) for k in range(d.n_seg)]
     ws_ = [_leaf(_f32(i.proj_w[k], H, d.seg_in_dim[k])) if d.seg_has_proj[k] else None for k in range(d.n_seg)]
     bs_ = [_leaf(_f32(i.proj_b[k], H)) if d.seg_has_proj[k] else None for k in range(d.n_seg)]
-    lng, lnb = _leaf(_f32(i.ln_g, H)), _leaf(_f32(i.ln_b, H))
+    lng = None if d.no_ln else _leaf(_f32(i.ln_g, H))
+    lnb = None if d.no_ln else _leaf(_f32(i.ln_b, H))
     table = _leaf(_f32(i.tok_table, T, H))
     z = torch.cat([O.linear(f, w, b) if w is not None else f for f, w, b in zip(feats, ws_, bs_)], dim=1)
-    x = O.layer_norm(z, lng, lnb, d.ln_eps) + table
+    x = z + table if d.no_ln else O.layer_norm(z, lng, lnb, d.ln_eps) + table
     leaves = [t for t in feats + ws_ + bs_ + [lng, lnb, table] if t is not None]
     gs = dict(zip(map(id, leaves), torch.autograd.grad(x, leaves, _f32(dx, B, T, H).clone(), allow_unused=True)))
     for k in range(d.n_seg):
@@ -342,8 +344,9 @@ def embed_bwd(desc, ein, esaved, dx, grads, ws, ws_bytes, st):
         if g.seg_embed[k]:          # column sums of the table gradient over segment k's tokens (+=: segments may share a row)
             off = d.seg_offset[k]
             _acc(g.seg_embed[k], gs[id(table)][off:off + d.seg_tokens[k]].sum(dim=0), H)
-    _acc(g.ln_g, gs[id(lng)], H)
-    _acc(g.ln_b, gs[id(lnb)], H)
+    if not d.no_ln:
+        _acc(g.ln_g, gs[id(lng)], H)
+        _acc(g.ln_b, gs[id(lnb)], H)
     _acc(g.tok_table, gs[id(table)], T, H)
 
 

@@ -94,6 +94,10 @@ def build_ours(case, backbones=True):
                       MODEL=CfgNode(FEAT_DROPOUT_RATE=0.5, FEAT_DROPOUT_MODE=0, TRANSFORMER_DROPOUT_RATE=sp.p_layer))
         bb = {"pnr_model": PrecomputedFeatures("pnr"), "oscc_model": PrecomputedFeatures("oscc")}
         return hoi.pnr.TaskFusionMFTransformerDropout(cfg, backbones=bb)
+    if sp.family == "hoi_pnr" and sp.encoder == "simple_vit" and len(sp.segments) == 2:
+        cfg = CfgNode(DATA=CfgNode(TASK="keyframe_localization" if sp.n_out == 16 else "state_change"))
+        bb = {"pnr_model": PrecomputedFeatures("pnr"), "oscc_model": PrecomputedFeatures("oscc")}
+        return hoi.pnr.TaskFusionMFTransformer(cfg, backbones=bb)
     if sp.family == "hoi_pnr" and sp.encoder == "simple_vit":
         cfg = CfgNode(DATA=CfgNode(TASK="keyframe_localization_2loader" if sp.n_out == 16 else "state_change"))
         bb = {"pnr_model": PrecomputedFeatures("pnr"), "oscc_model": PrecomputedFeatures("oscc"),
@@ -155,7 +159,7 @@ def run_ours(case, m, feats, extra, dev, labels=None):
     if sp.family in ("hhi_ttm", "hhi_asd"):
         v = _Feats(f)
         return m(v, v, None, None)
-    if sp.family == "hoi_pnr" and sp.head == "pool_linear":
+    if sp.family == "hoi_pnr" and len(sp.segments) == 2:
         out = m([{"pnr": f["pnr"], "oscc": f["oscc"]}])
         return out.squeeze(1) if sp.n_out == 16 else out.squeeze(2)
     if sp.family == "hoi_pnr":
@@ -199,7 +203,7 @@ def test_container_forward_is_poisoned():
 @pytest.mark.requires_reference
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_l1", "hhi_asd_h128_l1", "hoi_pnr_h128_l6", "hoi_lta_h512_l4",
                                   "hhi_g_ttm_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2", "hoi_lta2_h512_l1",
-                                  "hoi_g_h128_l2", "hoi_g6_lta_h128_l2", "hoi_pnr_vit_h256_l3", "hoi_lta2_h2048_l1"])
+                                  "hoi_g_h128_l2", "hoi_g6_lta_h128_l2", "hoi_pnr_vit_h256_l3", "hoi_lta2_h2048_l1", "hoi_pnr2_vit_h256_l3"])
 def test_same_seed_same_init_as_reference(name):
     """ctor parity: under the same torch seed our module draws exactly the reference's initial weights."""
     from oracle import ref_shims as rs
