@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY - oracles of rows that are NEXT in SURVEY.md §8(f) and have no CUDA path yet.
+"""TEST INFRASTRUCTURE ONLY - fixtures of the rows of SURVEY.md §8(f) that were pinned before their engine paths existed
+(the same rows now also have regular cases in oracle/cases.py; this file keeps the greedy-decoding golden).
 
 HOI EgoT2-g `TaskTranslationPromptTransformer` (HOI/models/multitask/video_model_builder.py:223-275): the restatement in
 translator_oracle.py (hoi_g_*) is pinned here against the real reference class, and a golden (forward logits, CE loss,

@@ -360,7 +360,7 @@ def hoi_lta2_forward(P: Params, action: Tensor, lta: Tensor, n_heads: int = 4, p
 
 
 # --------------------------------------------------------------------------------------
-# HOI EgoT2-g (oracle only so far: the CUDA path is a round-2 row)
+# HOI EgoT2-g (engine path: egot2_b200.hoi.multitask, specs.hoi_g_spec)
 # --------------------------------------------------------------------------------------
 def _hoi_g_tokens(P: Params, tasks: Sequence[Tensor], n_heads: int, p_drop: float, training: bool) -> Tensor:
     """encode_prepare per TASK (HOI/models/multitask/video_model_builder.py:144-148: ln + task_embed[id] + sinusoid that
@@ -443,7 +443,7 @@ def hoi_g_predict_ac(P: Params, pnr: Tensor, oscc: Tensor, slow: Tensor, fast: T
 
 
 # --------------------------------------------------------------------------------------
-# simple_vit translators (oracle only so far: pre-norm / GELU kernels are a round-2 row)
+# simple_vit translators (engine path: csrc/vit.cu, specs.hoi_pnr_vit_spec / hoi_pnr2_vit_spec)
 # --------------------------------------------------------------------------------------
 def simple_vit_transformer(x: Tensor, P: Params, pre: str, heads: int = 8) -> Tensor:
     """HOI/models/pnr/simple_vit.py:55-107 `Transformer`: depth x [x = Attention(x) + x ; x = FeedForward(x) + x], both
