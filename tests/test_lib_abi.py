@@ -43,9 +43,17 @@ def test_struct_layouts_match_header(built):
              "egot2_embed_grads": _lib.EmbedGrads, "egot2_layer_desc": _lib.LayerDesc,
              "egot2_layer_params": _lib.LayerParams, "egot2_layer_grads": _lib.LayerGrads,
              "egot2_layer_saved": _lib.LayerSaved, "egot2_head_desc": _lib.HeadDesc, "egot2_head_in": _lib.HeadIn,
-             "egot2_head_out": _lib.HeadOut, "egot2_head_grads": _lib.HeadGrads}
-    prog = '#include <stdio.h>\n#include "egot2.h"\nint main(){' + "".join(
-        f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
+             "egot2_head_out": _lib.HeadOut, "egot2_head_grads": _lib.HeadGrads,
+             "egot2_decoder_desc": _lib.DecoderDesc, "egot2_decoder_params": _lib.DecoderParams,
+             "egot2_decoder_grads": _lib.DecoderGrads, "egot2_decoder_saved": _lib.DecoderSaved,
+             "egot2_vit_desc": _lib.VitDesc, "egot2_vit_params": _lib.VitParams, "egot2_vit_grads": _lib.VitGrads,
+             "egot2_vit_saved": _lib.VitSaved}
+    # (struct, field) pairs whose byte offsets are compared as well: the last fields of the descriptors that grew
+    offsets = [("egot2_embed_desc", "seed"), ("egot2_embed_desc", "no_ln"), ("egot2_vit_desc", "ln_eps"),
+               ("egot2_vit_saved", "act"), ("egot2_decoder_desc", "seed"), ("egot2_head_desc", "seed")]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "egot2.h"\nint main(){' + "".join(
+        f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "".join(
+        f'printf("{n}.{f} %zu\\n", offsetof({n}, {f}));' for n, f in offsets) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "probe.c")
         open(src, "w").write(prog)
@@ -54,7 +62,11 @@ def test_struct_layouts_match_header(built):
         out = subprocess.check_output([exe], text=True)
     for line in out.strip().splitlines():
         n, size = line.split()
-        assert C.sizeof(names[n]) == int(size), f"{n}: ctypes {C.sizeof(names[n])} != C {size}"
+        if "." in n:
+            st, f = n.split(".")
+            assert getattr(names[st], f).offset == int(size), f"{n}: ctypes offset {getattr(names[st], f).offset} != C {size}"
+        else:
+            assert C.sizeof(names[n]) == int(size), f"{n}: ctypes {C.sizeof(names[n])} != C {size}"
 
 
 def test_no_fallback_without_cuda():
