@@ -1,9 +1,17 @@
 #!/bin/bash
 # First GPU round-trip for code that was written without hardware: the xfail(non-strict) parity tests of
 # oracle.cases.UNVALIDATED_ON_GPU (+ greedy decoding, fused AdamW) with full tracebacks, then the bench lines of the new
-# workloads.  Usage (under gpurun): tools/gpu_pending.sh [tag]      -> gpurun_out/pending_<tag>.log, bench_*_<tag>.json
+# workloads.  Usage (under gpurun): tools/gpu_pending.sh [tag] [memcheck]   -> gpurun_out/pending_<tag>.log, bench_*_<tag>.json
+# "memcheck" as the second argument first runs the fp32 tests of the NEW device code (vit.cu, attention_wide.cu, the H = 2048
+# LayerNorm instantiations) under compute-sanitizer (slow: a few minutes).
 tag=${1:-run}
 mkdir -p gpurun_out
+if [ "$2" = "memcheck" ]; then
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_unvalidated_gpu.py -m gpu -q \
+    --runxfail -k "fp32 and (vit or lta2_h2048)" -p no:cacheprovider > gpurun_out/memcheck_$tag.log 2>&1
+  echo "memcheck rc=$?" >> gpurun_out/memcheck_$tag.log
+  grep -E "ERROR SUMMARY|Invalid|passed|failed|rc=" gpurun_out/memcheck_$tag.log | tail -12
+fi
 # --runxfail: report real pass / fail (with tracebacks) instead of XPASS / XFAIL
 timeout 900 python -m pytest tests/test_zz_unvalidated_gpu.py -m gpu -q --runxfail -rA --tb=short \
   > gpurun_out/pending_$tag.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pending_$tag.log
