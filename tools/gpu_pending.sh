@@ -29,3 +29,8 @@ except Exception as e:
     print("$wl bench parse failed", e)
 PY
 done
+# forward-only throughput (the other half of the metric; bench.py reports the training step)
+for wl in hhi_ttm3_train_b256 hoi_pnr_train_b256 hoi_lta_train_b512; do
+  timeout 300 python tools/bench_infer.py --workload $wl > gpurun_out/infer_${wl}_$tag.json 2> gpurun_out/infer_${wl}_$tag.err
+  tail -c 300 gpurun_out/infer_${wl}_$tag.err; tail -c 400 gpurun_out/infer_${wl}_$tag.json | cut -c1-300
+done
