@@ -126,12 +126,13 @@ def test_hoi_g6_predict_returns_verb_noun_pairs(recorder):
     assert m.predict(vid, ac, "action", predict_verb_only=True) is None
 
 
-def test_hoi_g_training_step_plan(recorder):
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_hoi_g_training_step_plan(dtype, recorder):
     """Unified3TaskTranslation.training_step (HOI/tasks/multitask/video_task.py:182-204): three forward/backward passes
     into one gradient arena (cleared by the first only), one fused AdamW launch."""
     from egot2_b200 import synth
     from egot2_b200.trainer import HoiPromptTranslatorTrainer
-    tr = HoiPromptTranslatorTrainer(hidden=128, heads=4, layers=2, vocab=40, device="cpu", dtype="fp32")
+    tr = HoiPromptTranslatorTrainer(hidden=128, heads=4, layers=2, vocab=40, device="cpu", dtype=dtype)
     sp = tr.spec
     tr.engine.arena.param.fill_(1.0)
     feats, labels = [], []
@@ -151,6 +152,10 @@ def test_hoi_g_training_step_plan(recorder):
     assert adam[5] == pytest.approx(1e-4) and adam[9] == pytest.approx(1e-4)          # lr, decoupled weight decay (:265-268)
     assert float(tr.engine.arena.param[0]) == 1.0                                      # nothing touches the arena on the host
     assert tr._grad_clean
+    assert (adam[12] is not None) == (dtype == "bf16")                                 # the launch also writes the bf16 shadow
+    del recorder[:]
+    tr.train_step(feats, torch.cat(labels))                                            # second step: shadow and gradients are current
+    assert "egot2_cast_f32_to_bf16" not in _names(recorder)
 
 
 @pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n].spec.embed == "task_sinusoid"])
