@@ -20,7 +20,70 @@ from .parallel import allreduce_gradients
 from .specs import TranslatorSpec
 
 
-class PromptTranslatorTrainer:
+def _cur_stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _PromptStepGraphs:
+    """Optional CUDA-graph replay of an EgoT2-g step's forward/backward launch sequence (several hundred small eager
+    launches per step otherwise).  EGOT2_G_GRAPH=1 turns it on; the default stays eager because this path was written after
+    round 1's GPU minutes were spent and has not run on hardware yet.  One graph per `graph_key` (= one fixed set of input
+    buffers); the captured kernels keep their dropout seeds, the library's device-resident dropout epoch (advanced once per
+    step) gives every replay fresh masks; gradient all-reduce (N > 1) and the fused Adam / AdamW stay eager launches behind
+    the replay, which also leaves the gradient arena cleared and the bf16 shadow current for the next replay."""
+
+    def _init_step_graphs(self):
+        import os
+        self.use_graphs = os.environ.get("EGOT2_G_GRAPH", "0") == "1"
+        self._graphs: Dict[int, tuple] = {}
+        self._grad_clean = False
+        self.dropout_epoch = self.use_graphs and os.environ.get("EGOT2_DROPOUT_EPOCH", "1") != "0"
+        if self.dropout_epoch:
+            L.call("egot2_dropout_epoch_enable", 1)
+            L.call("egot2_dropout_epoch_set", 0, _cur_stream(self.device))
+
+    def _capture_graph(self, body):
+        """body(): forward/backward launches accumulating into a CLEAN gradient arena, returns the loss tensor."""
+        cur = torch.cuda.current_stream(self.device)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):                       # warm-up: buffer allocation, workspace sizing
+            body()
+        cur.wait_stream(s)
+        arena = self.engine.arena
+        arena.grad.zero_()
+        if self.engine.dtype == "bf16":
+            arena.refresh_shadow()
+            arena.shadow_fresh = True
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            total = body()
+        return g.replay, total
+
+    def _graph_step(self, body, graph_key: int, decoupled: bool):
+        arena = self.engine.arena
+        entry = self._graphs.get(graph_key)
+        if entry is None:
+            entry = self._graphs[graph_key] = self._capture_graph(body)
+        replay, total = entry
+        if not self._grad_clean:
+            arena.grad.zero_()
+        if self.engine.dtype == "bf16" and not arena.shadow_fresh:
+            arena.refresh_shadow()
+        replay()
+        scale = 1.0
+        if self.world > 1:
+            scale = allreduce_gradients(arena.grad, self.pg)
+        self.engine.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
+                              self.hp["weight_decay"], grad_scale=scale, fused=True, decoupled=decoupled)
+        self._grad_clean = True
+        if self.dropout_epoch:
+            L.call("egot2_dropout_epoch_advance", _cur_stream(self.device))
+        return total
+
+
+class PromptTranslatorTrainer(_PromptStepGraphs):
     """EgoT2-g training step (HHI/tasks/multitask/video_tasktranslation.py:39-66): THREE forwards of one shared model
     per step - 'lam' (LAM tokens only), 'ttm' (lam+ttm+asd tokens) and 'asd' (same encoder, 3-token memory per frame) -
     an unweighted CE over the 7-word vocabulary at the two answer positions of each, loss = sum_i ratio_i * loss_i,
@@ -51,7 +114,7 @@ class PromptTranslatorTrainer:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self.use_graphs = False            # three engines share one workspace: eager launches
+        self._init_step_graphs()           # eager launches unless EGOT2_G_GRAPH=1
         self._h2d: Dict[int, List[torch.Tensor]] = {}
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.loss_kind, self.class_weight = L.LOSS_CE, None
@@ -59,8 +122,26 @@ class PromptTranslatorTrainer:
     def load_state_dict(self, sd):
         self.engine.arena.load_state_dict(sd)
 
+    def _fwd_bwd_all(self, feats, labels, seed0: int):
+        """The three forward/backward passes into a clean gradient arena (the graph-captured body)."""
+        groups = {"lam": list(feats[0:1]), "ttm": list(feats[1:4]), "asd": list(feats[4:7])}
+        off, total = 0, None
+        for ratio, mode in zip(self.ratios, ("lam", "ttm", "asd")):
+            rows = groups[mode][0].shape[0] * (groups[mode][0].shape[1] if mode == "asd" else 1)
+            tgt = labels[off:off + rows]
+            off += rows
+            eng = self.engines[mode]
+            act = eng.forward(groups[mode], training=True, seed=seed0 + len(mode), labels=tgt[:, 1:], loss=L.LOSS_CE,
+                              persistent=True, prompt=tgt[:, :-1])
+            eng.backward(act, dloss_scale=float(ratio), zero_grad=False)
+            l = act.t["loss"][0] * ratio
+            total = l if total is None else total + l
+        return total
+
     def train_step(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, graph_key: Optional[int] = None):
         self.step_count += 1
+        if self.use_graphs and graph_key is not None:
+            return self._graph_step(lambda: self._fwd_bwd_all(feats, labels, 4 * (abs(graph_key) + 1)), graph_key, False)
         groups = {"lam": list(feats[0:1]), "ttm": list(feats[1:4]), "asd": list(feats[4:7])}
         rows = {"lam": groups["lam"][0].shape[0], "ttm": groups["ttm"][0].shape[0],
                 "asd": groups["asd"][0].shape[0] * groups["asd"][0].shape[1]}
@@ -81,12 +162,13 @@ class PromptTranslatorTrainer:
             scale = allreduce_gradients(self.engine.arena.grad, self.pg)
         self.engine.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
                               self.hp["weight_decay"], grad_scale=scale)
+        self._grad_clean = False           # the plain Adam launch leaves the gradients in place
         return total
 
     train_stream_host = None     # bound below to TranslatorTrainer's implementation (same double-buffered host path)
 
 
-class HoiPromptTranslatorTrainer:
+class HoiPromptTranslatorTrainer(_PromptStepGraphs):
     """HOI EgoT2-g training step (Unified3TaskTranslation, HOI/tasks/multitask/video_task.py:182-204): THREE forwards of
     one model per step - a PNR batch, an OSCC batch and an action batch, each the (pnr16, oscc16, slow8, fast8) features
     of its clips plus (B_i, 3) target tokens [task word, answer, answer] - an unweighted CE over the vocabulary at the two
@@ -111,18 +193,33 @@ class HoiPromptTranslatorTrainer:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self.use_graphs = False
+        self._init_step_graphs()           # eager launches unless EGOT2_G_GRAPH=1; _grad_clean: True after a fused AdamW
         self._h2d: Dict[int, List[torch.Tensor]] = {}
         self.copy_stream = None if self.device.type != "cuda" else torch.cuda.Stream(device=self.device)
         self.loss_kind, self.class_weight = L.LOSS_CE, None
-        self._grad_clean = False           # True after a fused AdamW launch (it clears the gradient arena)
 
     def load_state_dict(self, sd):
         self.engine.arena.load_state_dict(sd)
 
+    def _fwd_bwd_all(self, feats, labels, seed0: int):
+        """The three forward/backward passes into a clean gradient arena (the graph-captured body)."""
+        off, total = 0, None
+        for i, ratio in enumerate(self.ratios):
+            group = list(feats[4 * i:4 * i + 4])
+            tgt = labels[off:off + group[0].shape[0]]
+            off += group[0].shape[0]
+            act = self.engine.forward(group, training=True, seed=seed0 + i, labels=tgt[:, 1:], loss=L.LOSS_CE,
+                                      persistent=True, prompt=tgt[:, :-1])
+            self.engine.backward(act, dloss_scale=float(ratio), zero_grad=False)
+            l = act.t["loss"][0] * ratio
+            total = l if total is None else total + l
+        return total
+
     def train_step(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, graph_key: Optional[int] = None):
         assert len(feats) == 12, "three batches x (pnr, oscc, slow, fast)"
         self.step_count += 1
+        if self.use_graphs and graph_key is not None:
+            return self._graph_step(lambda: self._fwd_bwd_all(feats, labels, 4 * (abs(graph_key) + 1)), graph_key, True)
         eng = self.engine
         off, total = 0, None
         for i, ratio in enumerate(self.ratios):

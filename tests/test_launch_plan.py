@@ -187,3 +187,59 @@ def test_simple_vit_layers_replace_the_torch_encoder(recorder):
     assert names.count("egot2_vit_layer_bwd") == 3 and names[-1] == "egot2_embed_bwd"
     for k in m._param_names:
         assert m.get_parameter(k).grad is not None, k
+
+
+@pytest.mark.parametrize("kind", ["hhi", "hoi"])
+def test_prompt_trainer_graph_mode_plan(kind, recorder, monkeypatch):
+    """EGOT2_G_GRAPH=1 (default off, not yet run on hardware): per graph key the three forward/backward passes are captured
+    once and replayed, accumulating into an arena that the fused optimizer launch of the previous step left clean; the
+    dropout epoch advances once per step.  The CUDA-graph capture itself is replaced by an eager stand-in here."""
+    from egot2_b200 import specs, synth, trainer as T
+    monkeypatch.setenv("EGOT2_G_GRAPH", "1")
+    monkeypatch.setattr(T, "_cur_stream", lambda device: 0)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: None)
+    captured = []
+
+    def fake_capture(self, body):
+        captured.append(1)
+        return (lambda: body()), body()
+    monkeypatch.setattr(T._PromptStepGraphs, "_capture_graph", fake_capture)
+    if kind == "hoi":
+        tr = T.HoiPromptTranslatorTrainer(hidden=128, heads=4, layers=1, vocab=40, device="cpu", dtype="bf16")
+        sp = tr.spec
+        feats, labels = [], []
+        for i, B in enumerate((2, 3, 2)):
+            f = synth.make_features(sp, B, seed=60 + i)
+            feats += [f[s.name] for s in sp.segments]
+            labels.append(synth.make_labels(sp, B, seed=60 + i))
+        opt = "egot2_adamw_step_fused"
+    else:
+        tr = T.PromptTranslatorTrainer(hidden=128, heads=4, layers=1, device="cpu", dtype="bf16")
+        feats, labels = [], []
+        for mode, (B, D) in (("lam", (4, 7)), ("ttm", (2, 6)), ("asd", (2, 6))):
+            sp = specs.hhi_g_spec(128, 4, 1, 0.1, mode)
+            seg = (D,) if mode == "lam" else (D, D, D)
+            f = synth.make_features(sp, B, seg, seed=70)
+            feats += [f[s.name] for s in sp.segments]
+            labels.append(synth.make_labels(sp, B, seg, seed=70))
+        opt = "egot2_adam_step_fused"
+    assert tr.use_graphs and tr.dropout_epoch
+    assert _names(recorder)[:2] == ["egot2_dropout_epoch_enable", "egot2_dropout_epoch_set"]
+    lab = torch.cat(labels)
+    for step in range(3):
+        del recorder[:]
+        tr.train_step(feats, lab, graph_key=5)
+        names = _names(recorder)
+        assert names.count(opt) == 1 and names[-2:] == [opt, "egot2_dropout_epoch_advance"]
+        assert tr._grad_clean
+        if step > 0:                                  # replay only: exactly one forward/backward sequence, no re-cast
+            assert names.count("egot2_embed_fwd") == 3 and "egot2_cast_f32_to_bf16" not in names
+    assert len(captured) == 1
+    tr.train_step(feats, lab, graph_key=6)
+    assert len(captured) == 2
+    # an eager step in between (bench.py counts launches that way) must not leave stale state behind
+    tr.use_graphs = False
+    tr.train_step(feats, lab, graph_key=5)
+    tr.use_graphs = True
+    if kind == "hhi":
+        assert not tr._grad_clean                     # plain Adam keeps the gradients: the next replay clears them first
