@@ -34,3 +34,9 @@ for wl in hhi_ttm3_train_b256 hoi_pnr_train_b256 hoi_lta_train_b512; do
   timeout 300 python tools/bench_infer.py --workload $wl > gpurun_out/infer_${wl}_$tag.json 2> gpurun_out/infer_${wl}_$tag.err
   tail -c 300 gpurun_out/infer_${wl}_$tag.err; tail -c 400 gpurun_out/infer_${wl}_$tag.json | cut -c1-300
 done
+# EgoT2-g steps replayed from a CUDA graph (default off until this has passed once)
+for wl in hhi_g_train hoi_g_train; do
+  EGOT2_G_GRAPH=1 timeout 300 python bench.py --workload $wl --skip-cpu-baseline --steps 20 --warmup 3 \
+    > gpurun_out/bench_${wl}_graph_$tag.json 2> gpurun_out/bench_${wl}_graph_$tag.err
+  tail -c 300 gpurun_out/bench_${wl}_graph_$tag.err; tail -c 600 gpurun_out/bench_${wl}_graph_$tag.json | cut -c1-200
+done
