@@ -83,3 +83,50 @@ def test_fused_adamw_matches_torch():
         assert float((p - ref.detach()).abs().max()) < 1e-6
         assert float(g.abs().max()) == 0.0
         assert torch.equal(shadow, p.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("kind", ["hhi", "hoi"])
+def test_prompt_trainer_graph_mode_trains(kind, monkeypatch):
+    """EGOT2_G_GRAPH=1: the replayed EgoT2-g step optimises like the eager one - on one fixed batch the loss falls from its
+    initial value within a few steps in both modes and ends up in the same range (the two modes draw different dropout
+    masks by construction, so the comparison is statistical)."""
+    import torch
+
+    from egot2_b200 import specs, synth, trainer as T
+
+    def batch():
+        feats, labels = [], []
+        if kind == "hoi":
+            sp = specs.hoi_g_spec(128, 4, 1, 0.1, 40)
+            for i, B in enumerate((8, 8, 8)):
+                f = synth.make_features(sp, B, seed=60 + i, dtype=torch.bfloat16)
+                feats += [f[s.name].cuda() for s in sp.segments]
+                labels.append(synth.make_labels(sp, B, seed=60 + i))
+        else:
+            for mode, (B, D) in (("lam", (16, 7)), ("ttm", (4, 10)), ("asd", (4, 10))):
+                sp = specs.hhi_g_spec(128, 4, 1, 0.1, mode)
+                seg = (D,) if mode == "lam" else (D, D, D)
+                f = synth.make_features(sp, B, seg, seed=70, dtype=torch.bfloat16)
+                feats += [f[s.name].cuda() for s in sp.segments]
+                labels.append(synth.make_labels(sp, B, seg, seed=70))
+        return feats, torch.cat(labels).cuda()
+
+    def run(graph):
+        monkeypatch.setenv("EGOT2_G_GRAPH", "1" if graph else "0")
+        if kind == "hoi":
+            tr = T.HoiPromptTranslatorTrainer(hidden=128, heads=4, layers=1, vocab=40, device="cuda:0", dtype="bf16", lr=2e-3)
+            sd = synth.make_state_dict(tr.spec, 3)
+        else:
+            tr = T.PromptTranslatorTrainer(hidden=128, heads=4, layers=1, device="cuda:0", dtype="bf16", lr=2e-3)
+            sd = synth.make_state_dict(tr.spec, 3)
+        tr.load_state_dict(sd)
+        assert tr.use_graphs == graph
+        feats, lab = batch()
+        return [float(tr.train_step(feats, lab, graph_key=0)) for _ in range(12)]
+
+    eager, graph = run(False), run(True)
+    for losses in (eager, graph):
+        assert all(l == l and abs(l) < 1e4 for l in losses)
+        assert min(losses[-3:]) < 0.8 * losses[0]
+    assert abs(graph[0] - eager[0]) < 0.25 * eager[0]
+    assert abs(sum(graph[-3:]) - sum(eager[-3:])) < 0.5 * sum(eager[-3:])
