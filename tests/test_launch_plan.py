@@ -243,3 +243,29 @@ def test_prompt_trainer_graph_mode_plan(kind, recorder, monkeypatch):
     tr.use_graphs = True
     if kind == "hhi":
         assert not tr._grad_clean                     # plain Adam keeps the gradients: the next replay clears them first
+
+
+@pytest.mark.parametrize("wl", ["hhi_ttm3_train_b256", "hoi_pnr_train_b256", "hoi_lta_train_b512"])
+def test_bench_workload_eager_step_plan(wl, recorder, monkeypatch):
+    """The benchmark's trainer on its workload specs (small batch, eager launches): one fused Adam per step, the bf16 shadow
+    is cast once and then kept current by the optimizer launch, `infer` runs the forward only."""
+    import bench
+    from egot2_b200 import synth, trainer as T
+    monkeypatch.setenv("EGOT2_DROPOUT_EPOCH", "0")
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: None)
+    w = bench.WORKLOADS[wl]
+    spec, seg = w["spec"](), w["seg_tokens"]
+    tr = T.TranslatorTrainer(spec, "cpu", "bf16", use_graphs=False)
+    tr.load_state_dict(synth.make_state_dict(spec, 0))
+    f = synth.make_features(spec, 4, seg, seed=1, dtype=torch.bfloat16)
+    fe, la = [f[s.name] for s in spec.segments], synth.make_labels(spec, 4, seg, seed=1)
+    tr.train_step(fe, la)
+    del recorder[:]
+    tr.train_step(fe, la)
+    names = _names(recorder)
+    assert names.count("egot2_adam_step_fused") == 1 and names[-1] == "egot2_adam_step_fused"
+    assert names.count("egot2_encoder_layer_fwd") == spec.layers == names.count("egot2_encoder_layer_bwd")
+    assert "egot2_cast_f32_to_bf16" not in names
+    del recorder[:]
+    out = tr.infer(fe)
+    assert tuple(out.shape) == (4, spec.n_out) and not any(n.endswith("_bwd") for n in _names(recorder))
