@@ -23,7 +23,7 @@ class EmbedDesc(C.Structure):
     _fields_ = [("dtype", i32), ("feat_dtype", i32), ("B", i32), ("T", i32), ("H", i32), ("n_seg", i32),
                 ("seg_tokens", i32 * MAX_SEG), ("seg_in_dim", i32 * MAX_SEG), ("seg_offset", i32 * MAX_SEG),
                 ("seg_has_proj", i32 * MAX_SEG), ("training", i32), ("p_feat", f32), ("p_embed", f32),
-                ("ln_eps", f32), ("seed", u64), ("no_ln", i32)]
+                ("ln_eps", f32), ("seed", u64), ("no_ln", i32), ("feat_drop_tokens", i32)]
 
 
 class EmbedIn(C.Structure):

@@ -412,8 +412,13 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   }
   for (int i = 0; i < 2; ++i) if (used[i]) EGOT2_TRY(side_join(st, sides[i]));
   const size_t n = (size_t)d->B * d->T * d->H;
-  if (d->training && d->p_feat > 0.f)
-    EGOT2_TRY(dropout_inplace(d->dtype, out->z, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+  if (d->training && d->p_feat > 0.f) {
+    if (d->feat_drop_tokens > 0 && d->feat_drop_tokens < d->T)
+      EGOT2_TRY(dropout_prefix_inplace(d->dtype, out->z, n, (size_t)d->T * d->H, (size_t)d->feat_drop_tokens * d->H, d->p_feat,
+                                       site_key(d->seed, SITE_FEAT, 0), st));
+    else
+      EGOT2_TRY(dropout_inplace(d->dtype, out->z, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+  }
   if (d->no_ln) return add_table(d->dtype, n, (size_t)d->T * d->H, out->z, in->tok_table, out->x, st);
   LayerNormArgs l;
   l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = out->z; l.g = in->ln_g; l.b = in->ln_b; l.eps = d->ln_eps;
@@ -462,8 +467,13 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
     l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = saved->z; l.stat = saved->stat; l.g = in->ln_g;
     l.dy = dx; l.dx = dz; l.dg = g->ln_g; l.db = g->ln_b; l.dy_p_drop = pe; l.dy_drop_key = ke;
     EGOT2_TRY(layernorm_bwd(l, st));
-    if (d->training && d->p_feat > 0.f)
-      EGOT2_TRY(dropout_inplace(d->dtype, dz, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+    if (d->training && d->p_feat > 0.f) {
+      if (d->feat_drop_tokens > 0 && d->feat_drop_tokens < d->T)
+        EGOT2_TRY(dropout_prefix_inplace(d->dtype, dz, n, (size_t)d->T * d->H, (size_t)d->feat_drop_tokens * d->H, d->p_feat,
+                                         site_key(d->seed, SITE_FEAT, 0), st));
+      else
+        EGOT2_TRY(dropout_inplace(d->dtype, dz, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
+    }
   }
   const bool par = d->feat_dtype == d->dtype;
   Side* sides[2] = {par ? get_side(0) : nullptr, par ? get_side(1) : nullptr};

@@ -118,8 +118,10 @@ int pool_bwd(int dtype, int B, int T, int H, int pool, int row_tokens, const flo
 int cast_f32_to(int dtype, const float* src, void* dst, size_t n, cudaStream_t st);
 int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t st);
 int zero_f32(float* p, size_t n, cudaStream_t st);
-// x[i] = z[i] + table[i % table_elems]   (vit.cu: the embed stage without LayerNorm)
+// x[i] = z[i] + table[i % table_elems]   (embed_extra.cu: the embed stage without LayerNorm)
 int add_table(int dtype, size_t n, size_t table_elems, const void* z, const float* table, void* x, cudaStream_t st);
+// in-place dropout of the first `prefix` elements of every `period`-element clip (mask index = linear element index)
+int dropout_prefix_inplace(int dtype, void* x, size_t n, size_t period, size_t prefix, float p, uint64_t key, cudaStream_t st);
 // dst[r, 0..ld) = bf16(src[r, 0..n)) followed by zeros (ld >= n)
 int cast_rows_f32_to_bf16(const float* src, int rows, int n, void* dst, int ld, cudaStream_t st);
 

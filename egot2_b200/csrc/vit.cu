@@ -89,14 +89,6 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ u, T* __restrict__ d, size
     d[i] = from_f32<T>(to_f32(d[i]) * gelu_grad_f(to_f32(u[i])));
 }
 
-template <typename T>
-__global__ void add_table_kernel(const T* __restrict__ z, const float* __restrict__ table, T* __restrict__ x, size_t n,
-                                 size_t table_elems) {
-  EGOT2_PDL_ENTER();
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    x[i] = from_f32<T>(to_f32(z[i]) + table[i % table_elems]);
-}
-
 int ew_grid(size_t n) {
   size_t ctas = (n + 255) / 256;
   const size_t cap = (size_t)sm_count() * 16;
@@ -121,17 +113,6 @@ int gelu_bwd(int dt, const void* u, void* d, size_t n, cudaStream_t st) {
 }
 
 }  // namespace
-
-int add_table(int dt, size_t n, size_t table_elems, const void* z, const float* table, void* x, cudaStream_t st) {
-  if (n == 0) return 0;
-  EGOT2_CHECK(table_elems > 0 && table, "add_table: empty table");
-  ProfScope prof(st, "add_table n%zu", n);
-  if (dt == EGOT2_F32) launch(add_table_kernel<float>, dim3(ew_grid(n)), dim3(256), 0, st, (const float*)z, table, (float*)x, n, table_elems);
-  else launch(add_table_kernel<bf16>, dim3(ew_grid(n)), dim3(256), 0, st, (const bf16*)z, table, (bf16*)x, n, table_elems);
-  EGOT2_LAUNCH_CHECK();
-  return 0;
-}
-
 }  // namespace egot2
 
 using namespace egot2;

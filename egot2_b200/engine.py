@@ -273,6 +273,7 @@ class TranslatorEngine:
                 ein.proj_w[k] = self._mat(s.proj + ".weight").data_ptr()
                 ein.proj_b[k] = self._vec(s.proj + ".bias").data_ptr()
         d.no_ln = 0 if sp.embed_ln else 1
+        d.feat_drop_tokens = sp.feat_drop_tokens
         if sp.embed_ln:
             ein.ln_g, ein.ln_b = self._vec("ln.weight").data_ptr(), self._vec("ln.bias").data_ptr()
         ein.tok_table = table.data_ptr()

@@ -214,14 +214,11 @@ class _PNR2TaskDropout(TranslatorBase):
             num_layers=3, enable_nested_tensor=False)
         self.linear_head = nn.Linear(self.feature_dim, self.num_classes)
         self._poison_containers(self.proj1, self.proj2, self.transformer, self.linear_head, self.ln)
-        self._init_translator(hoi_pnr2_spec(self.num_classes, cfg.MODEL.TRANSFORMER_DROPOUT_RATE))
+        # FEAT_DROPOUT_MODE > 0 (:95-96): Dropout(FEAT_DROPOUT_RATE) on the projected PNR features only
+        self._init_translator(hoi_pnr2_spec(self.num_classes, cfg.MODEL.TRANSFORMER_DROPOUT_RATE,
+                                            cfg.MODEL.FEAT_DROPOUT_RATE, self.dpmode))
 
     def forward(self, x):
-        if self.dpmode > 0 and self.training:
-            # reference :95-98 then drops the PNR segment's projected features only; the embed stage has one
-            # feature-dropout switch for all segments, so this (non-default) mode is refused rather than approximated
-            raise L.Egot2Error("TaskFusionMFTransformerDropout: FEAT_DROPOUT_MODE > 0 (per-segment feature dropout) is "
-                               "not built; the shipped default is 0")
         x2 = x.copy()
         pnr_feat = self.pnr_model(x, middle=True)                        # (bs, 16, 8192)
         oscc_feat = self.oscc_model(x2, middle=True)                     # (bs, 16, 8192)

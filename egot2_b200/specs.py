@@ -57,6 +57,7 @@ class TranslatorSpec:
                                         # bias-free attention with `dim_head` independent of `hidden` (HOI/models/pnr/simple_vit.py)
     dim_head: int = 0                   # simple_vit only: inner = heads * dim_head
     embed_ln: bool = True               # False: tokens = projected features + pe, no LayerNorm (2-task simple_vit sibling)
+    feat_drop_tokens: int = 0           # > 0: p_feat reaches only the first N tokens of a clip (2-task PNR, FEAT_DROPOUT_MODE > 0)
 
     @property
     def fixed_tokens(self) -> Optional[int]:
@@ -287,13 +288,15 @@ def hoi_pnr2_vit_spec(n_cls=16) -> TranslatorSpec:
                           0.0, 0.0, 0.0, 0.0, encoder="simple_vit", dim_head=128, embed_ln=False)
 
 
-def hoi_pnr2_spec(n_cls=16, tr_dropout=0.1) -> TranslatorSpec:
+def hoi_pnr2_spec(n_cls=16, tr_dropout=0.1, feat_dropout=0.0, feat_dropout_mode=0) -> TranslatorSpec:
     """2-task PNR/OSCC sibling `TaskFusionMFTransformerDropout` (HOI/models/pnr/video_model_transfer.py:70-105): tokens
     (pnr16, oscc16), H=256, nh=8, FF=2H, 3 layers, shared-nothing head = a bare Linear(H, n_cls) on the mean token (no
-    LayerNorm).  FEAT_DROPOUT_MODE = 0 (the shipped default, configs/pnr/defaults.py:240) = no feature dropout."""
+    LayerNorm).  FEAT_DROPOUT_MODE = 0 (the shipped default, configs/pnr/defaults.py:240) = no feature dropout; any mode
+    > 0 drops the projected PNR features alone (:95-96; the `elif dpmode > 1` branch behind it can never run)."""
     segs = (Segment("pnr", 8192, "proj1", 16), Segment("oscc", 8192, "proj2", 16))
+    on = feat_dropout_mode > 0 and feat_dropout > 0.0
     return TranslatorSpec("hoi_pnr", 256, 8, 512, 3, segs, "learned_pe", "transformer.", "pool_linear", n_cls, False,
-                          tr_dropout, 0.0, 0.0, 0.0)
+                          tr_dropout, 0.0, feat_dropout if on else 0.0, 0.0, feat_drop_tokens=16 if on else 0)
 
 
 def hoi_ar_spec(hidden=128, layers=3, heads=8, dropout=0.1, num_classes=(115, 478), ffn=2048) -> TranslatorSpec:

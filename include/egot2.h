@@ -107,6 +107,9 @@ typedef struct {
   uint64_t seed;
   int32_t no_ln;                      /* 1: no LayerNorm - tokens = projected features + tok_table (the 2-task simple_vit
                                        * sibling, HOI/models/pnr/video_model_transfer.py:63); needs p_feat = p_embed = 0 */
+  int32_t feat_drop_tokens;           /* > 0: p_feat applies to the first feat_drop_tokens tokens of every clip only (the
+                                       * 2-task PNR translator's FEAT_DROPOUT_MODE > 0 drops the PNR segment alone,
+                                       * HOI/models/pnr/video_model_transfer.py:95-96); 0 = all tokens */
 } egot2_embed_desc;
 
 typedef struct {

@@ -269,3 +269,21 @@ def test_bench_workload_eager_step_plan(wl, recorder, monkeypatch):
     del recorder[:]
     out = tr.infer(fe)
     assert tuple(out.shape) == (4, spec.n_out) and not any(n.endswith("_bwd") for n in _names(recorder))
+
+
+def test_pnr2_feature_dropout_mode_reaches_the_pnr_segment_only(recorder):
+    """FEAT_DROPOUT_MODE > 0 (HOI/models/pnr/video_model_transfer.py:95-96): Dropout(FEAT_DROPOUT_RATE) on the projected PNR
+    features alone = the first 16 tokens of every clip; mode 0 (shipped default) = no feature dropout at all."""
+    from egot2_b200 import hoi
+    from egot2_b200.modules import PrecomputedFeatures
+    for mode, want in ((0, (0.0, 0)), (1, (0.5, 16)), (2, (0.5, 16))):
+        cfg = tm.CfgNode(DATA=tm.CfgNode(TASK="keyframe_localization"),
+                         MODEL=tm.CfgNode(FEAT_DROPOUT_RATE=0.5, FEAT_DROPOUT_MODE=mode, TRANSFORMER_DROPOUT_RATE=0.1))
+        m = hoi.pnr.TaskFusionMFTransformerDropout(cfg, backbones={"pnr_model": PrecomputedFeatures("pnr"),
+                                                                   "oscc_model": PrecomputedFeatures("oscc")})
+        m.train()
+        del recorder[:]
+        m([{"pnr": torch.randn(2, 16, 8192), "oscc": torch.randn(2, 16, 8192)}])
+        (eargs,) = [a for n, a in recorder if n == "egot2_embed_fwd"]
+        d = C.cast(eargs[0], C.POINTER(L.EmbedDesc)).contents
+        assert d.training == 1 and (round(d.p_feat, 6), d.feat_drop_tokens) == want

@@ -130,3 +130,28 @@ def test_prompt_trainer_graph_mode_trains(kind, monkeypatch):
         assert min(losses[-3:]) < 0.8 * losses[0]
     assert abs(graph[0] - eager[0]) < 0.25 * eager[0]
     assert abs(sum(graph[-3:]) - sum(eager[-3:])) < 0.5 * sum(eager[-3:])
+
+
+def test_pnr2_feature_dropout_hits_only_the_pnr_tokens():
+    """egot2_embed_desc.feat_drop_tokens: in train mode about p of the projected PNR features (tokens 0..15 of every clip)
+    are zero in the saved LayerNorm input, none of the OSCC ones; the same seed reproduces the mask."""
+    import torch
+
+    from egot2_b200 import specs, synth
+    from egot2_b200.engine import TranslatorEngine
+    sp = specs.hoi_pnr2_spec(16, 0.1, 0.5, 1)
+    eng = TranslatorEngine(sp, "cuda:0", "fp32")
+    eng.arena.load_state_dict(synth.make_state_dict(sp, 5))
+    f = synth.make_features(sp, 8, seed=5)
+    feats = [f[s.name].cuda() for s in sp.segments]
+    z1 = eng.forward(feats, training=True, seed=11).t["z"].clone()
+    z2 = eng.forward(feats, training=True, seed=11).t["z"].clone()
+    z3 = eng.forward(feats, training=True, seed=12).t["z"].clone()
+    assert torch.equal(z1, z2) and not torch.equal(z1, z3)
+    frac_pnr = float((z1[:, :16] == 0).float().mean())
+    assert abs(frac_pnr - 0.5) < 0.03, frac_pnr
+    assert float((z1[:, 16:] == 0).float().mean()) == 0.0
+    z_eval = eng.forward(feats, training=False).t["z"]
+    kept = z1[:, :16] != 0
+    assert torch.allclose(z1[:, :16][kept], 2.0 * z_eval[:, :16][kept], rtol=1e-5, atol=1e-6)       # kept values scaled by 1/(1-p)
+    assert torch.equal(z1[:, 16:], z_eval[:, 16:])
