@@ -35,7 +35,10 @@ __global__ void epoch_advance_kernel(unsigned long long* slot, unsigned long lon
   EGOT2_PDL_ENTER();
   if (threadIdx.x == 0 && blockIdx.x == 0) *slot += add;
 }
-unsigned long long* g_epoch_slot = nullptr;
+constexpr int kMaxDev = 64;
+unsigned long long* g_epoch_slots[kMaxDev] = {};      // one slot per device (allocated on first enable on that device)
+int cur_dev() { int d = 0; return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < kMaxDev) ? d : 0; }
+#define g_epoch_slot (g_epoch_slots[cur_dev()])
 }  // namespace
 
 bool pdl_enabled() {
@@ -176,8 +179,12 @@ struct Side {
   cudaEvent_t join = nullptr;
 };
 Side* get_side(int idx) {
-  static Side sides[3];
-  static int state = 0;      // 0 untried, 1 ok, -1 disabled / failed
+  // per device: streams and events belong to the device that was current when they were created
+  static Side all_sides[kMaxDev][3];
+  static int states[kMaxDev] = {};      // 0 untried, 1 ok, -1 disabled / failed
+  const int dev = cur_dev();
+  Side* sides = all_sides[dev];
+  int& state = states[dev];
   if (state == 0) {
     state = 1;
     if (env_is("EGOT2_STREAMS", "0")) state = -1;

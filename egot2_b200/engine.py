@@ -32,7 +32,24 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream() -> int:
+    """Current stream of the CURRENT device: every public engine entry point runs under torch.cuda.device(engine.device)
+    (`_on_device`), so this is the engine's device whatever the caller's current device is."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device(fn):
+    """Run an engine method with the engine's device current: the library's launches, its per-device side streams and
+    dropout-epoch slot and torch's current stream then all refer to `self.device`, also for an engine on cuda:1 in a
+    process whose current device is cuda:0."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if self.device.type != "cuda":            # CPU only under tests/abi_emulator.py (host-wiring checks)
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 class ParamArena:
@@ -112,6 +129,7 @@ class ParamArena:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {name: self.view(name).clone() for name in self.shapes}
 
+    @_on_device
     def refresh_shadow(self):
         """fp32 -> bf16 shadow of the whole arena (one launch)."""
         if self.shadow is None:
@@ -171,6 +189,7 @@ class TranslatorEngine:
         self.pe_buffer: Optional[torch.Tensor] = None     # HHI: (max_len, H) sinusoid table (pos_embed.pe)
         self.lossav: Optional[Dict[str, torch.Tensor]] = None
         self._ws: Optional[torch.Tensor] = None
+        self._ws_retired: List[torch.Tensor] = []     # outgrown workspaces: CUDA graphs captured earlier still point into them
         self._persistent: Dict[Tuple, Activations] = {}
 
     # ------------------------------------------------------------------ helpers
@@ -185,6 +204,10 @@ class TranslatorEngine:
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
+            if self._ws is not None:
+                # never hand an outgrown workspace back to the allocator: a graph captured for a smaller batch has its raw
+                # pointer baked in and would scribble over whatever reuses the block
+                self._ws_retired.append(self._ws)
             self._ws = torch.empty(int(nbytes), device=self.device, dtype=torch.uint8)
         return self._ws
 
@@ -193,6 +216,7 @@ class TranslatorEngine:
         self.pe_buffer = pe.reshape(pe.shape[0], -1).to(device=self.device, dtype=torch.float32).contiguous()
 
     # ------------------------------------------------------------------ forward
+    @_on_device
     def forward(self, feats: Sequence[torch.Tensor], training: bool = False, seed: int = 0,
                 labels: Optional[torch.Tensor] = None, loss: int = L.LOSS_NONE,
                 class_weight: Optional[torch.Tensor] = None, persistent: bool = False,
@@ -542,6 +566,7 @@ class TranslatorEngine:
         t["out"] = logits
         return act
 
+    @_on_device
     def decode_again(self, act: Activations, prompt: torch.Tensor) -> Activations:
         """Greedy decoding step of EgoT2-g (predict_ac, HOI/models/multitask/video_model_builder.py:264-275): only the
         decoder and the vocabulary head run, for a new (longer) prompt, over the encoder memory `act` already holds.
@@ -609,6 +634,7 @@ class TranslatorEngine:
                 setattr(lp, f, self._vec(p + n).data_ptr())
 
     # ------------------------------------------------------------------ backward
+    @_on_device
     def backward(self, act: Activations, dout: Optional[torch.Tensor] = None, dloss_scale: float = 1.0,
                  grad: Optional[torch.Tensor] = None, zero_grad: bool = True,
                  want_dfeat: Sequence[bool] = (), stage: str = "all") -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
@@ -715,6 +741,7 @@ class TranslatorEngine:
         return grad, dfeats
 
     # ------------------------------------------------------------------ fused optimizer
+    @_on_device
     def adam_step(self, state: Dict[str, torch.Tensor], step: int, lr: float = 5e-4, betas=(0.9, 0.999),
                   eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0, fused: bool = False,
                   step_dev: Optional[torch.Tensor] = None, decoupled: bool = False):

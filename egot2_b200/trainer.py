@@ -24,6 +24,12 @@ def _cur_stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _dev_guard(device):
+    """Make `device` current for library calls that own per-device state (side streams, the dropout-epoch slot)."""
+    import contextlib
+    return torch.cuda.device(device) if torch.device(device).type == "cuda" else contextlib.nullcontext()
+
+
 class _PromptStepGraphs:
     """Optional CUDA-graph replay of an EgoT2-g step's forward/backward launch sequence (several hundred small eager
     launches per step otherwise).  EGOT2_G_GRAPH=1 turns it on; the default stays eager because this path was written after
@@ -39,8 +45,9 @@ class _PromptStepGraphs:
         self._grad_clean = False
         self.dropout_epoch = self.use_graphs and os.environ.get("EGOT2_DROPOUT_EPOCH", "1") != "0"
         if self.dropout_epoch:
-            L.call("egot2_dropout_epoch_enable", 1)
-            L.call("egot2_dropout_epoch_set", 0, _cur_stream(self.device))
+            with _dev_guard(self.device):      # the slot and the per-translation-unit pointers are per device
+                L.call("egot2_dropout_epoch_enable", 1)
+                L.call("egot2_dropout_epoch_set", 0, _cur_stream(self.device))
 
     def _capture_graph(self, body):
         """body(): forward/backward launches accumulating into a CLEAN gradient arena, returns the loss tensor."""
@@ -79,7 +86,8 @@ class _PromptStepGraphs:
                               self.hp["weight_decay"], grad_scale=scale, fused=True, decoupled=decoupled)
         self._grad_clean = True
         if self.dropout_epoch:
-            L.call("egot2_dropout_epoch_advance", _cur_stream(self.device))
+            with _dev_guard(self.device):
+                L.call("egot2_dropout_epoch_advance", _cur_stream(self.device))
         return total
 
 
@@ -126,12 +134,12 @@ class PromptTranslatorTrainer(_PromptStepGraphs):
         """The three forward/backward passes into a clean gradient arena (the graph-captured body)."""
         groups = {"lam": list(feats[0:1]), "ttm": list(feats[1:4]), "asd": list(feats[4:7])}
         off, total = 0, None
-        for ratio, mode in zip(self.ratios, ("lam", "ttm", "asd")):
+        for mi, (ratio, mode) in enumerate(zip(self.ratios, ("lam", "ttm", "asd"))):
             rows = groups[mode][0].shape[0] * (groups[mode][0].shape[1] if mode == "asd" else 1)
             tgt = labels[off:off + rows]
             off += rows
             eng = self.engines[mode]
-            act = eng.forward(groups[mode], training=True, seed=seed0 + len(mode), labels=tgt[:, 1:], loss=L.LOSS_CE,
+            act = eng.forward(groups[mode], training=True, seed=seed0 + mi, labels=tgt[:, 1:], loss=L.LOSS_CE,
                               persistent=True, prompt=tgt[:, :-1])
             eng.backward(act, dloss_scale=float(ratio), zero_grad=False)
             l = act.t["loss"][0] * ratio
@@ -147,11 +155,11 @@ class PromptTranslatorTrainer(_PromptStepGraphs):
                 "asd": groups["asd"][0].shape[0] * groups["asd"][0].shape[1]}
         off, total = 0, None
         first = True
-        for ratio, mode in zip(self.ratios, ("lam", "ttm", "asd")):
+        for mi, (ratio, mode) in enumerate(zip(self.ratios, ("lam", "ttm", "asd"))):
             tgt = labels[off:off + rows[mode]]
             off += rows[mode]
             eng = self.engines[mode]
-            act = eng.forward(groups[mode], training=True, seed=self.step_count * 4 + len(mode), labels=tgt[:, 1:],
+            act = eng.forward(groups[mode], training=True, seed=self.step_count * 4 + mi, labels=tgt[:, 1:],
                               loss=L.LOSS_CE, persistent=True, prompt=tgt[:, :-1])
             eng.backward(act, dloss_scale=float(ratio), zero_grad=first)      # one arena, accumulated over the three
             first = False
@@ -298,7 +306,7 @@ class TranslatorTrainer:
         # epoch (advanced once per step, XORed into every key at execution time) gives every replay fresh masks.
         self.dropout_epoch = bool(use_graphs) and os.environ.get("EGOT2_DROPOUT_EPOCH", "1") != "0"
         if self.dropout_epoch:
-            with torch.cuda.device(self.device):
+            with _dev_guard(self.device):
                 L.call("egot2_dropout_epoch_enable", 1)
                 L.call("egot2_dropout_epoch_set", 0, torch.cuda.current_stream(self.device).cuda_stream)
         self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
@@ -378,12 +386,17 @@ class TranslatorTrainer:
         return act.t["loss"][0]
 
     def _capture(self, feats, labels, key):
-        labels = labels.to(self.device, torch.int64).contiguous()
+        # labels are NOT converted here: engine.forward() does it inside the captured region, so a caller's int32 / strided
+        # label buffer is re-read (and re-converted) on every replay instead of being frozen at capture-time values
+        if self.engine.spec.p_layer > 0 or self.engine.spec.p_embed > 0 or self.engine.spec.p_feat > 0 or self.engine.spec.p_head > 0:
+            if not self.dropout_epoch:
+                raise L.Egot2Error("graph replay with training dropout needs the device-resident dropout epoch "
+                                   "(EGOT2_DROPOUT_EPOCH=0 would replay ONE frozen mask): use use_graphs=False")
         # warm-up on a side stream (allocations, workspace sizing), then capture
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self._fwd_bwd(feats, labels, seed=1 + key)
+            self._fwd_bwd(feats, labels, seed=self._graph_seed(key))
         torch.cuda.current_stream().wait_stream(s)
         # the captured sequence is the steady state: shadow current and gradient arena cleared by the previous step's
         # fused Adam, so neither the cast nor the fill is part of the graph
@@ -404,7 +417,7 @@ class TranslatorTrainer:
             torch.cuda.synchronize(self.device)
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
-                act = self._fwd_bwd(feats, labels, seed=1 + key, stage="pre_embed")
+                act = self._fwd_bwd(feats, labels, seed=self._graph_seed(key), stage="pre_embed")
             with torch.cuda.graph(g2, pool=g1.pool()):
                 self.engine.backward(act, zero_grad=False, stage="embed")
             self._graphs[key] = (g1, g2, act)
@@ -417,7 +430,7 @@ class TranslatorTrainer:
                 self._bump_stream.wait_stream(cur)
                 with torch.cuda.stream(self._bump_stream):
                     self._step_dev.add_(1)
-            act = self._fwd_bwd(feats, labels, seed=1 + key)
+            act = self._fwd_bwd(feats, labels, seed=self._graph_seed(key))
             if self.graph_update:
                 cur.wait_stream(self._bump_stream)
                 # every dropout consumer of this step has been enqueued before this point: the epoch advances for the
@@ -430,9 +443,16 @@ class TranslatorTrainer:
         self._graphs[key] = (g, act)
         return g, act
 
+    @staticmethod
+    def _graph_seed(key: int) -> int:
+        """Dropout seed a graph is captured with: positive, distinct for every key (device pool keys are >= 0, the host
+        path's double-buffer slots are -(slot + 1))."""
+        return 2 * abs(int(key)) + (1 if key >= 0 else 2) + 1000
+
     def _advance_epoch(self):
         if self.dropout_epoch:
-            L.call("egot2_dropout_epoch_advance", torch.cuda.current_stream(self.device).cuda_stream)      # current = the stream in effect
+            with _dev_guard(self.device):
+                L.call("egot2_dropout_epoch_advance", torch.cuda.current_stream(self.device).cuda_stream)      # current = the stream in effect
 
     def _reduce_and_update(self, step_dev: Optional[torch.Tensor] = None):
         eng = self.engine

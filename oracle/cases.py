@@ -65,12 +65,9 @@ CASES = {c.name: c for c in [
 ]}
 
 
-#: cases added after the round's GPU budget was spent: CPU-side checks (state_dict keys, same-seed init, oracle pinned
-#: against the reference class, golden) are green, the GPU parity tests for them are marked xfail(strict=False) until
-#: they have run on hardware once (tests/test_zz_unvalidated_gpu.py)
-# (hoi_lta2_h512_l1 went this way: 4 x XPASS on a B200 at the end of round 1, then moved into the regular lists)
-UNVALIDATED_ON_GPU = {"hoi_g_h128_l2", "hoi_g6_clip_h128_l1", "hoi_g6_lta_h128_l2", "hoi_pnr_vit_h256_l3", "hoi_lta2_h2048_l1",
-                      "hoi_pnr2_vit_h256_l3"}
+#: cases whose GPU parity has not run on hardware yet.  Empty since round 2: every case above has passed `-m gpu` on a
+#: B200 in fp32 and bf16 and sits in the regular parametrisations; anything that regresses turns the suite red.
+UNVALIDATED_ON_GPU: set = set()
 
 
 def case_inputs(case: Case):
@@ -151,3 +148,33 @@ def grad_digest(g: torch.Tensor) -> torch.Tensor:
     n = f.numel()
     idx = torch.linspace(0, n - 1, 61).long()
     return torch.cat([torch.stack([f.sum(), f.norm(), f.abs().max()]), f[idx]]).float()
+
+
+_BF16_COND: Dict[str, Dict[str, float]] = {}
+
+
+def bf16_conditioning(case: Case) -> Dict[str, float]:
+    """How ill-conditioned each parameter gradient of `case` is under bf16 rounding: the relative L2 error that STOCK
+    torch bf16 arithmetic (CPU autocast of this same restatement: bf16 matmuls, fp32 LayerNorm / softmax / loss) makes
+    against the fp32 gradients.  Most tensors sit at 1-3e-2; a few are inherently worse - e.g. the first decoder layer's
+    self-attention in-projection of `hoi_g_h128_l2` (a causal 2-token softmax over 3 clips: 0.17-0.19, embedding.weight
+    0.09) - and a bf16 kernel cannot be asked to beat the arithmetic it is specified in.  The bf16 GPU tests therefore
+    bound every gradient by max(floor, 1.5 x this figure); fp32 mode has no such allowance."""
+    if case.name in _BF16_COND:
+        return _BF16_COND[case.name]
+    sd, feats, labels, extra = case_inputs(case)
+    names = list(sd.keys())
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    _, l32 = oracle_forward_loss(case, P, feats, labels, extra)
+    g32 = torch.autograd.grad(l32, [P[k] for k in names], allow_unused=True)
+    Pb = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        _, lb = oracle_forward_loss(case, Pb, feats, labels, extra)
+    gb = torch.autograd.grad(lb.float(), [Pb[k] for k in names], allow_unused=True)
+    out = {}
+    for k, a, b in zip(names, g32, gb):
+        if a is None or b is None:
+            continue
+        out[k] = float((b.float() - a).norm()) / (float(a.norm()) + 1e-12)
+    _BF16_COND[case.name] = out
+    return out

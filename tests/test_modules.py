@@ -227,7 +227,8 @@ def test_same_seed_same_init_as_reference(name):
 @pytest.mark.parametrize("name", ["hhi2_h128_l1", "hhi3_h128_d30", "hhi_asd_h128_l1", "hoi_pnr_h128_l6",
                                   "hoi_pnr_raw_maps", "hoi_lta_h512_l4", "hhi_g_lam_h128_l2", "hhi_g_ttm_h128_l2",
                                   "hhi_g_asd_h128_l2", "hoi_pnr2_h256_l3", "hoi_ar_h128_l3", "hoi_ar2_h128_l2",
-                                  "hoi_lta2_h512_l1"])
+                                  "hoi_lta2_h512_l1", "hoi_g_h128_l2", "hoi_g6_clip_h128_l1", "hoi_g6_lta_h128_l2",
+                                  "hoi_pnr_vit_h256_l3", "hoi_lta2_h2048_l1", "hoi_pnr2_vit_h256_l3"])
 def test_module_forward_backward_vs_oracle(name, dtype):
     from oracle import translator_oracle as O
     warnings.filterwarnings("ignore")
@@ -242,7 +243,9 @@ def test_module_forward_backward_vs_oracle(name, dtype):
     out = run_ours(case, m, feats, extra, dev, labels)
     P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     o_out, o_loss = oracle_forward_loss(case, P, feats, labels, extra)
-    tol_o, tol_g = (2e-4, 2e-3) if dtype == "fp32" else (2e-2, 0.1)
+    tol_o, tol_g = (2e-4, 2e-3) if dtype == "fp32" else (2e-2, 4e-2)
+    from oracle.cases import bf16_conditioning
+    cond = bf16_conditioning(case) if dtype == "bf16" else {}
     scale = float(o_out.abs().max())
     assert out.shape == tuple(o_out.reshape(out.shape).shape)
     assert float((out.float().cpu() - o_out.detach().reshape(out.shape)).abs().max()) <= tol_o * scale
@@ -278,7 +281,8 @@ def test_module_forward_backward_vs_oracle(name, dtype):
         assert g is not None, k
         err = float((g.cpu() - g_ref).norm()) / (float(g_ref.norm()) + 1e-12)
         # fp32: an isolated ReLU-gate flip (pre-activation within rounding of zero) is legitimate, see test_gpu_parity.py
-        assert err <= (3 * tol_g if dtype == "fp32" else tol_g), f"{k}: rel L2 err {err:.3e}"
+        # bf16: bounded by what stock torch bf16 arithmetic loses on this tensor (oracle.cases.bf16_conditioning)
+        assert err <= (3 * tol_g if dtype == "fp32" else max(tol_g, 2.0 * cond.get(k, 0.0))), f"{k}: rel L2 err {err:.3e}"
 
 
 @pytest.mark.gpu
