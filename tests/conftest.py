@@ -28,3 +28,17 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "requires_reference" in item.keywords and not ref:
             item.add_marker(pytest.mark.skip(reason="/root/reference not present"))
+
+
+@pytest.fixture(autouse=True)
+def _reset_dropout_epoch(request):
+    """Trainers switch the library's device-resident dropout epoch on for the whole process (and advance it); the tests
+    that regenerate the documented masks on the host assume epoch 0.  Reset before every GPU test (trainers re-enable it in
+    their constructors)."""
+    if "gpu" in request.keywords:
+        import torch
+        if torch.cuda.is_available():
+            from egot2_b200 import _lib as L
+            L.call("egot2_dropout_epoch_host", 0)
+            L.call("egot2_dropout_epoch_enable", 0)
+    yield

@@ -282,7 +282,7 @@ def test_module_forward_backward_vs_oracle(name, dtype):
         err = float((g.cpu() - g_ref).norm()) / (float(g_ref.norm()) + 1e-12)
         # fp32: an isolated ReLU-gate flip (pre-activation within rounding of zero) is legitimate, see test_gpu_parity.py
         # bf16: bounded by what stock torch bf16 arithmetic loses on this tensor (oracle.cases.bf16_conditioning)
-        assert err <= (3 * tol_g if dtype == "fp32" else max(tol_g, 2.0 * cond.get(k, 0.0))), f"{k}: rel L2 err {err:.3e}"
+        assert err <= (3 * tol_g if dtype == "fp32" else max(tol_g, 2.5 * cond.get(k, 0.0))), f"{k}: rel L2 err {err:.3e}"
 
 
 @pytest.mark.gpu
