@@ -136,6 +136,8 @@ SIGNATURES = {
     "egot2_dropout_epoch_host": (C.c_int, [u64]),
     "egot2_pnr_metrics": (C.c_int, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "egot2_prof_enable": (C.c_int, [C.c_int]),
+    "egot2_side_defer": (C.c_int, [C.c_int]),
+    "egot2_side_join_all": (C.c_int, [vp]),
     "egot2_timeline_set": (C.c_int, [vp]),
     "egot2_prof_report": (C.c_int, [C.c_char_p, sz]),
     "egot2_embed_workspace_bytes": (sz, [P(EmbedDesc), C.c_int]),

@@ -177,7 +177,16 @@ struct Side {
   cudaStream_t s = nullptr;
   cudaEvent_t fork[8] = {};
   cudaEvent_t join = nullptr;
+  // deferred joins (egot2_side_defer): instead of joining at the end of an encoder-layer backward, the layer records a
+  // `pend` event per workspace it used; the next layer backward that is handed the SAME workspace waits for it first.
+  // With the caller alternating two workspaces, a layer's parameter-gradient backlog overlaps the whole next layer (or
+  // the embedding backward) instead of stalling the data-gradient chain at the layer boundary.
+  cudaEvent_t pend[2] = {};
+  const void* pend_ws[2] = {nullptr, nullptr};
+  int pend_next = 0;
+  bool dirty = false;
 };
+int g_side_defer[kMaxDev] = {};
 Side* get_side(int idx) {
   // per device: streams and events belong to the device that was current when they were created
   static Side all_sides[kMaxDev][3];
@@ -193,6 +202,8 @@ Side* get_side(int idx) {
       for (int k = 0; k < 8 && state == 1; ++k)
         if (cudaEventCreateWithFlags(&sides[i].fork[k], cudaEventDisableTiming) != cudaSuccess) state = -1;
       if (state == 1 && cudaEventCreateWithFlags(&sides[i].join, cudaEventDisableTiming) != cudaSuccess) state = -1;
+      for (int k = 0; k < 2 && state == 1; ++k)
+        if (cudaEventCreateWithFlags(&sides[i].pend[k], cudaEventDisableTiming) != cudaSuccess) state = -1;
     }
   }
   return state == 1 ? &sides[idx] : nullptr;
@@ -222,6 +233,28 @@ int side_join(cudaStream_t main, Side* sd) {
   if (!sd || prof_enabled()) return 0;
   EGOT2_CUDA(cudaEventRecord(sd->join, sd->s));
   EGOT2_CUDA(cudaStreamWaitEvent(main, sd->join, 0));
+  sd->dirty = false;
+  sd->pend_ws[0] = sd->pend_ws[1] = nullptr;
+  return 0;
+}
+bool side_deferred() { return g_side_defer[cur_dev()] != 0 && !prof_enabled(); }
+// end of a layer backward in deferred mode: remember that side work reading `ws` is in flight
+int side_mark_pending(Side* sd, const void* ws) {
+  if (!sd) return 0;
+  int slot = sd->pend_ws[0] == ws ? 0 : sd->pend_ws[1] == ws ? 1 : (sd->pend_next++ & 1);
+  EGOT2_CUDA(cudaEventRecord(sd->pend[slot], sd->s));
+  sd->pend_ws[slot] = ws;
+  sd->dirty = true;
+  return 0;
+}
+// start of a layer backward in deferred mode: side work that still reads this workspace must finish before it is rewritten
+int side_wait_pending(cudaStream_t main, Side* sd, const void* ws) {
+  if (!sd) return 0;
+  for (int k = 0; k < 2; ++k)
+    if (sd->pend_ws[k] == ws) {
+      EGOT2_CUDA(cudaStreamWaitEvent(main, sd->pend[k], 0));
+      sd->pend_ws[k] = nullptr;
+    }
   return 0;
 }
 
@@ -332,8 +365,25 @@ extern "C" int egot2_prof_report(char* buf, size_t buf_bytes) {
 }
 
 // =============================================================================== embed stage
+namespace {
+// Split-K projections into an fp32 accumulator + one finishing pass (embed_extra.cu) pay off when a projection is a long-K,
+// few-tile GEMM (HOI PNR / OSCC: 8192 -> 128 over clips x 16 rows = 32 output tiles for 148 SMs).
+bool embed_splitk(const egot2_embed_desc* d) {
+  if (env_is("EGOT2_EMBED_SPLITK", "0")) return false;
+  if (d->no_ln || !embed_finish_supported(d->dtype, d->H)) return false;
+  if (env_is("EGOT2_EMBED_SPLITK", "1")) return true;
+  for (int k = 0; k < d->n_seg; ++k) {
+    if (!d->seg_has_proj[k] || d->seg_tokens[k] == 0) continue;
+    const long long tiles = (((long long)d->B * d->seg_tokens[k] + 127) / 128) * ((d->H + 127) / 128);
+    if (d->seg_in_dim[k] >= 2048 && tiles * 2 <= sm_count()) return true;
+  }
+  return false;
+}
+}  // namespace
+
 extern "C" size_t egot2_embed_workspace_bytes(const egot2_embed_desc* d, int backward) {
   size_t n = 256;
+  if (!backward && embed_splitk(d)) n += align_up((size_t)d->B * d->T * d->H * 4);
   if (!backward && d->feat_dtype != d->dtype) {
     size_t mx = 0;
     for (int k = 0; k < d->n_seg; ++k) {
@@ -379,8 +429,20 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   const size_t es = dtype_size(d->dtype);
   Carver ws(workspace, ws_bytes);
   void* cast_buf = nullptr;
+  const bool splitk = embed_splitk(d);
+  float* zf = nullptr;
+  if (splitk) {
+    zf = (float*)ws.take((size_t)d->B * d->T * d->H * 4);
+    EGOT2_CHECK(ws.ok(), "embed_fwd: workspace too small (%zu < %zu)", ws_bytes, ws.off);
+    EGOT2_CUDA(cudaMemsetAsync(zf, 0, (size_t)d->B * d->T * d->H * 4, st));
+  }
   if (d->feat_dtype != d->dtype) {
-    cast_buf = ws.take(egot2_embed_workspace_bytes(d, 0) - 256);
+    size_t mx = 0;
+    for (int k = 0; k < d->n_seg; ++k) {
+      const size_t e = (size_t)d->B * d->seg_tokens[k] * d->seg_in_dim[k];
+      if (e > mx) mx = e;
+    }
+    cast_buf = ws.take(mx * dtype_size(d->dtype));
     EGOT2_CHECK(ws.ok(), "embed_fwd: workspace too small (%zu < %zu)", ws_bytes, ws.off);
   }
   // the per-task projections are independent: task 0 stays on `st`, the others alternate over two side streams
@@ -411,7 +473,15 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
       g.C = zk; g.ldc = d->H; g.c_rpg = Dk; g.c_gstride = d->T;
       g.bias = in->proj_b[k];
       g.in_dtype = d->dtype; g.out_dtype = d->dtype;
+      if (splitk) {       // this segment's rows of the fp32 accumulator; the first split adds the bias
+        g.C = zf + (size_t)d->seg_offset[k] * d->H; g.out_dtype = EGOT2_F32; g.accumulate = 1;
+        g.split_k = suggest_split_k(g.M, g.N, g.K);
+      }
       EGOT2_TRY(gemm(g, sk));
+    } else if (splitk) {  // pass-through segment: widen into the accumulator (rare: LTA action features)
+      for (int b = 0; b < d->B; ++b)
+        EGOT2_TRY(cast_to_f32(d->dtype, (const char*)feat + (size_t)b * Dk * d->H * es, zf + ((size_t)b * d->T + d->seg_offset[k]) * d->H,
+                              (size_t)Dk * d->H, sk));
     } else {
       EGOT2_CUDA(cudaMemcpy2DAsync(zk, (size_t)d->T * d->H * es, feat, (size_t)Dk * d->H * es, (size_t)Dk * d->H * es,
                                    d->B, cudaMemcpyDeviceToDevice, sk));
@@ -419,6 +489,10 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   }
   for (int i = 0; i < 2; ++i) if (used[i]) EGOT2_TRY(side_join(st, sides[i]));
   const size_t n = (size_t)d->B * d->T * d->H;
+  if (splitk)
+    return embed_finish(d->B * d->T, d->T, d->H, zf, (d->feat_drop_tokens > 0 && d->feat_drop_tokens < d->T) ? d->feat_drop_tokens : 0,
+                        d->training ? d->p_feat : 0.f, site_key(d->seed, SITE_FEAT, 0), in->ln_g, in->ln_b, d->ln_eps, in->tok_table,
+                        d->training ? d->p_embed : 0.f, site_key(d->seed, SITE_EMBED, 0), out->z, out->stat, out->x, st);
   if (d->training && d->p_feat > 0.f) {
     if (d->feat_drop_tokens > 0 && d->feat_drop_tokens < d->T)
       EGOT2_TRY(dropout_prefix_inplace(d->dtype, out->z, n, (size_t)d->T * d->H, (size_t)d->feat_drop_tokens * d->H, d->p_feat,
@@ -669,6 +743,12 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   Side* sd0 = get_side(0);
   Side* sd1 = get_side(1);
   Side* sd2 = get_side(2);
+  const bool defer = side_deferred();
+  if (defer) {
+    EGOT2_TRY(side_wait_pending(st, sd0, workspace));
+    EGOT2_TRY(side_wait_pending(st, sd1, workspace));
+    EGOT2_TRY(side_wait_pending(st, sd2, workspace));
+  }
 
   // 1. through norm2: d1 = dL/dy2, and (same kernel) d2 = dropout2 mask applied to d1 = dL/d(linear2 out)
   const void* d2 = w.d1;
@@ -749,9 +829,24 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
     m.C = dx_in; m.ldc = H; m.residual = w.d4; m.ldr = H; m.in_dtype = dt; m.out_dtype = dt;
     EGOT2_TRY(gemm(m, st));
   }
+  if (defer) {
+    EGOT2_TRY(side_mark_pending(sd0, workspace));
+    EGOT2_TRY(side_mark_pending(sd1, workspace));
+    return side_mark_pending(sd2, workspace);
+  }
   EGOT2_TRY(side_join(st, sd0));
   EGOT2_TRY(side_join(st, sd1));
   return side_join(st, sd2);
+}
+
+extern "C" int egot2_side_defer(int on) { g_side_defer[cur_dev()] = on ? 1 : 0; return 0; }
+
+extern "C" int egot2_side_join_all(void* stream) {
+  for (int i = 0; i < 3; ++i) {
+    Side* sd = get_side(i);
+    if (sd && sd->dirty) EGOT2_TRY(side_join((cudaStream_t)stream, sd));
+  }
+  return 0;
 }
 
 // =============================================================================== head + loss

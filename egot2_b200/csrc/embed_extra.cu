@@ -25,6 +25,80 @@ __global__ void dropout_prefix_kernel(T* __restrict__ x, size_t n, size_t period
     if (i % period < prefix) x[i] = from_f32<T>(to_f32(x[i]) * drop_scale(key ^ egot2_ep, i, p, inv_keep));
 }
 
+// ---- embed_finish: everything of the embed stage that follows the projections, in ONE pass over the tokens.
+// The long-K projections (PNR / OSCC: K = 8192 onto H = 128, M = clips x 16 rows: a 32-tile GEMM that cannot fill 148 SMs)
+// run split-K into an fp32 (B,T,H) accumulator (bias added by the first split); this kernel reads that accumulator once and
+// applies feature dropout -> z (bf16, the LayerNorm input saved for backward) -> LayerNorm -> + token table -> embedding
+// dropout -> x.  One warp per token row, S = H / 128 segments of 4 consecutive columns per lane (16 B loads, 8 B stores).
+// HOI/models/pnr/video_model_transfer_3task.py:249-253 (dp(proj), cat, ln, + pe); HHI model_taskspecific.py:217-222.
+template <int S>
+__global__ void __launch_bounds__(256) embed_finish_kernel(const float* __restrict__ zf, int rows, int T, int drop_tokens,
+                                                           float p_feat, uint64_t key_feat, const float* __restrict__ g,
+                                                           const float* __restrict__ b, float eps,
+                                                           const float* __restrict__ table, float p_embed, uint64_t key_embed,
+                                                           bf16* __restrict__ z, float* __restrict__ stat, bf16* __restrict__ x) {
+  EGOT2_PDL_ENTER();
+  constexpr int HH = S * 128;
+  const int lane = threadIdx.x & 31;
+  const float ik_f = p_feat > 0.f ? 1.f / (1.f - p_feat) : 1.f, ik_e = p_embed > 0.f ? 1.f / (1.f - p_embed) : 1.f;
+  float gg[S][4], bb[S][4];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const float4 g4 = *reinterpret_cast<const float4*>(g + s * 128 + lane * 4), b4 = *reinterpret_cast<const float4*>(b + s * 128 + lane * 4);
+    gg[s][0] = g4.x; gg[s][1] = g4.y; gg[s][2] = g4.z; gg[s][3] = g4.w;
+    bb[s][0] = b4.x; bb[s][1] = b4.y; bb[s][2] = b4.z; bb[s][3] = b4.w;
+  }
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+    const int t = row % T;
+    const bool fdrop = p_feat > 0.f && (drop_tokens <= 0 || t < drop_tokens);
+    float v[S][4], sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int c0 = s * 128 + lane * 4;
+      const float4 a4 = *reinterpret_cast<const float4*>(zf + (size_t)row * HH + c0);
+      float w[4] = {a4.x, a4.y, a4.z, a4.w};
+      if (fdrop) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] *= drop_scale(key_feat ^ egot2_ep, (uint64_t)row * HH + c0 + i, p_feat, ik_f);
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(w[0], w[1]), p1 = __floats2bfloat162_rn(w[2], w[3]);
+      uint2 zw; zw.x = *reinterpret_cast<uint32_t*>(&p0); zw.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(z + (size_t)row * HH + c0) = zw;
+      // LayerNorm sees the rounded values (what backward re-reads)
+      v[s][0] = __uint_as_float(zw.x << 16); v[s][1] = __uint_as_float(zw.x & 0xffff0000u);
+      v[s][2] = __uint_as_float(zw.y << 16); v[s][3] = __uint_as_float(zw.y & 0xffff0000u);
+      sum += (v[s][0] + v[s][1]) + (v[s][2] + v[s][3]);
+    }
+    const float mean = warp_sum(sum) * (1.f / HH);
+    float q = 0.f;
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float d = v[s][i] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / HH) + eps);
+    if (stat && lane == 0) { stat[2 * (size_t)row] = mean; stat[2 * (size_t)row + 1] = rstd; }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int c0 = s * 128 + lane * 4;
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = (v[s][i] - mean) * rstd * gg[s][i] + bb[s][i];
+      if (table) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(table + (size_t)t * HH + c0));
+        o[0] += t4.x; o[1] += t4.y; o[2] += t4.z; o[3] += t4.w;
+      }
+      if (p_embed > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] *= drop_scale(key_embed ^ egot2_ep, (uint64_t)row * HH + c0 + i, p_embed, ik_e);
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+      uint2 xw; xw.x = *reinterpret_cast<uint32_t*>(&p0); xw.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(x + (size_t)row * HH + c0) = xw;
+    }
+  }
+}
+
 int ew_grid(size_t n) {
   size_t ctas = (n + 255) / 256;
   const size_t cap = (size_t)sm_count() * 16;
@@ -40,6 +114,30 @@ int add_table(int dt, size_t n, size_t table_elems, const void* z, const float* 
   ProfScope prof(st, "add_table n%zu", n);
   if (dt == EGOT2_F32) launch(add_table_kernel<float>, dim3(ew_grid(n)), dim3(256), 0, st, (const float*)z, table, (float*)x, n, table_elems);
   else launch(add_table_kernel<bf16>, dim3(ew_grid(n)), dim3(256), 0, st, (const bf16*)z, table, (bf16*)x, n, table_elems);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
+bool embed_finish_supported(int dt, int H) { return dt == EGOT2_BF16 && (H == 128 || H == 256 || H == 512 || H == 1024); }
+
+int embed_finish(int rows, int T, int H, const float* zf, int drop_tokens, float p_feat, uint64_t key_feat, const float* g,
+                 const float* b, float eps, const float* table, float p_embed, uint64_t key_embed, void* z, float* stat, void* x,
+                 cudaStream_t st) {
+  if (rows == 0) return 0;
+  EGOT2_CHECK(embed_finish_supported(EGOT2_BF16, H), "embed_finish: H=%d not supported", H);
+  ProfScope prof(st, "embed_finish rows%d H%d", rows, H);
+  int grid = (rows + 7) / 8;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+#define EGOT2_EF(S) launch(embed_finish_kernel<S>, dim3(grid), dim3(256), 0, st, zf, rows, T, drop_tokens, p_feat, key_feat, g, b, \
+                           eps, table, p_embed, key_embed, (bf16*)z, stat, (bf16*)x)
+  switch (H) {
+    case 128: EGOT2_EF(1); break;
+    case 256: EGOT2_EF(2); break;
+    case 512: EGOT2_EF(4); break;
+    default: EGOT2_EF(8); break;
+  }
+#undef EGOT2_EF
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

@@ -120,6 +120,12 @@ int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t s
 int zero_f32(float* p, size_t n, cudaStream_t st);
 // x[i] = z[i] + table[i % table_elems]   (embed_extra.cu: the embed stage without LayerNorm)
 int add_table(int dtype, size_t n, size_t table_elems, const void* z, const float* table, void* x, cudaStream_t st);
+// embed stage after split-K projections into the fp32 accumulator zf (embed_extra.cu): feature dropout -> z, LN, + table,
+// embedding dropout -> x, one pass
+bool embed_finish_supported(int dtype, int H);
+int embed_finish(int rows, int T, int H, const float* zf, int drop_tokens, float p_feat, uint64_t key_feat, const float* g,
+                 const float* b, float eps, const float* table, float p_embed, uint64_t key_embed, void* z, float* stat, void* x,
+                 cudaStream_t st);
 // in-place dropout of the first `prefix` elements of every `period`-element clip (mask index = linear element index)
 int dropout_prefix_inplace(int dtype, void* x, size_t n, size_t period, size_t prefix, float p, uint64_t key, cudaStream_t st);
 // dst[r, 0..ld) = bf16(src[r, 0..n)) followed by zeros (ld >= n)

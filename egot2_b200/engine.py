@@ -7,6 +7,7 @@ FLOP on the path is executed by libegot2.so.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -189,6 +190,10 @@ class TranslatorEngine:
         self.pe_buffer: Optional[torch.Tensor] = None     # HHI: (max_len, H) sinusoid table (pos_embed.pe)
         self.lossav: Optional[Dict[str, torch.Tensor]] = None
         self._ws: Optional[torch.Tensor] = None
+        self._ws_alt: Dict[int, torch.Tensor] = {}
+        # measured on B200 (HHI b256, PNR b256, LTA b512): 347.1 vs 345.2, 1064 vs 1050, 1644 vs 1655 us per step with / without
+        # deferral - the parameter-gradient backlog is real SM time, not an idle gap, so the default stays "join per layer"
+        self.defer_joins = os.environ.get("EGOT2_DEFER_JOIN", "0") == "1"
         self._ws_retired: List[torch.Tensor] = []     # outgrown workspaces: CUDA graphs captured earlier still point into them
         self._persistent: Dict[Tuple, Activations] = {}
 
@@ -202,7 +207,17 @@ class TranslatorEngine:
     def _vec(self, name: str) -> torch.Tensor:
         return self.arena.view(name)
 
-    def _workspace(self, nbytes: int) -> torch.Tensor:
+    def _workspace(self, nbytes: int, slot: int = 0) -> torch.Tensor:
+        """slot 0: the shared scratch of every stage; slots 1, 2: the alternate encoder-layer workspace and the embedding
+        stage's own one, used by backward() while the side-stream joins are deferred (egot2_side_defer)."""
+        if slot:
+            cur = self._ws_alt.get(slot)
+            if cur is None or cur.numel() < nbytes:
+                if cur is not None:
+                    self._ws_retired.append(cur)
+                cur = torch.empty(int(nbytes), device=self.device, dtype=torch.uint8)
+                self._ws_alt[slot] = cur
+            return cur
         if self._ws is None or self._ws.numel() < nbytes:
             if self._ws is not None:
                 # never hand an outgrown workspace back to the allocator: a graph captured for a smaller batch has its raw
@@ -697,20 +712,32 @@ class TranslatorEngine:
         # ---- encoder layers (reverse)
         if sp.encoder == "simple_vit":
             self._vit_backward(act, dx, grad)
-        for i in reversed(range(sp.layers if sp.encoder == "torch" else 0)):
-            ld = act.layer_desc[i]
-            lg = L.LayerGrads()
-            self._fill_layer_params(lg, i, grads_base=grad)
-            x_in = t["x0"] if i == 0 else t[f"x{i}"]
-            ws = self._workspace(L.load().egot2_encoder_layer_workspace_bytes(C.byref(ld), 1))
-            L.call("egot2_encoder_layer_bwd", C.byref(ld), C.byref(act.layer_params[i]), x_in.data_ptr(),
-                   C.byref(act.layer_saved[i]), dx.data_ptr(), dx.data_ptr(), C.byref(lg), ws.data_ptr(), ws.numel(), st)
+        # The parameter-gradient branches of a layer (side streams) are not joined at the layer boundary: they overlap the
+        # next layer's chain (two alternating workspaces) and the embedding backward (its own workspace), and everything is
+        # joined once before this call returns.
+        n_enc = sp.layers if sp.encoder == "torch" else 0
+        defer = self.defer_joins and n_enc > 0
+        if defer:
+            L.call("egot2_side_defer", 1)
+        try:
+            for i in reversed(range(n_enc)):
+                ld = act.layer_desc[i]
+                lg = L.LayerGrads()
+                self._fill_layer_params(lg, i, grads_base=grad)
+                x_in = t["x0"] if i == 0 else t[f"x{i}"]
+                ws = self._workspace(L.load().egot2_encoder_layer_workspace_bytes(C.byref(ld), 1),
+                                     slot=(i & 1) if defer else 0)
+                L.call("egot2_encoder_layer_bwd", C.byref(ld), C.byref(act.layer_params[i]), x_in.data_ptr(),
+                       C.byref(act.layer_saved[i]), dx.data_ptr(), dx.data_ptr(), C.byref(lg), ws.data_ptr(), ws.numel(), st)
+            if stage == "pre_embed":
+                return grad, [None] * len(sp.segments)
+            return self._embed_backward(act, dx, grad, gv, want_dfeat, ws_slot=2 if defer else 0)
+        finally:
+            if defer:
+                L.call("egot2_side_defer", 0)
+                L.call("egot2_side_join_all", st)
 
-        if stage == "pre_embed":
-            return grad, [None] * len(sp.segments)
-        return self._embed_backward(act, dx, grad, gv, want_dfeat)
-
-    def _embed_backward(self, act: Activations, dx: torch.Tensor, grad: torch.Tensor, gv, want_dfeat):
+    def _embed_backward(self, act: Activations, dx: torch.Tensor, grad: torch.Tensor, gv, want_dfeat, ws_slot: int = 0):
         sp = self.spec
         B, T, H = act.B, act.T, sp.hidden
         dev, st = self.device, _stream()
@@ -735,7 +762,7 @@ class TranslatorEngine:
         else:
             eg.tok_table = gv("pe").view(T, H).data_ptr()
         d = act.embed_desc
-        ws = self._workspace(L.load().egot2_embed_workspace_bytes(C.byref(d), 1))
+        ws = self._workspace(L.load().egot2_embed_workspace_bytes(C.byref(d), 1), slot=ws_slot)
         L.call("egot2_embed_bwd", C.byref(d), C.byref(act.embed_in), C.byref(act.embed_out), dx.data_ptr(), C.byref(eg),
                ws.data_ptr(), ws.numel(), st)
         return grad, dfeats

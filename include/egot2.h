@@ -84,6 +84,15 @@ int egot2_dropout_epoch_set(uint64_t value, void* stream);
 int egot2_dropout_epoch_advance(void* stream);
 int egot2_dropout_epoch_host(uint64_t value);
 int egot2_prof_enable(int on);
+/* Deferred joins of the library's side streams (the parameter-gradient branches of egot2_encoder_layer_bwd).  While
+ * egot2_side_defer(1) is in effect (per device), egot2_encoder_layer_bwd returns WITHOUT making `stream` wait for its
+ * weight-gradient / bias-sum launches, so that they overlap the next layer's (or the embedding stage's) data-gradient
+ * chain; a later egot2_encoder_layer_bwd that is handed the same `workspace` pointer first waits for them (callers
+ * alternate two workspaces).  The caller MUST call egot2_side_join_all(stream) before anything on `stream` (or the host)
+ * consumes the parameter gradients or reuses the saved activations, and before a stream capture ends.  Default off:
+ * every call joins before returning (reference semantics: loss.backward() leaves every .grad complete). */
+int egot2_side_defer(int on);
+int egot2_side_join_all(void* stream);
 /* Diagnostics, -DEGOT2_TIMELINE builds only (otherwise returns an error): every kernel stamps %globaltimer when it starts
  * (after its programmatic-dependent-launch wait) into dev_buf: u64[0] = number of stamps, then (ns, file_id*100000+line)
  * pairs, at most 2000.  Works inside CUDA-graph replays; NULL switches it off.  See tools/timeline.py. */
