@@ -158,9 +158,41 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ---------------------------------------------------------------------------------------------- CPU reference arm
+# ---------------------------------------------------------------------------------------------- reference legs
+# which roofline bounds each configuration (the table, not a self-made byte count)
+TABLE_BOUND = {"hhi_ttm3_train_b256": "tensor", "hoi_pnr_train_b256": "hbm+tensor", "hoi_lta_train_b512": "tensor",
+               "hhi_g_train": "tensor", "hoi_g_train": "tensor"}
+
+
+def time_reference_cpu(name, wl, steps, warmup, batch=0, budget_s=25.0):
+    """The UNMODIFIED reference translator class (oracle/ref_shims: source tree here, oracle/_ref on the GPU box; the oracle
+    port only if neither exists) on the host cores, all threads, fp32: forward (train mode) + loss + backward + Adam.
+    Bounded: stops early when `budget_s` is exceeded.  Returns (clips/s, s/step, steps done, kind, info)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    B = batch or wl["batch"]
+    from oracle import ref_bench
+    if ref_bench.available():
+        step, info = ref_bench.make_step(name, wl, "cpu", autocast_bf16=False, adam=True, batch=B)
+        kind = "reference"
+    else:
+        spec = wl["spec"]()
+        fn = cpu_oracle_g_step_fn(wl) if wl.get("prompt") else cpu_oracle_step_fn(spec, B, wl["seg_tokens"])
+        step, info, kind = (lambda i: fn()), {"class": "oracle port", "source": "oracle/translator_oracle.py"}, "port"
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        step(warmup + i)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return B * done / dt, dt / done, done, kind, info
+
+
 def cpu_oracle_step_fn(spec, batch, seg_tokens, seed=0):
-    """fwd (train mode, dropout on) + loss + backward of the CPU oracle on `batch` clips; returns a closure."""
+    """Fallback when the reference classes are unavailable: the CPU oracle port (fwd train mode + loss + backward)."""
     from oracle import translator_oracle as O
     sd = synth.make_state_dict(spec, seed)
     P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
@@ -188,7 +220,7 @@ def cpu_oracle_step_fn(spec, batch, seg_tokens, seed=0):
 
 
 def cpu_oracle_g_step_fn(wl, seed=0):
-    """EgoT2-g: the three forwards + summed CE + backward of the CPU oracle (train mode, dropout on)."""
+    """EgoT2-g fallback: the three forwards + summed CE + backward of the CPU oracle port."""
     from oracle import translator_oracle as O
     spec = wl["spec"]()
     sd = synth.make_state_dict(spec, seed)
@@ -228,48 +260,131 @@ def cpu_oracle_g_step_fn(wl, seed=0):
     return step
 
 
-def time_cpu(spec, batch, seg_tokens, steps, warmup, wl=None):
-    torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_oracle_g_step_fn(wl) if (wl is not None and wl.get("prompt")) else cpu_oracle_step_fn(spec, batch, seg_tokens)
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
-
-
 def run_reference(args, wl, spec):
+    """--impl reference: the reference's own implementation of the path on the host cores (rank 0 only), same steps/warmup as
+    our arm; every step is the workload's full batch unless the run would exceed the time budget (then it stops early and
+    says so in `sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_batch = min(wl["batch"], 256)
-    steps, warm = max(1, args.steps), max(1, min(args.warmup, 2))
-    # bound the run: ~2 s per 256-clip step on 8 cores -> cap the number of timed steps
-    steps = min(steps, 10)
-    cps, sec = time_cpu(spec, sample_batch, wl["seg_tokens"], steps, warm, wl)
+    steps, warm = max(1, args.steps), max(1, args.warmup)
+    cps, sec, done, kind, info = time_reference_cpu(args.workload, wl, steps, min(warm, 3), budget_s=150.0)
     cores = torch.get_num_threads()
-    sample = f"{steps} steps x {sample_batch} clips (fwd+loss+bwd, dropout on) of the CPU oracle, {cores} threads"
+    sample = (f"{done} of {steps} requested steps x {wl['batch']} clips; {info.get('class')} from {info.get('source')}; "
+              f"{info.get('step', 'fwd + loss + bwd')}; fp32; {cores} host threads; bounded at 150 s of CPU work")
     line = {"impl": "reference", "metric": "translator fwd+bwd clips/sec", "value": cps, "unit": "clips/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "steps_timed": done, "ms_per_step": sec * 1e3,
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "translator": spec.family, "hidden": spec.hidden, "layers": spec.layers,
-                       "heads": spec.heads, "ffn": spec.ffn, "clips_per_gpu": sample_batch,
-                       "tokens_per_clip": sum(wl["seg_tokens"]),
-                       "step": "fwd + loss + bwd (all translator grads) of the CPU oracle (torch restatement of the "
-                               "reference translator), fp32, all host threads; one bounded sample of the same workload"},
-            "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": config_of(args.workload, wl, spec, wl["batch"]),
+            "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+def config_of(name, wl, spec, B):
+    """The workload description both arms print (identical keys and values: the driver compares them)."""
+    return {"workload": name, "translator": spec.family, "hidden": spec.hidden, "layers": spec.layers, "heads": spec.heads,
+            "ffn": spec.ffn, "clips_per_gpu": B, "tokens_per_clip": sum(wl["seg_tokens"]),
+            "step": "fwd (train mode, dropout on) + loss + bwd (all translator grads) + Adam"}
+
+
 # ---------------------------------------------------------------------------------------------- our arm
+def build_trainer(name, wl, spec, dev, dtype, use_graphs=True):
+    from egot2_b200.trainer import HoiPromptTranslatorTrainer, PromptTranslatorTrainer, TranslatorTrainer
+    if wl.get("prompt") and wl.get("g_kind") == "hoi":
+        tr = HoiPromptTranslatorTrainer(spec.hidden, spec.heads, spec.layers, spec.p_layer, spec.vocab, dev, dtype)
+    elif wl.get("prompt"):
+        tr = PromptTranslatorTrainer(256, 4, 3, 0.1, dev, dtype)
+    else:
+        tr = TranslatorTrainer(spec, dev, dtype, use_graphs=use_graphs)
+    tr.load_state_dict(synth.make_state_dict(spec, 0))          # identical weights on every rank
+    return tr
+
+
+def build_pool(wl, spec, B, dev, dtype, rank, max_pool=64):
+    """Distinct input batches resident in HBM, together >= 2 x L2, so that no step finds its inputs in L2."""
+    fdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    seg = wl["seg_tokens"]
+    if wl.get("prompt"):
+        feat_bytes = sum(t.numel() * t.element_size() for t in make_g_batch(wl, 0, fdt)[0])
+    else:
+        feat_bytes = spec.feature_elems_per_clip(seg) * B * (2 if dtype == "bf16" else 4)
+    n_pool = min(max_pool, max(3, -(-2 * L2_BYTES // feat_bytes)))
+    pool = []
+    for i in range(n_pool):
+        if wl.get("prompt"):
+            fe, la = make_g_batch(wl, 1000 * rank + i, fdt)
+            pool.append(([t.to(dev) for t in fe], la.to(dev)))
+            continue
+        f = synth.make_features(spec, B, seg, seed=1000 * rank + i, dtype=fdt)
+        pool.append(([f[s.name].to(dev) for s in spec.segments], synth.make_labels(spec, B, seg, seed=1000 * rank + i).to(dev)))
+    return pool, feat_bytes
+
+
+def timed(fn, n, dev, world):
+    """CUDA-event time of fn(0..n-1) in ms, barrier + synchronize on both sides, max over ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def measure_train(name, wl, spec, B, dev, dtype, rank, world, steps, warmup, use_graphs=True):
+    """Device-resident training throughput of one workload at `world` GPUs: (trainer, pool, ms_total)."""
+    tr = build_trainer(name, wl, spec, dev, dtype, use_graphs)
+    pool, feat_bytes = build_pool(wl, spec, B, dev, dtype, rank)
+    n_pool = len(pool)
+
+    def step(i):
+        fe, la = pool[i % n_pool]
+        tr.train_step(fe, la, graph_key=i % n_pool)
+    for i in range(max(warmup, n_pool if tr.use_graphs else warmup)):      # capture every pool graph first
+        step(i)
+    ms = timed(lambda i: step(i + 1), steps, dev, world)
+    return tr, pool, feat_bytes, ms
+
+
+def other_workload_line(name, dev, rank, world, steps, warmup, batch=0):
+    """A further BASELINE.json configuration, device-resident at `world` GPUs (weak scaling), compact record."""
+    wl = dict(WORKLOADS[name])
+    if batch:
+        wl["batch"] = batch
+    spec = wl["spec"]()
+    B = wl["batch"]
+    tr, pool, feat_bytes, ms = measure_train(name, wl, spec, B, dev, "bf16", rank, world, steps, warmup)
+    peaks = load_peaks()
+    is_g = bool(wl.get("prompt"))
+    flops = g_flops_per_step(wl) if is_g else spec.flops_per_clip(wl["seg_tokens"], backward=True) * B
+    sec = ms * 1e-3 / steps
+    rec = {"workload": name, "clips_per_gpu": B, "n_gpus": world, "value": world * B / sec, "unit": "clips/s",
+           "ms_per_step": sec * 1e3, "steps": steps, "model_tflops_per_s_per_gpu": flops / sec / 1e12,
+           "frac_tensor_sustained": flops / sec / 1e12 / peaks["bf16_tflops_sustained"], "bound_8d": TABLE_BOUND.get(name)}
+    if not is_g:
+        # SURVEY 8(d): Bytes_fwd+bwd = 2 x feature bytes (+ 3 x parameter bytes, which matter at small batch)
+        pbytes = 3 * sum(v.numel() for v in synth.make_state_dict(spec, 0).values()) * 2
+        rec["frac_hbm"] = (2 * feat_bytes + pbytes) / sec / 1e9 / peaks["hbm_gbs"]
+    del tr, pool
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="hhi_ttm3_train_b256", choices=sorted(WORKLOADS))
@@ -277,6 +392,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's)")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="headline line only (A/B runs): no fwd_only / fp32 / "
+                    "module_path / gpu_baseline / other workloads")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -294,34 +411,10 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     from egot2_b200 import _lib as L
-    from egot2_b200.trainer import TranslatorTrainer
 
     B, seg = wl["batch"], wl["seg_tokens"]
     fdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     is_g = bool(wl.get("prompt"))
-    if is_g and wl.get("g_kind") == "hoi":
-        from egot2_b200.trainer import HoiPromptTranslatorTrainer
-        tr = HoiPromptTranslatorTrainer(spec.hidden, spec.heads, spec.layers, spec.p_layer, spec.vocab, dev, args.dtype)
-    elif is_g:
-        from egot2_b200.trainer import PromptTranslatorTrainer
-        tr = PromptTranslatorTrainer(256, 4, 3, 0.1, dev, args.dtype)
-    else:
-        tr = TranslatorTrainer(spec, dev, args.dtype, use_graphs=not args.no_graphs)
-    tr.load_state_dict(synth.make_state_dict(spec, 0))          # identical weights on every rank
-    feat_bytes = spec.feature_elems_per_clip(seg) * B * (2 if args.dtype == "bf16" else 4)
-    if is_g:
-        feat_bytes = sum(t.numel() * t.element_size() for t in make_g_batch(wl, 0, fdt)[0])
-    n_pool = max(3, -(-2 * L2_BYTES // feat_bytes))              # pool of distinct batches >= 2 x L2
-    n_pool = min(n_pool, 64)
-    pool = []
-    for i in range(n_pool):
-        if is_g:
-            fe, la = make_g_batch(wl, 1000 * rank + i, fdt)
-            pool.append(([t.to(dev) for t in fe], la.to(dev)))
-            continue
-        f = synth.make_features(spec, B, seg, seed=1000 * rank + i, dtype=fdt)
-        pool.append(([f[s.name].to(dev) for s in spec.segments],
-                     synth.make_labels(spec, B, seg, seed=1000 * rank + i).to(dev)))
     lib = L.load()
 
     def barrier():
@@ -329,12 +422,17 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---- device-resident throughput (the contract's K steps) ...
+    clocks = ClockSampler(local_rank)
+    tr = build_trainer(args.workload, wl, spec, dev, args.dtype, not args.no_graphs)
+    pool, feat_bytes = build_pool(wl, spec, B, dev, args.dtype, rank)
+    n_pool = len(pool)
+
     def run_steps(n, start=0):
         for i in range(n):
             fe, la = pool[(start + i) % n_pool]
             tr.train_step(fe, la, graph_key=(start + i) % n_pool)
 
-    # ---- device-resident throughput
     run_steps(max(args.warmup, n_pool if tr.use_graphs else args.warmup))     # capture every pool graph first
     barrier()
     l0 = lib.egot2_launch_count()
@@ -343,19 +441,13 @@ def main():
     launches_per_step = lib.egot2_launch_count() - l0
     tr.use_graphs = keep
     barrier()
-    clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    run_steps(args.steps, start=1)
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = timed(lambda i: run_steps(1, start=1 + i), args.steps, dev, world)
+    # ... and a sustained region of >= 0.5 s (the K-step region is a few ms at the driver's K), reported beside it
+    sus_steps = max(args.steps, int(0.6 / max(ms_total / args.steps * 1e-3, 1e-6)))
+    sus_steps = min(sus_steps, 20000)
+    ms_sus = timed(lambda i: run_steps(1, start=7 + i), sus_steps, dev, world)
     clock_info = clocks.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total * 1e-3)
 
@@ -369,8 +461,9 @@ def main():
         f = synth.make_features(spec, B, seg, seed=5000 + 10 * rank + i, dtype=fdt)
         host.append(([f[s.name].pin_memory() for s in spec.segments],
                      synth.make_labels(spec, B, seg, seed=5000 + 10 * rank + i).pin_memory()))
-    e2e_steps = max(5, min(args.steps, 30))
+    e2e_steps = max(5, min(args.steps, 200))
     tr.train_stream_host(host, 4)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     losses = tr.train_stream_host(host, e2e_steps)        # returns after the last loss has been read back
@@ -383,6 +476,29 @@ def main():
     e2e_value = world * B * e2e_steps / (float(ms2.item()) * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0][0]) + host[0][1].numel() * 8
 
+    # ---- the other BASELINE.json configurations at this GPU count (every rank takes part: they all-reduce too)
+    others = []
+    if not args.skip_extras and args.workload == "hhi_ttm3_train_b256" and args.dtype == "bf16":
+        del host
+        o_steps, o_warm = max(10, min(args.steps, 30)), 3
+        for name in ("hoi_pnr_train_b256", "hoi_lta_train_b512", "hhi_g_train"):
+            try:
+                others.append(other_workload_line(name, dev, rank, world, o_steps, o_warm))
+            except Exception as e:      # a secondary line must not take the headline down
+                others.append({"workload": name, "error": repr(e)[:200]})
+        # BASELINE configs[4]: batch sweep 64..4096 clips GLOBAL over the GPUs of this run (weight-HBM <-> tensor crossover)
+        sweep = []
+        for gb in (64, 256, 1024, 4096):
+            if gb % world or gb // world < 8:
+                continue
+            try:
+                r = other_workload_line("hoi_lta_train_b512", dev, rank, world, o_steps, o_warm, batch=gb // world)
+                sweep.append({"global_batch": gb, "clips_per_gpu": gb // world, "value": r["value"], "ms_per_step": r["ms_per_step"],
+                              "frac_tensor_sustained": r["frac_tensor_sustained"], "frac_hbm": r.get("frac_hbm")})
+            except Exception as e:
+                sweep.append({"global_batch": gb, "error": repr(e)[:200]})
+        others.append({"workload": "hoi_lta batch sweep", "n_gpus": world, "sweep": sweep})
+
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -393,31 +509,27 @@ def main():
     es = 2 if args.dtype == "bf16" else 4
     prof_steps = max(3, min(args.steps, 10))
     rows = profile_step_launchers(tr, [(fe, la) for fe, la in pool], n_pool, prof_steps, es)
-    roof = dominant_kernel_roofline(rows, prof_steps, peaks, es, ms_total / args.steps * 1e3)
+    roof = dominant_kernel_roofline(rows, prof_steps, peaks, es, ms_total / args.steps * 1e3, TABLE_BOUND.get(args.workload))
     traffic = load_ncu_traffic(roof["kernel"])
     if traffic is not None:
         roof["traffic"] = traffic
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
-    cpu = None
-    if world == 1 and not args.skip_cpu_baseline and not is_g:
-        sample_b = min(B, 256)
-        cps, sec = time_cpu(spec, sample_b, seg, steps=5, warmup=1)
-        cpu = {"value": cps, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"5 steps x {sample_b} clips (fwd+loss+bwd, dropout on) of the CPU oracle"}
-
     flops_step = g_flops_per_step(wl) if is_g else spec.flops_per_clip(seg, backward=True) * B
+    tfs = flops_step * world * args.steps / (ms_total * 1e-3) / 1e12
     line = {
         "metric": "translator fwd+bwd clips/sec", "value": value, "unit": "clips/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "translator": spec.family, "hidden": spec.hidden, "layers": spec.layers,
-                   "heads": spec.heads, "ffn": spec.ffn, "clips_per_gpu": B, "tokens_per_clip": sum(seg),
-                   "step": "fwd + fused loss + bwd (all translator grads) + grad all-reduce (N>1) + fused Adam",
-                   "l2_policy": f"inputs rotate over a pool of {n_pool} batches = {n_pool * feat_bytes / 2**20:.0f} MiB "
-                                f"> 126 MiB L2; saved activations add more per step",
-                   "cuda_graphs": bool(tr.use_graphs), "parallelism": f"dp{world} (clips sharded, no data-path collective)"},
-        "model_tflops_per_s": flops_step * world * args.steps / (ms_total * 1e-3) / 1e12,
+        "config": config_of(args.workload, wl, spec, B),       # identical in the reference arm's line
+        "run": {"l2_policy": f"inputs rotate over a pool of {n_pool} batches = {n_pool * feat_bytes / 2**20:.0f} MiB "
+                             f"> 126 MiB L2; saved activations add more per step",
+                "cuda_graphs": bool(tr.use_graphs), "parallelism": f"dp{world} (clips sharded; one gradient all-reduce per step)"},
+        "model_tflops_per_s": tfs,
+        "step_roofline": {"bound": "tensor", "achieved": tfs / world, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                          "frac": tfs / world / peaks["bf16_tflops_sustained"],
+                          "note": "whole step, per GPU: SURVEY 8(d) FLOPs_fwd+bwd per clip x clips / step time"},
+        "sustained": {"steps": sus_steps, "ms_per_step": ms_sus / sus_steps, "value": world * B * sus_steps / (ms_sus * 1e-3),
+                      "note": "same step, timed region >= 0.5 s"},
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "steps": e2e_steps},
@@ -425,11 +537,125 @@ def main():
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roof,
     }
-    if cpu is not None:
-        line["cpu_baseline"] = cpu
+    if others:
+        line["other_workloads"] = others
+
+    if world == 1 and not args.skip_extras and not is_g:
+        extras = extra_legs(args, wl, spec, tr, pool, dev)
+        line.update(extras)
+    # ---- CPU baseline (rank 0, N=1 only): the reference class on the host cores, bounded sample
+    if world == 1 and not args.skip_cpu_baseline:
+        cps, sec, done, kind, info = time_reference_cpu(args.workload, wl, steps=5, warmup=1, budget_s=20.0)
+        line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind,
+                                "sample": f"{done} steps x {B} clips; {info.get('class')} from {info.get('source')}; "
+                                          f"{info.get('step', 'fwd + loss + bwd')}; fp32"}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def extra_legs(args, wl, spec, tr, pool, dev):
+    """N = 1 only, rank 0: forward-only, fp32 mode, the drop-in nn.Module path, and the reference classes in stock torch
+    eager on this same GPU (the comparator SURVEY 8(d) names)."""
+    out = {}
+    B, seg, n_pool = wl["batch"], wl["seg_tokens"], len(pool)
+    n = max(20, min(args.steps, 200))
+
+    def rec(ms, steps, **kw):
+        return dict({"value": B * steps / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms / steps, "steps": steps}, **kw)
+    # forward only (eval mode, no dropout), device-resident, eager launches
+    try:
+        for i in range(3):
+            tr.infer(pool[i % n_pool][0])
+        ms = timed(lambda i: tr.infer(pool[i % n_pool][0]), n, dev, 1)
+        fl = spec.flops_per_clip(seg, backward=False) * B
+        out["fwd_only"] = rec(ms, n, dtype=args.dtype, model_tflops_per_s=fl * n / (ms * 1e-3) / 1e12, mode="eval forward, eager launches")
+    except Exception as e:
+        out["fwd_only"] = {"error": repr(e)[:200]}
+    # fp32 parity mode (CUDA-core fp32 kernels: the mode whose argmax is bit-exact against the reference)
+    try:
+        tr32 = build_trainer(args.workload, wl, spec, dev, "fp32", True)
+        pool32, _ = build_pool(wl, spec, B, dev, "fp32", 0, max_pool=6)
+        for i in range(max(3, len(pool32))):
+            tr32.train_step(*pool32[i % len(pool32)], graph_key=i % len(pool32))
+        n32 = max(5, min(n, 20))
+        ms = timed(lambda i: tr32.train_step(*pool32[i % len(pool32)], graph_key=i % len(pool32)), n32, dev, 1)
+        out["fp32"] = rec(ms, n32, dtype="f32", mode="fp32 parity mode, full training step")
+        del tr32, pool32
+    except Exception as e:
+        out["fp32"] = {"error": repr(e)[:200]}
+    # the drop-in nn.Module (what run_ttm.py gets): module forward + torch loss + loss.backward() + torch.optim.Adam
+    try:
+        out["module_path"] = module_path_leg(wl, spec, pool, dev, n)
+    except Exception as e:
+        out["module_path"] = {"error": repr(e)[:300]}
+    # the reference classes in torch eager on this GPU
+    try:
+        from oracle import ref_bench
+        gb = {"kind": "reference classes (oracle/ref_shims) in stock torch eager on the same GPU" if ref_bench.available() else "unavailable"}
+        if ref_bench.available():
+            for key, ac in (("fp32", False), ("bf16_autocast", True)):
+                step, info = ref_bench.make_step(args.workload, wl, str(dev), autocast_bf16=ac, adam=True, n_batches=4)
+                for i in range(5):
+                    step(i)
+                nb = max(10, min(n, 50))
+                ms = timed(step, nb, dev, 1)
+                gb[key] = rec(ms, nb)
+                gb["class"], gb["source"], gb["step"] = info["class"], info["source"], info["step"]
+                fstep, _ = ref_bench.make_step(args.workload, wl, str(dev), autocast_bf16=ac, training=False, n_batches=4)
+                for i in range(3):
+                    fstep(i)
+                ms = timed(fstep, nb, dev, 1)
+                gb[key + "_fwd_only"] = rec(ms, nb)
+                del step, fstep
+        out["gpu_baseline"] = gb
+    except Exception as e:
+        out["gpu_baseline"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    return out
+
+
+def module_path_leg(wl, spec, pool, dev, n):
+    from types import SimpleNamespace
+    from egot2_b200 import hhi
+    from egot2_b200.modules import PrecomputedFeatures
+    if spec.family != "hhi_ttm" or len(spec.segments) != 3:
+        return {"skipped": "module-path leg is wired for the HHI 3-task translator"}
+
+    class _Talk(torch.nn.Module):
+        def forward_audio_frontend(self, a): return a
+        def forward_visual_frontend(self, v): return v
+        def forward_cross_attention(self, a, v): return a, v
+        def forward_audio_visual_backend(self, a, v): return v["asd"].reshape(-1, v["asd"].shape[-1])
+
+    class _Feats(dict):
+        @property
+        def shape(self):
+            b, d, _ = self["asd"].shape
+            return (b, d, 1, 1)
+    margs = SimpleNamespace(lam_checkpoint="x", ttm_checkpoint="x", asd_checkpoint="x", nofreeze=False, hidden_dim=spec.hidden,
+                            num_heads=spec.heads, dropout=spec.p_layer, num_layers=spec.layers)
+    m = hhi.ttm.TaskFusionMFTransformer3Task(margs, backbones={"lam_model": PrecomputedFeatures("lam"), "ttm_model": PrecomputedFeatures("ttm"),
+                                                               "asd_model": _Talk()})
+    m.load_state_dict(synth.make_state_dict(spec, 0), strict=False)
+    m.to(dev).set_compute_dtype("bf16").train()
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=5e-4)
+    cw = torch.tensor([0.266, 0.734], device=dev)
+    names = [s.name for s in spec.segments]
+
+    def step(i):
+        fe, la = pool[i % len(pool)]
+        v = _Feats({k: t for k, t in zip(names, fe)})
+        opt.zero_grad(set_to_none=True)
+        out = m(v, v, None, None)
+        loss = torch.nn.functional.cross_entropy(out.float(), la, weight=cw)
+        loss.backward()
+        opt.step()
+    for i in range(5):
+        step(i)
+    ms = timed(step, n, dev, 1)
+    return {"value": wl["batch"] * n / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms / n, "steps": n,
+            "mode": "egot2_b200.hhi.ttm.TaskFusionMFTransformer3Task (bf16 compute) + torch cross_entropy + loss.backward() + torch.optim.Adam"}
 
 
 def launcher_cost(tag: str, es: int):
@@ -493,7 +719,7 @@ def profile_step_launchers(tr, pool, n_pool, steps, es):
     return rows
 
 
-def dominant_kernel_roofline(rows, steps, peaks, es, step_us_graph):
+def dominant_kernel_roofline(rows, steps, peaks, es, step_us_graph, table_bound=None):
     """rows: [(tag, launches, total_us)] from the profiled pass.  The dominant launcher = the largest share of the
     summed kernel time; its achieved rate = algorithmic flops|bytes of one launch / its mean event-timed duration."""
     tot = sum(r[2] for r in rows) or 1.0
@@ -512,7 +738,11 @@ def dominant_kernel_roofline(rows, steps, peaks, es, step_us_graph):
     sec = us * 1e-6 / n
     ai = flops / nbytes
     # inside a long step the sustained tensor figure is the fair ceiling (MEASURED_PEAKS.json: burst vs sustained)
-    if es == 2 and ai >= ridge:
+    # Which roofline bounds the kernel: SURVEY 8(d)'s table for the configuration (a contraction kernel of a tensor-bound
+    # configuration is measured against the tensor pipe even when its own byte count - which includes activations that
+    # are saved by design choice, not by necessity - would put it a hair under the ridge); otherwise by arithmetic intensity.
+    contraction = tag.startswith(("ffn_", "gemm_", "attn_"))
+    if es == 2 and ((table_bound == "tensor" and contraction) or ai >= ridge):
         bound, achieved, peak, unit = "tensor", flops / sec / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
     else:
         bound, achieved, peak, unit = "hbm", nbytes / sec / 1e9, peaks["hbm_gbs"], "GB/s"

@@ -124,6 +124,12 @@ int gemm(const GemmArgs& a, cudaStream_t st) {
     if (rc >= 0) { if (rc == 0) g_gemm_impl = "tcgen05"; return rc; }
   }
   g_gemm_impl = "simt";
+  if (a.split_stride > 0) {      // the CUDA-core GEMM has no split-K: one split, written to slab 0
+    GemmArgs b = a;
+    b.split_k = 1; b.split_stride = 0;
+    if (a.splits_out) *a.splits_out = 1;
+    return gemm_simt(b, st);
+  }
   return gemm_simt(a, st);
 }
 
@@ -379,11 +385,27 @@ bool embed_splitk(const egot2_embed_desc* d) {
   }
   return false;
 }
+// splits of segment k's projection: half of the resident CTA slots each (two projections run side by side on two streams),
+// at least 8 k-blocks of 64 per split
+int embed_seg_splits(const egot2_embed_desc* d, int k) {
+  if (!d->seg_has_proj[k] || d->seg_tokens[k] == 0) return 1;
+  const long long tiles = (((long long)d->B * d->seg_tokens[k] + 127) / 128) * ((d->H + 127) / 128);
+  long long s = sm_count() / tiles;
+  if (s > d->seg_in_dim[k] / 512) s = d->seg_in_dim[k] / 512;
+  if (s > 16) s = 16;
+  return s < 1 ? 1 : (int)s;
+}
+size_t embed_slab_floats(const egot2_embed_desc* d) {
+  size_t n = 0;
+  for (int k = 0; k < d->n_seg; ++k)
+    if (d->seg_has_proj[k]) n += (size_t)embed_seg_splits(d, k) * d->B * d->seg_tokens[k] * d->H;
+  return n;
+}
 }  // namespace
 
 extern "C" size_t egot2_embed_workspace_bytes(const egot2_embed_desc* d, int backward) {
   size_t n = 256;
-  if (!backward && embed_splitk(d)) n += align_up((size_t)d->B * d->T * d->H * 4);
+  if (!backward && embed_splitk(d)) n += align_up(embed_slab_floats(d) * 4);
   if (!backward && d->feat_dtype != d->dtype) {
     size_t mx = 0;
     for (int k = 0; k < d->n_seg; ++k) {
@@ -431,10 +453,11 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   void* cast_buf = nullptr;
   const bool splitk = embed_splitk(d);
   float* zf = nullptr;
+  EmbedSrc src;
+  src.n = d->n_seg;
   if (splitk) {
-    zf = (float*)ws.take((size_t)d->B * d->T * d->H * 4);
+    zf = (float*)ws.take(embed_slab_floats(d) * 4);
     EGOT2_CHECK(ws.ok(), "embed_fwd: workspace too small (%zu < %zu)", ws_bytes, ws.off);
-    EGOT2_CUDA(cudaMemsetAsync(zf, 0, (size_t)d->B * d->T * d->H * 4, st));
   }
   if (d->feat_dtype != d->dtype) {
     size_t mx = 0;
@@ -461,6 +484,10 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
     cudaStream_t sk = k > 0 ? side_st[(k - 1) & 1] : st;
     char* zk = (char*)out->z + (size_t)d->seg_offset[k] * d->H * es;
     const void* feat = in->feat[k];
+    if (splitk && !d->seg_has_proj[k]) {      // pass-through segment (LTA action features): the finishing pass reads it in place
+      src.direct[k] = feat; src.direct_f32[k] = d->feat_dtype == EGOT2_F32 && d->dtype != EGOT2_F32;
+      continue;
+    }
     if (d->feat_dtype != d->dtype) {
       EGOT2_TRY(cast_f32_to(d->dtype, (const float*)feat, cast_buf, (size_t)d->B * Dk * Kk, sk));
       feat = cast_buf;
@@ -473,15 +500,17 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
       g.C = zk; g.ldc = d->H; g.c_rpg = Dk; g.c_gstride = d->T;
       g.bias = in->proj_b[k];
       g.in_dtype = d->dtype; g.out_dtype = d->dtype;
-      if (splitk) {       // this segment's rows of the fp32 accumulator; the first split adds the bias
-        g.C = zf + (size_t)d->seg_offset[k] * d->H; g.out_dtype = EGOT2_F32; g.accumulate = 1;
-        g.split_k = suggest_split_k(g.M, g.N, g.K);
+      if (splitk) {       // deterministic split-K: split s writes slab s of this segment (B*Dk, H) fp32; the first adds the bias
+        g.C = zf; g.ldc = d->H; g.c_rpg = 0; g.c_gstride = 0; g.out_dtype = EGOT2_F32;
+        g.split_k = embed_seg_splits(d, k); g.split_stride = (long long)d->B * Dk * d->H;
+        int used = 1;
+        g.splits_out = &used;
+        EGOT2_TRY(gemm(g, sk));
+        src.slab[k] = zf; src.splits[k] = used;
+        zf += (size_t)embed_seg_splits(d, k) * d->B * Dk * d->H;
+      } else {
+        EGOT2_TRY(gemm(g, sk));
       }
-      EGOT2_TRY(gemm(g, sk));
-    } else if (splitk) {  // pass-through segment: widen into the accumulator (rare: LTA action features)
-      for (int b = 0; b < d->B; ++b)
-        EGOT2_TRY(cast_to_f32(d->dtype, (const char*)feat + (size_t)b * Dk * d->H * es, zf + ((size_t)b * d->T + d->seg_offset[k]) * d->H,
-                              (size_t)Dk * d->H, sk));
     } else {
       EGOT2_CUDA(cudaMemcpy2DAsync(zk, (size_t)d->T * d->H * es, feat, (size_t)Dk * d->H * es, (size_t)Dk * d->H * es,
                                    d->B, cudaMemcpyDeviceToDevice, sk));
@@ -489,10 +518,12 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   }
   for (int i = 0; i < 2; ++i) if (used[i]) EGOT2_TRY(side_join(st, sides[i]));
   const size_t n = (size_t)d->B * d->T * d->H;
-  if (splitk)
-    return embed_finish(d->B * d->T, d->T, d->H, zf, (d->feat_drop_tokens > 0 && d->feat_drop_tokens < d->T) ? d->feat_drop_tokens : 0,
+  if (splitk) {
+    for (int k = 0; k < d->n_seg; ++k) { src.tok_begin[k] = d->seg_offset[k]; src.tokens[k] = d->seg_tokens[k]; }
+    return embed_finish(d->B, d->T, d->H, src, (d->feat_drop_tokens > 0 && d->feat_drop_tokens < d->T) ? d->feat_drop_tokens : 0,
                         d->training ? d->p_feat : 0.f, site_key(d->seed, SITE_FEAT, 0), in->ln_g, in->ln_b, d->ln_eps, in->tok_table,
                         d->training ? d->p_embed : 0.f, site_key(d->seed, SITE_EMBED, 0), out->z, out->stat, out->x, st);
+  }
   if (d->training && d->p_feat > 0.f) {
     if (d->feat_drop_tokens > 0 && d->feat_drop_tokens < d->T)
       EGOT2_TRY(dropout_prefix_inplace(d->dtype, out->z, n, (size_t)d->T * d->H, (size_t)d->feat_drop_tokens * d->H, d->p_feat,

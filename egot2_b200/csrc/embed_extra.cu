@@ -27,12 +27,13 @@ __global__ void dropout_prefix_kernel(T* __restrict__ x, size_t n, size_t period
 
 // ---- embed_finish: everything of the embed stage that follows the projections, in ONE pass over the tokens.
 // The long-K projections (PNR / OSCC: K = 8192 onto H = 128, M = clips x 16 rows: a 32-tile GEMM that cannot fill 148 SMs)
-// run split-K into an fp32 (B,T,H) accumulator (bias added by the first split); this kernel reads that accumulator once and
-// applies feature dropout -> z (bf16, the LayerNorm input saved for backward) -> LayerNorm -> + token table -> embedding
+// run a DETERMINISTIC split-K: split s of segment k writes its partial product (bias added by the first split) to slab s, an
+// fp32 (B*D_k, H) matrix (the slabs of PNR b256 are 32 MB: they stay in the 126 MB L2); this kernel sums the slabs in a fixed
+// order - no atomics, bit-reproducible - reads pass-through segments (already H wide) in place, and applies feature dropout -> z (bf16, the LayerNorm input saved for backward) -> LayerNorm -> + token table -> embedding
 // dropout -> x.  One warp per token row, S = H / 128 segments of 4 consecutive columns per lane (16 B loads, 8 B stores).
 // HOI/models/pnr/video_model_transfer_3task.py:249-253 (dp(proj), cat, ln, + pe); HHI model_taskspecific.py:217-222.
 template <int S>
-__global__ void __launch_bounds__(256) embed_finish_kernel(const float* __restrict__ zf, int rows, int T, int drop_tokens,
+__global__ void __launch_bounds__(256) embed_finish_kernel(const EmbedSrc src, int B, int T, int drop_tokens,
                                                            float p_feat, uint64_t key_feat, const float* __restrict__ g,
                                                            const float* __restrict__ b, float eps,
                                                            const float* __restrict__ table, float p_embed, uint64_t key_embed,
@@ -48,16 +49,38 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const float* __restri
     gg[s][0] = g4.x; gg[s][1] = g4.y; gg[s][2] = g4.z; gg[s][3] = g4.w;
     bb[s][0] = b4.x; bb[s][1] = b4.y; bb[s][2] = b4.z; bb[s][3] = b4.w;
   }
-  const int warps = gridDim.x * (blockDim.x >> 5);
+  const int warps = gridDim.x * (blockDim.x >> 5), rows = B * T;
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
-    const int t = row % T;
+    const int t = row % T, bclip = row / T;
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < EGOT2_MAX_SEG; ++i) if (i < src.n && t >= src.tok_begin[i] && src.tokens[i] > 0) k = i;
+    const size_t srow = (size_t)bclip * src.tokens[k] + (t - src.tok_begin[k]);       // row inside the segment's (B*D_k, H) matrix
+    const size_t slab_elems = (size_t)B * src.tokens[k] * HH;
+    const float* slab = src.slab[k];
+    const bf16* direct = (const bf16*)src.direct[k];
+    const int ns = src.splits[k];
     const bool fdrop = p_feat > 0.f && (drop_tokens <= 0 || t < drop_tokens);
     float v[S][4], sum = 0.f;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const int c0 = s * 128 + lane * 4;
-      const float4 a4 = *reinterpret_cast<const float4*>(zf + (size_t)row * HH + c0);
-      float w[4] = {a4.x, a4.y, a4.z, a4.w};
+      float w[4];
+      if (direct && src.direct_f32[k]) {
+        const float4 a4 = *reinterpret_cast<const float4*>((const float*)src.direct[k] + srow * HH + c0);
+        w[0] = a4.x; w[1] = a4.y; w[2] = a4.z; w[3] = a4.w;
+      } else if (direct) {
+        const uint2 dw = *reinterpret_cast<const uint2*>(direct + srow * HH + c0);
+        w[0] = __uint_as_float(dw.x << 16); w[1] = __uint_as_float(dw.x & 0xffff0000u);
+        w[2] = __uint_as_float(dw.y << 16); w[3] = __uint_as_float(dw.y & 0xffff0000u);
+      } else {
+        const float4 a4 = *reinterpret_cast<const float4*>(slab + srow * HH + c0);
+        w[0] = a4.x; w[1] = a4.y; w[2] = a4.z; w[3] = a4.w;
+        for (int sp = 1; sp < ns; ++sp) {
+          const float4 p4 = *reinterpret_cast<const float4*>(slab + sp * slab_elems + srow * HH + c0);
+          w[0] += p4.x; w[1] += p4.y; w[2] += p4.z; w[3] += p4.w;
+        }
+      }
       if (fdrop) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[i] *= drop_scale(key_feat ^ egot2_ep, (uint64_t)row * HH + c0 + i, p_feat, ik_f);
@@ -120,16 +143,17 @@ int add_table(int dt, size_t n, size_t table_elems, const void* z, const float* 
 
 bool embed_finish_supported(int dt, int H) { return dt == EGOT2_BF16 && (H == 128 || H == 256 || H == 512 || H == 1024); }
 
-int embed_finish(int rows, int T, int H, const float* zf, int drop_tokens, float p_feat, uint64_t key_feat, const float* g,
+int embed_finish(int B, int T, int H, const EmbedSrc& src, int drop_tokens, float p_feat, uint64_t key_feat, const float* g,
                  const float* b, float eps, const float* table, float p_embed, uint64_t key_embed, void* z, float* stat, void* x,
                  cudaStream_t st) {
+  const int rows = B * T;
   if (rows == 0) return 0;
   EGOT2_CHECK(embed_finish_supported(EGOT2_BF16, H), "embed_finish: H=%d not supported", H);
   ProfScope prof(st, "embed_finish rows%d H%d", rows, H);
   int grid = (rows + 7) / 8;
   const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
-#define EGOT2_EF(S) launch(embed_finish_kernel<S>, dim3(grid), dim3(256), 0, st, zf, rows, T, drop_tokens, p_feat, key_feat, g, b, \
+#define EGOT2_EF(S) launch(embed_finish_kernel<S>, dim3(grid), dim3(256), 0, st, src, B, T, drop_tokens, p_feat, key_feat, g, b, \
                            eps, table, p_embed, key_embed, (bf16*)z, stat, (bf16*)x)
   switch (H) {
     case 128: EGOT2_EF(1); break;

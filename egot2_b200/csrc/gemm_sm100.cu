@@ -35,6 +35,7 @@ struct EpiArgs {
   float p_drop; uint64_t drop_key; int drop_bit_mode;
   const void* residual; int ldr;
   int accumulate; int atomic;
+  long long split_stride;        // > 0: split z writes its own slab at C + z * split_stride (no atomics)
   int tma_store;     // bf16 C, plain rows: the tile leaves through shared memory + TMA (coalesced) instead of per-row stores
   // grouped-K addressing for gathered MN-major operands (3-D tensor maps): 64-row k-block = kg groups x kdpad rows
   int k_grouped, kg, kdblocks;
@@ -238,7 +239,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
       const bool row_ok = (m < e.M) && nkb > 0;
       const long long crow = row_ok ? remap(m, e.c_rpg, e.c_gstride) : 0;
-      TO* __restrict__ crow_ptr = (TO*)e.C + crow * e.ldc;
+      TO* __restrict__ crow_ptr = (TO*)e.C + (long long)blockIdx.z * e.split_stride + crow * e.ldc;
       const TO* mask_row = e.mask ? (const TO*)e.mask + (long long)(row_ok ? m : 0) * e.ldm : nullptr;
       const TO* res_row = (e.residual && first_split) ? (const TO*)e.residual + (long long)(row_ok ? m : 0) * e.ldr : nullptr;
       const bool vec_ok = aligned16(crow_ptr) && aligned16(mask_row) && aligned16(res_row);
@@ -463,7 +464,9 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   }
   const int kb_per = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per - 1) / kb_per;
-  e.atomic = splits > 1;
+  e.atomic = splits > 1 && a.split_stride == 0;
+  e.split_stride = a.split_stride;
+  if (a.splits_out) *a.splits_out = splits;
   const int tiles_n = (a.N + BN - 1) / BN, num_tiles = tiles_n * ((a.M + BM - 1) / BM);
   // persistent CTAs: as many as are resident at once, evened out so that every CTA walks the same number of tiles
   int ctas = num_tiles;
@@ -520,7 +523,8 @@ int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
   if (a.M < 1 || a.N < 32 || a.K < 16) return -1;                  // degenerate tiles (tiny heads) stay on CUDA cores
   if (!host_aligned16(a.A) || !host_aligned16(a.B) || (a.lda % 8) || (a.ldb % 8)) return -1;
   if (a.accumulate && a.out_dtype != EGOT2_F32) return -1;
-  if (a.split_k > 1 && (!a.accumulate || a.relu || a.mask || a.p_drop > 0.f)) return -1;
+  if (a.split_k > 1 && a.split_stride == 0 && (!a.accumulate || a.relu || a.mask || a.p_drop > 0.f)) return -1;
+  if (a.split_stride > 0 && (a.accumulate || a.out_dtype != EGOT2_F32 || a.relu || a.mask || a.p_drop > 0.f || a.residual)) return -1;
   // short-K problems are epilogue/store bound: 128-wide tiles run two CTAs per SM; long-K ones amortise A over 256 columns
   int bn = a.N <= 64 ? 64 : ((a.N <= 128 || a.K <= 512) ? 128 : ((a.N % 256 == 0 || a.N > 512) ? 256 : 128));
   if (a.accumulate && a.split_k > 1) {

@@ -26,6 +26,11 @@ struct GemmArgs {
   const void* residual = nullptr; int ldr = 0;                       // + residual[m,n]
   int accumulate = 0;            // C += value (fp32 C only); split-K uses atomics
   int split_k = 1;
+  // split_stride > 0 (fp32 C, no accumulate): split z WRITES its partial product to C + z * split_stride (elements) instead
+  // of adding atomically - a deterministic split-K whose slabs the consumer sums in a fixed order (embed stage); the number
+  // of splits actually launched (<= split_k) is returned through *splits_out
+  long long split_stride = 0;
+  int* splits_out = nullptr;
 };
 int gemm(const GemmArgs& a, cudaStream_t st);          // dispatch: tcgen05 (bf16, supported shapes) or CUDA-core
 int gemm_simt(const GemmArgs& a, cudaStream_t st);     // gemm_simt.cu
@@ -120,10 +125,15 @@ int cast_to_f32(int dtype, const void* src, float* dst, size_t n, cudaStream_t s
 int zero_f32(float* p, size_t n, cudaStream_t st);
 // x[i] = z[i] + table[i % table_elems]   (embed_extra.cu: the embed stage without LayerNorm)
 int add_table(int dtype, size_t n, size_t table_elems, const void* z, const float* table, void* x, cudaStream_t st);
-// embed stage after split-K projections into the fp32 accumulator zf (embed_extra.cu): feature dropout -> z, LN, + table,
-// embedding dropout -> x, one pass
+// embed stage after deterministic split-K projections (embed_extra.cu): sum of the slabs -> feature dropout -> z, LN,
+// + table, embedding dropout -> x, one pass
 bool embed_finish_supported(int dtype, int H);
-int embed_finish(int rows, int T, int H, const float* zf, int drop_tokens, float p_feat, uint64_t key_feat, const float* g,
+struct EmbedSrc {      // where segment k's projected rows are: `splits` fp32 slabs of (B*tokens, H), or the bf16 features themselves
+  int n = 0; int tok_begin[EGOT2_MAX_SEG] = {}; int tokens[EGOT2_MAX_SEG] = {}; int splits[EGOT2_MAX_SEG] = {};
+  const float* slab[EGOT2_MAX_SEG] = {}; const void* direct[EGOT2_MAX_SEG] = {};
+  int direct_f32[EGOT2_MAX_SEG] = {};      // the pass-through features are fp32 (caller hands fp32 features to a bf16 engine)
+};
+int embed_finish(int B, int T, int H, const EmbedSrc& src, int drop_tokens, float p_feat, uint64_t key_feat, const float* g,
                  const float* b, float eps, const float* table, float p_embed, uint64_t key_embed, void* z, float* stat, void* x,
                  cudaStream_t st);
 // in-place dropout of the first `prefix` elements of every `period`-element clip (mask index = linear element index)

@@ -124,8 +124,9 @@ def hoi_g_reference_forward(sp, m, feats, target_in):
     return m(vid, None, target_in)
 
 
-def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
-    """Drive the reference module through its own forward() and the loss its Lightning task uses."""
+def reference_forward_loss(case: Case, m, hhi, feats, labels, extra, keep_head_dropout: bool = False):
+    """Drive the reference module through its own forward() and the loss its Lightning task uses.
+    keep_head_dropout: leave the LTA head's Dropout(0.5) on (benchmark legs in train mode; the goldens switch it off)."""
     sp = case.spec
     if sp.family == "hhi_ttm":
         if len(sp.segments) == 3:
@@ -133,7 +134,7 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         else:
             out = m(rs._DictVideo(feats), None)
         # HHI/tasks/ttm/video_task.py:23-24,36
-        loss = torch.nn.CrossEntropyLoss(weight=torch.tensor([0.266, 0.734]))(out, labels)
+        loss = torch.nn.CrossEntropyLoss(weight=torch.tensor([0.266, 0.734], device=out.device))(out, labels)
     elif sp.family == "hhi_asd":
         out = m(*rs.hhi_inputs(feats))
         lav = hhi.asd_loss.lossAV(dim=sp.hidden)
@@ -153,7 +154,8 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         out = m([{"pnr": feats["pnr"], "oscc": feats["oscc"]}])
         if sp.n_out == 16:
             out = out.squeeze(1)
-            loss = torch.nn.BCELoss()(torch.sigmoid(out), torch.nn.functional.one_hot(labels, 16).float())
+            with torch.autocast(out.device.type, enabled=False):      # BCELoss refuses to run under autocast (benchmark legs)
+                loss = torch.nn.BCELoss()(torch.sigmoid(out.float()), torch.nn.functional.one_hot(labels, 16).float())
         else:
             out = out.squeeze(2)
             loss = torch.nn.functional.cross_entropy(out, labels)
@@ -172,7 +174,8 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         if sp.n_out == 16:
             out = out.squeeze(1)                                   # (B,1,16) -> (B,16)
             # HOI/tasks/pnr/video_taskspecific_pnr.py:29-31
-            loss = torch.nn.BCELoss()(torch.sigmoid(out), torch.nn.functional.one_hot(labels, 16).float())
+            with torch.autocast(out.device.type, enabled=False):      # BCELoss refuses to run under autocast (benchmark legs)
+                loss = torch.nn.BCELoss()(torch.sigmoid(out.float()), torch.nn.functional.one_hot(labels, 16).float())
         else:
             out = out.squeeze(2)                                   # (B,2,1) -> (B,2)
             loss = torch.nn.functional.cross_entropy(out, labels)  # :143-146
@@ -204,7 +207,7 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         feat = m.ln(feat) + m.pe
         out_t = m.transformer(feat).mean(dim=1)
         m.head.training = True                                     # raw logits (train-mode head), dropout is p=0 below
-        if hasattr(m.head, "dropout"):
+        if hasattr(m.head, "dropout") and not keep_head_dropout:
             m.head.dropout.p = 0.0
         preds = m.decode(out_t)
         out = torch.cat(preds, dim=-1)
@@ -219,7 +222,7 @@ def reference_forward_loss(case: Case, m, hhi, feats, labels, extra):
         feat = m.ln(feat) + m.pe
         out_t = m.transformer(feat).mean(dim=1)
         m.head.training = True                                     # raw logits (train-mode head), dropout is p=0 below
-        if hasattr(m.head, "dropout"):
+        if hasattr(m.head, "dropout") and not keep_head_dropout:
             m.head.dropout.p = 0.0
         preds = m.decode(out_t)                                    # [(B,Z,115),(B,Z,478)]
         out = torch.cat(preds, dim=-1)

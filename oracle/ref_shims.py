@@ -21,6 +21,8 @@ from __future__ import annotations
 import contextlib
 import copy
 import importlib
+import importlib.machinery
+import importlib.util
 import os
 import sys
 import types
@@ -29,11 +31,37 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("EGOT2_REFERENCE_ROOT", "/root/reference")
+# Where the reference classes come from: the source tree in the build container, else `oracle/_ref/` - the same modules
+# byte-compiled by `oracle/build_ref.py` (run by __graft_entry__.build() where /root/reference exists; git-ignored, not
+# gpurun-ignored, so the compiled files travel to the GPU box where /root/reference does not exist).  No reference SOURCE
+# is ever copied into the repository.
+_SOURCE_ROOT = os.environ.get("EGOT2_REFERENCE_ROOT", "/root/reference")
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = _SOURCE_ROOT if os.path.isdir(os.path.join(_SOURCE_ROOT, "HHI", "models")) else COMPILED_ROOT
+#: files of the reference tree that the loaders below actually imported (build_ref.py compiles exactly these)
+LOADED_FILES: set = set()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "HHI", "models"))
+
+
+def reference_kind() -> str:
+    return "source tree" if REFERENCE_ROOT == _SOURCE_ROOT else "oracle/_ref (byte-compiled reference modules)"
+
+
+def _load_file(name: str, rel: str):
+    """Import one reference file by path (source in the build container, its .pyc under oracle/_ref elsewhere)."""
+    src = os.path.join(REFERENCE_ROOT, rel)
+    if os.path.exists(src):
+        spec = importlib.util.spec_from_file_location(name, src)
+        LOADED_FILES.add(src)
+    else:
+        pyc = src[:-3] + ".pyc"
+        spec = importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, pyc))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 # --------------------------------------------------------------------------------------
@@ -137,6 +165,9 @@ def _reference_tree(sub: str):
         sys.path.remove(path)
         for k in list(sys.modules):
             if k.split(".")[0] in ("models", "utils", "configs", "tasks", "dataset", "evaluation", "optimizers"):
+                f = getattr(sys.modules[k], "__file__", None)
+                if f and f.startswith(REFERENCE_ROOT) and f.endswith(".py"):
+                    LOADED_FILES.add(f)
                 del sys.modules[k]
         sys.modules.update(saved)
         for k, v in saved_tp.items():
@@ -238,10 +269,7 @@ def load_hhi():
             mt = e
         lossmod = None
         try:
-            spec = importlib.util.spec_from_file_location(
-                "_ref_hhi_asd_loss", os.path.join(REFERENCE_ROOT, "HHI/tasks/asd/loss.py"))
-            lossmod = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(lossmod)
+            lossmod = _load_file("_ref_hhi_asd_loss", "HHI/tasks/asd/loss.py")
         except Exception as e:  # pragma: no cover
             lossmod = e
     return SimpleNamespace(ttm=ttm, asd=asd, multitask=mt, asd_loss=lossmod)

@@ -19,7 +19,8 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:
         has_gpu = False
-    ref = os.path.isdir("/root/reference/HHI/models")
+    from oracle import ref_shims
+    ref = ref_shims.reference_available()      # the source tree, or its byte-compiled modules under oracle/_ref (GPU box)
     has_timeout = config.pluginmanager.hasplugin("timeout")
     for item in items:
         if "gpu" in item.keywords and has_timeout and item.get_closest_marker("timeout") is None:
@@ -27,7 +28,7 @@ def pytest_collection_modifyitems(config, items):
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "requires_reference" in item.keywords and not ref:
-            item.add_marker(pytest.mark.skip(reason="/root/reference not present"))
+            item.add_marker(pytest.mark.skip(reason="neither /root/reference nor oracle/_ref present"))
 
 
 @pytest.fixture(autouse=True)
