@@ -68,7 +68,30 @@ constexpr int AB = EGOT2_FFN_AB;           // acc1 buffers in TMEM (acc2 follows
 constexpr bool TS = EGOT2_FFN_TS != 0;
 constexpr int XB = AB * 128 + 128;         // TMEM column of the A tile (after acc1 buffers and acc2)
 static_assert(AB * 128 + 128 + (TS ? 64 : 0) <= 512, "TMEM: acc1 buffers + acc2 (+ A tile) must fit 512 columns");
-constexpr int NTHREADS = 384;
+// Epilogue parallelism: EG column groups x 4 TMEM lane quadrants = 4*EG epilogue warps per CTA, each thread one token row x
+// CW = 128/EG hidden columns of every chunk.  EG = 2 (8 warps x 64 columns, 144 registers) left two epilogue warps per
+// scheduler: each warp's own chain per chunk (accumulator wait -> tcgen05.ld -> ~330 dependent ALU instructions -> st.shared ->
+// fence -> arrive) took ~1.9k cycles at 32 % issue utilisation and set the chunk period, not the MMAs (1.0k) or shared memory
+// (1.5k).  EG = 4 (16 warps x 32 columns, <= 96 registers) halves that chain and doubles the warps that hide it.
+#ifndef EGOT2_FFN_EG
+#define EGOT2_FFN_EG 4
+#endif
+// EGOT2_FFN_DBG (timing experiments only - results are WRONG): bit 0 = the epilogue does not write the hidden tile to shared
+// memory, bit 1 = no TMA store of the hidden tile, bit 2 = the epilogue skips its arithmetic, bit 3 = GEMM2 is not issued,
+// bit 4 = GEMM1 is not issued, bit 5 = the weight stages are loaded only while the rings first fill (stale weights afterwards:
+// no L2 -> SM weight traffic in the steady state)
+#ifndef EGOT2_FFN_DBG
+#define EGOT2_FFN_DBG 0
+#endif
+constexpr int DBG = EGOT2_FFN_DBG;
+constexpr int EG = EGOT2_FFN_EG;
+constexpr int CW = 128 / EG;               // hidden columns per epilogue thread and chunk
+constexpr int EPW = 4 * EG;                // epilogue warps per CTA (warps 2 .. 2+EPW-1)
+constexpr int WS = 2 + EPW;                // TMA-store warp
+constexpr int WB = 3 + EPW;                // MMA issuer B
+constexpr int NTHREADS = 32 * (4 + EPW);
+static_assert(EG == 2 || EG == 4, "EG: 2 or 4 column groups");
+static_assert(!TS || EG == 2, "the TS (A tile in tensor memory) experiment is written for EG = 2");
 constexpr uint32_t TILE = 128 * 128 * 2;   // one 128x128 bf16 operand tile = two 16 KB K-halves
 constexpr uint32_t HALF = 16384;
 constexpr uint32_t STAGE = 16384;          // one weight stage
@@ -94,8 +117,13 @@ struct FfnArgs {
 
 #ifdef EGOT2_FFN_TRACE
 #define TR(c, slot) do { if (blockIdx.x == 0 && a.trace) a.trace[(c) * 16 + (slot)] = clock64(); } while (0)
+// per-warp stamps of the first cluster (both CTAs): [cta][warp][chunk][k], k = 0 accumulator seen, 1 hidden tile handed over
+// (globaltimer: comparable across the two SMs)
+#define TRW(c, k) do { if (blockIdx.x < 2 && a.trace && lane == 0 && (c) < 16) { unsigned long long t_; \
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[5120 + (((blockIdx.x * 24 + warp) * 16 + (c)) * 2 + (k))] = (long long)t_; } } while (0)
 #else
 #define TR(c, slot) do { } while (0)
+#define TRW(c, k) do { } while (0)
 #endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -145,12 +173,12 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   // barriers used in the leader only (arrivals from both CTAs)
   const uint32_t x_pair = a2_full + 8, r1_full = x_pair + 8, r2_full = r1_full + 8 * R1, a1_empty = r2_full + 8 * R2,
                  h_full = a1_empty + 8 * AB, xt_full = h_full + 8 * HB, tmem_slot = xt_full + 8;
-  const uint32_t red_off = (tmem_slot + 8 + 15u) & ~15u;   // float red[2][128] for the LayerNorm row statistics (16 B aligned)
+  const uint32_t red_off = (tmem_slot + 8 + 15u) & ~15u;   // float red[2][EG][128] for the LayerNorm row statistics (16 B aligned)
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));   // generic pointer to `base`
   float* red = reinterpret_cast<float*>(gen + (red_off - base));
   // bias / LayerNorm vectors live in shared memory: every lane of an epilogue warp reads the same column values, so
   // these are conflict-free broadcasts instead of a chain of dependent global loads on the per-chunk critical path
-  float* sVec = red + 512;                 // b2[128], ln_g[128], ln_b[128]   (red: sum[2][128], sumsq[2][128])
+  float* sVec = red + 2 * EG * 128;        // b2[128], ln_g[128], ln_b[128]   (red: sum[EG][128], sumsq[EG][128])
   float* sB1 = sVec + 384;                 // b1[FF]
   pdl_launch_dependents();       // the next kernel may become resident and run its prologue under this one
   const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(gen + (tmem_slot - base));
@@ -181,17 +209,56 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2);
     tma_prefetch_desc(&tm_hid); tma_prefetch_desc(&tm_y2); tma_prefetch_desc(&tm_out);
-    mbar_init(x_full, 1); mbar_init(x_pair, 2); mbar_init(a2_full, 1); mbar_init(xt_full, 16);
+    mbar_init(x_full, 1); mbar_init(x_pair, 2); mbar_init(a2_full, 1); mbar_init(xt_full, 2 * EPW);
     for (int s = 0; s < R1; ++s) { mbar_init(r1_full + 8 * s, 1); mbar_init(r1_empty + 8 * s, 1); }
     for (int s = 0; s < R2; ++s) { mbar_init(r2_full + 8 * s, 1); mbar_init(r2_empty + 8 * s, 1); }
-    for (int s = 0; s < AB; ++s) { mbar_init(a1_full + 8 * s, 1); mbar_init(a1_empty + 8 * s, 16); }
+    for (int s = 0; s < AB; ++s) { mbar_init(a1_full + 8 * s, 1); mbar_init(a1_empty + 8 * s, 2 * EPW); }
     for (int s = 0; s < HB; ++s) {
-      mbar_init(h_full + 8 * s, 16); mbar_init(hl_full + 8 * s, 8); mbar_init(h_empty + 8 * s, 1); mbar_init(hs_empty + 8 * s, 1);
+      mbar_init(h_full + 8 * s, 2 * EPW); mbar_init(hl_full + 8 * s, EPW); mbar_init(h_empty + 8 * s, 1); mbar_init(hs_empty + 8 * s, 1);
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
-  pdl_wait();                    // first global-memory access of the kernel is below
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                         // both CTAs' barriers are initialised before anything targets them remotely
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t acc2 = tmem + AB * 128;
+  // this CTA's half of the weight stage of local chunk i (the complete_tx goes to the LEADER's stage barrier, which expects
+  // the bytes of both halves)
+  auto load_w1 = [&](int i) {                 // GEMM1 operand of chunk i into W1-ring stage i % R1
+    const int s = i % R1;
+    const uint32_t bar = mapa(r1_full + 8 * s, 0);
+    if (leader) mbar_expect_tx(r1_full + 8 * s, 2 * STAGE);
+    if (!BWD) {       // GEMM1 B = W1 rows (ff) c*128 + rank*64 .., K-major: two 64-k halves
+      tma_load_2d_cg2(sW1 + s * STAGE, &tm_w1, bar, 0, (c_begin + i) * FC + rank * 64);
+      tma_load_2d_cg2(sW1 + s * STAGE + 8192, &tm_w1, bar, 64, (c_begin + i) * FC + rank * 64);
+    } else {          // GEMM1 B = W2[:, ff], MN-major: 128 k-rows (h) x this CTA's 64 ff columns, one box
+      tma_load_2d_cg2(sW1 + s * STAGE, &tm_w2, bar, (c_begin + i) * FC + rank * 64, 0);
+    }
+  };
+  auto load_w2 = [&](int i) {                 // GEMM2 operand of chunk i into W2-ring stage i % R2
+    const int s = i % R2;
+    const uint32_t bar = mapa(r2_full + 8 * s, 0);
+    if (leader) mbar_expect_tx(r2_full + 8 * s, 2 * STAGE);
+    if (!BWD) {       // GEMM2 B = W2 rows (h) rank*64 .., K-major over ff c*128 ..
+      tma_load_2d_cg2(sW2 + s * STAGE, &tm_w2, bar, (c_begin + i) * FC, rank * 64);
+      tma_load_2d_cg2(sW2 + s * STAGE + 8192, &tm_w2, bar, (c_begin + i) * FC + 64, rank * 64);
+    } else {          // GEMM2 B = W1[ff, :], MN-major: 128 k-rows (ff) x this CTA's 64 h columns
+      tma_load_2d_cg2(sW2 + s * STAGE, &tm_w1, bar, rank * 64, (c_begin + i) * FC);
+    }
+  };
+  // The first fill of both weight rings is requested BEFORE the programmatic-dependent-launch wait: the weights (and biases)
+  // are parameters - nothing the two launches in front of this one write (LayerNorm / GEMM / head kernels of the same layer;
+  // the optimizer that updates them is at least a whole stage away) - so their L2 -> SM latency (2-4k cycles at kernel start,
+  // when every pair asks for the same lines) overlaps the tail of the previous kernel instead of this kernel's first chunk.
+  const int pre1 = NC < R1 ? NC : R1, pre2 = NC < R2 ? NC : R2;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < pre1; ++i) load_w1(i);
+    for (int i = 0; i < pre2; ++i) load_w2(i);
+  }
+  pdl_wait();                    // first access to anything a previous kernel produced is below
   EGOT2_TL(EGOT2_FILE_ID);
   const unsigned long long egot2_ep = epoch_xor();
   if (BWD) {                     // sB1 doubles as this CTA's db1 accumulator (the forward's bias stage is not needed)
@@ -202,12 +269,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i] * s1;
     for (int i = threadIdx.x; i < 128; i += NTHREADS) { sVec[i] = a.b2[i]; sVec[128 + i] = a.ln_g[i]; sVec[256 + i] = a.ln_b[i]; }
   }
-  tc_fence_before();
   __syncthreads();
-  cluster_sync_all();                         // both CTAs' barriers are initialised before anything targets them remotely
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t acc2 = tmem + AB * 128;
   if (threadIdx.x == 64) TR(60, 1);
 
   if (warp == 0) {
@@ -216,39 +278,21 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       mbar_expect_tx(x_full, TILE);
       tma_load_2d(sX, &tm_x, x_full, 0, m0);
       tma_load_2d(sX + HALF, &tm_x, x_full, 64, m0);
-      // this CTA's 64 rows of every weight stage; the complete_tx goes to the LEADER's stage barrier, which expects the
-      // bytes of both halves.  The two rings are polled (try_wait) so that a full W2 ring never holds back W1 loads.
-      int i1 = 0, i2 = 0;
+      // the rings' first fill was requested in the prologue; from there on the two rings are polled (try_wait) so that a
+      // full W2 ring never holds back W1 loads
+      int i1 = pre1, i2 = pre2;
       while (i1 < NC || i2 < NC) {
-        if (i1 < NC) {                                // W1 rows c*128 + rank*64 .., all 128 k
-          const int s = i1 % R1;
-          if (mbar_try_wait(r1_empty + 8 * s, ((i1 / R1) & 1) ^ 1)) {
-            TR(i1, 0);
-            const uint32_t bar = mapa(r1_full + 8 * s, 0);
-            if (leader) mbar_expect_tx(r1_full + 8 * s, 2 * STAGE);
-            if (!BWD) {       // GEMM1 B = W1 rows (ff) c*128 + rank*64 .., K-major: two 64-k halves
-              tma_load_2d_cg2(sW1 + s * STAGE, &tm_w1, bar, 0, (c_begin + i1) * FC + rank * 64);
-              tma_load_2d_cg2(sW1 + s * STAGE + 8192, &tm_w1, bar, 64, (c_begin + i1) * FC + rank * 64);
-            } else {          // GEMM1 B = W2[:, ff], MN-major: 128 k-rows (h) x this CTA's 64 ff columns, one box
-              tma_load_2d_cg2(sW1 + s * STAGE, &tm_w2, bar, (c_begin + i1) * FC + rank * 64, 0);
-            }
-            ++i1;
-          }
+        if (i1 < NC && mbar_try_wait(r1_empty + 8 * (i1 % R1), ((i1 / R1) & 1) ^ 1)) {
+          TR(i1, 0);
+          if ((DBG & 32)) { if (leader) mbar_arrive(r1_full + 8 * (i1 % R1)); }
+          else load_w1(i1);
+          ++i1;
         }
-        if (i2 < NC && i2 < i1) {                     // W2 rows rank*64 .. (output features), k = ff c*128 ..
-          const int s = i2 % R2;
-          if (mbar_try_wait(r2_empty + 8 * s, ((i2 / R2) & 1) ^ 1)) {
-            TR(i2, 1);
-            const uint32_t bar = mapa(r2_full + 8 * s, 0);
-            if (leader) mbar_expect_tx(r2_full + 8 * s, 2 * STAGE);
-            if (!BWD) {       // GEMM2 B = W2 rows (h) rank*64 .., K-major over ff c*128 ..
-              tma_load_2d_cg2(sW2 + s * STAGE, &tm_w2, bar, (c_begin + i2) * FC, rank * 64);
-              tma_load_2d_cg2(sW2 + s * STAGE + 8192, &tm_w2, bar, (c_begin + i2) * FC + 64, rank * 64);
-            } else {          // GEMM2 B = W1[ff, :], MN-major: 128 k-rows (ff) x this CTA's 64 h columns
-              tma_load_2d_cg2(sW2 + s * STAGE, &tm_w1, bar, rank * 64, (c_begin + i2) * FC);
-            }
-            ++i2;
-          }
+        if (i2 < NC && i2 < i1 && mbar_try_wait(r2_empty + 8 * (i2 % R2), ((i2 / R2) & 1) ^ 1)) {
+          TR(i2, 1);
+          if ((DBG & 32)) { if (leader) mbar_arrive(r2_full + 8 * (i2 % R2)); }
+          else load_w2(i2);
+          ++i2;
         }
       }
     }
@@ -263,13 +307,16 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         if (TS) { mbar_wait(xt_full, 0); tc_fence_after(); }      // both CTAs' A tiles are in tensor memory
         for (int c = 0; c < NC; ++c) {
           const int bsel = c % AB, s = c % R1;
-          mbar_wait(a1_empty + 8 * bsel, ((c / AB) & 1) ^ 1);
-          TR(c, 3);
-          mbar_wait(r1_full + 8 * s, (c / R1) & 1);
-          TR(c, 2);
+          {   // both probes in flight together; the blocking waits only where a probe said "not yet"
+            const bool p0 = mbar_test_wait(a1_empty + 8 * bsel, ((c / AB) & 1) ^ 1), p1 = mbar_test_wait(r1_full + 8 * s, (c / R1) & 1);
+            if (!p0) mbar_wait(a1_empty + 8 * bsel, ((c / AB) & 1) ^ 1);
+            TR(c, 3);
+            if (!p1) mbar_wait(r1_full + 8 * s, (c / R1) & 1);
+            TR(c, 2);
+          }
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
+          for (int kk = 0; kk < ((DBG & 16) ? 0 : 8); ++kk) {
             if (TS) umma_bf16_cg2_ts(tmem + bsel * 128, tmem + XB + kk * 8, wdesc<BWD>(sW1 + s * STAGE, kk), idesc, kk > 0 ? 1u : 0u);
             else umma_bf16_cg2(tmem + bsel * 128, kdesc(sX, kk), wdesc<BWD>(sW1 + s * STAGE, kk), idesc, kk > 0 ? 1u : 0u);
           }
@@ -278,33 +325,36 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
       }
     }
-  } else if (warp == 11) {
+  } else if (warp == WB) {
     // ------------------------------------------------------------ MMA issuer B (leader): GEMM2(c): acc2 += hid(c) . W2c^T
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 128, false, BWD);
       for (int cp = 0; cp < NC; ++cp) {
         const int hb = cp % HB, s = cp % R2;
-        mbar_wait(h_full + 8 * hb, (cp / HB) & 1);
-        TR(cp, 5);
-        mbar_wait(r2_full + 8 * s, (cp / R2) & 1);
-        TR(cp, 4);
+        {
+          const bool p0 = mbar_test_wait(h_full + 8 * hb, (cp / HB) & 1), p1 = mbar_test_wait(r2_full + 8 * s, (cp / R2) & 1);
+          if (!p0) mbar_wait(h_full + 8 * hb, (cp / HB) & 1);
+          TR(cp, 5);
+          if (!p1) mbar_wait(r2_full + 8 * s, (cp / R2) & 1);
+          TR(cp, 4);
+        }
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
+        for (int kk = 0; kk < ((DBG & 8) ? 0 : 8); ++kk)
           umma_bf16_cg2(acc2, kdesc(sHid + hb * TILE, kk), wdesc<BWD>(sW2 + s * STAGE, kk), idesc, (cp > 0 || kk > 0) ? 1u : 0u);
         umma_commit_cg2(r2_empty + 8 * s, 3);
         umma_commit_cg2(h_empty + 8 * hb, 3);         // hid buffers may be overwritten (once the TMA stores have read them too)
       }
       umma_commit_cg2(a2_full, 3);
     }
-  } else if (warp == 10) {
+  } else if (warp == WS) {
     // ------------------------------------------------------------ TMA store of the hidden tile (saved for backward)
     if (lane == 0) {
       for (int c = 0; c < NC; ++c) {
         const int hb = c % HB;
         mbar_wait(hl_full + 8 * hb, (c / HB) & 1);      // this CTA's epilogue wrote (and proxy-fenced) hid(c)
         TR(c, 11);
-        if (a.save_hid) {
+        if (a.save_hid && !(DBG & 2)) {
           if (a.hid_tiled) {      // box (tile, ff-half) is one contiguous 16 KB block
             const int row = ((m0 / BM) * (a.FF / 64) + (c_begin + c) * 2) * 128;
             tma_store_2d(&tm_hid, sHid + hb * TILE, 0, row);
@@ -319,12 +369,14 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         TR(c, 12);
         mbar_arrive(hs_empty + 8 * hb);
       }
-      tma_store_wait_all();
+      tma_store_wait_read();                  // shared memory may be released; the writes are complete when the grid is
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                  // TMEM lane quadrant
-    const int ch = (warp - 2) >> 2;          // which 64-column half of the 128-column tile
+    const int ch = (warp - 2) >> 2;          // which CW-column group of the 128-column tile
+    const int half = (ch * CW) >> 6;         // the 64-column K-half of the swizzled tiles that group lives in ...
+    const int jb = ((ch * CW) & 63) >> 3;    // ... and its first 16-byte chunk inside the 128-byte swizzle row
     const int r = q * 32 + lane;             // row inside the tile == TMEM lane
     const int m = m0 + r;
     const bool row_ok = m < a.M;
@@ -334,7 +386,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t a1_empty_ldr = mapa(a1_empty, 0), h_full_ldr = mapa(h_full, 0);
     // backward: the ReLU/dropout gate bits of chunk c+1 are fetched while chunk c is processed (a dependent global
     // load in front of every chunk's arithmetic was ~1 us of exposed latency per chunk)
-    if (TS) {
+    if constexpr (TS) {
       // this thread's half row of the A tile (64 bf16 = 32 packed words, k ascending) from the swizzled smem tile into TMEM
       mbar_wait(x_full, 0);
       uint32_t xw[32];
@@ -349,34 +401,52 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa(xt_full, 0));
     }
-    uint2 gate_next = make_uint2(0u, 0u);
-    if (BWD && row_ok) gate_next = __ldg(a.hmask + (size_t)(c_begin * 2 + ch) * a.M + m);
+    // gate words: hmask is [FF/64][M] x 64 bit; this thread owns CW/32 consecutive 32-bit words of its row's 64-bit entry
+    const uint32_t* hm32 = reinterpret_cast<const uint32_t*>(a.hmask);
+    auto gate_idx = [&](int cgl) { return ((size_t)(cgl * 2 + half) * a.M + m) * 2 + (((ch * CW) & 63) >> 5); };
+    uint32_t gate_next[CW / 32] = {};
+    if (BWD && row_ok) {
+#pragma unroll
+      for (int w = 0; w < CW / 32; ++w) gate_next[w] = __ldg(hm32 + gate_idx(c_begin) + w);
+    }
     for (int c = 0; c < NC; ++c) {
       const int bsel = c % AB;
       const int hb = c % HB;
-      const uint2 gate_cur = gate_next;
+      uint32_t gate_cur[CW / 32];
+#pragma unroll
+      for (int w = 0; w < CW / 32; ++w) gate_cur[w] = gate_next[w];
       const int cg = c_begin + c;
-      if (BWD && row_ok && c + 1 < NC) gate_next = __ldg(a.hmask + (size_t)((cg + 1) * 2 + ch) * a.M + m);
-      const uint32_t hrow = sHid + hb * TILE + ch * HALF + (uint32_t)r * 128;
+      if (BWD && row_ok && c + 1 < NC) {
+#pragma unroll
+        for (int w = 0; w < CW / 32; ++w) gate_next[w] = __ldg(hm32 + gate_idx(cg + 1) + w);
+      }
+      const uint32_t hrow = sHid + hb * TILE + half * HALF + (uint32_t)r * 128;
       mbar_wait(a1_full + 8 * bsel, (c / AB) & 1);
       if (threadIdx.x == 64) TR(c, 6);
+      TRW(c, 0);
       tc_fence_after();
-      uint32_t packed[32];
-      uint32_t rr0[32], rr1[32];
-      tmem_ld_32x32(tmem + lane_addr + bsel * 128 + ch * 64, rr0);
-      tmem_ld_32x32(tmem + lane_addr + bsel * 128 + ch * 64 + 32, rr1);
+      // probe the hidden-tile buffer's two release barriers now, consume the answer after the arithmetic
+      bool buf_free = true;
+      if (c >= HB) buf_free = mbar_test_wait(h_empty + 8 * hb, ((c - HB) / HB) & 1) & mbar_test_wait(hs_empty + 8 * hb, ((c - HB) / HB) & 1);
+      uint32_t packed[CW / 2];
+      uint32_t rra[CW / 32][32];
+#pragma unroll
+      for (int w = 0; w < CW / 32; ++w) tmem_ld_32x32(tmem + lane_addr + bsel * 128 + ch * CW + w * 32, rra[w]);
       tmem_ld_wait();
       if (threadIdx.x == 64) TR(c, 7);
       // acc1[bsel] is in registers: hand the accumulator back (to the leader's MMA thread) before the arithmetic
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(a1_empty_ldr + 8 * bsel);
-      if (!BWD) {
-        uint32_t gate[2];
+      if constexpr ((DBG & 4) != 0) {
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
-          const int n0 = cg * FC + ch * 64 + h2 * 32;
+        for (int j = 0; j < CW / 2; ++j) packed[j] = rra[j / 16][(2 * j) % 32];
+      } else if (!BWD) {
+        uint32_t gate[CW / 32];
+#pragma unroll
+        for (int h2 = 0; h2 < CW / 32; ++h2) {
+          const uint32_t (&rr)[32] = rra[h2];
+          const int n0 = cg * FC + ch * CW + h2 * 32;
           const uint64_t idx0 = (uint64_t)m * a.FF + n0;          // multiple of 32: this thread owns one 32-bit mask word
           // pre-activations (dropout scale folded in: relu(acc + b) / (1-p) == relu(acc/(1-p) + b/(1-p)), sB1 holds the
           // pre-scaled bias in training), and the word of their sign bits gathered with one funnel shift per element
@@ -415,13 +485,16 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
           gate[h2] = gw;
         }
-        if (a.hmask && row_ok) a.hmask[(size_t)(cg * 2 + ch) * a.M + m] = make_uint2(gate[0], gate[1]);
+        if (a.hmask && row_ok) {
+          uint32_t* hw = reinterpret_cast<uint32_t*>(a.hmask) + gate_idx(cg);
+          if constexpr (CW == 64) *reinterpret_cast<uint2*>(hw) = make_uint2(gate[0], gate[CW / 32 - 1]);
+          else hw[0] = gate[0];
+        }
       } else {
-        const uint2 gate = gate_cur;
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const uint32_t (&rr)[32] = h2 ? rr1 : rr0;
-          const uint32_t gw = h2 ? gate.y : gate.x;
+        for (int h2 = 0; h2 < CW / 32; ++h2) {
+          const uint32_t (&rr)[32] = rra[h2];
+          const uint32_t gw = gate_cur[h2];
           float cs[32];          // this row's 32 dhid values; reduced over the warp's 32 rows below
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -447,24 +520,25 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 cs[i] = (up ? cs[i + s] : cs[i]) + recv;
               }
             }
-            atomicAdd(sB1 + cg * FC + ch * 64 + h2 * 32 + lane, cs[0]);
+            atomicAdd(sB1 + cg * FC + ch * CW + h2 * 32 + lane, cs[0]);
           }
         }
       }
       // the hid buffer is free once GEMM2(c-HB) retired and the TMA store of chunk c-HB has read it
       if (threadIdx.x == 64) TR(c, 8);
-      if (c >= HB) {
+      if (c >= HB && !buf_free) {
         mbar_wait(h_empty + 8 * hb, ((c - HB) / HB) & 1);
         mbar_wait(hs_empty + 8 * hb, ((c - HB) / HB) & 1);
       }
       if (threadIdx.x == 64) TR(c, 9);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)             // 8 x 16 B chunks = this thread's 64 columns, 128B-swizzled row
-        sts128(hrow + (uint32_t)((j ^ (r & 7)) << 4), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      for (int j = 0; j < CW / 8; ++j)        // CW/8 x 16 B chunks = this thread's CW columns, 128B-swizzled row
+        if (!(DBG & 1) || a.M < 0) sts128(hrow + (uint32_t)(((jb + j) ^ (r & 7)) << 4), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { mbar_arrive_cluster(h_full_ldr + 8 * hb); mbar_arrive(hl_full + 8 * hb); }
       if (threadIdx.x == 64) TR(c, 10);
+      TRW(c, 1);
     }
     // ------------------------------------------------------------ final: + b2, dropout2, + residual, LayerNorm2
     mbar_wait(a2_full, 0);                    // every GEMM of the pair retired: sHid / sX are free to stage the outputs
@@ -476,15 +550,15 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // The final epilogue runs ONCE per CTA: fully unrolled over 64 columns it was ~2k straight-line instructions whose
     // cold instruction-cache misses cost ~20k cycles per CTA (stall_no_inst in ncu).  It is therefore written as two
     // compact loops over 8-column groups (8-column TMEM loads, nothing indexed dynamically).
-    const int nb = ch * 64;
-    const uint32_t xrow = sX + ch * HALF + (uint32_t)r * 128;
-    const uint32_t yrow = sHid + ch * HALF + (uint32_t)r * 128;
+    const int nb = ch * CW;
+    const uint32_t xrow = sX + half * HALF + (uint32_t)r * 128;
+    const uint32_t yrow = sHid + half * HALF + (uint32_t)r * 128;
     if (split) {
       // FF-split tail unit: this pair's partial sum over its chunk range joins the others' in fp32; the fix-up kernel
       // applies everything that follows the second GEMM once all S partials are in
       float* prow = a.partial + ((size_t)(m - a.split_pair0 * 2 * BM)) * H + nb;
 #pragma unroll 1
-      for (int j8 = 0; j8 < 8; ++j8) {
+      for (int j8 = 0; j8 < CW / 8; ++j8) {
         uint32_t rr[8];
         tmem_ld_32x8(acc2 + lane_addr + nb + j8 * 8, rr);
         tmem_ld_wait();
@@ -495,12 +569,12 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       }
     } else if constexpr (BWD) {
       // d3 = acc2 + d1 (gradient through the residual branch); with no dropout2, d1 IS the d2 tile still in sX
-      const bf16* d1row = (a.d1 && row_ok) ? a.d1 + (size_t)m * H + nb : nullptr;
+      const bf16* d1row = (a.d1 && row_ok) ? a.d1 + (size_t)m * H + nb : nullptr;      // nb is a multiple of 32: 16 B aligned
 #pragma unroll 1
-      for (int j8 = 0; j8 < 8; ++j8) {
+      for (int j8 = 0; j8 < CW / 8; ++j8) {
         uint32_t rr[8];
         tmem_ld_32x8(acc2 + lane_addr + nb + j8 * 8, rr);
-        const uint32_t sw = (uint32_t)((j8 ^ (r & 7)) << 4);
+        const uint32_t sw = (uint32_t)(((jb + j8) ^ (r & 7)) << 4);
         uint32_t w0, w1, w2, w3;
         if (a.d1) {
           uint4 t = make_uint4(0u, 0u, 0u, 0u);
@@ -521,22 +595,22 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         sts128(yrow + sw, oo[0], oo[1], oo[2], oo[3]);
       }
       fence_proxy_async();
-      named_bar_sync(2, 256);
+      named_bar_sync(2, EPW * 32);
       if (warp == 2 && lane == 0) {
         tma_store_2d(&tm_y2, sHid, 0, m0);
         tma_store_2d(&tm_y2, sHid + HALF, 64, m0);
         tma_store_commit();
-        tma_store_wait_all();
+        tma_store_wait_read();
       }
     } else {
       // pass 1: y = acc2 + b2 -> dropout2 -> + x1, rounded to bf16 (what LayerNorm2 sees and what is saved); staged in the
       // first hid buffer; row sum / sum of squares on the rounded values
       float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-      for (int j8 = 0; j8 < 8; ++j8) {
+      for (int j8 = 0; j8 < CW / 8; ++j8) {
         uint32_t rr[8];
         tmem_ld_32x8(acc2 + lane_addr + nb + j8 * 8, rr);
-        const uint32_t sw = (uint32_t)((j8 ^ (r & 7)) << 4);
+        const uint32_t sw = (uint32_t)(((jb + j8) ^ (r & 7)) << 4);
         uint32_t w0, w1, w2, w3;                  // residual: 8 bf16 of x1 from the swizzled smem tile
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(xrow + sw));
         tmem_ld_wait();
@@ -562,17 +636,20 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         sts128(yrow + sw, yy[0], yy[1], yy[2], yy[3]);
       }
       red[ch * 128 + r] = sum;
-      red[256 + ch * 128 + r] = sq;
-      named_bar_sync(1, 256);
-      const float mean = (red[r] + red[128 + r]) * (1.f / H);
-      const float var = fmaxf((red[256 + r] + red[384 + r]) * (1.f / H) - mean * mean, 0.f);
+      red[EG * 128 + ch * 128 + r] = sq;
+      named_bar_sync(1, EPW * 32);
+      float tsum = 0.f, tsq = 0.f;
+#pragma unroll
+      for (int e = 0; e < EG; ++e) { tsum += red[e * 128 + r]; tsq += red[EG * 128 + e * 128 + r]; }
+      const float mean = tsum * (1.f / H);
+      const float var = fmaxf(tsq * (1.f / H) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + a.eps);
       if (row_ok && ch == 0) { a.stat2[2 * (size_t)m] = mean; a.stat2[2 * (size_t)m + 1] = rstd; }
       // pass 2: x_out = (y - mean) * rstd * g + b, staged in the x1 tile (its residual reads are done)
       const uint32_t orow = xrow;
 #pragma unroll 1
-      for (int j8 = 0; j8 < 8; ++j8) {
-        const uint32_t sw = (uint32_t)((j8 ^ (r & 7)) << 4);
+      for (int j8 = 0; j8 < CW / 8; ++j8) {
+        const uint32_t sw = (uint32_t)(((jb + j8) ^ (r & 7)) << 4);
         uint32_t w0, w1, w2, w3;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(yrow + sw));
         const uint32_t w[4] = {w0, w1, w2, w3};
@@ -588,14 +665,14 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         sts128(orow + sw, oo[0], oo[1], oo[2], oo[3]);
       }
       fence_proxy_async();
-      named_bar_sync(2, 256);
+      named_bar_sync(2, EPW * 32);
       if (warp == 2 && lane == 0) {
         tma_store_2d(&tm_y2, sHid, 0, m0);
         tma_store_2d(&tm_y2, sHid + HALF, 64, m0);
         tma_store_2d(&tm_out, sX, 0, m0);
         tma_store_2d(&tm_out, sX + HALF, 64, m0);
         tma_store_commit();
-        tma_store_wait_all();
+        tma_store_wait_read();
       }
     }
   }
@@ -733,7 +810,7 @@ bool ffn_fused_supported(int dtype, int Hdim, int FF) {
 
 static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2,
                       const CUtensorMap& thid, const CUtensorMap& ty2, const CUtensorMap& tout, FfnArgs& a, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)TILE * (1 + HB) + (size_t)RING * STAGE + 512 + (512 + 384 + (size_t)FF) * 4;
+  const size_t smem = 1024 + (size_t)TILE * (1 + HB) + (size_t)RING * STAGE + 512 + (2 * EG * 128 + 384 + (size_t)FF) * 4;
   EGOT2_CHECK(smem <= 227 * 1024, "ffn_fused: FF=%d does not fit the bias stage in shared memory", FF);
   const int drop = bwd ? 0 : (a.p_drop <= 0.f ? 0 : (a.p_drop == 0.5f ? 1 : 2));
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FfnArgs);
@@ -748,8 +825,8 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
   a.trace = nullptr;
 #ifdef EGOT2_FFN_TRACE
   static long long* dtrace = nullptr;
-  if (!dtrace) cudaMalloc(&dtrace, (1024 + 4 * 1024) * 8);
-  cudaMemsetAsync(dtrace, 0, (1024 + 4 * 1024) * 8, st);
+  if (!dtrace) cudaMalloc(&dtrace, (5120 + 2 * 24 * 16 * 2) * 8);
+  cudaMemsetAsync(dtrace, 0, (5120 + 2 * 24 * 16 * 2) * 8, st);
   a.trace = dtrace;
 #endif
   {
@@ -799,7 +876,7 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
     static int printed = 0;
     static const int trace_at = getenv("EGOT2_FFN_TRACE_AT") ? atoi(getenv("EGOT2_FFN_TRACE_AT")) : 3;
     if (printed++ == trace_at) {
-      static long long h[1024 + 4 * 1024];
+      static long long h[5120 + 2 * 24 * 16 * 2];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, dtrace, sizeof(h), cudaMemcpyDeviceToHost);
       long long t0 = h[0];
@@ -811,6 +888,18 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
         for (int k = 0; k < 13; ++k) printf(" %7lld%s", h[c * 16 + k] ? h[c * 16 + k] - t0 : -1LL, (k == 1 || k == 5 || k == 10) ? " |" : "");
         printf("\n");
       }
+      // per-warp view: ns since the earliest stamp; rows = (cta, warp), columns = chunks, "seen/handed"
+      long long w0 = 0;
+      for (int i = 5120; i < 5120 + 2 * 24 * 16 * 2; ++i) if (h[i] > 0 && (w0 == 0 || h[i] < w0)) w0 = h[i];
+      for (int cta = 0; cta < 2; ++cta)
+        for (int w = 2; w < 2 + EPW; ++w) {
+          printf("cta%d w%02d q%d g%d |", cta, w, w & 3, (w - 2) >> 2);
+          for (int c = 0; c < 16 && c < FF / FC; ++c) {
+            const long long* e = h + 5120 + ((cta * 24 + w) * 16 + c) * 2;
+            printf(" %5lld/%5lld", e[0] ? e[0] - w0 : -1LL, e[1] ? e[1] - w0 : -1LL);
+          }
+          printf("\n");
+        }
     }
   }
 #endif
