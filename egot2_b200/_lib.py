@@ -135,6 +135,10 @@ SIGNATURES = {
     "egot2_dropout_epoch_advance": (C.c_int, [vp]),
     "egot2_dropout_epoch_host": (C.c_int, [u64]),
     "egot2_pnr_metrics": (C.c_int, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "egot2_row_softmax": (C.c_int, [C.c_int64, i32, vp, vp, vp]),
+    "egot2_segment_softmax_mean": (C.c_int, [i32, i32, vp, vp, vp, vp]),
+    "egot2_topk_correct": (C.c_int, [i32, i32, vp, vp, i32, vp, vp, vp]),
+    "egot2_edit_distance_prefix": (C.c_int, [i32, i32, i32, vp, vp, vp, vp, vp]),
     "egot2_prof_enable": (C.c_int, [C.c_int]),
     "egot2_side_defer": (C.c_int, [C.c_int]),
     "egot2_side_join_all": (C.c_int, [vp]),

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib
 from .engine import TranslatorEngine
-from .modules import PrecomputedFeatures, TranslatorBase
+from .modules import PrecomputedFeatures, TranslatorBase, device_softmax
 from .functional import translator_apply
 from .specs import hhi_asd_spec, hhi_g_spec, hhi_ttm_spec
 
@@ -271,7 +271,7 @@ class lossAV(nn.Module):
             logits, _ = linear_ce(x, self.FC.weight, self.FC.bias, None, None)
             return logits[:, 1].t().reshape(-1).detach().cpu().numpy()
         logits, nloss = linear_ce(x, self.FC.weight, self.FC.bias, labels, self.criterion.weight)
-        predScore = torch.softmax(logits.detach(), dim=-1)
+        predScore = device_softmax(logits)
         predLabel = torch.round(predScore)[:, 1]
         correctNum = (predLabel == labels).sum().float()
         return nloss, predScore, predLabel, correctNum

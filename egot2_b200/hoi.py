@@ -29,7 +29,7 @@ from torch.distributions.categorical import Categorical
 from . import _lib as L
 from .engine import TranslatorEngine, _stream
 from .functional import translator_apply
-from .modules import PrecomputedFeatures, TranslatorBase
+from .modules import PrecomputedFeatures, TranslatorBase, device_mean_dim1, device_softmax
 from .specs import (hoi_ar2_spec, hoi_ar_spec, hoi_g_spec, hoi_lta2_spec, hoi_lta_spec, hoi_pnr2_spec, hoi_pnr2_vit_spec,
                     hoi_pnr_spec, hoi_pnr_vit_spec)
 
@@ -443,7 +443,7 @@ class _LTA4Task(TranslatorBase):
         return torch.stack(feats, dim=1)                       # (bs, num_inputs, d)
 
     def encode_clips_pnr(self, model, x):
-        feats = [model([x[:, i, ...]], middle=True).mean(dim=1) for i in range(x.shape[1])]
+        feats = [device_mean_dim1(model([x[:, i, ...]], middle=True)) for i in range(x.shape[1])]
         return torch.stack(feats, dim=1)                       # (bs, num_inputs, 8192)
 
     def translate(self, pnr, oscc, action, lta):
@@ -452,7 +452,7 @@ class _LTA4Task(TranslatorBase):
         B = out.shape[0]
         out = out.view(B, len(self.head.projections), -1)
         if not self.training and not self.test_noact:
-            out = torch.softmax(out, dim=-1)                   # MultiTaskHead eval activation (head_helper.py:284-286)
+            out = device_softmax(out)                          # MultiTaskHead eval activation (head_helper.py:284-286)
         return list(torch.split(out, self.num_classes, dim=-1))
 
     def forward(self, x_lta, x_pnr):
@@ -519,7 +519,7 @@ class _LTA2Task(TranslatorBase):
         B = out.shape[0]
         out = out.view(B, len(self.head.projections), -1)
         if not self.training and not self.test_noact:
-            out = torch.softmax(out, dim=-1)                   # MultiTaskHead eval activation (head_helper.py:284-286)
+            out = device_softmax(out)                          # MultiTaskHead eval activation (head_helper.py:284-286)
         return list(torch.split(out, self.num_classes, dim=-1))
 
     def forward(self, x, tgts=None):

@@ -9,6 +9,7 @@ through libegot2.so.  `_poison_containers` makes that a hard guarantee.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Dict, List, Optional, Sequence
 
@@ -41,6 +42,42 @@ class PrecomputedFeatures(nn.Module):
         if isinstance(x, dict):
             return x[self.key]
         return x
+
+
+def _device_ctx(device: torch.device):
+    return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
+
+
+def device_softmax(x: torch.Tensor) -> torch.Tensor:
+    """softmax over the last dimension by libegot2 (egot2_row_softmax), fp32; no autograd (evaluation-time activations:
+    HOI/models/lta/head_helper.py:284-286, HHI/tasks/asd/loss.py:24)."""
+    _require_cuda(x.device)
+    from .engine import _stream
+    xin = x.detach().to(torch.float32).contiguous()
+    out = torch.empty_like(xin)
+    n = xin.shape[-1]
+    with _device_ctx(x.device):
+        _lib.call("egot2_row_softmax", xin.numel() // n, n, xin.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def device_mean_dim1(x: torch.Tensor) -> torch.Tensor:
+    """x.mean(dim=1) of a (B, D, K) feature map by libegot2 (egot2_pool_fwd: one pass, fp32 accumulation); the temporal
+    mean of the PNR / OSCC features in front of the LTA translator (HOI/models/lta/lta_models_lta_transfer.py:339-346).
+    The backbones are frozen: no autograd."""
+    _require_cuda(x.device)
+    from .engine import _stream
+    assert x.dim() == 3
+    xin = x.detach()
+    if xin.dtype not in (torch.float32, torch.bfloat16):
+        xin = xin.to(torch.float32)
+    xin = xin.contiguous()
+    B, D, K = xin.shape
+    out = torch.empty((B, K), device=x.device, dtype=torch.float32)
+    with _device_ctx(x.device):
+        _lib.call("egot2_pool_fwd", _lib.F32 if xin.dtype == torch.float32 else _lib.BF16, B, D, K, 1, D, xin.data_ptr(),
+                  out.data_ptr(), _stream())
+    return out.to(x.dtype)
 
 
 def _require_cuda(device: torch.device):

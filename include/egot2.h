@@ -408,6 +408,26 @@ int egot2_pnr_metrics(int32_t B, int32_t n, const float* logits, const int64_t* 
                       const int64_t* sc_label, const double* fps, const int64_t* start_frame, const int64_t* end_frame,
                       const int64_t* pnr_frame, double* err_sec, int64_t* out_counts, double* out_dist_sum, void* stream);
 
+/* TTM evaluation (HHI/utils/ttm/utils.py:71-80, PostProcessor._merge_output): out[s, :] = softmax(mean over rows
+ * [seg_offsets[s], seg_offsets[s+1]) of logits (rows, n_cls)), one launch for all segments; the TTM score is out[s, 1].
+ * n_cls <= 8; device pointers; seg_offsets has n_seg + 1 entries. */
+int egot2_segment_softmax_mean(int32_t n_seg, int32_t n_cls, const float* logits, const int32_t* seg_offsets, float* out,
+                               void* stream);
+/* out = softmax(in) over the n columns of every row (fp32; may alias): the eval-mode activation of the LTA MultiTaskHead
+ * (HOI/models/lta/head_helper.py:284-286) and lossAV's predScore (HHI/tasks/asd/loss.py:24). */
+int egot2_row_softmax(int64_t rows, int32_t n, const float* in, float* out, void* stream);
+/* LTA / AR evaluation (HOI/evaluation/lta/lta_metrics.py:39-73, topks_correct): correct[i] = number of rows whose label is among
+ * the ks[i] largest of preds (N, C) (ties resolved towards the smaller class index); ks is a HOST array of n_k <= 8 values;
+ * correct is a device array of n_k int64, overwritten. */
+int egot2_topk_correct(int32_t N, int32_t C, const float* preds, const int64_t* labels, int32_t n_k, const int32_t* ks_host,
+                       int64_t* correct, void* stream);
+/* LTA evaluation (lta_metrics.py:87-110, edit_distance / AUED; `editdistance.eval` = Levenshtein distance): for every clip n and
+ * prefix length z = 1..Z, min over the K sampled sequences of lev(preds[n, :z, k], labels[n, :z]) -> min_dist[n, z-1] (optional)
+ * and sum_min[z-1] = sum over the clips (int64, overwritten).  preds (N, Z, K) and labels (N, Z) int64; Z <= 64.
+ * ED_z of the reference = sum_min[z-1] / (z * N); AUED = trapz(ED) / (Z - 1). */
+int egot2_edit_distance_prefix(int32_t N, int32_t Z, int32_t K, const int64_t* preds, const int64_t* labels, int32_t* min_dist,
+                               int64_t* sum_min, void* stream);
+
 /* ------------------------------------------------------------------ op-level entry points (diagnostics / unit tests) */
 /* C[M,N] = op(A)[M,K] . op(B)[K,N] (+bias[N]) ; A stored (M,K) or, if trans_a, (K,M); B stored (K,N) or, if
  * trans_b, (N,K) [nn.Linear weight layout]; relu optional; C fp32 or bf16 per `dtype` (A,B in `dtype`). */

@@ -139,6 +139,10 @@ def pool_fwd(dtype, B, T, H, pool, row_tokens, x, out, st):
         _f32(out, B * row_tokens, H).copy_(xt[:, :row_tokens].reshape(-1, H))
 
 
+def row_softmax(rows, n, x, out, st):
+    _f32(out, rows, n).copy_(torch.softmax(_f32(x, rows, n), dim=-1))
+
+
 def head_loss_fwd(desc, hin, hout, st):
     d, i, o = _st(desc, L.HeadDesc), _st(hin, L.HeadIn), _st(hout, L.HeadOut)
     _need_fp32(d.dtype)
@@ -356,7 +360,8 @@ BACKWARD = {"egot2_encoder_layer_bwd": encoder_layer_bwd, "egot2_vit_layer_bwd":
 
 FORWARD = {"egot2_hhi_tok_table_fwd": tok_table_fwd, "egot2_embed_fwd": embed_fwd, "egot2_encoder_layer_fwd": encoder_layer_fwd,
            "egot2_vit_layer_fwd": vit_layer_fwd, "egot2_prompt_embed_fwd": prompt_embed_fwd,
-           "egot2_decoder_layer_fwd": decoder_layer_fwd, "egot2_pool_fwd": pool_fwd, "egot2_head_loss_fwd": head_loss_fwd}
+           "egot2_decoder_layer_fwd": decoder_layer_fwd, "egot2_pool_fwd": pool_fwd, "egot2_head_loss_fwd": head_loss_fwd,
+           "egot2_row_softmax": row_softmax}
 
 
 def install(monkeypatch):
