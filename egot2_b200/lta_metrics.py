@@ -46,7 +46,8 @@ def topks_correct(preds: torch.Tensor, labels: torch.Tensor, ks: Sequence[int]) 
     assert preds.size(0) == labels.size(0), "Batch dim of predictions and labels must match"
     _need_cuda(preds, "topks_correct")
     dev = preds.device
-    p = preds.reshape(preds.shape[0], -1).to(torch.float32).contiguous()
+    assert preds.dim() == 2, "preds: (N, classes)"
+    p = preds.to(torch.float32).contiguous()
     lab = labels.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
     ks = [int(k) for k in ks]
     arr = (C.c_int32 * len(ks))(*ks)
