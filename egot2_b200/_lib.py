@@ -98,6 +98,13 @@ class HeadOut(C.Structure):
     _fields_ = [(n, vp) for n in ["pooled", "stat", "g", "logits", "loss", "argmax", "row_loss"]]
 
 
+class DpDesc(C.Structure):
+    _fields_ = [("world", i32), ("rank", i32), ("numel", C.c_int64), ("slab", vp * 8), ("off_param", C.c_int64),
+                ("off_grad", C.c_int64), ("off_shadow", C.c_int64), ("off_flags", C.c_int64), ("exp_avg", vp), ("exp_avg_sq", vp),
+                ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("step", i32), ("step_dev", vp),
+                ("decoupled", i32)]
+
+
 class HeadGrads(C.Structure):
     _fields_ = [(n, vp) for n in ["ln_g", "ln_b", "w", "b"]]
 
@@ -140,6 +147,14 @@ SIGNATURES = {
     "egot2_topk_correct": (C.c_int, [i32, i32, vp, vp, i32, vp, vp, vp]),
     "egot2_edit_distance_prefix": (C.c_int, [i32, i32, i32, vp, vp, vp, vp, vp]),
     "egot2_prof_enable": (C.c_int, [C.c_int]),
+    "egot2_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "egot2_peer_free": (C.c_int, [vp]),
+    "egot2_peer_handle_bytes": (C.c_int, []),
+    "egot2_peer_export": (C.c_int, [vp, vp]),
+    "egot2_peer_import": (C.c_int, [vp, C.POINTER(vp)]),
+    "egot2_peer_unimport": (C.c_int, [vp]),
+    "egot2_dp_flag_bytes": (C.c_size_t, []),
+    "egot2_dp_reduce_adam": (C.c_int, [vp, vp]),
     "egot2_side_defer": (C.c_int, [C.c_int]),
     "egot2_side_join_all": (C.c_int, [vp]),
     "egot2_timeline_set": (C.c_int, [vp]),

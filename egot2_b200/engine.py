@@ -106,6 +106,23 @@ class ParamArena:
         self.shadow_fresh = False
         self.head_w_names, self.head_b_names = head_w, head_b
 
+    def rebase(self, param: torch.Tensor, grad: torch.Tensor, shadow: Optional[torch.Tensor]):
+        """Move the arena into caller-provided storage (same layout; e.g. an IPC-shared slab, parallel.PeerExchange): the
+        current contents are copied over and every later call reads the new buffers.  Only for trainer-owned arenas, before
+        any CUDA graph is captured - the drop-in nn.Modules alias their nn.Parameters to the original storage."""
+        assert param.numel() == self.numel and grad.numel() == self.numel and param.dtype == grad.dtype == torch.float32
+        param.copy_(self.param)
+        grad.copy_(self.grad)
+        if shadow is not None:
+            assert shadow.numel() == self.numel and shadow.dtype == torch.bfloat16
+            if self.shadow is not None:
+                shadow.copy_(self.shadow)
+            else:
+                self.shadow_fresh = False
+        self.param, self.grad = param, grad
+        if shadow is not None:
+            self.shadow = shadow
+
     def view(self, name: str, base: Optional[torch.Tensor] = None) -> torch.Tensor:
         base = self.param if base is None else base
         shp = self.shapes[name]

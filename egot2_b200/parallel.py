@@ -68,3 +68,104 @@ def gather_outputs(local_out: torch.Tensor, n_clips: int, group=None) -> torch.T
         lo, hi = shard_range(n_clips, world, r)
         out.append(p[: hi - lo])
     return torch.cat(out, dim=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The exchange step as one kernel over NVLink peer memory (csrc/peer.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+def slab_layout(numel: int, with_shadow: bool, flag_bytes: int):
+    """Byte offsets of (param fp32, grad fp32, shadow bf16 | -1, flags) inside a rank's slab and the slab size; identical
+    on every rank by construction (a pure function of the arena size)."""
+    a = lambda x: (x + 255) // 256 * 256
+    off_param = 0
+    off_grad = a(off_param + 4 * numel)
+    off_shadow = a(off_grad + 4 * numel) if with_shadow else -1
+    off_flags = a((off_shadow + 2 * numel) if with_shadow else (off_grad + 4 * numel))
+    return off_param, off_grad, off_shadow, off_flags, off_flags + flag_bytes
+
+
+class _DeviceMemory:
+    """Zero-copy view of raw device memory for torch (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """Puts an engine's parameter / gradient / bf16-shadow arenas into an IPC-shared slab, maps every peer's slab, and runs
+    `egot2_dp_reduce_adam` - gradient reduce-scatter + Adam on this rank's slice + parameter all-gather in ONE kernel - in
+    place of [NCCL all-reduce + fused Adam].  One node, at most 8 ranks, every GPU peer-accessible (NVSwitch).
+
+    `available()` is False (and the trainer keeps the NCCL path) for CPU process groups, more than 8 ranks, or when the
+    handle exchange fails."""
+
+    def __init__(self, engine, group=None):
+        import ctypes as C
+        from . import _lib as L
+        self.engine, self.group = engine, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if not (1 < self.world <= 8) or engine.device.type != "cuda":
+            raise L.Egot2Error("PeerExchange: needs 2..8 CUDA ranks on one node")
+        arena = engine.arena
+        with_shadow = engine.dtype == "bf16"
+        lib = L.load()
+        self.offs = slab_layout(arena.numel, with_shadow, int(lib.egot2_dp_flag_bytes()))
+        off_param, off_grad, off_shadow, off_flags, nbytes = self.offs
+        with torch.cuda.device(engine.device):
+            ptr = C.c_void_p()
+            L.call("egot2_peer_alloc", nbytes, C.byref(ptr))
+            self.local = int(ptr.value)
+            hb = int(lib.egot2_peer_handle_bytes())
+            handle = C.create_string_buffer(hb)
+            L.call("egot2_peer_export", self.local, handle)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.slabs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.slabs.append(self.local)
+                    continue
+                p = C.c_void_p()
+                L.call("egot2_peer_import", C.create_string_buffer(h, hb), C.byref(p))
+                self.slabs.append(int(p.value))
+            raw = torch.as_tensor(_DeviceMemory(self.local, nbytes), device=engine.device)
+            self._raw = raw                                            # keeps the view alive; the slab itself is freed in close()
+            param = raw[off_param:off_param + 4 * arena.numel].view(torch.float32)
+            grad = raw[off_grad:off_grad + 4 * arena.numel].view(torch.float32)
+            shadow = raw[off_shadow:off_shadow + 2 * arena.numel].view(torch.bfloat16) if with_shadow else None
+            arena.rebase(param, grad, shadow)
+            torch.cuda.synchronize(engine.device)
+        dist.barrier(group=group)                                      # every slab is mapped everywhere before the first step
+        self.desc = L.DpDesc()
+        self.desc.world, self.desc.rank, self.desc.numel = self.world, self.rank, arena.numel
+        for r, p in enumerate(self.slabs):
+            self.desc.slab[r] = p
+        self.desc.off_param, self.desc.off_grad, self.desc.off_shadow, self.desc.off_flags = off_param, off_grad, off_shadow, off_flags
+
+    def step(self, state, step: int, hp, stream: int, step_dev: Optional[torch.Tensor] = None, decoupled: bool = False):
+        """The whole exchange + optimizer step of this rank; afterwards the gradient arena is cleared (stream order)."""
+        import ctypes as C
+        from . import _lib as L
+        arena = self.engine.arena
+        if "m" not in state:
+            state["m"] = torch.zeros_like(arena.param)
+            state["v"] = torch.zeros_like(arena.param)
+        d = self.desc
+        d.exp_avg, d.exp_avg_sq = state["m"].data_ptr(), state["v"].data_ptr()
+        d.lr, (d.beta1, d.beta2), d.eps, d.weight_decay = hp["lr"], hp["betas"], hp["eps"], hp["weight_decay"]
+        d.step = int(step)
+        d.step_dev = step_dev.data_ptr() if step_dev is not None else None
+        d.decoupled = 1 if decoupled else 0
+        with torch.cuda.device(self.engine.device):
+            L.call("egot2_dp_reduce_adam", C.byref(d), stream)
+        arena.grad.zero_()            # safe: the kernel returned only after every peer finished reading these gradients
+        arena.shadow_fresh = self.engine.dtype == "bf16"
+
+    def close(self):
+        from . import _lib as L
+        with torch.cuda.device(self.engine.device):
+            torch.cuda.synchronize(self.engine.device)
+            for r, p in enumerate(self.slabs):
+                if r != self.rank and p:
+                    L.call("egot2_peer_unimport", p)
+            self.slabs = []

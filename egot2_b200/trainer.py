@@ -30,6 +30,26 @@ def _dev_guard(device):
     return torch.cuda.device(device) if torch.device(device).type == "cuda" else contextlib.nullcontext()
 
 
+def _make_peer_exchange(engine, process_group, world):
+    """parallel.PeerExchange for this engine, or None (one rank, EGOT2_DP_FUSED=0, CPU group, or the IPC set-up failed on
+    some rank - decided collectively, so that every rank takes the same path)."""
+    import os
+    if world <= 1 or os.environ.get("EGOT2_DP_FUSED", "1") == "0" or engine.device.type != "cuda" or world > 8:
+        return None
+    import torch.distributed as dist
+    from .parallel import PeerExchange
+    peer, ok = None, 1
+    try:
+        peer = PeerExchange(engine, process_group)
+    except Exception as e:      # noqa: BLE001 - any failure means "use NCCL", never a silent wrong answer
+        import warnings
+        warnings.warn(f"egot2_b200: peer-memory exchange unavailable ({e!r}); using the NCCL all-reduce path")
+        ok = 0
+    flag = torch.tensor([ok], device=engine.device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=process_group)
+    return peer if int(flag.item()) == 1 else None
+
+
 class _PromptStepGraphs:
     """Optional CUDA-graph replay of an EgoT2-g step's forward/backward launch sequence (several hundred small eager
     launches per step otherwise).  EGOT2_G_GRAPH=1 turns it on; the default stays eager because this path was written after
@@ -79,11 +99,14 @@ class _PromptStepGraphs:
         if self.engine.dtype == "bf16" and not arena.shadow_fresh:
             arena.refresh_shadow()
         replay()
-        scale = 1.0
-        if self.world > 1:
-            scale = allreduce_gradients(arena.grad, self.pg)
-        self.engine.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
-                              self.hp["weight_decay"], grad_scale=scale, fused=True, decoupled=decoupled)
+        if getattr(self, "peer", None) is not None:
+            self.peer.step(self.opt_state, self.step_count, self.hp, _cur_stream(self.device), decoupled=decoupled)
+        else:
+            scale = 1.0
+            if self.world > 1:
+                scale = allreduce_gradients(arena.grad, self.pg)
+            self.engine.adam_step(self.opt_state, self.step_count, self.hp["lr"], self.hp["betas"], self.hp["eps"],
+                                  self.hp["weight_decay"], grad_scale=scale, fused=True, decoupled=decoupled)
         self._grad_clean = True
         if self.dropout_epoch:
             with _dev_guard(self.device):
@@ -122,6 +145,7 @@ class PromptTranslatorTrainer(_PromptStepGraphs):
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+        self.peer = _make_peer_exchange(self.engine, process_group, self.world)
         self._init_step_graphs()           # eager launches unless EGOT2_G_GRAPH=1
         self._h2d: Dict[int, List[torch.Tensor]] = {}
         self.copy_stream = torch.cuda.Stream(device=self.device)
@@ -165,6 +189,10 @@ class PromptTranslatorTrainer(_PromptStepGraphs):
             first = False
             l = act.t["loss"][0] * ratio
             total = l if total is None else total + l
+        if self.peer is not None:
+            self.peer.step(self.opt_state, self.step_count, self.hp, _cur_stream(self.device))
+            self._grad_clean = True
+            return total
         scale = 1.0
         if self.world > 1:
             scale = allreduce_gradients(self.engine.arena.grad, self.pg)
@@ -201,6 +229,7 @@ class HoiPromptTranslatorTrainer(_PromptStepGraphs):
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+        self.peer = _make_peer_exchange(self.engine, process_group, self.world)
         self._init_step_graphs()           # eager launches unless EGOT2_G_GRAPH=1; _grad_clean: True after a fused AdamW
         self._h2d: Dict[int, List[torch.Tensor]] = {}
         self.copy_stream = None if self.device.type != "cuda" else torch.cuda.Stream(device=self.device)
@@ -241,6 +270,10 @@ class HoiPromptTranslatorTrainer(_PromptStepGraphs):
             eng.backward(act, dloss_scale=float(ratio), zero_grad=(i == 0 and not self._grad_clean))
             l = act.t["loss"][0] * ratio
             total = l if total is None else total + l
+        if self.peer is not None:
+            self.peer.step(self.opt_state, self.step_count, self.hp, _cur_stream(self.device), decoupled=True)
+            self._grad_clean = True
+            return total
         scale = 1.0
         if self.world > 1:
             scale = allreduce_gradients(eng.arena.grad, self.pg)
@@ -300,6 +333,13 @@ class TranslatorTrainer:
         # reduced after it.  EGOT2_DP_OVERLAP=0: one graph, one all-reduce behind it.
         ov = os.environ.get("EGOT2_DP_OVERLAP", "1")       # "force": also with one rank (tests; needs an initialised group)
         self.dp_overlap = ((self.world > 1 and ov != "0") or ov == "force") and spec.head != "decoder"
+        # N > 1, preferred: the exchange as ONE kernel over NVLink peer memory (parallel.PeerExchange / csrc/peer.cu: gradient
+        # reduce-scatter + Adam on this rank's slice + parameter all-gather).  No NCCL call and no host launch inside the step,
+        # so the whole step is again ONE CUDA graph, exactly like on one GPU.  EGOT2_DP_FUSED=0 keeps the NCCL path above.
+        self.peer = _make_peer_exchange(self.engine, process_group, self.world)
+        if self.peer is not None:
+            self.dp_overlap = False
+            self.graph_update = gu != "0"
         if self.dp_overlap:
             self.graph_update = False
         # Graph replays re-run kernels whose dropout keys were frozen at capture: the library's device-resident dropout
@@ -409,7 +449,7 @@ class TranslatorTrainer:
             if "m" not in self.opt_state:                 # optimizer state must exist before capture
                 self.opt_state["m"] = torch.zeros_like(self.engine.arena.param)
                 self.opt_state["v"] = torch.zeros_like(self.engine.arena.param)
-            if self.world > 1:                            # communicator warm-up outside the capture (grad arena is zero)
+            if self.world > 1 and self.peer is None:      # communicator warm-up outside the capture (grad arena is zero)
                 allreduce_gradients(self.engine.arena.grad, self.pg)
             self._step_dev.fill_(self.step_count - 1)
             self._step_dev_val = self.step_count - 1
@@ -456,6 +496,11 @@ class TranslatorTrainer:
 
     def _reduce_and_update(self, step_dev: Optional[torch.Tensor] = None):
         eng = self.engine
+        if self.peer is not None:                         # one kernel: reduce-scatter + Adam + all-gather over peer memory
+            self.peer.step(self.opt_state, self.step_count, self.hp, torch.cuda.current_stream(self.device).cuda_stream,
+                           step_dev=step_dev)
+            self._grad_clean = True
+            return
         scale = 1.0
         if self.world > 1:
             scale = allreduce_gradients(eng.arena.grad, self.pg)            # ONE flat NCCL all-reduce (NVLink)

@@ -398,6 +398,39 @@ int egot2_adamw_step_fused(float* param, float* grad, float* exp_avg, float* exp
                            float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                            void* shadow_bf16, int32_t zero_grad, void* stream);
 
+/* ------------------------------------------------------------------ data-parallel exchange over NVLink peer memory
+ * The reference trains under DDP / DP (HOI/scripts/lta/run_lta.py:249, HOI/tasks/pnr/video_task.py:39-42): an all-reduce of the
+ * translator gradients after backward, then the optimizer on every rank.  Here that is ONE kernel (csrc/peer.cu): gradient
+ * reduce-scatter over peer memory -> Adam on this rank's slice -> all-gather of the updated fp32 parameters and bf16 shadow.
+ *
+ * Every rank keeps parameters, gradients and shadow in one "slab" allocated by egot2_peer_alloc (cudaMalloc; zero-filled) with
+ * the same byte offsets on every rank, followed by egot2_dp_flag_bytes() bytes of flag words.  The ranks exchange the
+ * egot2_peer_handle_bytes()-byte IPC handles (egot2_peer_export) through their own channel (torch.distributed) and map each
+ * other's slabs (egot2_peer_import).  All ranks must call egot2_dp_reduce_adam the same number of times; a rank that never
+ * does makes the others trap after ~4 s (no hang).  After the call (stream order) this rank's arena holds the new parameters,
+ * identical bit for bit on every rank, and no peer reads this rank's gradients any more (the caller clears them). */
+typedef struct {
+  int32_t world, rank;
+  int64_t numel;                      /* arena elements (a multiple of 4) */
+  void* slab[8];                      /* slab[p]: rank p's slab as mapped in THIS process; slab[rank] = the local one */
+  int64_t off_param, off_grad;        /* byte offsets of the fp32 parameter / gradient arenas inside a slab (16-byte aligned) */
+  int64_t off_shadow;                 /* byte offset of the bf16 shadow, or -1 (fp32 engines) */
+  int64_t off_flags;                  /* byte offset of the flag words */
+  float* exp_avg; float* exp_avg_sq;  /* LOCAL Adam moments, arena layout (only this rank's slice is touched) */
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;                       /* optimizer step count (1-based) for the bias corrections, unless step_dev */
+  const int32_t* step_dev;            /* optional: the count lives on the device (CUDA-graph replays) */
+  int32_t decoupled;                  /* 1: AdamW */
+} egot2_dp_desc;
+int egot2_peer_alloc(size_t bytes, void** ptr);
+int egot2_peer_free(void* ptr);
+int egot2_peer_handle_bytes(void);
+int egot2_peer_export(void* ptr, void* handle_out);
+int egot2_peer_import(const void* handle, void** ptr);
+int egot2_peer_unimport(void* ptr);
+size_t egot2_dp_flag_bytes(void);
+int egot2_dp_reduce_adam(const egot2_dp_desc* d, void* stream);
+
 /* Batched PNR / OSCC evaluation metrics in one launch (replaces the per-clip `.item()` loops of
  * HOI/evaluation/pnr/metrics.py:11-80: state_change_accuracy, keyframe_accuracy, keyframe_distance).
  * logits (B,n) fp32; label_idx (B) int64 OR label_onehot (B,n) fp32; sc_label (B) int64 or NULL (every clip counts);

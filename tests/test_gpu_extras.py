@@ -219,8 +219,9 @@ def test_feature_gradients_of_trainable_backbones(name, which, dtype):
     assert all(d is None for d, w in zip(dfeats, want) if not w)
 
 
-def _nccl_rank_worker(rank, world, port, q):
+def _nccl_rank_worker(rank, world, port, q, fused="1", graphs=False, steps=1):
     import os
+    os.environ["EGOT2_DP_FUSED"] = fused
 
     import torch
     import torch.distributed as dist
@@ -237,19 +238,56 @@ def _nccl_rank_worker(rank, world, port, q):
         f = synth.make_features(sp, B, seg, seed=77, dtype=torch.bfloat16)
         lab = synth.make_labels(sp, B, seg, seed=77)
         lo, hi = rank * B // world, (rank + 1) * B // world
-        tr = TranslatorTrainer(sp, f"cuda:{rank}", "bf16", use_graphs=False)
+        tr = TranslatorTrainer(sp, f"cuda:{rank}", "bf16", use_graphs=graphs)
+        assert (tr.peer is not None) == (fused == "1"), "the exchange path is not the one asked for"
         tr.load_state_dict(synth.make_state_dict(sp, 9))
         feats = [f[s.name][lo:hi].cuda() for s in sp.segments]
-        tr.train_step(feats, lab[lo:hi].cuda())
+        labels = lab[lo:hi].cuda()
+        for _ in range(steps):
+            tr.train_step(feats, labels, graph_key=0 if graphs else None)
         torch.cuda.synchronize()
-        if rank == 0:
-            q.put({k: v.cpu() for k, v in tr.state_dict().items()})
+        q.put((rank, {k: v.cpu() for k, v in tr.state_dict().items()}))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_nccl_step_equals_one_rank_step():
+def _run_two_ranks(fused, graphs, steps):
+    import socket
+
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_rank_worker, args=(r, 2, port, q, fused, graphs, steps)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=170) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return got[0], got[1]
+
+
+def test_two_rank_fused_exchange_multi_step_graphs():
+    """The peer-memory exchange kernel (csrc/peer.cu) inside the whole-step CUDA graph: after 4 replayed steps the two ranks
+    hold BIT-IDENTICAL parameters (every slice is computed once, by its owner, and written to both arenas), and they agree
+    with 4 steps of the NCCL all-reduce + fused-Adam path to bf16-training accuracy."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    a0, a1 = _run_two_ranks("1", True, 4)
+    for k in a0:
+        assert torch.equal(a0[k], a1[k]), f"{k}: ranks diverged"
+    n0, _ = _run_two_ranks("0", True, 4)
+    for k in a0:
+        assert float((a0[k] - n0[k]).abs().max()) <= 2e-4 + 1e-3 * float(n0[k].abs().max()), k
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_two_rank_nccl_step_equals_one_rank_step(fused):
     """SURVEY 4(5) on hardware: one optimisation step on 16 clips sharded over 2 ranks (NCCL all-reduce of the flat
     gradient arena, DDP-mean) leaves the same parameters as the same step on the concatenated batch on one rank.
     CE with class weights normalises by each shard's own weight sum (exactly what DDP does with the reference's loss), so
@@ -265,18 +303,10 @@ def test_two_rank_nccl_step_equals_one_rank_step():
     from egot2_b200.hhi import PositionalEncoding
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_nccl_rank_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    sd2 = q.get(timeout=170)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    sd2, sd2_r1 = _run_two_ranks(fused, False, 1)      # fused = "1": the peer-memory kernel; "0": NCCL all-reduce + fused Adam
+    if fused == "1":
+        for k in sd2:
+            assert torch.equal(sd2[k], sd2_r1[k]), f"{k}: ranks diverged"
     # 1-rank reference: the two half-batch gradients averaged = what the 2-rank all-reduce (mean) produced
     sp = specs.hhi_ttm_spec(128, 4, 1, 0.0, True)
     sp = __import__("dataclasses").replace(sp, p_embed=0.0)
