@@ -412,7 +412,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        from egot2_b200.parallel import bind_to_gpu_numa
+        numa = bind_to_gpu_numa(local_rank)        # pinned staging buffers land on the GPU's own NUMA node
         torch.distributed.init_process_group("nccl", device_id=dev)
     from egot2_b200 import _lib as L
 
@@ -527,7 +530,11 @@ def main():
         "config": config_of(args.workload, wl, spec, B),       # identical in the reference arm's line
         "run": {"l2_policy": f"inputs rotate over a pool of {n_pool} batches = {n_pool * feat_bytes / 2**20:.0f} MiB "
                              f"> 126 MiB L2; saved activations add more per step",
-                "cuda_graphs": bool(tr.use_graphs), "parallelism": f"dp{world} (clips sharded; one gradient all-reduce per step)"},
+                "cuda_graphs": bool(tr.use_graphs), "numa_bind": numa,
+                "parallelism": f"dp{world} (clips sharded; one gradient exchange per step)",
+                "exchange": ("none" if world == 1 else ("peer-memory kernel: reduce-scatter + Adam + all-gather (csrc/peer.cu)"
+                                                        if getattr(tr, "peer", None) is not None else
+                                                        "NCCL all-reduce overlapped with the embedding backward + fused Adam"))},
         "model_tflops_per_s": tfs,
         "step_roofline": {"bound": "tensor", "achieved": tfs / world, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                           "frac": tfs / world / peaks["bf16_tflops_sustained"],
@@ -708,8 +715,8 @@ def profile_step_launchers(tr, pool, n_pool, steps, es):
     """Per-launcher CUDA-event timing of `steps` eager (un-graphed) training steps, through the library's own
     egot2_prof_* hooks: every launcher brackets its kernel(s) with events on the launch stream."""
     from egot2_b200 import _lib as L
-    keep, keep_world = tr.use_graphs, tr.world
-    tr.use_graphs, tr.world = False, 1          # rank 0 profiles alone: no collective in this pass
+    keep, keep_world, keep_peer = tr.use_graphs, tr.world, getattr(tr, "peer", None)
+    tr.use_graphs, tr.world, tr.peer = False, 1, None      # rank 0 profiles alone: no collective / peer exchange in this pass
     for i in range(2):
         tr.train_step(*pool[i % n_pool])
     torch.cuda.synchronize()
@@ -719,7 +726,7 @@ def profile_step_launchers(tr, pool, n_pool, steps, es):
     torch.cuda.synchronize()
     rows = L.prof_report()
     L.prof_enable(False)
-    tr.use_graphs, tr.world = keep, keep_world
+    tr.use_graphs, tr.world, tr.peer = keep, keep_world, keep_peer
     return rows
 
 

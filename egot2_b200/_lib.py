@@ -102,7 +102,7 @@ class DpDesc(C.Structure):
     _fields_ = [("world", i32), ("rank", i32), ("numel", C.c_int64), ("slab", vp * 8), ("off_param", C.c_int64),
                 ("off_grad", C.c_int64), ("off_shadow", C.c_int64), ("off_flags", C.c_int64), ("exp_avg", vp), ("exp_avg_sq", vp),
                 ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("step", i32), ("step_dev", vp),
-                ("decoupled", i32)]
+                ("decoupled", i32), ("zero_grads_remote", i32)]
 
 
 class HeadGrads(C.Structure):
@@ -155,6 +155,7 @@ SIGNATURES = {
     "egot2_peer_unimport": (C.c_int, [vp]),
     "egot2_dp_flag_bytes": (C.c_size_t, []),
     "egot2_dp_reduce_adam": (C.c_int, [vp, vp]),
+    "egot2_dp_reduce_adam_range": (C.c_int, [vp, C.c_int64, C.c_int64, i32, vp]),
     "egot2_side_defer": (C.c_int, [C.c_int]),
     "egot2_side_join_all": (C.c_int, [vp]),
     "egot2_timeline_set": (C.c_int, [vp]),

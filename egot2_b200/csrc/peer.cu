@@ -25,11 +25,17 @@ namespace egot2 {
 namespace {
 
 constexpr int kMaxRanks = 8;
-constexpr int kFlagWords = 64;         // u32 words of the flag area at the end of a slab (arrive[8], done[8], epoch, grid counter)
+constexpr int kChannels = 2;           // independent exchanges in flight (e.g. [embed_numel, n) during the embedding backward, then [0, embed_numel))
+constexpr int kChanWords = 32;         // u32 words per channel: arrive[8], done[8], epoch, grid counter
+constexpr int kFlagWords = kChannels * kChanWords;
 
 struct DpArgs {
   int world, rank;
   size_t n;                            // arena elements
+  size_t lo, hi;                       // the element range this launch exchanges (multiples of 4), split over the ranks
+  int channel;
+  int zero_remote;                     // 1: the owner of a slice clears that slice of EVERY rank's gradient arena right after
+                                       // reading it (small arenas: saves the caller's separate clear launch)
   char* slab[kMaxRanks];               // every rank's slab as THIS process addresses it (slab[rank] = the local one)
   size_t off_param, off_grad, off_shadow, off_flags;     // byte offsets inside a slab (identical on every rank)
   float* m; float* v;                  // local Adam moments (full arena layout; only this rank's slice is used)
@@ -57,7 +63,7 @@ __device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t want) {
 
 __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpArgs a) {
   EGOT2_PDL_ENTER();
-  uint32_t* my_flags = reinterpret_cast<uint32_t*>(a.slab[a.rank] + a.off_flags);
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(a.slab[a.rank] + a.off_flags) + a.channel * kChanWords;
   uint32_t* arrive = my_flags;                 // arrive[p]: rank p's gradients of that epoch are complete
   uint32_t* done = my_flags + kMaxRanks;       // done[p]:   rank p's slice of that epoch is in this rank's arena
   uint32_t* epoch_w = my_flags + 2 * kMaxRanks;
@@ -66,8 +72,7 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpArgs a) {
 
   // 1. announce (the backward kernels that produced the gradients precede this launch in stream order)
   if (blockIdx.x == 0 && threadIdx.x < a.world) {
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<uint32_t*>(a.slab[threadIdx.x] + a.off_flags) + a.rank, e);
+    st_release_sys(reinterpret_cast<uint32_t*>(a.slab[threadIdx.x] + a.off_flags) + a.channel * kChanWords + a.rank, e);
   }
   // 2. every CTA waits for every rank's announcement
   if (threadIdx.x < a.world) spin_until(arrive + threadIdx.x, e);
@@ -81,50 +86,69 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpArgs a) {
   }
   const float inv_world = 1.f / (float)a.world;
   // slices in units of 4 floats (the arena is padded to a multiple of 64)
-  const size_t n4 = a.n / 4, per = (n4 + a.world - 1) / a.world;
-  const size_t q0 = per * a.rank, q1 = q0 + per < n4 ? q0 + per : n4;
-  for (size_t q = q0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < q1; q += (size_t)gridDim.x * blockDim.x) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < a.world; ++p) {          // rank order: the same sum on whichever rank owns the slice
-      const float4 x = reinterpret_cast<const float4*>(a.slab[p] + a.off_grad)[q];
-      g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
-    }
-    float gg[4] = {g.x * inv_world, g.y * inv_world, g.z * inv_world, g.w * inv_world};
-    const float4 w4 = reinterpret_cast<const float4*>(a.slab[a.rank] + a.off_param)[q];
-    float w[4] = {w4.x, w4.y, w4.z, w4.w};
-    float4 m4 = reinterpret_cast<float4*>(a.m)[q], v4 = reinterpret_cast<float4*>(a.v)[q];
-    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+  const size_t n4 = (a.hi - a.lo) / 4, per = (n4 + a.world - 1) / a.world, base = a.lo / 4;
+  const size_t q0 = base + per * a.rank, q1 = (per * (a.rank + 1) < n4 ? per * (a.rank + 1) : n4) + base;
+  constexpr int U = 2;                           // independent quads per thread and iteration: 2 * world loads in flight
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t qb = q0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; qb < q1; qb += stride * U) {
+    float4 g[U], w4[U], m4[U], v4[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {                // the arithmetic of adam_kernel (rowops.cu), element for element
-      float grad = gg[k];
-      float wk = w[k];
-      if (a.decoupled) wk *= 1.f - a.lr * a.wd;
-      else if (a.wd != 0.f) grad += a.wd * wk;
-      mm[k] = a.b1 * mm[k] + (1.f - a.b1) * grad;
-      vv[k] = a.b2 * vv[k] + (1.f - a.b2) * grad * grad;
-      w[k] = wk - (a.lr / bc1) * mm[k] / (sqrtf(vv[k]) / bc2_sqrt + a.eps);
+    for (int u = 0; u < U; ++u) {
+      const size_t q = qb + u * stride;
+      g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < q1) {
+        for (int p = 0; p < a.world; ++p) {      // rank order: the same sum on whichever rank owns the slice
+          const float4 x = reinterpret_cast<const float4*>(a.slab[p] + a.off_grad)[q];
+          g[u].x += x.x; g[u].y += x.y; g[u].z += x.z; g[u].w += x.w;
+        }
+        w4[u] = reinterpret_cast<const float4*>(a.slab[a.rank] + a.off_param)[q];
+        m4[u] = reinterpret_cast<float4*>(a.m)[q];
+        v4[u] = reinterpret_cast<float4*>(a.v)[q];
+      }
     }
-    reinterpret_cast<float4*>(a.m)[q] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-    reinterpret_cast<float4*>(a.v)[q] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    const float4 wn = make_float4(w[0], w[1], w[2], w[3]);
-    __nv_bfloat162 s0 = __floats2bfloat162_rn(w[0], w[1]), s1 = __floats2bfloat162_rn(w[2], w[3]);
-    uint2 sh; sh.x = *reinterpret_cast<uint32_t*>(&s0); sh.y = *reinterpret_cast<uint32_t*>(&s1);
-    for (int p = 0; p < a.world; ++p) {          // all-gather: the owner writes its slice into every arena
-      reinterpret_cast<float4*>(a.slab[p] + a.off_param)[q] = wn;
-      if (a.off_shadow != (size_t)-1) reinterpret_cast<uint2*>(a.slab[p] + a.off_shadow)[q] = sh;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t q = qb + u * stride;
+      if (q >= q1) continue;
+      float gg[4] = {g[u].x * inv_world, g[u].y * inv_world, g[u].z * inv_world, g[u].w * inv_world};
+      float w[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+      float mm[4] = {m4[u].x, m4[u].y, m4[u].z, m4[u].w}, vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {              // the arithmetic of adam_kernel (rowops.cu), element for element
+        float grad = gg[k];
+        float wk = w[k];
+        if (a.decoupled) wk *= 1.f - a.lr * a.wd;
+        else if (a.wd != 0.f) grad += a.wd * wk;
+        mm[k] = a.b1 * mm[k] + (1.f - a.b1) * grad;
+        vv[k] = a.b2 * vv[k] + (1.f - a.b2) * grad * grad;
+        w[k] = wk - (a.lr / bc1) * mm[k] / (sqrtf(vv[k]) / bc2_sqrt + a.eps);
+      }
+      reinterpret_cast<float4*>(a.m)[q] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      reinterpret_cast<float4*>(a.v)[q] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      const float4 wn = make_float4(w[0], w[1], w[2], w[3]);
+      __nv_bfloat162 s0 = __floats2bfloat162_rn(w[0], w[1]), s1 = __floats2bfloat162_rn(w[2], w[3]);
+      uint2 sh; sh.x = *reinterpret_cast<uint32_t*>(&s0); sh.y = *reinterpret_cast<uint32_t*>(&s1);
+      for (int p = 0; p < a.world; ++p) {        // all-gather: the owner writes its slice into every arena
+        reinterpret_cast<float4*>(a.slab[p] + a.off_param)[q] = wn;
+        if (a.off_shadow != (size_t)-1) reinterpret_cast<uint2*>(a.slab[p] + a.off_shadow)[q] = sh;
+        if (a.zero_remote) reinterpret_cast<float4*>(a.slab[p] + a.off_grad)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
-  // 3. everything this rank wrote is visible system-wide before it says so
-  __threadfence_system();
+  // 3. everything this rank wrote is visible system-wide before it says so: the CTA barrier orders the CTA's writes before
+  //    thread 0's system-scope fence (cumulativity), which precedes the grid counter; one fence per CTA, not per thread
   __syncthreads();
   __shared__ uint32_t s_last;
-  if (threadIdx.x == 0) s_last = atomicAdd(grid_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(grid_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
   __syncthreads();
   if (!s_last) return;
   // the last CTA of this rank: every CTA's writes are fenced
   if (threadIdx.x < a.world) {
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<uint32_t*>(a.slab[threadIdx.x] + a.off_flags) + kMaxRanks + a.rank, e);
+    __threadfence_system();                       // acquire side of the counter: the other CTAs' fenced writes, then the flag
+    st_release_sys(reinterpret_cast<uint32_t*>(a.slab[threadIdx.x] + a.off_flags) + a.channel * kChanWords + kMaxRanks + a.rank, e);
     spin_until(done + threadIdx.x, e);           // ... and every rank's slice is in THIS arena before the launch completes
   }
   __syncthreads();
@@ -172,11 +196,20 @@ extern "C" int egot2_peer_unimport(void* ptr) {
 }
 extern "C" size_t egot2_dp_flag_bytes(void) { return kFlagWords * sizeof(uint32_t); }
 
-extern "C" int egot2_dp_reduce_adam(const egot2_dp_desc* d, void* stream) {
+static int dp_launch(const egot2_dp_desc* d, long long lo, long long hi, int channel, void* stream);
+extern "C" int egot2_dp_reduce_adam(const egot2_dp_desc* d, void* stream) { return dp_launch(d, 0, d ? d->numel : 0, 0, stream); }
+extern "C" int egot2_dp_reduce_adam_range(const egot2_dp_desc* d, int64_t lo, int64_t hi, int32_t channel, void* stream) {
+  return dp_launch(d, lo, hi, channel, stream);
+}
+static int dp_launch(const egot2_dp_desc* d, long long lo, long long hi, int channel, void* stream) {
   EGOT2_CHECK(d && d->world >= 1 && d->world <= kMaxRanks && d->rank >= 0 && d->rank < d->world, "dp_reduce_adam: world/rank");
   EGOT2_CHECK(d->numel > 0 && d->numel % 4 == 0 && d->exp_avg && d->exp_avg_sq, "dp_reduce_adam: arena (numel %% 4 == 0) / moments");
+  EGOT2_CHECK(lo >= 0 && hi <= d->numel && lo <= hi && lo % 4 == 0 && hi % 4 == 0 && channel >= 0 && channel < kChannels,
+              "dp_reduce_adam: range [%lld, %lld) / channel %d", lo, hi, channel);
+  if (lo == hi) return 0;
   DpArgs a;
   a.world = d->world; a.rank = d->rank; a.n = (size_t)d->numel;
+  a.lo = (size_t)lo; a.hi = (size_t)hi; a.channel = channel;
   for (int p = 0; p < d->world; ++p) {
     EGOT2_CHECK(d->slab[p] != nullptr, "dp_reduce_adam: slab of rank %d missing", p);
     a.slab[p] = (char*)d->slab[p];
@@ -194,12 +227,15 @@ extern "C" int egot2_dp_reduce_adam(const egot2_dp_desc* d, void* stream) {
   a.step_dev = d->step_dev;
   a.decoupled = d->decoupled;
   // a few CTAs per rank: the message is latency-bound, and the spinning CTAs must never crowd out other work
-  const size_t per4 = ((size_t)d->numel / 4 + d->world - 1) / d->world;
-  int grid = (int)((per4 + 255) / 256);
-  if (grid > 64) grid = 64;
+  const size_t per4 = ((size_t)(hi - lo) / 4 + d->world - 1) / d->world;
+  // latency-bound for the small arenas (a few CTAs), bandwidth-bound for the large ones (two waves of resident CTAs)
+  int grid = (int)((per4 + 511) / 512);
+  const int cap = sm_count() * 4;
+  if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
+  a.zero_remote = d->zero_grads_remote ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  ProfScope prof(st, "dp_reduce_adam n%lld world%d", (long long)d->numel, d->world);
+  ProfScope prof(st, "dp_reduce_adam n%lld world%d ch%d", (long long)(hi - lo), d->world, channel);
   launch(dp_reduce_adam_kernel, dim3(grid), dim3(256), 0, st, a);
   EGOT2_LAUNCH_CHECK();
   return 0;

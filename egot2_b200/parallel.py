@@ -14,6 +14,31 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates pinned host buffers (first touch
+    then places them on that node).  With 8 ranks each streaming features to its own GPU every step, buffers on the wrong
+    socket halve the host->device rate.  Best effort: returns (numa node, #cpus) or None when sysfs / the PCI ids are missing."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except Exception:      # noqa: BLE001 - purely an optimisation
+        return None
+
+
 def shard_range(n_clips: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous, balanced clip range [lo, hi) of `rank`: the first n % world ranks get one extra clip
     (reference: DistributedSampler's per-GPU batch = BATCH_SIZE / NUM_GPUS, HOI/dataset/lta/loader.py:73-74)."""
@@ -142,8 +167,10 @@ class PeerExchange:
             self.desc.slab[r] = p
         self.desc.off_param, self.desc.off_grad, self.desc.off_shadow, self.desc.off_flags = off_param, off_grad, off_shadow, off_flags
 
-    def step(self, state, step: int, hp, stream: int, step_dev: Optional[torch.Tensor] = None, decoupled: bool = False):
-        """The whole exchange + optimizer step of this rank; afterwards the gradient arena is cleared (stream order)."""
+    def step(self, state, step: int, hp, stream: int, step_dev: Optional[torch.Tensor] = None, decoupled: bool = False,
+             lo: int = 0, hi: Optional[int] = None, channel: int = 0):
+        """The exchange + optimizer step of this rank for arena elements [lo, hi) (default: everything) on flag `channel`;
+        afterwards that part of the gradient arena is cleared (stream order)."""
         import ctypes as C
         from . import _lib as L
         arena = self.engine.arena
@@ -156,9 +183,15 @@ class PeerExchange:
         d.step = int(step)
         d.step_dev = step_dev.data_ptr() if step_dev is not None else None
         d.decoupled = 1 if decoupled else 0
+        hi = arena.numel if hi is None else hi
+        # small exchanges: the slice owners clear the gradients in the same kernel; large ones: one local clear afterwards
+        # (clearing over NVLink would double the remote traffic)
+        remote_zero = (hi - lo) * 4 <= (16 << 20)
+        d.zero_grads_remote = 1 if remote_zero else 0
         with torch.cuda.device(self.engine.device):
-            L.call("egot2_dp_reduce_adam", C.byref(d), stream)
-        arena.grad.zero_()            # safe: the kernel returned only after every peer finished reading these gradients
+            L.call("egot2_dp_reduce_adam_range", C.byref(d), int(lo), int(hi), int(channel), stream)
+        if not remote_zero:
+            arena.grad[lo:hi].zero_() # safe: the kernel returned only after every peer finished reading these gradients
         arena.shadow_fresh = self.engine.dtype == "bf16"
 
     def close(self):

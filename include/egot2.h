@@ -421,6 +421,8 @@ typedef struct {
   int32_t step;                       /* optimizer step count (1-based) for the bias corrections, unless step_dev */
   const int32_t* step_dev;            /* optional: the count lives on the device (CUDA-graph replays) */
   int32_t decoupled;                  /* 1: AdamW */
+  int32_t zero_grads_remote;          /* 1: the owner of a slice clears that slice of every rank's gradient arena after reading
+                                       * it (small arenas: no separate clear launch); 0: the caller clears its arena afterwards */
 } egot2_dp_desc;
 int egot2_peer_alloc(size_t bytes, void** ptr);
 int egot2_peer_free(void* ptr);
@@ -430,6 +432,10 @@ int egot2_peer_import(const void* handle, void** ptr);
 int egot2_peer_unimport(void* ptr);
 size_t egot2_dp_flag_bytes(void);
 int egot2_dp_reduce_adam(const egot2_dp_desc* d, void* stream);
+/* The same exchange restricted to arena elements [lo, hi) (multiples of 4) on flag channel 0 or 1: two exchanges may be in
+ * flight at once on different channels and streams - e.g. everything but the embedding-stage gradients while the embedding
+ * backward still runs, then the embedding prefix (the arena keeps those parameters first for exactly this purpose). */
+int egot2_dp_reduce_adam_range(const egot2_dp_desc* d, int64_t lo, int64_t hi, int32_t channel, void* stream);
 
 /* Batched PNR / OSCC evaluation metrics in one launch (replaces the per-clip `.item()` loops of
  * HOI/evaluation/pnr/metrics.py:11-80: state_change_accuracy, keyframe_accuracy, keyframe_distance).
