@@ -412,10 +412,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = None
+    from egot2_b200.parallel import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank)            # pinned staging buffers land on the GPU's own NUMA node
     if world > 1:
-        from egot2_b200.parallel import bind_to_gpu_numa
-        numa = bind_to_gpu_numa(local_rank)        # pinned staging buffers land on the GPU's own NUMA node
         torch.distributed.init_process_group("nccl", device_id=dev)
     from egot2_b200 import _lib as L
 
