@@ -185,6 +185,7 @@ SIGNATURES = {
     "egot2_head_loss_bwd": (C.c_int, [P(HeadDesc), P(HeadIn), P(HeadOut), vp, f32, vp, P(HeadGrads), vp, sz, vp]),
     "egot2_slowfast_pool_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
     "egot2_cast_f32_to_bf16": (C.c_int, [vp, vp, sz, vp]),
+    "egot2_sum_into_f32": (C.c_int, [vp, vp, vp, sz, vp]),
     "egot2_cast_bf16_to_f32": (C.c_int, [vp, vp, sz, vp]),
     "egot2_adam_step": (C.c_int, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp]),
     "egot2_adam_step_fused": (C.c_int, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp, i32, vp]),

@@ -595,8 +595,16 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   cudaStream_t side_st[2] = {st, st};
   for (int i = 0; i < 2 && i + 1 < d->n_seg; ++i)
     if (sides[i]) { side_st[i] = side_fork(st, sides[i], 0); used[i] = side_st[i] != st; }
-  int n_proj = 0;
-  for (int k = 0; k < d->n_seg; ++k) n_proj += (d->seg_has_proj[k] && d->seg_tokens[k] > 0) ? 1 : 0;
+  int n_proj = 0, n_big = 0;
+  for (int k = 0; k < d->n_seg; ++k) {
+    const bool on = d->seg_has_proj[k] && d->seg_tokens[k] > 0;
+    n_proj += on ? 1 : 0;
+    n_big += (on && d->seg_in_dim[k] >= 2048) ? 1 : 0;
+  }
+  // the weight-gradient GEMMs of the projections run side by side and share the resident CTA slots - among the LONG-K ones
+  // only when there are any (PNR / OSCC 8192-wide beside SlowFast's 2048 / 256: the two big ones stream 134 MB and used to get
+  // 32 CTAs each because the split was divided by all four)
+  const int share_all = n_big > 0 ? n_big : n_proj;
   {
     // every projection's bias gradient (column sums of its segment's rows of dz) in ONE launch of the per-segment
     // column-sum kernel instead of one strided column-sum launch per task
@@ -626,7 +634,8 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
         feat = cast_buf;
       }
       if (g->proj_w[k])
-        EGOT2_TRY(wgrad(d->dtype, d->B * Dk, d->H, Kk, dzk, d->H, Dk, d->T, feat, Kk, 0, 0, g->proj_w[k], sk, par ? n_proj : 1));
+        EGOT2_TRY(wgrad(d->dtype, d->B * Dk, d->H, Kk, dzk, d->H, Dk, d->T, feat, Kk, 0, 0, g->proj_w[k], sk,
+                        !par ? 1 : ((n_big > 0 && Kk < 2048) ? 8 : share_all)));
       if (g->dfeat[k]) {   // dF = dZ . W   (only for a trainable backbone: HHI --nofreeze)
         GemmArgs m;
         m.M = d->B * Dk; m.N = Kk; m.K = d->H;
@@ -976,6 +985,10 @@ extern "C" int egot2_gemm(int32_t dtype, int32_t M, int32_t N, int32_t K, const 
   g.in_dtype = dtype; g.out_dtype = c_is_f32 ? EGOT2_F32 : dtype; g.accumulate = accumulate;
   if (accumulate && !relu) g.split_k = suggest_split_k(M, N, K);
   return gemm(g, (cudaStream_t)stream);
+}
+
+extern "C" int egot2_sum_into_f32(float* dst, float* a, float* b, size_t n, void* stream) {
+  return sum_into_clear(dst, a, b, n, (cudaStream_t)stream);
 }
 
 extern "C" const char* egot2_gemm_last_impl(void) { return gemm_last_impl(); }

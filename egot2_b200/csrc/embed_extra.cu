@@ -122,6 +122,24 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const EmbedSrc src, i
   }
 }
 
+// dst += a (+ b), then a (and b) are cleared: the per-branch gradient arenas of an EgoT2-g step (three forwards of one model
+// running side by side on three streams) meet in the shared arena and are left clean for the next step, one pass
+__global__ void __launch_bounds__(256) sum_into_clear_kernel(float* __restrict__ dst, float* __restrict__ a, float* __restrict__ b, size_t n4) {
+  EGOT2_PDL_ENTER();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 d = reinterpret_cast<float4*>(dst)[i];
+    const float4 x = reinterpret_cast<float4*>(a)[i];
+    d.x += x.x; d.y += x.y; d.z += x.z; d.w += x.w;
+    reinterpret_cast<float4*>(a)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b) {
+      const float4 y = reinterpret_cast<float4*>(b)[i];
+      d.x += y.x; d.y += y.y; d.z += y.z; d.w += y.w;
+      reinterpret_cast<float4*>(b)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    reinterpret_cast<float4*>(dst)[i] = d;
+  }
+}
+
 int ew_grid(size_t n) {
   size_t ctas = (n + 255) / 256;
   const size_t cap = (size_t)sm_count() * 16;
@@ -137,6 +155,15 @@ int add_table(int dt, size_t n, size_t table_elems, const void* z, const float* 
   ProfScope prof(st, "add_table n%zu", n);
   if (dt == EGOT2_F32) launch(add_table_kernel<float>, dim3(ew_grid(n)), dim3(256), 0, st, (const float*)z, table, (float*)x, n, table_elems);
   else launch(add_table_kernel<bf16>, dim3(ew_grid(n)), dim3(256), 0, st, (const bf16*)z, table, (bf16*)x, n, table_elems);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
+int sum_into_clear(float* dst, float* a, float* b, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  EGOT2_CHECK(dst && a && n % 4 == 0, "sum_into_clear: buffers / n %% 4");
+  ProfScope prof(st, "sum_into_clear n%zu", n);
+  launch(sum_into_clear_kernel, dim3(ew_grid(n / 4)), dim3(256), 0, st, dst, a, b, n / 4);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

@@ -136,6 +136,8 @@ struct EmbedSrc {      // where segment k's projected rows are: `splits` fp32 sl
 int embed_finish(int B, int T, int H, const EmbedSrc& src, int drop_tokens, float p_feat, uint64_t key_feat, const float* g,
                  const float* b, float eps, const float* table, float p_embed, uint64_t key_embed, void* z, float* stat, void* x,
                  cudaStream_t st);
+// dst += a (+ b); a (and b) cleared (embed_extra.cu)
+int sum_into_clear(float* dst, float* a, float* b, size_t n, cudaStream_t st);
 // in-place dropout of the first `prefix` elements of every `period`-element clip (mask index = linear element index)
 int dropout_prefix_inplace(int dtype, void* x, size_t n, size_t period, size_t prefix, float p, uint64_t key, cudaStream_t st);
 // dst[r, 0..ld) = bf16(src[r, 0..n)) followed by zeros (ld >= n)

@@ -58,15 +58,16 @@ def _make_peer_exchange(engine, process_group, world):
 
 class _PromptStepGraphs:
     """Optional CUDA-graph replay of an EgoT2-g step's forward/backward launch sequence (several hundred small eager
-    launches per step otherwise).  EGOT2_G_GRAPH=1 turns it on; the default stays eager because this path was written after
-    round 1's GPU minutes were spent and has not run on hardware yet.  One graph per `graph_key` (= one fixed set of input
+    launches per step otherwise).  On by default since it ran green on hardware (round 2); EGOT2_G_GRAPH=0 keeps eager
+    launches.  One graph per `graph_key` (= one fixed set of input
     buffers); the captured kernels keep their dropout seeds, the library's device-resident dropout epoch (advanced once per
     step) gives every replay fresh masks; gradient all-reduce (N > 1) and the fused Adam / AdamW stay eager launches behind
     the replay, which also leaves the gradient arena cleared and the bf16 shadow current for the next replay."""
 
     def _init_step_graphs(self):
         import os
-        self.use_graphs = os.environ.get("EGOT2_G_GRAPH", "0") == "1"
+        g = os.environ.get("EGOT2_G_GRAPH", "auto")          # "1" on, "0" off, default: on for CUDA devices
+        self.use_graphs = g == "1" or (g == "auto" and torch.device(self.device).type == "cuda")
         self._graphs: Dict[int, tuple] = {}
         self._grad_clean = False
         self.dropout_epoch = self.use_graphs and os.environ.get("EGOT2_DROPOUT_EPOCH", "1") != "0"
@@ -152,7 +153,11 @@ class PromptTranslatorTrainer(_PromptStepGraphs):
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.peer = _make_peer_exchange(self.engine, process_group, self.world)
-        self._init_step_graphs()           # eager launches unless EGOT2_G_GRAPH=1
+        self._init_step_graphs()           # one CUDA graph per step unless EGOT2_G_GRAPH=0
+        self._branch_streams = self._branch_grads = None
+        if os.environ.get("EGOT2_G_STREAMS", "1") != "0" and self.device.type == "cuda":
+            self._branch_streams = {m: torch.cuda.Stream(device=self.device) for m in ("lam", "asd")}
+            self._branch_grads = {m: torch.zeros_like(self.engine.arena.grad) for m in ("lam", "asd")}
         self._h2d: Dict[int, List[torch.Tensor]] = {}
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.loss_kind, self.class_weight = L.LOSS_CE, None
@@ -161,18 +166,40 @@ class PromptTranslatorTrainer(_PromptStepGraphs):
         self.engine.arena.load_state_dict(sd)
 
     def _fwd_bwd_all(self, feats, labels, seed0: int):
-        """The three forward/backward passes into a clean gradient arena (the graph-captured body)."""
+        """The three forward/backward passes into a clean gradient arena (the graph-captured body).
+
+        The three passes are independent until their gradients meet, and each is a chain of several hundred tiny kernels
+        (7 / 90 / 90 tokens x at most 64 clips) that leave most of the GPU idle: they run SIDE BY SIDE on three streams
+        (three parallel branches of the CUDA graph).  The shared arena's accumulation is not atomic everywhere, so 'lam' and
+        'asd' write their gradients to buffers of their own, and one launch (egot2_sum_into_f32) adds both into the arena
+        and clears them.  EGOT2_G_STREAMS=0: one after the other on the caller's stream."""
         groups = {"lam": list(feats[0:1]), "ttm": list(feats[1:4]), "asd": list(feats[4:7])}
-        off, total = 0, None
+        par = self._branch_streams is not None
+        cur = torch.cuda.current_stream(self.device)
+        off, total, losses = 0, None, []
         for mi, (ratio, mode) in enumerate(zip(self.ratios, ("lam", "ttm", "asd"))):
             rows = groups[mode][0].shape[0] * (groups[mode][0].shape[1] if mode == "asd" else 1)
             tgt = labels[off:off + rows]
             off += rows
             eng = self.engines[mode]
-            act = eng.forward(groups[mode], training=True, seed=seed0 + mi, labels=tgt[:, 1:], loss=L.LOSS_CE,
-                              persistent=True, prompt=tgt[:, :-1])
-            eng.backward(act, dloss_scale=float(ratio), zero_grad=False)
-            l = act.t["loss"][0] * ratio
+            st = self._branch_streams[mode] if (par and mode != "ttm") else cur
+            if st is not cur:
+                st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                act = eng.forward(groups[mode], training=True, seed=seed0 + mi, labels=tgt[:, 1:], loss=L.LOSS_CE,
+                                  persistent=True, prompt=tgt[:, :-1])
+                eng.backward(act, dloss_scale=float(ratio), zero_grad=False,
+                             grad=self._branch_grads[mode] if (par and mode != "ttm") else None)
+            losses.append((act.t["loss"], ratio))
+        if par:
+            for mode in ("lam", "asd"):
+                cur.wait_stream(self._branch_streams[mode])
+            g = self.engine.arena.grad
+            with _dev_guard(self.device):
+                L.call("egot2_sum_into_f32", g.data_ptr(), self._branch_grads["lam"].data_ptr(),
+                       self._branch_grads["asd"].data_ptr(), g.numel(), _cur_stream(self.device))
+        for lt, ratio in losses:
+            l = lt[0] * ratio
             total = l if total is None else total + l
         return total
 
@@ -180,21 +207,9 @@ class PromptTranslatorTrainer(_PromptStepGraphs):
         self.step_count += 1
         if self.use_graphs and graph_key is not None:
             return self._graph_step(lambda: self._fwd_bwd_all(feats, labels, 4 * (abs(graph_key) + 1)), graph_key, False)
-        groups = {"lam": list(feats[0:1]), "ttm": list(feats[1:4]), "asd": list(feats[4:7])}
-        rows = {"lam": groups["lam"][0].shape[0], "ttm": groups["ttm"][0].shape[0],
-                "asd": groups["asd"][0].shape[0] * groups["asd"][0].shape[1]}
-        off, total = 0, None
-        first = True
-        for mi, (ratio, mode) in enumerate(zip(self.ratios, ("lam", "ttm", "asd"))):
-            tgt = labels[off:off + rows[mode]]
-            off += rows[mode]
-            eng = self.engines[mode]
-            act = eng.forward(groups[mode], training=True, seed=self.step_count * 4 + mi, labels=tgt[:, 1:],
-                              loss=L.LOSS_CE, persistent=True, prompt=tgt[:, :-1])
-            eng.backward(act, dloss_scale=float(ratio), zero_grad=first)      # one arena, accumulated over the three
-            first = False
-            l = act.t["loss"][0] * ratio
-            total = l if total is None else total + l
+        if not self._grad_clean:
+            self.engine.arena.grad.zero_()
+        total = self._fwd_bwd_all(feats, labels, self.step_count * 4)         # one arena, accumulated over the three
         if self.peer is not None:
             self.peer.step(self.opt_state, self.step_count, self.hp, _cur_stream(self.device))
             self._grad_clean = True

@@ -377,6 +377,9 @@ int egot2_slowfast_pool_fwd(const void* in, int32_t in_dtype, int32_t B, int32_t
                             int32_t Tout, void* out, int32_t out_dtype, void* stream);
 /* fp32 -> bf16 shadow copy of (part of) the parameter arena. */
 int egot2_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
+/* dst[i] += a[i] (+ b[i], b may be NULL), then a (and b) are cleared; n %% 4 == 0.  Joins the per-branch gradient arenas of an
+ * EgoT2-g step (three forwards of one model on three streams, HHI/tasks/multitask/video_tasktranslation.py:48-61). */
+int egot2_sum_into_f32(float* dst, float* a, float* b, size_t n, void* stream);
 int egot2_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);
 /* torch.optim.Adam (no amsgrad) over a flat arena; grad_scale multiplies the gradient first (1/world for DP mean). */
 int egot2_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
