@@ -193,26 +193,46 @@ struct Side {
   bool dirty = false;
 };
 int g_side_defer[kMaxDev] = {};
-Side* get_side(int idx) {
+// One SET of three side streams per calling stream (up to kCallers sets per device, least-recently-used reuse): callers on
+// different streams - the three forward/backward branches of an EgoT2-g step - then do not meet on a shared side stream,
+// which would chain every branch's joins behind the other branches' parameter-gradient work.  All streams and events of a
+// device are created on first use, so nothing is created while a stream capture is in progress; sharing a set (more than
+// kCallers calling streams) only over-synchronises, it is never incorrect.
+constexpr int kCallers = 4;
+struct SideSets {
+  Side sides[kCallers][3];
+  cudaStream_t owner[kCallers] = {};
+  unsigned long long used[kCallers] = {};
+  unsigned long long tick = 0;
+  int state = 0;      // 0 untried, 1 ok, -1 disabled / failed
+};
+SideSets g_side_sets[kMaxDev];
+Side* get_side(int idx, cudaStream_t caller) {
   // per device: streams and events belong to the device that was current when they were created
-  static Side all_sides[kMaxDev][3];
-  static int states[kMaxDev] = {};      // 0 untried, 1 ok, -1 disabled / failed
-  const int dev = cur_dev();
-  Side* sides = all_sides[dev];
-  int& state = states[dev];
-  if (state == 0) {
-    state = 1;
-    if (env_is("EGOT2_STREAMS", "0")) state = -1;
-    for (int i = 0; i < 3 && state == 1; ++i) {
-      if (cudaStreamCreateWithFlags(&sides[i].s, cudaStreamNonBlocking) != cudaSuccess) state = -1;
-      for (int k = 0; k < 8 && state == 1; ++k)
-        if (cudaEventCreateWithFlags(&sides[i].fork[k], cudaEventDisableTiming) != cudaSuccess) state = -1;
-      if (state == 1 && cudaEventCreateWithFlags(&sides[i].join, cudaEventDisableTiming) != cudaSuccess) state = -1;
-      for (int k = 0; k < 2 && state == 1; ++k)
-        if (cudaEventCreateWithFlags(&sides[i].pend[k], cudaEventDisableTiming) != cudaSuccess) state = -1;
-    }
+  SideSets& ss = g_side_sets[cur_dev()];
+  if (ss.state == 0) {
+    ss.state = 1;
+    if (env_is("EGOT2_STREAMS", "0")) ss.state = -1;
+    for (int c = 0; c < kCallers && ss.state == 1; ++c)
+      for (int i = 0; i < 3 && ss.state == 1; ++i) {
+        Side& sd = ss.sides[c][i];
+        if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) ss.state = -1;
+        for (int k = 0; k < 8 && ss.state == 1; ++k)
+          if (cudaEventCreateWithFlags(&sd.fork[k], cudaEventDisableTiming) != cudaSuccess) ss.state = -1;
+        if (ss.state == 1 && cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) ss.state = -1;
+        for (int k = 0; k < 2 && ss.state == 1; ++k)
+          if (cudaEventCreateWithFlags(&sd.pend[k], cudaEventDisableTiming) != cudaSuccess) ss.state = -1;
+      }
   }
-  return state == 1 ? &sides[idx] : nullptr;
+  if (ss.state != 1) return nullptr;
+  int slot = -1, lru = 0;
+  for (int c = 0; c < kCallers; ++c) {
+    if (ss.used[c] && ss.owner[c] == caller) { slot = c; break; }
+    if (ss.used[c] < ss.used[lru]) lru = c;
+  }
+  if (slot < 0) { slot = lru; ss.owner[slot] = caller; }
+  ss.used[slot] = ++ss.tick;
+  return &ss.sides[slot][idx];
 }
 }  // namespace
 int launch_priority(cudaStream_t st) {
@@ -222,9 +242,12 @@ int launch_priority(cudaStream_t st) {
     if (env_is("EGOT2_PRIO", "0") || cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess || lo == hi) state = -1;
   }
   if (state != 1) return INT_MIN;
-  for (int i = 0; i < 3; ++i) {
-    Side* sd = get_side(i);
-    if (sd && sd->s == st) return lo;          // numerically largest = least urgent
+  {
+    const SideSets& ss = g_side_sets[cur_dev()];
+    if (ss.state == 1)
+      for (int c = 0; c < kCallers; ++c)
+        for (int i = 0; i < 3; ++i)
+          if (ss.sides[c][i].s == st) return lo;          // numerically largest = least urgent
   }
   return hi;
 }
@@ -471,7 +494,7 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   // the per-task projections are independent: task 0 stays on `st`, the others alternate over two side streams
   // (not when the features need the shared fp32 -> bf16 staging buffer)
   const bool par = d->feat_dtype == d->dtype;
-  Side* sides[2] = {par ? get_side(0) : nullptr, par ? get_side(1) : nullptr};
+  Side* sides[2] = {par ? get_side(0, st) : nullptr, par ? get_side(1, st) : nullptr};
   bool used[2] = {false, false};
   // fork BOTH side streams before anything of this stage is enqueued on `st`: a fork event recorded after segment 0's
   // launch would make the other segments wait for it (seen in the in-graph timeline: they started when it had finished)
@@ -570,7 +593,7 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   so.n = d->n_seg;
   bool want_table = g->tok_table != nullptr;
   for (int k = 0; k < d->n_seg; ++k) { so.tokens[k] = d->seg_tokens[k]; so.out[k] = g->seg_embed[k]; want_table |= g->seg_embed[k] != nullptr; }
-  Side* tside = want_table ? get_side(2) : nullptr;
+  Side* tside = want_table ? get_side(2, st) : nullptr;
   if (want_table) EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dx, g->tok_table, so, pe, ke, side_fork(st, tside, 0)));
   if (d->no_ln) {
     dz = dx;                              // x = z + table: the token gradient IS the projection-output gradient
@@ -588,7 +611,7 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
     }
   }
   const bool par = d->feat_dtype == d->dtype;
-  Side* sides[2] = {par ? get_side(0) : nullptr, par ? get_side(1) : nullptr};
+  Side* sides[2] = {par ? get_side(0, st) : nullptr, par ? get_side(1, st) : nullptr};
   bool used[2] = {false, false};
   // fork BOTH side streams before anything of this stage is enqueued on `st`: a fork event recorded after segment 0's
   // launch would make the other segments wait for it (seen in the in-graph timeline: they started when it had finished)
@@ -616,7 +639,7 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
       sb.out[k] = (d->seg_has_proj[k] && d->seg_tokens[k] > 0) ? g->proj_b[k] : nullptr;
       any |= sb.out[k] != nullptr;
     }
-    Side* bside = get_side(2);
+    Side* bside = get_side(2, st);
     if (any) {
       EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dz, nullptr, sb, 0.f, 0, side_fork(st, bside, 1)));
       if (bside && !tside) tside = bside;       // joined below
@@ -780,9 +803,9 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
   // Three side streams: the four parameter-gradient groups total more kernel time than the data-gradient chain they hang
   // off, so on one stream the join at the end of the layer stalled the main chain; spread out, every group finishes
   // before the chain does.
-  Side* sd0 = get_side(0);
-  Side* sd1 = get_side(1);
-  Side* sd2 = get_side(2);
+  Side* sd0 = get_side(0, st);
+  Side* sd1 = get_side(1, st);
+  Side* sd2 = get_side(2, st);
   const bool defer = side_deferred();
   if (defer) {
     EGOT2_TRY(side_wait_pending(st, sd0, workspace));
@@ -882,10 +905,11 @@ extern "C" int egot2_encoder_layer_bwd(const egot2_layer_desc* d, const egot2_la
 extern "C" int egot2_side_defer(int on) { g_side_defer[cur_dev()] = on ? 1 : 0; return 0; }
 
 extern "C" int egot2_side_join_all(void* stream) {
-  for (int i = 0; i < 3; ++i) {
-    Side* sd = get_side(i);
-    if (sd && sd->dirty) EGOT2_TRY(side_join((cudaStream_t)stream, sd));
-  }
+  SideSets& ss = g_side_sets[cur_dev()];
+  if (ss.state == 1)
+    for (int c = 0; c < kCallers; ++c)
+      for (int i = 0; i < 3; ++i)
+        if (ss.sides[c][i].dirty) EGOT2_TRY(side_join((cudaStream_t)stream, &ss.sides[c][i]));
   return 0;
 }
 

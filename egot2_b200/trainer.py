@@ -174,22 +174,22 @@ class PromptTranslatorTrainer(_PromptStepGraphs):
         'asd' write their gradients to buffers of their own, and one launch (egot2_sum_into_f32) adds both into the arena
         and clears them.  EGOT2_G_STREAMS=0: one after the other on the caller's stream."""
         groups = {"lam": list(feats[0:1]), "ttm": list(feats[1:4]), "asd": list(feats[4:7])}
+        import contextlib
         par = self._branch_streams is not None
-        cur = torch.cuda.current_stream(self.device)
+        cur = torch.cuda.current_stream(self.device) if par else None
         off, total, losses = 0, None, []
         for mi, (ratio, mode) in enumerate(zip(self.ratios, ("lam", "ttm", "asd"))):
             rows = groups[mode][0].shape[0] * (groups[mode][0].shape[1] if mode == "asd" else 1)
             tgt = labels[off:off + rows]
             off += rows
             eng = self.engines[mode]
-            st = self._branch_streams[mode] if (par and mode != "ttm") else cur
-            if st is not cur:
-                st.wait_stream(cur)
-            with torch.cuda.stream(st):
+            side = par and mode != "ttm"
+            if side:
+                self._branch_streams[mode].wait_stream(cur)
+            with (torch.cuda.stream(self._branch_streams[mode]) if side else contextlib.nullcontext()):
                 act = eng.forward(groups[mode], training=True, seed=seed0 + mi, labels=tgt[:, 1:], loss=L.LOSS_CE,
                                   persistent=True, prompt=tgt[:, :-1])
-                eng.backward(act, dloss_scale=float(ratio), zero_grad=False,
-                             grad=self._branch_grads[mode] if (par and mode != "ttm") else None)
+                eng.backward(act, dloss_scale=float(ratio), zero_grad=False, grad=self._branch_grads[mode] if side else None)
             losses.append((act.t["loss"], ratio))
         if par:
             for mode in ("lam", "asd"):

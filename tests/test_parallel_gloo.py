@@ -57,7 +57,7 @@ def _worker(rank, world, port, case_name, n_clips, q):
         exact = g2 * scale2
         full_out = par.gather_outputs(out, n_clips)
         if rank == 0:
-            q.put((ddp, exact, full_out))
+            q.put(tuple(t.detach().numpy().copy() for t in (ddp, exact, full_out)))      # plain arrays: no fd passing race with the exiting worker
     finally:
         dist.destroy_process_group()
 
@@ -71,7 +71,7 @@ def test_two_rank_gradient_allreduce_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, world, port, case_name, n_clips, q)) for r in range(world)]
     for p in procs:
         p.start()
-    ddp, exact, full_out = q.get(timeout=240)
+    ddp, exact, full_out = (torch.from_numpy(a) for a in q.get(timeout=240))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -105,7 +105,7 @@ def _overlap_worker(rank, world, port, q):
         whole = full.clone()
         dist.all_reduce(whole)                            # the single-bucket schedule
         if rank == 0:
-            q.put((arena.grad.clone(), whole, nb, arena.numel))
+            q.put((arena.grad.numpy().copy(), whole.numpy().copy(), nb, arena.numel))
     finally:
         dist.destroy_process_group()
 
@@ -120,6 +120,7 @@ def test_two_piece_overlapped_allreduce_equals_single_bucket():
     for p in procs:
         p.start()
     two_piece, whole, nb, numel = q.get(timeout=240)
+    two_piece, whole = torch.from_numpy(two_piece), torch.from_numpy(whole)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
