@@ -28,6 +28,7 @@
 // Barriers that the leader's MMA threads wait on (operands of BOTH CTAs ready, accumulators drained by BOTH epilogues)
 // live in the leader and receive remote arrivals; completion barriers are signalled in both CTAs by multicast commits.
 #include <stdlib.h>
+#include <string.h>
 
 #define EGOT2_FILE_ID 5
 #include "ops.h"
@@ -111,6 +112,7 @@ struct FfnArgs {
   // their partial GEMM2 accumulator into `partial` (fp32, rows relative to token split_pair0*256); a fix-up kernel finishes
   int split_pair0, S;
   float* partial;
+  int* tile_ctr;         // one arrival counter per 128-row tail tile (zero on entry and on exit); nullptr: separate fix-up kernels
   const bf16* fix_x1; const bf16* fix_d1; bf16* fix_y2; bf16* fix_out;     // global tensors the fix-up kernel reads / writes
   long long* trace;      // EGOT2_FFN_TRACE builds only: per-chunk clock64 stamps of CTA 0
 };
@@ -144,6 +146,65 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 __device__ __forceinline__ void sts128(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// Finishing one token row of an FF-split tail tile once all S partial sums are in `prow` (fp32, this row's 128 columns): what
+// the main kernel's final epilogue does for a regular tile, by ONE WARP (4 columns per lane); the scratch row is left zeroed.
+// Called by the stand-alone fix-up kernels (default) or by the last-arriving slice of the tile (EGOT2_FFN_FIXUP=inkernel).
+__device__ __forceinline__ void fixup_row_fwd(int lane, int m, float* __restrict__ prow, const bf16* __restrict__ x1,
+                                              const float* __restrict__ b2, const float* __restrict__ ln_g,
+                                              const float* __restrict__ ln_b, float eps, float p_drop, uint64_t key_drop2,
+                                              unsigned long long ep, bf16* __restrict__ y2, float* __restrict__ stat2,
+                                              bf16* __restrict__ x_out) {
+  const int c0 = lane * 4;
+  float4* pp = reinterpret_cast<float4*>(prow + c0);
+  const float4 acc = ld_cg_f4(prow + c0);                   // the partials were added in L2 (red.global): read them there
+  *pp = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint2 xw = *reinterpret_cast<const uint2*>(x1 + (size_t)m * H + c0);
+  const float4 bb = *reinterpret_cast<const float4*>(b2 + c0);
+  float v[4] = {acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w};
+  if (p_drop > 0.f) {
+    const float inv_keep = 1.f / (1.f - p_drop);
+    const uint32_t thr = drop_threshold(p_drop);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = drop_bits(key_drop2 ^ ep, (uint64_t)m * H + c0 + i) >= thr ? v[i] * inv_keep : 0.f;
+  }
+  v[0] += __uint_as_float(xw.x << 16); v[1] += __uint_as_float(xw.x & 0xffff0000u);
+  v[2] += __uint_as_float(xw.y << 16); v[3] += __uint_as_float(xw.y & 0xffff0000u);
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 yw; yw.x = *reinterpret_cast<uint32_t*>(&t0); yw.y = *reinterpret_cast<uint32_t*>(&t1);
+  *reinterpret_cast<uint2*>(y2 + (size_t)m * H + c0) = yw;
+  v[0] = __uint_as_float(yw.x << 16); v[1] = __uint_as_float(yw.x & 0xffff0000u);
+  v[2] = __uint_as_float(yw.y << 16); v[3] = __uint_as_float(yw.y & 0xffff0000u);
+  float sum = (v[0] + v[1]) + (v[2] + v[3]);
+  float sq = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
+  sum = warp_sum(sum); sq = warp_sum(sq);
+  const float mean = sum * (1.f / H);
+  const float var = fmaxf(sq * (1.f / H) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  if (lane == 0) { stat2[2 * (size_t)m] = mean; stat2[2 * (size_t)m + 1] = rstd; }
+  const float4 g4 = *reinterpret_cast<const float4*>(ln_g + c0), e4 = *reinterpret_cast<const float4*>(ln_b + c0);
+  __nv_bfloat162 o0 = __floats2bfloat162_rn((v[0] - mean) * rstd * g4.x + e4.x, (v[1] - mean) * rstd * g4.y + e4.y);
+  __nv_bfloat162 o1 = __floats2bfloat162_rn((v[2] - mean) * rstd * g4.z + e4.z, (v[3] - mean) * rstd * g4.w + e4.w);
+  uint2 ow; ow.x = *reinterpret_cast<uint32_t*>(&o0); ow.y = *reinterpret_cast<uint32_t*>(&o1);
+  *reinterpret_cast<uint2*>(x_out + (size_t)m * H + c0) = ow;
+}
+// backward: d3 = partial + d1 (the gradient arriving through the residual branch)
+__device__ __forceinline__ void fixup_row_bwd(int lane, int m, float* __restrict__ prow, const bf16* __restrict__ d1,
+                                              bf16* __restrict__ d3) {
+  const int c0 = lane * 4;
+  const float4 acc = ld_cg_f4(prow + c0);
+  *reinterpret_cast<float4*>(prow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint2 dw = *reinterpret_cast<const uint2*>(d1 + (size_t)m * H + c0);
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(acc.x + __uint_as_float(dw.x << 16), acc.y + __uint_as_float(dw.x & 0xffff0000u));
+  __nv_bfloat162 t1 = __floats2bfloat162_rn(acc.z + __uint_as_float(dw.y << 16), acc.w + __uint_as_float(dw.y & 0xffff0000u));
+  uint2 ow; ow.x = *reinterpret_cast<uint32_t*>(&t0); ow.y = *reinterpret_cast<uint32_t*>(&t1);
+  *reinterpret_cast<uint2*>(d3 + (size_t)m * H + c0) = ow;
 }
 
 // BWD = false: the forward block described above.
@@ -567,6 +628,26 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           red_add_v4(prow + j8 * 8 + 4, __uint_as_float(rr[4]), __uint_as_float(rr[5]), __uint_as_float(rr[6]), __uint_as_float(rr[7]));
         }
       }
+      if (a.tile_ctr) {
+        // The slice that arrives LAST at this CTA's 128-row tile finishes it right here (what used to be a separate fix-up
+        // launch behind the kernel): fence the partial sums, count this slice in, and if all S are in, one warp per row.
+        __threadfence();
+        named_bar_sync(2, EPW * 32);
+        volatile uint32_t* s_flag = reinterpret_cast<volatile uint32_t*>(red);
+        int* ctr = a.tile_ctr + (m0 - a.split_pair0 * 2 * BM) / BM;
+        if (warp == 2 && lane == 0) s_flag[0] = (uint32_t)atomicAdd(ctr, 1);
+        named_bar_sync(1, EPW * 32);
+        if ((int)s_flag[0] == a.S - 1) {
+          __threadfence();
+          float* pbase = a.partial + (size_t)(m0 - a.split_pair0 * 2 * BM) * H;
+          for (int rloc = warp - 2; rloc < BM && m0 + rloc < a.M; rloc += EPW) {
+            if constexpr (BWD) fixup_row_bwd(lane, m0 + rloc, pbase + (size_t)rloc * H, a.fix_d1, a.fix_out);
+            else fixup_row_fwd(lane, m0 + rloc, pbase + (size_t)rloc * H, a.fix_x1, sVec, sVec + 128, sVec + 256, a.eps, a.p_drop,
+                               a.key_drop2, egot2_ep, a.fix_y2, a.stat2, a.fix_out);
+          }
+          if (warp == 2 && lane == 0) *ctr = 0;
+        }
+      }
     } else if constexpr (BWD) {
       // d3 = acc2 + d1 (gradient through the residual branch); with no dropout2, d1 IS the d2 tile still in sX
       const bf16* d1row = (a.d1 && row_ok) ? a.d1 + (size_t)m * H + nb : nullptr;      // nb is a multiple of 32: 16 B aligned
@@ -699,9 +780,8 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   }
 }
 
-// ---------------------------------------------------------------- fix-up of the FF-split tail tiles
-// One warp per token row (4 columns per lane).  Reads the summed fp32 partials, finishes the block exactly like the main
-// kernel's final epilogue does for a regular tile, and leaves the scratch rows zeroed for the next launch.
+// ---------------------------------------------------------------- stand-alone fix-up of the FF-split tail tiles
+// (the default; EGOT2_FFN_FIXUP=inkernel lets the last-arriving slice of a tile finish it inside the main kernel instead)
 __global__ void __launch_bounds__(256) ffn_fixup_fwd_kernel(int rows, int m_base, float* __restrict__ partial,
                                                             const bf16* __restrict__ x1, const float* __restrict__ b2,
                                                             const float* __restrict__ ln_g, const float* __restrict__ ln_b,
@@ -709,58 +789,17 @@ __global__ void __launch_bounds__(256) ffn_fixup_fwd_kernel(int rows, int m_base
                                                             bf16* __restrict__ y2, float* __restrict__ stat2,
                                                             bf16* __restrict__ x_out) {
   EGOT2_PDL_ENTER();
-  const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
-  const int m = m_base + r, c0 = lane * 4;
-  float4* pp = reinterpret_cast<float4*>(partial + (size_t)r * H + c0);
-  const float4 acc = *pp;
-  *pp = make_float4(0.f, 0.f, 0.f, 0.f);
-  const uint2 xw = *reinterpret_cast<const uint2*>(x1 + (size_t)m * H + c0);
-  const float4 bb = *reinterpret_cast<const float4*>(b2 + c0);
-  float v[4] = {acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w};
-  if (p_drop > 0.f) {
-    const float inv_keep = 1.f / (1.f - p_drop);
-    const uint32_t thr = drop_threshold(p_drop);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = drop_bits(key_drop2 ^ egot2_ep, (uint64_t)m * H + c0 + i) >= thr ? v[i] * inv_keep : 0.f;
-  }
-  v[0] += __uint_as_float(xw.x << 16); v[1] += __uint_as_float(xw.x & 0xffff0000u);
-  v[2] += __uint_as_float(xw.y << 16); v[3] += __uint_as_float(xw.y & 0xffff0000u);
-  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
-  uint2 yw; yw.x = *reinterpret_cast<uint32_t*>(&t0); yw.y = *reinterpret_cast<uint32_t*>(&t1);
-  *reinterpret_cast<uint2*>(y2 + (size_t)m * H + c0) = yw;
-  v[0] = __uint_as_float(yw.x << 16); v[1] = __uint_as_float(yw.x & 0xffff0000u);
-  v[2] = __uint_as_float(yw.y << 16); v[3] = __uint_as_float(yw.y & 0xffff0000u);
-  float sum = (v[0] + v[1]) + (v[2] + v[3]);
-  float sq = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
-  sum = warp_sum(sum); sq = warp_sum(sq);
-  const float mean = sum * (1.f / H);
-  const float var = fmaxf(sq * (1.f / H) - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + eps);
-  if (lane == 0) { stat2[2 * (size_t)m] = mean; stat2[2 * (size_t)m + 1] = rstd; }
-  const float4 g4 = *reinterpret_cast<const float4*>(ln_g + c0), e4 = *reinterpret_cast<const float4*>(ln_b + c0);
-  __nv_bfloat162 o0 = __floats2bfloat162_rn((v[0] - mean) * rstd * g4.x + e4.x, (v[1] - mean) * rstd * g4.y + e4.y);
-  __nv_bfloat162 o1 = __floats2bfloat162_rn((v[2] - mean) * rstd * g4.z + e4.z, (v[3] - mean) * rstd * g4.w + e4.w);
-  uint2 ow; ow.x = *reinterpret_cast<uint32_t*>(&o0); ow.y = *reinterpret_cast<uint32_t*>(&o1);
-  *reinterpret_cast<uint2*>(x_out + (size_t)m * H + c0) = ow;
+  fixup_row_fwd(threadIdx.x & 31, m_base + r, partial + (size_t)r * H, x1, b2, ln_g, ln_b, eps, p_drop, key_drop2, egot2_ep, y2,
+                stat2, x_out);
 }
-// d3 = partial + d1 (the gradient arriving through the residual branch)
 __global__ void __launch_bounds__(256) ffn_fixup_bwd_kernel(int rows, int m_base, float* __restrict__ partial,
                                                             const bf16* __restrict__ d1, bf16* __restrict__ d3) {
   EGOT2_PDL_ENTER();
-  const int i = blockIdx.x * 256 + threadIdx.x;          // one thread per 4 columns
-  if (i >= rows * (H / 4)) return;
-  const int r = i / (H / 4), c0 = (i % (H / 4)) * 4;
-  const size_t g = (size_t)(m_base + r) * H + c0;
-  float4* pp = reinterpret_cast<float4*>(partial + (size_t)r * H + c0);
-  const float4 acc = *pp;
-  *pp = make_float4(0.f, 0.f, 0.f, 0.f);
-  const uint2 dw = *reinterpret_cast<const uint2*>(d1 + g);
-  __nv_bfloat162 t0 = __floats2bfloat162_rn(acc.x + __uint_as_float(dw.x << 16), acc.y + __uint_as_float(dw.x & 0xffff0000u));
-  __nv_bfloat162 t1 = __floats2bfloat162_rn(acc.z + __uint_as_float(dw.y << 16), acc.w + __uint_as_float(dw.y & 0xffff0000u));
-  uint2 ow; ow.x = *reinterpret_cast<uint32_t*>(&t0); ow.y = *reinterpret_cast<uint32_t*>(&t1);
-  *reinterpret_cast<uint2*>(d3 + g) = ow;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  fixup_row_bwd(threadIdx.x & 31, m_base + r, partial + (size_t)r * H, d1, d3);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -801,7 +840,8 @@ size_t ffn_scratch_bytes(int M) {
   // the tail is always shorter than one wave of pairs, whatever the occupancy query says at launch time
   const int pairs = (M + 2 * BM - 1) / (2 * BM), slots = sm_count() / 2;
   const int tail = pairs < slots ? pairs : slots;
-  return pairs > 1 ? (size_t)tail * 2 * BM * H * sizeof(float) : 0;
+  // fp32 partial sums of the tail tiles' rows + one arrival counter per 128-row tile (both zero on entry and on exit)
+  return pairs > 1 ? (size_t)tail * 2 * BM * H * sizeof(float) + (size_t)tail * 2 * sizeof(int) : 0;
 }
 
 bool ffn_fused_supported(int dtype, int Hdim, int FF) {
@@ -858,13 +898,23 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
     }
     a.S = S;
     a.split_pair0 = S > 1 ? pairs - tail : pairs;
+    // the counters sit behind the partial rows of the largest tail this scratch was sized for
+    // EGOT2_FFN_FIXUP=inkernel: the last-arriving slice of a tail tile finishes it inside the main kernel (no fix-up launch).
+    // Measured on B200 (HHI b256): 62.1 / 64.2 us (forward / backward-dx launchers) against 54.1 / 58.6 with the separate
+    // fix-up kernels - the last CTA walks its 128 rows with 16 warps at the very end of the kernel, the separate launch
+    // spreads them over 512 CTAs - so the separate launches stay the default.
+    static const bool separate = !(getenv("EGOT2_FFN_FIXUP") && strcmp(getenv("EGOT2_FFN_FIXUP"), "inkernel") == 0);
+    {
+      const int slots_max = sm_count() / 2, tail_max = pairs < slots_max ? pairs : slots_max;
+      a.tile_ctr = (S > 1 && !separate) ? reinterpret_cast<int*>(a.partial + (size_t)tail_max * 2 * BM * H) : nullptr;
+    }
     const int grid_pairs = S > 1 ? (pairs - tail) + tail * S : pairs;
     launch(kernels[ki], dim3(2 * grid_pairs), dim3(NTHREADS), smem, st, tx, tw1, tw2, thid, ty2, tout, a);
     EGOT2_LAUNCH_CHECK();
-    if (S > 1) {
+    if (S > 1 && separate) {
       const int m_base = a.split_pair0 * 2 * BM, rows = M - m_base;
       if (bwd)
-        launch(ffn_fixup_bwd_kernel, dim3((rows * (H / 4) + 255) / 256), dim3(256), 0, st, rows, m_base, a.partial, a.fix_d1, a.fix_out);
+        launch(ffn_fixup_bwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, rows, m_base, a.partial, a.fix_d1, a.fix_out);
       else
         launch(ffn_fixup_fwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, rows, m_base, a.partial, a.fix_x1, a.b2, a.ln_g, a.ln_b,
                a.eps, a.p_drop, a.key_drop2, a.fix_y2, a.stat2, a.fix_out);
