@@ -7,8 +7,8 @@
 //   forward            S = Q_i K^T, P = softmax(scale S) (quad shuffles), O_i = P V, lse
 //   backward, pass 1   rows = queries: recompute P from lse, dP = dO_i V^T, dS = P (dP - D), dQ_i = scale dS K
 //   backward, pass 2   rows = keys:    S^T = K_j Q^T, dP^T = V_j dO^T, dV_j = P^T dO, dK_j = scale dS^T Q
-// T <= 128 (the HOI translators: 48 / 8 tokens; HHI at D <= 42 frames x 3 tasks); longer clips use the
-// shape-general kernels of attention_simt.cu.  Dropout masks are regenerated from (key, b, h, query, key index).
+// T <= 128 with head dims 16 / 32 / 64 (the HOI translators: 48 / 8 tokens; HHI at D <= 42 frames x 3 tasks) and T <= 32 with
+// head dim 128 (LTA at H = 1024); longer clips use the shape-general kernels of attention_simt.cu.  Dropout masks are regenerated from (key, b, h, query, key index).
 #include <math.h>
 
 #define EGOT2_FILE_ID 6
@@ -469,6 +469,8 @@ inline int pick_tk16(int T) { return T <= 16 ? 1 : (T <= 32 ? 2 : (T <= 64 ? 4 :
 bool attention_mma_supported(int dtype, int T, int H, int heads) {
   if (dtype != EGOT2_BF16 || heads <= 0 || H % heads) return false;
   const int dh = H / heads;
+  if (dh == 128) return T >= 1 && T <= 32 && (H % 8 == 0);      // LTA at its shipped width (H 1024 / 8 heads, 8 tokens): the
+                                                                 // output tile alone is 64 registers, so short clips only
   return T >= 1 && T <= 128 && (dh == 16 || dh == 32 || dh == 64) && (H % 8 == 0);
 }
 
@@ -483,6 +485,7 @@ bool attention_mma_supported(int dtype, int T, int H, int heads) {
     case 64 * 16 + 1: return FN<64, 1>(__VA_ARGS__);  case 64 * 16 + 2: return FN<64, 2>(__VA_ARGS__); \
     case 64 * 16 + 4: return FN<64, 4>(__VA_ARGS__);  case 64 * 16 + 6: return FN<64, 6>(__VA_ARGS__); \
     case 64 * 16 + 8: return FN<64, 8>(__VA_ARGS__);                                  \
+    case 128 * 16 + 1: return FN<128, 1>(__VA_ARGS__); case 128 * 16 + 2: return FN<128, 2>(__VA_ARGS__); \
   }
 
 int attention_mma_fwd(int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p_drop,

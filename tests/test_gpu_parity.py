@@ -289,7 +289,7 @@ def attn_mask_oracle(seed, n_bh, T, p):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-@pytest.mark.parametrize("T,H,heads", [(90, 128, 4), (48, 128, 8), (128, 256, 4), (33, 64, 4), (150, 128, 4)])
+@pytest.mark.parametrize("T,H,heads", [(90, 128, 4), (48, 128, 8), (128, 256, 4), (33, 64, 4), (150, 128, 4), (8, 1024, 8)])
 def test_attention_dropout_mask_is_exact(dtype, T, H, heads):
     """Attention with dropout on the probabilities (train mode): forward and backward must use exactly the mask of
     the documented counter-based generator — checked against a torch reference fed the same mask."""
