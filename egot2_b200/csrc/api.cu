@@ -150,6 +150,8 @@ int attention_fwd(int dtype, int B, int T, int H, int heads, const void* qkv, vo
     return attention_wide_fwd(dtype, B, T, H, heads, qkv, out, lse, p_drop, drop_key, st);
   if (attention_mma_supported(dtype, T, H, heads) && !force_simt_attention())
     return attention_mma_fwd(B, T, H, heads, qkv, out, lse, p_drop, drop_key, st);
+  if (attention_long_supported(dtype, T, H, heads) && !force_simt_attention())
+    return attention_long_fwd(B, T, H, heads, qkv, out, lse, p_drop, drop_key, st);
   return attention_simt_fwd(dtype, B, T, H, heads, qkv, out, lse, p_drop, drop_key, st);
 }
 int attention_bwd(int dtype, int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse,
@@ -159,6 +161,8 @@ int attention_bwd(int dtype, int B, int T, int H, int heads, const void* qkv, co
     return attention_wide_bwd(dtype, B, T, H, heads, qkv, out, lse, dout, dqkv, p_drop, drop_key, st);
   if (attention_mma_supported(dtype, T, H, heads) && !force_simt_attention())
     return attention_mma_bwd(B, T, H, heads, qkv, out, lse, dout, dqkv, p_drop, drop_key, st);
+  if (attention_long_supported(dtype, T, H, heads) && !force_simt_attention())
+    return attention_long_bwd(B, T, H, heads, qkv, out, lse, dout, dqkv, p_drop, drop_key, st);
   return attention_simt_bwd(dtype, B, T, H, heads, qkv, out, lse, dout, dqkv, p_drop, drop_key, ws, ws_bytes, st);
 }
 

@@ -77,6 +77,12 @@ int attention_mma_fwd(int B, int T, int H, int heads, const void* qkv, void* out
                       uint64_t drop_key, cudaStream_t st);
 int attention_mma_bwd(int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse,
                       const void* dout, void* dqkv, float p_drop, uint64_t drop_key, cudaStream_t st);
+// attention_long.cu: tensor-core kernels for 128 < T <= 512 (bf16, head dim 16 / 32 / 64; online softmax over key blocks)
+bool attention_long_supported(int dtype, int T, int H, int heads);
+int attention_long_fwd(int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p_drop, uint64_t drop_key,
+                       cudaStream_t st);
+int attention_long_bwd(int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse, const void* dout,
+                       void* dqkv, float p_drop, uint64_t drop_key, cudaStream_t st);
 // attention_wide.cu: head dim > 128 over T <= 32 tokens (LTA 2-task at H = 2048, 4 heads)
 int attention_wide_fwd(int dtype, int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p_drop,
                        uint64_t drop_key, cudaStream_t st);

@@ -289,14 +289,15 @@ def attn_mask_oracle(seed, n_bh, T, p):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-@pytest.mark.parametrize("T,H,heads", [(90, 128, 4), (48, 128, 8), (128, 256, 4), (33, 64, 4), (150, 128, 4), (8, 1024, 8)])
+@pytest.mark.parametrize("T,H,heads", [(90, 128, 4), (48, 128, 8), (128, 256, 4), (33, 64, 4), (150, 128, 4), (8, 1024, 8), (200, 128, 4),
+                                         (453, 64, 2), (300, 256, 4)])
 def test_attention_dropout_mask_is_exact(dtype, T, H, heads):
     """Attention with dropout on the probabilities (train mode): forward and backward must use exactly the mask of
     the documented counter-based generator — checked against a torch reference fed the same mask."""
     from egot2_b200 import engine as E
     torch.manual_seed(4)
     B, seed = 2, 99
-    p = 0.5 if T in (48, 128, 150) else 0.25     # p == 0.5: one random bit per (query, key) pair, 32 keys per hash
+    p = 0.5 if T in (48, 128, 150, 453) else 0.25     # p == 0.5: one random bit per (query, key) pair, 32 keys per hash
     tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
     qkv = (torch.randn(B, T, 3 * H, device="cuda") * 0.7).to(tdt)
     dout = torch.randn(B, T, H, device="cuda").to(tdt)
@@ -320,6 +321,33 @@ def test_attention_dropout_mask_is_exact(dtype, T, H, heads):
     t_out, t_g = (1e-4, 1e-3) if dtype == "fp32" else (1.5e-2, 3e-2)
     assert float((out.double() - ref.detach()).abs().max()) <= t_out * float(ref.abs().max())
     assert float((dqkv.double() - gref).abs().max()) <= t_g * float(gref.abs().max())
+
+
+@pytest.mark.parametrize("T,H,heads,want", [(90, 128, 4, "attn_mma_"), (8, 1024, 8, "attn_mma_"), (150, 256, 4, "attn_long_"),
+                                            (453, 64, 2, "attn_long_"), (512, 128, 4, "attn_long_"), (384, 256, 4, "attn_long_")])
+def test_bf16_attention_runs_on_tensor_cores(T, H, heads, want):
+    """In bf16 mode no translator shape of the reference may fall back to the FFMA attention kernels: T <= 128 (and head dim
+    128 at T <= 32) take attention_mma.cu, 128 < T <= 512 take attention_long.cu - checked on the launcher tags."""
+    from egot2_b200 import engine as E
+    B = 2
+    qkv = (torch.randn(B, T, 3 * H, device="cuda") * 0.5).to(torch.bfloat16)
+    dout = torch.randn(B, T, H, device="cuda").to(torch.bfloat16)
+    out = torch.empty(B, T, H, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, T, device="cuda", dtype=torch.float32)
+    dqkv = torch.empty_like(qkv)
+    nws = L.load().egot2_attention_bwd_workspace_bytes(L.BF16, B, T, H, heads)
+    ws = torch.empty(max(nws, 16), device="cuda", dtype=torch.uint8)
+    L.prof_enable(True)
+    try:
+        L.call("egot2_attention_fwd", L.BF16, B, T, H, heads, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), 0.1, 1, 3, E._stream())
+        L.call("egot2_attention_bwd", L.BF16, B, T, H, heads, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
+               dqkv.data_ptr(), 0.1, 1, 3, ws.data_ptr(), nws, E._stream())
+        torch.cuda.synchronize()
+        tags = [r[0] for r in L.prof_report()]
+    finally:
+        L.prof_enable(False)
+    assert any(t.startswith(want + "fwd") for t in tags) and any(t.startswith(want + "bwd") for t in tags), tags
+    assert torch.isfinite(out.float()).all() and torch.isfinite(dqkv.float()).all()
 
 
 @pytest.mark.parametrize("name", ["hhi3_h128_d30", "hoi_pnr_h128_l6"])
