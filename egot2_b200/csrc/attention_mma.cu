@@ -10,6 +10,7 @@
 // T <= 128 with head dims 16 / 32 / 64 (the HOI translators: 48 / 8 tokens; HHI at D <= 42 frames x 3 tasks) and T <= 32 with
 // head dim 128 (LTA at H = 1024); longer clips use the shape-general kernels of attention_simt.cu.  Dropout masks are regenerated from (key, b, h, query, key index).
 #include <math.h>
+#include <stdlib.h>
 
 #define EGOT2_FILE_ID 6
 #include "ops.h"
@@ -117,8 +118,9 @@ __device__ __forceinline__ void gemm_pv_kb(float (&o)[Tile<DH>::ND][4], const ui
 template <int DH, int TK16>
 __device__ __forceinline__ void stage(uint32_t dst, const bf16* __restrict__ src, int ld_src, int T) {
   constexpr int CH = DH / 8;                 // 16-byte chunks per row
-  constexpr int RPI = TK16 * 32 / CH;        // rows covered by one pass of the CTA
-  const int r0 = threadIdx.x / CH, c = (threadIdx.x % CH) * 8;
+  constexpr int RPI = TK16 * 32 / CH;        // rows covered by one pass of the head's TK16 warps
+  const int tid = threadIdx.x % (TK16 * 32); // several heads share a CTA (HPC): each head's warps stage that head's matrices
+  const int r0 = tid / CH, c = (tid % CH) * 8;
 #pragma unroll
   for (int i = 0; i < DH / 16; ++i) {
     const int r = r0 + i * RPI;
@@ -150,15 +152,25 @@ __device__ __forceinline__ void mask_words(uint64_t key, uint64_t row, int wpr, 
 // Dropout handling is a template parameter (the three variants share nothing on the per-element path and the unused ones
 // would only dilute the instruction cache): MODE 0 no dropout, 1 p == 0.5 (one random bit per pair), 2 general p.
 // ------------------------------------------------------------------ forward
-template <int DH, int TK16, int MODE>
-__global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) attn_mma_fwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv,
-                                                                 bf16* __restrict__ out, float* __restrict__ lse,
-                                                                 float p_drop, uint64_t drop_key) {
+// resident CTAs per SM the register allocation aims at: 4 for the small tiles, 2 where the score tile (T = 128) or the
+// accumulators (head dim 64: the backward keeps two DH-wide tiles) need more than 80 registers - the dh-64 / T-96 backward
+// spilled 2.4 KB per thread at 4 - divided by the heads a CTA carries
+template <int DH, int TK16, int HPC> constexpr int min_blocks() {
+  constexpr int base = (TK16 == 8 || DH >= 64) ? 2 : EGOT2_ATTN_MINB;
+  return base / HPC > 0 ? base / HPC : 1;
+}
+// HPC heads of one clip per CTA (each head on its own TK16 warps): one staging round trip and one CTA launch serve HPC heads -
+// with 8 heads of 16 dims over 48 tokens (HOI PNR) a (clip, head) CTA moved 4.5 KB and was all fixed cost.
+template <int DH, int TK16, int MODE, int HPC>
+__global__ void __launch_bounds__(TK16 * 32 * HPC, min_blocks<DH, TK16, HPC>())
+attn_mma_fwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
+                    float p_drop, uint64_t drop_key) {
   constexpr int NT = TK16 * 2, LD = Tile<DH>::LD, TP = TK16 * 16;
   extern __shared__ __align__(16) uint8_t smem[];
-  const uint32_t uQ = (uint32_t)__cvta_generic_to_shared(smem), uK = uQ + TP * LD * 2, uV = uK + TP * LD * 2;
-  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hl = (threadIdx.x >> 5) / TK16;                       // which of this CTA's heads
+  const uint32_t uQ = (uint32_t)__cvta_generic_to_shared(smem) + hl * (3 * TP * LD * 2), uK = uQ + TP * LD * 2, uV = uK + TP * LD * 2;
+  const int hg = heads / HPC, b = blockIdx.x / hg, h = (blockIdx.x % hg) * HPC + hl, bh = b * heads + h;
+  const int warp = (threadIdx.x >> 5) % TK16, lane = threadIdx.x & 31;
   const bf16* base = qkv + (size_t)b * T * 3 * H + h * DH;
   EGOT2_PDL_ENTER();
   stage<DH, TK16>(uQ, base, 3 * H, T);
@@ -243,19 +255,22 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
 }
 
 // ------------------------------------------------------------------ backward
-template <int DH, int TK16, int MODE>
-__global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) attn_mma_bwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv,
-                                                                 const bf16* __restrict__ out, const float* __restrict__ lse,
-                                                                 const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
-                                                                 float p_drop, uint64_t drop_key) {
+template <int DH, int TK16, int MODE, int HPC>
+__global__ void __launch_bounds__(TK16 * 32 * HPC, min_blocks<DH, TK16, HPC>())
+attn_mma_bwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+                    const float* __restrict__ lse, const bf16* __restrict__ dout, bf16* __restrict__ dqkv, float p_drop,
+                    uint64_t drop_key) {
   constexpr int LD = Tile<DH>::LD, TP = TK16 * 16;
+  constexpr int HEAD_BYTES = 4 * TP * LD * 2 + 2 * TP * 4;                   // Q, K, V, dO tiles + lse / D vectors of one head
   extern __shared__ __align__(16) uint8_t smem[];
-  const uint32_t uQ = (uint32_t)__cvta_generic_to_shared(smem), uK = uQ + TP * LD * 2, uV = uK + TP * LD * 2,
+  const int hl = (threadIdx.x >> 5) / TK16;                                  // which of this CTA's heads
+  const uint32_t uQ = (uint32_t)__cvta_generic_to_shared(smem) + hl * HEAD_BYTES, uK = uQ + TP * LD * 2, uV = uK + TP * LD * 2,
                  udO = uV + TP * LD * 2;
-  float* sL = reinterpret_cast<float*>(smem + (size_t)4 * TP * LD * 2);      // lse * log2(e) per query
+  float* sL = reinterpret_cast<float*>(smem + (size_t)hl * HEAD_BYTES + (size_t)4 * TP * LD * 2);      // lse * log2(e) per query
   float* sD = sL + TP;                                                       // D = rowsum(dO * O) per query
-  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hg = heads / HPC, b = blockIdx.x / hg, h = (blockIdx.x % hg) * HPC + hl, bh = b * heads + h;
+  const int warp = (threadIdx.x >> 5) % TK16, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x % (TK16 * 32);                                 // thread index inside the head's warp group
   const bf16* base = qkv + (size_t)b * T * 3 * H + h * DH;
   const bf16* ob = out + (size_t)b * T * H + h * DH;
   const bf16* dob = dout + (size_t)b * T * H + h * DH;
@@ -270,11 +285,11 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
     constexpr int RPI = TK16 * 8;              // rows per pass (4 lanes each)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int r = (threadIdx.x >> 2) + i * RPI;
+      const int r = (tid >> 2) + i * RPI;
       float d = 0.f;
       if (r < T) {
 #pragma unroll
-        for (int c = (threadIdx.x & 3) * 8; c < DH; c += 32) {
+        for (int c = (tid & 3) * 8; c < DH; c += 32) {
           const uint4 a4 = *reinterpret_cast<const uint4*>(dob + (size_t)r * H + c);
           const uint4 o4 = *reinterpret_cast<const uint4*>(ob + (size_t)r * H + c);
           const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, ow[4] = {o4.x, o4.y, o4.z, o4.w};
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
       }
       d += __shfl_xor_sync(0xffffffffu, d, 1);
       d += __shfl_xor_sync(0xffffffffu, d, 2);
-      if ((threadIdx.x & 3) == 0) { sD[r] = d; sL[r] = r < T ? lse[(size_t)bh * T + r] * l2e : 0.f; }
+      if ((tid & 3) == 0) { sD[r] = d; sL[r] = r < T ? lse[(size_t)bh * T + r] * l2e : 0.f; }
     }
   }
   stage_wait();
@@ -429,37 +444,63 @@ __global__ void __launch_bounds__(TK16 * 32, TK16 == 8 ? 2 : EGOT2_ATTN_MINB) at
 
 inline int drop_mode(float p) { return p <= 0.f ? 0 : (p == 0.5f ? 1 : 2); }
 
-template <int DH, int TK16>
-int launch_fwd(int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p, uint64_t key, cudaStream_t st) {
-  constexpr size_t smem = (size_t)3 * TK16 * 16 * Tile<DH>::LD * 2;
+// MEASURED (B200, B 256): carrying several heads per CTA is SLOWER - T 48 / 8 heads of 16: forward 20.0 vs 13.0 us, backward
+// 35.5 vs 24.8 with 4 heads per CTA; T 90 / 4 heads of 32: 13.4 vs 11.9 and 32.6 vs 28.6 with 2 - the many small CTAs hide
+// the staging round trip better than fewer large ones do.  So one head per CTA it stays; the HPC parameter is kept (set
+// hpc_max to try again) but nothing above 1 is instantiated.
+template <int DH, int TK16> constexpr int hpc_max() { return 1; }
+
+template <int DH, int TK16, int HPC>
+int launch_fwd_h(int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p, uint64_t key, cudaStream_t st) {
+  constexpr size_t smem = (size_t)HPC * 3 * TK16 * 16 * Tile<DH>::LD * 2;
   typedef void (*Kern)(int, int, int, const bf16*, bf16*, float*, float, uint64_t);
-  static const Kern kerns[3] = {attn_mma_fwd_kernel<DH, TK16, 0>, attn_mma_fwd_kernel<DH, TK16, 1>, attn_mma_fwd_kernel<DH, TK16, 2>};
+  static const Kern kerns[3] = {attn_mma_fwd_kernel<DH, TK16, 0, HPC>, attn_mma_fwd_kernel<DH, TK16, 1, HPC>, attn_mma_fwd_kernel<DH, TK16, 2, HPC>};
   static bool set = false;
   if (!set) {
     for (int i = 0; i < 3; ++i) EGOT2_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set = true;
   }
-  ProfScope prof(st, "attn_mma_fwd<dh%d,tk%d> B%d T%d H%d", DH, TK16 * 16, B, T, H);
-  launch(kerns[drop_mode(p)], dim3(B * heads), dim3(TK16 * 32), smem, st, T, H, heads, (const bf16*)qkv, (bf16*)out, lse, p, key);
+  ProfScope prof(st, "attn_mma_fwd<dh%d,tk%d,hpc%d> B%d T%d H%d", DH, TK16 * 16, HPC, B, T, H);
+  launch(kerns[drop_mode(p)], dim3(B * heads / HPC), dim3(TK16 * 32 * HPC), smem, st, T, H, heads, (const bf16*)qkv, (bf16*)out, lse, p, key);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+inline bool hpc_off() { const char* e = getenv("EGOT2_ATTN_HPC"); return e && e[0] == '1' && e[1] == 0; }
+template <int DH, int TK16>
+int launch_fwd(int B, int T, int H, int heads, const void* qkv, void* out, float* lse, float p, uint64_t key, cudaStream_t st) {
+  constexpr int M = hpc_max<DH, TK16>();
+  if (!hpc_off()) {
+    if constexpr (M >= 4) if (heads % 4 == 0) return launch_fwd_h<DH, TK16, 4>(B, T, H, heads, qkv, out, lse, p, key, st);
+    if constexpr (M >= 2) if (heads % 2 == 0) return launch_fwd_h<DH, TK16, 2>(B, T, H, heads, qkv, out, lse, p, key, st);
+  }
+  return launch_fwd_h<DH, TK16, 1>(B, T, H, heads, qkv, out, lse, p, key, st);
+}
+template <int DH, int TK16, int HPC>
+int launch_bwd_h(int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse, const void* dout,
+                 void* dqkv, float p, uint64_t key, cudaStream_t st) {
+  constexpr size_t smem = (size_t)HPC * ((size_t)4 * TK16 * 16 * Tile<DH>::LD * 2 + 2 * TK16 * 16 * 4);
+  typedef void (*Kern)(int, int, int, const bf16*, const bf16*, const float*, const bf16*, bf16*, float, uint64_t);
+  static const Kern kerns[3] = {attn_mma_bwd_kernel<DH, TK16, 0, HPC>, attn_mma_bwd_kernel<DH, TK16, 1, HPC>, attn_mma_bwd_kernel<DH, TK16, 2, HPC>};
+  static bool set = false;
+  if (!set) {
+    for (int i = 0; i < 3; ++i) EGOT2_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = true;
+  }
+  ProfScope prof(st, "attn_mma_bwd<dh%d,tk%d,hpc%d> B%d T%d H%d", DH, TK16 * 16, HPC, B, T, H);
+  launch(kerns[drop_mode(p)], dim3(B * heads / HPC), dim3(TK16 * 32 * HPC), smem, st, T, H, heads, (const bf16*)qkv, (const bf16*)out, lse,
+         (const bf16*)dout, (bf16*)dqkv, p, key);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }
 template <int DH, int TK16>
 int launch_bwd(int B, int T, int H, int heads, const void* qkv, const void* out, const float* lse, const void* dout,
                void* dqkv, float p, uint64_t key, cudaStream_t st) {
-  constexpr size_t smem = (size_t)4 * TK16 * 16 * Tile<DH>::LD * 2 + 2 * TK16 * 16 * 4;
-  typedef void (*Kern)(int, int, int, const bf16*, const bf16*, const float*, const bf16*, bf16*, float, uint64_t);
-  static const Kern kerns[3] = {attn_mma_bwd_kernel<DH, TK16, 0>, attn_mma_bwd_kernel<DH, TK16, 1>, attn_mma_bwd_kernel<DH, TK16, 2>};
-  static bool set = false;
-  if (!set) {
-    for (int i = 0; i < 3; ++i) EGOT2_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set = true;
+  constexpr int M = hpc_max<DH, TK16>();
+  if (!hpc_off()) {
+    if constexpr (M >= 4) if (heads % 4 == 0) return launch_bwd_h<DH, TK16, 4>(B, T, H, heads, qkv, out, lse, dout, dqkv, p, key, st);
+    if constexpr (M >= 2) if (heads % 2 == 0) return launch_bwd_h<DH, TK16, 2>(B, T, H, heads, qkv, out, lse, dout, dqkv, p, key, st);
   }
-  ProfScope prof(st, "attn_mma_bwd<dh%d,tk%d> B%d T%d H%d", DH, TK16 * 16, B, T, H);
-  launch(kerns[drop_mode(p)], dim3(B * heads), dim3(TK16 * 32), smem, st, T, H, heads, (const bf16*)qkv, (const bf16*)out, lse,
-         (const bf16*)dout, (bf16*)dqkv, p, key);
-  EGOT2_LAUNCH_CHECK();
-  return 0;
+  return launch_bwd_h<DH, TK16, 1>(B, T, H, heads, qkv, out, lse, dout, dqkv, p, key, st);
 }
 
 inline int pick_tk16(int T) { return T <= 16 ? 1 : (T <= 32 ? 2 : (T <= 64 ? 4 : (T <= 96 ? 6 : 8))); }
