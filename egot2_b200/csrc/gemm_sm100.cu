@@ -25,7 +25,16 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements = one 128-byte swizzle row
-constexpr int NTHREADS = 192;
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2.. epilogue: EPG column groups x 4 TMEM lane quadrants.  EPG = 2 (8 epilogue
+// warps, each thread one accumulator row x half of the tile's columns) was tried because most GEMMs of the translators are one
+// or two tiles per CTA, i.e. the serial chain load -> MMA -> epilogue -> store IS the kernel - and MEASURED SLOWER on every
+// workload (B200, us per step, EPG 2 vs 1: HHI 372 vs 343, PNR 1071 vs 1003, LTA 1730 vs 1628): 320 threads x 2 CTAs per SM cap
+// the kernel at 96 registers and the epilogue spills.  So 4 epilogue warps it stays.
+#ifndef EGOT2_GEMM_EPG
+#define EGOT2_GEMM_EPG 1
+#endif
+constexpr int EPG = EGOT2_GEMM_EPG;
+constexpr int NTHREADS = 64 + 128 * EPG;
 
 struct EpiArgs {
   int M, N;
@@ -136,7 +145,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     tma_prefetch_desc(&tma_b);
     if (e.tma_store) tma_prefetch_desc(&tma_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 4 * EPG); }
     fence_barrier_init();
   }
   // split-K CTAs own exactly one tile: a single accumulator (BN columns) - the double buffer would only keep other
@@ -224,6 +233,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     // a 128-bit vector, the one large auxiliary operand (ReLU gate or residual) is fetched while the TMEM load is
     // in flight, and there is no per-element control flow.  Edge chunks take the scalar path.
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int c_lo = ((warp - 2) >> 2) * (BN / EPG), c_hi = c_lo + BN / EPG;      // this warp's columns of every tile
     const float inv_keep = e.p_drop > 0.f ? 1.f / (1.f - e.p_drop) : 1.f;
     const bool first_split = blockIdx.z == 0;
     const float* bias = first_split ? e.bias : nullptr;
@@ -248,7 +258,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       // chunk ahead: its global-load latency hides behind the MMAs / the previous chunk instead of in front of each chunk
       float aux[32], aux_next[32];
       const bool aux_vec = row_ok && vec_ok && aux_row != nullptr;
-      if (aux_vec && n0 + 32 <= e.N) load32(aux_row + n0, aux_next);
+      if (aux_vec && n0 + c_lo + 32 <= e.N) load32(aux_row + n0 + c_lo, aux_next);
       if (e.tma_store && lt > 0) {              // the previous tile's TMA store has finished reading the staged tile
         if (warp == 2 && lane == 0) tma_store_wait_read();
         named_bar_sync(3, NTHREADS - 64);
@@ -256,7 +266,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       mbar_wait(tmem_full + 8 * buf, (lt >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
         const int nb = n0 + c0;
@@ -264,9 +274,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const bool fast = active && vec_ok && (nb + 32 <= e.N);
 #pragma unroll
         for (int j = 0; j < 32; ++j) aux[j] = aux_next[j];
-        if (aux_vec && c0 + 32 < BN && nb + 64 <= e.N) load32(aux_row + nb + 32, aux_next);
+        if (aux_vec && c0 + 32 < c_hi && nb + 64 <= e.N) load32(aux_row + nb + 32, aux_next);
         tmem_ld_wait();
-        if (c0 + 32 >= BN) {                    // the whole accumulator of this tile is in registers: release the buffer
+        if (c0 + 32 >= c_hi) {                  // this warp's part of the accumulator is in registers: release the buffer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
