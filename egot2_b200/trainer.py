@@ -251,7 +251,19 @@ class HoiPromptTranslatorTrainer(_PromptStepGraphs):
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.peer = _make_peer_exchange(self.engine, process_group, self.world)
-        self._init_step_graphs()           # eager launches unless EGOT2_G_GRAPH=1; _grad_clean: True after a fused AdamW
+        self._init_step_graphs()           # one CUDA graph per step unless EGOT2_G_GRAPH=0; _grad_clean: True after a fused AdamW
+        # the three forward/backward passes of a step side by side (see PromptTranslatorTrainer._fwd_bwd_all): passes 2 and 3 get
+        # engines (workspaces, saved activations), streams and gradient arenas of their own; one arena of parameters
+        self.engines = [self.engine]
+        self._branch_streams = self._branch_grads = None
+        if os.environ.get("EGOT2_G_STREAMS", "1") != "0" and self.device.type == "cuda":
+            pe = PositionalEncoding(hidden, max_len=200).pe
+            for _ in range(2):
+                e = TranslatorEngine(self.spec, self.device, dtype, arena=self.engine.arena)
+                e.set_sinusoid(pe)
+                self.engines.append(e)
+            self._branch_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            self._branch_grads = [torch.zeros_like(self.engine.arena.grad) for _ in range(2)]
         self._h2d: Dict[int, List[torch.Tensor]] = {}
         self.copy_stream = None if self.device.type != "cuda" else torch.cuda.Stream(device=self.device)
         self.loss_kind, self.class_weight = L.LOSS_CE, None
@@ -261,15 +273,32 @@ class HoiPromptTranslatorTrainer(_PromptStepGraphs):
 
     def _fwd_bwd_all(self, feats, labels, seed0: int):
         """The three forward/backward passes into a clean gradient arena (the graph-captured body)."""
-        off, total = 0, None
+        import contextlib
+        par = self._branch_streams is not None
+        cur = torch.cuda.current_stream(self.device) if par else None
+        off, total, losses = 0, None, []
         for i, ratio in enumerate(self.ratios):
             group = list(feats[4 * i:4 * i + 4])
             tgt = labels[off:off + group[0].shape[0]]
             off += group[0].shape[0]
-            act = self.engine.forward(group, training=True, seed=seed0 + i, labels=tgt[:, 1:], loss=L.LOSS_CE,
-                                      persistent=True, prompt=tgt[:, :-1])
-            self.engine.backward(act, dloss_scale=float(ratio), zero_grad=False)
-            l = act.t["loss"][0] * ratio
+            side = par and i > 0
+            eng = self.engines[i] if par else self.engine
+            if side:
+                self._branch_streams[i - 1].wait_stream(cur)
+            with (torch.cuda.stream(self._branch_streams[i - 1]) if side else contextlib.nullcontext()):
+                act = eng.forward(group, training=True, seed=seed0 + i, labels=tgt[:, 1:], loss=L.LOSS_CE,
+                                  persistent=True, prompt=tgt[:, :-1])
+                eng.backward(act, dloss_scale=float(ratio), zero_grad=False, grad=self._branch_grads[i - 1] if side else None)
+            losses.append((act.t["loss"], ratio))
+        if par:
+            for st in self._branch_streams:
+                cur.wait_stream(st)
+            g = self.engine.arena.grad
+            with _dev_guard(self.device):
+                L.call("egot2_sum_into_f32", g.data_ptr(), self._branch_grads[0].data_ptr(), self._branch_grads[1].data_ptr(),
+                       g.numel(), _cur_stream(self.device))
+        for lt, ratio in losses:
+            l = lt[0] * ratio
             total = l if total is None else total + l
         return total
 
