@@ -47,10 +47,11 @@ def test_struct_layouts_match_header(built):
              "egot2_decoder_desc": _lib.DecoderDesc, "egot2_decoder_params": _lib.DecoderParams,
              "egot2_decoder_grads": _lib.DecoderGrads, "egot2_decoder_saved": _lib.DecoderSaved,
              "egot2_vit_desc": _lib.VitDesc, "egot2_vit_params": _lib.VitParams, "egot2_vit_grads": _lib.VitGrads,
-             "egot2_vit_saved": _lib.VitSaved}
+             "egot2_vit_saved": _lib.VitSaved, "egot2_dp_desc": _lib.DpDesc}
     # (struct, field) pairs whose byte offsets are compared as well: the last fields of the descriptors that grew
     offsets = [("egot2_embed_desc", "seed"), ("egot2_embed_desc", "no_ln"), ("egot2_embed_desc", "feat_drop_tokens"), ("egot2_vit_desc", "ln_eps"),
-               ("egot2_vit_saved", "act"), ("egot2_decoder_desc", "seed"), ("egot2_head_desc", "seed")]
+               ("egot2_vit_saved", "act"), ("egot2_decoder_desc", "seed"), ("egot2_head_desc", "seed"),
+               ("egot2_dp_desc", "off_flags"), ("egot2_dp_desc", "exp_avg"), ("egot2_dp_desc", "step_dev"), ("egot2_dp_desc", "zero_grads_remote")]
     prog = '#include <stdio.h>\n#include <stddef.h>\n#include "egot2.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "".join(
         f'printf("{n}.{f} %zu\\n", offsetof({n}, {f}));' for n, f in offsets) + "return 0;}"

@@ -128,3 +128,24 @@ def test_two_piece_overlapped_allreduce_equals_single_bucket():
     assert torch.equal(two_piece, whole)                  # the two slices tile the arena exactly; same sums
     expect = sum(torch.randn(numel, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
     assert torch.allclose(whole, expect, rtol=0, atol=1e-6)
+
+
+def test_peer_slab_layout_is_aligned_and_disjoint():
+    """parallel.slab_layout: the byte offsets every rank derives for its IPC slab (parameters | gradients | bf16 shadow | flag
+    words) from the arena size alone - 256-byte aligned, non-overlapping, identical for identical arenas (csrc/peer.cu relies on it)."""
+    from egot2_b200.parallel import slab_layout
+    for numel in (64, 692928, 28137600):
+        for shadow in (True, False):
+            p, g, s, f, total = slab_layout(numel, shadow, 256)
+            assert p == 0 and g >= p + 4 * numel and f % 256 == 0 and g % 256 == 0 and total == f + 256
+            if shadow:
+                assert s >= g + 4 * numel and s % 256 == 0 and f >= s + 2 * numel
+            else:
+                assert s == -1 and f >= g + 4 * numel
+            assert slab_layout(numel, shadow, 256) == (p, g, s, f, total)
+
+
+def test_bind_to_gpu_numa_is_best_effort():
+    """No CUDA device here: the binding must decline quietly, never raise."""
+    from egot2_b200.parallel import bind_to_gpu_numa
+    assert bind_to_gpu_numa(0) is None or isinstance(bind_to_gpu_numa(0), tuple)
