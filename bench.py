@@ -481,6 +481,22 @@ def main():
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / (float(ms2.item()) * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0][0]) + host[0][1].numel() * 8
+    # what the box's host -> device path allows: the same pinned buffers copied back to back, nothing else running
+    # (the e2e step cannot be faster than this copy; on a shared VM it varies from box to box)
+    devb = [torch.empty_like(t, device=dev) for t in host[0][0]]
+    for _ in range(3):
+        for d_, t in zip(devb, host[0][0]):
+            d_.copy_(t, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(20):
+        for d_, t in zip(devb, host[0][0]):
+            d_.copy_(t, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    h2d_ms = e0.elapsed_time(e1) / 20
+    h2d_gbs = sum(t.numel() * t.element_size() for t in host[0][0]) / (h2d_ms * 1e-3) / 1e9
+    del devb
 
     # ---- the other BASELINE.json configurations at this GPU count (every rank takes part: they all-reduce too)
     others = []
@@ -542,7 +558,8 @@ def main():
                       "note": "same step, timed region >= 0.5 s"},
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                "steps": e2e_steps},
+                "steps": e2e_steps, "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_gbs": h2d_gbs,
+                "h2d_bound_clips_per_s": world * B / (h2d_ms * 1e-3)},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roof,
