@@ -2,7 +2,7 @@
 unchanged, the C-ABI calls they issue are served by tests/abi_emulator.py (oracle ops behind the real descriptor structs
 and pointers).  A wrong parameter-to-field mapping, segment offset, token-table run, decoder memory mapping or buffer
 chain shows up here as a golden mismatch before the case reaches hardware.  Cases whose GPU parity is green validate the
-emulator's reading of the ABI; for the cases in oracle.cases.UNVALIDATED_ON_GPU this is the strongest check available
+emulator's reading of the ABI; for a case whose GPU parity has not run yet (oracle.cases.UNVALIDATED_ON_GPU, empty since round 2) this is the strongest check available
 without a GPU (the kernels themselves are only exercised by the `-m gpu` tests)."""
 import os
 import warnings
