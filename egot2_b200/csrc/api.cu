@@ -124,6 +124,7 @@ int gemm(const GemmArgs& a, cudaStream_t st) {
     if (rc >= 0) { if (rc == 0) g_gemm_impl = "tcgen05"; return rc; }
   }
   g_gemm_impl = "simt";
+  EGOT2_CHECK(a.ln_g == nullptr, "gemm: a fused LayerNorm was requested but the tcgen05 kernel did not take the problem");
   if (a.split_stride > 0) {      // the CUDA-core GEMM has no split-K: one split, written to slab 0
     GemmArgs b = a;
     b.split_k = 1; b.split_stride = 0;
@@ -505,6 +506,12 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   cudaStream_t side_st[2] = {st, st};
   for (int i = 0; i < 2 && i + 1 < d->n_seg; ++i)
     if (sides[i]) { side_st[i] = side_fork(st, sides[i], 0); used[i] = side_st[i] != st; }
+  // LayerNorm + token table (+ embedding dropout) inside the projection GEMMs' epilogue (H = 128: a tile holds whole rows):
+  // possible when nothing sits between projection and LayerNorm (no feature dropout in this call) and every segment is projected
+  bool ln_fused = !splitk && !d->no_ln && d->dtype == EGOT2_BF16 && d->feat_dtype == EGOT2_BF16 && d->H == 128 &&
+                  !(d->training && d->p_feat > 0.f) && gemm_impl_mode() == 0 && env_is("EGOT2_GEMM_LN", "1");
+  for (int k = 0; k < d->n_seg && ln_fused; ++k)
+    if (d->seg_tokens[k] > 0 && (!d->seg_has_proj[k] || d->seg_in_dim[k] % 8 != 0)) ln_fused = false;
   for (int k = 0; k < d->n_seg; ++k) {
     const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
     if (Dk == 0) continue;
@@ -536,6 +543,16 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
         src.slab[k] = zf; src.splits[k] = used;
         zf += (size_t)embed_seg_splits(d, k) * d->B * Dk * d->H;
       } else {
+        if (ln_fused) {
+          g.ln_g = in->ln_g; g.ln_b = in->ln_b; g.ln_eps = d->ln_eps;
+          g.ln_out = (char*)out->x + (size_t)d->seg_offset[k] * d->H * es; g.ln_stat = out->stat;
+          g.ln_table = in->tok_table; g.ln_table_rows = d->T; g.ln_row0 = d->seg_offset[k];
+          if (d->training && d->p_embed > 0.f) { g.ln_p_drop = d->p_embed; g.ln_drop_key = site_key(d->seed, SITE_EMBED, 0); }
+          if (!gemm_sm100_ln_ok(g)) {        // e.g. an unaligned feature tensor: this segment cannot fuse, so none does
+            ln_fused = false;                // the separate LayerNorm pass below then covers ALL rows (also those already fused)
+            g.ln_g = nullptr; g.ln_b = nullptr; g.ln_out = nullptr; g.ln_stat = nullptr; g.ln_table = nullptr; g.ln_p_drop = 0.f;
+          }
+        }
         EGOT2_TRY(gemm(g, sk));
       }
     } else {
@@ -559,6 +576,7 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
       EGOT2_TRY(dropout_inplace(d->dtype, out->z, n, d->p_feat, site_key(d->seed, SITE_FEAT, 0), st));
   }
   if (d->no_ln) return add_table(d->dtype, n, (size_t)d->T * d->H, out->z, in->tok_table, out->x, st);
+  if (ln_fused) return 0;                 // x and stat came out of the projection GEMMs
   LayerNormArgs l;
   l.rows = d->B * d->T; l.H = d->H; l.dtype = d->dtype; l.x = out->z; l.g = in->ln_g; l.b = in->ln_b; l.eps = d->ln_eps;
   l.y = out->x; l.stat = out->stat; l.table = in->tok_table; l.table_rows = d->T;
@@ -736,6 +754,7 @@ extern "C" int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_la
   if (M == 0) return 0;
   const float pd = d->training ? d->p_drop : 0.f;
   const uint32_t L = (uint32_t)d->layer_index;
+  bool ln1_fused = false;
   // 1. packed in-projection: qkv = x . Win^T + bin
   {
     GemmArgs g; g.M = M; g.N = 3 * H; g.K = H; g.A = x_in; g.lda = H; g.B = p->in_proj_w; g.ldb = H; g.trans_b = 1;
@@ -749,10 +768,14 @@ extern "C" int egot2_encoder_layer_fwd(const egot2_layer_desc* d, const egot2_la
     GemmArgs g; g.M = M; g.N = H; g.K = H; g.A = s->attn; g.lda = H; g.B = p->out_proj_w; g.ldb = H; g.trans_b = 1;
     g.C = s->y1; g.ldc = H; g.bias = p->out_proj_b; g.residual = x_in; g.ldr = H;
     g.p_drop = pd; g.drop_key = site_key(d->seed, SITE_DROP1, L); g.in_dtype = d->dtype; g.out_dtype = d->dtype;
+    // 4. x1 = norm1(y1) inside the same epilogue when a tile holds whole rows (H = 128)
+    g.ln_g = p->norm1_g; g.ln_b = p->norm1_b; g.ln_eps = d->ln_eps; g.ln_out = s->x1; g.ln_stat = s->stat1;
+    ln1_fused = d->dtype == EGOT2_BF16 && gemm_sm100_ln_ok(g) && !env_is("EGOT2_GEMM", "simt");
+    if (!ln1_fused) { g.ln_g = nullptr; g.ln_b = nullptr; g.ln_out = nullptr; g.ln_stat = nullptr; }
     EGOT2_TRY(gemm(g, st));
   }
   // 4. x1 = norm1(y1)
-  {
+  if (!ln1_fused) {
     LayerNormArgs l; l.rows = M; l.H = H; l.dtype = d->dtype; l.x = s->y1; l.g = p->norm1_g; l.b = p->norm1_b;
     l.eps = d->ln_eps; l.y = s->x1; l.stat = s->stat1;
     EGOT2_TRY(layernorm_fwd(l, st));

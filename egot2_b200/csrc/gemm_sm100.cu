@@ -48,6 +48,11 @@ struct EpiArgs {
   int tma_store;     // bf16 C, plain rows: the tile leaves through shared memory + TMA (coalesced) instead of per-row stores
   // grouped-K addressing for gathered MN-major operands (3-D tensor maps): 64-row k-block = kg groups x kdpad rows
   int k_grouped, kg, kdblocks;
+  // LayerNorm fused behind the epilogue (BN = N = 128, bf16 C): ln_out[row] = LN(C[row]) * g + b (+ table[row % table_rows])
+  // (* dropout); the row statistics go to ln_stat.  Row indices of stat / table / dropout are (storage row of C) + ln_row0.
+  const float* ln_g; const float* ln_b; float ln_eps;
+  void* ln_out; float* ln_stat; const float* ln_table; int ln_table_rows; int ln_row0;
+  float ln_p_drop; uint64_t ln_drop_key;
 };
 
 __device__ __forceinline__ long long remap(int r, int rpg, int gstride) {
@@ -265,6 +270,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
       mbar_wait(tmem_full + 8 * buf, (lt >> 1) & 1);
       tc_fence_after();
+      float ln_sum = 0.f, ln_sq = 0.f;
 #pragma unroll 1
       for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         uint32_t r[32];
@@ -324,8 +330,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                 store32(dst, v);
               }
             }
-          } else if (BN <= 128 && sizeof(TO) == 2 && e.tma_store) {
-            // this thread's 32 columns = 4 x 16 B chunks of its 128 B swizzle row in the staged tile
+          } else if (BN <= 128 && sizeof(TO) == 2 && (e.tma_store || e.ln_g)) {
+            // this thread's 32 columns = 4 x 16 B chunks of its 128 B swizzle row in the staged tile (with a fused
+            // LayerNorm the staged row is also where its second pass reads the rounded values back from)
             const int r = q * 32 + lane;
             const uint32_t srow = sOut + (uint32_t)(c0 >> 6) * 16384u + (uint32_t)r * 128u;
 #pragma unroll
@@ -335,9 +342,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
               for (int k = 0; k < 4; ++k) {
                 __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
                 w[k] = *reinterpret_cast<uint32_t*>(&t);
+                if (e.ln_g) {          // row statistics on the ROUNDED values: what a separate LayerNorm kernel would read
+                  const float y0 = __uint_as_float(w[k] << 16), y1 = __uint_as_float(w[k] & 0xffff0000u);
+                  ln_sum += y0 + y1;
+                  ln_sq = fmaf(y0, y0, fmaf(y1, y1, ln_sq));
+                }
               }
               sts128(srow + (uint32_t)(((((c0 & 63) >> 3) + j) ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
             }
+            if (!e.tma_store) store32(crow_ptr + nb, v);      // scattered rows (embedding segments): C goes straight to global
           } else {
             store32(crow_ptr + nb, v);
           }
@@ -359,6 +372,54 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
               }
             } else {
               crow_ptr[n] = from_f32<TO>(x);
+            }
+          }
+        }
+      }
+      if constexpr (BN == 128 && sizeof(TO) == 2) {
+        if (e.ln_g && row_ok) {
+          // fused LayerNorm, second pass: this thread's row is in the staged tile (it wrote it itself: no barrier)
+          const float mean = ln_sum * (1.f / 128.f);
+          const float rstd = rsqrtf(fmaxf(ln_sq * (1.f / 128.f) - mean * mean, 0.f) + e.ln_eps);
+          const long long lrow = crow + e.ln_row0;
+          if (e.ln_stat) { e.ln_stat[2 * lrow] = mean; e.ln_stat[2 * lrow + 1] = rstd; }
+          bf16* orow = (bf16*)e.ln_out + crow * e.ldc;
+          const float* trow = e.ln_table ? e.ln_table + (lrow % e.ln_table_rows) * 128 : nullptr;
+          const float ln_keep = e.ln_p_drop > 0.f ? 1.f / (1.f - e.ln_p_drop) : 1.f;
+          const int r = q * 32 + lane;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            const uint32_t srow = sOut + (uint32_t)(c0 >> 6) * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                           : "r"(srow + (uint32_t)(((((c0 & 63) >> 3) + j) ^ (r & 7)) << 4)));
+              const uint32_t w[4] = {w0, w1, w2, w3};
+              const int c = c0 + 8 * j;
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.ln_g + c)), g1 = __ldg(reinterpret_cast<const float4*>(e.ln_g + c + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.ln_b + c)), b1 = __ldg(reinterpret_cast<const float4*>(e.ln_b + c + 4));
+              const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                o[2 * k] = (__uint_as_float(w[k] << 16) - mean) * rstd * gg[2 * k] + bb[2 * k];
+                o[2 * k + 1] = (__uint_as_float(w[k] & 0xffff0000u) - mean) * rstd * gg[2 * k + 1] + bb[2 * k + 1];
+              }
+              if (trow) {
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(trow + c)), t1 = __ldg(reinterpret_cast<const float4*>(trow + c + 4));
+                o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w; o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
+              }
+              if (e.ln_p_drop > 0.f) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] *= drop_scale(e.ln_drop_key ^ egot2_ep, (uint64_t)lrow * 128 + c + k, e.ln_p_drop, ln_keep);
+              }
+              uint4 pk;
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(orow + c) = pk;
             }
           }
         }
@@ -452,6 +513,8 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   e.bias = a.bias; e.relu = a.relu; e.mask = a.mask; e.ldm = a.ldm; e.mask_scale = a.mask_scale;
   e.p_drop = a.p_drop; e.drop_key = a.drop_key; e.drop_bit_mode = a.drop_bit_mode; e.residual = a.residual; e.ldr = a.ldr;
   e.accumulate = a.accumulate; e.atomic = a.split_k > 1;
+  e.ln_g = a.ln_g; e.ln_b = a.ln_b; e.ln_eps = a.ln_eps; e.ln_out = a.ln_out; e.ln_stat = a.ln_stat; e.ln_table = a.ln_table;
+  e.ln_table_rows = a.ln_table_rows > 0 ? a.ln_table_rows : 1; e.ln_row0 = a.ln_row0; e.ln_p_drop = a.ln_p_drop; e.ln_drop_key = a.ln_drop_key;
   e.k_grouped = kg.on; e.kg = kg.g; e.kdblocks = kg.dblocks;
   // TMA-store epilogue: bf16 output in plain row order, whole 32-column chunks, every per-row operand 16 B aligned (the
   // vector path then never falls back to direct stores that would race with the tile store)
@@ -514,9 +577,22 @@ bool host_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15
 
 }  // namespace
 
+// Can the LayerNorm behind this GEMM run inside its epilogue?  One 128-column tile holds whole rows (N = 128), bf16 in and out,
+// plain (non-accumulating, single-split) output with vector-aligned rows, no ReLU gate operand.
+bool gemm_sm100_ln_ok(const GemmArgs& a) {
+  // Opt-in (EGOT2_GEMM_LN=1): measured on B200 the fused tail costs ~1 % of the step (352.0 vs 347.6 us HHI, 1033 vs 1022 us PNR,
+  // profiles/r02_ln_epilogue.txt) - the 60-CTA GEMM grid normalises its rows more slowly than the 960-CTA LayerNorm kernel it replaces.
+  if (!(getenv("EGOT2_GEMM_LN") && getenv("EGOT2_GEMM_LN")[0] == '1')) return false;
+  return a.in_dtype == EGOT2_BF16 && a.out_dtype == EGOT2_BF16 && a.N == 128 && a.K >= 16 && !a.accumulate && a.split_k <= 1 &&
+         a.split_stride == 0 && !a.mask && !a.trans_a && a.a_rpg == 0 && a.b_rpg == 0 && a.ldc == 128 && host_al16(a.C) &&
+         host_al16(a.A) && host_al16(a.B) && a.lda % 8 == 0 && a.ldb % 8 == 0 && (!a.residual || (host_al16(a.residual) && a.ldr % 8 == 0)) &&
+         (a.c_rpg == 0 || (a.c_rpg * 128 * 2) % 16 == 0);
+}
+
 // returns -1 when this kernel does not take the problem (caller falls back to the CUDA-core GEMM)
 int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
   if (a.in_dtype != EGOT2_BF16) return -1;
+  if (a.ln_g && !gemm_sm100_ln_ok(a)) return -2;            // the caller asked for a fusion this kernel cannot do: a bug upstream
   KGroup kg;
   if (a.a_rpg > 0 || a.b_rpg > 0) {
     // gathered token rows are supported for the weight-gradient orientation (both operands MN-major, K = tokens)

@@ -31,7 +31,13 @@ struct GemmArgs {
   // of splits actually launched (<= split_k) is returned through *splits_out
   long long split_stride = 0;
   int* splits_out = nullptr;
+  // LayerNorm fused behind the epilogue (tcgen05 path only, see gemm_sm100_ln_ok): ln_out[row] = LN(C[row]) * ln_g + ln_b
+  // (+ ln_table[(row + ln_row0) % ln_table_rows]) (* dropout(ln_p_drop)); statistics to ln_stat[row + ln_row0]; rows = C's storage rows
+  const float* ln_g = nullptr; const float* ln_b = nullptr; float ln_eps = 1e-5f;
+  void* ln_out = nullptr; float* ln_stat = nullptr; const float* ln_table = nullptr; int ln_table_rows = 0; int ln_row0 = 0;
+  float ln_p_drop = 0.f; uint64_t ln_drop_key = 0;
 };
+bool gemm_sm100_ln_ok(const GemmArgs& a);
 int gemm(const GemmArgs& a, cudaStream_t st);          // dispatch: tcgen05 (bf16, supported shapes) or CUDA-core
 int gemm_simt(const GemmArgs& a, cudaStream_t st);     // gemm_simt.cu
 int gemm_sm100(const GemmArgs& a, cudaStream_t st);    // gemm_sm100.cu; returns -1 if the shape is not handled

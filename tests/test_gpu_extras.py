@@ -185,6 +185,46 @@ def test_benchmark_shape_matches_oracle(dtype):
         assert err_l2 <= bound, f"{k}: rel L2 err {err_l2:.3e} > {bound:.3e}"
 
 
+@pytest.mark.parametrize("name", ["hhi3_h128_d30", "hoi_pnr_h128_l6", "hoi_ar_h128_l3"])
+def test_layernorm_in_gemm_epilogue_matches_separate_kernel(name, monkeypatch):
+    """EGOT2_GEMM_LN=1 (opt-in, see gemm_sm100_ln_ok) normalises the rows of the embedding projections and of the attention
+    out-projection inside the tcgen05 GEMM's epilogue instead of in a LayerNorm kernel of its own.  Both read the same
+    bf16-rounded pre-norm rows, so output, loss and gradients must agree to bf16 rounding of the normalised rows."""
+    import torch
+
+    import test_gpu_parity as tg
+    from egot2_b200 import _lib as L
+    from egot2_b200.engine import TranslatorEngine
+    from oracle import translator_oracle as O
+    from oracle.cases import CASES, case_inputs
+    case = next(c for c in CASES if c.name == name)
+    sd, feats, labels, extra = case_inputs(case)
+    res = {}
+    loss_kind, cw = tg._loss_kind(case)
+    for mode in ("0", "1"):
+        monkeypatch.setenv("EGOT2_GEMM_LN", mode)
+        eng = TranslatorEngine(case.spec, "cuda:0", "bf16")
+        eng.arena.load_state_dict(sd)
+        eng.set_sinusoid(O.sinusoid_table(1000, case.spec.hidden))
+        gf = tg._engine_feats(case, eng, feats, extra, "bf16")
+        L.prof_enable(True)
+        try:
+            act = eng.forward(gf, training=False, labels=labels, loss=loss_kind, class_weight=cw)
+            torch.cuda.synchronize()
+            n_ln = sum(1 for r in L.prof_report() if r[0].startswith("ln_fwd"))
+        finally:
+            L.prof_enable(False)
+        grad, _ = eng.backward(act)
+        torch.cuda.synchronize()
+        res[mode] = (act.t["out"].float().cpu(), float(act.t["loss"][0]), grad.float().cpu().clone(), n_ln)
+    (o0, l0, g0, n0), (o1, l1, g1, n1) = res["0"], res["1"]
+    assert n1 < n0, f"the fused path did not replace any LayerNorm launch ({n0} -> {n1})"
+    scale = float(o0.abs().max())
+    assert float((o0 - o1).abs().max()) <= 2e-2 * scale
+    assert abs(l0 - l1) <= 2e-2 * abs(l0)
+    assert float((g0 - g1).norm()) <= 5e-2 * float(g0.norm())
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("name,which", [("hhi3_h128_l1", "ttm"), ("hoi_lta_h512_l4", "action"), ("hoi_lta_h512_l4", "lta")])
 def test_feature_gradients_of_trainable_backbones(name, which, dtype):
