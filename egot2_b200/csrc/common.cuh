@@ -202,13 +202,22 @@ __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   const float t = p * 4294967296.0f;
   return t >= 4294967040.0f ? 0xFFFFFF00u : (uint32_t)(t + 0.5f);
 }
-// Bernoulli(1-p) keep decision for element idx: drop_bits(key, idx) >= p * 2^32.
-// bit_mode (FFN hidden-activation site only, and only for p == 0.5, the HHI default): ONE random bit per element - bit
-// idx%32 of the hash of idx/32 - so a kernel that owns 32 consecutive elements pays one hash per 32 elements instead of
-// one per element; that is what keeps the fused FFN epilogue off the critical path in training.
+// Bernoulli(1-p) keep decision for element idx.
+//   p == 0.5 (the HHI / HOI encoder default): ONE random bit per element - bit idx%32 of the hash of idx/32 - at EVERY
+//   elementwise dropout site, so a thread that owns an aligned run of elements pays one hash per run (drop_scale_n below)
+//   instead of one per element: the per-element hash was the larger half of the out-projection epilogue and of the
+//   LayerNorm-backward / FFN final epilogues in training.
+//   other p: drop_bits(key, idx) >= p * 2^32, one hash per element.
+// (bit_mode is kept for source compatibility; the p == 0.5 rule no longer depends on it.)
 __host__ __device__ __forceinline__ bool drop_keep(uint64_t key, uint64_t idx, float p, uint32_t thr, bool bit_mode = false) {
-  if (bit_mode && p == 0.5f) return (drop_bits(key, idx >> 5) >> (uint32_t)(idx & 31)) & 1u;
+  (void)bit_mode;
+  if (p == 0.5f) return (drop_bits(key, idx >> 5) >> (uint32_t)(idx & 31)) & 1u;
   return drop_bits(key, idx) >= thr;
+}
+// keep bits of the aligned word that holds element idx (p == 0.5 rule), shifted so that bit i belongs to element idx + i;
+// valid for the elements up to the next multiple of 32
+__host__ __device__ __forceinline__ uint32_t drop_word(uint64_t key, uint64_t idx) {
+  return drop_bits(key, idx >> 5) >> (uint32_t)(idx & 31);
 }
 // Attention-probability dropout for one (query row, key) pair; row = (b*heads + h)*T + query.
 // p == 0.5 (the HHI default) takes ONE random bit per pair: bit key%32 of the hash of (row * ceil(T/32) + key/32), so a
@@ -223,6 +232,21 @@ __device__ __forceinline__ float attn_drop_scale(uint64_t key, uint64_t row, int
 // returns the multiplier: 0 if dropped, 1/(1-p) if kept
 __device__ __forceinline__ float drop_scale(uint64_t key, uint64_t idx, float p, float inv_keep, bool bit_mode = false) {
   return drop_keep(key, idx, p, drop_threshold(p), bit_mode) ? inv_keep : 0.0f;
+}
+// multipliers of N consecutive elements idx0 .. idx0+N-1 that do not straddle a multiple of 32 (N | 32, idx0 % N == 0):
+// one hash for all of them at p == 0.5, one per element otherwise - the same decisions as drop_scale element by element
+template <int N>
+__device__ __forceinline__ void drop_scale_n(uint64_t key, uint64_t idx0, float p, float inv_keep, float (&m)[N]) {
+  static_assert(N >= 1 && N <= 32 && (32 % N) == 0, "drop_scale_n: N must divide 32");
+  if (p == 0.5f) {
+    const uint32_t w = drop_word(key, idx0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) m[i] = (w >> i) & 1u ? inv_keep : 0.0f;
+  } else {
+    const uint32_t thr = drop_threshold(p);
+#pragma unroll
+    for (int i = 0; i < N; ++i) m[i] = drop_bits(key, idx0 + i) >= thr ? inv_keep : 0.0f;
+  }
 }
 
 }  // namespace egot2

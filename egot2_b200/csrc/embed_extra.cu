@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const EmbedSrc src, i
         }
       }
       if (fdrop) {
+        float dmf[4];
+        drop_scale_n<4>(key_feat ^ egot2_ep, (uint64_t)row * HH + c0, p_feat, ik_f, dmf);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) w[i] *= drop_scale(key_feat ^ egot2_ep, (uint64_t)row * HH + c0 + i, p_feat, ik_f);
+        for (int i = 0; i < 4; ++i) w[i] *= dmf[i];
       }
       __nv_bfloat162 p0 = __floats2bfloat162_rn(w[0], w[1]), p1 = __floats2bfloat162_rn(w[2], w[3]);
       uint2 zw; zw.x = *reinterpret_cast<uint32_t*>(&p0); zw.y = *reinterpret_cast<uint32_t*>(&p1);
@@ -112,8 +114,10 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const EmbedSrc src, i
         o[0] += t4.x; o[1] += t4.y; o[2] += t4.z; o[3] += t4.w;
       }
       if (p_embed > 0.f) {
+        float dme[4];
+        drop_scale_n<4>(key_embed ^ egot2_ep, (uint64_t)row * HH + c0, p_embed, ik_e, dme);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] *= drop_scale(key_embed ^ egot2_ep, (uint64_t)row * HH + c0 + i, p_embed, ik_e);
+        for (int i = 0; i < 4; ++i) o[i] *= dme[i];
       }
       __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
       uint2 xw; xw.x = *reinterpret_cast<uint32_t*>(&p0); xw.y = *reinterpret_cast<uint32_t*>(&p1);

@@ -169,10 +169,10 @@ __device__ __forceinline__ void fixup_row_fwd(int lane, int m, float* __restrict
   const float4 bb = *reinterpret_cast<const float4*>(b2 + c0);
   float v[4] = {acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w};
   if (p_drop > 0.f) {
-    const float inv_keep = 1.f / (1.f - p_drop);
-    const uint32_t thr = drop_threshold(p_drop);
+    float dm[4];
+    drop_scale_n<4>(key_drop2 ^ ep, (uint64_t)m * H + c0, p_drop, 1.f / (1.f - p_drop), dm);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = drop_bits(key_drop2 ^ ep, (uint64_t)m * H + c0 + i) >= thr ? v[i] * inv_keep : 0.f;
+    for (int i = 0; i < 4; ++i) v[i] = dm[i] * v[i];
   }
   v[0] += __uint_as_float(xw.x << 16); v[1] += __uint_as_float(xw.x & 0xffff0000u);
   v[2] += __uint_as_float(xw.y << 16); v[3] += __uint_as_float(xw.y & 0xffff0000u);
@@ -687,6 +687,8 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       // pass 1: y = acc2 + b2 -> dropout2 -> + x1, rounded to bf16 (what LayerNorm2 sees and what is saved); staged in the
       // first hid buffer; row sum / sum of squares on the rounded values
       float sum = 0.f, sq = 0.f;
+      static_assert(CW <= 32, "the drop2 keep word covers one aligned run of 32 columns per thread");
+      const uint32_t keep2 = DROP == 1 ? drop_word(a.key_drop2 ^ egot2_ep, (uint64_t)m * H + nb) : 0u;
 #pragma unroll 1
       for (int j8 = 0; j8 < CW / 8; ++j8) {
         uint32_t rr[8];
@@ -701,7 +703,10 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         for (int k = 0; k < 4; ++k) {
           const int j = j8 * 8 + 2 * k;
           float v0 = __uint_as_float(rr[2 * k]) + sVec[nb + j], v1 = __uint_as_float(rr[2 * k + 1]) + sVec[nb + j + 1];
-          if constexpr (DROP != 0) {
+          if constexpr (DROP == 1) {          // p == 0.5: this thread's CW columns share one keep word (nb % 32 == 0)
+            v0 = (keep2 >> j) & 1u ? v0 * inv_keep : 0.f;
+            v1 = (keep2 >> (j + 1)) & 1u ? v1 * inv_keep : 0.f;
+          } else if constexpr (DROP == 2) {
             v0 = drop_bits(a.key_drop2 ^ egot2_ep, (uint64_t)m * H + nb + j) >= thr ? v0 * inv_keep : 0.f;
             v1 = drop_bits(a.key_drop2 ^ egot2_ep, (uint64_t)m * H + nb + j + 1) >= thr ? v1 * inv_keep : 0.f;
           }

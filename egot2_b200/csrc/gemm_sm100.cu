@@ -11,6 +11,7 @@
 //   K-major  (row-major, K contiguous; activations (M,K) / nn.Linear weights (N,K)): one TMA box {64 k, rows}
 //   MN-major (K rows, M|N contiguous; used by dX = dY.W and dW = dY^T.X):            boxes of {64 mn, 64 k}
 // gridDim.z > 1 = split-K for the weight-gradient GEMMs (K = every token of the batch): fp32 atomics into C.
+#include <stdio.h>
 #include <stdlib.h>
 
 #define EGOT2_FILE_ID 4
@@ -53,7 +54,16 @@ struct EpiArgs {
   const float* ln_g; const float* ln_b; float ln_eps;
   void* ln_out; float* ln_stat; const float* ln_table; int ln_table_rows; int ln_row0;
   float ln_p_drop; uint64_t ln_drop_key;
+  int trace_slot;    // -DEGOT2_GEMM_TRACE builds: CTA (0,0,0) stamps its phases into g_gtrace[trace_slot]
 };
+
+// -DEGOT2_GEMM_TRACE: where one CTA of a launch spends its time (clock64 stamps of CTA (0,0,0); egot2_gemm_trace_dump prints them)
+#ifdef EGOT2_GEMM_TRACE
+__device__ long long g_gtrace[512][16];
+#define GTR(k) do { if (blockIdx.x == 0 && blockIdx.z == 0 && e.trace_slot >= 0) g_gtrace[e.trace_slot][k] = clock64(); } while (0)
+#else
+#define GTR(k) do { } while (0)
+#endif
 
 __device__ __forceinline__ long long remap(int r, int rpg, int gstride) {
   return rpg > 0 ? (long long)(r / rpg) * gstride + (r % rpg) : (long long)r;
@@ -145,6 +155,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int nkb = kb_end - kb_begin;
 
   pdl_launch_dependents();      // the next kernel's prologue may overlap this one's main loop
+  if (threadIdx.x == 0) GTR(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -157,7 +168,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   // tensor-core kernels' CTAs (the data-gradient chain beside these weight-gradient GEMMs) from allocating TMEM on this SM
   const bool one_tile = gridDim.z > 1;
   if (warp == 1) { if (one_tile) tmem_alloc<BN>(tmem_slot); else tmem_alloc<2 * BN>(tmem_slot); }
+  if (threadIdx.x == 0) GTR(1);
   pdl_wait();                   // everything above touched only kernel parameters, shared memory and TMEM
+  if (threadIdx.x == 0) GTR(2);
   EGOT2_TL(EGOT2_FILE_ID);
   const unsigned long long egot2_ep = epoch_xor();
   float* sbias = reinterpret_cast<float*>(smem_raw + (bias_off - smem_u32(smem_raw)));
@@ -165,6 +178,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) GTR(3);
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -201,6 +215,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + s * B_BYTES + j * 8192, &tma_b, full0 + 8 * s, n0 + 64 * j, k);
           }
+          if (tile == (int)blockIdx.x && (i == 0 || i == nkb - 1)) GTR(i == 0 ? 4 : 5);
         }
       }
     }
@@ -217,6 +232,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(full0 + 8 * s, ph);
+          if (lt == 0 && (i == 0 || i == nkb - 1)) GTR(i == 0 ? 6 : 7);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
@@ -269,6 +285,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         named_bar_sync(3, NTHREADS - 64);
       }
       mbar_wait(tmem_full + 8 * buf, (lt >> 1) & 1);
+      if (lt == 0 && threadIdx.x == 64) GTR(8);
       tc_fence_after();
       float ln_sum = 0.f, ln_sq = 0.f;
 #pragma unroll 1
@@ -308,8 +325,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             for (int j = 0; j < 32; ++j) v[j] = aux[j] > 0.f ? v[j] * e.mask_scale : 0.f;
           }
           if (e.p_drop > 0.f) {
+            const uint64_t idx0 = (uint64_t)m * e.N + nb;
+            if (e.p_drop == 0.5f && (idx0 & 31) == 0) {     // one hash for the chunk's 32 columns (common.cuh drop_keep)
+              const uint32_t kw = drop_word(e.drop_key ^ egot2_ep, idx0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key ^ egot2_ep, (uint64_t)m * e.N + nb + j, e.p_drop, inv_keep, e.drop_bit_mode != 0);
+              for (int j = 0; j < 32; ++j) v[j] = (kw >> j) & 1u ? v[j] * inv_keep : 0.f;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key ^ egot2_ep, idx0 + j, e.p_drop, inv_keep);
+            }
           }
           if (res_row) {
             if (mask_row) load32(res_row + nb, aux);
@@ -411,8 +435,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                 o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w; o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
               }
               if (e.ln_p_drop > 0.f) {
+                { float dm[8]; drop_scale_n<8>(e.ln_drop_key ^ egot2_ep, (uint64_t)lrow * 128 + c, e.ln_p_drop, ln_keep, dm);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] *= drop_scale(e.ln_drop_key ^ egot2_ep, (uint64_t)lrow * 128 + c + k, e.ln_p_drop, ln_keep);
+                  for (int k = 0; k < 8; ++k) o[k] *= dm[k]; }
               }
               uint4 pk;
               __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
@@ -424,9 +449,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           }
         }
       }
+      if (lt == 0 && threadIdx.x == 64) GTR(9);
       if (BN <= 128 && e.tma_store) {
         fence_proxy_async();                      // the generic-proxy smem writes become visible to the TMA engine
         named_bar_sync(2, NTHREADS - 64);
+        if (lt == 0 && threadIdx.x == 64) GTR(10);
         if (warp == 2 && lane == 0) {
 #pragma unroll
           for (int h = 0; h < BN / 64; ++h) tma_store_2d(&tma_c, sOut + h * 16384, n0 + h * 64, m0);
@@ -435,12 +462,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
     }
     if (e.tma_store && warp == 2 && lane == 0) tma_store_wait_all();
+    if (threadIdx.x == 64) GTR(11);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) GTR(12);
   if (warp == 1) {
     __syncwarp();
     if (one_tile) tmem_dealloc<BN>(tmem_base); else tmem_dealloc<2 * BN>(tmem_base);
+    if (lane == 0) GTR(13);
   }
 }
 
@@ -496,6 +526,11 @@ int make_map3(CUtensorMap* map, const void* base, int inner, int rpg, int groups
 }
 
 struct KGroup { int on = 0, g = 1, dblocks = 1, kb_total = 0; };
+#ifdef EGOT2_GEMM_TRACE
+struct GTraceTag { char txt[96]; };
+GTraceTag g_gtrace_tags[512];
+int g_gtrace_n = 0;
+#endif
 static bool host_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int BN, bool A_MN, bool B_MN, typename TO>
@@ -549,6 +584,14 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
     ctas = (num_tiles + rounds - 1) / rounds;
   }
   dim3 grid(ctas, 1, splits);
+  e.trace_slot = -1;
+#ifdef EGOT2_GEMM_TRACE
+  if (g_gtrace_n < 512) {
+    snprintf(g_gtrace_tags[g_gtrace_n].txt, 96, "bn%d %s%s %s M%d N%d K%d grid(%d,%d) tma_store%d%s%s", BN, A_MN ? "mn" : "k", B_MN ? "mn" : "k",
+             sizeof(TO) == 4 ? "f32" : "bf16", a.M, a.N, a.K, ctas, splits, e.tma_store, a.residual ? " +res" : "", a.p_drop > 0.f ? " +drop" : "");
+    e.trace_slot = g_gtrace_n++;
+  }
+#endif
   ProfScope prof(st, "gemm_sm100<bn%d,%s%s,%s> M%d N%d K%d sk%d%s", BN, A_MN ? "mn" : "k", B_MN ? "mn" : "k",
                  sizeof(TO) == 4 ? "f32" : "bf16", a.M, a.N, a.K, splits, a.mask ? " +mask" : (a.residual ? " +res" : ""));
   ::egot2::launch(kern, grid, dim3(NTHREADS), smem, st, ma, mb, mc, e, kb_total, kb_per, tiles_n, num_tiles);
@@ -588,6 +631,25 @@ bool gemm_sm100_ln_ok(const GemmArgs& a) {
          host_al16(a.A) && host_al16(a.B) && a.lda % 8 == 0 && a.ldb % 8 == 0 && (!a.residual || (host_al16(a.residual) && a.ldr % 8 == 0)) &&
          (a.c_rpg == 0 || (a.c_rpg * 128 * 2) % 16 == 0);
 }
+
+#ifdef EGOT2_GEMM_TRACE
+// prints, for every traced launch since the last dump, the cycles CTA (0,0,0) spent up to each phase (relative to its entry)
+extern "C" int egot2_gemm_trace_dump() {
+  static long long h[512][16];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_gtrace, sizeof(h));
+  printf("# cycles since CTA entry: prologue | pdl_wait done | sync | tma first,last issued | mma saw first,last stage | epi saw acc | epi done | bar | stored | cta sync | dealloc\n");
+  for (int i = 0; i < g_gtrace_n; ++i) {
+    const long long t0 = h[i][0];
+    printf("%-64s", g_gtrace_tags[i].txt);
+    for (int k = 1; k < 14; ++k) printf(" %6lld", h[i][k] ? h[i][k] - t0 : -1LL);
+    printf("\n");
+  }
+  g_gtrace_n = 0;
+  fflush(stdout);
+  return 0;
+}
+#endif
 
 // returns -1 when this kernel does not take the problem (caller falls back to the CUDA-core GEMM)
 int gemm_sm100(const GemmArgs& a, cudaStream_t st) {

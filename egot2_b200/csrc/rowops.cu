@@ -142,7 +142,6 @@ __global__ void __launch_bounds__(128) table_grad_vec_kernel(int B, int T, int H
   const int t = blockIdx.x;
   const int b0 = blockIdx.y * clips_per_cta, b1 = min(B, b0 + clips_per_cta);
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  const uint32_t thr = drop_threshold(p_drop);
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -150,13 +149,12 @@ __global__ void __launch_bounds__(128) table_grad_vec_kernel(int B, int T, int H
     const size_t idx = ((size_t)b * T + t) * H + cg * 8;
     const uint4 v = *reinterpret_cast<const uint4*>(dy + idx);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float dm[8];
+    if (p_drop > 0.f) drop_scale_n<8>(drop_key ^ egot2_ep, idx, p_drop, inv_keep, dm);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
-      if (p_drop > 0.f) {
-        lo = drop_bits(drop_key ^ egot2_ep, idx + 2 * k) >= thr ? lo * inv_keep : 0.f;
-        hi = drop_bits(drop_key ^ egot2_ep, idx + 2 * k + 1) >= thr ? hi * inv_keep : 0.f;
-      }
+      if (p_drop > 0.f) { lo *= dm[2 * k]; hi *= dm[2 * k + 1]; }
       acc[2 * k] += lo; acc[2 * k + 1] += hi;
     }
   }
@@ -502,8 +500,10 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const LayerNormArgs a) 
         o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w; o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
       }
       if (a.p_drop > 0.f) {
+        float dm[8];
+        drop_scale_n<8>(a.drop_key ^ egot2_ep, (uint64_t)row * HH + c0, a.p_drop, inv_keep, dm);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] *= drop_scale(a.drop_key ^ egot2_ep, (uint64_t)row * HH + c0 + i, a.p_drop, inv_keep);
+        for (int i = 0; i < 8; ++i) o[i] *= dm[i];
       }
       reinterpret_cast<uint4*>(y)[s * V::LPR + cl] = pack8(o);
     }
@@ -563,9 +563,14 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
       unpack8(xc[s], xv);
       unpack8(dc[s], d);
       const int c0 = (s * V::LPR + cl) * 8;
+      if (a.dy_p_drop > 0.f) {
+        float dm[8];
+        drop_scale_n<8>(a.dy_drop_key ^ egot2_ep, (uint64_t)row * HH + c0, a.dy_p_drop, dy_keep, dm);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] *= dm[i];
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (a.dy_p_drop > 0.f) d[i] *= drop_scale(a.dy_drop_key ^ egot2_ep, (uint64_t)row * HH + c0 + i, a.dy_p_drop, dy_keep);
         if (!valid) d[i] = 0.f;
         xh[s][i] = (xv[i] - mean) * rstd;
         dyg[s][i] = d[i] * g[s][i];
@@ -598,8 +603,10 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const LayerNormBwdArgs 
       if (dx2p) {
         float o2[8];
         unpack8(packed, o2);        // the unfused sequence masks the bf16-rounded dx
+        float dm2[8];
+        drop_scale_n<8>(a.dx2_drop_key ^ egot2_ep, (uint64_t)row * HH + c0, a.dx2_p_drop, dx2_keep, dm2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o2[i] *= drop_scale(a.dx2_drop_key ^ egot2_ep, (uint64_t)row * HH + c0 + i, a.dx2_p_drop, dx2_keep);
+        for (int i = 0; i < 8; ++i) o2[i] *= dm2[i];
         const uint4 packed2 = pack8(o2);
         dx2p[s * V::LPR + cl] = packed2;
         if (a.dcol) {               // column sums of what the next Linear's backward sees (the rounded values)

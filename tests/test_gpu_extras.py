@@ -197,7 +197,7 @@ def test_layernorm_in_gemm_epilogue_matches_separate_kernel(name, monkeypatch):
     from egot2_b200.engine import TranslatorEngine
     from oracle import translator_oracle as O
     from oracle.cases import CASES, case_inputs
-    case = next(c for c in CASES if c.name == name)
+    case = CASES[name]
     sd, feats, labels, extra = case_inputs(case)
     res = {}
     loss_kind, cw = tg._loss_kind(case)

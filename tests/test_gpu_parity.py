@@ -266,7 +266,7 @@ def dropout_mask_oracle(seed, site, layer, n, p, bit_mode=False, raw_bits=False)
         idx = np.arange(n, dtype=np.uint64)
         if raw_bits:
             return bits(key, idx)
-        if bit_mode and p == 0.5:      # FFN hidden site: one random bit per element (bit idx%32 of the hash of idx/32)
+        if p == 0.5:      # every elementwise site at p == 0.5: one random bit per element (bit idx%32 of the hash of idx/32)
             keep = ((bits(key, idx >> np.uint64(5)) >> (idx & np.uint64(31))) & np.uint64(1)) == 1
         else:
             thr = np.uint64(int(np.float32(p) * np.float32(4294967296.0) + np.float32(0.5)))

@@ -19,7 +19,8 @@ from egot2_b200 import _lib as L, synth  # noqa: E402
 from egot2_b200.trainer import TranslatorTrainer  # noqa: E402
 
 FILES = {1: "rowops.cu", 2: "loss.cu", 3: "head_fused.cu", 4: "gemm_sm100.cu", 5: "ffn_sm100.cu", 6: "attention_mma.cu",
-         7: "decoder.cu", 8: "attention_small.cu", 9: "attention_simt.cu", 10: "gemm_simt.cu", 11: "api.cu"}
+         7: "decoder.cu", 8: "attention_small.cu", 9: "attention_simt.cu", 10: "gemm_simt.cu", 11: "api.cu", 12: "vit.cu",
+         13: "attention_wide.cu", 14: "embed_extra.cu", 15: "metrics.cu", 16: "peer.cu", 17: "attention_long.cu"}
 
 
 def kernel_at(fid, line, cache={}):
