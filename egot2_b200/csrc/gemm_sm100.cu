@@ -54,6 +54,7 @@ struct EpiArgs {
   const float* ln_g; const float* ln_b; float ln_eps;
   void* ln_out; float* ln_stat; const float* ln_table; int ln_table_rows; int ln_row0;
   float ln_p_drop; uint64_t ln_drop_key;
+  int tma_red;       // split-K fp32 accumulation: the tile is staged in shared memory and added to C by bulk tensor reductions (tma_c = fp32 map)
   int trace_slot;    // -DEGOT2_GEMM_TRACE builds: CTA (0,0,0) stamps its phases into g_gtrace[trace_slot]
 };
 
@@ -159,7 +160,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if (e.tma_store) tma_prefetch_desc(&tma_c);
+    if (e.tma_store || e.tma_red) tma_prefetch_desc(&tma_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 4 * EPG); }
     fence_barrier_init();
@@ -258,6 +259,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const float inv_keep = e.p_drop > 0.f ? 1.f / (1.f - e.p_drop) : 1.f;
     const bool first_split = blockIdx.z == 0;
     const float* bias = first_split ? e.bias : nullptr;
+    // warp-uniform: plain fp32 split-K accumulation (what every weight-gradient GEMM is) leaves by TMA reduction (below)
+    const bool tma_red = sizeof(TO) == 4 && e.tma_red && gridDim.z > 1 && nkb > 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -288,6 +291,42 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       if (lt == 0 && threadIdx.x == 64) GTR(8);
       tc_fence_after();
       float ln_sum = 0.f, ln_sq = 0.f;
+      if (tma_red) {
+        // Split-K partial sums leave through shared memory + bulk tensor reductions instead of a red.v4 per thread and 4
+        // columns: the LSU pays ~1.8 cycles per lane and red instruction, which made the epilogue of the weight-gradient
+        // GEMMs (128 x 256 fp32 per CTA = 8192 lane-reds, ~15k cycles) as long as their K loop.  The operand ring is idle
+        // by now (one tile per CTA, all of its MMAs have retired) and takes the fp32 tile, [column group of 32][128 rows]
+        // [128 B], 128B-swizzled like every other TMA tile.  Every warp sends its own 32 rows x 32 columns (4 KB box) as
+        // soon as they are staged - no CTA-wide barrier - and the TMEM load of the next group is in flight meanwhile.
+        const int rr = q * 32 + lane;
+        uint32_t ra[32], rb[32];
+        auto stage = [&](const uint32_t (&r)[32], int c0) {
+          const uint32_t srow = sA + (uint32_t)(c0 >> 5) * 16384u + (uint32_t)rr * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts128(srow + (uint32_t)((j ^ (rr & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && n0 + c0 < e.N) tma_reduce_add_2d(&tma_c, sA + (uint32_t)(c0 >> 5) * 16384u + (uint32_t)(q * 32) * 128u, n0 + c0, m0 + q * 32);
+        };
+        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+        tmem_ld_32x32(tcol + c_lo, ra);
+#pragma unroll 1
+        for (int c0 = c_lo; c0 < c_hi; c0 += 64) {
+          tmem_ld_wait();
+          if (c0 + 32 < c_hi) tmem_ld_32x32(tcol + c0 + 32, rb);
+          stage(ra, c0);
+          if (c0 + 32 < c_hi) {
+            tmem_ld_wait();
+            if (c0 + 64 < c_hi) tmem_ld_32x32(tcol + c0 + 64, ra);
+            stage(rb, c0 + 32);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(tmem_empty + 8 * buf); tma_store_commit(); tma_store_wait_read(); }    // shared memory may be released
+        if (lt == 0 && threadIdx.x == 64) GTR(9);
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         uint32_t r[32];
@@ -508,6 +547,21 @@ int make_map(CUtensorMap* map, const void* base, int inner, int rows, int ld, in
   return 0;
 }
 
+// 2-D fp32 map over a row-major (rows, inner) matrix (the target of the split-K bulk reductions)
+int make_map_f32(CUtensorMap* map, const void* base, int inner, int rows, int ld, int box_inner, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  EGOT2_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGOT2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32) failed (%d) inner=%d rows=%d ld=%d", (int)r, inner, rows, ld);
+  return 0;
+}
+
 // 3-D bf16 map over rows that live in groups: element (c, d, g) at base + ((g * gstride_rows + d) * ld + c)
 int make_map3(CUtensorMap* map, const void* base, int inner, int rpg, int groups, int ld, long long gstride_rows,
               int box_inner, int box_d, int box_g) {
@@ -574,6 +628,14 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   splits = (kb_total + kb_per - 1) / kb_per;
   e.atomic = splits > 1 && a.split_stride == 0;
   e.split_stride = a.split_stride;
+  // split-K accumulation by bulk tensor reduction (EGOT2_GEMM_TMARED=0: per-thread red.v4 instead)
+  static const bool tma_red_on = !(getenv("EGOT2_GEMM_TMARED") && getenv("EGOT2_GEMM_TMARED")[0] == '0');
+  e.tma_red = 0;
+  if (sizeof(TO) == 4 && tma_red_on && e.atomic && a.accumulate && !a.bias && !a.residual && !a.relu && !a.mask && a.p_drop <= 0.f &&
+      a.c_rpg == 0 && a.N % 32 == 0 && a.ldc % 4 == 0 && host_al16(a.C) && (size_t)(BN / 32) * 16384 <= (size_t)STAGES * (BM * BK * 2 + BN * BK * 2)) {
+    EGOT2_TRY(make_map_f32(&mc, a.C, a.N, a.M, a.ldc, 32, 32));
+    e.tma_red = 1;
+  }
   if (a.splits_out) *a.splits_out = splits;
   const int tiles_n = (a.N + BN - 1) / BN, num_tiles = tiles_n * ((a.M + BM - 1) / BM);
   // persistent CTAs: as many as are resident at once, evened out so that every CTA walks the same number of tiles
