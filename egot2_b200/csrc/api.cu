@@ -124,6 +124,7 @@ int gemm(const GemmArgs& a, cudaStream_t st) {
     if (rc >= 0) { if (rc == 0) g_gemm_impl = "tcgen05"; return rc; }
   }
   g_gemm_impl = "simt";
+  EGOT2_CHECK(!a.trans_c, "gemm: transposed accumulation exists in the tcgen05 kernel only");
   EGOT2_CHECK(a.ln_g == nullptr, "gemm: a fused LayerNorm was requested but the tcgen05 kernel did not take the problem");
   if (a.split_stride > 0) {      // the CUDA-core GEMM has no split-K: one split, written to slab 0
     GemmArgs b = a;
@@ -297,6 +298,21 @@ int side_wait_pending(cudaStream_t main, Side* sd, const void* ws) {
 // resident CTA slots so that all of them fit ONE wave together instead of queueing behind each other
 int wgrad(int dtype, int rows, int n_out, int k_in, const void* dY, int ld_dy, int dy_rpg, int dy_gs, const void* X,
           int ld_x, int x_rpg, int x_gs, float* dW, cudaStream_t st, int share = 1) {
+  // Tall outputs with a narrow input side (dW1 of the FFN: 2048 x 128) are computed as the TRANSPOSE, dW^T = X^T . dY:
+  // with the token dimension as K every 128-row tile of the output re-streams the other operand, so the long side
+  // belongs in N (256-wide tiles) - 3/4 of the L2 -> SM bytes of the plain orientation, which bound these GEMMs.  The
+  // bulk-reduction epilogue adds the tile into the row-major dW transposed, at no extra cost.
+  static const bool swap_on = !env_is("EGOT2_WGRAD_SWAP", "0");
+  if (swap_on && dtype == EGOT2_BF16 && gemm_impl_mode() == 0 && k_in <= 128 && n_out >= 512 && !dy_rpg && !x_rpg && share == 1) {
+    GemmArgs t;
+    t.M = k_in; t.N = n_out; t.K = rows;
+    t.A = X; t.lda = ld_x; t.trans_a = 1;
+    t.B = dY; t.ldb = ld_dy; t.trans_b = 0;
+    t.C = dW; t.ldc = k_in; t.trans_c = 1; t.in_dtype = dtype; t.out_dtype = EGOT2_F32; t.accumulate = 1;
+    t.split_k = suggest_split_k(t.M, t.N, t.K);
+    const int rc = t.split_k >= 2 ? gemm_sm100(t, st) : -3;
+    if (rc >= 0) return rc;
+  }
   GemmArgs g;
   g.M = n_out; g.N = k_in; g.K = rows;
   g.A = dY; g.lda = ld_dy; g.trans_a = 1; g.a_rpg = dy_rpg; g.a_gstride = dy_gs;

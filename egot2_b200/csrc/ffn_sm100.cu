@@ -220,7 +220,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_hid,
                      const __grid_constant__ CUtensorMap tm_y2, const __grid_constant__ CUtensorMap tm_out,
-                     const FfnArgs a) {
+                     const __grid_constant__ CUtensorMap tm_part, const FfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sX = base;                         // 32 KB
@@ -269,7 +269,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2);
-    tma_prefetch_desc(&tm_hid); tma_prefetch_desc(&tm_y2); tma_prefetch_desc(&tm_out);
+    tma_prefetch_desc(&tm_hid); tma_prefetch_desc(&tm_y2); tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_part);
     mbar_init(x_full, 1); mbar_init(x_pair, 2); mbar_init(a2_full, 1); mbar_init(xt_full, 2 * EPW);
     for (int s = 0; s < R1; ++s) { mbar_init(r1_full + 8 * s, 1); mbar_init(r1_empty + 8 * s, 1); }
     for (int s = 0; s < R2; ++s) { mbar_init(r2_full + 8 * s, 1); mbar_init(r2_empty + 8 * s, 1); }
@@ -322,15 +322,20 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   pdl_wait();                    // first access to anything a previous kernel produced is below
   EGOT2_TL(EGOT2_FILE_ID);
   const unsigned long long egot2_ep = epoch_xor();
-  if (BWD) {                     // sB1 doubles as this CTA's db1 accumulator (the forward's bias stage is not needed)
-    for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = 0.f;
+  // The bias / LayerNorm vectors (forward) and the db1 accumulators (backward) are touched by the epilogue warps only, and
+  // those idle until the first accumulator arrives: THEY stage them (named barrier among themselves) while the producer and
+  // the MMA threads start the first chunk - a CTA-wide fill + __syncthreads here sat in front of the first TMA load.
+  if (warp >= 2 && warp < 2 + EPW) {
+    const int et = (int)threadIdx.x - 64;
+    if (BWD) {                   // sB1 doubles as this CTA's db1 accumulator (the forward's bias stage is not needed)
+      for (int i = et; i < a.FF; i += EPW * 32) sB1[i] = 0.f;
+    } else {
+      const float s1 = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;    // dropout scale folded into the bias (see epilogue)
+      for (int i = et; i < a.FF; i += EPW * 32) sB1[i] = a.b1[i] * s1;
+      for (int i = et; i < 128; i += EPW * 32) { sVec[i] = a.b2[i]; sVec[128 + i] = a.ln_g[i]; sVec[256 + i] = a.ln_b[i]; }
+    }
+    named_bar_sync(3, EPW * 32);
   }
-  if (!BWD) {
-    const float s1 = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;      // dropout scale folded into the bias (see epilogue)
-    for (int i = threadIdx.x; i < a.FF; i += NTHREADS) sB1[i] = a.b1[i] * s1;
-    for (int i = threadIdx.x; i < 128; i += NTHREADS) { sVec[i] = a.b2[i]; sVec[128 + i] = a.ln_g[i]; sVec[256 + i] = a.ln_b[i]; }
-  }
-  __syncthreads();
   if (threadIdx.x == 64) TR(60, 1);
 
   if (warp == 0) {
@@ -614,9 +619,38 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int nb = ch * CW;
     const uint32_t xrow = sX + half * HALF + (uint32_t)r * 128;
     const uint32_t yrow = sHid + half * HALF + (uint32_t)r * 128;
-    if (split) {
+    if (split && !a.tile_ctr) {
       // FF-split tail unit: this pair's partial sum over its chunk range joins the others' in fp32; the fix-up kernel
-      // applies everything that follows the second GEMM once all S partials are in
+      // applies everything that follows the second GEMM once all S partials are in.  The tile leaves through the (idle)
+      // hidden-tile buffers and bulk tensor reductions - [column group of 32][128 rows][128 B], 128B-swizzled, one 32 x 32
+      // box per warp - because per-thread red.v4 is LSU-bound at ~1.8 cycles per lane (4096 lane-reds per CTA, ~7k cycles).
+      static_assert(HB * TILE >= 128 * 128 * 4, "the fp32 partial tile is staged in the hidden-tile buffers");
+#pragma unroll 1
+      for (int j8 = 0; j8 < CW / 8; ++j8) {
+        uint32_t rr[8];
+        tmem_ld_32x8(acc2 + lane_addr + nb + j8 * 8, rr);
+        tmem_ld_wait();
+        if (!row_ok) {            // rows past M carry relu(b1) . W2, not zero: the scratch must stay clean for the next launch
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rr[k] = 0u;
+        }
+        const int col = nb + j8 * 8;                                     // this thread's 8 columns = two 16 B chunks of its row
+        const uint32_t srow = sHid + (uint32_t)(col >> 5) * 16384u + (uint32_t)r * 128u;
+        const int jc = (col & 31) >> 2;
+        sts128(srow + (uint32_t)((jc ^ (r & 7)) << 4), rr[0], rr[1], rr[2], rr[3]);
+        sts128(srow + (uint32_t)(((jc + 1) ^ (r & 7)) << 4), rr[4], rr[5], rr[6], rr[7]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        const int row0 = m0 - a.split_pair0 * 2 * BM + q * 32;
+#pragma unroll
+        for (int g = 0; g < (CW + 31) / 32; ++g)
+          tma_reduce_add_2d(&tm_part, sHid + (uint32_t)((nb >> 5) + g) * 16384u + (uint32_t)(q * 32) * 128u, ((nb >> 5) + g) * 32, row0);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+    } else if (split) {
       float* prow = a.partial + ((size_t)(m - a.split_pair0 * 2 * BM)) * H + nb;
 #pragma unroll 1
       for (int j8 = 0; j8 < CW / 8; ++j8) {
@@ -858,7 +892,7 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
   const size_t smem = 1024 + (size_t)TILE * (1 + HB) + (size_t)RING * STAGE + 512 + (2 * EG * 128 + 384 + (size_t)FF) * 4;
   EGOT2_CHECK(smem <= 227 * 1024, "ffn_fused: FF=%d does not fit the bias stage in shared memory", FF);
   const int drop = bwd ? 0 : (a.p_drop <= 0.f ? 0 : (a.p_drop == 0.5f ? 1 : 2));
-  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FfnArgs);
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FfnArgs);
   static const KernelFn kernels[4] = {ffn_sm100_kernel<false, 0>, ffn_sm100_kernel<false, 1>, ffn_sm100_kernel<false, 2>,
                                       ffn_sm100_kernel<true, 0>};
   const int ki = bwd ? 3 : drop;
@@ -914,7 +948,21 @@ static int ffn_launch(bool bwd, int M, int FF, const CUtensorMap& tx, const CUte
       a.tile_ctr = (S > 1 && !separate) ? reinterpret_cast<int*>(a.partial + (size_t)tail_max * 2 * BM * H) : nullptr;
     }
     const int grid_pairs = S > 1 ? (pairs - tail) + tail * S : pairs;
-    launch(kernels[ki], dim3(2 * grid_pairs), dim3(NTHREADS), smem, st, tx, tw1, tw2, thid, ty2, tout, a);
+    // fp32 map over the tail's partial rows (the target of the split units' bulk reductions); unused when S == 1
+    CUtensorMap tpart = tx;
+    if (S > 1) {
+      const int tail_rows = tail * 2 * BM;
+      EncodeTiledFn fn = ffn_encode_fn();
+      EGOT2_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+      cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)tail_rows};
+      cuuint64_t strides[1] = {(cuuint64_t)H * 4};
+      cuuint32_t box[2] = {32, 32};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = fn(&tpart, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.partial, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      EGOT2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(partial) failed (%d)", (int)r);
+    }
+    launch(kernels[ki], dim3(2 * grid_pairs), dim3(NTHREADS), smem, st, tx, tw1, tw2, thid, ty2, tout, tpart, a);
     EGOT2_LAUNCH_CHECK();
     if (S > 1 && separate) {
       const int m_base = a.split_pair0 * 2 * BM, rows = M - m_base;

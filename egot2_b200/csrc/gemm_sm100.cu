@@ -54,6 +54,7 @@ struct EpiArgs {
   const float* ln_g; const float* ln_b; float ln_eps;
   void* ln_out; float* ln_stat; const float* ln_table; int ln_table_rows; int ln_row0;
   float ln_p_drop; uint64_t ln_drop_key;
+  int trans_c;       // tma_red only: the tile is added to the transpose of C (C is (N, M) row-major, ld = ldc)
   int tma_red;       // split-K fp32 accumulation: the tile is staged in shared memory and added to C by bulk tensor reductions (tma_c = fp32 map)
   int trace_slot;    // -DEGOT2_GEMM_TRACE builds: CTA (0,0,0) stamps its phases into g_gtrace[trace_slot]
 };
@@ -301,12 +302,24 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const int rr = q * 32 + lane;
         uint32_t ra[32], rb[32];
         auto stage = [&](const uint32_t (&r)[32], int c0) {
-          const uint32_t srow = sA + (uint32_t)(c0 >> 5) * 16384u + (uint32_t)rr * 128u;
+          const uint32_t wbox = sA + (uint32_t)(c0 >> 5) * 16384u + (uint32_t)(q * 32) * 128u;      // this warp's 4 KB box
+          if (e.trans_c) {
+            // C is stored transposed ((N, M) row-major): the box is [32 columns n][32 rows m], one 128-byte smem row per
+            // column of the accumulator; lane = m writes one float of every row (32 lanes = one conflict-free 128 B row)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) sts128(srow + (uint32_t)((j ^ (rr & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            for (int j = 0; j < 32; ++j)
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(wbox + (uint32_t)j * 128u + (uint32_t)((((lane >> 2) ^ (j & 7)) << 4) | ((lane & 3) << 2))), "r"(r[j]) : "memory");
+          } else {
+            const uint32_t srow = wbox + (uint32_t)lane * 128u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts128(srow + (uint32_t)((j ^ (rr & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && n0 + c0 < e.N) tma_reduce_add_2d(&tma_c, sA + (uint32_t)(c0 >> 5) * 16384u + (uint32_t)(q * 32) * 128u, n0 + c0, m0 + q * 32);
+          if (lane == 0 && n0 + c0 < e.N) {
+            if (e.trans_c) tma_reduce_add_2d(&tma_c, wbox, m0 + q * 32, n0 + c0);
+            else tma_reduce_add_2d(&tma_c, wbox, n0 + c0, m0 + q * 32);
+          }
         };
         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
         tmem_ld_32x32(tcol + c_lo, ra);
@@ -633,9 +646,12 @@ int launch(const GemmArgs& a, const CUtensorMap& ma, const CUtensorMap& mb, cons
   e.tma_red = 0;
   if (sizeof(TO) == 4 && tma_red_on && e.atomic && a.accumulate && !a.bias && !a.residual && !a.relu && !a.mask && a.p_drop <= 0.f &&
       a.c_rpg == 0 && a.N % 32 == 0 && a.ldc % 4 == 0 && host_al16(a.C) && (size_t)(BN / 32) * 16384 <= (size_t)STAGES * (BM * BK * 2 + BN * BK * 2)) {
-    EGOT2_TRY(make_map_f32(&mc, a.C, a.N, a.M, a.ldc, 32, 32));
+    if (a.trans_c) EGOT2_TRY(make_map_f32(&mc, a.C, a.M, a.N, a.ldc, 32, 32));
+    else EGOT2_TRY(make_map_f32(&mc, a.C, a.N, a.M, a.ldc, 32, 32));
     e.tma_red = 1;
   }
+  e.trans_c = a.trans_c;
+  if (a.trans_c && !e.tma_red) return -3;      // only the bulk-reduction epilogue can transpose: the caller uses the plain orientation
   if (a.splits_out) *a.splits_out = splits;
   const int tiles_n = (a.N + BN - 1) / BN, num_tiles = tiles_n * ((a.M + BM - 1) / BM);
   // persistent CTAs: as many as are resident at once, evened out so that every CTA walks the same number of tiles
@@ -733,6 +749,7 @@ int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
   if (a.M < 1 || a.N < 32 || a.K < 16) return -1;                  // degenerate tiles (tiny heads) stay on CUDA cores
   if (!host_aligned16(a.A) || !host_aligned16(a.B) || (a.lda % 8) || (a.ldb % 8)) return -1;
   if (a.accumulate && a.out_dtype != EGOT2_F32) return -1;
+  if (a.trans_c && (!a.accumulate || a.out_dtype != EGOT2_F32 || a.split_k < 2 || a.split_stride > 0 || a.c_rpg > 0)) return -3;
   if (a.split_k > 1 && a.split_stride == 0 && (!a.accumulate || a.relu || a.mask || a.p_drop > 0.f)) return -1;
   if (a.split_stride > 0 && (a.accumulate || a.out_dtype != EGOT2_F32 || a.relu || a.mask || a.p_drop > 0.f || a.residual)) return -1;
   // short-K problems are epilogue/store bound: 128-wide tiles run two CTAs per SM; long-K ones amortise A over 256 columns

@@ -22,6 +22,7 @@ struct GemmArgs {
   int relu = 0;                  // max(.,0)
   const void* mask = nullptr; int ldm = 0; float mask_scale = 1.f;   // * (mask[m,n] > 0 ? mask_scale : 0)
   float p_drop = 0.f; uint64_t drop_key = 0;                         // * dropmask(m*N+n)/(1-p)
+  int trans_c = 0;               // fp32 split-K accumulation into the TRANSPOSE: element (m, n) is added to C[n * ldc + m] (tcgen05 kernel only)
   int drop_bit_mode = 0;         // FFN hidden site: one random bit per element when p == 0.5 (common.cuh drop_keep)
   const void* residual = nullptr; int ldr = 0;                       // + residual[m,n]
   int accumulate = 0;            // C += value (fp32 C only); split-K uses atomics

@@ -4,6 +4,7 @@
 // Loads/stores are coalesced (lane-strided columns); grids are sized to a multiple of the SM count.
 #include <math.h>
 
+#include <stdlib.h>
 #define EGOT2_FILE_ID 1
 #include "ops.h"
 
@@ -683,6 +684,7 @@ template <int HH> int ln_bwd_vec_launch(const LayerNormBwdArgs& a, cudaStream_t 
   if (occ == 0) {                             // atomics on the same addresses
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_vec_kernel<HH>, 256, 0) != cudaSuccess || occ < 1) occ = 2;
     if (occ > 4) occ = 4;
+    if (getenv("EGOT2_LN_BWD_OCC") && atoi(getenv("EGOT2_LN_BWD_OCC")) > 0) occ = atoi(getenv("EGOT2_LN_BWD_OCC"));      // experiments
   }
   const int cap = sm_count() * occ;
   if (grid > cap) grid = cap;
