@@ -657,15 +657,24 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   for (int i = 0; i < 2 && i + 1 < d->n_seg; ++i)
     if (sides[i]) { side_st[i] = side_fork(st, sides[i], 0); used[i] = side_st[i] != st; }
   int n_proj = 0, n_big = 0;
+  long long sum_big = 0;
   for (int k = 0; k < d->n_seg; ++k) {
     const bool on = d->seg_has_proj[k] && d->seg_tokens[k] > 0;
     n_proj += on ? 1 : 0;
     n_big += (on && d->seg_in_dim[k] >= 2048) ? 1 : 0;
+    if (on && d->seg_in_dim[k] >= 2048) sum_big += (long long)d->seg_in_dim[k] * d->seg_tokens[k];
   }
   // the weight-gradient GEMMs of the projections run side by side and share the resident CTA slots - among the LONG-K ones
   // only when there are any (PNR / OSCC 8192-wide beside SlowFast's 2048 / 256: the two big ones stream 134 MB and used to get
   // 32 CTAs each because the split was divided by all four)
   const int share_all = n_big > 0 ? n_big : n_proj;
+  // ... and among the long-K ones in proportion to the bytes each streams (in_dim x tokens): PNR's two 8192-wide projections
+  // beside SlowFast's 2048-wide one take a split of 2 each (64 CTAs) instead of 1 (32 CTAs, half of the GPU idle)
+  auto big_share = [&](int Kk, int Dk) {
+    const long long w = (long long)Kk * Dk;
+    const long long sh = w > 0 ? (sum_big + w / 2) / w : 1;
+    return (int)(sh < 1 ? 1 : sh);
+  };
   {
     // every projection's bias gradient (column sums of its segment's rows of dz) in ONE launch of the per-segment
     // column-sum kernel instead of one strided column-sum launch per task
@@ -696,7 +705,7 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
       }
       if (g->proj_w[k])
         EGOT2_TRY(wgrad(d->dtype, d->B * Dk, d->H, Kk, dzk, d->H, Dk, d->T, feat, Kk, 0, 0, g->proj_w[k], sk,
-                        !par ? 1 : ((n_big > 0 && Kk < 2048) ? 8 : share_all)));
+                        !par ? 1 : ((n_big > 0 && Kk < 2048) ? 8 : (n_big > 0 ? big_share(Kk, Dk) : share_all))));
       if (g->dfeat[k]) {   // dF = dZ . W   (only for a trainable backbone: HHI --nofreeze)
         GemmArgs m;
         m.M = d->B * Dk; m.N = Kk; m.K = d->H;
@@ -1022,12 +1031,23 @@ extern "C" int egot2_head_loss_bwd(const egot2_head_desc* d, const egot2_head_in
   }
   if (g->w) EGOT2_TRY(wgrad(d->dtype, rows, d->n_out, d->H, dl, ldl, 0, 0, saved->g, d->H, 0, 0, g->w, st));
   if (g->b) EGOT2_TRY(colsum_accum(EGOT2_F32, rows, d->n_out, dlogits, d->n_out, 0, 0, g->b, st));
+  const float ph = d->training ? d->p_head : 0.f;
+  // Wide heads (LTA: 20 x 593 classes) make dG = dlogits . W a long-K GEMM with a small output - 8 tiles for 148 SMs.  Without a
+  // head LayerNorm the next consumer wants fp32 anyway: split K and accumulate straight into `dpooled`.
+  if (d->dtype == EGOT2_BF16 && !d->use_ln && d->n_out >= 2048 && !env_is("EGOT2_HEAD_SPLITK", "0")) {
+    EGOT2_CUDA(cudaMemsetAsync(dpooled, 0, (size_t)rows * d->H * 4, st));
+    GemmArgs m; m.M = rows; m.N = d->H; m.K = d->n_out; m.A = dl; m.lda = ldl; m.B = in->w; m.ldb = d->H; m.trans_b = 0;
+    m.C = dpooled; m.ldc = d->H; m.in_dtype = d->dtype; m.out_dtype = EGOT2_F32; m.accumulate = 1;
+    m.split_k = suggest_split_k(m.M, m.N, m.K);
+    EGOT2_TRY(gemm(m, st));
+    EGOT2_TRY(dropout_inplace(EGOT2_F32, dpooled, (size_t)rows * d->H, ph, site_key(d->seed, SITE_HEAD, 0), st));
+    return pool_bwd(d->dtype, d->B, d->T, d->H, d->pool, d->row_tokens, dpooled, dx, st);
+  }
   {
     GemmArgs m; m.M = rows; m.N = d->H; m.K = d->n_out; m.A = dl; m.lda = ldl; m.B = in->w; m.ldb = d->H; m.trans_b = 0;
     m.C = dg; m.ldc = d->H; m.in_dtype = d->dtype; m.out_dtype = d->dtype;
     EGOT2_TRY(gemm(m, st));
   }
-  const float ph = d->training ? d->p_head : 0.f;
   EGOT2_TRY(dropout_inplace(d->dtype, dg, (size_t)rows * d->H, ph, site_key(d->seed, SITE_HEAD, 0), st));
   if (d->use_ln) {
     LayerNormBwdArgs l; l.rows = rows; l.H = d->H; l.dtype = d->dtype; l.x = saved->pooled; l.x_is_f32 = 1;

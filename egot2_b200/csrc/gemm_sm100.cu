@@ -740,7 +740,10 @@ int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
     const int rpg = a.a_rpg > 0 ? a.a_rpg : a.b_rpg;
     if ((a.a_rpg > 0 && a.b_rpg > 0 && a.a_rpg != a.b_rpg) || a.K % rpg) return -1;
     kg.on = 1;
-    const int dpad = rpg <= 16 ? 16 : (rpg <= 32 ? 32 : 64);
+    // rows per group padded to the next power of two (a divisor of the 64-row k-block); the padding rows are zero-filled by
+    // TMA.  (A floor of 16 here made the 2-token segments of the LTA translators walk 8x the k-blocks they needed.)
+    int dpad = 1;
+    while (dpad < rpg && dpad < 64) dpad <<= 1;
     kg.g = 64 / dpad;
     kg.dblocks = (rpg + 63) / 64;
     const int groups = a.K / rpg;
