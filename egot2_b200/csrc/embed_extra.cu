@@ -130,17 +130,30 @@ __global__ void __launch_bounds__(256) embed_finish_kernel(const EmbedSrc src, i
 // running side by side on three streams) meet in the shared arena and are left clean for the next step, one pass
 __global__ void __launch_bounds__(256) sum_into_clear_kernel(float* __restrict__ dst, float* __restrict__ a, float* __restrict__ b, size_t n4) {
   EGOT2_PDL_ENTER();
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 d = reinterpret_cast<float4*>(dst)[i];
-    const float4 x = reinterpret_cast<float4*>(a)[i];
-    d.x += x.x; d.y += x.y; d.z += x.z; d.w += x.w;
-    reinterpret_cast<float4*>(a)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b) {
-      const float4 y = reinterpret_cast<float4*>(b)[i];
-      d.x += y.x; d.y += y.y; d.z += y.z; d.w += y.w;
-      reinterpret_cast<float4*>(b)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // every thread owns 4 float4 per pass and requests all of its (up to 12) loads before the first store: written as
+  // load-store-load-store per element the pass ran at 1.2 TB/s (175 us for the 8.9 M parameters of the HHI EgoT2-g model)
+  for (size_t c = blockIdx.x; c * 1024 < n4; c += gridDim.x) {
+    const size_t i0 = c * 1024 + threadIdx.x;
+    float4 d[4], x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t i = i0 + (size_t)k * 256;
+      if (i < n4) {
+        d[k] = __ldcs(reinterpret_cast<const float4*>(dst) + i);
+        x[k] = __ldcs(reinterpret_cast<const float4*>(a) + i);
+        y[k] = b ? __ldcs(reinterpret_cast<const float4*>(b) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-    reinterpret_cast<float4*>(dst)[i] = d;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t i = i0 + (size_t)k * 256;
+      if (i < n4) {
+        d[k].x += x[k].x + y[k].x; d[k].y += x[k].y + y[k].y; d[k].z += x[k].z + y[k].z; d[k].w += x[k].w + y[k].w;
+        reinterpret_cast<float4*>(dst)[i] = d[k];
+        reinterpret_cast<float4*>(a)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b) reinterpret_cast<float4*>(b)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
   }
 }
 
@@ -167,7 +180,10 @@ int sum_into_clear(float* dst, float* a, float* b, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
   EGOT2_CHECK(dst && a && n % 4 == 0, "sum_into_clear: buffers / n %% 4");
   ProfScope prof(st, "sum_into_clear n%zu", n);
-  launch(sum_into_clear_kernel, dim3(ew_grid(n / 4)), dim3(256), 0, st, dst, a, b, n / 4);
+  // a pure streaming kernel (three reads, three writes per element): enough CTAs to keep every SM's load queue full
+  size_t ctas = (n / 4 + 1023) / 1024;
+  const size_t cap = (size_t)sm_count() * 8;
+  launch(sum_into_clear_kernel, dim3((unsigned)(ctas > cap ? cap : ctas)), dim3(256), 0, st, dst, a, b, n / 4);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

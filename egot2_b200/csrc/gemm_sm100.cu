@@ -757,6 +757,14 @@ int gemm_sm100(const GemmArgs& a, cudaStream_t st) {
   if (a.split_stride > 0 && (a.accumulate || a.out_dtype != EGOT2_F32 || a.relu || a.mask || a.p_drop > 0.f || a.residual)) return -1;
   // short-K problems are epilogue/store bound: 128-wide tiles run two CTAs per SM; long-K ones amortise A over 256 columns
   int bn = a.N <= 64 ? 64 : ((a.N <= 128 || a.K <= 512) ? 128 : ((a.N % 256 == 0 || a.N > 512) ? 256 : 128));
+  {
+    // few output tiles (the EgoT2-g branches: 16 .. 1800 token rows; LTA: 4096 rows x 512 columns): a long K loop on a
+    // handful of SMs is bound by what ONE SM can pull from L2, so narrower tiles on more SMs win although they re-read A
+    static const bool small_on = !(getenv("EGOT2_GEMM_BN_SMALL") && getenv("EGOT2_GEMM_BN_SMALL")[0] == '0');
+    const long long mt = (a.M + BM - 1) / BM;
+    if (small_on && !(a.accumulate && a.split_k > 1) && a.K >= 1024)
+      while (bn > 64 && mt * ((a.N + bn - 1) / bn) < sm_count() / 4) bn >>= 1;      // (at 64 tiles of 256 columns LTA is faster as is)
+  }
   if (a.accumulate && a.split_k > 1) {
     // split-K weight gradients with a small output: narrower tiles until the grid covers the SMs
     const long long mt = (a.M + BM - 1) / BM;
