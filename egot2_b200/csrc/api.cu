@@ -416,6 +416,28 @@ extern "C" int egot2_prof_report(char* buf, size_t buf_bytes) {
 
 // =============================================================================== embed stage
 namespace {
+// Which of the three streams (0 = the caller's, 1 / 2 = the side streams) runs segment k's projection: longest first onto the
+// least loaded stream, cost = in_dim x tokens.  (Round-robin put PNR's 256-wide LTA projection behind the 8192-wide OSCC one
+// while the stream of the 2048-wide one idled: the embedding stage ended 10 us later than its longest GEMM.)
+void seg_stream_plan(const egot2_embed_desc* d, int* idx) {
+  long long load[3] = {0, 0, 0};
+  bool done[EGOT2_MAX_SEG] = {};
+  for (int it = 0; it < d->n_seg; ++it) {
+    int best = -1;
+    long long bc = -1;
+    for (int k = 0; k < d->n_seg; ++k) {
+      if (done[k]) continue;
+      const long long c = d->seg_has_proj[k] ? (long long)d->seg_in_dim[k] * d->seg_tokens[k] : 1;
+      if (c > bc) { bc = c; best = k; }
+    }
+    int sidx = 0;
+    for (int j = 1; j < 3; ++j) if (load[j] < load[sidx]) sidx = j;
+    idx[best] = sidx;
+    load[sidx] += bc;
+    done[best] = true;
+  }
+}
+
 // Split-K projections into an fp32 accumulator + one finishing pass (embed_extra.cu) pay off when a projection is a long-K,
 // few-tile GEMM (HOI PNR / OSCC: 8192 -> 128 over clips x 16 rows = 32 output tiles for 148 SMs).
 bool embed_splitk(const egot2_embed_desc* d) {
@@ -520,6 +542,8 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   // fork BOTH side streams before anything of this stage is enqueued on `st`: a fork event recorded after segment 0's
   // launch would make the other segments wait for it (seen in the in-graph timeline: they started when it had finished)
   cudaStream_t side_st[2] = {st, st};
+  int seg_idx[EGOT2_MAX_SEG] = {};
+  seg_stream_plan(d, seg_idx);
   for (int i = 0; i < 2 && i + 1 < d->n_seg; ++i)
     if (sides[i]) { side_st[i] = side_fork(st, sides[i], 0); used[i] = side_st[i] != st; }
   // LayerNorm + token table (+ embedding dropout) inside the projection GEMMs' epilogue (H = 128: a tile holds whole rows):
@@ -531,7 +555,7 @@ extern "C" int egot2_embed_fwd(const egot2_embed_desc* d, const egot2_embed_in* 
   for (int k = 0; k < d->n_seg; ++k) {
     const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
     if (Dk == 0) continue;
-    cudaStream_t sk = k > 0 ? side_st[(k - 1) & 1] : st;
+    cudaStream_t sk = seg_idx[k] > 0 ? side_st[seg_idx[k] - 1] : st;
     char* zk = (char*)out->z + (size_t)d->seg_offset[k] * d->H * es;
     const void* feat = in->feat[k];
     if (splitk && !d->seg_has_proj[k]) {      // pass-through segment (LTA action features): the finishing pass reads it in place
@@ -654,6 +678,8 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   // fork BOTH side streams before anything of this stage is enqueued on `st`: a fork event recorded after segment 0's
   // launch would make the other segments wait for it (seen in the in-graph timeline: they started when it had finished)
   cudaStream_t side_st[2] = {st, st};
+  int seg_idx[EGOT2_MAX_SEG] = {};
+  seg_stream_plan(d, seg_idx);
   for (int i = 0; i < 2 && i + 1 < d->n_seg; ++i)
     if (sides[i]) { side_st[i] = side_fork(st, sides[i], 0); used[i] = side_st[i] != st; }
   int n_proj = 0, n_big = 0;
@@ -695,7 +721,7 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
   for (int k = 0; k < d->n_seg; ++k) {
     const int Dk = d->seg_tokens[k], Kk = d->seg_in_dim[k];
     if (Dk == 0) continue;
-    cudaStream_t sk = k > 0 ? side_st[(k - 1) & 1] : st;
+    cudaStream_t sk = seg_idx[k] > 0 ? side_st[seg_idx[k] - 1] : st;
     const char* dzk = (const char*)dz + (size_t)d->seg_offset[k] * d->H * es;
     if (d->seg_has_proj[k]) {
       const void* feat = in->feat[k];

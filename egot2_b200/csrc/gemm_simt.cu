@@ -7,6 +7,7 @@
 // memory, TMxTN outputs per thread, 256 threads.  Handles all four operand orientations, storage-row
 // remapping (segment scatter inside (B,T,H) tensors), the fused epilogue of ops.h and split-K
 // with fp32 atomics for the weight-gradient GEMMs (K = all tokens of the batch).
+#include <stdlib.h>
 #define EGOT2_FILE_ID 10
 #include "ops.h"
 
@@ -184,6 +185,65 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const GemmArgs a) {
   }
 }
 
+// ---------------------------------------------------------------- skinny problems (the 7-word vocabulary head of HHI EgoT2-g)
+// The register-tiled kernel above pays a 16-deep k-slab round trip per 16 k and a 64- or 128-wide tile whatever N is: 27 us
+// for (1200 x 256) . (256 x 7), 45-56 us for (1200 x 7) . (7 x 256).  Two direct kernels instead (bf16 operands only: the
+// fp32 parity mode keeps the summation order of the tiled kernel).
+// N <= 8, B stored (N, K): one warp per output row, lanes stride over k, warp-shuffle reduction.
+template <typename TO>
+__global__ void __launch_bounds__(256) gemm_skinny_n_kernel(const GemmArgs a) {
+  EGOT2_PDL_ENTER();
+  const int lane = threadIdx.x & 31, m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= a.M) return;
+  const bf16* __restrict__ A = (const bf16*)a.A + (size_t)m * a.lda;
+  const bf16* __restrict__ B = (const bf16*)a.B;
+  float acc[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+  for (int k = lane; k < a.K; k += 32) {
+    const float x = to_f32(A[k]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n < a.N) acc[n] = fmaf(x, to_f32(B[(size_t)n * a.ldb + k]), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = warp_sum(acc[n]);
+  if (lane < a.N) {
+    float v = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v = lane == n ? acc[n] : v;
+    if (a.bias) v += a.bias[lane];
+    ((TO*)a.C)[(size_t)m * a.ldc + lane] = from_f32<TO>(v);
+  }
+}
+// K <= 8, B stored (K, N): one thread per output element, k ascending (the tiled kernel's order).
+template <typename TO>
+__global__ void __launch_bounds__(256) gemm_skinny_k_kernel(const GemmArgs a) {
+  EGOT2_PDL_ENTER();
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)a.M * a.N) return;
+  const int m = (int)(idx / a.N), n = (int)(idx % a.N);
+  const bf16* __restrict__ A = (const bf16*)a.A + (size_t)m * a.lda;
+  const bf16* __restrict__ B = (const bf16*)a.B + n;
+  float v = 0.f;
+  for (int k = 0; k < a.K; ++k) v = fmaf(to_f32(A[k]), to_f32(B[(size_t)k * a.ldb]), v);
+  if (a.bias) v += a.bias[n];
+  ((TO*)a.C)[(size_t)m * a.ldc + n] = from_f32<TO>(v);
+}
+
+template <typename TO>
+int launch_skinny(const GemmArgs& a, cudaStream_t st) {
+  if (a.N <= 8 && a.trans_b) {
+    ProfScope prof(st, "gemm_skinny_n M%d N%d K%d", a.M, a.N, a.K);
+    launch(gemm_skinny_n_kernel<TO>, dim3((a.M + 7) / 8), dim3(256), 0, st, a);
+  } else {
+    ProfScope prof(st, "gemm_skinny_k M%d N%d K%d", a.M, a.N, a.K);
+    launch(gemm_skinny_k_kernel<TO>, dim3((unsigned)(((long long)a.M * a.N + 255) / 256)), dim3(256), 0, st, a);
+  }
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename TI, typename TO>
 int launch(const GemmArgs& a, cudaStream_t st) {
   const bool small = (a.M <= 64 || a.N <= 64);
@@ -207,6 +267,11 @@ int gemm_simt(const GemmArgs& a, cudaStream_t st) {
   EGOT2_CHECK(!(a.accumulate && a.out_dtype != EGOT2_F32), "gemm: accumulate needs fp32 C");
   EGOT2_CHECK(a.split_k == 1 || (a.accumulate && !a.relu && !a.mask && a.p_drop == 0.f),
               "gemm: split-K only for plain accumulating GEMMs");
+  const bool plain = !a.trans_a && !a.relu && !a.mask && a.p_drop <= 0.f && !a.residual && !a.accumulate && a.split_k <= 1 &&
+                     a.split_stride == 0 && !a.a_rpg && !a.b_rpg && !a.c_rpg && !a.trans_c;
+  static const bool skinny_on = !(getenv("EGOT2_GEMM_SKINNY") && getenv("EGOT2_GEMM_SKINNY")[0] == '0');
+  if (skinny_on && plain && a.in_dtype == EGOT2_BF16 && ((a.N <= 8 && a.trans_b) || (a.K <= 8 && !a.trans_b)))
+    return a.out_dtype == EGOT2_F32 ? launch_skinny<float>(a, st) : launch_skinny<bf16>(a, st);
   if (a.in_dtype == EGOT2_F32 && a.out_dtype == EGOT2_F32) return launch<float, float>(a, st);
   if (a.in_dtype == EGOT2_BF16 && a.out_dtype == EGOT2_BF16) return launch<bf16, bf16>(a, st);
   if (a.in_dtype == EGOT2_BF16 && a.out_dtype == EGOT2_F32) return launch<bf16, float>(a, st);
