@@ -333,7 +333,7 @@ extern "C" const char* egot2_last_error(void) { return g_err; }
 extern "C" int egot2_sm_count(void) { return sm_count(); }
 extern "C" uint64_t egot2_launch_count(void) { return g_launch_count; }
 
-// EGOT2_TIMELINE builds: device buffer of 1 + 2*2000 u64 ([0] = count, then (globaltimer ns, file*100000+line) pairs); NULL = off
+// EGOT2_TIMELINE builds: device buffer of 1 + 2*4000 u64 ([0] = count, then (globaltimer ns, file*100000+line) pairs); NULL = off
 extern "C" int egot2_timeline_set(void* dev_buf) {
 #ifdef EGOT2_TIMELINE
   for (int i = 0; i < g_tl_n; ++i) g_tl_setters[i]((unsigned long long*)dev_buf);

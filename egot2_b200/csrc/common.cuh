@@ -71,7 +71,7 @@ __device__ __forceinline__ void tl_stamp(unsigned loc) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     const unsigned i = atomicAdd(reinterpret_cast<unsigned*>(tl_buf_dev), 1u);
-    if (i < 2000) { tl_buf_dev[1 + 2 * i] = t; tl_buf_dev[2 + 2 * i] = loc; }
+    if (i < 4000) { tl_buf_dev[1 + 2 * i] = t; tl_buf_dev[2 + 2 * i] = loc; }
   }
 }
 #define EGOT2_TL(id) ::egot2::tl_stamp((unsigned)(id) * 100000u + (unsigned)__LINE__)

@@ -179,11 +179,11 @@ extern "C" int egot2_decoder_layer_bwd(const egot2_decoder_desc* d, const egot2_
     LayerNormBwdArgs l; l.rows = R; l.H = H; l.dtype = dt; l.x = s->y3; l.stat = s->stat3; l.g = p->norm3_g;
     l.dy = dy_out; l.dx = w.d1; l.dg = g->norm3_g; l.db = g->norm3_b;
     if (pd > 0.f) { l.dx2 = w.dm; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DEC_DROP3, L); dm = w.dm; }
+    l.dcol = g->lin2_b;            // db2 = colsum(dm) comes out of the same pass (as in the encoder layer)
     EGOT2_TRY(layernorm_bwd(l, st));
   }
   // ---- feed-forward
   EGOT2_TRY(wgrad2(dt, R, H, FF, dm, H, s->hid, FF, g->lin2_w, st));
-  EGOT2_TRY(colsum_accum(dt, R, H, dm, H, 0, 0, g->lin2_b, st));
   EGOT2_TRY(dgrad(dt, R, H, FF, dm, H, p->lin2_w, FF, w.dhid, FF, st, nullptr, s->hid, inv_keep));
   EGOT2_TRY(wgrad2(dt, R, FF, H, w.dhid, FF, s->x2, H, g->lin1_w, st));
   EGOT2_TRY(colsum_accum(dt, R, FF, w.dhid, FF, 0, 0, g->lin1_b, st));
@@ -194,14 +194,14 @@ extern "C" int egot2_decoder_layer_bwd(const egot2_decoder_desc* d, const egot2_
     LayerNormBwdArgs l; l.rows = R; l.H = H; l.dtype = dt; l.x = s->y2; l.stat = s->stat2; l.g = p->norm2_g;
     l.dy = w.d2; l.dx = w.d1; l.dg = g->norm2_g; l.db = g->norm2_b;
     if (pd > 0.f) { l.dx2 = w.dm; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DEC_DROP2, L); dm = w.dm; }
+    l.dcol = g->ca_out_b;
     EGOT2_TRY(layernorm_bwd(l, st));
   }
   // ---- cross-attention
   EGOT2_TRY(wgrad2(dt, R, H, H, dm, H, s->a2, H, g->ca_out_w, st));
-  EGOT2_TRY(colsum_accum(dt, R, H, dm, H, 0, 0, g->ca_out_b, st));
   EGOT2_TRY(dgrad(dt, R, H, H, dm, H, p->ca_out_w, H, w.da, H, st));                    // da = dL/da2
-  EGOT2_TRY(zero_f32(w.dq32, (size_t)R * H, st));
-  EGOT2_TRY(zero_f32(w.dkv32, (size_t)d->mem_rows * 2 * H, st));
+  // the three fp32 attention-gradient buffers are consecutive in the workspace: ONE clear for all of them
+  EGOT2_TRY(zero_f32(w.dq32, (size_t)((w.dqkv32 + (size_t)R * 3 * H) - w.dq32), st));
   {
     SmallAttnArgs a; a.dtype = dt; a.rows = d->rows; a.S = d->S; a.M = d->M; a.H = H; a.heads = d->heads; a.causal = 0;
     a.q = s->qc; a.ldq = H; a.k = s->kvc; a.v = (const char*)s->kvc + (size_t)H * es; a.ldkv = 2 * H;
@@ -211,16 +211,17 @@ extern "C" int egot2_decoder_layer_bwd(const egot2_decoder_desc* d, const egot2_
     EGOT2_TRY(small_attn_bwd(a, st));
   }
   const void* dq = w.dq32; const void* dkv = w.dkv32;
-  if (dt != EGOT2_F32) {
-    EGOT2_TRY(cast_f32_to(dt, w.dq32, w.dq_lp, (size_t)R * H, st));
-    EGOT2_TRY(cast_f32_to(dt, w.dkv32, w.dkv_lp, (size_t)d->mem_rows * 2 * H, st));
+  if (dt != EGOT2_F32) {       // bf16 copies for the GEMMs and the in_proj bias gradients (column sums) in the same pass
+    EGOT2_TRY(colsum_cast_bf16(R, H, w.dq32, H, w.dq_lp, H, g->ca_in_b, st));
+    EGOT2_TRY(colsum_cast_bf16(d->mem_rows, 2 * H, w.dkv32, 2 * H, w.dkv_lp, 2 * H, g->ca_in_b + H, st));
     dq = w.dq_lp; dkv = w.dkv_lp;
+  } else {
+    EGOT2_TRY(colsum_accum(EGOT2_F32, R, H, w.dq32, H, 0, 0, g->ca_in_b, st));
+    EGOT2_TRY(colsum_accum(EGOT2_F32, d->mem_rows, 2 * H, w.dkv32, 2 * H, 0, 0, g->ca_in_b + H, st));
   }
   //   in_proj rows [0,H): queries (input x1) ; rows [H,3H): keys|values (input mem)
   EGOT2_TRY(wgrad2(dt, R, H, H, dq, H, s->x1, H, g->ca_in_w, st));
-  EGOT2_TRY(colsum_accum(EGOT2_F32, R, H, w.dq32, H, 0, 0, g->ca_in_b, st));
   EGOT2_TRY(wgrad2(dt, d->mem_rows, 2 * H, H, dkv, 2 * H, mem, H, g->ca_in_w + (size_t)H * H, st));
-  EGOT2_TRY(colsum_accum(EGOT2_F32, d->mem_rows, 2 * H, w.dkv32, 2 * H, 0, 0, g->ca_in_b + H, st));
   if (dmem) {   // dmem += dkv . Wkv   (fp32, accumulated over the decoder layers)
     GemmArgs m; m.M = d->mem_rows; m.N = H; m.K = 2 * H; m.A = dkv; m.lda = 2 * H;
     m.B = (const char*)p->ca_in_w + (size_t)H * H * es; m.ldb = H; m.trans_b = 0; m.C = dmem; m.ldc = H;
@@ -234,13 +235,12 @@ extern "C" int egot2_decoder_layer_bwd(const egot2_decoder_desc* d, const egot2_
     LayerNormBwdArgs l; l.rows = R; l.H = H; l.dtype = dt; l.x = s->y1; l.stat = s->stat1; l.g = p->norm1_g;
     l.dy = w.d2; l.dx = w.d1; l.dg = g->norm1_g; l.db = g->norm1_b;
     if (pd > 0.f) { l.dx2 = w.dm; l.dx2_p_drop = pd; l.dx2_drop_key = site_key(d->seed, SITE_DEC_DROP1, L); dm = w.dm; }
+    l.dcol = g->sa_out_b;
     EGOT2_TRY(layernorm_bwd(l, st));
   }
   // ---- self-attention
   EGOT2_TRY(wgrad2(dt, R, H, H, dm, H, s->a1, H, g->sa_out_w, st));
-  EGOT2_TRY(colsum_accum(dt, R, H, dm, H, 0, 0, g->sa_out_b, st));
   EGOT2_TRY(dgrad(dt, R, H, H, dm, H, p->sa_out_w, H, w.da, H, st));
-  EGOT2_TRY(zero_f32(w.dqkv32, (size_t)R * 3 * H, st));
   {
     SmallAttnArgs a; a.dtype = dt; a.rows = d->rows; a.S = d->S; a.M = d->S; a.H = H; a.heads = d->heads; a.causal = 1;
     a.q = s->qkv; a.ldq = 3 * H; a.k = (const char*)s->qkv + (size_t)H * es; a.v = (const char*)s->qkv + (size_t)2 * H * es;
@@ -250,9 +250,9 @@ extern "C" int egot2_decoder_layer_bwd(const egot2_decoder_desc* d, const egot2_
     EGOT2_TRY(small_attn_bwd(a, st));
   }
   const void* dqkv = w.dqkv32;
-  if (dt != EGOT2_F32) { EGOT2_TRY(cast_f32_to(dt, w.dqkv32, w.dqkv_lp, (size_t)R * 3 * H, st)); dqkv = w.dqkv_lp; }
+  if (dt != EGOT2_F32) { EGOT2_TRY(colsum_cast_bf16(R, 3 * H, w.dqkv32, 3 * H, w.dqkv_lp, 3 * H, g->sa_in_b, st)); dqkv = w.dqkv_lp; }
+  else EGOT2_TRY(colsum_accum(EGOT2_F32, R, 3 * H, w.dqkv32, 3 * H, 0, 0, g->sa_in_b, st));
   EGOT2_TRY(wgrad2(dt, R, 3 * H, H, dqkv, 3 * H, y_in, H, g->sa_in_w, st));
-  EGOT2_TRY(colsum_accum(EGOT2_F32, R, 3 * H, w.dqkv32, 3 * H, 0, 0, g->sa_in_b, st));
   EGOT2_TRY(dgrad(dt, R, 3 * H, H, dqkv, 3 * H, p->sa_in_w, H, dy_in, H, st, w.d1));
   return 0;
 }

@@ -128,6 +128,7 @@ int table_grad(int dtype, int B, int T, int H, const void* dy, float* dtable, co
                cudaStream_t st);
 // column sums: out[n] += sum_m x[m,n]   (bias gradients)
 int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int gstride, float* out, cudaStream_t st);
+int colsum_cast_bf16(int M, int N, const float* x, int ldx, void* y, int ldy, float* out, cudaStream_t st);   // y = bf16(x), out += colsum(x)
 // in-place x *= dropmask/(1-p) over n elements (idx = linear element index)
 int dropout_inplace(int dtype, void* x, size_t n, float p, uint64_t key, cudaStream_t st);
 // pooled[b,:] = mean_t x[b,t,:]   or gather of the first row_tokens tokens (pool==0)

@@ -219,6 +219,46 @@ __global__ void colsum_kernel(int M, int N, const T* __restrict__ x, int ldx, in
   }
 }
 
+// fp32 (M, N) -> bf16 copy AND column sums in one pass (the decoder's attention gradients arrive in fp32 because several
+// queries add into the same key rows; the GEMMs behind them want bf16, the bias gradient wants the column sums): N even,
+// both row pitches even.  Same block shape and summation order as colsum_kernel<float>.
+__global__ void colsum_cast_kernel(int M, int N, const float* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
+                                   float* __restrict__ out, int rows_per_cta) {
+  EGOT2_PDL_ENTER();
+  const int n = (blockIdx.x * 32 + threadIdx.x) * 2;
+  const int mbeg = blockIdx.y * rows_per_cta, mend = min(M, mbeg + rows_per_cta);
+  float s0 = 0.f, s1 = 0.f;
+  if (n < N) {
+    for (int mb = mbeg + threadIdx.y; mb < mend; mb += 32) {
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int m = mb + 8 * u;
+        v[u] = make_float2(0.f, 0.f);
+        if (m < mend) {
+          v[u] = *reinterpret_cast<const float2*>(x + (size_t)m * ldx + n);
+          *reinterpret_cast<__nv_bfloat162*>(y + (size_t)m * ldy + n) = __floats2bfloat162_rn(v[u].x, v[u].y);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s0 += v[u].x; s1 += v[u].y; }
+    }
+  }
+  __shared__ float red[8][65];
+  red[threadIdx.y][2 * threadIdx.x] = s0;
+  red[threadIdx.y][2 * threadIdx.x + 1] = s1;
+  __syncthreads();
+  if (threadIdx.y < 2) {
+    const int c = 2 * threadIdx.x + threadIdx.y, nn = blockIdx.x * 64 + c;
+    if (nn < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][c];
+      atomicAdd(out + nn, t);
+    }
+  }
+}
+
 // bf16 fast path: 128-bit loads, CW = 8 * lanes_per_row columns per CTA (N % 8 == 0, 16 B-aligned rows)
 __global__ void __launch_bounds__(256) colsum_bf16_vec_kernel(int M, int N, const bf16* __restrict__ x, int ldx, int rpg,
                                                               int gstride, float* __restrict__ out, int rows_per_cta,
@@ -840,6 +880,22 @@ int colsum_accum(int dtype, int M, int N, const void* x, int ldx, int rpg, int g
   ProfScope prof(st, "colsum M%d N%d", M, N);
   if (dtype == EGOT2_F32) launch(colsum_kernel<float>, dim3(grid), dim3(block), 0, st, M, N, (const float*)x, ldx, rpg, gstride, out, rows_per_cta);
   else launch(colsum_kernel<bf16>, dim3(grid), dim3(block), 0, st, M, N, (const bf16*)x, ldx, rpg, gstride, out, rows_per_cta);
+  EGOT2_LAUNCH_CHECK();
+  return 0;
+}
+
+// y (bf16) = x (fp32) and out += column sums of x, one launch
+int colsum_cast_bf16(int M, int N, const float* x, int ldx, void* y, int ldy, float* out, cudaStream_t st) {
+  if (M == 0 || N == 0) return 0;
+  EGOT2_CHECK((N & 1) == 0 && (ldx & 1) == 0 && (ldy & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
+              (reinterpret_cast<uintptr_t>(y) & 3) == 0, "colsum_cast: N and the row pitches must be even");
+  const int col_blocks = (N + 63) / 64;
+  int row_blocks = (sm_count() * 8 + col_blocks - 1) / col_blocks;
+  int rows_per_cta = (M + row_blocks - 1) / row_blocks;
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  row_blocks = (M + rows_per_cta - 1) / rows_per_cta;
+  ProfScope prof(st, "colsum_cast M%d N%d", M, N);
+  launch(colsum_cast_kernel, dim3(col_blocks, row_blocks), dim3(32, 8), 0, st, M, N, x, ldx, (bf16*)y, ldy, out, rows_per_cta);
   EGOT2_LAUNCH_CHECK();
   return 0;
 }

@@ -45,19 +45,17 @@ def main():
     ap.add_argument("--workload", default="hhi_ttm3_train_b256")
     ap.add_argument("--replays", type=int, default=3)
     args = ap.parse_args()
-    wl = bench.WORKLOADS[args.workload]
+    wl = dict(bench.WORKLOADS[args.workload])
     spec = wl["spec"]()
-    B, seg = wl["batch"], wl["seg_tokens"]
     dev = torch.device("cuda:0")
-    tr = TranslatorTrainer(spec, dev, "bf16", use_graphs=True)
-    tr.load_state_dict(synth.make_state_dict(spec, 0))
-    f = synth.make_features(spec, B, seg, seed=0, dtype=torch.bfloat16)
-    feats = [f[s.name].to(dev) for s in spec.segments]
-    labels = synth.make_labels(spec, B, seg, seed=0).to(dev)
+    torch.cuda.set_device(dev)
+    tr = bench.build_trainer(args.workload, wl, spec, dev, "bf16", use_graphs=True)      # any workload, incl. the EgoT2-g trainers
+    pool, _ = bench.build_pool(wl, spec, wl["batch"], dev, "bf16", 0, max_pool=1)
+    feats, labels = pool[0]
     for _ in range(4):
         tr.train_step(feats, labels, graph_key=0)
     torch.cuda.synchronize()
-    buf = torch.zeros(1 + 2 * 2000, device=dev, dtype=torch.int64)
+    buf = torch.zeros(1 + 2 * 4000, device=dev, dtype=torch.int64)
     L.call("egot2_timeline_set", buf.data_ptr())
     for r in range(args.replays):
         buf.zero_()
@@ -65,7 +63,7 @@ def main():
         tr.train_step(feats, labels, graph_key=0)
         torch.cuda.synchronize()
         h = buf.cpu().tolist()
-        n = min(h[0] & 0xffffffff, 2000)
+        n = min(h[0] & 0xffffffff, 4000)
         ev = sorted((h[1 + 2 * i], h[2 + 2 * i]) for i in range(n))
         if r < args.replays - 1:
             continue
