@@ -139,6 +139,13 @@ def test_pnr2_feature_dropout_hits_only_the_pnr_tokens():
     kept = z1[:, :16] != 0
     assert torch.allclose(z1[:, :16][kept], 2.0 * z_eval[:, :16][kept], rtol=1e-5, atol=1e-6)       # kept values scaled by 1/(1-p)
     assert torch.equal(z1[:, 16:], z_eval[:, 16:])
+    # ... and the mask is exactly the documented generator (csrc/common.cuh drop_keep): at p == 0.5 every elementwise site
+    # takes ONE random bit per element - bit idx % 32 of the hash of idx / 32 - with idx the flat (clip, token, column) index
+    import test_gpu_parity as tg
+    B, T, H = z1.shape
+    want = tg.dropout_mask_oracle(11, 1, 0, B * T * H, 0.5).reshape(B, T, H)[:, :16] != 0          # SITE_FEAT = 1
+    live = z_eval[:, :16] != 0                      # an exactly-zero projection says nothing about its mask bit
+    assert torch.equal(kept.cpu()[live.cpu()], want[live.cpu()])
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
