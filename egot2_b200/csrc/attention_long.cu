@@ -172,10 +172,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) attn_long_fwd_kernel(int T, in
           e2 = (k1 & 1u) ? e2 : 0.f; e3 = (k1 & 2u) ? e3 : 0.f;
         } else if (MODE == 2) {
           const int c = k32 * 32 + nt * 8 + 2 * (lane & 3);
-          e0 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q0, T, c, p_drop, inv_keep);
-          e1 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q0, T, c + 1, p_drop, inv_keep);
-          e2 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q1, T, c, p_drop, inv_keep);
-          e3 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q1, T, c + 1, p_drop, inv_keep);
+          attn_drop_scale2(drop_key ^ egot2_ep, (uint64_t)bh * T + q0, T, c, p_drop, inv_keep, e0, e1);
+          attn_drop_scale2(drop_key ^ egot2_ep, (uint64_t)bh * T + q1, T, c, p_drop, inv_keep, e2, e3);
         }
         p[nt >> 1][(nt & 1) * 2] = pack_bf16(e0, e1);
         p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(e2, e3);
@@ -286,10 +284,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) attn_long_bwd_kernel(int T, in
             g0 = (k0 & 1u) ? g0 + g0 : 0.f; g1 = (k0 & 2u) ? g1 + g1 : 0.f;
             g2 = (k1 & 1u) ? g2 + g2 : 0.f; g3 = (k1 & 2u) ? g3 + g3 : 0.f;
           } else if (MODE == 2) {
-            g0 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + ra, T, c, p_drop, inv_keep);
-            g1 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + ra, T, c + 1, p_drop, inv_keep);
-            g2 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + rb, T, c, p_drop, inv_keep);
-            g3 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + rb, T, c + 1, p_drop, inv_keep);
+            attn_drop_scale2(drop_key ^ egot2_ep, (uint64_t)bh * T + ra, T, c, p_drop, inv_keep, g0, g1);
+            attn_drop_scale2(drop_key ^ egot2_ep, (uint64_t)bh * T + rb, T, c, p_drop, inv_keep, g2, g3);
           }
           ds[h2 * 2] = pack_bf16(p0 * (g0 - da), p1 * (g1 - da));
           ds[h2 * 2 + 1] = pack_bf16(p2 * (g2 - db), p3 * (g3 - db));

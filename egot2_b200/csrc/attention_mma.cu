@@ -224,10 +224,8 @@ attn_mma_fwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv, bf16*
       e2 = (m1 & 1u) ? e2 : 0.f; e3 = (m1 & 2u) ? e3 : 0.f;
     } else if (MODE == 2) {
       const int c = nt * 8 + 2 * (lane & 3);
-      e0 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q0, T, c, p_drop, inv_keep);
-      e1 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q0, T, c + 1, p_drop, inv_keep);
-      e2 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q1, T, c, p_drop, inv_keep);
-      e3 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + q1, T, c + 1, p_drop, inv_keep);
+      attn_drop_scale2(drop_key ^ egot2_ep, (uint64_t)bh * T + q0, T, c, p_drop, inv_keep, e0, e1);
+      attn_drop_scale2(drop_key ^ egot2_ep, (uint64_t)bh * T + q1, T, c, p_drop, inv_keep, e2, e3);
     }
     p[nt >> 1][(nt & 1) * 2] = pack_bf16(e0, e1);
     p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(e2, e3);
@@ -353,10 +351,8 @@ attn_mma_bwd_kernel(int T, int H, int heads, const bf16* __restrict__ qkv, const
           g2 = (m1 & 1u) ? g2 + g2 : 0.f; g3 = (m1 & 2u) ? g3 + g3 : 0.f;
         } else if (MODE == 2) {
           const int c = kb * 16 + h2 * 8 + 2 * (lane & 3);
-          g0 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + ra, T, c, p_drop, inv_keep);
-          g1 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + ra, T, c + 1, p_drop, inv_keep);
-          g2 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + rb, T, c, p_drop, inv_keep);
-          g3 *= attn_drop_scale(drop_key ^ egot2_ep, (uint64_t)bh * T + rb, T, c + 1, p_drop, inv_keep);
+          attn_drop_scale2(drop_key ^ egot2_ep, (uint64_t)bh * T + ra, T, c, p_drop, inv_keep, g0, g1);
+          attn_drop_scale2(drop_key ^ egot2_ep, (uint64_t)bh * T + rb, T, c, p_drop, inv_keep, g2, g3);
         }
         ds[h2 * 2] = pack_bf16(p0 * (g0 - da), p1 * (g1 - da));
         ds[h2 * 2 + 1] = pack_bf16(p2 * (g2 - db), p3 * (g3 - db));

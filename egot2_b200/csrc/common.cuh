@@ -207,12 +207,18 @@ __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
 //   elementwise dropout site, so a thread that owns an aligned run of elements pays one hash per run (drop_scale_n below)
 //   instead of one per element: the per-element hash was the larger half of the out-projection epilogue and of the
 //   LayerNorm-backward / FFN final epilogues in training.
-//   other p: drop_bits(key, idx) >= p * 2^32, one hash per element.
-// (bit_mode is kept for source compatibility; the p == 0.5 rule no longer depends on it.)
+//   other p: a 16-bit field per element - half idx%2 of the hash of idx/2 - compared with round(p * 2^16): one hash per TWO
+//   elements (p is honoured to 2^-16: 0.1 becomes 0.100006).
+// (thr and bit_mode are kept for source compatibility; neither rule depends on them any more.)
+__host__ __device__ __forceinline__ uint32_t drop_threshold16(float p) {
+  const float t = p * 65536.0f;
+  return t >= 65535.0f ? 65535u : (uint32_t)(t + 0.5f);
+}
+__host__ __device__ __forceinline__ uint32_t drop_field16(uint32_t h, uint32_t odd) { return odd ? (h >> 16) : (h & 0xffffu); }
 __host__ __device__ __forceinline__ bool drop_keep(uint64_t key, uint64_t idx, float p, uint32_t thr, bool bit_mode = false) {
-  (void)bit_mode;
+  (void)bit_mode; (void)thr;
   if (p == 0.5f) return (drop_bits(key, idx >> 5) >> (uint32_t)(idx & 31)) & 1u;
-  return drop_bits(key, idx) >= thr;
+  return drop_field16(drop_bits(key, idx >> 1), (uint32_t)(idx & 1)) >= drop_threshold16(p);
 }
 // keep bits of the aligned word that holds element idx (p == 0.5 rule), shifted so that bit i belongs to element idx + i;
 // valid for the elements up to the next multiple of 32
@@ -222,12 +228,27 @@ __host__ __device__ __forceinline__ uint32_t drop_word(uint64_t key, uint64_t id
 // Attention-probability dropout for one (query row, key) pair; row = (b*heads + h)*T + query.
 // p == 0.5 (the HHI default) takes ONE random bit per pair: bit key%32 of the hash of (row * ceil(T/32) + key/32), so a
 // thread that owns several keys of one query row pays one hash per 32 keys (attention_mma.cu); other p: one hash per pair.
+// other p: the 16-bit field key%2 of the hash of (row * ceil(T/2) + key/2): the two adjacent keys of an mma accumulator pair
+// share one hash.
 __host__ __device__ __forceinline__ bool attn_drop_keep(uint64_t key, uint64_t row, int T, int c, float p, uint32_t thr) {
+  (void)thr;
   if (p == 0.5f) return (drop_bits(key, row * (uint64_t)((T + 31) >> 5) + (uint32_t)(c >> 5)) >> (c & 31)) & 1u;
-  return drop_bits(key, row * (uint64_t)T + (uint32_t)c) >= thr;
+  return drop_field16(drop_bits(key, row * (uint64_t)((T + 1) >> 1) + (uint32_t)(c >> 1)), (uint32_t)(c & 1)) >= drop_threshold16(p);
 }
 __device__ __forceinline__ float attn_drop_scale(uint64_t key, uint64_t row, int T, int c, float p, float inv_keep) {
   return attn_drop_keep(key, row, T, c, p, drop_threshold(p)) ? inv_keep : 0.0f;
+}
+// the two adjacent keys c (EVEN) and c + 1 of one query row - an mma accumulator pair - with one hash (general p; the p == 0.5
+// kernels read whole keep words instead): a *= multiplier(c), b *= multiplier(c + 1), the same decisions as attn_drop_scale
+__device__ __forceinline__ void attn_drop_scale2(uint64_t key, uint64_t row, int T, int c, float p, float inv_keep, float& a, float& b) {
+  if (p == 0.5f) {
+    a *= attn_drop_scale(key, row, T, c, p, inv_keep);
+    b *= attn_drop_scale(key, row, T, c + 1, p, inv_keep);
+    return;
+  }
+  const uint32_t h = drop_bits(key, row * (uint64_t)((T + 1) >> 1) + (uint32_t)(c >> 1)), thr = drop_threshold16(p);
+  a = (h & 0xffffu) >= thr ? a * inv_keep : 0.0f;
+  b = (h >> 16) >= thr ? b * inv_keep : 0.0f;
 }
 // returns the multiplier: 0 if dropped, 1/(1-p) if kept
 __device__ __forceinline__ float drop_scale(uint64_t key, uint64_t idx, float p, float inv_keep, bool bit_mode = false) {
@@ -242,10 +263,16 @@ __device__ __forceinline__ void drop_scale_n(uint64_t key, uint64_t idx0, float 
     const uint32_t w = drop_word(key, idx0);
 #pragma unroll
     for (int i = 0; i < N; ++i) m[i] = (w >> i) & 1u ? inv_keep : 0.0f;
-  } else {
-    const uint32_t thr = drop_threshold(p);
+  } else if constexpr ((N & 1) == 0) {       // idx0 is even: elements 2i, 2i+1 are the two halves of one hash
+    const uint32_t thr = drop_threshold16(p);
 #pragma unroll
-    for (int i = 0; i < N; ++i) m[i] = drop_bits(key, idx0 + i) >= thr ? inv_keep : 0.0f;
+    for (int i = 0; i < N; i += 2) {
+      const uint32_t h = drop_bits(key, (idx0 + i) >> 1);
+      m[i] = (h & 0xffffu) >= thr ? inv_keep : 0.0f;
+      m[i + 1] = (h >> 16) >= thr ? inv_keep : 0.0f;
+    }
+  } else {
+    m[0] = drop_keep(key, idx0, p, 0u) ? inv_keep : 0.0f;
   }
 }
 

@@ -448,7 +448,7 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const bool row_ok = m < a.M;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-    const uint32_t thr = drop_threshold(a.p_drop);
+    const uint32_t thr16 = drop_threshold16(a.p_drop);
     const uint32_t a1_empty_ldr = mapa(a1_empty, 0), h_full_ldr = mapa(h_full, 0);
     // backward: the ReLU/dropout gate bits of chunk c+1 are fetched while chunk c is processed (a dependent global
     // load in front of every chunk's arithmetic was ~1 us of exposed latency per chunk)
@@ -535,9 +535,13 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if constexpr (DROP == 1) {
             keep = drop_bits(a.key_ffn ^ egot2_ep, idx0 >> 5);
           } else if constexpr (DROP == 2) {
-            keep = 0;
+            keep = 0;             // general p: a 16-bit field per element, two elements per hash (common.cuh drop_keep)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) keep |= (drop_bits(a.key_ffn ^ egot2_ep, idx0 + j) >= thr ? 1u : 0u) << j;
+            for (int j = 0; j < 32; j += 2) {
+              const uint32_t hh = drop_bits(a.key_ffn ^ egot2_ep, (idx0 + j) >> 1);
+              keep |= ((hh & 0xffffu) >= thr16 ? 1u : 0u) << j;
+              keep |= ((hh >> 16) >= thr16 ? 1u : 0u) << (j + 1);
+            }
           } else {
             keep = 0xFFFFFFFFu;
           }
@@ -740,9 +744,10 @@ ffn_sm100_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if constexpr (DROP == 1) {          // p == 0.5: this thread's CW columns share one keep word (nb % 32 == 0)
             v0 = (keep2 >> j) & 1u ? v0 * inv_keep : 0.f;
             v1 = (keep2 >> (j + 1)) & 1u ? v1 * inv_keep : 0.f;
-          } else if constexpr (DROP == 2) {
-            v0 = drop_bits(a.key_drop2 ^ egot2_ep, (uint64_t)m * H + nb + j) >= thr ? v0 * inv_keep : 0.f;
-            v1 = drop_bits(a.key_drop2 ^ egot2_ep, (uint64_t)m * H + nb + j + 1) >= thr ? v1 * inv_keep : 0.f;
+          } else if constexpr (DROP == 2) {       // columns j, j + 1 (j even) are the two halves of one hash
+            const uint32_t hh = drop_bits(a.key_drop2 ^ egot2_ep, ((uint64_t)m * H + nb + j) >> 1);
+            v0 = (hh & 0xffffu) >= thr16 ? v0 * inv_keep : 0.f;
+            v1 = (hh >> 16) >= thr16 ? v1 * inv_keep : 0.f;
           }
           v0 += __uint_as_float(w[k] << 16);
           v1 += __uint_as_float(w[k] & 0xffff0000u);

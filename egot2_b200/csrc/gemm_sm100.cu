@@ -382,6 +382,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
               const uint32_t kw = drop_word(e.drop_key ^ egot2_ep, idx0);
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = (kw >> j) & 1u ? v[j] * inv_keep : 0.f;
+            } else if (e.p_drop != 0.5f && (idx0 & 1) == 0) {      // general p: two columns per hash
+              float dm[32];
+              drop_scale_n<32>(e.drop_key ^ egot2_ep, idx0, e.p_drop, inv_keep, dm);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= dm[j];
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] *= drop_scale(e.drop_key ^ egot2_ep, idx0 + j, e.p_drop, inv_keep);

@@ -268,17 +268,25 @@ def dropout_mask_oracle(seed, site, layer, n, p, bit_mode=False, raw_bits=False)
             return bits(key, idx)
         if p == 0.5:      # every elementwise site at p == 0.5: one random bit per element (bit idx%32 of the hash of idx/32)
             keep = ((bits(key, idx >> np.uint64(5)) >> (idx & np.uint64(31))) & np.uint64(1)) == 1
-        else:
-            thr = np.uint64(int(np.float32(p) * np.float32(4294967296.0) + np.float32(0.5)))
-            keep = bits(key, idx) >= thr
+        else:             # other p: a 16-bit field per element (half idx % 2 of the hash of idx / 2) against round(p * 2^16)
+            thr = np.uint64(min(65535, int(np.float32(p) * np.float32(65536.0) + np.float32(0.5))))
+            h = bits(key, idx >> np.uint64(1))
+            keep = np.where((idx & np.uint64(1)) == 1, h >> np.uint64(16), h & np.uint64(0xffff)) >= thr
     return torch.from_numpy(np.where(keep, np.float32(1.0 / (1.0 - p)), np.float32(0.0)))
 
 
 def attn_mask_oracle(seed, n_bh, T, p):
     """csrc/common.cuh attn_drop_keep() for every (b*heads+h, query, key): multiplier 0 or 1/(1-p), shape (n_bh*T*T,)."""
     import numpy as np
-    if p != 0.5:
-        return dropout_mask_oracle(seed, 3, 0, n_bh * T * T, p)              # SITE_ATTN = 3, idx = row*T + key
+    if p != 0.5:          # 16-bit field key % 2 of the hash of (row * ceil(T/2) + key // 2)
+        hp = (T + 1) // 2
+        words = dropout_mask_oracle(seed, 3, 0, n_bh * T * hp, 0.25, raw_bits=True)
+        rows = np.arange(n_bh * T, dtype=np.int64)[:, None]
+        keys = np.arange(T, dtype=np.int64)[None, :]
+        h = words[rows * hp + keys // 2]
+        f = np.where(keys % 2 == 1, h >> np.uint64(16), h & np.uint64(0xffff))
+        thr = np.uint64(min(65535, int(np.float32(p) * np.float32(65536.0) + np.float32(0.5))))
+        return torch.from_numpy(np.where(f >= thr, np.float32(1.0 / (1.0 - p)), np.float32(0.0)).reshape(-1))
     wpr = (T + 31) // 32
     words = dropout_mask_oracle(seed, 3, 0, n_bh * T * wpr, 0.25, raw_bits=True)      # hash of row*wpr + key//32
     rows = np.arange(n_bh * T, dtype=np.int64)[:, None]
