@@ -701,6 +701,8 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
     const long long sh = w > 0 ? (sum_big + w / 2) / w : 1;
     return (int)(sh < 1 ? 1 : sh);
   };
+  bool bias_on_main = false;
+  SegOut sb_main;
   {
     // every projection's bias gradient (column sums of its segment's rows of dz) in ONE launch of the per-segment
     // column-sum kernel instead of one strided column-sum launch per task
@@ -712,8 +714,14 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
       sb.out[k] = (d->seg_has_proj[k] && d->seg_tokens[k] > 0) ? g->proj_b[k] : nullptr;
       any |= sb.out[k] != nullptr;
     }
+    // On side stream 2 - unless the token-table gradient already runs there (HHI: two of these ~10 us reductions one after
+    // the other on one stream were the end of the step; the in-graph timeline shows Adam waiting for the second): then on
+    // the caller's stream, behind its projection weight gradient (below).
     Side* bside = get_side(2, st);
-    if (any) {
+    if (any && tside) {
+      bias_on_main = true;
+      sb_main = sb;
+    } else if (any) {
       EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dz, nullptr, sb, 0.f, 0, side_fork(st, bside, 1)));
       if (bside && !tside) tside = bside;       // joined below
     }
@@ -751,6 +759,7 @@ extern "C" int egot2_embed_bwd(const egot2_embed_desc* d, const egot2_embed_in* 
       }
     }
   }
+  if (bias_on_main) EGOT2_TRY(table_grad(d->dtype, d->B, d->T, d->H, dz, nullptr, sb_main, 0.f, 0, st));
   for (int i = 0; i < 2; ++i) if (used[i]) EGOT2_TRY(side_join(st, sides[i]));
   if (tside) EGOT2_TRY(side_join(st, tside));
   return 0;
